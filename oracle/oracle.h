@@ -1,0 +1,132 @@
+/*
+ * oracle.h -- CPU ORACLE for the vrad-b200 hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is the executable specification the CUDA path is checked against.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it.  Nothing under vrad_b200/ links, imports or calls it.
+ *
+ * PARITY UNPINNED: the reference (Galaco/VRAD, /root/reference) ships no golden
+ * vectors or known-answer tests for this path, its Trace4Rays is a stub
+ * (raytracer/environment.go:140-145), its radiosity stages are absent, and no Go
+ * toolchain exists in the build image, so the reference cannot be executed.  The
+ * oracle restates
+ *   - the reference's data layouts      (raytracer/cache/optimisedkdnode.go:15-54,
+ *                                        raytracer/cache/triangle/triintersectdata.go:3-22,
+ *                                        raytracer/types/fourrays.go:8-11, result.go:8-12,
+ *                                        common/types/patch.go:9-64, transfer.go:3-6, light.go:10-44)
+ *   - the reference's SAH kd build      (raytracer/environment.go:119-138,181-236,238-387)
+ *   - its triangle precomputation       (raytracer/cache/optimisedtriangle.go:30-103,
+ *                                        vmath/polygon/edge.go:5-25, surface.go:5-8)
+ *   - its trace call surface            (raytracer/trace/testline.go:18-94)
+ * with the SURVEY.md App. A defect corrections, and encodes Source-SDK-2013
+ * semantics (uncited) for the stubbed/absent stages.
+ * Independent arbiters: the brute-force tracer and the analytic known-answer
+ * tests in tests/.
+ *
+ * Arithmetic contract: IEEE-754 binary32, round-to-nearest-even per operation,
+ * no FMA contraction (compile with -ffp-contract=off), exact division and sqrt
+ * (vmath/ssemath/simd/simd.go:110-117,162-178 use exact 1/x and math.Sqrt).
+ */
+#ifndef VRAD_ORACLE_H
+#define VRAD_ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* raytracer/constants.go:9-16 */
+#define ORC_TRACE_ID_SKY        0x01000000
+#define ORC_TRACE_ID_OPAQUE     0x02000000
+#define ORC_TRACE_ID_STATICPROP 0x04000000
+#define ORC_KDNODE_LEAF 3
+
+/* raytracer/cache/triangle/triintersectdata.go:3-22 -- 48 bytes */
+typedef struct {
+    float nx, ny, nz, d;
+    int32_t id;
+    float e[6];
+    uint8_t sel0, sel1, flags, unused;
+} orc_tri48;
+
+/* light record shared with include/vrad_cuda.h (vrad_light): 96 bytes.
+ * Fields follow common/types/light.go:10-44 + worldlight fields set in
+ * rad/lightmap/lights.go:71-81,216-256,259-341. */
+typedef struct {
+    int32_t type;            /* 0 surface, 1 point, 2 spotlight, 3 skylight, 5 skyambient (bsp emittype_t order) */
+    float origin[3];
+    float intensity[3];
+    float normal[3];
+    float stopdot, stopdot2, exponent, radius;
+    float constant_attn, linear_attn, quadratic_attn;
+    float start_fade, end_fade, cap_dist;
+    int32_t flags;
+    float pad[3];
+} orc_light;
+
+typedef struct orc_env orc_env;
+
+orc_env* orc_env_create(void);
+void     orc_env_destroy(orc_env*);
+/* Environment.AddTriangleWithMaterial, raytracer/environment.go:45-69 */
+int  orc_env_add_triangles(orc_env*, int n, const int32_t* ids, const float* verts9, const uint8_t* flags);
+/* Environment.SetupAccelerationStructure, raytracer/environment.go:119-138 */
+int  orc_env_build(orc_env*);
+int  orc_env_sizes(orc_env*, int* n_nodes, int* n_idx, int* n_tris, int* max_depth, int* n_leaves);
+int  orc_env_export(orc_env*, int32_t* children, float* split, int32_t* tri_index, orc_tri48* tris, float aabb[6]);
+double orc_env_build_seconds(orc_env*);
+
+/* nearest hit over ALL triangles (ground truth; O(n_tris) per ray) */
+int  orc_trace_brute(orc_env*, int64_t n, const float* ox, const float* oy, const float* oz,
+                     const float* dx, const float* dy, const float* dz,
+                     const float* tmin, const float* tmax, int32_t skip_id,
+                     int32_t* hit_tri, int32_t* hit_sid, float* hit_t, int threads);
+/* THE SPEC: single-ray kd traversal (scalar form) */
+int  orc_trace1(orc_env*, int64_t n, const float* ox, const float* oy, const float* oz,
+                const float* dx, const float* dy, const float* dz,
+                const float* tmin, const float* tmax, int32_t skip_id,
+                int32_t* hit_tri, int32_t* hit_sid, float* hit_t, int threads);
+/* 4-wide packet traversal with FourRays semantics (the timed "reference CPU path").
+ * Rays are taken 4 at a time in input order; n need not be a multiple of 4. */
+int  orc_trace4(orc_env*, int64_t n, const float* ox, const float* oy, const float* oz,
+                const float* dx, const float* dy, const float* dz,
+                const float* tmin, const float* tmax, int32_t skip_id,
+                int32_t* hit_tri, int32_t* hit_sid, float* hit_t, int threads);
+/* one FourRays packet, exact RayTracingResult layout (raytracer/types/result.go:8-12) */
+int  orc_trace4_packet(orc_env*, const float origin_xyz4[12], const float dir_xyz4[12],
+                       const float tmin[4], const float tmax[4], int32_t skip_id,
+                       int32_t hit_ids[4], float hit_dist[4], float normal_xyz4[12]);
+/* TestLine / TestLineDoesHitSky, raytracer/trace/testline.go:22-51,91-93 (no skybox recursion).
+ * start/stop: SoA blocks x[n] y[n] z[n].  vis_bits: bit i of word i/32; 1 = visible.
+ * mode 0 = single-ray spec, 1 = packet tracer, 2 = brute force. */
+int  orc_test_lines(orc_env*, int64_t n, const float* start_soa, const float* stop_soa,
+                    int sky_mode, uint32_t* vis_bits, int mode, int threads);
+/* counters for the last orc_trace1 call with threads==1 (nodes visited, triangles tested) */
+int  orc_trace_counters(orc_env*, int64_t* nodes_visited, int64_t* tris_tested, int64_t* leaves_visited);
+
+/* ---- radiosity stages ---- */
+int  orc_patches_set(orc_env*, int n, const float* origin3, const float* normal3, const float* plane_dist,
+                     const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags);
+/* K2: builds CSR transfers.  pvs: n_clusters x n_clusters bytes (nonzero = visible) or NULL. */
+int  orc_build_transfers(orc_env*, int n_clusters, const uint8_t* pvs, int64_t* nnz_out, int threads);
+int  orc_transfers_get(orc_env*, int64_t* rowptr, int32_t* col, float* w);
+/* sky-ambient sample directions (the 162 `Anorms`, vmath/constants.go:15,21-184), copied */
+int  orc_set_sky_dirs(int n, const float* dirs3);
+/* K3: direct light per luxel; rgb_out 3 floats per luxel */
+int  orc_direct_light(orc_env*, int64_t n_luxels, const float* pos3, const float* normal3,
+                      int n_lights, const orc_light* lights, float* rgb_out, int threads);
+/* K4: bounce.  emit0_rgb: N*3.  total_rgb_out: N*3 (accumulated bounced light, excludes emit0). */
+int  orc_bounce(orc_env*, const float* emit0_rgb, int n_bounces, int early_out,
+                float* total_rgb_out, float added_last[3], int* bounces_done, int threads);
+/* one gather iteration on caller-supplied CSR (for sharded tests/timing): out[r-row0] for rows [row0,row1) */
+int  orc_gather_rows(int64_t row0, int64_t row1, const int64_t* rowptr, const int32_t* col, const float* w,
+                     const float* emit_rgb, const float* refl_rgb, float* out_rgb, int threads);
+
+int  orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

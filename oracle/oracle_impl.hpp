@@ -1,0 +1,73 @@
+// oracle_impl.hpp -- internal types of the CPU oracle (TEST INFRASTRUCTURE; see oracle.h).
+#pragma once
+#include "oracle.h"
+#include <vector>
+#include <cstdint>
+#include <cmath>
+#include <cstring>
+
+namespace orc {
+
+// maxps/minps-style selects: return b when either operand is NaN.  The CUDA path
+// uses the same expressions so NaN-degenerate rays take the same branches.
+static inline float min_sel(float a, float b) { return a < b ? a : b; }
+static inline float max_sel(float a, float b) { return a > b ? a : b; }
+
+struct KDNode {            // raytracer/cache/optimisedkdnode.go:15-54 (App. A #7: int32)
+    int32_t children;      // (index<<2) | axis(0..2) or LEAF(3)
+    float   split;         // split value; for leaves the triangle count as a float
+};
+
+struct TriGeom {           // raytracer/cache/triangle/trigeometrydata.go:3-12
+    int32_t id;
+    float   v[9];
+    uint8_t flags;
+    int8_t  tmp0, tmp1;
+};
+
+struct Patches {
+    int n = 0;
+    std::vector<float> origin, normal, plane_dist, area, refl;
+    std::vector<int32_t> cluster;
+    std::vector<uint8_t> flags;     // bit0 = sky
+};
+
+struct Counters { int64_t nodes = 0, tris = 0, leaves = 0; };
+
+} // namespace orc
+
+struct orc_env {
+    std::vector<orc::TriGeom> geom;
+    std::vector<orc_tri48>    tris;        // intersection format, same index as geom
+    std::vector<orc::KDNode>  nodes;
+    std::vector<int32_t>      tri_index;
+    float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+    int   max_depth = 0, n_leaves = 0;
+    bool  built = false;
+    double build_seconds = 0.0;
+    orc::Counters counters;
+    orc::Patches patches;
+    std::vector<int64_t> rowptr;
+    std::vector<int32_t> col;
+    std::vector<float>   w;
+};
+
+namespace orc {
+
+struct Hit { int32_t tri; float t; };
+
+void tri_to_intersection_format(const TriGeom& g, orc_tri48& out);
+void build_tree(orc_env* e);
+
+// single-ray spec traversal.  any_hit_len >= 0 selects the visibility-only variant
+// that stops at the first hit with t < any_hit_len.
+Hit trace1(const orc_env* e, const float o[3], const float d[3], float tmin, float tmax,
+           int32_t skip_id, Counters* ctr);
+Hit trace_brute(const orc_env* e, const float o[3], const float d[3], float tmin, float tmax, int32_t skip_id);
+void trace4(const orc_env* e, const float o[3][4], const float d[3][4], const float tmin[4], const float tmax[4],
+            int32_t skip_id, int32_t hit_tri[4], float hit_t[4]);
+
+// TestLine on one segment: returns 1 if visible.  mode: 0 spec, 2 brute.
+int test_line1(const orc_env* e, const float a[3], const float b[3], int sky_mode, int mode);
+
+} // namespace orc

@@ -1,0 +1,254 @@
+// radiosity.cpp -- ORACLE (test infrastructure): transfers (K2), direct light (K3), bounce (K4).
+//
+// None of these stages exists in the reference: `Transfer` is only a type
+// (common/types/transfer.go:3-6), `Patch` carries the fields read here (common/types/patch.go:9-64),
+// `DirectLight` + worldlight carry the light parameters (common/types/light.go:10-44,
+// rad/lightmap/lights.go:216-341) and the radiosity step is commented out
+// (cmd/tasks/computerad/main.go:5-10).  The algorithms encode the upstream semantics restated in
+// SURVEY.md App. B.2-B.4 (uncited) -- PARITY UNPINNED; analytic known-answer tests are the arbiter.
+#include "oracle_impl.hpp"
+#include <omp.h>
+
+namespace orc {
+
+static const float PLANE_TEST_EPSILON = 0.01f;
+static const float TRANS_EPSILON = 1.0e-7f;
+static const float PI_F = 3.14159265358979323846f;           // vmath/constants.go:5
+static const float EQUAL_EPSILON = 0.001f;                   // vmath/constants.go:9
+static const float MAX_TRACE_LENGTH = 1.732050807569f * 32768.0f;   // common/constants/constants.go:15-19
+
+static inline float dot3(const float* a, const float* b) { return ((a[0] * b[0]) + (a[1] * b[1])) + (a[2] * b[2]); }
+
+// App. B.3 MakeTransfer: differential-to-differential form factor * emitter area.
+// Returns 0 when the pair transfers nothing.
+static inline float transfer_weight(const Patches& P, int i, int j) {
+    if ((P.flags[j] & 1) || !(P.area[j] > 0.0f)) return 0.0f;
+    const float* oi = &P.origin[3 * i]; const float* oj = &P.origin[3 * j];
+    const float* ni = &P.normal[3 * i]; const float* nj = &P.normal[3 * j];
+    if (!(dot3(oj, ni) > P.plane_dist[i] + PLANE_TEST_EPSILON)) return 0.0f;
+    float dl[3] = {oi[0] - oj[0], oi[1] - oj[1], oi[2] - oj[2]};
+    float len2 = dot3(dl, dl);
+    float len = sqrtf(len2);
+    if (!(len > 0.0f)) return 0.0f;
+    float r = 1.0f / len;
+    dl[0] = dl[0] * r; dl[1] = dl[1] * r; dl[2] = dl[2] * r;
+    float d1 = dot3(dl, ni), d2 = dot3(dl, nj);
+    float scale = -(d1 * d2) / ((len * len) * PI_F);
+    if (!(scale > 0.0f)) return 0.0f;
+    float trans = P.area[j] * scale;
+    if (!(trans > TRANS_EPSILON)) return 0.0f;
+    return trans;
+}
+
+// shadow test between two patches; the segment always runs from the lower to the higher patch
+// index so that visibility is symmetric by construction.
+static inline int patches_see(const orc_env* e, int i, int j) {
+    const Patches& P = e->patches;
+    int lo = i < j ? i : j, hi = i < j ? j : i;
+    float a[3], b[3];
+    for (int c = 0; c < 3; c++) {
+        a[c] = P.origin[3 * lo + c] + P.normal[3 * lo + c];
+        b[c] = P.origin[3 * hi + c] + P.normal[3 * hi + c];
+    }
+    return test_line1(e, a, b, 0, 0);
+}
+
+} // namespace orc
+using namespace orc;
+
+extern "C" {
+
+int orc_patches_set(orc_env* e, int n, const float* origin3, const float* normal3, const float* plane_dist,
+                    const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags) {
+    if (!e || n < 0) return -1;
+    Patches& P = e->patches;
+    P.n = n;
+    P.origin.assign(origin3, origin3 + 3 * (size_t)n);
+    P.normal.assign(normal3, normal3 + 3 * (size_t)n);
+    P.plane_dist.assign(plane_dist, plane_dist + n);
+    P.area.assign(area, area + n);
+    P.refl.assign(reflectivity3, reflectivity3 + 3 * (size_t)n);
+    if (cluster) P.cluster.assign(cluster, cluster + n); else P.cluster.assign(n, 0);
+    if (flags) P.flags.assign(flags, flags + n); else P.flags.assign(n, 0);
+    e->rowptr.clear(); e->col.clear(); e->w.clear();
+    return 0;
+}
+
+int orc_build_transfers(orc_env* e, int n_clusters, const uint8_t* pvs, int64_t* nnz_out, int threads) {
+    if (!e || !e->built) return -1;
+    const Patches& P = e->patches;
+    int N = P.n;
+    std::vector<std::vector<int32_t>> cols(N);
+    std::vector<std::vector<float>> ws(N);
+#pragma omp parallel for schedule(dynamic, 8) num_threads(threads > 0 ? threads : 1)
+    for (int i = 0; i < N; i++) {
+        if (P.flags[i] & 1) continue;                    // sky patches receive nothing
+        for (int j = 0; j < N; j++) {
+            if (j == i) continue;
+            if (pvs && !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[j]]) continue;
+            float tr = transfer_weight(P, i, j);
+            if (tr == 0.0f) continue;
+            if (!patches_see(e, i, j)) continue;
+            cols[i].push_back(j); ws[i].push_back(tr);
+        }
+        // MakeScales (App. B.3): cap the row sum at 1
+        float total = 0.0f;
+        for (float v : ws[i]) total = total + v;
+        if (total > 1.0f) {
+            float s = 1.0f / total;
+            for (float& v : ws[i]) v = v * s;
+        }
+    }
+    e->rowptr.assign(N + 1, 0);
+    for (int i = 0; i < N; i++) e->rowptr[i + 1] = e->rowptr[i] + (int64_t)cols[i].size();
+    e->col.resize(e->rowptr[N]); e->w.resize(e->rowptr[N]);
+    for (int i = 0; i < N; i++) {
+        std::copy(cols[i].begin(), cols[i].end(), e->col.begin() + e->rowptr[i]);
+        std::copy(ws[i].begin(), ws[i].end(), e->w.begin() + e->rowptr[i]);
+    }
+    if (nnz_out) *nnz_out = e->rowptr[N];
+    return 0;
+}
+
+int orc_transfers_get(orc_env* e, int64_t* rowptr, int32_t* col, float* w) {
+    if (!e || e->rowptr.empty()) return -1;
+    if (rowptr) memcpy(rowptr, e->rowptr.data(), e->rowptr.size() * sizeof(int64_t));
+    if (col) memcpy(col, e->col.data(), e->col.size() * sizeof(int32_t));
+    if (w) memcpy(w, e->w.data(), e->w.size() * sizeof(float));
+    return 0;
+}
+
+// App. B.2.  Anorm directions for sky ambient arrive through lights of type 5 via `sky_dirs`.
+static std::vector<float> g_sky_dirs; static int g_n_sky_dirs = 0;
+int orc_set_sky_dirs(int n, const float* dirs3) { g_sky_dirs.assign(dirs3, dirs3 + 3 * (size_t)n); g_n_sky_dirs = n; return 0; }
+
+int orc_direct_light(orc_env* e, int64_t n_luxels, const float* pos3, const float* normal3, int n_lights,
+                     const orc_light* lights, float* rgb_out, int threads) {
+    if (!e || !e->built) return -1;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads > 0 ? threads : 1)
+    for (int64_t i = 0; i < n_luxels; i++) {
+        const float* pos = &pos3[3 * i]; const float* n = &normal3[3 * i];
+        float rgb[3] = {0, 0, 0};
+        for (int L = 0; L < n_lights; L++) {
+            const orc_light& dl = lights[L];
+            float scale = 0.0f;
+            if (dl.type == 0 || dl.type == 1 || dl.type == 2) {        // surface / point / spotlight
+                float delta[3] = {dl.origin[0] - pos[0], dl.origin[1] - pos[1], dl.origin[2] - pos[2]};
+                float dist2 = dot3(delta, delta);
+                float dist = sqrtf(dist2);
+                if (!(dist > 0.0f)) continue;
+                float r = 1.0f / dist;
+                delta[0] = delta[0] * r; delta[1] = delta[1] * r; delta[2] = delta[2] * r;
+                float dot = dot3(delta, n);
+                if (!(dot > 0.0f)) continue;
+                if (dl.end_fade > dl.start_fade && dist > dl.end_fade) continue;
+                dist = max_sel(dist, 1.0f);
+                float d = min_sel(dist, dl.cap_dist);
+                float denom = (dl.constant_attn + (dl.linear_attn * d)) + ((dl.quadratic_attn * d) * d);
+                float falloff;
+                if (dl.type == 1) {
+                    falloff = 1.0f / denom;
+                } else if (dl.type == 2) {
+                    float dot2 = -dot3(delta, dl.normal);
+                    if (dot2 <= dl.stopdot2) continue;
+                    falloff = dot2 / denom;
+                    if (dot2 <= dl.stopdot) {
+                        float m = (dot2 - dl.stopdot2) / (dl.stopdot - dl.stopdot2);
+                        m = min_sel(max_sel(m, 0.0f), 1.0f);
+                        if (dl.exponent != 0.0f && dl.exponent != 1.0f) m = powf(m, dl.exponent);
+                        falloff = falloff * m;
+                    }
+                } else {
+                    float dot2 = -dot3(delta, dl.normal);
+                    if (!(dot2 > 0.0f)) continue;
+                    dot = dot * dot2;
+                    falloff = 1.0f / (dist * dist);
+                }
+                if (dl.end_fade > dl.start_fade && dist > dl.start_fade) {
+                    float t = (dist - dl.start_fade) / (dl.end_fade - dl.start_fade);
+                    t = min_sel(max_sel(t, 0.0f), 1.0f);
+                    float s = 1.0f - ((t * t) * (3.0f - (2.0f * t)));
+                    falloff = falloff * s;
+                }
+                if (!test_line1(e, pos, dl.origin, 0, 0)) continue;
+                scale = falloff * dot;
+            } else if (dl.type == 3) {                                  // skylight (sun)
+                float dot = -dot3(dl.normal, n);
+                if (!(dot > 0.0f)) continue;
+                float stop[3] = {pos[0] - (dl.normal[0] * MAX_TRACE_LENGTH), pos[1] - (dl.normal[1] * MAX_TRACE_LENGTH),
+                                 pos[2] - (dl.normal[2] * MAX_TRACE_LENGTH)};
+                if (!test_line1(e, pos, stop, 1, 0)) continue;
+                scale = dot;
+            } else if (dl.type == 5) {                                  // sky ambient
+                float sum = 0.0f, possible = 0.0f;
+                for (int k = 0; k < g_n_sky_dirs; k++) {
+                    const float* a = &g_sky_dirs[3 * k];
+                    float dot = dot3(a, n);
+                    if (!(dot > EQUAL_EPSILON)) continue;
+                    possible = possible + dot;
+                    float stop[3] = {pos[0] + (a[0] * MAX_TRACE_LENGTH), pos[1] + (a[1] * MAX_TRACE_LENGTH),
+                                     pos[2] + (a[2] * MAX_TRACE_LENGTH)};
+                    if (test_line1(e, pos, stop, 1, 0)) sum = sum + dot;
+                }
+                if (!(possible > 0.0f)) continue;
+                scale = sum / possible;
+            } else continue;
+            rgb[0] = rgb[0] + (dl.intensity[0] * scale);
+            rgb[1] = rgb[1] + (dl.intensity[1] * scale);
+            rgb[2] = rgb[2] + (dl.intensity[2] * scale);
+        }
+        rgb_out[3 * i] = rgb[0]; rgb_out[3 * i + 1] = rgb[1]; rgb_out[3 * i + 2] = rgb[2];
+    }
+    return 0;
+}
+
+// App. B.4 GatherLight for rows [row0,row1): sequential fp32 sums in CSR order.
+int orc_gather_rows(int64_t row0, int64_t row1, const int64_t* rowptr, const int32_t* col, const float* w,
+                    const float* emit_rgb, const float* refl_rgb, float* out_rgb, int threads) {
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads > 0 ? threads : 1)
+    for (int64_t i = row0; i < row1; i++) {
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; k++) {
+            int32_t j = col[k]; float wt = w[k];
+            s0 = s0 + (wt * (emit_rgb[3 * j] * refl_rgb[3 * j]));
+            s1 = s1 + (wt * (emit_rgb[3 * j + 1] * refl_rgb[3 * j + 1]));
+            s2 = s2 + (wt * (emit_rgb[3 * j + 2] * refl_rgb[3 * j + 2]));
+        }
+        float* o = &out_rgb[3 * (i - row0)];
+        o[0] = s0; o[1] = s1; o[2] = s2;
+    }
+    return 0;
+}
+
+int orc_bounce(orc_env* e, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out,
+               float added_last[3], int* bounces_done, int threads) {
+    if (!e || e->rowptr.empty()) return -1;
+    const Patches& P = e->patches;
+    int N = P.n;
+    std::vector<float> emit(emit0_rgb, emit0_rgb + 3 * (size_t)N), add(3 * (size_t)N), total(3 * (size_t)N, 0.0f);
+    float added[3] = {0, 0, 0};
+    int done = 0;
+    for (int b = 0; b < n_bounces; b++) {
+        orc_gather_rows(0, N, e->rowptr.data(), e->col.data(), e->w.data(), emit.data(), P.refl.data(), add.data(), threads);
+        // CollectLight (leaf patches only)
+        added[0] = added[1] = added[2] = 0.0f;
+        for (int i = 0; i < N; i++) {
+            for (int c = 0; c < 3; c++) {
+                if (P.flags[i] & 1) { emit[3 * i + c] = 0.0f; continue; }
+                total[3 * i + c] = total[3 * i + c] + add[3 * i + c];
+                emit[3 * i + c] = add[3 * i + c];
+                added[c] = added[c] + emit[3 * i + c];
+            }
+        }
+        done++;
+        if (early_out && added[0] < 1.0f && added[1] < 1.0f && added[2] < 1.0f) break;
+    }
+    memcpy(total_rgb_out, total.data(), total.size() * sizeof(float));
+    if (added_last) { added_last[0] = added[0]; added_last[1] = added[1]; added_last[2] = added[2]; }
+    if (bounces_done) *bounces_done = done;
+    return 0;
+}
+
+int orc_num_threads(void) { return omp_get_max_threads(); }
+
+} // extern "C"

@@ -1,0 +1,355 @@
+"""Deterministic synthetic scenes for the hot path (BASELINE.json configs).
+
+The generator plays the role of the reference's input producers -- brush -> triangle extraction
+(cmd/tasks/loadbsp/main.go:241-340: world triangles carry TRACE_ID_OPAQUE, sky faces TRACE_ID_SKY),
+face -> patch creation (rad/patches/face.go:30-197: origin lifted off the face along the normal,
+reflectivity clamped, area) and light creation (rad/lightmap/lights.go:210-341) -- and emits the
+flat arrays the C-ABI takes.  Geometry is appended exactly the way raytracer.Environment's
+AddQuad / AddAxisAlignedRectangularSolid do (raytracer/environment.go:71-117), so triangle order
+and ids are what the reference's own helper calls would produce.
+
+RNG: splitmix64 -> 24-bit uniform floats; seeds are fixed per scene.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+TRACE_ID_SKY = 0x01000000         # raytracer/constants.go:9
+TRACE_ID_OPAQUE = 0x02000000      # raytracer/constants.go:10
+TRACE_ID_STATICPROP = 0x04000000  # raytracer/constants.go:11
+MAX_TRACE_LENGTH = np.float32(1.732050807569 * 32768.0)   # common/constants/constants.go:15-19
+
+EMIT_SURFACE, EMIT_POINT, EMIT_SPOTLIGHT, EMIT_SKYLIGHT, EMIT_SKYAMBIENT = 0, 1, 2, 3, 5
+
+# 96-byte light record == vrad_light in include/vrad_cuda.h
+LIGHT_DTYPE = np.dtype([
+    ("type", "<i4"), ("origin", "<f4", 3), ("intensity", "<f4", 3), ("normal", "<f4", 3),
+    ("stopdot", "<f4"), ("stopdot2", "<f4"), ("exponent", "<f4"), ("radius", "<f4"),
+    ("constant_attn", "<f4"), ("linear_attn", "<f4"), ("quadratic_attn", "<f4"),
+    ("start_fade", "<f4"), ("end_fade", "<f4"), ("cap_dist", "<f4"),
+    ("flags", "<i4"), ("pad", "<f4", 3)])
+assert LIGHT_DTYPE.itemsize == 96
+
+_MASK = (1 << 64) - 1
+
+
+class SplitMix64:
+    """Scalar + vectorised splitmix64."""
+
+    def __init__(self, seed: int):
+        self.state = seed & _MASK
+
+    def u64(self, n: int) -> np.ndarray:
+        with np.errstate(over="ignore"):
+            idx = np.arange(1, n + 1, dtype=np.uint64)
+            z = np.uint64(self.state) + idx * np.uint64(0x9E3779B97F4A7C15)
+            self.state = int(z[-1]) if n else self.state
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return z ^ (z >> np.uint64(31))
+
+    def uniform(self, n: int, lo: float = 0.0, hi: float = 1.0) -> np.ndarray:
+        u = (self.u64(n) >> np.uint64(40)).astype(np.float64) * (1.0 / (1 << 24))
+        return (lo + (hi - lo) * u).astype(np.float32)
+
+    def integers(self, n: int, hi: int) -> np.ndarray:
+        return (self.u64(n) % np.uint64(hi)).astype(np.int64)
+
+
+@dataclass
+class Scene:
+    name: str
+    tri_ids: np.ndarray            # int32 [T]
+    tri_verts: np.ndarray          # float32 [T, 9]
+    tri_flags: np.ndarray          # uint8 [T]
+    patch_origin: np.ndarray = None      # float32 [N,3]  (lifted 1 unit off the face)
+    patch_normal: np.ndarray = None
+    patch_plane_dist: np.ndarray = None
+    patch_area: np.ndarray = None
+    patch_refl: np.ndarray = None        # float32 [N,3]
+    patch_cluster: np.ndarray = None     # int32 [N]
+    patch_flags: np.ndarray = None       # uint8 [N], bit0 = sky
+    n_clusters: int = 1
+    pvs: np.ndarray = None               # uint8 [C, C] or None (everything visible)
+    luxel_pos: np.ndarray = None         # float32 [L,3]
+    luxel_normal: np.ndarray = None
+    lights: np.ndarray = None            # LIGHT_DTYPE [n]
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_tris(self): return int(self.tri_ids.shape[0])
+
+    @property
+    def n_patches(self): return 0 if self.patch_origin is None else int(self.patch_origin.shape[0])
+
+
+class _Geom:
+    """Mirror of the reference's triangle-append helpers (raytracer/environment.go:41-117)."""
+
+    def __init__(self):
+        self.ids, self.verts = [], []
+
+    def add_triangle(self, tid, v1, v2, v3):
+        self.ids.append(tid)
+        self.verts.append([*v1, *v2, *v3])
+
+    def add_quad(self, tid, v1, v2, v3, v4):           # environment.go:71-75
+        self.add_triangle(tid, v1, v2, v3)
+        self.add_triangle(tid + 1, v1, v3, v4)
+
+    def add_box(self, tid, mn, mx):                    # environment.go:77-117 (same face/vertex order)
+        q = self.add_quad
+        q(tid, (mn[0], mx[1], mx[2]), (mx[0], mx[1], mx[2]), (mx[0], mn[1], mx[2]), (mn[0], mn[1], mx[2]))
+        q(tid, (mn[0], mx[1], mn[2]), (mx[0], mx[1], mn[2]), (mx[0], mn[1], mn[2]), (mn[0], mn[1], mn[2]))
+        q(tid, (mn[0], mx[1], mx[2]), (mn[0], mx[1], mn[2]), (mn[0], mn[1], mn[2]), (mn[0], mn[1], mx[2]))
+        q(tid, (mx[0], mx[1], mx[2]), (mx[0], mx[1], mn[2]), (mx[0], mn[1], mn[2]), (mx[0], mn[1], mx[2]))
+        q(tid, (mn[0], mx[1], mx[2]), (mx[0], mx[1], mx[2]), (mx[0], mx[1], mn[2]), (mn[0], mx[1], mn[2]))
+        q(tid, (mn[0], mn[1], mx[2]), (mx[0], mn[1], mx[2]), (mx[0], mn[1], mn[2]), (mn[0], mn[1], mn[2]))
+
+    def add_box_array(self, tid, mins, maxs):
+        for mn, mx in zip(mins, maxs):
+            self.add_box(tid, mn, mx)
+
+    def arrays(self):
+        ids = np.asarray(self.ids, dtype=np.int32)
+        verts = np.asarray(self.verts, dtype=np.float32).reshape(-1, 9)
+        return ids, verts, np.zeros(ids.shape[0], dtype=np.uint8)
+
+
+def _grid_points(origin, udir, vdir, nu, nv, cell, normal, lift):
+    """Centres of an nu x nv grid of square cells on a planar face, lifted off the face."""
+    origin = np.asarray(origin, np.float64); udir = np.asarray(udir, np.float64)
+    vdir = np.asarray(vdir, np.float64); normal = np.asarray(normal, np.float64)
+    iu, iv = np.meshgrid(np.arange(nu), np.arange(nv), indexing="ij")
+    c = (origin[None, :] + (iu.reshape(-1, 1) + 0.5) * cell * udir[None, :]
+         + (iv.reshape(-1, 1) + 0.5) * cell * vdir[None, :])
+    centres = c.astype(np.float32)
+    pos = (c + lift * normal[None, :]).astype(np.float32)
+    nrm = np.broadcast_to(normal.astype(np.float32), pos.shape).copy()
+    return centres, pos, nrm
+
+
+def _room_faces(x0, y0, z0, sx, sy, sz):
+    """Six inward-facing faces of a room: (origin, udir, vdir, ulen, vlen, normal)."""
+    x1, y1, z1 = x0 + sx, y0 + sy, z0 + sz
+    return [
+        ((x0, y0, z0), (1, 0, 0), (0, 1, 0), sx, sy, (0, 0, 1)),     # floor
+        ((x0, y0, z1), (1, 0, 0), (0, 1, 0), sx, sy, (0, 0, -1)),    # ceiling
+        ((x0, y0, z0), (0, 1, 0), (0, 0, 1), sy, sz, (1, 0, 0)),     # wall x = x0
+        ((x1, y0, z0), (0, 1, 0), (0, 0, 1), sy, sz, (-1, 0, 0)),    # wall x = x1
+        ((x0, y0, z0), (1, 0, 0), (0, 0, 1), sx, sz, (0, 1, 0)),     # wall y = y0
+        ((x0, y1, z0), (1, 0, 0), (0, 0, 1), sx, sz, (0, -1, 0)),    # wall y = y1
+    ]
+
+
+def _face_quad(g: _Geom, tid, face):
+    o, u, v, ul, vl, _ = face
+    o = np.asarray(o, np.float64); u = np.asarray(u, np.float64) * ul; v = np.asarray(v, np.float64) * vl
+    g.add_quad(tid, tuple(o), tuple(o + u), tuple(o + u + v), tuple(o + v))
+
+
+def _place_boxes(rng: SplitMix64, count, x0, y0, x1, y1, z0, smin=16.0, smax=96.0, margin=8.0):
+    """Non-overlapping axis-aligned boxes resting on the floor z0 (rejection sampling)."""
+    mins, maxs = [], []
+    guard = 0
+    while len(mins) < count:
+        guard += 1
+        if guard > 100000:
+            raise RuntimeError("box placement did not converge")
+        s = rng.uniform(3, smin, smax).astype(np.float64)
+        p = rng.uniform(2).astype(np.float64)
+        bx0 = x0 + margin + p[0] * (x1 - x0 - 2 * margin - s[0])
+        by0 = y0 + margin + p[1] * (y1 - y0 - 2 * margin - s[1])
+        mn = (bx0, by0, z0); mx = (bx0 + s[0], by0 + s[1], z0 + s[2])
+        ok = True
+        for m2, x2 in zip(mins, maxs):
+            if mn[0] < x2[0] + 4 and mx[0] > m2[0] - 4 and mn[1] < x2[1] + 4 and mx[1] > m2[1] - 4:
+                ok = False
+                break
+        if ok:
+            mins.append(tuple(np.float32(v) for v in mn)); maxs.append(tuple(np.float32(v) for v in mx))
+    return mins, maxs
+
+
+def _make_lights(rng: SplitMix64, n_point, n_spot, x0, y0, x1, y1, zlo, zhi):
+    n = n_point + n_spot
+    lights = np.zeros(n, dtype=LIGHT_DTYPE)
+    for k in range(n):
+        p = rng.uniform(3)
+        lights[k]["origin"] = (x0 + 64 + p[0] * (x1 - x0 - 128), y0 + 64 + p[1] * (y1 - y0 - 128), zlo + p[2] * (zhi - zlo))
+        inten = rng.uniform(3, 100.0, 400.0)
+        # quadratic falloff: c=0, l=0, q=1; "scale intensity for unit 100 distance" (lights.go:335-339)
+        lights[k]["constant_attn"], lights[k]["linear_attn"], lights[k]["quadratic_attn"] = 0.0, 0.0, 1.0
+        ratio = np.float32(0.0 + 100 * 0.0 + 100 * 100 * 1.0)
+        lights[k]["intensity"] = inten * ratio
+        lights[k]["start_fade"], lights[k]["end_fade"], lights[k]["cap_dist"] = 0.0, -1.0, 1.0e22   # light.go:38-44
+        if k < n_point:
+            lights[k]["type"] = EMIT_POINT
+        else:
+            lights[k]["type"] = EMIT_SPOTLIGHT
+            d = rng.uniform(2, -0.5, 0.5).astype(np.float64)
+            v = np.array([d[0], d[1], -1.0]); v /= np.linalg.norm(v)
+            lights[k]["normal"] = v.astype(np.float32)
+            lights[k]["stopdot"] = np.float32(math.cos(30.0 / 180.0 * math.pi))    # lights.go:251-252
+            lights[k]["stopdot2"] = np.float32(math.cos(45.0 / 180.0 * math.pi))
+            lights[k]["exponent"] = 1.0
+    return lights
+
+
+def _surface_samples(faces, cell, lift, skip=None):
+    cs, ps, ns, fi = [], [], [], []
+    for k, (o, u, v, ul, vl, nrm) in enumerate(faces):
+        c, p, n = _grid_points(o, u, v, int(round(ul / cell)), int(round(vl / cell)), cell, nrm, lift)
+        if skip is not None:
+            keep = ~skip(k, c)
+            c, p, n = c[keep], p[keep], n[keep]
+        cs.append(c); ps.append(p); ns.append(n); fi.append(np.full(p.shape[0], k, np.int32))
+    return np.concatenate(cs), np.concatenate(ps), np.concatenate(ns), np.concatenate(fi)
+
+
+def box_room(seed: int = 0x5EED0001, n_boxes: int = 82, size=(1024.0, 1024.0, 512.0), patch_cell=32.0,
+             luxel_cell=16.0, n_point=4, n_spot=4) -> Scene:
+    """S1 (configs C1/C2): one room + box occluders: 12 + 12*n_boxes triangles (996 by default),
+    4096 leaf patches, 16384 luxels, 8 lights."""
+    rng = SplitMix64(seed)
+    sx, sy, sz = size
+    x0, y0, z0 = -sx / 2, -sy / 2, 0.0
+    g = _Geom()
+    faces = _room_faces(x0, y0, z0, sx, sy, sz)
+    for f in faces:
+        _face_quad(g, TRACE_ID_OPAQUE, f)
+    mins, maxs = _place_boxes(rng, n_boxes, x0, y0, x0 + sx, y0 + sy, z0)
+    g.add_box_array(TRACE_ID_OPAQUE, mins, maxs)
+    ids, verts, flags = g.arrays()
+
+    centres, origin, normal, face_idx = _surface_samples(faces, patch_cell, 1.0)
+    refl_face = rng.uniform(6 * 3, 0.2, 0.7).reshape(6, 3)
+    refl = np.minimum(refl_face[face_idx], np.float32(0.99))         # rad/patches/face.go:225-230
+    plane_dist = np.einsum("ij,ij->i", normal.astype(np.float64), centres.astype(np.float64)).astype(np.float32)
+    area = np.full(origin.shape[0], patch_cell * patch_cell, np.float32)
+    _, lpos, lnrm, _ = _surface_samples(faces, luxel_cell, 1.0)
+    lights = _make_lights(rng, n_point, n_spot, x0, y0, x0 + sx, y0 + sy, sz * 0.5, sz - 32.0)
+    return Scene("S1_box_room", ids, verts, flags, origin, normal, plane_dist, area, refl.astype(np.float32),
+                 np.zeros(origin.shape[0], np.int32), np.zeros(origin.shape[0], np.uint8), 1, None, lpos, lnrm, lights,
+                 {"seed": seed, "n_boxes": n_boxes})
+
+
+def multi_room(seed: int = 0x5EED0002, nx: int = 12, ny: int = 11, room: float = 512.0, boxes_per_room: int = 30,
+               patch_cell: float = 32.0, door_w: float = 128.0, door_h: float = 256.0, pvs_radius: int = 2) -> Scene:
+    """S2 (configs C3/C4): nx x ny rooms on a grid, shared zero-thickness walls with a centred door
+    between neighbours, box occluders in every room.  One cluster per room; PVS = self + rooms reached
+    through <= pvs_radius collinear doors."""
+    rng = SplitMix64(seed)
+    g = _Geom()
+    R = room
+
+    def wall_with_door(o, u, h_axis_len, door):
+        # wall spans u in [0,R], z in [0,R]; door centred: three quads (left, right, above) or one solid quad
+        o = np.asarray(o, np.float64); u = np.asarray(u, np.float64)
+        z = np.array([0.0, 0.0, 1.0])
+        def quad(u0, u1, z0, z1):
+            g.add_quad(TRACE_ID_OPAQUE, tuple(o + u * u0 + z * z0), tuple(o + u * u1 + z * z0),
+                       tuple(o + u * u1 + z * z1), tuple(o + u * u0 + z * z1))
+        if not door:
+            quad(0.0, R, 0.0, R)
+        else:
+            a, b = (R - door_w) / 2, (R + door_w) / 2
+            quad(0.0, a, 0.0, R); quad(b, R, 0.0, R); quad(a, b, door_h, R)
+
+    for i in range(nx):
+        for j in range(ny):
+            x0, y0 = i * R, j * R
+            fl = _room_faces(x0, y0, 0.0, R, R, R)
+            _face_quad(g, TRACE_ID_OPAQUE, fl[0]); _face_quad(g, TRACE_ID_OPAQUE, fl[1])
+    for i in range(nx + 1):          # walls on planes x = i*R
+        for j in range(ny):
+            wall_with_door((i * R, j * R, 0.0), (0, 1, 0), R, 0 < i < nx)
+    for j in range(ny + 1):          # walls on planes y = j*R
+        for i in range(nx):
+            wall_with_door((i * R, j * R, 0.0), (1, 0, 0), R, 0 < j < ny)
+    for i in range(nx):
+        for j in range(ny):
+            mins, maxs = _place_boxes(rng, boxes_per_room, i * R, j * R, (i + 1) * R, (j + 1) * R, 0.0, margin=40.0)
+            g.add_box_array(TRACE_ID_OPAQUE, mins, maxs)
+    ids, verts, flags = g.arrays()
+
+    a, b = (R - door_w) / 2, (R + door_w) / 2
+    origins, normals, pdists, refls, clusters = [], [], [], [], []
+    for i in range(nx):
+        for j in range(ny):
+            x0, y0 = i * R, j * R
+            faces = _room_faces(x0, y0, 0.0, R, R, R)
+            has_door = {2: i > 0, 3: i < nx - 1, 4: j > 0, 5: j < ny - 1}
+
+            def skip(k, c, x0=x0, y0=y0, has_door=has_door):
+                if k < 2 or not has_door[k]:
+                    return np.zeros(c.shape[0], bool)
+                along = (c[:, 1] - y0) if k in (2, 3) else (c[:, 0] - x0)
+                return (along > a) & (along < b) & (c[:, 2] < door_h)
+            centres, origin, normal, face_idx = _surface_samples(faces, patch_cell, 1.0, skip)
+            rf = rng.uniform(6 * 3, 0.2, 0.7).reshape(6, 3)
+            origins.append(origin); normals.append(normal)
+            pdists.append(np.einsum("ij,ij->i", normal.astype(np.float64), centres.astype(np.float64)).astype(np.float32))
+            refls.append(rf[face_idx]); clusters.append(np.full(origin.shape[0], i * ny + j, np.int32))
+    origin = np.concatenate(origins); normal = np.concatenate(normals)
+    nC = nx * ny
+    pvs = np.zeros((nC, nC), np.uint8)
+    for i in range(nx):
+        for j in range(ny):
+            c = i * ny + j
+            pvs[c, c] = 1
+            for r in range(1, pvs_radius + 1):
+                for (di, dj) in ((r, 0), (-r, 0), (0, r), (0, -r)):
+                    ii, jj = i + di, j + dj
+                    if 0 <= ii < nx and 0 <= jj < ny:
+                        pvs[c, ii * ny + jj] = 1
+    # one point light per room near the ceiling centre (used by the direct-light stage of C3/C4)
+    lights = np.zeros(nC, dtype=LIGHT_DTYPE)
+    for i in range(nx):
+        for j in range(ny):
+            k = i * ny + j
+            p = rng.uniform(2, -64.0, 64.0)
+            lights[k]["type"] = EMIT_POINT
+            lights[k]["origin"] = (i * R + R / 2 + p[0], j * R + R / 2 + p[1], R - 48.0)
+            lights[k]["quadratic_attn"] = 1.0
+            lights[k]["intensity"] = rng.uniform(3, 100.0, 400.0) * np.float32(10000.0)
+            lights[k]["start_fade"], lights[k]["end_fade"], lights[k]["cap_dist"] = 0.0, -1.0, 1.0e22
+    N = origin.shape[0]
+    return Scene("S2_multi_room", ids, verts, flags, origin, normal, np.concatenate(pdists),
+                 np.full(N, patch_cell * patch_cell, np.float32),
+                 np.minimum(np.concatenate(refls), np.float32(0.99)).astype(np.float32),
+                 np.concatenate(clusters), np.zeros(N, np.uint8), nC, pvs, None, None, lights,
+                 {"seed": seed, "nx": nx, "ny": ny, "boxes_per_room": boxes_per_room})
+
+
+def shadow_segments(scene: Scene, n: int, seed: int = 0xC0FFEE) -> tuple[np.ndarray, np.ndarray]:
+    """C1 ray workload: n shadow segments as SoA blocks [3, n] (start, stop): even lanes run
+    patch -> light, odd lanes patch -> patch, both from `origin + normal` like the transfer test."""
+    rng = SplitMix64(seed)
+    N = scene.n_patches
+    a = rng.integers(n, N)
+    b = rng.integers(n, N)
+    start = (scene.patch_origin[a] + scene.patch_normal[a]).astype(np.float32)
+    stop = (scene.patch_origin[b] + scene.patch_normal[b]).astype(np.float32)
+    if scene.lights is not None and len(scene.lights):
+        li = rng.integers(n, len(scene.lights))
+        to_light = (np.arange(n) % 2) == 0
+        stop[to_light] = scene.lights["origin"][li[to_light]]
+    return np.ascontiguousarray(start.T), np.ascontiguousarray(stop.T)
+
+
+def random_rays(scene: Scene, n: int, seed: int = 0xBEEF) -> dict:
+    """General closest-hit rays: origins inside the scene AABB, uniform directions, tmax = MAX_TRACE_LENGTH."""
+    rng = SplitMix64(seed)
+    v = scene.tri_verts.reshape(-1, 3)
+    lo, hi = v.min(axis=0), v.max(axis=0)
+    o = np.stack([rng.uniform(n, float(lo[c]) + 1.0, float(hi[c]) - 1.0) for c in range(3)])
+    z = rng.uniform(n, -1.0, 1.0).astype(np.float64)
+    phi = rng.uniform(n, 0.0, 2.0 * math.pi).astype(np.float64)
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    d = np.stack([r * np.cos(phi), r * np.sin(phi), z]).astype(np.float32)
+    return {"o": np.ascontiguousarray(o), "d": np.ascontiguousarray(d),
+            "tmax": np.full(n, MAX_TRACE_LENGTH, np.float32)}
