@@ -1,0 +1,166 @@
+/*
+ * vrad_cuda.h -- C-ABI of libvradcuda.so: the B200 (sm_100a) drop-in for the data-parallel hot
+ * path of VRADiant (Galaco/VRAD).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository root).  The Go driver keeps cache/ BSP loading, rad/ entry points and the
+ * raytracer/trace call surface and binds these symbols through cgo.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative vrad_status on failure;
+ *     vrad_last_error() returns a thread-local message.  The reference has no error returns
+ *     (failures are log.Fatal or log.Panicln, e.g. raytracer/trace/testline.go:21); the Go shim
+ *     turns a non-zero status into log.Fatalf.
+ *   - a handle is NOT thread-safe (the reference is single-goroutine: common/constants/constants.go:43).
+ *   - one handle drives ONE GPU.  Multi-GPU = one handle per process/GPU with (rank, world) set in
+ *     vrad_config; rays/luxels/patch rows are sharded by rank and the only data-path collective is
+ *     the per-bounce radiance all-gather (vrad_comm_init).
+ *   - data pointers may be pageable host, pinned host (vrad_host_alloc) or device memory; the
+ *     library inspects them with cudaPointerGetAttributes.  Host pointers are copied in/out
+ *     before the call returns (cgo rule: C must not retain Go pointers).
+ *   - there is no CPU fallback: without a CUDA device vrad_env_create fails with VRAD_E_CUDA.
+ */
+#ifndef VRAD_CUDA_H
+#define VRAD_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    VRAD_OK = 0,
+    VRAD_E_INVALID = -1,     /* bad argument / call order */
+    VRAD_E_CUDA = -2,        /* CUDA runtime error (message in vrad_last_error) */
+    VRAD_E_NOMEM = -3,
+    VRAD_E_STATE = -4,       /* e.g. trace before build */
+    VRAD_E_COMM = -5,        /* NCCL error */
+    VRAD_E_UNSUPPORTED = -6  /* e.g. FCACHETRI_TRANSPARENT triangles (callback cannot cross into a kernel) */
+} vrad_status;
+
+/* raytracer/constants.go:5-18 */
+#define VRAD_TRACE_ID_SKY        0x01000000
+#define VRAD_TRACE_ID_OPAQUE     0x02000000
+#define VRAD_TRACE_ID_STATICPROP 0x04000000
+#define VRAD_KDNODE_LEAF 3
+
+typedef struct vrad_env vrad_env;   /* opaque; stands in for raytracer.Environment (raytracer/environment.go:28-39) */
+
+typedef struct {
+    int device;      /* CUDA device ordinal driven by this handle */
+    int rank;        /* shard index of this handle, 0..world-1 */
+    int world;       /* number of cooperating handles (1 = single GPU) */
+    int flags;       /* VRAD_CFG_* */
+} vrad_config;
+#define VRAD_CFG_DEFAULT 0
+
+/* raytracer/cache/triangle/triintersectdata.go:3-22 -- 48-byte intersection record */
+typedef struct {
+    float nx, ny, nz, d;
+    int32_t id;
+    float e[6];
+    uint8_t sel0, sel1, flags, unused;
+} vrad_tri48;
+
+/* common/types/light.go:10-44 + worldlight fields set in rad/lightmap/lights.go:71-81,216-256,259-341 */
+typedef struct {
+    int32_t type;            /* emittype: 0 surface, 1 point, 2 spotlight, 3 skylight, 5 skyambient */
+    float origin[3];
+    float intensity[3];
+    float normal[3];
+    float stopdot, stopdot2, exponent, radius;
+    float constant_attn, linear_attn, quadratic_attn;
+    float start_fade, end_fade, cap_dist;
+    int32_t flags;
+    float pad[3];
+} vrad_light;               /* 96 bytes */
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+/* raytracer.GetEnvironment / NewEnvironment (raytracer/environment.go:17-25,434-442) */
+int  vrad_env_create(const vrad_config* cfg, vrad_env** out);
+void vrad_env_destroy(vrad_env*);
+const char* vrad_last_error(void);
+/* run the library's work on the caller's CUDA stream (cudaStream_t as void*); NULL = own stream */
+int  vrad_env_set_stream(vrad_env*, void* cuda_stream);
+/* async != 0: calls whose data pointers are all device memory return without synchronising */
+int  vrad_env_set_async(vrad_env*, int async);
+/* device time (ms, CUDA events on the launching stream) and kernel-launch count of the last call */
+int  vrad_env_last_timing(vrad_env*, float* kernel_ms, int* n_launches);
+/* pinned staging buffers for the batched calls */
+void* vrad_host_alloc(size_t bytes);
+void  vrad_host_free(void* p);
+
+/* ---- geometry + acceleration structure -------------------------------------------------- */
+/* Environment.AddTriangleWithMaterial (raytracer/environment.go:45-69): ids int32, 9 floats per triangle, flags */
+int  vrad_env_add_triangles(vrad_env*, int n, const int32_t* ids, const float* verts9, const uint8_t* flags);
+/* Environment.SetupAccelerationStructure (raytracer/environment.go:119-138): host SAH build
+ * (RefineNode :238-387, CalculateCostsOfSplit :181-236), ChangeIntoIntersectionFormat
+ * (raytracer/cache/optimisedtriangle.go:30-78), upload */
+int  vrad_env_build(vrad_env*);
+/* adopt a tree built elsewhere, in the reference's own layouts (OptimisedKDNode, TriangleIndexList, TriIntersectData) */
+int  vrad_env_upload_tree(vrad_env*, int n_nodes, const int32_t* children, const float* split,
+                          int n_idx, const int32_t* tri_index, int n_tris, const vrad_tri48* tris,
+                          const float aabb[6]);
+int  vrad_env_stats(vrad_env*, int* n_nodes, int* n_idx, int* n_tris, int* max_depth, int* n_leaves,
+                    float aabb[6], double* build_seconds);
+/* read the tree back in reference layout (Environment.OptimizedKDTree / TriangleIndexList /
+ * OptimizedTriangleList, raytracer/environment.go:33-35; GetTriangle :422-424) */
+int  vrad_env_download_tree(vrad_env*, int32_t* children, float* split, int32_t* tri_index, vrad_tri48* tris);
+
+/* ---- K1: ray casting --------------------------------------------------------------------- */
+/* Environment.Trace4Rays (raytracer/environment.go:140-145): one FourRays packet
+ * (raytracer/types/fourrays.go:8-11) -> RayTracingResult (raytracer/types/result.go:8-12).
+ * origin/dir/normal are x[4] y[4] z[4].  Latency path; kept for call-surface fidelity. */
+int  vrad_trace4(vrad_env*, const float origin_xyz4[12], const float dir_xyz4[12], const float tmin[4],
+                 const float tmax[4], int32_t skip_id, int32_t hit_ids[4], float hit_dist[4], float normal_xyz4[12]);
+/* batched Trace4Rays: n rays SoA.  tmin may be NULL (0).  hit_tri = index into the triangle list or -1,
+ * hit_sid = NTriangleID of that triangle (or -1), hit_t = distance (1e23 on a miss).  Outputs may be NULL.
+ * With world > 1 the handle traces rays [rank*n/world, (rank+1)*n/world) only when n is the global count
+ * and shard != 0; otherwise all n rays. */
+int  vrad_trace_rays(vrad_env*, int64_t n, const float* ox, const float* oy, const float* oz,
+                     const float* dx, const float* dy, const float* dz, const float* tmin, const float* tmax,
+                     int32_t skip_id, int32_t* hit_tri, int32_t* hit_sid, float* hit_t);
+/* trace.TestLine / trace.TestLineDoesHitSky (raytracer/trace/testline.go:18-94, without the 3D-skybox
+ * recursion of :57-89): n segments, SoA blocks x[n] y[n] z[n]; vis_bits bit (i%32) of word i/32, 1 = visible.
+ * sky_mode 0: any hit occludes; 1: a nearest hit on a TRACE_ID_SKY triangle does not occlude (:46-48). */
+int  vrad_test_lines(vrad_env*, int64_t n, const float* start_xyz_soa, const float* stop_xyz_soa,
+                     int sky_mode, uint32_t* vis_bits);
+
+/* ---- patches, K2 transfers, K3 direct light, K4 bounce ---------------------------------- */
+/* fields of common/types/patch.go:9-64 the kernels read (leaf patches only) */
+int  vrad_patches_upload(vrad_env*, int n, const float* origin3, const float* normal3, const float* plane_dist,
+                         const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags);
+/* patch-to-patch visibility + form factor -> transfer lists (common/types/transfer.go:3-6;
+ * Patch.NumTransfers/Transfers patch.go:60-61).  pvs: n_clusters x n_clusters bytes (non-zero = visible)
+ * or NULL.  Builds and keeps resident the CSR rows owned by this rank.  nnz_out = local nnz. */
+int  vrad_build_transfers(vrad_env*, int n_clusters, const uint8_t* pvs, int64_t* nnz_out);
+/* adopt prebuilt transfer rows [row0,row1): rowptr has row1-row0+1 entries starting at 0 */
+int  vrad_transfers_upload(vrad_env*, int64_t row0, int64_t row1, const int64_t* rowptr, const int32_t* col, const float* w);
+int  vrad_transfers_info(vrad_env*, int64_t* row0, int64_t* row1, int64_t* nnz);
+int  vrad_transfers_download(vrad_env*, int64_t* rowptr, int32_t* col, float* w);
+/* sky-ambient sample directions (vmath.Anorms, vmath/constants.go:15,21-184) */
+int  vrad_set_sky_dirs(vrad_env*, int n, const float* dirs3);
+/* per-luxel direct lighting with shadow rays (north_star K3; light parameters per vrad_light) */
+int  vrad_direct_light(vrad_env*, int64_t n_luxels, const float* pos3, const float* normal3,
+                       int n_lights, const vrad_light* lights, float* rgb_out);
+/* iterative bounce gather over the resident transfers (north_star K4).  emit0_rgb: N*3 initial patch
+ * radiance; total_rgb_out: N*3 accumulated bounced light (all rows, gathered across ranks);
+ * added_last: RGB sum emitted by the last bounce; early_out: stop when all of added < 1. */
+int  vrad_bounce(vrad_env*, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out,
+                 float added_last[3], int* bounces_done);
+
+/* ---- multi-GPU plumbing ------------------------------------------------------------------ */
+/* 128-byte NCCL unique id: rank 0 calls vrad_comm_unique_id, the driver distributes it, every rank
+ * calls vrad_comm_init before vrad_bounce. */
+int  vrad_comm_unique_id(void* out128);
+int  vrad_comm_init(vrad_env*, const void* unique_id128);
+
+/* library / build identification */
+const char* vrad_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRAD_CUDA_H */

@@ -1,0 +1,101 @@
+// comm.cu -- multi-GPU plumbing: one handle per process/GPU; the only data-path collective is the
+// per-bounce radiance all-gather of K4 (plus a 3-float all-reduce of `added`).  NCCL is resolved at
+// run time with dlopen("libnccl.so.2") so that a process that already loaded NCCL (e.g. through
+// torch.distributed) shares that copy and a single-GPU user needs no NCCL at all.
+// The reference has no communication layer of any kind.
+#include "env_internal.cuh"
+#include <dlfcn.h>
+
+namespace vrad {
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm_t;
+typedef int (*fn_get_uid)(nccl_uid*);
+typedef int (*fn_init_rank)(nccl_comm_t*, int, nccl_uid, int);
+typedef int (*fn_destroy)(nccl_comm_t);
+typedef const char* (*fn_errstr)(int);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+
+static struct {
+    void* h = nullptr;
+    fn_get_uid get_uid; fn_init_rank init_rank; fn_destroy destroy; fn_errstr errstr;
+    fn_allgather allgather; fn_allreduce allreduce;
+} g_nccl;
+
+constexpr int kNcclFloat = 7;   // ncclFloat32
+constexpr int kNcclSum = 0;     // ncclSum
+
+static int load_nccl() {
+    if (g_nccl.h) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { set_error("cannot load libnccl.so.2: %s", dlerror()); return VRAD_E_COMM; }
+    g_nccl.get_uid = (fn_get_uid)dlsym(h, "ncclGetUniqueId");
+    g_nccl.init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
+    g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
+    g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
+    g_nccl.allgather = (fn_allgather)dlsym(h, "ncclAllGather");
+    g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
+    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.errstr || !g_nccl.allgather || !g_nccl.allreduce) {
+        set_error("libnccl.so.2 lacks a required symbol"); dlclose(h); return VRAD_E_COMM;
+    }
+    g_nccl.h = h;
+    return 0;
+}
+
+#define VRAD_NCCL_CHECK(expr)                                                                  \
+    do {                                                                                       \
+        int _r = (expr);                                                                       \
+        if (_r != 0) { set_error("%s failed: %s", #expr, g_nccl.errstr(_r)); return VRAD_E_COMM; } \
+    } while (0)
+
+// in-place all-gather: rank r's rows_per_rank float4 rows already sit at buf + r*rows_per_rank
+int comm_allgather_f4(vrad_env* e, float4* buf, size_t rows_per_rank) {
+    if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
+    const float4* send = buf + (size_t)e->cfg.rank * rows_per_rank;
+    VRAD_NCCL_CHECK(g_nccl.allgather(send, buf, rows_per_rank * 4, kNcclFloat, (nccl_comm_t)e->nccl_comm, e->stream));
+    return 0;
+}
+
+int comm_allreduce3(vrad_env* e, float* d3) {
+    if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
+    VRAD_NCCL_CHECK(g_nccl.allreduce(d3, d3, 3, kNcclFloat, kNcclSum, (nccl_comm_t)e->nccl_comm, e->stream));
+    return 0;
+}
+
+} // namespace vrad
+using namespace vrad;
+
+extern "C" {
+
+int vrad_comm_unique_id(void* out128) {
+    if (!out128) return VRAD_E_INVALID;
+    int rc = load_nccl();
+    if (rc) return rc;
+    nccl_uid id;
+    VRAD_NCCL_CHECK(g_nccl.get_uid(&id));
+    memcpy(out128, id.internal, 128);
+    return VRAD_OK;
+}
+
+int vrad_comm_init(vrad_env* e, const void* unique_id128) {
+    if (!e || !unique_id128) return VRAD_E_INVALID;
+    if (e->cfg.world == 1) return VRAD_OK;
+    if (e->nccl_comm) { set_error("vrad_comm_init: already initialised"); return VRAD_E_STATE; }
+    int rc = load_nccl();
+    if (rc) return rc;
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    nccl_uid id;
+    memcpy(id.internal, unique_id128, 128);
+    nccl_comm_t c = nullptr;
+    VRAD_NCCL_CHECK(g_nccl.init_rank(&c, e->cfg.world, id, e->cfg.rank));
+    e->nccl_comm = c;
+    return VRAD_OK;
+}
+
+void vrad_comm_destroy_internal(vrad_env* e) {
+    if (e && e->nccl_comm && g_nccl.h) { g_nccl.destroy((nccl_comm_t)e->nccl_comm); e->nccl_comm = nullptr; }
+}
+
+} // extern "C"

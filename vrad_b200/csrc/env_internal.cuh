@@ -1,0 +1,131 @@
+// env_internal.cuh -- the vrad_env handle and small host helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/vrad_cuda.h"
+#include "common.cuh"
+#include "kd_builder.hpp"
+
+namespace vrad {
+
+void set_error(const char* fmt, ...);
+
+#define VRAD_CUDA_CHECK(expr)                                                                       \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            vrad::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return VRAD_E_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+// Owning device buffer (raw cudaMalloc; freed with the handle).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return 0;
+        release();
+        if (count == 0) return 0;
+        if (cudaMalloc((void**)&p, count * sizeof(T)) != cudaSuccess) { p = nullptr; n = 0; cudaGetLastError(); return -1; }
+        n = count;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// A caller pointer staged for device use: device pointers pass through, host pointers are
+// copied into a scratch buffer on the handle's stream.
+struct Staged {
+    const void* dev = nullptr;
+    bool was_host = false;
+};
+
+struct PatchesDev {
+    int n = 0;
+    DevBuf<float4> origin_area;     // origin.xyz, area
+    DevBuf<float4> normal_dist;     // normal.xyz, plane_dist
+    DevBuf<float4> refl;            // reflectivity.rgb, sky flag (1.0 = sky)
+    DevBuf<int32_t> cluster;
+    std::vector<int32_t> h_cluster;
+    std::vector<uint8_t> h_flags;
+};
+
+struct TransfersDev {
+    int64_t row0 = 0, row1 = 0;     // rows owned by this rank
+    int64_t nnz = 0;                // logical (unpadded) entries
+    int64_t nnz_padded = 0;         // device entries (rows padded to multiples of 4)
+    DevBuf<int64_t> rowptr;         // padded offsets, row1-row0+1 entries, in units of entries
+    DevBuf<int32_t> rowlen;         // logical row lengths
+    DevBuf<int32_t> col;
+    DevBuf<float>   w;
+    bool ready = false;
+};
+
+} // namespace vrad
+
+struct vrad_env {
+    vrad_config cfg{};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    bool async = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.0f;
+    int last_launches = 0;
+    int sm_count = 148;
+
+    // host geometry (Environment.OptimizedTriangleList before SetupAccelerationStructure)
+    std::vector<int32_t> h_ids;
+    std::vector<float>   h_verts;
+    std::vector<uint8_t> h_flags;
+    // host copies of the built tree in reference layout
+    vrad::KdTree tree;
+    std::vector<vrad_tri48> h_tris;
+    double build_seconds = 0.0;
+    bool built = false;
+
+    // device scene
+    vrad::DevBuf<int2> d_nodes;
+    vrad::DevBuf<int32_t> d_tri_index;
+    vrad::DevBuf<float4> d_q0, d_q1, d_q2;
+    vrad::DevScene scene{};
+
+    // scratch for staging host pointers
+    std::vector<vrad::DevBuf<unsigned char>> scratch;
+    size_t scratch_used = 0;
+
+    vrad::PatchesDev patches;
+    vrad::TransfersDev transfers;
+    vrad::DevBuf<float> d_sky_dirs; int n_sky_dirs = 0;
+
+    // bounce state
+    vrad::DevBuf<float4> d_er[2];      // emit*refl (rgb, pad), full N (padded to world*rows_per_rank)
+    vrad::DevBuf<float4> d_total;      // accumulated bounced light for local rows
+    vrad::DevBuf<float>  d_partials;   // per-block partial sums of `added`
+    void* nccl_comm = nullptr;         // ncclComm_t
+};
+
+namespace vrad {
+
+bool is_device_ptr(const void* p);
+// returns a device pointer for `p` (n bytes); host memory is copied H2D on e->stream into scratch slot `slot`
+int stage_in(vrad_env* e, int slot, const void* p, size_t bytes, const void** dev_out, bool* was_host);
+// returns a device pointer to write results into; if `p` is host memory a scratch buffer is used
+int stage_out(vrad_env* e, int slot, void* p, size_t bytes, void** dev_out, bool* was_host);
+int finish_out(vrad_env* e, void* host_p, const void* dev_p, size_t bytes, bool was_host);
+void timing_begin(vrad_env* e);
+void timing_end(vrad_env* e, int launches);
+int sync_if_needed(vrad_env* e, bool any_host);
+
+// kernel launchers implemented in the k*.cu files
+int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, const float* oz, const float* dx,
+                      const float* dy, const float* dz, const float* tmin, const float* tmax, int32_t skip_id,
+                      int32_t* hit_tri, int32_t* hit_sid, float* hit_t, float* normal_soa);
+int launch_test_lines(vrad_env* e, int64_t n, const float* start_soa, const float* stop_soa, int sky_mode, uint32_t* bits);
+
+} // namespace vrad

@@ -1,0 +1,241 @@
+// k2_transfers.cu -- K2: patch-to-patch visibility + form factor -> resident CSR transfer lists.
+//
+// Absent from the reference: only the element type exists (common/types/transfer.go:3-6, counters
+// Patch.NumTransfers/Transfers at common/types/patch.go:60-61); the patch fields read here are
+// those of common/types/patch.go:9-64.  Semantics follow SURVEY.md App. B.3 (vismat.cpp):
+// for receiver i and every candidate j in the clusters visible from cluster(i):
+//   keep (j, area_j * scale)  iff  j not sky, area_j > 0, origin_j in front of i's plane (+0.01),
+//   scale = -(D.n_i)(D.n_j) / (pi * len^2) > 0, area_j*scale > 1e-7, and the segment between
+//   origin+normal of the two patches (always traced from the lower to the higher index) is clear.
+// MakeScales: rows whose weights sum above 1 are rescaled to sum 1.
+//
+// Rows are independent -> sharded by rank with no collective.  Three device passes:
+//   A  thread per (row, candidate): cheap tests, then the shadow ray; one ballot word per 32 pairs
+//      into a bit matrix (rays are generated on the device -- no per-pair HBM input at all);
+//   B  warp per row: popcount -> row lengths; exclusive scan (cub) over 4-entry padded lengths;
+//   C  warp per row: expand set bits in order into (col, w), sequential row sum, MakeScales.
+// Algorithmic HBM bytes: 8*nnz + 64*N + 4*(N+1).
+#include "env_internal.cuh"
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+
+namespace vrad {
+
+constexpr float kPlaneTestEpsilon = 0.01f;
+constexpr float kTransEpsilon = 1.0e-7f;
+constexpr float kPiF = 3.14159265358979323846f;
+
+struct PatchView {
+    const float4* origin_area;
+    const float4* normal_dist;
+    const float4* refl;        // .w = sky flag
+};
+
+// MakeTransfer weight (0 = nothing transfers).  Same operation order as the CPU formulation.
+__device__ __forceinline__ float transfer_weight(const float4 oi, const float4 ni, const float4 oj, const float4 nj, float sky_j) {
+    if (sky_j != 0.0f || !(oj.w > 0.0f)) return 0.0f;
+    const float side = ((oj.x * ni.x) + (oj.y * ni.y)) + (oj.z * ni.z);
+    if (!(side > ni.w + kPlaneTestEpsilon)) return 0.0f;
+    float dx = oi.x - oj.x, dy = oi.y - oj.y, dz = oi.z - oj.z;
+    const float len2 = ((dx * dx) + (dy * dy)) + (dz * dz);
+    const float len = sqrtf(len2);
+    if (!(len > 0.0f)) return 0.0f;
+    const float r = 1.0f / len;
+    dx = dx * r; dy = dy * r; dz = dz * r;
+    const float d1 = ((dx * ni.x) + (dy * ni.y)) + (dz * ni.z);
+    const float d2 = ((dx * nj.x) + (dy * nj.y)) + (dz * nj.z);
+    const float scale = -(d1 * d2) / ((len * len) * kPiF);
+    if (!(scale > 0.0f)) return 0.0f;
+    const float trans = oj.w * scale;
+    if (!(trans > kTransEpsilon)) return 0.0f;
+    return trans;
+}
+
+// Pass A.  One block per local row; threads sweep that row's candidate list.
+__global__ void __launch_bounds__(256)
+k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __restrict__ cluster,
+              const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx,
+              const int64_t* __restrict__ bit_ptr, uint32_t* __restrict__ bits) {
+    for (int row = blockIdx.x; row < nloc; row += gridDim.x) {
+        const int i = (int)(row0 + row);
+        const float4 oi = __ldg(&P.origin_area[i]), ni = __ldg(&P.normal_dist[i]);
+        const bool sky_i = __ldg(&P.refl[i]).w != 0.0f;
+        const int c = __ldg(&cluster[i]);
+        const int64_t c0 = __ldg(&cand_ptr[c]);
+        const int K = (int)(__ldg(&cand_ptr[c + 1]) - c0);
+        const int Kpad = (K + 31) & ~31;
+        uint32_t* out = bits + bit_ptr[row];
+        for (int p = threadIdx.x; p < Kpad; p += blockDim.x) {
+            int keep = 0;
+            if (p < K && !sky_i) {
+                const int j = __ldg(&cand_idx[c0 + p]);
+                if (j != i) {
+                    const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
+                    const float w = transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w);
+                    if (w != 0.0f) {
+                        const bool lo = i < j;
+                        const float4 a = lo ? oi : oj, an = lo ? ni : nj, b = lo ? oj : oi, bn = lo ? nj : ni;
+                        keep = segment_visible(S, a.x + an.x, a.y + an.y, a.z + an.z, b.x + bn.x, b.y + bn.y, b.z + bn.z, 0);
+                    }
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if ((threadIdx.x & 31) == 0) out[p >> 5] = m;
+        }
+    }
+}
+
+// Pass B.  Warp per row: number of kept transfers, and the 4-entry padded length for the scan.
+__global__ void k2_count(int nloc, const int64_t* __restrict__ bit_ptr, const uint32_t* __restrict__ bits,
+                         int32_t* __restrict__ rowlen, int64_t* __restrict__ padded_len) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= nloc) return;
+    const int64_t w0 = bit_ptr[row], w1 = bit_ptr[row + 1];
+    int cnt = 0;
+    for (int64_t w = w0 + lane; w < w1; w += 32) cnt += __popc(bits[w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) { rowlen[row] = cnt; padded_len[row] = (cnt + 3) & ~3; }
+}
+
+// Pass C.  Warp per row: expand bits in candidate order, then MakeScales.
+__global__ void k2_fill(PatchView P, int nloc, int64_t row0, const int32_t* __restrict__ cluster,
+                        const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx,
+                        const int64_t* __restrict__ bit_ptr, const uint32_t* __restrict__ bits,
+                        const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen,
+                        int32_t* __restrict__ col, float* __restrict__ w) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= nloc) return;
+    const int i = (int)(row0 + row);
+    const float4 oi = P.origin_area[i], ni = P.normal_dist[i];
+    const int64_t c0 = cand_ptr[cluster[i]];
+    const int64_t w0 = bit_ptr[row], w1 = bit_ptr[row + 1];
+    const int64_t base = rowptr[row];
+    const int len = rowlen[row];
+    int pos = 0;
+    for (int64_t wd = w0; wd < w1; wd++) {
+        const uint32_t m = bits[wd];
+        if (m == 0) continue;
+        if ((m >> lane) & 1u) {
+            const int j = cand_idx[c0 + (wd - w0) * 32 + lane];
+            const int k = pos + __popc(m & ((1u << lane) - 1u));
+            col[base + k] = j;
+            w[base + k] = transfer_weight(oi, ni, P.origin_area[j], P.normal_dist[j], P.refl[j].w);
+        }
+        pos += __popc(m);
+    }
+    const int lenp = (len + 3) & ~3;
+    for (int k = len + lane; k < lenp; k += 32) { col[base + k] = 0; w[base + k] = 0.0f; }   // padding entries
+    __syncwarp();
+    float total = 0.0f;
+    if (lane == 0) for (int k = 0; k < len; k++) total = total + w[base + k];               // CSR-order fp32 sum
+    total = __shfl_sync(0xffffffffu, total, 0);
+    if (total > 1.0f) {
+        const float s = 1.0f / total;
+        for (int k = lane; k < len; k += 32) w[base + k] = w[base + k] * s;
+    }
+}
+
+} // namespace vrad
+using namespace vrad;
+
+extern "C" {
+
+int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_t* nnz_out) {
+    if (!e) return VRAD_E_INVALID;
+    if (!e->built) { set_error("vrad_build_transfers: acceleration structure not built"); return VRAD_E_STATE; }
+    PatchesDev& P = e->patches;
+    if (P.n == 0) { set_error("vrad_build_transfers: upload patches first"); return VRAD_E_STATE; }
+    if (pvs && n_clusters <= 0) { set_error("vrad_build_transfers: pvs given but n_clusters <= 0"); return VRAD_E_INVALID; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const int N = P.n;
+    const int C = pvs ? n_clusters : 1;
+    // host: per-cluster patch lists, then per-cluster sorted candidate lists (PVS-visible clusters)
+    std::vector<int32_t> clus(N, 0);
+    if (pvs) {
+        for (int i = 0; i < N; i++) {
+            int c = P.h_cluster[i];
+            if (c < 0 || c >= C) { set_error("vrad_build_transfers: patch %d has cluster %d outside [0,%d)", i, c, C); return VRAD_E_INVALID; }
+            clus[i] = c;
+        }
+    }
+    std::vector<std::vector<int32_t>> members(C);
+    for (int i = 0; i < N; i++) members[clus[i]].push_back(i);
+    std::vector<int64_t> cand_ptr(C + 1, 0);
+    std::vector<int32_t> cand_idx;
+    for (int c = 0; c < C; c++) {
+        size_t start = cand_idx.size();
+        for (int c2 = 0; c2 < C; c2++)
+            if (!pvs || pvs[(size_t)c * C + c2]) cand_idx.insert(cand_idx.end(), members[c2].begin(), members[c2].end());
+        std::sort(cand_idx.begin() + start, cand_idx.end());
+        cand_ptr[c + 1] = (int64_t)cand_idx.size();
+    }
+    const int world = e->cfg.world;
+    const int64_t rpr = ((int64_t)N + world - 1) / world;
+    const int64_t row0 = std::min<int64_t>(N, e->cfg.rank * rpr), row1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
+    const int nloc = (int)(row1 - row0);
+    std::vector<int64_t> bit_ptr(nloc + 1, 0);
+    for (int r = 0; r < nloc; r++) {
+        int c = clus[row0 + r];
+        bit_ptr[r + 1] = bit_ptr[r] + ((cand_ptr[c + 1] - cand_ptr[c] + 31) >> 5);
+    }
+    const int64_t nwords = bit_ptr[nloc];
+
+    DevBuf<int32_t> d_clus, d_cand_idx; DevBuf<int64_t> d_cand_ptr, d_bit_ptr, d_padlen; DevBuf<uint32_t> d_bits; DevBuf<unsigned char> d_tmp;
+    TransfersDev& T = e->transfers;
+    T.ready = false;
+    auto cleanup = [&]() { d_clus.release(); d_cand_idx.release(); d_cand_ptr.release(); d_bit_ptr.release(); d_padlen.release(); d_bits.release(); d_tmp.release(); };
+    if (d_clus.alloc(N) || d_cand_idx.alloc(cand_idx.size() + 1) || d_cand_ptr.alloc(C + 1) || d_bit_ptr.alloc(nloc + 1) ||
+        d_padlen.alloc(nloc + 1) || d_bits.alloc(nwords + 1) || T.rowptr.alloc(nloc + 1) || T.rowlen.alloc(nloc + 1)) {
+        cleanup(); set_error("out of device memory for transfer build (%lld visibility words)", (long long)nwords); return VRAD_E_NOMEM;
+    }
+#define K2_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); return VRAD_E_CUDA; } } while (0)
+    K2_CHECK(cudaMemcpyAsync(d_clus.p, clus.data(), (size_t)N * 4, cudaMemcpyHostToDevice, e->stream));
+    if (!cand_idx.empty()) K2_CHECK(cudaMemcpyAsync(d_cand_idx.p, cand_idx.data(), cand_idx.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    K2_CHECK(cudaMemcpyAsync(d_cand_ptr.p, cand_ptr.data(), (C + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    K2_CHECK(cudaMemcpyAsync(d_bit_ptr.p, bit_ptr.data(), (nloc + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    K2_CHECK(cudaMemsetAsync(d_padlen.p, 0, (nloc + 1) * 8, e->stream));
+
+    PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p};
+    timing_begin(e);
+    int launches = 0;
+    if (nloc > 0) {
+        k2_visibility<<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p);
+        launches++;
+        const int wblocks = (nloc * 32 + 255) / 256;
+        k2_count<<<wblocks, 256, 0, e->stream>>>(nloc, d_bit_ptr.p, d_bits.p, T.rowlen.p, d_padlen.p);
+        launches++;
+    }
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_padlen.p, T.rowptr.p, nloc + 1, e->stream);
+    if (d_tmp.alloc(tmp_bytes + 16)) { cleanup(); set_error("out of device memory (scan scratch)"); return VRAD_E_NOMEM; }
+    K2_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_padlen.p, T.rowptr.p, nloc + 1, e->stream));
+    launches++;
+    int64_t np = 0;
+    K2_CHECK(cudaMemcpyAsync(&np, T.rowptr.p + nloc, 8, cudaMemcpyDeviceToHost, e->stream));
+    K2_CHECK(cudaStreamSynchronize(e->stream));
+    if (T.col.alloc(np + 4) || T.w.alloc(np + 4)) { cleanup(); set_error("out of device memory for %lld transfers", (long long)np); return VRAD_E_NOMEM; }
+    if (nloc > 0) {
+        const int wblocks = (nloc * 32 + 255) / 256;
+        k2_fill<<<wblocks, 256, 0, e->stream>>>(pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
+                                               T.rowptr.p, T.rowlen.p, T.col.p, T.w.p);
+        launches++;
+    }
+    timing_end(e, launches);
+    // logical nnz = sum of row lengths
+    std::vector<int32_t> rl(nloc ? nloc : 1);
+    if (nloc) K2_CHECK(cudaMemcpyAsync(rl.data(), T.rowlen.p, (size_t)nloc * 4, cudaMemcpyDeviceToHost, e->stream));
+    K2_CHECK(cudaStreamSynchronize(e->stream));
+    K2_CHECK(cudaGetLastError());
+#undef K2_CHECK
+    int64_t nnz = 0;
+    for (int r = 0; r < nloc; r++) nnz += rl[r];
+    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.ready = true;
+    cleanup();
+    if (nnz_out) *nnz_out = nnz;
+    return VRAD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,302 @@
+// k4_bounce.cu -- patches, resident transfer lists and K4: the iterative bounce gather.
+//
+// The reference has no bounce code (cmd/tasks/computerad/main.go:5-10 comments the step out);
+// the data it would run on is common/types/patch.go:9-64 (Reflectivity, TotalLight, Sky, ...)
+// and common/types/transfer.go:3-6 ({Patch, Transfer} = one CSR entry).  Semantics follow
+// SURVEY.md App. B.4 (GatherLight / CollectLight / BounceLight, leaf patches only):
+//     add[i]   = sum_k w[i,k] * (emit[col[i,k]] * refl[col[i,k]])
+//     total[i] += add[i];  emit[i] = add[i];  added += emit[i]        (sky patches: emit = 0)
+//
+// HBM layout: transfers are a padded CSR -- every row starts on a 4-entry (16-byte) boundary so a
+// lane loads 4 columns + 4 weights as two 128-bit vectors; `er` = emit*refl is kept as one float4
+// per patch (16 B gathers that live in L2: 3.2 MB at 200k patches, 32 MB at 2M).  Algorithmic
+// bytes per bounce: 8*nnz + 40*N; the kernel is HBM-bound on the 8*nnz stream.
+// One warp per row, warp-shuffle reduction, collect step fused into the epilogue.
+#include "env_internal.cuh"
+#include <algorithm>
+
+namespace vrad {
+
+int comm_allgather_f4(vrad_env* e, float4* buf, size_t rows_per_rank);
+int comm_allreduce3(vrad_env* e, float* d3);
+
+constexpr int kGatherBlock = 256;
+constexpr int kGatherWarps = kGatherBlock / 32;
+
+__global__ void k4_init_er(int n_pad, int n, const float* __restrict__ emit0, const float4* __restrict__ refl,
+                           float4* __restrict__ er) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+        float4 r = refl[i];
+        if (r.w == 0.0f) v = make_float4(emit0[3 * i] * r.x, emit0[3 * i + 1] * r.y, emit0[3 * i + 2] * r.z, 0.f);
+    }
+    er[i] = v;
+}
+
+__global__ void __launch_bounds__(kGatherBlock)
+k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int4* __restrict__ col4,
+          const float4* __restrict__ w4, const float4* __restrict__ er, const float4* __restrict__ refl,
+          float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * kGatherWarps + warp;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    if (row < nloc) {
+        const int64_t q0 = rowptr[row] >> 2, q1 = rowptr[row + 1] >> 2;     // in 4-entry groups
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        int64_t q = q0 + lane;
+        for (; q + 32 < q1; q += 64) {                                      // two groups in flight per lane
+            const int4 ca = __ldcs(&col4[q]); const float4 wa = __ldcs(&w4[q]);
+            const int4 cb = __ldcs(&col4[q + 32]); const float4 wb = __ldcs(&w4[q + 32]);
+            const float4 a0 = __ldg(&er[ca.x]), a1 = __ldg(&er[ca.y]), a2 = __ldg(&er[ca.z]), a3 = __ldg(&er[ca.w]);
+            const float4 b0 = __ldg(&er[cb.x]), b1 = __ldg(&er[cb.y]), b2 = __ldg(&er[cb.z]), b3 = __ldg(&er[cb.w]);
+            s0 += wa.x * a0.x + wa.y * a1.x + wa.z * a2.x + wa.w * a3.x;
+            s1 += wa.x * a0.y + wa.y * a1.y + wa.z * a2.y + wa.w * a3.y;
+            s2 += wa.x * a0.z + wa.y * a1.z + wa.z * a2.z + wa.w * a3.z;
+            t0 += wb.x * b0.x + wb.y * b1.x + wb.z * b2.x + wb.w * b3.x;
+            t1 += wb.x * b0.y + wb.y * b1.y + wb.z * b2.y + wb.w * b3.y;
+            t2 += wb.x * b0.z + wb.y * b1.z + wb.z * b2.z + wb.w * b3.z;
+        }
+        if (q < q1) {
+            const int4 ca = __ldcs(&col4[q]); const float4 wa = __ldcs(&w4[q]);
+            const float4 a0 = __ldg(&er[ca.x]), a1 = __ldg(&er[ca.y]), a2 = __ldg(&er[ca.z]), a3 = __ldg(&er[ca.w]);
+            s0 += wa.x * a0.x + wa.y * a1.x + wa.z * a2.x + wa.w * a3.x;
+            s1 += wa.x * a0.y + wa.y * a1.y + wa.z * a2.y + wa.w * a3.y;
+            s2 += wa.x * a0.z + wa.y * a1.z + wa.z * a2.z + wa.w * a3.z;
+        }
+        s0 += t0; s1 += t1; s2 += t2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            const float4 r = refl[row0 + row];
+            if (r.w == 0.0f) {                                              // CollectLight, leaf patch
+                float4 t = total[row];
+                t.x += s0; t.y += s1; t.z += s2;
+                total[row] = t;
+                er_next[row0 + row] = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                e0 = s0; e1 = s1; e2 = s2;
+            } else {
+                er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);     // sky: emit = 0
+            }
+        }
+    }
+    // deterministic per-block partial of `added`
+    __shared__ float sm[kGatherWarps][3];
+    if (lane == 0) { sm[warp][0] = e0; sm[warp][1] = e1; sm[warp][2] = e2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < kGatherWarps; k++) a += sm[k][threadIdx.x];
+        partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    }
+}
+
+// single block: fixed-order tree reduction of the per-block partials -> added[3]
+__global__ void k4_reduce_added(int nblocks, const float* __restrict__ partials, float* __restrict__ added) {
+    __shared__ float sm[3][256];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int i = threadIdx.x; i < nblocks; i += 256) { a0 += partials[3 * i]; a1 += partials[3 * i + 1]; a2 += partials[3 * i + 2]; }
+    sm[0][threadIdx.x] = a0; sm[1][threadIdx.x] = a1; sm[2][threadIdx.x] = a2;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) for (int c = 0; c < 3; c++) sm[c][threadIdx.x] += sm[c][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) added[threadIdx.x] = sm[threadIdx.x][0];
+}
+
+__global__ void k4_unpack_total(int64_t n, const float4* __restrict__ total, float* __restrict__ out3) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 t = total[i];
+    out3[3 * i] = t.x; out3[3 * i + 1] = t.y; out3[3 * i + 2] = t.z;
+}
+
+static inline int64_t rows_per_rank(const vrad_env* e, int64_t n) { return (n + e->cfg.world - 1) / e->cfg.world; }
+
+} // namespace vrad
+using namespace vrad;
+
+extern "C" {
+
+int vrad_patches_upload(vrad_env* e, int n, const float* origin3, const float* normal3, const float* plane_dist,
+                        const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags) {
+    if (!e || n <= 0 || !origin3 || !normal3 || !plane_dist || !area || !reflectivity3) { set_error("vrad_patches_upload: bad arguments"); return VRAD_E_INVALID; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    PatchesDev& P = e->patches;
+    if (P.origin_area.alloc(n) || P.normal_dist.alloc(n) || P.refl.alloc(n) || P.cluster.alloc(n)) { set_error("out of device memory for patches"); return VRAD_E_NOMEM; }
+    std::vector<float4> oa(n), nd(n), rf(n);
+    P.h_cluster.assign(n, 0); P.h_flags.assign(n, 0);
+    for (int i = 0; i < n; i++) {
+        oa[i] = make_float4(origin3[3 * i], origin3[3 * i + 1], origin3[3 * i + 2], area[i]);
+        nd[i] = make_float4(normal3[3 * i], normal3[3 * i + 1], normal3[3 * i + 2], plane_dist[i]);
+        uint8_t f = flags ? flags[i] : 0;
+        rf[i] = make_float4(reflectivity3[3 * i], reflectivity3[3 * i + 1], reflectivity3[3 * i + 2], (f & 1) ? 1.0f : 0.0f);
+        P.h_flags[i] = f;
+        if (cluster) P.h_cluster[i] = cluster[i];
+    }
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(P.origin_area.p, oa.data(), (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(P.normal_dist.p, nd.data(), (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(P.refl.p, rf.data(), (size_t)n * 16, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(P.cluster.p, P.h_cluster.data(), (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    P.n = n;
+    e->transfers.ready = false;
+    return VRAD_OK;
+}
+
+int vrad_transfers_upload(vrad_env* e, int64_t row0, int64_t row1, const int64_t* rowptr, const int32_t* col, const float* w) {
+    if (!e || !rowptr || row0 < 0 || row1 < row0) { set_error("vrad_transfers_upload: bad arguments"); return VRAD_E_INVALID; }
+    const int64_t N = e->patches.n;
+    if (N == 0) { set_error("vrad_transfers_upload: upload patches first"); return VRAD_E_STATE; }
+    if (row1 > N) { set_error("vrad_transfers_upload: rows [%lld,%lld) exceed %lld patches", (long long)row0, (long long)row1, (long long)N); return VRAD_E_INVALID; }
+    if (e->cfg.world > 1) {
+        const int64_t rpr = rows_per_rank(e, N);
+        const int64_t want0 = std::min<int64_t>(N, e->cfg.rank * rpr), want1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
+        if (row0 != want0 || row1 != want1) { set_error("vrad_transfers_upload: rank %d owns rows [%lld,%lld)", e->cfg.rank, (long long)want0, (long long)want1); return VRAD_E_INVALID; }
+    }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const int64_t nloc = row1 - row0;
+    const int64_t nnz = rowptr[nloc] - rowptr[0];
+    if (nnz > 0 && (!col || !w)) { set_error("vrad_transfers_upload: col/w missing"); return VRAD_E_INVALID; }
+    std::vector<int64_t> prow(nloc + 1);
+    std::vector<int32_t> rlen(nloc ? nloc : 1);
+    prow[0] = 0;
+    for (int64_t i = 0; i < nloc; i++) {
+        int64_t len = rowptr[i + 1] - rowptr[i];
+        if (len < 0) { set_error("vrad_transfers_upload: rowptr not monotone at row %lld", (long long)i); return VRAD_E_INVALID; }
+        rlen[i] = (int32_t)len;
+        prow[i + 1] = prow[i] + ((len + 3) & ~(int64_t)3);
+    }
+    const int64_t np = prow[nloc];
+    std::vector<int32_t> pcol(np ? np : 4, 0);
+    std::vector<float> pw(np ? np : 4, 0.0f);
+    for (int64_t i = 0; i < nloc; i++) {
+        const int64_t s = rowptr[i] - rowptr[0];
+        for (int64_t k = 0; k < rlen[i]; k++) {
+            int32_t c = col[s + k];
+            if (c < 0 || c >= N) { set_error("vrad_transfers_upload: column %d out of range at row %lld", c, (long long)(row0 + i)); return VRAD_E_INVALID; }
+            pcol[prow[i] + k] = c; pw[prow[i] + k] = w[s + k];
+        }
+    }
+    TransfersDev& T = e->transfers;
+    if (T.rowptr.alloc(nloc + 1) || T.rowlen.alloc(nloc ? nloc : 1) || T.col.alloc(pcol.size()) || T.w.alloc(pw.size())) { set_error("out of device memory for transfers"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(T.rowptr.p, prow.data(), (nloc + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(T.rowlen.p, rlen.data(), rlen.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(T.col.p, pcol.data(), pcol.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(T.w.p, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.ready = true;
+    return VRAD_OK;
+}
+
+int vrad_transfers_info(vrad_env* e, int64_t* row0, int64_t* row1, int64_t* nnz) {
+    if (!e) return VRAD_E_INVALID;
+    if (!e->transfers.ready) { set_error("vrad_transfers_info: no transfers resident"); return VRAD_E_STATE; }
+    if (row0) *row0 = e->transfers.row0;
+    if (row1) *row1 = e->transfers.row1;
+    if (nnz) *nnz = e->transfers.nnz;
+    return VRAD_OK;
+}
+
+int vrad_transfers_download(vrad_env* e, int64_t* rowptr, int32_t* col, float* w) {
+    if (!e) return VRAD_E_INVALID;
+    TransfersDev& T = e->transfers;
+    if (!T.ready) { set_error("vrad_transfers_download: no transfers resident"); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const int64_t nloc = T.row1 - T.row0;
+    std::vector<int64_t> prow(nloc + 1);
+    std::vector<int32_t> rlen(nloc ? nloc : 1);
+    VRAD_CUDA_CHECK(cudaMemcpy(prow.data(), T.rowptr.p, (nloc + 1) * 8, cudaMemcpyDeviceToHost));
+    if (nloc) VRAD_CUDA_CHECK(cudaMemcpy(rlen.data(), T.rowlen.p, nloc * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> pcol(T.nnz_padded ? T.nnz_padded : 1);
+    std::vector<float> pw(T.nnz_padded ? T.nnz_padded : 1);
+    if (T.nnz_padded) {
+        VRAD_CUDA_CHECK(cudaMemcpy(pcol.data(), T.col.p, T.nnz_padded * 4, cudaMemcpyDeviceToHost));
+        VRAD_CUDA_CHECK(cudaMemcpy(pw.data(), T.w.p, T.nnz_padded * 4, cudaMemcpyDeviceToHost));
+    }
+    int64_t pos = 0;
+    for (int64_t i = 0; i < nloc; i++) {
+        if (rowptr) rowptr[i] = pos;
+        for (int32_t k = 0; k < rlen[i]; k++) {
+            if (col) col[pos + k] = pcol[prow[i] + k];
+            if (w) w[pos + k] = pw[prow[i] + k];
+        }
+        pos += rlen[i];
+    }
+    if (rowptr) rowptr[nloc] = pos;
+    return VRAD_OK;
+}
+
+int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out,
+                float added_last[3], int* bounces_done) {
+    if (!e || !emit0_rgb || n_bounces < 0) { set_error("vrad_bounce: bad arguments"); return VRAD_E_INVALID; }
+    TransfersDev& T = e->transfers;
+    if (!T.ready) { set_error("vrad_bounce: no transfers resident (vrad_build_transfers / vrad_transfers_upload first)"); return VRAD_E_STATE; }
+    if (e->cfg.world > 1 && !e->nccl_comm) { set_error("vrad_bounce: world=%d but vrad_comm_init was not called", e->cfg.world); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const int64_t N = e->patches.n;
+    const int world = e->cfg.world;
+    const int64_t rpr = rows_per_rank(e, N);
+    const int64_t n_pad = rpr * world;
+    const int nloc = (int)(T.row1 - T.row0);
+    const int nblocks = std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
+    // `total` is sized for a full gather at the end (rank r's rows live at r*rpr)
+    if (e->d_er[0].alloc(n_pad) || e->d_er[1].alloc(n_pad) || e->d_total.alloc(n_pad) || e->d_partials.alloc(3 * (size_t)nblocks + 8)) {
+        set_error("out of device memory for bounce state"); return VRAD_E_NOMEM;
+    }
+    int rc; const void* d_emit0; bool h_in, h_out;
+    if ((rc = stage_in(e, 0, emit0_rgb, (size_t)N * 12, &d_emit0, &h_in))) return rc;
+    void* d_out3;
+    if ((rc = stage_out(e, 1, total_rgb_out, (size_t)N * 12, &d_out3, &h_out))) return rc;
+    float* d_added = e->d_partials.p + 3 * (size_t)nblocks;       // 3 floats after the partials
+
+    timing_begin(e);
+    int launches = 0;
+    float4* total_local = e->d_total.p + (world > 1 ? e->cfg.rank * rpr : 0);
+    VRAD_CUDA_CHECK(cudaMemsetAsync(e->d_total.p, 0, (size_t)n_pad * 16, e->stream));
+    VRAD_CUDA_CHECK(cudaMemsetAsync(d_added, 0, 12, e->stream));
+    k4_init_er<<<(int)((n_pad + 255) / 256), 256, 0, e->stream>>>((int)n_pad, (int)N, (const float*)d_emit0, e->patches.refl.p, e->d_er[0].p);
+    launches++;
+    int cur = 0, done = 0;
+    float h_added[3] = {0.f, 0.f, 0.f};
+    for (int b = 0; b < n_bounces; b++) {
+        k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, (const int4*)T.col.p, (const float4*)T.w.p,
+                                                         e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
+        launches++;
+        if (world > 1 && (rc = comm_allgather_f4(e, e->d_er[cur ^ 1].p, (size_t)rpr))) return rc;
+        cur ^= 1; done++;
+        const bool last = (b + 1 == n_bounces);
+        if (early_out || last) {
+            k4_reduce_added<<<1, 256, 0, e->stream>>>(nblocks, e->d_partials.p, d_added);
+            launches++;
+            if (world > 1 && (rc = comm_allreduce3(e, d_added))) return rc;
+        }
+        if (early_out && !last) {
+            VRAD_CUDA_CHECK(cudaMemcpyAsync(h_added, d_added, 12, cudaMemcpyDeviceToHost, e->stream));
+            VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            if (h_added[0] < 1.0f && h_added[1] < 1.0f && h_added[2] < 1.0f) break;
+        }
+    }
+    if (world > 1 && (rc = comm_allgather_f4(e, e->d_total.p, (size_t)rpr))) return rc;
+    if (d_out3) {
+        k4_unpack_total<<<(int)((N + 255) / 256), 256, 0, e->stream>>>(N, e->d_total.p, (float*)d_out3);
+        launches++;
+    }
+    timing_end(e, launches);
+    VRAD_CUDA_CHECK(cudaGetLastError());
+    if ((rc = finish_out(e, total_rgb_out, d_out3, (size_t)N * 12, h_out))) return rc;
+    const bool need_sync = h_in || h_out || added_last != nullptr;
+    if (added_last) VRAD_CUDA_CHECK(cudaMemcpyAsync(added_last, d_added, 12, cudaMemcpyDeviceToHost, e->stream));
+    if (bounces_done) *bounces_done = done;
+    return sync_if_needed(e, need_sync);
+}
+
+} // extern "C"

@@ -1,0 +1,355 @@
+// vrad_env.cu -- handle lifetime, geometry/tree management and the K1 entry points of the C-ABI.
+// Reference map per function: see include/vrad_cuda.h.
+#include "env_internal.cuh"
+#include <chrono>
+#include <cstdarg>
+#include <new>
+
+namespace vrad {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int scratch_get(vrad_env* e, int slot, size_t bytes, void** out) {
+    if ((size_t)slot >= e->scratch.size()) e->scratch.resize(slot + 1);
+    if (e->scratch[slot].alloc(bytes ? bytes : 1) != 0) { set_error("out of device memory (%zu bytes)", bytes); return VRAD_E_NOMEM; }
+    *out = e->scratch[slot].p;
+    return 0;
+}
+
+int stage_in(vrad_env* e, int slot, const void* p, size_t bytes, const void** dev_out, bool* was_host) {
+    if (!p) { *dev_out = nullptr; if (was_host) *was_host = false; return 0; }
+    if (is_device_ptr(p)) { *dev_out = p; if (was_host) *was_host = false; return 0; }
+    void* d = nullptr;
+    int rc = scratch_get(e, slot, bytes, &d);
+    if (rc) return rc;
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, e->stream));
+    *dev_out = d;
+    if (was_host) *was_host = true;
+    return 0;
+}
+
+int stage_out(vrad_env* e, int slot, void* p, size_t bytes, void** dev_out, bool* was_host) {
+    if (!p) { *dev_out = nullptr; *was_host = false; return 0; }
+    if (is_device_ptr(p)) { *dev_out = p; *was_host = false; return 0; }
+    int rc = scratch_get(e, slot, bytes, dev_out);
+    if (rc) return rc;
+    *was_host = true;
+    return 0;
+}
+
+int finish_out(vrad_env* e, void* host_p, const void* dev_p, size_t bytes, bool was_host) {
+    if (!was_host || !host_p) return 0;
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(host_p, dev_p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    return 0;
+}
+
+void timing_begin(vrad_env* e) { cudaEventRecord(e->ev0, e->stream); }
+void timing_end(vrad_env* e, int launches) { cudaEventRecord(e->ev1, e->stream); e->last_launches = launches; e->last_ms = -1.0f; }
+
+int sync_if_needed(vrad_env* e, bool any_host) {
+    if (any_host || !e->async) {
+        VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        VRAD_CUDA_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int upload_scene(vrad_env* e) {
+    const KdTree& T = e->tree;
+    const size_t nn = T.children.size(), ni = T.tri_index.size(), nt = e->h_tris.size();
+    if (e->d_nodes.alloc(nn) || e->d_tri_index.alloc(ni ? ni : 1) || e->d_q0.alloc(nt ? nt : 1) ||
+        e->d_q1.alloc(nt ? nt : 1) || e->d_q2.alloc(nt ? nt : 1)) {
+        set_error("out of device memory for scene"); return VRAD_E_NOMEM;
+    }
+    std::vector<int2> nodes(nn);
+    for (size_t i = 0; i < nn; i++) { nodes[i].x = T.children[i]; memcpy(&nodes[i].y, &T.split[i], 4); }
+    std::vector<float4> q0(nt), q1(nt), q2(nt);
+    for (size_t i = 0; i < nt; i++) {
+        const vrad_tri48& t = e->h_tris[i];
+        q0[i] = make_float4(t.nx, t.ny, t.nz, t.d);
+        q1[i] = make_float4(t.e[0], t.e[1], t.e[2], t.e[3]);
+        int32_t sel = (int32_t)t.sel0 | ((int32_t)t.sel1 << 8) | ((int32_t)t.flags << 16);
+        float idf, self;
+        memcpy(&idf, &t.id, 4); memcpy(&self, &sel, 4);
+        q2[i] = make_float4(t.e[4], t.e[5], idf, self);
+    }
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(e->d_nodes.p, nodes.data(), nn * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+    if (ni) VRAD_CUDA_CHECK(cudaMemcpyAsync(e->d_tri_index.p, T.tri_index.data(), ni * 4, cudaMemcpyHostToDevice, e->stream));
+    if (nt) {
+        VRAD_CUDA_CHECK(cudaMemcpyAsync(e->d_q0.p, q0.data(), nt * 16, cudaMemcpyHostToDevice, e->stream));
+        VRAD_CUDA_CHECK(cudaMemcpyAsync(e->d_q1.p, q1.data(), nt * 16, cudaMemcpyHostToDevice, e->stream));
+        VRAD_CUDA_CHECK(cudaMemcpyAsync(e->d_q2.p, q2.data(), nt * 16, cudaMemcpyHostToDevice, e->stream));
+    }
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    DevScene& S = e->scene;
+    S.nodes = e->d_nodes.p; S.tri_index = e->d_tri_index.p; S.q0 = e->d_q0.p; S.q1 = e->d_q1.p; S.q2 = e->d_q2.p;
+    for (int c = 0; c < 3; c++) { S.bmin[c] = T.bmin[c]; S.bmax[c] = T.bmax[c]; }
+    S.n_nodes = (int)nn; S.n_idx = (int)ni; S.n_tris = (int)nt;
+    e->built = true;
+    return 0;
+}
+
+} // namespace vrad
+
+using namespace vrad;
+
+extern "C" {
+
+const char* vrad_last_error(void) { return g_err; }
+const char* vrad_version(void) { return "vrad-b200 0.1 (sm_100a)"; }
+
+int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
+    if (!out) { set_error("vrad_env_create: out is NULL"); return VRAD_E_INVALID; }
+    *out = nullptr;
+    vrad_config c{0, 0, 1, 0};
+    if (cfg) c = *cfg;
+    if (c.world < 1 || c.rank < 0 || c.rank >= c.world) { set_error("vrad_env_create: bad rank/world %d/%d", c.rank, c.world); return VRAD_E_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("vrad_env_create: no CUDA device (this library has no CPU fallback)");
+        return VRAD_E_CUDA;
+    }
+    if (c.device < 0 || c.device >= ndev) { set_error("vrad_env_create: device %d out of range (%d devices)", c.device, ndev); return VRAD_E_INVALID; }
+    VRAD_CUDA_CHECK(cudaSetDevice(c.device));
+    vrad_env* e = new (std::nothrow) vrad_env();
+    if (!e) return VRAD_E_NOMEM;
+    e->cfg = c;
+    cudaDeviceProp prop;
+    VRAD_CUDA_CHECK(cudaGetDeviceProperties(&prop, c.device));
+    e->sm_count = prop.multiProcessorCount;
+    VRAD_CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    VRAD_CUDA_CHECK(cudaEventCreate(&e->ev0));
+    VRAD_CUDA_CHECK(cudaEventCreate(&e->ev1));
+    *out = e;
+    return VRAD_OK;
+}
+
+void vrad_env_destroy(vrad_env* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    extern void vrad_comm_destroy_internal(vrad_env*);
+    vrad_comm_destroy_internal(e);
+    e->d_nodes.release(); e->d_tri_index.release(); e->d_q0.release(); e->d_q1.release(); e->d_q2.release();
+    for (auto& s : e->scratch) s.release();
+    e->patches.origin_area.release(); e->patches.normal_dist.release(); e->patches.refl.release(); e->patches.cluster.release();
+    e->transfers.rowptr.release(); e->transfers.rowlen.release(); e->transfers.col.release(); e->transfers.w.release();
+    e->d_sky_dirs.release(); e->d_er[0].release(); e->d_er[1].release(); e->d_total.release(); e->d_partials.release();
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int vrad_env_set_stream(vrad_env* e, void* cuda_stream) {
+    if (!e) return VRAD_E_INVALID;
+    cudaStreamSynchronize(e->stream);
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return VRAD_OK;
+}
+
+int vrad_env_set_async(vrad_env* e, int async) {
+    if (!e) return VRAD_E_INVALID;
+    e->async = async != 0;
+    return VRAD_OK;
+}
+
+int vrad_env_last_timing(vrad_env* e, float* kernel_ms, int* n_launches) {
+    if (!e) return VRAD_E_INVALID;
+    if (e->last_ms < 0.0f) {
+        VRAD_CUDA_CHECK(cudaEventSynchronize(e->ev1));
+        VRAD_CUDA_CHECK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    }
+    if (kernel_ms) *kernel_ms = e->last_ms;
+    if (n_launches) *n_launches = e->last_launches;
+    return VRAD_OK;
+}
+
+void* vrad_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); set_error("vrad_host_alloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void vrad_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int vrad_env_add_triangles(vrad_env* e, int n, const int32_t* ids, const float* verts9, const uint8_t* flags) {
+    if (!e || n < 0 || (n > 0 && (!ids || !verts9))) { set_error("vrad_env_add_triangles: bad arguments"); return VRAD_E_INVALID; }
+    if (e->built) { set_error("vrad_env_add_triangles: acceleration structure already built"); return VRAD_E_STATE; }
+    for (int i = 0; i < n; i++) {
+        uint8_t f = flags ? flags[i] : 0;
+        if (f & 0x01) {   // FCACHETRI_TRANSPARENT needs ITransparentTriangleCallback (raytracer/types/coverageCount.go:11-13)
+            set_error("vrad_env_add_triangles: transparent triangles are not supported (callback cannot run in a kernel)");
+            return VRAD_E_UNSUPPORTED;
+        }
+    }
+    e->h_ids.insert(e->h_ids.end(), ids, ids + n);
+    e->h_verts.insert(e->h_verts.end(), verts9, verts9 + 9 * (size_t)n);
+    if (flags) e->h_flags.insert(e->h_flags.end(), flags, flags + n); else e->h_flags.insert(e->h_flags.end(), n, 0);
+    return VRAD_OK;
+}
+
+int vrad_env_build(vrad_env* e) {
+    if (!e) return VRAD_E_INVALID;
+    if (e->built) { set_error("vrad_env_build: already built"); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    auto t0 = std::chrono::steady_clock::now();
+    const int n = (int)e->h_ids.size();
+    build_kd_tree(e->h_verts.data(), n, e->tree);
+    e->h_tris.resize(n);
+    make_intersection_records(e->h_ids.data(), e->h_verts.data(), e->h_flags.data(), n, e->h_tris.data());
+    e->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (e->tree.max_depth >= kStackMax) { set_error("vrad_env_build: tree depth %d exceeds %d", e->tree.max_depth, kStackMax - 1); return VRAD_E_UNSUPPORTED; }
+    return upload_scene(e);
+}
+
+int vrad_env_upload_tree(vrad_env* e, int n_nodes, const int32_t* children, const float* split, int n_idx,
+                         const int32_t* tri_index, int n_tris, const vrad_tri48* tris, const float aabb[6]) {
+    if (!e || !children || !split || (n_idx > 0 && !tri_index) || (n_tris > 0 && !tris) || !aabb) { set_error("vrad_env_upload_tree: bad arguments"); return VRAD_E_INVALID; }
+    if (e->built) { set_error("vrad_env_upload_tree: already built"); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const char* why = nullptr;
+    int leaves = 0;
+    int depth = validate_kd_tree(n_nodes, children, split, n_idx, tri_index, n_tris, &leaves, &why);
+    if (depth < 0) { set_error("vrad_env_upload_tree: %s", why); return VRAD_E_INVALID; }
+    if (depth >= kStackMax) { set_error("vrad_env_upload_tree: tree depth %d exceeds %d", depth, kStackMax - 1); return VRAD_E_UNSUPPORTED; }
+    for (int i = 0; i < n_tris; i++)
+        if (tris[i].sel0 > 2 || tris[i].sel1 > 2) { set_error("vrad_env_upload_tree: triangle %d has bad coordinate selectors", i); return VRAD_E_INVALID; }
+    e->tree.children.assign(children, children + n_nodes);
+    e->tree.split.assign(split, split + n_nodes);
+    e->tree.tri_index.assign(tri_index, tri_index + n_idx);
+    for (int c = 0; c < 3; c++) { e->tree.bmin[c] = aabb[c]; e->tree.bmax[c] = aabb[3 + c]; }
+    e->tree.max_depth = depth; e->tree.n_leaves = leaves;
+    e->h_tris.assign(tris, tris + n_tris);
+    return upload_scene(e);
+}
+
+int vrad_env_stats(vrad_env* e, int* n_nodes, int* n_idx, int* n_tris, int* max_depth, int* n_leaves, float aabb[6], double* build_seconds) {
+    if (!e) return VRAD_E_INVALID;
+    if (!e->built) { set_error("vrad_env_stats: not built"); return VRAD_E_STATE; }
+    if (n_nodes) *n_nodes = (int)e->tree.children.size();
+    if (n_idx) *n_idx = (int)e->tree.tri_index.size();
+    if (n_tris) *n_tris = (int)e->h_tris.size();
+    if (max_depth) *max_depth = e->tree.max_depth;
+    if (n_leaves) *n_leaves = e->tree.n_leaves;
+    if (aabb) for (int c = 0; c < 3; c++) { aabb[c] = e->tree.bmin[c]; aabb[3 + c] = e->tree.bmax[c]; }
+    if (build_seconds) *build_seconds = e->build_seconds;
+    return VRAD_OK;
+}
+
+int vrad_env_download_tree(vrad_env* e, int32_t* children, float* split, int32_t* tri_index, vrad_tri48* tris) {
+    if (!e) return VRAD_E_INVALID;
+    if (!e->built) { set_error("vrad_env_download_tree: not built"); return VRAD_E_STATE; }
+    // read back from the device copy so the test sees what the kernels see
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const size_t nn = e->scene.n_nodes, ni = e->scene.n_idx, nt = e->scene.n_tris;
+    std::vector<int2> nodes(nn);
+    VRAD_CUDA_CHECK(cudaMemcpy(nodes.data(), e->d_nodes.p, nn * sizeof(int2), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nn; i++) {
+        if (children) children[i] = nodes[i].x;
+        if (split) memcpy(&split[i], &nodes[i].y, 4);
+    }
+    if (tri_index && ni) VRAD_CUDA_CHECK(cudaMemcpy(tri_index, e->d_tri_index.p, ni * 4, cudaMemcpyDeviceToHost));
+    if (tris && nt) {
+        std::vector<float4> q0(nt), q1(nt), q2(nt);
+        VRAD_CUDA_CHECK(cudaMemcpy(q0.data(), e->d_q0.p, nt * 16, cudaMemcpyDeviceToHost));
+        VRAD_CUDA_CHECK(cudaMemcpy(q1.data(), e->d_q1.p, nt * 16, cudaMemcpyDeviceToHost));
+        VRAD_CUDA_CHECK(cudaMemcpy(q2.data(), e->d_q2.p, nt * 16, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < nt; i++) {
+            vrad_tri48& t = tris[i];
+            t.nx = q0[i].x; t.ny = q0[i].y; t.nz = q0[i].z; t.d = q0[i].w;
+            t.e[0] = q1[i].x; t.e[1] = q1[i].y; t.e[2] = q1[i].z; t.e[3] = q1[i].w;
+            t.e[4] = q2[i].x; t.e[5] = q2[i].y;
+            int32_t sel;
+            memcpy(&t.id, &q2[i].z, 4); memcpy(&sel, &q2[i].w, 4);
+            t.sel0 = sel & 0xff; t.sel1 = (sel >> 8) & 0xff; t.flags = (sel >> 16) & 0xff; t.unused = 0;
+        }
+    }
+    return VRAD_OK;
+}
+
+int vrad_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, const float* oz, const float* dx,
+                    const float* dy, const float* dz, const float* tmin, const float* tmax, int32_t skip_id,
+                    int32_t* hit_tri, int32_t* hit_sid, float* hit_t) {
+    if (!e || n < 0 || (n > 0 && (!ox || !oy || !oz || !dx || !dy || !dz || !tmax))) { set_error("vrad_trace_rays: bad arguments"); return VRAD_E_INVALID; }
+    if (!e->built) { set_error("vrad_trace_rays: acceleration structure not built"); return VRAD_E_STATE; }
+    if (n == 0) return VRAD_OK;
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const size_t b = (size_t)n * 4;
+    const void* in[8]; bool hin[8]; bool any_host = false;
+    const float* src[8] = {ox, oy, oz, dx, dy, dz, tmin, tmax};
+    for (int k = 0; k < 8; k++) { int rc = stage_in(e, k, src[k], b, &in[k], &hin[k]); if (rc) return rc; any_host |= hin[k]; }
+    void* o_tri; void* o_sid; void* o_t; bool h0, h1, h2;
+    int rc;
+    if ((rc = stage_out(e, 8, hit_tri, b, &o_tri, &h0))) return rc;
+    if ((rc = stage_out(e, 9, hit_sid, b, &o_sid, &h1))) return rc;
+    if ((rc = stage_out(e, 10, hit_t, b, &o_t, &h2))) return rc;
+    any_host |= h0 | h1 | h2;
+    rc = launch_trace_rays(e, n, (const float*)in[0], (const float*)in[1], (const float*)in[2], (const float*)in[3],
+                           (const float*)in[4], (const float*)in[5], (const float*)in[6], (const float*)in[7], skip_id,
+                           (int32_t*)o_tri, (int32_t*)o_sid, (float*)o_t, nullptr);
+    if (rc) return rc;
+    if ((rc = finish_out(e, hit_tri, o_tri, b, h0))) return rc;
+    if ((rc = finish_out(e, hit_sid, o_sid, b, h1))) return rc;
+    if ((rc = finish_out(e, hit_t, o_t, b, h2))) return rc;
+    return sync_if_needed(e, any_host);
+}
+
+int vrad_trace4(vrad_env* e, const float origin_xyz4[12], const float dir_xyz4[12], const float tmin[4], const float tmax[4],
+                int32_t skip_id, int32_t hit_ids[4], float hit_dist[4], float normal_xyz4[12]) {
+    if (!e || !origin_xyz4 || !dir_xyz4 || !tmin || !tmax || !hit_ids || !hit_dist) { set_error("vrad_trace4: bad arguments"); return VRAD_E_INVALID; }
+    if (!e->built) { set_error("vrad_trace4: acceleration structure not built"); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    // one FourRays packet == a 4-ray batch: lanes are independent rays (FourVectors is x[4] y[4] z[4])
+    float h_in[32];
+    memcpy(h_in, origin_xyz4, 48); memcpy(h_in + 12, dir_xyz4, 48); memcpy(h_in + 24, tmin, 16); memcpy(h_in + 28, tmax, 16);
+    const void* d_in; bool hh;
+    int rc = stage_in(e, 0, h_in, sizeof(h_in), &d_in, &hh);
+    if (rc) return rc;
+    void* d_out;
+    if ((rc = stage_out(e, 1, hit_ids, 4 * (4 + 4 + 12), &d_out, &hh))) return rc;
+    const float* f = (const float*)d_in;
+    int32_t* o_tri = (int32_t*)d_out; float* o_t = (float*)d_out + 4; float* o_n = (float*)d_out + 8;
+    rc = launch_trace_rays(e, 4, f, f + 4, f + 8, f + 12, f + 16, f + 20, f + 24, f + 28, skip_id, o_tri, nullptr, o_t, o_n);
+    if (rc) return rc;
+    float h_out[20];
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    memcpy(hit_ids, h_out, 16); memcpy(hit_dist, h_out + 4, 16);
+    if (normal_xyz4) memcpy(normal_xyz4, h_out + 8, 48);
+    return VRAD_OK;
+}
+
+int vrad_test_lines(vrad_env* e, int64_t n, const float* start_xyz_soa, const float* stop_xyz_soa, int sky_mode, uint32_t* vis_bits) {
+    if (!e || n < 0 || (n > 0 && (!start_xyz_soa || !stop_xyz_soa || !vis_bits))) { set_error("vrad_test_lines: bad arguments"); return VRAD_E_INVALID; }
+    if (!e->built) { set_error("vrad_test_lines: acceleration structure not built"); return VRAD_E_STATE; }
+    if (n == 0) return VRAD_OK;
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const size_t b = (size_t)n * 12, wb = (size_t)((n + 31) / 32) * 4;
+    const void *d_a, *d_b; bool ha, hb, ho;
+    int rc;
+    if ((rc = stage_in(e, 0, start_xyz_soa, b, &d_a, &ha))) return rc;
+    if ((rc = stage_in(e, 1, stop_xyz_soa, b, &d_b, &hb))) return rc;
+    void* d_o;
+    if ((rc = stage_out(e, 2, vis_bits, wb, &d_o, &ho))) return rc;
+    if ((rc = launch_test_lines(e, n, (const float*)d_a, (const float*)d_b, sky_mode, (uint32_t*)d_o))) return rc;
+    if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
+    return sync_if_needed(e, ha | hb | ho);
+}
+
+} // extern "C"

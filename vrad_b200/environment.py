@@ -1,0 +1,280 @@
+"""Host-side mirror of the reference's ray-tracing call surface, on top of the C-ABI.
+
+`Environment` follows raytracer.Environment (raytracer/environment.go:28-39): AddTriangle (:41),
+AddTriangleWithMaterial (:45), AddQuad (:71), AddAxisAlignedRectangularSolid (:77),
+SetupAccelerationStructure (:119), Trace4Rays (:140), GetTriangle (:422).  `test_line_does_hit_sky`
+follows trace.TestLineDoesHitSky (raytracer/trace/testline.go:18-94).  The batched methods
+(`trace_rays`, `test_lines`, `build_transfers`, `direct_light`, `bounce`) are the throughput path.
+
+Arrays may be numpy (host) or torch CUDA tensors (device-resident, zero-copy).  Everything runs in
+libvradcuda.so on the GPU; nothing here computes on the CPU and there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import TRI48_DTYPE, VradConfig, VradError, check, ptr
+
+TRACE_ID_SKY = 0x01000000         # raytracer/constants.go:9-11
+TRACE_ID_OPAQUE = 0x02000000
+TRACE_ID_STATICPROP = 0x04000000
+KDNODE_STATE_LEAF = 3             # raytracer/constants.go:16
+
+
+def _is_torch(a):
+    return hasattr(a, "data_ptr")
+
+
+def _f32(a):
+    if a is None or _is_torch(a):
+        return a
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Environment:
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1):
+        self._l = _lib.load()
+        self._h = C.c_void_p()
+        cfg = VradConfig(device, rank, world, 0)
+        check(self._l.vrad_env_create(C.byref(cfg), C.byref(self._h)))
+        self.device, self.rank, self.world = device, rank, world
+        self.n_patches = 0
+        self._pending_ids, self._pending_verts, self._pending_flags = [], [], []
+
+    # ---- lifetime ----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._l.vrad_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        check(self._l.vrad_env_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_async(self, flag: bool):
+        check(self._l.vrad_env_set_async(self._h, C.c_int(int(flag))))
+
+    def last_timing(self):
+        ms, nl = C.c_float(), C.c_int()
+        check(self._l.vrad_env_last_timing(self._h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    # ---- geometry (reference names) ----------------------------------------------------
+    def add_triangle(self, tri_id, v1, v2, v3, colour=None):                       # environment.go:41-43
+        self.add_triangle_with_material(tri_id, v1, v2, v3, colour, 0, 0)
+
+    def add_triangle_with_material(self, tri_id, v1, v2, v3, colour=None, flags=0, material_index=0):  # :45-69
+        self._pending_ids.append(int(tri_id))
+        self._pending_verts.append([*v1, *v2, *v3])
+        self._pending_flags.append(int(flags) & 0xFF)
+
+    def add_quad(self, tri_id, v1, v2, v3, v4, colour=None):                       # :71-75
+        self.add_triangle(tri_id, v1, v2, v3, colour)
+        self.add_triangle(tri_id + 1, v1, v3, v4, colour)
+
+    def add_axis_aligned_rectangular_solid(self, tri_id, mn, mx, colour=None):     # :77-117
+        q = self.add_quad
+        q(tri_id, (mn[0], mx[1], mx[2]), (mx[0], mx[1], mx[2]), (mx[0], mn[1], mx[2]), (mn[0], mn[1], mx[2]))
+        q(tri_id, (mn[0], mx[1], mn[2]), (mx[0], mx[1], mn[2]), (mx[0], mn[1], mn[2]), (mn[0], mn[1], mn[2]))
+        q(tri_id, (mn[0], mx[1], mx[2]), (mn[0], mx[1], mn[2]), (mn[0], mn[1], mn[2]), (mn[0], mn[1], mx[2]))
+        q(tri_id, (mx[0], mx[1], mx[2]), (mx[0], mx[1], mn[2]), (mx[0], mn[1], mn[2]), (mx[0], mn[1], mx[2]))
+        q(tri_id, (mn[0], mx[1], mx[2]), (mx[0], mx[1], mx[2]), (mx[0], mx[1], mn[2]), (mn[0], mx[1], mn[2]))
+        q(tri_id, (mn[0], mn[1], mx[2]), (mx[0], mn[1], mx[2]), (mx[0], mn[1], mn[2]), (mn[0], mn[1], mn[2]))
+
+    def add_triangles(self, ids, verts9, flags=None):
+        """Bulk form of AddTriangleWithMaterial."""
+        self._flush_pending()
+        ids = np.ascontiguousarray(ids, np.int32)
+        verts9 = np.ascontiguousarray(verts9, np.float32).reshape(-1, 9)
+        assert verts9.shape[0] == ids.shape[0]
+        flags = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        check(self._l.vrad_env_add_triangles(self._h, C.c_int(ids.shape[0]), ptr(ids), ptr(verts9), ptr(flags)))
+
+    def _flush_pending(self):
+        if self._pending_ids:
+            ids = np.asarray(self._pending_ids, np.int32)
+            verts = np.asarray(self._pending_verts, np.float32).reshape(-1, 9)
+            flags = np.asarray(self._pending_flags, np.uint8)
+            self._pending_ids, self._pending_verts, self._pending_flags = [], [], []
+            check(self._l.vrad_env_add_triangles(self._h, C.c_int(ids.shape[0]), ptr(ids), ptr(verts), ptr(flags)))
+
+    def setup_acceleration_structure(self):                                         # :119-138
+        self._flush_pending()
+        check(self._l.vrad_env_build(self._h))
+        return self.stats()["build_seconds"]
+
+    def upload_tree(self, children, split, tri_index, tris, aabb):
+        children = np.ascontiguousarray(children, np.int32); split = np.ascontiguousarray(split, np.float32)
+        tri_index = np.ascontiguousarray(tri_index, np.int32); tris = np.ascontiguousarray(tris)
+        assert tris.dtype.itemsize == 48
+        aabb = np.ascontiguousarray(aabb, np.float32)
+        check(self._l.vrad_env_upload_tree(self._h, C.c_int(children.shape[0]), ptr(children), ptr(split),
+                                           C.c_int(tri_index.shape[0]), ptr(tri_index), C.c_int(tris.shape[0]), ptr(tris), ptr(aabb)))
+
+    def stats(self):
+        v = [C.c_int() for _ in range(5)]
+        aabb = np.empty(6, np.float32); secs = C.c_double()
+        check(self._l.vrad_env_stats(self._h, *[C.byref(x) for x in v], ptr(aabb), C.byref(secs)))
+        d = dict(zip(("n_nodes", "n_idx", "n_tris", "max_depth", "n_leaves"), [x.value for x in v]))
+        d["aabb"] = aabb; d["build_seconds"] = secs.value
+        return d
+
+    def download_tree(self):
+        s = self.stats()
+        children = np.empty(s["n_nodes"], np.int32); split = np.empty(s["n_nodes"], np.float32)
+        tri_index = np.empty(s["n_idx"], np.int32); tris = np.empty(s["n_tris"], TRI48_DTYPE)
+        check(self._l.vrad_env_download_tree(self._h, ptr(children), ptr(split), ptr(tri_index), ptr(tris)))
+        return {"children": children, "split": split, "tri_index": tri_index, "tris": tris, "aabb": s["aabb"]}
+
+    def get_triangle(self, index: int):                                             # :422-424
+        return self.download_tree()["tris"][index]
+
+    # ---- K1 ----------------------------------------------------------------------------
+    def trace4_rays(self, origin_xyz4, dir_xyz4, tmin, tmax, skip_id=-1):           # :140-145
+        """One FourRays packet -> (HitIds[4], HitDistance[4], SurfaceNormal[3,4])."""
+        o = np.ascontiguousarray(origin_xyz4, np.float32).reshape(12)
+        d = np.ascontiguousarray(dir_xyz4, np.float32).reshape(12)
+        tmin = np.ascontiguousarray(tmin, np.float32); tmax = np.ascontiguousarray(tmax, np.float32)
+        ids = np.empty(4, np.int32); dist = np.empty(4, np.float32); nrm = np.empty(12, np.float32)
+        check(self._l.vrad_trace4(self._h, ptr(o), ptr(d), ptr(tmin), ptr(tmax), C.c_int32(skip_id), ptr(ids), ptr(dist), ptr(nrm)))
+        return ids, dist, nrm.reshape(3, 4)
+
+    def trace_rays(self, o, d, tmax, tmin=None, skip_id=-1, out=None):
+        """Batched closest hit.  o, d: [3, n] SoA.  Returns (hit_tri, hit_sid, hit_t)."""
+        o = _f32(o); d = _f32(d); tmax = _f32(tmax); tmin = _f32(tmin)
+        n = int(o.shape[1])
+        if out is None:
+            if _is_torch(o):
+                import torch
+                out = (torch.empty(n, dtype=torch.int32, device=o.device), torch.empty(n, dtype=torch.int32, device=o.device),
+                       torch.empty(n, dtype=torch.float32, device=o.device))
+            else:
+                out = (np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32))
+        check(self._l.vrad_trace_rays(self._h, C.c_int64(n), ptr(o[0]), ptr(o[1]), ptr(o[2]), ptr(d[0]), ptr(d[1]), ptr(d[2]),
+                                      ptr(tmin), ptr(tmax), C.c_int32(skip_id), ptr(out[0]), ptr(out[1]), ptr(out[2])))
+        return out
+
+    def test_lines(self, start_soa, stop_soa, sky_mode=0, out=None):
+        """Batched TestLine: [3, n] SoA endpoints -> uint32 visibility words (bit = 1: visible)."""
+        s = _f32(start_soa); e = _f32(stop_soa)
+        n = int(s.shape[1])
+        nw = (n + 31) // 32
+        if out is None:
+            if _is_torch(s):
+                import torch
+                out = torch.empty(nw, dtype=torch.int32, device=s.device)
+            else:
+                out = np.empty(nw, np.uint32)
+        check(self._l.vrad_test_lines(self._h, C.c_int64(n), ptr(s), ptr(e), C.c_int(sky_mode), ptr(out)))
+        return out
+
+    # ---- patches / K2 / K3 / K4 --------------------------------------------------------
+    def patches_upload(self, origin, normal, plane_dist, area, refl, cluster=None, flags=None):
+        origin = _f32(origin); normal = _f32(normal); plane_dist = _f32(plane_dist); area = _f32(area); refl = _f32(refl)
+        n = int(origin.shape[0])
+        cluster = None if cluster is None else np.ascontiguousarray(cluster, np.int32)
+        flags = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        check(self._l.vrad_patches_upload(self._h, C.c_int(n), ptr(origin), ptr(normal), ptr(plane_dist), ptr(area), ptr(refl), ptr(cluster), ptr(flags)))
+        self.n_patches = n
+
+    def build_transfers(self, pvs=None):
+        nnz = C.c_int64(); nc = 0
+        if pvs is not None:
+            pvs = np.ascontiguousarray(pvs, np.uint8); nc = int(pvs.shape[0])
+        check(self._l.vrad_build_transfers(self._h, C.c_int(nc), ptr(pvs), C.byref(nnz)))
+        return nnz.value
+
+    def transfers_upload(self, row0, row1, rowptr, col, w):
+        rowptr = np.ascontiguousarray(rowptr, np.int64); col = np.ascontiguousarray(col, np.int32); w = np.ascontiguousarray(w, np.float32)
+        check(self._l.vrad_transfers_upload(self._h, C.c_int64(row0), C.c_int64(row1), ptr(rowptr), ptr(col), ptr(w)))
+
+    def transfers_info(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._l.vrad_transfers_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def transfers_download(self):
+        row0, row1, nnz = self.transfers_info()
+        rowptr = np.empty(row1 - row0 + 1, np.int64); col = np.empty(nnz, np.int32); w = np.empty(nnz, np.float32)
+        check(self._l.vrad_transfers_download(self._h, ptr(rowptr), ptr(col), ptr(w)))
+        return rowptr, col, w
+
+    def set_sky_dirs(self, dirs3):
+        d = np.ascontiguousarray(dirs3, np.float32).reshape(-1, 3)
+        check(self._l.vrad_set_sky_dirs(self._h, C.c_int(d.shape[0]), ptr(d)))
+
+    def direct_light(self, pos, normal, lights, out=None):
+        pos = _f32(pos); normal = _f32(normal)
+        lights = np.ascontiguousarray(lights)
+        assert lights.dtype.itemsize == 96
+        n = int(pos.shape[0])
+        if out is None:
+            if _is_torch(pos):
+                import torch
+                out = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
+            else:
+                out = np.empty((n, 3), np.float32)
+        check(self._l.vrad_direct_light(self._h, C.c_int64(n), ptr(pos), ptr(normal), C.c_int(lights.shape[0]), ptr(lights), ptr(out)))
+        return out
+
+    def bounce(self, emit0, n_bounces, early_out=False, out=None, want_added=True):
+        emit0 = _f32(emit0)
+        if out is None:
+            if _is_torch(emit0):
+                import torch
+                out = torch.empty_like(emit0)
+            else:
+                out = np.empty_like(emit0)
+        added = np.zeros(3, np.float32) if want_added else None
+        done = C.c_int()
+        check(self._l.vrad_bounce(self._h, ptr(emit0), C.c_int(n_bounces), C.c_int(int(early_out)), ptr(out), ptr(added), C.byref(done)))
+        return out, added, done.value
+
+    # ---- multi-GPU ---------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_lib.load().vrad_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes):
+        assert len(unique_id) == 128
+        check(self._l.vrad_comm_init(self._h, C.c_char_p(unique_id)))
+
+
+def environment_from_scene(scene, device=0, rank=0, world=1, with_patches=True) -> Environment:
+    env = Environment(device, rank, world)
+    env.add_triangles(scene.tri_ids, scene.tri_verts, scene.tri_flags)
+    env.setup_acceleration_structure()
+    if with_patches and scene.patch_origin is not None:
+        env.patches_upload(scene.patch_origin, scene.patch_normal, scene.patch_plane_dist, scene.patch_area,
+                           scene.patch_refl, scene.patch_cluster, scene.patch_flags)
+    return env
+
+
+def test_line_does_hit_sky(env: Environment, start_xyz4, stop_xyz4, can_recurse=True, static_prop_to_skip=-1, do_debug=False):
+    """trace.TestLineDoesHitSky for one FourVectors pair (raytracer/trace/testline.go:18-94).
+
+    Returns fractionVisible[4].  The 3D-skybox recursion (:57-89) needs BSP leaf/area data that the
+    synthetic path does not carry; it is a listed NEXT row, so `can_recurse`
+    is accepted and ignored.
+    """
+    s = np.ascontiguousarray(start_xyz4, np.float32).reshape(3, 4)
+    e = np.ascontiguousarray(stop_xyz4, np.float32).reshape(3, 4)
+    bits = env.test_lines(s, e, sky_mode=1)
+    word = int(bits[0])
+    return np.array([1.0 if (word >> i) & 1 else 0.0 for i in range(4)], np.float32)
+
+
+def row_partition(n_rows: int, world: int):
+    """Row ranges owned by each rank (equal blocks of ceil(n/world); the same rule the library uses)."""
+    rpr = (n_rows + world - 1) // world
+    return [(min(n_rows, r * rpr), min(n_rows, (r + 1) * rpr)) for r in range(world)]
