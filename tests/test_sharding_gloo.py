@@ -1,0 +1,82 @@
+"""World-size-2 gloo test (CPU): the row-sharded bounce recurrence with one all-gather per iteration
+reproduces the unsharded result.  Compute per rank is the oracle's row gather; the exchange and the
+partition rule are the product's host logic (vrad_b200/sharding.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vrad_b200 import sharding
+
+
+def _make_problem(N=301, seed=1):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(0, 40, N)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    col = rng.integers(0, N, rowptr[-1]).astype(np.int32)
+    w = (rng.random(rowptr[-1]) * 0.05).astype(np.float32)
+    refl = (rng.random((N, 3)) * 0.7).astype(np.float32)
+    emit0 = (rng.random((N, 3)) * 100).astype(np.float32)
+    return rowptr, col, w, refl, emit0
+
+
+def _worker(rank, world, port, n_bounces, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pyoracle
+    rowptr, col, w, refl, emit0 = _make_problem()
+    N = emit0.shape[0]
+    row0, row1 = sharding.row_partition(N, world)[rank]
+    rpr = sharding.rows_per_rank(N, world)
+    lrp, lcol, lw = sharding.slice_csr(rowptr, col, w, row0, row1)
+    emit = sharding.padded_gather_buffer(N, world)
+    emit[:N] = emit0
+    refl_pad = sharding.padded_gather_buffer(N, world); refl_pad[:N] = refl
+    total = np.zeros((row1 - row0, 3), np.float32)
+    for _ in range(n_bounces):
+        add = pyoracle.gather_rows(0, row1 - row0, lrp, lcol, lw, emit, refl_pad)     # local rows only
+        total += add
+        mine = torch.zeros((rpr, 3), dtype=torch.float32); mine[: row1 - row0] = torch.from_numpy(add)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)                                                # the one collective per bounce
+        emit = torch.cat(parts).numpy()
+    tot = torch.zeros((rpr, 3), dtype=torch.float32); tot[: row1 - row0] = torch.from_numpy(total)
+    parts = [torch.empty_like(tot) for _ in range(world)]
+    dist.all_gather(parts, tot)
+    if rank == 0:
+        q.put(torch.cat(parts).numpy()[:N])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_bounce_equals_unsharded(world):
+    from oracle import pyoracle
+    n_bounces = 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_bounces, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rowptr, col, w, refl, emit0 = _make_problem()
+    N = emit0.shape[0]
+    emit = emit0.copy(); total = np.zeros_like(emit0)
+    for _ in range(n_bounces):
+        add = pyoracle.gather_rows(0, N, rowptr, col, w, emit, refl)
+        total += add; emit = add
+    assert np.array_equal(got, total)          # same per-row summation order -> bit-identical
+
+
+def test_partition_helpers():
+    assert sharding.range_partition(10, 3) == [(0, 3), (3, 6), (6, 10)]
+    rp = np.array([0, 2, 2, 5, 9]); col = np.arange(9); w = np.arange(9, dtype=np.float32)
+    lrp, lcol, lw = sharding.slice_csr(rp, col, w, 1, 3)
+    assert list(lrp) == [0, 0, 3] and list(lcol) == [2, 3, 4]
+    assert sharding.padded_gather_buffer(10, 4).shape == (12, 3)

@@ -57,7 +57,13 @@ class Environment:
             pass
 
     def set_stream(self, cuda_stream: int | None):
-        check(self._l.vrad_env_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """None: the library's own stream.  An integer cudaStream_t handle otherwise; torch's default
+        stream has handle 0, which is passed as cudaStreamLegacy (0x1) so that it is not mistaken for None."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = int(cuda_stream) or 1
+        check(self._l.vrad_env_set_stream(self._h, C.c_void_p(handle)))
 
     def set_async(self, flag: bool):
         check(self._l.vrad_env_set_async(self._h, C.c_int(int(flag))))

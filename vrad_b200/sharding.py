@@ -1,0 +1,34 @@
+"""Host-side sharding rules for the multi-GPU path (one process per GPU).
+
+Rays / luxels are independent: each rank takes a contiguous range.  Patch rows of the transfer matrix
+are block-partitioned in equal blocks of ceil(N / world) rows -- the same rule libvradcuda applies in
+vrad_build_transfers / vrad_transfers_upload -- so that rank r's rows sit at slot r*rows_per_rank of the
+all-gathered radiance buffer and patch index == buffer index.  The only data-path collective is the
+per-bounce all-gather of the new radiance rows.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .environment import row_partition  # noqa: F401  (re-exported)
+
+
+def rows_per_rank(n_rows: int, world: int) -> int:
+    return (n_rows + world - 1) // world
+
+
+def range_partition(n: int, world: int):
+    """Contiguous ranges for independent work items (rays, luxels)."""
+    return [(r * n // world, (r + 1) * n // world) for r in range(world)]
+
+
+def slice_csr(rowptr, col, w, row0: int, row1: int):
+    """Rows [row0,row1) of a CSR matrix, rowptr rebased to 0 (what vrad_transfers_upload takes)."""
+    rowptr = np.asarray(rowptr, np.int64)
+    s, e = int(rowptr[row0]), int(rowptr[row1])
+    return rowptr[row0:row1 + 1] - s, np.asarray(col[s:e], np.int32), np.asarray(w[s:e], np.float32)
+
+
+def padded_gather_buffer(n_rows: int, world: int, width: int = 3, dtype=np.float32):
+    """The all-gather buffer: world * rows_per_rank rows (tail rows of the last rank are padding)."""
+    return np.zeros((rows_per_rank(n_rows, world) * world, width), dtype)
