@@ -1,0 +1,24 @@
+"""Short workload for `ncu --set full` captures: a few K1 and K4 launches at bench sizes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from vrad_b200 import scenes
+from vrad_b200.environment import environment_from_scene
+
+what = sys.argv[1] if len(sys.argv) > 1 else "k1"
+if what == "k1":
+    s = scenes.box_room(); env = environment_from_scene(s, with_patches=False)
+    a, b = scenes.shadow_segments(s, 1 << 24)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.empty((1 << 24) // 32, dtype=torch.int32, device="cuda")
+    for _ in range(4): env.test_lines(ta, tb, out=out)
+    r = scenes.random_rays(s, 1 << 22)
+    env.trace_rays(torch.from_numpy(r["o"]).cuda(), torch.from_numpy(r["d"]).cuda(), torch.from_numpy(r["tmax"]).cuda())
+else:
+    s = scenes.multi_room(); env = environment_from_scene(s)
+    nnz = env.build_transfers(s.pvs)
+    e0 = torch.full((s.n_patches, 3), 100.0, device="cuda")
+    env.bounce(e0, 6)
+    pos, nrm = torch.from_numpy(s.patch_origin).cuda(), torch.from_numpy(s.patch_normal).cuda()
+    env.direct_light(pos, nrm, s.lights)
+torch.cuda.synchronize()

@@ -70,12 +70,23 @@ __device__ __forceinline__ bool test_triangle(const DevScene& S, int ti, const R
     return true;
 }
 
-// Single-ray traversal.  ANY_HIT: return at the first hit with t < any_len (visibility only);
-// the occlusion bit equals that of the closest-hit traversal (same leaf sequence until the
-// first leaf that holds such a hit).  Closest hit: ties resolve to the lower triangle index.
+// Single-ray traversal, executed warp-synchronously.
+//
+// Every lane of the warp must call this together (callers pad their index space to whole warps
+// and pass valid=false for the padding lanes).  Each lane traverses its own ray with its own
+// stack -- results are exactly those of the scalar algorithm -- but the warp moves in phases:
+// all lanes descend to their next leaf, reconverge, test their leaf's triangles, reconverge,
+// pop.  Without the explicit phase barriers independent thread scheduling lets the lanes drift
+// apart for good and the warp executes ~2 threads per instruction (ncu, profiles/k1_r01_*).
+// The node step is branch-free (selects + one predicated push).
+//
+// ANY_HIT: stop at the first hit with t < any_len (visibility only); the occlusion bit equals that
+// of the closest-hit traversal (same leaf sequence until the first leaf that holds such a hit).
+// Closest hit: ties resolve to the lower triangle index.
 template <bool ANY_HIT>
-__device__ __forceinline__ void trace_ray(const DevScene& S, const Ray& r, float tmin, float tmax, int skip_id,
-                                          float any_len, int& hit_tri, float& hit_t) {
+__device__ __forceinline__ void trace_ray(const DevScene& S, const Ray& r, bool valid, float tmin, float tmax,
+                                          int skip_id, float any_len, int& hit_tri, float& hit_t) {
+    constexpr unsigned kFull = 0xffffffffu;
     hit_tri = -1; hit_t = kHitInit;
     const float ix = 1.0f / (r.dx == 0.0f ? kFltEpsilon : r.dx);
     const float iy = 1.0f / (r.dy == 0.0f ? kFltEpsilon : r.dy);
@@ -88,47 +99,56 @@ __device__ __forceinline__ void trace_ray(const DevScene& S, const Ray& r, float
         t0 = (S.bmin[2] - r.oz) * iz; t1 = (S.bmax[2] - r.oz) * iz;
         tmin = max_sel(tmin, min_sel(t0, t1)); tmax = min_sel(tmax, max_sel(t0, t1));
     }
-    if (!(tmin <= tmax)) return;
+    bool active = valid && (tmin <= tmax);
     const int negx = r.dx < 0.0f, negy = r.dy < 0.0f, negz = r.dz < 0.0f;
 
     int   st_node[kStackMax];
     float st_tmin[kStackMax], st_tmax[kStackMax];
     int sp = 0;
     int node = 0;
-    for (;;) {
-        int2 nd = __ldg(&S.nodes[node]);
-        while ((nd.x & 3) != 3) {
-            const int axis = nd.x & 3;
-            const int left = nd.x >> 2;
-            const int neg = axis == 0 ? negx : (axis == 1 ? negy : negz);
-            const float o = pick3(axis, r.ox, r.oy, r.oz);
-            const float inv = pick3(axis, ix, iy, iz);
-            const float t = (__int_as_float(nd.y) - o) * inv;
-            const int front = left + neg, back = left + (neg ^ 1);
-            if (!(t >= tmin)) {
-                node = back; tmin = max_sel(tmin, t);
-            } else if (!(t <= tmax)) {
-                node = front; tmax = min_sel(tmax, t);
-            } else {
-                st_node[sp] = back; st_tmin[sp] = max_sel(tmin, t); st_tmax[sp] = tmax; sp++;
-                node = front; tmax = min_sel(tmax, t);
-            }
+    while (__any_sync(kFull, active)) {
+        int2 nd = make_int2(3, 0);
+        // ---- phase 1: descend to the next leaf
+        if (active) {
             nd = __ldg(&S.nodes[node]);
-        }
-        const int start = nd.x >> 2;
-        const int cnt = (int)__int_as_float(nd.y);
-        for (int k = 0; k < cnt; k++) {
-            const int ti = __ldg(&S.tri_index[start + k]);
-            float t;
-            if (ANY_HIT) {
-                if (test_triangle(S, ti, r, skip_id, any_len, -1, t)) { hit_tri = ti; hit_t = t; return; }
-            } else {
-                if (test_triangle(S, ti, r, skip_id, hit_t, hit_tri, t)) { hit_tri = ti; hit_t = t; }
+            while ((nd.x & 3) != 3) {
+                const int axis = nd.x & 3;
+                const int left = nd.x >> 2;
+                const int neg = axis == 0 ? negx : (axis == 1 ? negy : negz);
+                const float o = pick3(axis, r.ox, r.oy, r.oz);
+                const float inv = pick3(axis, ix, iy, iz);
+                const float t = (__int_as_float(nd.y) - o) * inv;
+                const int front = left + neg, back = left + (neg ^ 1);
+                const bool back_only = !(t >= tmin);
+                const bool both = !back_only && (t <= tmax);
+                const float tmin_far = max_sel(tmin, t);
+                if (both) { st_node[sp] = back; st_tmin[sp] = tmin_far; st_tmax[sp] = tmax; sp++; }
+                node = back_only ? back : front;
+                tmax = back_only ? tmax : min_sel(tmax, t);
+                tmin = back_only ? tmin_far : tmin;
+                nd = __ldg(&S.nodes[node]);
             }
         }
-        if (!(tmax <= hit_t)) return;
-        if (sp == 0) return;
-        sp--; node = st_node[sp]; tmin = st_tmin[sp]; tmax = st_tmax[sp];
+        __syncwarp(kFull);
+        // ---- phase 2: the leaf's triangles, then terminate or pop
+        if (active) {
+            const int start = nd.x >> 2;
+            const int cnt = (int)__int_as_float(nd.y);
+            for (int k = 0; k < cnt; k++) {
+                const int ti = __ldg(&S.tri_index[start + k]);
+                float t;
+                if (ANY_HIT) {
+                    if (test_triangle(S, ti, r, skip_id, any_len, -1, t)) { hit_tri = ti; hit_t = t; active = false; break; }
+                } else {
+                    if (test_triangle(S, ti, r, skip_id, hit_t, hit_tri, t)) { hit_tri = ti; hit_t = t; }
+                }
+            }
+            if (active) {
+                if (!(tmax <= hit_t) || sp == 0) active = false;
+                else { sp--; node = st_node[sp]; tmin = st_tmin[sp]; tmax = st_tmax[sp]; }
+            }
+        }
+        __syncwarp(kFull);
     }
 }
 
@@ -146,17 +166,19 @@ __device__ __forceinline__ bool segment_to_ray(float ax, float ay, float az, flo
     return true;
 }
 
-// Occlusion rule of testline.go:42-51.  Returns 1 when the segment is visible.
-__device__ __forceinline__ int segment_visible(const DevScene& S, float ax, float ay, float az,
+// Occlusion rule of testline.go:42-51.  Returns 1 when the segment is visible.  Warp-synchronous:
+// all 32 lanes call it; lanes with valid=false return 1 without tracing.
+__device__ __forceinline__ int segment_visible(const DevScene& S, bool valid, float ax, float ay, float az,
                                                float bx, float by, float bz, int sky_mode) {
-    Ray r; float len;
-    if (!segment_to_ray(ax, ay, az, bx, by, bz, r, len)) return 1;
+    Ray r; float len = 0.0f;
+    r.ox = r.oy = r.oz = 0.0f; r.dx = r.dy = r.dz = 1.0f;
+    const bool trace = valid && segment_to_ray(ax, ay, az, bx, by, bz, r, len);
     int tri; float t;
-    if (!sky_mode) {
-        trace_ray<true>(S, r, 0.0f, len, -1, len, tri, t);
+    if (!sky_mode) {      // sky_mode is warp-uniform (kernel argument)
+        trace_ray<true>(S, r, trace, 0.0f, len, -1, len, tri, t);
         return tri == -1;
     }
-    trace_ray<false>(S, r, 0.0f, len, -1, 0.0f, tri, t);
+    trace_ray<false>(S, r, trace, 0.0f, len, -1, 0.0f, tri, t);
     if (tri != -1 && t < len) {
         const int id = __float_as_int(__ldg(&S.q2[tri]).z);
         if ((id & 0x01000000) == 0) return 0;

@@ -62,8 +62,7 @@ struct TransfersDev {
     int64_t nnz_padded = 0;         // device entries (rows padded to multiples of 4)
     DevBuf<int64_t> rowptr;         // padded offsets, row1-row0+1 entries, in units of entries
     DevBuf<int32_t> rowlen;         // logical row lengths
-    DevBuf<int32_t> col;
-    DevBuf<float>   w;
+    DevBuf<int2>    tr;             // {col, w bits} pairs == the reference's Transfer struct (transfer.go:3-6)
     bool ready = false;
 };
 

@@ -19,10 +19,18 @@ k1_trace_rays(DevScene S, int64_t n, const float* __restrict__ ox, const float* 
               int skip_id, int32_t* __restrict__ hit_tri, int32_t* __restrict__ hit_sid,
               float* __restrict__ hit_t, float* __restrict__ normal_soa) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Ray r{ox[i], oy[i], oz[i], dx[i], dy[i], dz[i]};
+    const int64_t n_pad = (n + 31) & ~(int64_t)31;          // whole warps enter the traversal together
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        const bool valid = i < n;
+        Ray r{0.f, 0.f, 0.f, 1.f, 1.f, 1.f};
+        float t0 = 0.0f, t1 = 0.0f;
+        if (valid) {
+            r = Ray{ox[i], oy[i], oz[i], dx[i], dy[i], dz[i]};
+            t0 = tmin ? tmin[i] : 0.0f; t1 = tmax[i];
+        }
         int tri; float t;
-        trace_ray<false>(S, r, tmin ? tmin[i] : 0.0f, tmax[i], skip_id, 0.0f, tri, t);
+        trace_ray<false>(S, r, valid, t0, t1, skip_id, 0.0f, tri, t);
+        if (!valid) continue;
         if (hit_tri) hit_tri[i] = tri;
         if (hit_t) hit_t[i] = t;
         if (hit_sid) hit_sid[i] = tri >= 0 ? __float_as_int(__ldg(&S.q2[tri]).z) : -1;
@@ -39,8 +47,10 @@ k1_test_lines(DevScene S, int64_t n, const float* __restrict__ a, const float* _
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_pad = (n + 31) & ~(int64_t)31;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        int vis = 0;
-        if (i < n) vis = segment_visible(S, a[i], a[n + i], a[2 * n + i], b[i], b[n + i], b[2 * n + i], sky_mode);
+        const bool valid = i < n;
+        float ax = 0.f, ay = 0.f, az = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+        if (valid) { ax = a[i]; ay = a[n + i]; az = a[2 * n + i]; bx = b[i]; by = b[n + i]; bz = b[2 * n + i]; }
+        const int vis = segment_visible(S, valid, ax, ay, az, bx, by, bz, sky_mode) && valid;
         const uint32_t m = __ballot_sync(0xffffffffu, vis);
         if ((threadIdx.x & 31) == 0) bits[i >> 5] = m;
     }

@@ -66,19 +66,22 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
         const int Kpad = (K + 31) & ~31;
         uint32_t* out = bits + bit_ptr[row];
         for (int p = threadIdx.x; p < Kpad; p += blockDim.x) {
-            int keep = 0;
+            bool need_ray = false;
+            float4 a = oi, an = ni, b = oi, bn = ni;
             if (p < K && !sky_i) {
                 const int j = __ldg(&cand_idx[c0 + p]);
                 if (j != i) {
                     const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
                     const float w = transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w);
                     if (w != 0.0f) {
-                        const bool lo = i < j;
-                        const float4 a = lo ? oi : oj, an = lo ? ni : nj, b = lo ? oj : oi, bn = lo ? nj : ni;
-                        keep = segment_visible(S, a.x + an.x, a.y + an.y, a.z + an.z, b.x + bn.x, b.y + bn.y, b.z + bn.z, 0);
+                        need_ray = true;
+                        if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
                     }
                 }
             }
+            // warp-synchronous shadow test: every lane calls, lanes without a ray idle inside
+            const int keep = segment_visible(S, need_ray, a.x + an.x, a.y + an.y, a.z + an.z,
+                                             b.x + bn.x, b.y + bn.y, b.z + bn.z, 0) && need_ray;
             const uint32_t m = __ballot_sync(0xffffffffu, keep);
             if ((threadIdx.x & 31) == 0) out[p >> 5] = m;
         }
@@ -104,7 +107,7 @@ __global__ void k2_fill(PatchView P, int nloc, int64_t row0, const int32_t* __re
                         const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx,
                         const int64_t* __restrict__ bit_ptr, const uint32_t* __restrict__ bits,
                         const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen,
-                        int32_t* __restrict__ col, float* __restrict__ w) {
+                        int2* __restrict__ tr) {
     const int lane = threadIdx.x & 31;
     const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (row >= nloc) return;
@@ -121,20 +124,19 @@ __global__ void k2_fill(PatchView P, int nloc, int64_t row0, const int32_t* __re
         if ((m >> lane) & 1u) {
             const int j = cand_idx[c0 + (wd - w0) * 32 + lane];
             const int k = pos + __popc(m & ((1u << lane) - 1u));
-            col[base + k] = j;
-            w[base + k] = transfer_weight(oi, ni, P.origin_area[j], P.normal_dist[j], P.refl[j].w);
+            tr[base + k] = make_int2(j, __float_as_int(transfer_weight(oi, ni, P.origin_area[j], P.normal_dist[j], P.refl[j].w)));
         }
         pos += __popc(m);
     }
     const int lenp = (len + 3) & ~3;
-    for (int k = len + lane; k < lenp; k += 32) { col[base + k] = 0; w[base + k] = 0.0f; }   // padding entries
+    for (int k = len + lane; k < lenp; k += 32) tr[base + k] = make_int2(0, 0);               // padding entries (w = 0)
     __syncwarp();
     float total = 0.0f;
-    if (lane == 0) for (int k = 0; k < len; k++) total = total + w[base + k];               // CSR-order fp32 sum
+    if (lane == 0) for (int k = 0; k < len; k++) total = total + __int_as_float(tr[base + k].y);   // CSR-order fp32 sum
     total = __shfl_sync(0xffffffffu, total, 0);
     if (total > 1.0f) {
         const float s = 1.0f / total;
-        for (int k = lane; k < len; k += 32) w[base + k] = w[base + k] * s;
+        for (int k = lane; k < len; k += 32) tr[base + k].y = __float_as_int(__int_as_float(tr[base + k].y) * s);
     }
 }
 
@@ -216,11 +218,11 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     int64_t np = 0;
     K2_CHECK(cudaMemcpyAsync(&np, T.rowptr.p + nloc, 8, cudaMemcpyDeviceToHost, e->stream));
     K2_CHECK(cudaStreamSynchronize(e->stream));
-    if (T.col.alloc(np + 4) || T.w.alloc(np + 4)) { cleanup(); set_error("out of device memory for %lld transfers", (long long)np); return VRAD_E_NOMEM; }
+    if (T.tr.alloc(np + 4)) { cleanup(); set_error("out of device memory for %lld transfers", (long long)np); return VRAD_E_NOMEM; }
     if (nloc > 0) {
         const int wblocks = (nloc * 32 + 255) / 256;
         k2_fill<<<wblocks, 256, 0, e->stream>>>(pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
-                                               T.rowptr.p, T.rowlen.p, T.col.p, T.w.p);
+                                               T.rowptr.p, T.rowlen.p, T.tr.p);
         launches++;
     }
     timing_end(e, launches);

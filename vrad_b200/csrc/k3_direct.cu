@@ -21,24 +21,35 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
     return ((ax * bx) + (ay * by)) + (az * bz);
 }
 
+// Pair index space is light-major and padded to whole warps: a warp holds 32 consecutive luxels of
+// ONE light, so its rays share an end point (coherent traversal) and the light type / sky mode is
+// warp-uniform.  The shadow test is warp-synchronous: every lane calls segment_visible once.
 __global__ void __launch_bounds__(128)
 k3_pair_scale(DevScene S, int64_t n_luxels, int n_lights, const float* __restrict__ pos3,
               const float* __restrict__ nrm3, const vrad_light* __restrict__ lights, float* __restrict__ scale_out) {
-    const int64_t total = n_luxels * n_lights;
+    const int64_t n_pad = (n_luxels + 31) & ~(int64_t)31;
+    const int64_t total = n_pad * n_lights;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const int64_t i = idx / n_lights;
-        const int L = (int)(idx - i * n_lights);
+        const int L = (int)(idx / n_pad);
+        const int64_t i = idx - (int64_t)L * n_pad;
         const vrad_light& dl = lights[L];
         const int type = dl.type;
-        const float px = pos3[3 * i], py = pos3[3 * i + 1], pz = pos3[3 * i + 2];
-        const float nx = nrm3[3 * i], ny = nrm3[3 * i + 1], nz = nrm3[3 * i + 2];
-        float scale = 0.0f;
-        if (type == 0 || type == 1 || type == 2) {
+        if (!(type == 0 || type == 1 || type == 2 || type == 3)) continue;      // warp-uniform (sky ambient: k3_sky_ambient)
+        const bool in_range = i < n_luxels;
+        float px = 0.f, py = 0.f, pz = 0.f, nx = 0.f, ny = 0.f, nz = 1.f;
+        if (in_range) {
+            px = pos3[3 * i]; py = pos3[3 * i + 1]; pz = pos3[3 * i + 2];
+            nx = nrm3[3 * i]; ny = nrm3[3 * i + 1]; nz = nrm3[3 * i + 2];
+        }
+        float value = 0.0f;                 // falloff * dot before visibility
+        float sx = px, sy = py, sz = pz;    // far end of the shadow segment
+        bool ok = in_range;
+        if (type != 3) {
             float dx = dl.origin[0] - px, dy = dl.origin[1] - py, dz = dl.origin[2] - pz;
             const float dist2 = dot3(dx, dy, dz, dx, dy, dz);
             float dist = sqrtf(dist2);
-            bool ok = dist > 0.0f;
+            ok = ok && dist > 0.0f;
             float dot = 0.0f, falloff = 0.0f;
             if (ok) {
                 const float r = 1.0f / dist;
@@ -77,19 +88,17 @@ k3_pair_scale(DevScene S, int64_t n_luxels, int n_lights, const float* __restric
                 const float s = 1.0f - ((t * t) * (3.0f - (2.0f * t)));
                 falloff = falloff * s;
             }
-            if (ok && segment_visible(S, px, py, pz, dl.origin[0], dl.origin[1], dl.origin[2], 0))
-                scale = falloff * dot;
-        } else if (type == 3) {
-            const float dot = -dot3(dl.normal[0], dl.normal[1], dl.normal[2], nx, ny, nz);
-            if (dot > 0.0f) {
-                const float sx = px - (dl.normal[0] * kMaxTraceLength), sy = py - (dl.normal[1] * kMaxTraceLength),
-                            sz = pz - (dl.normal[2] * kMaxTraceLength);
-                if (segment_visible(S, px, py, pz, sx, sy, sz, 1)) scale = dot;
-            }
+            value = falloff * dot;
+            sx = dl.origin[0]; sy = dl.origin[1]; sz = dl.origin[2];
         } else {
-            continue;   // sky ambient handled by k3_sky_ambient; unknown types contribute nothing
+            const float dot = -dot3(dl.normal[0], dl.normal[1], dl.normal[2], nx, ny, nz);
+            ok = ok && dot > 0.0f;
+            value = dot;
+            sx = px - (dl.normal[0] * kMaxTraceLength); sy = py - (dl.normal[1] * kMaxTraceLength);
+            sz = pz - (dl.normal[2] * kMaxTraceLength);
         }
-        scale_out[idx] = scale;
+        const int vis = segment_visible(S, ok, px, py, pz, sx, sy, sz, type == 3 ? 1 : 0);
+        if (in_range) scale_out[i * n_lights + L] = (ok && vis) ? value : 0.0f;
     }
 }
 
@@ -106,14 +115,14 @@ k3_sky_ambient(DevScene S, int64_t n_luxels, int n_lights, int light_index, int 
         float sum = 0.0f, possible = 0.0f;
         for (int base = 0; base < n_dirs; base += 32) {
             const int k = base + lane;
-            int vis = 0;
+            float ax = 0.f, ay = 0.f, az = 1.f;
+            bool want = false;
             if (k < n_dirs) {
-                const float ax = dirs3[3 * k], ay = dirs3[3 * k + 1], az = dirs3[3 * k + 2];
-                const float dot = dot3(ax, ay, az, nx, ny, nz);
-                if (dot > kEqualEpsilon)
-                    vis = segment_visible(S, px, py, pz, px + (ax * kMaxTraceLength), py + (ay * kMaxTraceLength),
-                                          pz + (az * kMaxTraceLength), 1);
+                ax = dirs3[3 * k]; ay = dirs3[3 * k + 1]; az = dirs3[3 * k + 2];
+                want = dot3(ax, ay, az, nx, ny, nz) > kEqualEpsilon;
             }
+            const int vis = segment_visible(S, want, px, py, pz, px + (ax * kMaxTraceLength), py + (ay * kMaxTraceLength),
+                                            pz + (az * kMaxTraceLength), 1) && want;
             const uint32_t m = __ballot_sync(0xffffffffu, vis);
             if (lane == 0) {
                 const int cnt = min(32, n_dirs - base);
@@ -190,7 +199,7 @@ int vrad_direct_light(vrad_env* e, int64_t n_luxels, const float* pos3, const fl
     int launches = 0;
     if (n_lights) {
         VRAD_CUDA_CHECK(cudaMemsetAsync(d_scale, 0, nscale * 4, e->stream));
-        const int64_t total = n_luxels * n_lights;
+        const int64_t total = ((n_luxels + 31) & ~(int64_t)31) * n_lights;
         int64_t blocks = (total + 127) / 128, cap = (int64_t)e->sm_count * 64;
         k3_pair_scale<<<(int)(blocks < cap ? blocks : cap), 128, 0, e->stream>>>(e->scene, n_luxels, n_lights, (const float*)d_pos,
                                                                                (const float*)d_nrm, (const vrad_light*)d_l, (float*)d_scale);

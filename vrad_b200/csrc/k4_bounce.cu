@@ -7,9 +7,9 @@
 //     add[i]   = sum_k w[i,k] * (emit[col[i,k]] * refl[col[i,k]])
 //     total[i] += add[i];  emit[i] = add[i];  added += emit[i]        (sky patches: emit = 0)
 //
-// HBM layout: transfers are a padded CSR -- every row starts on a 4-entry (16-byte) boundary so a
-// lane loads 4 columns + 4 weights as two 128-bit vectors; `er` = emit*refl is kept as one float4
-// per patch (16 B gathers that live in L2: 3.2 MB at 200k patches, 32 MB at 2M).  Algorithmic
+// HBM layout: transfers are a padded CSR of {col:int32, w:float32} pairs (8 B, the reference's
+// Transfer struct) -- every row starts on a 4-entry (32-byte sector) boundary; `er` = emit*refl is
+// kept as one float4 per patch (16 B gathers that live in L2: 3.2 MB at 200k patches, 32 MB at 2M).  Algorithmic
 // bytes per bounce: 8*nnz + 40*N; the kernel is HBM-bound on the 8*nnz stream.
 // One warp per row, warp-shuffle reduction, collect step fused into the epilogue.
 #include "env_internal.cuh"
@@ -35,38 +35,41 @@ __global__ void k4_init_er(int n_pad, int n, const float* __restrict__ emit0, co
     er[i] = v;
 }
 
+// One warp per row.  Entries are {col, w} pairs -- the reference's Transfer struct
+// (common/types/transfer.go:3-6) -- read as one coalesced 64-bit load per lane with lanes on
+// CONSECUTIVE entries, so the 32 er[] gathers of one instruction hit consecutive patches wherever the
+// row has a run of adjacent columns (avg run length ~16 on the synthetic maps): few L1 wavefronts
+// per gather instead of one per lane (ncu r01: the int4-per-lane mapping was L1TEX-bound at 86%).
 __global__ void __launch_bounds__(kGatherBlock)
-k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int4* __restrict__ col4,
-          const float4* __restrict__ w4, const float4* __restrict__ er, const float4* __restrict__ refl,
+k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
+          const float4* __restrict__ er, const float4* __restrict__ refl,
           float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * kGatherWarps + warp;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     float e0 = 0.f, e1 = 0.f, e2 = 0.f;
     if (row < nloc) {
-        const int64_t q0 = rowptr[row] >> 2, q1 = rowptr[row + 1] >> 2;     // in 4-entry groups
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-        int64_t q = q0 + lane;
-        for (; q + 32 < q1; q += 64) {                                      // two groups in flight per lane
-            const int4 ca = __ldcs(&col4[q]); const float4 wa = __ldcs(&w4[q]);
-            const int4 cb = __ldcs(&col4[q + 32]); const float4 wb = __ldcs(&w4[q + 32]);
-            const float4 a0 = __ldg(&er[ca.x]), a1 = __ldg(&er[ca.y]), a2 = __ldg(&er[ca.z]), a3 = __ldg(&er[ca.w]);
-            const float4 b0 = __ldg(&er[cb.x]), b1 = __ldg(&er[cb.y]), b2 = __ldg(&er[cb.z]), b3 = __ldg(&er[cb.w]);
-            s0 += wa.x * a0.x + wa.y * a1.x + wa.z * a2.x + wa.w * a3.x;
-            s1 += wa.x * a0.y + wa.y * a1.y + wa.z * a2.y + wa.w * a3.y;
-            s2 += wa.x * a0.z + wa.y * a1.z + wa.z * a2.z + wa.w * a3.z;
-            t0 += wb.x * b0.x + wb.y * b1.x + wb.z * b2.x + wb.w * b3.x;
-            t1 += wb.x * b0.y + wb.y * b1.y + wb.z * b2.y + wb.w * b3.y;
-            t2 += wb.x * b0.z + wb.y * b1.z + wb.z * b2.z + wb.w * b3.z;
+        const int64_t k0 = rowptr[row], k1 = rowptr[row + 1];      // padded to 4 entries; padding has w = 0
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        // software pipeline: the {col,w} stream of step i+1 is in flight while step i's er[] gathers
+        // resolve, so the two dependent memory latencies overlap.  Out-of-row slots read as {0, 0.0f}.
+        const int2 zero = make_int2(0, 0);
+        int64_t k = k0 + lane;
+        int2 a = k < k1 ? __ldcs(&tr[k]) : zero, b = k + 32 < k1 ? __ldcs(&tr[k + 32]) : zero;
+        int2 c = k + 64 < k1 ? __ldcs(&tr[k + 64]) : zero, d = k + 96 < k1 ? __ldcs(&tr[k + 96]) : zero;
+        for (; k < k1; k += 128) {
+            const int64_t kn = k + 128;
+            const int2 na = kn < k1 ? __ldcs(&tr[kn]) : zero, nb = kn + 32 < k1 ? __ldcs(&tr[kn + 32]) : zero;
+            const int2 nc = kn + 64 < k1 ? __ldcs(&tr[kn + 64]) : zero, nd2 = kn + 96 < k1 ? __ldcs(&tr[kn + 96]) : zero;
+            const float4 xa = __ldg(&er[a.x]), xb = __ldg(&er[b.x]), xc = __ldg(&er[c.x]), xd = __ldg(&er[d.x]);
+            const float wa = __int_as_float(a.y), wb = __int_as_float(b.y), wc = __int_as_float(c.y), wd = __int_as_float(d.y);
+            s0 += wa * xa.x; s1 += wa * xa.y; s2 += wa * xa.z;
+            t0 += wb * xb.x; t1 += wb * xb.y; t2 += wb * xb.z;
+            u0 += wc * xc.x; u1 += wc * xc.y; u2 += wc * xc.z;
+            v0 += wd * xd.x; v1 += wd * xd.y; v2 += wd * xd.z;
+            a = na; b = nb; c = nc; d = nd2;
         }
-        if (q < q1) {
-            const int4 ca = __ldcs(&col4[q]); const float4 wa = __ldcs(&w4[q]);
-            const float4 a0 = __ldg(&er[ca.x]), a1 = __ldg(&er[ca.y]), a2 = __ldg(&er[ca.z]), a3 = __ldg(&er[ca.w]);
-            s0 += wa.x * a0.x + wa.y * a1.x + wa.z * a2.x + wa.w * a3.x;
-            s1 += wa.x * a0.y + wa.y * a1.y + wa.z * a2.y + wa.w * a3.y;
-            s2 += wa.x * a0.z + wa.y * a1.z + wa.z * a2.z + wa.w * a3.z;
-        }
-        s0 += t0; s1 += t1; s2 += t2;
+        s0 += t0 + u0 + v0; s1 += t1 + u1 + v1; s2 += t2 + u2 + v2;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -176,22 +179,21 @@ int vrad_transfers_upload(vrad_env* e, int64_t row0, int64_t row1, const int64_t
         prow[i + 1] = prow[i] + ((len + 3) & ~(int64_t)3);
     }
     const int64_t np = prow[nloc];
-    std::vector<int32_t> pcol(np ? np : 4, 0);
-    std::vector<float> pw(np ? np : 4, 0.0f);
+    std::vector<int2> ptr(np ? np : 4, make_int2(0, 0));              // {col, w bits}; padding = {0, 0.0f}
     for (int64_t i = 0; i < nloc; i++) {
         const int64_t s = rowptr[i] - rowptr[0];
         for (int64_t k = 0; k < rlen[i]; k++) {
             int32_t c = col[s + k];
             if (c < 0 || c >= N) { set_error("vrad_transfers_upload: column %d out of range at row %lld", c, (long long)(row0 + i)); return VRAD_E_INVALID; }
-            pcol[prow[i] + k] = c; pw[prow[i] + k] = w[s + k];
+            int2 v; v.x = c; memcpy(&v.y, &w[s + k], 4);
+            ptr[prow[i] + k] = v;
         }
     }
     TransfersDev& T = e->transfers;
-    if (T.rowptr.alloc(nloc + 1) || T.rowlen.alloc(nloc ? nloc : 1) || T.col.alloc(pcol.size()) || T.w.alloc(pw.size())) { set_error("out of device memory for transfers"); return VRAD_E_NOMEM; }
+    if (T.rowptr.alloc(nloc + 1) || T.rowlen.alloc(nloc ? nloc : 1) || T.tr.alloc(ptr.size())) { set_error("out of device memory for transfers"); return VRAD_E_NOMEM; }
     VRAD_CUDA_CHECK(cudaMemcpyAsync(T.rowptr.p, prow.data(), (nloc + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaMemcpyAsync(T.rowlen.p, rlen.data(), rlen.size() * 4, cudaMemcpyHostToDevice, e->stream));
-    VRAD_CUDA_CHECK(cudaMemcpyAsync(T.col.p, pcol.data(), pcol.size() * 4, cudaMemcpyHostToDevice, e->stream));
-    VRAD_CUDA_CHECK(cudaMemcpyAsync(T.w.p, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(T.tr.p, ptr.data(), ptr.size() * 8, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.ready = true;
     return VRAD_OK;
@@ -216,18 +218,14 @@ int vrad_transfers_download(vrad_env* e, int64_t* rowptr, int32_t* col, float* w
     std::vector<int32_t> rlen(nloc ? nloc : 1);
     VRAD_CUDA_CHECK(cudaMemcpy(prow.data(), T.rowptr.p, (nloc + 1) * 8, cudaMemcpyDeviceToHost));
     if (nloc) VRAD_CUDA_CHECK(cudaMemcpy(rlen.data(), T.rowlen.p, nloc * 4, cudaMemcpyDeviceToHost));
-    std::vector<int32_t> pcol(T.nnz_padded ? T.nnz_padded : 1);
-    std::vector<float> pw(T.nnz_padded ? T.nnz_padded : 1);
-    if (T.nnz_padded) {
-        VRAD_CUDA_CHECK(cudaMemcpy(pcol.data(), T.col.p, T.nnz_padded * 4, cudaMemcpyDeviceToHost));
-        VRAD_CUDA_CHECK(cudaMemcpy(pw.data(), T.w.p, T.nnz_padded * 4, cudaMemcpyDeviceToHost));
-    }
+    std::vector<int2> ptr(T.nnz_padded ? T.nnz_padded : 1);
+    if (T.nnz_padded) VRAD_CUDA_CHECK(cudaMemcpy(ptr.data(), T.tr.p, T.nnz_padded * 8, cudaMemcpyDeviceToHost));
     int64_t pos = 0;
     for (int64_t i = 0; i < nloc; i++) {
         if (rowptr) rowptr[i] = pos;
         for (int32_t k = 0; k < rlen[i]; k++) {
-            if (col) col[pos + k] = pcol[prow[i] + k];
-            if (w) w[pos + k] = pw[prow[i] + k];
+            if (col) col[pos + k] = ptr[prow[i] + k].x;
+            if (w) memcpy(&w[pos + k], &ptr[prow[i] + k].y, 4);
         }
         pos += rlen[i];
     }
@@ -268,7 +266,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     int cur = 0, done = 0;
     float h_added[3] = {0.f, 0.f, 0.f};
     for (int b = 0; b < n_bounces; b++) {
-        k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, (const int4*)T.col.p, (const float4*)T.w.p,
+        k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p,
                                                          e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
         launches++;
         if (world > 1 && (rc = comm_allgather_f4(e, e->d_er[cur ^ 1].p, (size_t)rpr))) return rc;

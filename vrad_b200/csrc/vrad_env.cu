@@ -149,7 +149,7 @@ void vrad_env_destroy(vrad_env* e) {
     e->d_nodes.release(); e->d_tri_index.release(); e->d_q0.release(); e->d_q1.release(); e->d_q2.release();
     for (auto& s : e->scratch) s.release();
     e->patches.origin_area.release(); e->patches.normal_dist.release(); e->patches.refl.release(); e->patches.cluster.release();
-    e->transfers.rowptr.release(); e->transfers.rowlen.release(); e->transfers.col.release(); e->transfers.w.release();
+    e->transfers.rowptr.release(); e->transfers.rowlen.release(); e->transfers.tr.release();
     e->d_sky_dirs.release(); e->d_er[0].release(); e->d_er[1].release(); e->d_total.release(); e->d_partials.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
