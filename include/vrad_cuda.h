@@ -117,8 +117,7 @@ int  vrad_trace4(vrad_env*, const float origin_xyz4[12], const float dir_xyz4[12
                  const float tmax[4], int32_t skip_id, int32_t hit_ids[4], float hit_dist[4], float normal_xyz4[12]);
 /* batched Trace4Rays: n rays SoA.  tmin may be NULL (0).  hit_tri = index into the triangle list or -1,
  * hit_sid = NTriangleID of that triangle (or -1), hit_t = distance (1e23 on a miss).  Outputs may be NULL.
- * With world > 1 the handle traces rays [rank*n/world, (rank+1)*n/world) only when n is the global count
- * and shard != 0; otherwise all n rays. */
+ * A handle traces exactly the n rays it is given; with several GPUs the caller gives each rank its own range. */
 int  vrad_trace_rays(vrad_env*, int64_t n, const float* ox, const float* oy, const float* oz,
                      const float* dx, const float* dy, const float* dz, const float* tmin, const float* tmax,
                      int32_t skip_id, int32_t* hit_tri, int32_t* hit_sid, float* hit_t);

@@ -1,0 +1,116 @@
+// vrad_environment.hpp -- host-side C++ mirror of the reference's ray-tracing call surface on top of
+// the C-ABI (include/vrad_cuda.h).  The reference is compiled code (Go) whose toolchain is absent from
+// the build image, so the host side above the C-ABI is written in C++ with the reference's own names,
+// argument meaning and error behaviour (fatal on failure, like log.Fatalf / log.Panicln):
+//
+//   raytracer::Environment            raytracer/environment.go:28-39
+//     AddTriangle                     :41-43
+//     AddTriangleWithMaterial         :45-69
+//     AddQuad                         :71-75
+//     AddAxisAlignedRectangularSolid  :77-117
+//     SetupAccelerationStructure      :119-138
+//     Trace4Rays                      :140-145   (FourRays raytracer/types/fourrays.go:8-11,
+//                                                 RayTracingResult raytracer/types/result.go:8-12)
+//     GetTriangle                     :422-424
+//   trace::TestLineDoesHitSky         raytracer/trace/testline.go:18-94
+#pragma once
+#include <array>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "vrad_cuda.h"
+
+namespace raytracer {
+
+constexpr int32_t TRACE_ID_SKY = VRAD_TRACE_ID_SKY;                  // raytracer/constants.go:9-11
+constexpr int32_t TRACE_ID_OPAQUE = VRAD_TRACE_ID_OPAQUE;
+constexpr int32_t TRACE_ID_STATICPROP = VRAD_TRACE_ID_STATICPROP;
+
+using Vec3 = std::array<float, 3>;
+using Flt4x = std::array<float, 4>;                                   // vmath/ssemath/simd/simd.go:9
+struct FourVectors { Flt4x X, Y, Z; };                                // vmath/ssemath/fourvectors.go:10-12
+struct FourRays { FourVectors Origin, Direction; };
+struct RayTracingResult { FourVectors SurfaceNormal; std::array<int32_t, 4> HitIds; Flt4x HitDistance; };
+
+inline void fatal_on(int rc, const char* what) {
+    if (rc != 0) { std::fprintf(stderr, "%s: vrad status %d: %s\n", what, rc, vrad_last_error()); std::abort(); }
+}
+
+class Environment {
+public:
+    explicit Environment(int device = 0) {
+        vrad_config cfg{device, 0, 1, 0};
+        fatal_on(vrad_env_create(&cfg, &h_), "vrad_env_create");
+    }
+    ~Environment() { vrad_env_destroy(h_); }
+    Environment(const Environment&) = delete;
+    Environment& operator=(const Environment&) = delete;
+
+    void AddTriangle(int32_t id, const Vec3& v1, const Vec3& v2, const Vec3& v3, const Vec3& colour = {1, 0, 0}) {
+        AddTriangleWithMaterial(id, v1, v2, v3, colour, 0, 0);
+    }
+    void AddTriangleWithMaterial(int32_t id, const Vec3& v1, const Vec3& v2, const Vec3& v3, const Vec3&, uint16_t flags, int) {
+        ids_.push_back(id);
+        for (const Vec3* v : {&v1, &v2, &v3}) for (float c : *v) verts_.push_back(c);
+        flags_.push_back(static_cast<uint8_t>(flags));
+    }
+    void AddQuad(int32_t id, const Vec3& v1, const Vec3& v2, const Vec3& v3, const Vec3& v4, const Vec3& colour = {1, 0, 0}) {
+        AddTriangle(id, v1, v2, v3, colour);
+        AddTriangle(id + 1, v1, v3, v4, colour);
+    }
+    void AddAxisAlignedRectangularSolid(int32_t id, const Vec3& mn, const Vec3& mx, const Vec3& colour = {1, 0, 0}) {
+        AddQuad(id, {mn[0], mx[1], mx[2]}, {mx[0], mx[1], mx[2]}, {mx[0], mn[1], mx[2]}, {mn[0], mn[1], mx[2]}, colour);
+        AddQuad(id, {mn[0], mx[1], mn[2]}, {mx[0], mx[1], mn[2]}, {mx[0], mn[1], mn[2]}, {mn[0], mn[1], mn[2]}, colour);
+        AddQuad(id, {mn[0], mx[1], mx[2]}, {mn[0], mx[1], mn[2]}, {mn[0], mn[1], mn[2]}, {mn[0], mn[1], mx[2]}, colour);
+        AddQuad(id, {mx[0], mx[1], mx[2]}, {mx[0], mx[1], mn[2]}, {mx[0], mn[1], mn[2]}, {mx[0], mn[1], mx[2]}, colour);
+        AddQuad(id, {mn[0], mx[1], mx[2]}, {mx[0], mx[1], mx[2]}, {mx[0], mx[1], mn[2]}, {mn[0], mx[1], mn[2]}, colour);
+        AddQuad(id, {mn[0], mn[1], mx[2]}, {mx[0], mn[1], mx[2]}, {mx[0], mn[1], mn[2]}, {mn[0], mn[1], mn[2]}, colour);
+    }
+    void SetupAccelerationStructure() {
+        fatal_on(vrad_env_add_triangles(h_, static_cast<int>(ids_.size()), ids_.data(), verts_.data(), flags_.data()), "vrad_env_add_triangles");
+        fatal_on(vrad_env_build(h_), "vrad_env_build");
+    }
+    void Trace4Rays(const FourRays& rays, const Flt4x& TMin, const Flt4x& TMax, RayTracingResult* resultOut, int skipId = -1) const {
+        float o[12], d[12], n[12];
+        for (int l = 0; l < 4; l++) {
+            o[l] = rays.Origin.X[l]; o[4 + l] = rays.Origin.Y[l]; o[8 + l] = rays.Origin.Z[l];
+            d[l] = rays.Direction.X[l]; d[4 + l] = rays.Direction.Y[l]; d[8 + l] = rays.Direction.Z[l];
+        }
+        fatal_on(vrad_trace4(h_, o, d, TMin.data(), TMax.data(), skipId, resultOut->HitIds.data(), resultOut->HitDistance.data(), n), "vrad_trace4");
+        for (int l = 0; l < 4; l++) { resultOut->SurfaceNormal.X[l] = n[l]; resultOut->SurfaceNormal.Y[l] = n[4 + l]; resultOut->SurfaceNormal.Z[l] = n[8 + l]; }
+    }
+    vrad_tri48 GetTriangle(int index) const {
+        int nn, ni, nt;
+        fatal_on(vrad_env_stats(h_, &nn, &ni, &nt, nullptr, nullptr, nullptr, nullptr), "vrad_env_stats");
+        std::vector<vrad_tri48> tris(nt);
+        fatal_on(vrad_env_download_tree(h_, nullptr, nullptr, nullptr, tris.data()), "vrad_env_download_tree");
+        return tris.at(index);
+    }
+    vrad_env* handle() const { return h_; }
+
+private:
+    vrad_env* h_ = nullptr;
+    std::vector<int32_t> ids_;
+    std::vector<float> verts_;
+    std::vector<uint8_t> flags_;
+};
+
+} // namespace raytracer
+
+namespace trace {
+
+// TestLineDoesHitSky (raytracer/trace/testline.go:18-94) for one FourVectors pair; the 3D-skybox
+// recursion (:57-89) is a NEXT row: canRecurse is accepted and ignored.
+inline void TestLineDoesHitSky(const raytracer::Environment& env, const raytracer::FourVectors& start, const raytracer::FourVectors& stop,
+                               raytracer::Flt4x* fractionVisible, bool /*canRecurse*/ = true, int /*staticPropToSkip*/ = -1, bool /*doDebug*/ = false) {
+    float a[12], b[12];
+    for (int l = 0; l < 4; l++) {
+        a[l] = start.X[l]; a[4 + l] = start.Y[l]; a[8 + l] = start.Z[l];
+        b[l] = stop.X[l]; b[4 + l] = stop.Y[l]; b[8 + l] = stop.Z[l];
+    }
+    uint32_t bits = 0;
+    raytracer::fatal_on(vrad_test_lines(env.handle(), 4, a, b, 1, &bits), "vrad_test_lines");
+    for (int l = 0; l < 4; l++) (*fractionVisible)[l] = ((bits >> l) & 1u) ? 1.0f : 0.0f;
+}
+
+} // namespace trace

@@ -1,0 +1,73 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): one process per GPU, NCCL all-gather per
+bounce inside libvradcuda, rows sharded by rank -- result must match the single-GPU run and the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["VRAD_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from vrad_b200 import scenes
+from vrad_b200.environment import Environment, environment_from_scene
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+scene = scenes.multi_room(nx=3, ny=2)
+env = environment_from_scene(scene, device=lr, rank=rank, world=world)
+uid = [Environment.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+env.comm_init(uid[0])
+nnz = env.build_transfers(scene.pvs)
+row0, row1, _ = env.transfers_info()
+N = scene.n_patches
+emit0 = scenes.SplitMix64(7).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
+total, added, done = env.bounce(emit0, 6)
+total_eo, added_eo, done_eo = env.bounce(emit0, 100, early_out=True)
+rp, col, w = env.transfers_download()
+np.savez(os.path.join(os.environ["VRAD_OUT"], f"rank{rank}.npz"), total=total, added=added, done=done, total_eo=total_eo,
+         done_eo=done_eo, row0=row0, row1=row1, nnz=nnz, rp=rp, col=col, w=w)
+env.close()
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_bounce_matches_single_and_oracle(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import pyoracle
+    from vrad_b200 import scenes
+    from vrad_b200.environment import row_partition
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, VRAD_ROOT=ROOT, VRAD_OUT=str(tmp_path))
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                    "--master-port", "29611", str(script)], check=True, env=env, timeout=600)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    scene = scenes.multi_room(nx=3, ny=2)
+    N = scene.n_patches
+    parts = row_partition(N, 2)
+    assert (int(r0["row0"]), int(r0["row1"])) == parts[0] and (int(r1["row0"]), int(r1["row1"])) == parts[1]
+    o = pyoracle.env_from_scene(scene)
+    nnz = o.build_transfers(scene.pvs, threads=8)
+    assert int(r0["nnz"]) + int(r1["nnz"]) == nnz
+    rp, col, w = o.transfers()
+    for r, (a, b) in zip((r0, r1), parts):           # each rank holds exactly its rows, bit-exact
+        assert np.array_equal(r["rp"], rp[a:b + 1] - rp[a])
+        assert np.array_equal(r["col"], col[rp[a]:rp[b]]) and np.array_equal(r["w"], w[rp[a]:rp[b]])
+    emit0 = scenes.SplitMix64(7).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
+    to, ao, do = o.bounce(emit0, 6, threads=8)
+    for r in (r0, r1):                                # every rank returns the full gathered result
+        assert np.abs(r["total"] - to).max() <= 1e-4 * np.abs(to).max()
+        assert np.allclose(r["added"], ao, rtol=1e-4) and int(r["done"]) == 6
+    assert np.array_equal(r0["total"], r1["total"])
+    te, ae, de = o.bounce(emit0, 100, early_out=True, threads=8)
+    assert int(r0["done_eo"]) == int(r1["done_eo"]) == de
+    assert np.abs(r0["total_eo"] - te).max() <= 1e-4 * np.abs(te).max()
