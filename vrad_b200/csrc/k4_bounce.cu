@@ -14,6 +14,8 @@
 // One warp per row, warp-shuffle reduction, collect step fused into the epilogue.
 #include "env_internal.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 
 namespace vrad {
 
@@ -40,7 +42,14 @@ __global__ void k4_init_er(int n_pad, int n, const float* __restrict__ emit0, co
 // CONSECUTIVE entries, so the 32 er[] gathers of one instruction hit consecutive patches wherever the
 // row has a run of adjacent columns (avg run length ~16 on the synthetic maps): few L1 wavefronts
 // per gather instead of one per lane (ncu r01: the int4-per-lane mapping was L1TEX-bound at 86%).
-__global__ void __launch_bounds__(kGatherBlock)
+// kGatherUnroll entries per lane are in flight and the {col,w} loads of the NEXT step are issued
+// before the current step's gathers (software pipeline), so the two dependent memory latencies
+// overlap.  The kernel is latency-bound: what matters is bytes in flight per SM = resident warps x
+// entries in flight, so the register budget is capped to keep 5 blocks (40 warps) per SM -- the
+// same loop at 60 registers (4 blocks) ran at 4.1 TB/s, at 48 registers 6.4 TB/s (tools/exp/k4_exp.cu).
+constexpr int kGatherUnroll = 8;
+
+__global__ void __launch_bounds__(kGatherBlock, 5)
 k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
           const float4* __restrict__ er, const float4* __restrict__ refl,
           float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
@@ -50,26 +59,26 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
     float e0 = 0.f, e1 = 0.f, e2 = 0.f;
     if (row < nloc) {
         const int64_t k0 = rowptr[row], k1 = rowptr[row + 1];      // padded to 4 entries; padding has w = 0
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f;
-        // software pipeline: the {col,w} stream of step i+1 is in flight while step i's er[] gathers
-        // resolve, so the two dependent memory latencies overlap.  Out-of-row slots read as {0, 0.0f}.
-        const int2 zero = make_int2(0, 0);
+        const int2 zero = make_int2(0, 0);                          // out-of-row slots: col 0, weight 0
+        int2 cur[kGatherUnroll], nxt[kGatherUnroll];
         int64_t k = k0 + lane;
-        int2 a = k < k1 ? __ldcs(&tr[k]) : zero, b = k + 32 < k1 ? __ldcs(&tr[k + 32]) : zero;
-        int2 c = k + 64 < k1 ? __ldcs(&tr[k + 64]) : zero, d = k + 96 < k1 ? __ldcs(&tr[k + 96]) : zero;
-        for (; k < k1; k += 128) {
-            const int64_t kn = k + 128;
-            const int2 na = kn < k1 ? __ldcs(&tr[kn]) : zero, nb = kn + 32 < k1 ? __ldcs(&tr[kn + 32]) : zero;
-            const int2 nc = kn + 64 < k1 ? __ldcs(&tr[kn + 64]) : zero, nd2 = kn + 96 < k1 ? __ldcs(&tr[kn + 96]) : zero;
-            const float4 xa = __ldg(&er[a.x]), xb = __ldg(&er[b.x]), xc = __ldg(&er[c.x]), xd = __ldg(&er[d.x]);
-            const float wa = __int_as_float(a.y), wb = __int_as_float(b.y), wc = __int_as_float(c.y), wd = __int_as_float(d.y);
-            s0 += wa * xa.x; s1 += wa * xa.y; s2 += wa * xa.z;
-            t0 += wb * xb.x; t1 += wb * xb.y; t2 += wb * xb.z;
-            u0 += wc * xc.x; u1 += wc * xc.y; u2 += wc * xc.z;
-            v0 += wd * xd.x; v1 += wd * xd.y; v2 += wd * xd.z;
-            a = na; b = nb; c = nc; d = nd2;
+#pragma unroll
+        for (int j = 0; j < kGatherUnroll; j++) cur[j] = k + 32 * j < k1 ? __ldcs(&tr[k + 32 * j]) : zero;
+        for (; k < k1; k += 32 * kGatherUnroll) {
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++)
+                nxt[j] = k + 32 * (kGatherUnroll + j) < k1 ? __ldcs(&tr[k + 32 * (kGatherUnroll + j)]) : zero;
+            float4 x[kGatherUnroll];
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) {
+                const float w = __int_as_float(cur[j].y);
+                s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
+            }
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
         }
-        s0 += t0 + u0 + v0; s1 += t1 + u1 + v1; s2 += t2 + u2 + v2;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -263,6 +272,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     VRAD_CUDA_CHECK(cudaMemsetAsync(d_added, 0, 12, e->stream));
     k4_init_er<<<(int)((n_pad + 255) / 256), 256, 0, e->stream>>>((int)n_pad, (int)N, (const float*)d_emit0, e->patches.refl.p, e->d_er[0].p);
     launches++;
+
     int cur = 0, done = 0;
     float h_added[3] = {0.f, 0.f, 0.f};
     for (int b = 0; b < n_bounces; b++) {
