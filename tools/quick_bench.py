@@ -31,6 +31,7 @@ best, med = ev_time(lambda: env.trace_rays(to, td, tm, out=outs))
 print(f"trace_rays random {which}: {(1<<22)/best/1e6:.1f} Mrays/s best ({best:.3f} ms)")
 # K2 + K4
 env.set_async(False)
+env.build_transfers(scene.pvs)
 t = time.time(); nnz = env.build_transfers(scene.pvs); dt = time.time() - t
 print(f"build_transfers: nnz={nnz} N={scene.n_patches} wall {dt:.3f}s kernel_ms={env.last_timing()}")
 N = scene.n_patches

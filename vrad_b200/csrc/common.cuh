@@ -44,112 +44,137 @@ struct Ray {
     float ox, oy, oz, dx, dy, dz;
 };
 
-// One triangle test.  Returns true when (t, ti) improves on (best_t, best_tri).
-__device__ __forceinline__ bool test_triangle(const DevScene& S, int ti, const Ray& r, int skip_id,
-                                              float best_t, int best_tri, float& t_out) {
-    const float4 a = __ldg(&S.q0[ti]);
-    const float ddotn = ((r.dx * a.x) + (r.dy * a.y)) + (r.dz * a.z);
-    if (!(ddotn > kDdotNEps || ddotn < -kDdotNEps)) return false;
-    const float odotn = ((r.ox * a.x) + (r.oy * a.y)) + (r.oz * a.z);
-    const float t = (a.w - odotn) / ddotn;
-    if (!(t > 0.0f)) return false;
-    if (!(t < best_t || (t == best_t && ti < best_tri))) return false;
-    const float4 c = __ldg(&S.q2[ti]);
-    if (__float_as_int(c.z) == skip_id) return false;
-    const int sel = __float_as_int(c.w);
-    const int s0 = sel & 3, s1 = (sel >> 8) & 3;
-    const float c0 = pick3(s0, r.ox, r.oy, r.oz) + (t * pick3(s0, r.dx, r.dy, r.dz));
-    const float c1 = pick3(s1, r.ox, r.oy, r.oz) + (t * pick3(s1, r.dx, r.dy, r.dz));
-    const float4 b = __ldg(&S.q1[ti]);
-    const float b0 = ((b.x * c0) + (b.y * c1)) + b.z;
-    if (!(b0 >= 0.0f)) return false;
-    const float b1 = ((b.w * c0) + (c.x * c1)) + c.y;
-    if (!(b1 >= 0.0f)) return false;
-    if (!((b0 + b1) <= 1.0f)) return false;
-    t_out = t;
-    return true;
-}
+// Per-lane traversal state.  All member functions are WARP-SYNCHRONOUS: every lane of the warp calls
+// them together (idle lanes carry active=false).  Each lane traverses its own ray with its own stack
+// -- results are exactly those of the scalar algorithm in oracle/trace.cpp -- but the warp moves in
+// phases: descend() takes every active lane to its next leaf, leaf() tests that leaf's triangles and
+// then pops or retires the lane.  Without explicit phase barriers independent thread scheduling lets
+// the lanes drift apart for good (ncu r01 v1: 2.5 threads per instruction).
+//
+// Closest hit: ties resolve to the lower triangle index.  ANY_HIT: the lane retires at the first
+// hit with t < any_len; the occlusion bit equals that of the closest-hit traversal (same leaf
+// sequence until the first leaf that holds such a hit).
+struct TraversalStack {        // lives in local memory (dynamically indexed); kept apart from the
+    int   node[kStackMax];     // scalar state so that the scalars stay in registers
+    float tmin[kStackMax], tmax[kStackMax];
+};
 
-// Single-ray traversal, executed warp-synchronously.
-//
-// Every lane of the warp must call this together (callers pad their index space to whole warps
-// and pass valid=false for the padding lanes).  Each lane traverses its own ray with its own
-// stack -- results are exactly those of the scalar algorithm -- but the warp moves in phases:
-// all lanes descend to their next leaf, reconverge, test their leaf's triangles, reconverge,
-// pop.  Without the explicit phase barriers independent thread scheduling lets the lanes drift
-// apart for good and the warp executes ~2 threads per instruction (ncu, profiles/k1_r01_*).
-// The node step is branch-free (selects + one predicated push).
-//
-// ANY_HIT: stop at the first hit with t < any_len (visibility only); the occlusion bit equals that
-// of the closest-hit traversal (same leaf sequence until the first leaf that holds such a hit).
-// Closest hit: ties resolve to the lower triangle index.
-template <bool ANY_HIT>
-__device__ __forceinline__ void trace_ray(const DevScene& S, const Ray& r, bool valid, float tmin, float tmax,
-                                          int skip_id, float any_len, int& hit_tri, float& hit_t) {
-    constexpr unsigned kFull = 0xffffffffu;
-    hit_tri = -1; hit_t = kHitInit;
-    const float ix = 1.0f / (r.dx == 0.0f ? kFltEpsilon : r.dx);
-    const float iy = 1.0f / (r.dy == 0.0f ? kFltEpsilon : r.dy);
-    const float iz = 1.0f / (r.dz == 0.0f ? kFltEpsilon : r.dz);
-    {
-        float t0 = (S.bmin[0] - r.ox) * ix, t1 = (S.bmax[0] - r.ox) * ix;
-        tmin = max_sel(tmin, min_sel(t0, t1)); tmax = min_sel(tmax, max_sel(t0, t1));
-        t0 = (S.bmin[1] - r.oy) * iy; t1 = (S.bmax[1] - r.oy) * iy;
-        tmin = max_sel(tmin, min_sel(t0, t1)); tmax = min_sel(tmax, max_sel(t0, t1));
-        t0 = (S.bmin[2] - r.oz) * iz; t1 = (S.bmax[2] - r.oz) * iz;
-        tmin = max_sel(tmin, min_sel(t0, t1)); tmax = min_sel(tmax, max_sel(t0, t1));
+struct Traversal {
+    Ray   r;
+    float ix, iy, iz;          // 1/d with zero components replaced by FLT_EPSILON first
+    float tmin, tmax;          // current interval
+    float hit_t;
+    int   hit_tri;
+    int   node, sp;
+    int   neg;                 // bit a set when d[a] < 0 (front child = right)
+    bool  active;
+
+    __device__ __forceinline__ void idle() { active = false; hit_tri = -1; hit_t = kHitInit; }
+
+    // start a new ray on this lane (may be called by a subset of lanes: no warp collectives inside)
+    __device__ __forceinline__ void begin(const DevScene& S, const Ray& ray, bool valid, float t0, float t1) {
+        r = ray;
+        hit_tri = -1; hit_t = kHitInit;
+        ix = 1.0f / (r.dx == 0.0f ? kFltEpsilon : r.dx);
+        iy = 1.0f / (r.dy == 0.0f ? kFltEpsilon : r.dy);
+        iz = 1.0f / (r.dz == 0.0f ? kFltEpsilon : r.dz);
+        float a0 = (S.bmin[0] - r.ox) * ix, a1 = (S.bmax[0] - r.ox) * ix;
+        t0 = max_sel(t0, min_sel(a0, a1)); t1 = min_sel(t1, max_sel(a0, a1));
+        a0 = (S.bmin[1] - r.oy) * iy; a1 = (S.bmax[1] - r.oy) * iy;
+        t0 = max_sel(t0, min_sel(a0, a1)); t1 = min_sel(t1, max_sel(a0, a1));
+        a0 = (S.bmin[2] - r.oz) * iz; a1 = (S.bmax[2] - r.oz) * iz;
+        t0 = max_sel(t0, min_sel(a0, a1)); t1 = min_sel(t1, max_sel(a0, a1));
+        tmin = t0; tmax = t1;
+        active = valid && (t0 <= t1);
+        neg = (r.dx < 0.0f ? 1 : 0) | (r.dy < 0.0f ? 2 : 0) | (r.dz < 0.0f ? 4 : 0);
+        node = 0; sp = 0;
     }
-    bool active = valid && (tmin <= tmax);
-    const int negx = r.dx < 0.0f, negy = r.dy < 0.0f, negz = r.dz < 0.0f;
 
-    int   st_node[kStackMax];
-    float st_tmin[kStackMax], st_tmax[kStackMax];
-    int sp = 0;
-    int node = 0;
-    while (__any_sync(kFull, active)) {
+    // phase 1: branch-free node steps down to the next leaf; returns that leaf's node word
+    __device__ __forceinline__ int2 descend(const DevScene& S, TraversalStack& st) {
         int2 nd = make_int2(3, 0);
-        // ---- phase 1: descend to the next leaf
         if (active) {
             nd = __ldg(&S.nodes[node]);
             while ((nd.x & 3) != 3) {
                 const int axis = nd.x & 3;
                 const int left = nd.x >> 2;
-                const int neg = axis == 0 ? negx : (axis == 1 ? negy : negz);
+                const int ng = (neg >> axis) & 1;
                 const float o = pick3(axis, r.ox, r.oy, r.oz);
                 const float inv = pick3(axis, ix, iy, iz);
                 const float t = (__int_as_float(nd.y) - o) * inv;
-                const int front = left + neg, back = left + (neg ^ 1);
+                const int front = left + ng, back = left + (ng ^ 1);
                 const bool back_only = !(t >= tmin);
                 const bool both = !back_only && (t <= tmax);
                 const float tmin_far = max_sel(tmin, t);
-                if (both) { st_node[sp] = back; st_tmin[sp] = tmin_far; st_tmax[sp] = tmax; sp++; }
+                if (both) { st.node[sp] = back; st.tmin[sp] = tmin_far; st.tmax[sp] = tmax; sp++; }
                 node = back_only ? back : front;
                 tmax = back_only ? tmax : min_sel(tmax, t);
                 tmin = back_only ? tmin_far : tmin;
                 nd = __ldg(&S.nodes[node]);
             }
         }
-        __syncwarp(kFull);
-        // ---- phase 2: the leaf's triangles, then terminate or pop
-        if (active) {
-            const int start = nd.x >> 2;
-            const int cnt = (int)__int_as_float(nd.y);
-            for (int k = 0; k < cnt; k++) {
+        __syncwarp(0xffffffffu);
+        return nd;
+    }
+
+    // phase 2: the leaf's triangles in two converged sub-phases per round -- (A) every lane scans
+    // forward to its next triangle whose plane hit is in range (cheap, one 16-B load each), (B) the
+    // lanes that found one run the projected edge tests together -- then terminate or pop.
+    template <bool ANY_HIT>
+    __device__ __forceinline__ void leaf(const DevScene& S, TraversalStack& st, int2 nd, int skip_id, float any_len) {
+        const int start = nd.x >> 2;
+        int cnt = active ? (int)__int_as_float(nd.y) : 0;
+        int k = 0;
+        for (;;) {
+            int cand = -1; float tc = 0.0f;
+            while (k < cnt) {
                 const int ti = __ldg(&S.tri_index[start + k]);
-                float t;
-                if (ANY_HIT) {
-                    if (test_triangle(S, ti, r, skip_id, any_len, -1, t)) { hit_tri = ti; hit_t = t; active = false; break; }
-                } else {
-                    if (test_triangle(S, ti, r, skip_id, hit_t, hit_tri, t)) { hit_tri = ti; hit_t = t; }
+                k++;
+                const float4 a = __ldg(&S.q0[ti]);
+                const float ddotn = ((r.dx * a.x) + (r.dy * a.y)) + (r.dz * a.z);
+                const float odotn = ((r.ox * a.x) + (r.oy * a.y)) + (r.oz * a.z);
+                const float t = (a.w - odotn) / ddotn;
+                const bool facing = ddotn > kDdotNEps || ddotn < -kDdotNEps;
+                const bool better = ANY_HIT ? (t < any_len) : (t < hit_t || (t == hit_t && ti < hit_tri));
+                if (facing && t > 0.0f && better) { cand = ti; tc = t; break; }
+            }
+            if (!__any_sync(0xffffffffu, cand >= 0)) break;
+            if (cand >= 0) {
+                const float4 c = __ldg(&S.q2[cand]);
+                const float4 b = __ldg(&S.q1[cand]);
+                const int sel = __float_as_int(c.w);
+                const int s0 = sel & 3, s1 = (sel >> 8) & 3;
+                const float c0 = pick3(s0, r.ox, r.oy, r.oz) + (tc * pick3(s0, r.dx, r.dy, r.dz));
+                const float c1 = pick3(s1, r.ox, r.oy, r.oz) + (tc * pick3(s1, r.dx, r.dy, r.dz));
+                const float b0 = ((b.x * c0) + (b.y * c1)) + b.z;
+                const float b1 = ((b.w * c0) + (c.x * c1)) + c.y;
+                const bool inside = (b0 >= 0.0f) && (b1 >= 0.0f) && ((b0 + b1) <= 1.0f);
+                if (inside && __float_as_int(c.z) != skip_id) {
+                    hit_tri = cand; hit_t = tc;
+                    if (ANY_HIT) { active = false; cnt = 0; }
                 }
             }
-            if (active) {
-                if (!(tmax <= hit_t) || sp == 0) active = false;
-                else { sp--; node = st_node[sp]; tmin = st_tmin[sp]; tmax = st_tmax[sp]; }
-            }
         }
-        __syncwarp(kFull);
+        if (active) {
+            if (!(tmax <= hit_t) || sp == 0) active = false;
+            else { sp--; node = st.node[sp]; tmin = st.tmin[sp]; tmax = st.tmax[sp]; }
+        }
+        __syncwarp(0xffffffffu);
     }
+};
+
+// One ray per lane, to completion (used where each lane has exactly one ray: K2, K3, trace4).
+template <bool ANY_HIT>
+__device__ __forceinline__ void trace_ray(const DevScene& S, const Ray& r, bool valid, float tmin, float tmax,
+                                          int skip_id, float any_len, int& hit_tri, float& hit_t) {
+    Traversal T;
+    TraversalStack st;
+    T.begin(S, r, valid, tmin, tmax);
+    while (__any_sync(0xffffffffu, T.active)) {
+        const int2 nd = T.descend(S, st);
+        T.leaf<ANY_HIT>(S, st, nd, skip_id, any_len);
+    }
+    hit_tri = T.hit_tri; hit_t = T.hit_t;
 }
 
 // trace.TestLine front end (raytracer/trace/testline.go:22-27): segment -> normalised ray.

@@ -18,6 +18,7 @@
 #include "env_internal.cuh"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
+#include <cstdlib>
 
 namespace vrad {
 
@@ -201,10 +202,15 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     K2_CHECK(cudaMemsetAsync(d_padlen.p, 0, (nloc + 1) * 8, e->stream));
 
     PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p};
+    static const bool verbose = getenv("VRAD_TIMING") != nullptr;
+    cudaEvent_t tv0 = nullptr, tv1 = nullptr;
+    if (verbose) { cudaEventCreate(&tv0); cudaEventCreate(&tv1); }
     timing_begin(e);
     int launches = 0;
     if (nloc > 0) {
+        if (verbose) cudaEventRecord(tv0, e->stream);
         k2_visibility<<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p);
+        if (verbose) cudaEventRecord(tv1, e->stream);
         launches++;
         const int wblocks = (nloc * 32 + 255) / 256;
         k2_count<<<wblocks, 256, 0, e->stream>>>(nloc, d_bit_ptr.p, d_bits.p, T.rowlen.p, d_padlen.p);
@@ -232,6 +238,12 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     K2_CHECK(cudaStreamSynchronize(e->stream));
     K2_CHECK(cudaGetLastError());
 #undef K2_CHECK
+    if (verbose && tv0) {
+        float ms = 0.f;
+        if (nloc > 0) cudaEventElapsedTime(&ms, tv0, tv1);
+        fprintf(stderr, "[vrad] k2_visibility %.3f ms (rows %d, visibility words %lld)\n", ms, nloc, (long long)nwords);
+        cudaEventDestroy(tv0); cudaEventDestroy(tv1);
+    }
     int64_t nnz = 0;
     for (int r = 0; r < nloc; r++) nnz += rl[r];
     T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.ready = true;
