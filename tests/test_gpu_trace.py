@@ -136,3 +136,18 @@ def test_errors_are_loud(s1_scene):
     with pytest.raises(VradError):
         e.setup_acceleration_structure()
     e.close()
+
+
+def test_pipelined_host_path_matches_device_path(s1_scene, s1_gpu, s1_oracle):
+    """Host batches >= 2^22 segments take the chunked, copy/compute-overlapped path: same bits."""
+    torch = pytest.importorskip("torch")
+    n = (1 << 22) + 12345
+    a, b = scenes.shadow_segments(s1_scene, n, seed=4242)
+    host_bits = s1_gpu.test_lines(a, b)
+    dev_bits = s1_gpu.test_lines(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(host_bits, dev_bits.cpu().numpy().view(np.uint32))
+    ns = 1 << 16
+    assert np.array_equal(host_bits[: ns // 32], s1_oracle.test_lines(a[:, :ns].copy(), b[:, :ns].copy(), threads=8))
+    tail0 = (n // 32) * 32 - 64
+    assert np.array_equal(host_bits[tail0 // 32:], s1_oracle.test_lines(a[:, tail0:].copy(), b[:, tail0:].copy(), threads=8))

@@ -94,6 +94,11 @@ struct vrad_env {
     vrad::DevBuf<float4> d_q0, d_q1, d_q2;
     vrad::DevScene scene{};
 
+    // second stream + double-buffered staging for the pipelined host-buffer paths
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    vrad::DevBuf<float> d_stage[2];
+
     // scratch for staging host pointers
     std::vector<vrad::DevBuf<unsigned char>> scratch;
     size_t scratch_used = 0;
@@ -126,5 +131,6 @@ int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, 
                       const float* dy, const float* dz, const float* tmin, const float* tmax, int32_t skip_id,
                       int32_t* hit_tri, int32_t* hit_sid, float* hit_t, float* normal_soa);
 int launch_test_lines(vrad_env* e, int64_t n, const float* start_soa, const float* stop_soa, int sky_mode, uint32_t* bits);
+int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, int sky_mode, uint32_t* d_bits);
 
 } // namespace vrad

@@ -83,8 +83,8 @@ k1_trace_rays(DevScene S, int64_t n, const float* __restrict__ ox, const float* 
 
 template <bool SKY>
 __global__ void __launch_bounds__(kTraceBlock)
-k1_test_lines(DevScene S, int64_t n, const float* __restrict__ a, const float* __restrict__ b,
-              uint32_t* __restrict__ bits) {
+k1_test_lines(DevScene S, int64_t n, int64_t stride, const float* __restrict__ a, const float* __restrict__ b,
+              uint32_t* __restrict__ bits) {            // a, b: SoA blocks x[stride] y[stride] z[stride]
     __shared__ uint32_t words[kTraceWarps][kRaysPerWarp / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_chunks = (n + kRaysPerWarp - 1) / kRaysPerWarp;
@@ -98,7 +98,7 @@ k1_test_lines(DevScene S, int64_t n, const float* __restrict__ a, const float* _
         auto fetch = [&](int64_t i, Ray& r, float& t0, float& t1, float& len) {
             t0 = 0.0f;
             r = Ray{0.f, 0.f, 0.f, 1.f, 1.f, 1.f}; len = 0.0f;
-            const bool ok = segment_to_ray(a[i], a[n + i], a[2 * n + i], b[i], b[n + i], b[2 * n + i], r, len);
+            const bool ok = segment_to_ray(a[i], a[stride + i], a[2 * stride + i], b[i], b[stride + i], b[2 * stride + i], r, len);
             t1 = len;
             return ok;
         };
@@ -136,11 +136,48 @@ int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, 
     return 0;
 }
 
+static void enqueue_test_lines(vrad_env* e, int64_t n, int64_t stride, const float* a, const float* b, int sky_mode, uint32_t* bits) {
+    if (sky_mode) k1_test_lines<true><<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(e->scene, n, stride, a, b, bits);
+    else k1_test_lines<false><<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(e->scene, n, stride, a, b, bits);
+}
+
 int launch_test_lines(vrad_env* e, int64_t n, const float* start_soa, const float* stop_soa, int sky_mode, uint32_t* bits) {
     timing_begin(e);
-    if (sky_mode) k1_test_lines<true><<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(e->scene, n, start_soa, stop_soa, bits);
-    else k1_test_lines<false><<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(e->scene, n, start_soa, stop_soa, bits);
+    enqueue_test_lines(e, n, n, start_soa, stop_soa, sky_mode, bits);
     timing_end(e, 1);
+    VRAD_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// Host-buffer path: the segments are copied in chunks on a second stream into two staging buffers
+// while the previous chunk is traced, so the call costs max(PCIe, kernel) instead of their sum.
+// h_a / h_b are host SoA blocks x[n] y[n] z[n]; d_bits is the device result (n bits).
+int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, int sky_mode, uint32_t* d_bits) {
+    constexpr int64_t kChunk = (int64_t)1 << 21;       // segments per chunk: 48 MiB of coordinates, multiple of kRaysPerWarp
+    for (int s = 0; s < 2; s++)
+        if (e->d_stage[s].alloc((size_t)6 * kChunk)) { set_error("out of device memory for staging"); return VRAD_E_NOMEM; }
+    timing_begin(e);
+    int launches = 0;
+    // the copy stream must not overwrite staging that earlier work on the main stream may still read
+    VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[0], e->stream));
+    VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[1], e->stream));
+    int c = 0;
+    for (int64_t c0 = 0; c0 < n; c0 += kChunk, c++) {
+        const int s = c & 1;
+        const int64_t m = n - c0 < kChunk ? n - c0 : kChunk;
+        float* st = e->d_stage[s].p;
+        VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, e->ev_done[s], 0));
+        for (int k = 0; k < 3; k++) {
+            VRAD_CUDA_CHECK(cudaMemcpyAsync(st + k * kChunk, h_a + k * n + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
+            VRAD_CUDA_CHECK(cudaMemcpyAsync(st + (3 + k) * kChunk, h_b + k * n + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
+        }
+        VRAD_CUDA_CHECK(cudaEventRecord(e->ev_copied[s], e->copy_stream));
+        VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_copied[s], 0));
+        enqueue_test_lines(e, m, kChunk, st, st + 3 * kChunk, sky_mode, d_bits + (c0 >> 5));
+        launches++;
+        VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[s], e->stream));
+    }
+    timing_end(e, launches);
     VRAD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

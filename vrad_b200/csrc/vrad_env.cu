@@ -136,6 +136,11 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
     e->stream = e->own_stream;
     VRAD_CUDA_CHECK(cudaEventCreate(&e->ev0));
     VRAD_CUDA_CHECK(cudaEventCreate(&e->ev1));
+    VRAD_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; s++) {
+        VRAD_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_copied[s], cudaEventDisableTiming));
+        VRAD_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done[s], cudaEventDisableTiming));
+    }
     *out = e;
     return VRAD_OK;
 }
@@ -151,6 +156,12 @@ void vrad_env_destroy(vrad_env* e) {
     e->patches.origin_area.release(); e->patches.normal_dist.release(); e->patches.refl.release(); e->patches.cluster.release();
     e->transfers.rowptr.release(); e->transfers.rowlen.release(); e->transfers.tr.release();
     e->d_sky_dirs.release(); e->d_er[0].release(); e->d_er[1].release(); e->d_total.release(); e->d_partials.release();
+    for (int s = 0; s < 2; s++) {
+        e->d_stage[s].release();
+        if (e->ev_copied[s]) cudaEventDestroy(e->ev_copied[s]);
+        if (e->ev_done[s]) cudaEventDestroy(e->ev_done[s]);
+    }
+    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -343,6 +354,14 @@ int vrad_test_lines(vrad_env* e, int64_t n, const float* start_xyz_soa, const fl
     const size_t b = (size_t)n * 12, wb = (size_t)((n + 31) / 32) * 4;
     const void *d_a, *d_b; bool ha, hb, ho;
     int rc;
+    if (n >= ((int64_t)1 << 22) && !is_device_ptr(start_xyz_soa) && !is_device_ptr(stop_xyz_soa)) {
+        // large host batch: overlap the H2D copies with the traversal
+        void* d_o;
+        if ((rc = stage_out(e, 2, vis_bits, wb, &d_o, &ho))) return rc;
+        if ((rc = launch_test_lines_pipelined(e, n, start_xyz_soa, stop_xyz_soa, sky_mode, (uint32_t*)d_o))) return rc;
+        if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
+        return sync_if_needed(e, true);
+    }
     if ((rc = stage_in(e, 0, start_xyz_soa, b, &d_a, &ha))) return rc;
     if ((rc = stage_in(e, 1, stop_xyz_soa, b, &d_b, &hb))) return rc;
     void* d_o;
