@@ -5,8 +5,13 @@
 // The reference has no communication layer of any kind.
 #include "env_internal.cuh"
 #include <dlfcn.h>
+#include <cstdlib>
+#include <string>
+#include <vector>
 
 namespace vrad {
+
+void comm_close_peers(vrad_env* e);
 
 typedef struct { char internal[128]; } nccl_uid;
 typedef void* nccl_comm_t;
@@ -64,6 +69,67 @@ int comm_allreduce3(vrad_env* e, float* d3) {
     return 0;
 }
 
+// Exchange CUDA IPC handles of er[0], er[1] and the flag words through the NCCL communicator and map
+// every peer's buffers.  Collective: all ranks call it with the same n_pad.  Returns VRAD_OK with
+// peers.ready == false when peer mapping is unavailable (the caller then keeps the NCCL all-gather).
+int comm_setup_peers(vrad_env* e, size_t n_pad) {
+    PeerLinks& P = e->peers;
+    const int world = e->cfg.world, rank = e->cfg.rank;
+    if (P.ready && P.n_pad == n_pad) return 0;
+    if (world > kMaxWorld) return 0;
+    static const bool force_nccl = [] { const char* v = getenv("VRAD_K4_EXCHANGE"); return v && std::string(v) == "nccl"; }();
+    if (force_nccl) return 0;
+    comm_close_peers(e);
+    if (P.d_flags.alloc(2 * kMaxWorld)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemsetAsync(P.d_flags.p, 0, 2 * kMaxWorld * sizeof(uint32_t), e->stream));
+    struct Handles { cudaIpcMemHandle_t h[3]; int ok; int pad[15]; };
+    static_assert(sizeof(Handles) % 4 == 0, "handle record must be a whole number of floats");
+    std::vector<Handles> all(world);
+    Handles mine{};
+    mine.ok = cudaIpcGetMemHandle(&mine.h[0], e->d_er[0].p) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.h[1], e->d_er[1].p) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.h[2], P.d_flags.p) == cudaSuccess;
+    cudaGetLastError();
+    DevBuf<unsigned char> d_all;
+    if (d_all.alloc(sizeof(Handles) * world)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(d_all.p + sizeof(Handles) * rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice, e->stream));
+    VRAD_NCCL_CHECK(g_nccl.allgather(d_all.p + sizeof(Handles) * rank, d_all.p, sizeof(Handles) / 4, kNcclFloat, (nccl_comm_t)e->nccl_comm, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Handles) * world, cudaMemcpyDeviceToHost, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    d_all.release();
+    bool ok = true;
+    for (int r = 0; r < world; r++) ok = ok && all[r].ok;
+    for (int r = 0; r < world && ok; r++) {
+        if (r == rank) { P.er[0][r] = e->d_er[0].p; P.er[1][r] = e->d_er[1].p; P.flags[r] = P.d_flags.p; continue; }
+        for (int k = 0; k < 3; k++) {
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            P.opened[k][r] = ptr;
+        }
+        P.er[0][r] = (float4*)P.opened[0][r]; P.er[1][r] = (float4*)P.opened[1][r]; P.flags[r] = (uint32_t*)P.opened[2][r];
+    }
+    // every rank must take the same path: agree on success with a 3-float all-reduce (min via negated sum)
+    DevBuf<float> d_ok;
+    if (d_ok.alloc(3)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    float h_ok[3] = {ok ? 0.0f : 1.0f, 0.0f, 0.0f};
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(d_ok.p, h_ok, 12, cudaMemcpyHostToDevice, e->stream));
+    VRAD_NCCL_CHECK(g_nccl.allreduce(d_ok.p, d_ok.p, 3, kNcclFloat, kNcclSum, (nccl_comm_t)e->nccl_comm, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(h_ok, d_ok.p, 12, cudaMemcpyDeviceToHost, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    d_ok.release();
+    if (h_ok[0] != 0.0f) { comm_close_peers(e); return 0; }
+    P.ready = true; P.n_pad = n_pad;
+    return 0;
+}
+
+void comm_close_peers(vrad_env* e) {
+    PeerLinks& P = e->peers;
+    for (int k = 0; k < 3; k++)
+        for (int r = 0; r < kMaxWorld; r++)
+            if (P.opened[k][r]) { cudaIpcCloseMemHandle(P.opened[k][r]); P.opened[k][r] = nullptr; }
+    P.ready = false; P.n_pad = 0;
+}
+
 } // namespace vrad
 using namespace vrad;
 
@@ -95,6 +161,7 @@ int vrad_comm_init(vrad_env* e, const void* unique_id128) {
 }
 
 void vrad_comm_destroy_internal(vrad_env* e) {
+    if (e) { comm_close_peers(e); e->peers.d_flags.release(); }
     if (e && e->nccl_comm && g_nccl.h) { g_nccl.destroy((nccl_comm_t)e->nccl_comm); e->nccl_comm = nullptr; }
 }
 

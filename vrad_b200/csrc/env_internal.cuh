@@ -66,6 +66,30 @@ struct TransfersDev {
     bool ready = false;
 };
 
+constexpr int kMaxWorld = 8;
+
+// Peer-memory view of the radiance buffers (multi-GPU K4): pointers into every rank's er[0]/er[1]
+// and flag words, obtained through CUDA IPC (one process per GPU).  Slot `rank` is the local buffer.
+struct PeerLinks {
+    bool      ready = false;
+    size_t    n_pad = 0;
+    float4*   er[2][kMaxWorld] = {};
+    uint32_t* flags[kMaxWorld] = {};
+    void*     opened[3][kMaxWorld] = {};     // mappings to close
+    DevBuf<uint32_t> d_flags;                // [kMaxWorld] arrival flags + [kMaxWorld] = this rank's epoch counter
+};
+
+struct GatherTargets {                       // where k4_gather writes a finished row of er_next
+    float4* dst[kMaxWorld];
+    int     n;
+};
+
+struct BarrierArgs {
+    uint32_t* local;                         // this rank's flag words (one per peer) followed by the epoch counter
+    uint32_t* peer[kMaxWorld];               // every rank's flag words
+    int world, rank;
+};
+
 } // namespace vrad
 
 struct vrad_env {
@@ -112,6 +136,7 @@ struct vrad_env {
     vrad::DevBuf<float4> d_total;      // accumulated bounced light for local rows
     vrad::DevBuf<float>  d_partials;   // per-block partial sums of `added`
     void* nccl_comm = nullptr;         // ncclComm_t
+    vrad::PeerLinks peers;             // K4 fused exchange over NVLink peer memory
 };
 
 namespace vrad {

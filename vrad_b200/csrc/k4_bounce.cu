@@ -20,6 +20,7 @@
 namespace vrad {
 
 int comm_allgather_f4(vrad_env* e, float4* buf, size_t rows_per_rank);
+int comm_setup_peers(vrad_env* e, size_t n_pad);
 int comm_allreduce3(vrad_env* e, float* d3);
 
 constexpr int kGatherBlock = 256;
@@ -52,7 +53,7 @@ constexpr int kGatherUnroll = 8;
 __global__ void __launch_bounds__(kGatherBlock, 5)
 k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
           const float4* __restrict__ er, const float4* __restrict__ refl,
-          float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
+          GatherTargets er_next, float4* __restrict__ total, float* __restrict__ partials) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * kGatherWarps + warp;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -87,15 +88,18 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
         }
         if (lane == 0) {
             const float4 r = refl[row0 + row];
+            float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r.w == 0.0f) {                                              // CollectLight, leaf patch
                 float4 t = total[row];
                 t.x += s0; t.y += s1; t.z += s2;
                 total[row] = t;
-                er_next[row0 + row] = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                nv = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
                 e0 = s0; e1 = s1; e2 = s2;
-            } else {
-                er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);     // sky: emit = 0
-            }
+            }                                                               // sky: emit = 0
+            // fused exchange: the finished row goes straight into every rank's next-bounce buffer
+            // (NVLink peer stores; dst[] holds the local buffer too) -- no separate all-gather pass
+#pragma unroll
+            for (int p = 0; p < kMaxWorld; p++) if (p < er_next.n) er_next.dst[p][row0 + row] = nv;
         }
     }
     // deterministic per-block partial of `added`
@@ -107,6 +111,23 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
 #pragma unroll
         for (int k = 0; k < kGatherWarps; k++) a += sm[k][threadIdx.x];
         partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    }
+}
+
+// Device-side barrier between bounces of the fused exchange: every rank bumps its epoch, stores it
+// into its slot of every peer's flag words (after a system-scope fence that orders the peer row
+// stores of the preceding k4_gather) and spins until all peers' epochs have arrived.  One block.
+__global__ void k4_peer_barrier(BarrierArgs a) {
+    __shared__ uint32_t epoch;
+    if (threadIdx.x == 0) epoch = ++a.local[kMaxWorld];
+    __syncthreads();
+    if ((int)threadIdx.x < a.world) {
+        __threadfence_system();
+        volatile uint32_t* dst = a.peer[threadIdx.x] + a.rank;
+        *dst = epoch;
+        volatile uint32_t* src = a.local + threadIdx.x;
+        while ((int32_t)(*src - epoch) < 0) { }
+        __threadfence_system();
     }
 }
 
@@ -264,6 +285,13 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     void* d_out3;
     if ((rc = stage_out(e, 1, total_rgb_out, (size_t)N * 12, &d_out3, &h_out))) return rc;
     float* d_added = e->d_partials.p + 3 * (size_t)nblocks;       // 3 floats after the partials
+    if (world > 1 && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
+    const bool p2p = world > 1 && e->peers.ready;
+    BarrierArgs bar{};
+    if (p2p) {
+        bar.local = e->peers.d_flags.p; bar.world = world; bar.rank = e->cfg.rank;
+        for (int r = 0; r < world; r++) bar.peer[r] = e->peers.flags[r];
+    }
 
     timing_begin(e);
     int launches = 0;
@@ -275,11 +303,23 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
 
     int cur = 0, done = 0;
     float h_added[3] = {0.f, 0.f, 0.f};
+    static const bool verbose = getenv("VRAD_TIMING") != nullptr;
+    constexpr int kProbe = 16;
+    cudaEvent_t pe[kProbe][3];
+    int n_probe = 0;
     for (int b = 0; b < n_bounces; b++) {
+        const bool probe = verbose && b >= 4 && n_probe < kProbe;
+        if (probe) { for (int k = 0; k < 3; k++) cudaEventCreate(&pe[n_probe][k]); cudaEventRecord(pe[n_probe][0], e->stream); }
+        GatherTargets tg{};
+        if (p2p) { tg.n = world; for (int r = 0; r < world; r++) tg.dst[r] = e->peers.er[cur ^ 1][r]; }
+        else { tg.n = 1; tg.dst[0] = e->d_er[cur ^ 1].p; }
         k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p,
-                                                         e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
+                                                         e->d_er[cur].p, e->patches.refl.p, tg, total_local, e->d_partials.p);
         launches++;
-        if (world > 1 && (rc = comm_allgather_f4(e, e->d_er[cur ^ 1].p, (size_t)rpr))) return rc;
+        if (probe) cudaEventRecord(pe[n_probe][1], e->stream);
+        if (p2p) { k4_peer_barrier<<<1, 32, 0, e->stream>>>(bar); launches++; }
+        else if (world > 1 && (rc = comm_allgather_f4(e, e->d_er[cur ^ 1].p, (size_t)rpr))) return rc;
+        if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
         cur ^= 1; done++;
         const bool last = (b + 1 == n_bounces);
         if (early_out || last) {
@@ -300,6 +340,18 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     }
     timing_end(e, launches);
     VRAD_CUDA_CHECK(cudaGetLastError());
+    if (n_probe) {
+        cudaStreamSynchronize(e->stream);
+        float g = 0.f, x = 0.f;
+        for (int i = 0; i < n_probe; i++) {
+            float a = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, pe[i][0], pe[i][1]); cudaEventElapsedTime(&c, pe[i][1], pe[i][2]);
+            g += a; x += c;
+            for (int k = 0; k < 3; k++) cudaEventDestroy(pe[i][k]);
+        }
+        fprintf(stderr, "[vrad] rank %d k4_gather %.1f us, exchange (%s) %.1f us per bounce (%d probed)\n", e->cfg.rank,
+                1e3f * g / n_probe, p2p ? "peer stores + barrier" : (world > 1 ? "ncclAllGather" : "none"), 1e3f * x / n_probe, n_probe);
+    }
     if ((rc = finish_out(e, total_rgb_out, d_out3, (size_t)N * 12, h_out))) return rc;
     const bool need_sync = h_in || h_out || added_last != nullptr;
     if (added_last) VRAD_CUDA_CHECK(cudaMemcpyAsync(added_last, d_added, 12, cudaMemcpyDeviceToHost, e->stream));
