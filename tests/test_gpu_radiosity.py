@@ -149,3 +149,4 @@ def test_bounce_ragged_rows_and_sky():
     assert _rel_err(tg, total) <= RTOL
     assert np.allclose(ag, emit.sum(axis=0), rtol=1e-4)
     env.close()
+

@@ -118,6 +118,11 @@ int comm_setup_peers(vrad_env* e, size_t n_pad) {
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     d_ok.release();
     if (h_ok[0] != 0.0f) { comm_close_peers(e); return 0; }
+    PeerTable tbl{};
+    for (int r = 0; r < world; r++) { tbl.er[0][r] = P.er[0][r]; tbl.er[1][r] = P.er[1][r]; tbl.flags[r] = P.flags[r]; }
+    tbl.world = world; tbl.rank = rank;
+    if (P.d_table.alloc(1)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemcpy(P.d_table.p, &tbl, sizeof(tbl), cudaMemcpyHostToDevice));
     P.ready = true; P.n_pad = n_pad;
     return 0;
 }
@@ -161,7 +166,7 @@ int vrad_comm_init(vrad_env* e, const void* unique_id128) {
 }
 
 void vrad_comm_destroy_internal(vrad_env* e) {
-    if (e) { comm_close_peers(e); e->peers.d_flags.release(); }
+    if (e) { comm_close_peers(e); e->peers.d_flags.release(); e->peers.d_table.release(); }
     if (e && e->nccl_comm && g_nccl.h) { g_nccl.destroy((nccl_comm_t)e->nccl_comm); e->nccl_comm = nullptr; }
 }
 

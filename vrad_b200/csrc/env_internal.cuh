@@ -70,6 +70,7 @@ constexpr int kMaxWorld = 8;
 
 // Peer-memory view of the radiance buffers (multi-GPU K4): pointers into every rank's er[0]/er[1]
 // and flag words, obtained through CUDA IPC (one process per GPU).  Slot `rank` is the local buffer.
+struct PeerTable;
 struct PeerLinks {
     bool      ready = false;
     size_t    n_pad = 0;
@@ -77,16 +78,13 @@ struct PeerLinks {
     uint32_t* flags[kMaxWorld] = {};
     void*     opened[3][kMaxWorld] = {};     // mappings to close
     DevBuf<uint32_t> d_flags;                // [kMaxWorld] arrival flags + [kMaxWorld] = this rank's epoch counter
+    DevBuf<PeerTable> d_table;
 };
 
-struct GatherTargets {                       // where k4_gather writes a finished row of er_next
-    float4* dst[kMaxWorld];
-    int     n;
-};
-
-struct BarrierArgs {
-    uint32_t* local;                         // this rank's flag words (one per peer) followed by the epoch counter
-    uint32_t* peer[kMaxWorld];               // every rank's flag words
+// the same pointers as one record in device memory, read by k4_gather<true> and the barrier kernels
+struct PeerTable {
+    float4*   er[2][kMaxWorld];
+    uint32_t* flags[kMaxWorld];              // flags[r][0..kMaxWorld) arrival words, flags[r][kMaxWorld] = rank r's epoch
     int world, rank;
 };
 

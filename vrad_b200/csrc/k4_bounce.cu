@@ -53,7 +53,7 @@ constexpr int kGatherUnroll = 8;
 __global__ void __launch_bounds__(kGatherBlock, 5)
 k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
           const float4* __restrict__ er, const float4* __restrict__ refl,
-          GatherTargets er_next, float4* __restrict__ total, float* __restrict__ partials) {
+          float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * kGatherWarps + warp;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -88,18 +88,15 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
         }
         if (lane == 0) {
             const float4 r = refl[row0 + row];
-            float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r.w == 0.0f) {                                              // CollectLight, leaf patch
                 float4 t = total[row];
                 t.x += s0; t.y += s1; t.z += s2;
                 total[row] = t;
-                nv = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                er_next[row0 + row] = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
                 e0 = s0; e1 = s1; e2 = s2;
-            }                                                               // sky: emit = 0
-            // fused exchange: the finished row goes straight into every rank's next-bounce buffer
-            // (NVLink peer stores; dst[] holds the local buffer too) -- no separate all-gather pass
-#pragma unroll
-            for (int p = 0; p < kMaxWorld; p++) if (p < er_next.n) er_next.dst[p][row0 + row] = nv;
+            } else {
+                er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);     // sky: emit = 0
+            }
         }
     }
     // deterministic per-block partial of `added`
@@ -114,20 +111,123 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
     }
 }
 
-// Device-side barrier between bounces of the fused exchange: every rank bumps its epoch, stores it
-// into its slot of every peer's flag words (after a system-scope fence that orders the peer row
-// stores of the preceding k4_gather) and spins until all peers' epochs have arrived.  One block.
-__global__ void k4_peer_barrier(BarrierArgs a) {
-    __shared__ uint32_t epoch;
-    if (threadIdx.x == 0) epoch = ++a.local[kMaxWorld];
+// out of line on purpose: keeps the peer-table loads out of the gather loop's register allocation
+__device__ __noinline__ void store_row_to_peers(const PeerTable* __restrict__ peers, int next_buf, int64_t row, float x, float y, float z) {
+    const int lane = threadIdx.x & 31;
+    x = __shfl_sync(0xffffffffu, x, 0); y = __shfl_sync(0xffffffffu, y, 0); z = __shfl_sync(0xffffffffu, z, 0);
+    if (lane < peers->world) peers->er[next_buf][lane][row] = make_float4(x, y, z, 0.f);
+}
+
+__device__ __noinline__ void wait_for_peers(const PeerTable* __restrict__ peers, int wait_world) {
+    if ((int)threadIdx.x < wait_world) {
+        volatile uint32_t* local = peers->flags[peers->rank];
+        const uint32_t epoch = local[kMaxWorld];
+        while ((int32_t)(local[threadIdx.x] - epoch) < 0) { }
+    }
     __syncthreads();
-    if ((int)threadIdx.x < a.world) {
+}
+
+// Multi-GPU form of the same kernel: `peers` (device memory) lists every rank's er_next buffer and this
+// rank's flag words; lanes 0..world-1 store the finished row into one rank each (fused exchange), and
+// the prologue is the wait half of the inter-bounce barrier.  Kept as a separate kernel so that the
+// single-GPU instantiation keeps its register allocation (the loop is occupancy-bound).
+template <bool MULTI>
+__global__ void __launch_bounds__(kGatherBlock, 5)
+k4_gather_multi(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
+          const float4* __restrict__ er, const float4* __restrict__ refl,
+          float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials,
+          const PeerTable* __restrict__ peers, int next_buf, int wait_world) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * kGatherWarps + warp;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    if (MULTI) {
+        // fused-exchange prologue: the radiance this bounce reads is complete once every rank's epoch has
+        // arrived in the local flag words (wait half of the barrier; k4_peer_signal is the other half)
+        if (wait_world > 1) wait_for_peers(peers, wait_world);
+    }
+    if (row < nloc) {
+        const int64_t k0 = rowptr[row], k1 = rowptr[row + 1];      // padded to 4 entries; padding has w = 0
+        const int2 zero = make_int2(0, 0);                          // out-of-row slots: col 0, weight 0
+        int2 cur[kGatherUnroll], nxt[kGatherUnroll];
+        int64_t k = k0 + lane;
+#pragma unroll
+        for (int j = 0; j < kGatherUnroll; j++) cur[j] = k + 32 * j < k1 ? __ldcs(&tr[k + 32 * j]) : zero;
+        for (; k < k1; k += 32 * kGatherUnroll) {
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++)
+                nxt[j] = k + 32 * (kGatherUnroll + j) < k1 ? __ldcs(&tr[k + 32 * (kGatherUnroll + j)]) : zero;
+            float4 x[kGatherUnroll];
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) {
+                const float w = __int_as_float(cur[j].y);
+                s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
+            }
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);                        // sky: emit = 0
+        if (lane == 0) {
+            const float4 r = refl[row0 + row];
+            if (r.w == 0.0f) {                                              // CollectLight, leaf patch
+                float4 t = total[row];
+                t.x += s0; t.y += s1; t.z += s2;
+                total[row] = t;
+                nv = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                e0 = s0; e1 = s1; e2 = s2;
+            }
+            if (!MULTI) er_next[row0 + row] = nv;
+        }
+        if (MULTI) {
+            // fused exchange: lane p stores the finished row straight into rank p's next-bounce buffer
+            // (NVLink peer store; slot `rank` is the local buffer) -- no separate all-gather pass
+            store_row_to_peers(peers, next_buf, row0 + row, nv.x, nv.y, nv.z);
+        }
+    }
+    // deterministic per-block partial of `added`
+    __shared__ float sm[kGatherWarps][3];
+    if (lane == 0) { sm[warp][0] = e0; sm[warp][1] = e1; sm[warp][2] = e2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < kGatherWarps; k++) a += sm[k][threadIdx.x];
+        partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    }
+}
+
+// Fused-exchange barrier between bounces, split in two so that no kernel sits spinning between them:
+// k4_peer_signal (one tiny block after each gather) bumps this rank's epoch and stores it into its
+// slot of every peer's flag words -- after a system-scope fence that orders the peer row stores of
+// the gather that just completed -- and the NEXT k4_gather waits in its prologue until all peers'
+// epochs have arrived.  k4_peer_wait closes the last bounce of a call.
+// wait half as a stand-alone kernel: closes the last bounce of a call (no later gather would wait for it)
+__global__ void k4_peer_wait(const PeerTable* __restrict__ peers) {
+    if ((int)threadIdx.x < peers->world) {
+        volatile uint32_t* local = peers->flags[peers->rank];
+        const uint32_t epoch = local[kMaxWorld];
+        while ((int32_t)(local[threadIdx.x] - epoch) < 0) { }
         __threadfence_system();
-        volatile uint32_t* dst = a.peer[threadIdx.x] + a.rank;
+    }
+}
+
+// signal half of the fused-exchange barrier (the wait half is the prologue of k4_gather)
+__global__ void k4_peer_signal(const PeerTable* __restrict__ peers) {
+    __shared__ uint32_t epoch;
+    if (threadIdx.x == 0) epoch = ++peers->flags[peers->rank][kMaxWorld];
+    __syncthreads();
+    if ((int)threadIdx.x < peers->world) {
+        __threadfence_system();
+        volatile uint32_t* dst = peers->flags[threadIdx.x] + peers->rank;
         *dst = epoch;
-        volatile uint32_t* src = a.local + threadIdx.x;
-        while ((int32_t)(*src - epoch) < 0) { }
-        __threadfence_system();
     }
 }
 
@@ -287,11 +387,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     float* d_added = e->d_partials.p + 3 * (size_t)nblocks;       // 3 floats after the partials
     if (world > 1 && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
     const bool p2p = world > 1 && e->peers.ready;
-    BarrierArgs bar{};
-    if (p2p) {
-        bar.local = e->peers.d_flags.p; bar.world = world; bar.rank = e->cfg.rank;
-        for (int r = 0; r < world; r++) bar.peer[r] = e->peers.flags[r];
-    }
+    const PeerTable* d_peers = p2p ? e->peers.d_table.p : nullptr;
 
     timing_begin(e);
     int launches = 0;
@@ -304,20 +400,23 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     int cur = 0, done = 0;
     float h_added[3] = {0.f, 0.f, 0.f};
     static const bool verbose = getenv("VRAD_TIMING") != nullptr;
+    bool pending_wait = false;      // a peer signal was sent that no gather prologue has waited for yet
     constexpr int kProbe = 16;
     cudaEvent_t pe[kProbe][3];
     int n_probe = 0;
     for (int b = 0; b < n_bounces; b++) {
         const bool probe = verbose && b >= 4 && n_probe < kProbe;
         if (probe) { for (int k = 0; k < 3; k++) cudaEventCreate(&pe[n_probe][k]); cudaEventRecord(pe[n_probe][0], e->stream); }
-        GatherTargets tg{};
-        if (p2p) { tg.n = world; for (int r = 0; r < world; r++) tg.dst[r] = e->peers.er[cur ^ 1][r]; }
-        else { tg.n = 1; tg.dst[0] = e->d_er[cur ^ 1].p; }
-        k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p,
-                                                         e->d_er[cur].p, e->patches.refl.p, tg, total_local, e->d_partials.p);
+        if (p2p)    // pending_wait false: nothing outstanding, the buffer read was initialised locally
+            k4_gather_multi<true><<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
+                                                                   e->d_er[cur ^ 1].p, total_local, e->d_partials.p, d_peers, cur ^ 1, pending_wait ? world : 0);
+        else
+            k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
+                                                             e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
         launches++;
+        pending_wait = false;
         if (probe) cudaEventRecord(pe[n_probe][1], e->stream);
-        if (p2p) { k4_peer_barrier<<<1, 32, 0, e->stream>>>(bar); launches++; }
+        if (p2p) { k4_peer_signal<<<1, 32, 0, e->stream>>>(d_peers); launches++; pending_wait = true; }
         else if (world > 1 && (rc = comm_allgather_f4(e, e->d_er[cur ^ 1].p, (size_t)rpr))) return rc;
         if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
         cur ^= 1; done++;
@@ -333,6 +432,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             if (h_added[0] < 1.0f && h_added[1] < 1.0f && h_added[2] < 1.0f) break;
         }
     }
+    if (pending_wait) { k4_peer_wait<<<1, 32, 0, e->stream>>>(d_peers); launches++; }
     if (world > 1 && (rc = comm_allgather_f4(e, e->d_total.p, (size_t)rpr))) return rc;
     if (d_out3) {
         k4_unpack_total<<<(int)((N + 255) / 256), 256, 0, e->stream>>>(N, e->d_total.p, (float*)d_out3);
