@@ -10,7 +10,8 @@ One JSON line on rank 0.  Top level = BASELINE.json's first metric, shadow rays/
   e2e      = the same call with pinned HOST buffers (H2D of the segments + D2H of the bits inside the timing).
   roofline = K1's algorithmic HBM bytes (24.125 B/segment) / CUDA-event time vs the measured HBM peak.
 `gather` = BASELINE.json's second metric, bounce-gather iters/sec (C4: S2 multi-room map, 100 bounces per
-step through K4, patch rows sharded over the ranks, NCCL all-gather per bounce; strong scaling), with its own
+step through K4, patch rows sharded over the ranks, radiance rows exchanged by peer stores fused into the
+kernel (NCCL all-gather fallback); strong scaling), with its own
 roofline (8*nnz + 40*N bytes per iteration), e2e and cpu_baseline.
 `cpu_baseline` = the CPU oracle (a port: the Go reference cannot be built or run, and its tracer is a stub)
 timed on this box's host cores on a bounded sample of the same workload.
@@ -355,8 +356,10 @@ def run_graft(args, rank, local_rank, world):
         "e2e": {"value": rays_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
         "gpu_launches": ray_launches,
         "roofline": {"bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
-                     "traffic": None, "kernel": "k1_test_lines", "peak_source": peak_src,
-                     "note": "K1 is latency/divergence-bound by design (SURVEY 8d); the binding target is >=1e9 rays/s"},
+                     "traffic": 425.8e6, "traffic_source": "profiles/r01_final_k1_ncu_summary.txt (dram read+write per launch)",
+                     "kernel": "k1_test_lines", "peak_source": peak_src,
+                     "note": "K1 is issue/divergence-bound by design (SURVEY 8d: HBM fraction ~1%); the binding target is >=1e9 rays/s. "
+                             "The HBM-bound kernel of this path is k4_gather: see gather.roofline"},
         "cpu_baseline": cpu_rays_obj,
         "clocks": clocks,
         "gather": {
@@ -368,7 +371,10 @@ def run_graft(args, rank, local_rank, world):
             "e2e": {"value": gather_e2e, "unit": "iters/s", "h2d_bytes_per_step": 12 * N, "d2h_bytes_per_step": 12 * N},
             "gpu_launches": bounce_launches * g_steps,
             "roofline": {"bound": "hbm", "achieved": gather_gbs_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": gather_gbs_gpu / hbm_peak,
-                         "traffic": None, "kernel": "k4_gather", "bytes_per_iter_per_gpu": bytes_per_iter_gpu, "peak_source": peak_src},
+                         "traffic": 1.5537e9 if world == 1 else None,
+                         "traffic_source": "profiles/r01_final_k2_k3_k4_ncu_summary.txt (dram read+write per launch, N=1)",
+                         "kernel": "k4_gather", "bytes_per_iter_per_gpu": bytes_per_iter_gpu, "peak_source": peak_src,
+                         "exchange": "none" if world == 1 else "peer stores into every rank's next-bounce buffer (NVLink, CUDA IPC) + epoch barrier; NCCL all-gather fallback"},
             "job_gbs": bytes_per_iter_job * iters / (gather_ms * 1e-3) / 1e9,
             "cpu_baseline": cpu_gather_obj,
             "transfer_build": {"wall_s": k2_s, "kernel_ms": k2_ms, "launches": k2_launches, "nnz_local_rank0": nnz_local},
