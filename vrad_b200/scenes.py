@@ -353,3 +353,87 @@ def random_rays(scene: Scene, n: int, seed: int = 0xBEEF) -> dict:
     d = np.stack([r * np.cos(phi), r * np.sin(phi), z]).astype(np.float32)
     return {"o": np.ascontiguousarray(o), "d": np.ascontiguousarray(d),
             "tmax": np.full(n, MAX_TRACE_LENGTH, np.float32)}
+
+
+def _value_noise(rng: SplitMix64, n: int, octaves=((64, 600.0), (16, 160.0), (4, 30.0))) -> np.ndarray:
+    """Deterministic value noise on an (n+1) x (n+1) vertex grid: bilinear interpolation of random lattices."""
+    h = np.zeros((n + 1, n + 1), np.float64)
+    xs = np.arange(n + 1, dtype=np.float64)
+    for cell, amp in octaves:
+        m = n // cell + 2
+        lat = rng.uniform(m * m).astype(np.float64).reshape(m, m)
+        g = xs / cell
+        i0 = np.floor(g).astype(np.int64); f = g - i0
+        f = f * f * (3 - 2 * f)
+        a = lat[i0][:, i0]; b = lat[i0 + 1][:, i0]; c = lat[i0][:, i0 + 1]; d = lat[i0 + 1][:, i0 + 1]
+        fx, fy = f[:, None], f[None, :]
+        h += amp * ((a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy)
+    return h
+
+
+def outdoor(seed: int = 0x5EED0003, cells: int = 708, cell: float = 46.0, n_buildings: int = 2000, patch_split: int = 2) -> Scene:
+    """S3 (config C5): value-noise heightfield (cells x cells x 2 triangles), box 'buildings' standing on it and a
+    TRACE_ID_SKY box around everything; one leaf patch per heightfield cell quarter; sun + sky-ambient lights."""
+    rng = SplitMix64(seed)
+    n = cells
+    ext = n * cell
+    h = _value_noise(rng, n)
+    h -= h.min()
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    x0 = (ii * cell - ext / 2).ravel(); y0 = (jj * cell - ext / 2).ravel()
+    z00 = h[ii, jj].ravel(); z10 = h[ii + 1, jj].ravel(); z01 = h[ii, jj + 1].ravel(); z11 = h[ii + 1, jj + 1].ravel()
+    x1, y1 = x0 + cell, y0 + cell
+    # two triangles per cell, same fan order as AddQuad: (v1,v2,v3), (v1,v3,v4)
+    t1 = np.stack([x0, y0, z00, x1, y0, z10, x1, y1, z11], axis=1)
+    t2 = np.stack([x0, y0, z00, x1, y1, z11, x0, y1, z01], axis=1)
+    terrain = np.empty((2 * n * n, 9), np.float32)
+    terrain[0::2] = t1; terrain[1::2] = t2
+    g = _Geom()
+    bi = rng.integers(n_buildings, n - 8) + 4; bj = rng.integers(n_buildings, n - 8) + 4
+    bs = rng.uniform(3 * n_buildings, 0.0, 1.0).reshape(n_buildings, 3)
+    for k in range(n_buildings):
+        cx = bi[k] * cell - ext / 2; cy = bj[k] * cell - ext / 2
+        base = float(h[bi[k]:bi[k] + 4, bj[k]:bj[k] + 4].min()) - 8.0
+        w, d, hh = 60 + 120 * bs[k, 0], 60 + 120 * bs[k, 1], 120 + 500 * bs[k, 2]
+        g.add_box(TRACE_ID_OPAQUE, (cx, cy, base), (cx + w, cy + d, base + hh))
+    zmax = float(h.max()) + 1200.0
+    g.add_box(TRACE_ID_SKY, (-ext / 2 - 64, -ext / 2 - 64, -64.0), (ext / 2 + 64, ext / 2 + 64, zmax))
+    bids, bverts, _ = g.arrays()
+    ids = np.concatenate([np.full(terrain.shape[0], TRACE_ID_OPAQUE, np.int32), bids])
+    verts = np.concatenate([terrain, bverts])
+    flags = np.zeros(ids.shape[0], np.uint8)
+    # leaf patches: patch_split x patch_split per cell, on the cell's bilinear surface, lifted along the cell normal
+    s = patch_split
+    u = (np.arange(s) + 0.5) / s
+    uu, vv = np.meshgrid(u, u, indexing="ij")
+    uu = uu.ravel()[None, :]; vv = vv.ravel()[None, :]
+    px = x0[:, None] + uu * cell; py = y0[:, None] + vv * cell
+    pz = (z00[:, None] * (1 - uu) * (1 - vv) + z10[:, None] * uu * (1 - vv) + z01[:, None] * (1 - uu) * vv + z11[:, None] * uu * vv)
+    nx = -(z10 - z00 + z11 - z01) / (2 * cell); ny = -(z01 - z00 + z11 - z10) / (2 * cell)
+    nrm = np.stack([nx, ny, np.ones_like(nx)], axis=1); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    normal = np.repeat(nrm, s * s, axis=0).astype(np.float32)
+    centres = np.stack([px.ravel(), py.ravel(), pz.ravel()], axis=1)
+    origin = (centres + normal.astype(np.float64)).astype(np.float32)
+    plane_dist = np.einsum("ij,ij->i", normal.astype(np.float64), centres).astype(np.float32)
+    N = origin.shape[0]
+    area = np.full(N, (cell / s) ** 2, np.float32)
+    refl = np.minimum(rng.uniform(3 * N, 0.2, 0.6).reshape(N, 3), np.float32(0.99)).astype(np.float32)
+    # clusters: 32x32-cell tiles; PVS = tiles within Chebyshev distance 1 (a far clip, like a real map's vis)
+    tile = 32
+    nt = (n + tile - 1) // tile
+    cluster_cell = (ii // tile * nt + jj // tile).ravel().astype(np.int32)
+    cluster = np.repeat(cluster_cell, s * s)
+    pvs = np.zeros((nt * nt, nt * nt), np.uint8)
+    for a in range(nt):
+        for b in range(nt):
+            for da in (-1, 0, 1):
+                for db in (-1, 0, 1):
+                    if 0 <= a + da < nt and 0 <= b + db < nt:
+                        pvs[a * nt + b, (a + da) * nt + (b + db)] = 1
+    lights = np.zeros(2, dtype=LIGHT_DTYPE)
+    sun = np.array([-0.4, -0.3, -0.87]); sun /= np.linalg.norm(sun)
+    lights["start_fade"], lights["end_fade"], lights["cap_dist"] = 0.0, -1.0, 1.0e22
+    lights[0]["type"] = EMIT_SKYLIGHT; lights[0]["normal"] = sun.astype(np.float32); lights[0]["intensity"] = (300.0, 280.0, 250.0)
+    lights[1]["type"] = EMIT_SKYAMBIENT; lights[1]["intensity"] = (40.0, 50.0, 70.0)
+    return Scene("S3_outdoor", ids, verts, flags, origin, normal, plane_dist, area, refl, cluster, np.zeros(N, np.uint8),
+                 nt * nt, pvs, origin, normal, lights, {"seed": seed, "cells": cells, "n_buildings": n_buildings})
