@@ -15,7 +15,7 @@ def ev_time(fn, iters=5, warm=2):
     return min(ts), float(np.median(ts))
 
 which = sys.argv[1] if len(sys.argv) > 1 else "s1"
-scene = scenes.box_room() if which == "s1" else scenes.multi_room()
+scene = scenes.box_room() if which == "s1" else (scenes.multi_room() if which == "s2" else scenes.outdoor())
 t = time.time(); env = environment_from_scene(scene); print("build+upload s", time.time() - t, env.stats())
 env.set_stream(torch.cuda.current_stream().cuda_stream); env.set_async(True)
 n = 1 << 24
@@ -29,6 +29,8 @@ to, td, tm = torch.from_numpy(r["o"]).cuda(), torch.from_numpy(r["d"]).cuda(), t
 outs = (torch.empty(1 << 22, dtype=torch.int32, device="cuda"), torch.empty(1 << 22, dtype=torch.int32, device="cuda"), torch.empty(1 << 22, dtype=torch.float32, device="cuda"))
 best, med = ev_time(lambda: env.trace_rays(to, td, tm, out=outs))
 print(f"trace_rays random {which}: {(1<<22)/best/1e6:.1f} Mrays/s best ({best:.3f} ms)")
+if which == "s3":
+    sys.exit(0)
 # K2 + K4
 env.set_async(False)
 env.build_transfers(scene.pvs)

@@ -40,6 +40,24 @@ __device__ __forceinline__ float min_sel(float a, float b) { return a < b ? a : 
 __device__ __forceinline__ float max_sel(float a, float b) { return a > b ? a : b; }
 __device__ __forceinline__ float pick3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
 
+// Axis selects of the node step as predicated selects.  Written in PTX because nvcc turned the ternary
+// chains into a three-way divergent branch inside the traversal loop (ncu r01 v3: BSSY/BSYNC pair run
+// 45 M times at 4-7 active lanes).
+__device__ __forceinline__ void pick_axis(int axis, float ox, float oy, float oz, float ix, float iy, float iz,
+                                          float& o, float& inv) {
+    asm("{\n\t"
+        ".reg .pred p1, p2;\n\t"
+        "setp.eq.s32 p1, %8, 1;\n\t"
+        "setp.eq.s32 p2, %8, 2;\n\t"
+        "selp.f32 %0, %3, %2, p1;\n\t"
+        "selp.f32 %0, %4, %0, p2;\n\t"
+        "selp.f32 %1, %6, %5, p1;\n\t"
+        "selp.f32 %1, %7, %1, p2;\n\t"
+        "}"
+        : "=&f"(o), "=&f"(inv)
+        : "f"(ox), "f"(oy), "f"(oz), "f"(ix), "f"(iy), "f"(iz), "r"(axis));
+}
+
 struct Ray {
     float ox, oy, oz, dx, dy, dz;
 };
@@ -99,8 +117,8 @@ struct Traversal {
                 const int axis = nd.x & 3;
                 const int left = nd.x >> 2;
                 const int ng = (neg >> axis) & 1;
-                const float o = pick3(axis, r.ox, r.oy, r.oz);
-                const float inv = pick3(axis, ix, iy, iz);
+                float o, inv;
+                pick_axis(axis, r.ox, r.oy, r.oz, ix, iy, iz, o, inv);
                 const float t = (__int_as_float(nd.y) - o) * inv;
                 const int front = left + ng, back = left + (ng ^ 1);
                 const bool back_only = !(t >= tmin);
@@ -133,10 +151,14 @@ struct Traversal {
                 const float4 a = __ldg(&S.q0[ti]);
                 const float ddotn = ((r.dx * a.x) + (r.dy * a.y)) + (r.dz * a.z);
                 const float odotn = ((r.ox * a.x) + (r.oy * a.y)) + (r.oz * a.z);
-                const float t = (a.w - odotn) / ddotn;
-                const bool facing = ddotn > kDdotNEps || ddotn < -kDdotNEps;
-                const bool better = ANY_HIT ? (t < any_len) : (t < hit_t || (t == hit_t && ti < hit_tri));
-                if (facing && t > 0.0f && better) { cand = ti; tc = t; break; }
+                const float num = a.w - odotn;
+                // sign pre-filter (exact: t > 0 needs num and ddotn of one sign, both non-zero) keeps
+                // back-facing and parallel planes off the IEEE divider and its slow path
+                if ((ddotn > kDdotNEps && num > 0.0f) || (ddotn < -kDdotNEps && num < 0.0f)) {
+                    const float t = num / ddotn;
+                    const bool better = ANY_HIT ? (t < any_len) : (t < hit_t || (t == hit_t && ti < hit_tri));
+                    if (t > 0.0f && better) { cand = ti; tc = t; break; }
+                }
             }
             if (!__any_sync(0xffffffffu, cand >= 0)) break;
             if (cand >= 0) {
