@@ -6,8 +6,8 @@ from vrad_b200 import scenes
 from vrad_b200.environment import environment_from_scene
 
 what = sys.argv[1] if len(sys.argv) > 1 else "k1"
-if what == "k1":
-    s = scenes.box_room(); env = environment_from_scene(s, with_patches=False)
+if what in ("k1", "k1s3"):
+    s = scenes.box_room() if what == "k1" else scenes.outdoor(); env = environment_from_scene(s, with_patches=False)
     a, b = scenes.shadow_segments(s, 1 << 24)
     ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     out = torch.empty((1 << 24) // 32, dtype=torch.int32, device="cuda")

@@ -7,9 +7,9 @@
 //
 // Work decomposition: one thread per (luxel, light) pair computes that pair's scalar
 // `falloff * dot * visibility` (rays generated on the device: 36 B of HBM traffic per luxel for
-// n_lights rays); sky-ambient lights use one warp per luxel with lanes over the sample
-// directions; a final pass accumulates RGB per luxel in light order, which keeps the sum
-// bit-identical to the sequential CPU formulation.
+// n_lights rays); sky-ambient lights use one thread per luxel with the warp walking the sample
+// directions together (parallel rays per round); a final pass accumulates RGB per luxel in light
+// order, which keeps the sum bit-identical to the sequential CPU formulation.
 #include "env_internal.cuh"
 
 namespace vrad {
@@ -102,40 +102,35 @@ k3_pair_scale(DevScene S, int64_t n_luxels, int n_lights, const float* __restric
     }
 }
 
-// one warp per luxel: lanes over the sample directions; lane 0 then replays the sum in direction order
+// Sky ambient: one thread per luxel, the warp walks the sample directions together -- in every round the 32
+// lanes trace PARALLEL rays from neighbouring luxels, which traverse the same nodes (a warp per luxel
+// with lanes over the 162 directions fans out over the whole hemisphere and ran at 0.8 G rays/s on the
+// 1 M-triangle map against 3.2 G rays/s for the parallel sun rays).  Each lane accumulates its own luxel
+// in direction order, i.e. exactly the sequential CPU sum.
 __global__ void __launch_bounds__(128)
 k3_sky_ambient(DevScene S, int64_t n_luxels, int n_lights, int light_index, int n_dirs, const float* __restrict__ dirs3,
                const float* __restrict__ pos3, const float* __restrict__ nrm3, float* __restrict__ scale_out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < n_luxels; i += nwarps) {
-        const float px = pos3[3 * i], py = pos3[3 * i + 1], pz = pos3[3 * i + 2];
-        const float nx = nrm3[3 * i], ny = nrm3[3 * i + 1], nz = nrm3[3 * i + 2];
-        float sum = 0.0f, possible = 0.0f;
-        for (int base = 0; base < n_dirs; base += 32) {
-            const int k = base + lane;
-            float ax = 0.f, ay = 0.f, az = 1.f;
-            bool want = false;
-            if (k < n_dirs) {
-                ax = dirs3[3 * k]; ay = dirs3[3 * k + 1]; az = dirs3[3 * k + 2];
-                want = dot3(ax, ay, az, nx, ny, nz) > kEqualEpsilon;
-            }
-            const int vis = segment_visible(S, want, px, py, pz, px + (ax * kMaxTraceLength), py + (ay * kMaxTraceLength),
-                                            pz + (az * kMaxTraceLength), 1) && want;
-            const uint32_t m = __ballot_sync(0xffffffffu, vis);
-            if (lane == 0) {
-                const int cnt = min(32, n_dirs - base);
-                for (int b = 0; b < cnt; b++) {
-                    const int kk = base + b;
-                    const float dot = dot3(dirs3[3 * kk], dirs3[3 * kk + 1], dirs3[3 * kk + 2], nx, ny, nz);
-                    if (!(dot > kEqualEpsilon)) continue;
-                    possible = possible + dot;
-                    if ((m >> b) & 1u) sum = sum + dot;
-                }
-            }
+    const int64_t n_pad = (n_luxels + 31) & ~(int64_t)31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        const bool in_range = i < n_luxels;
+        float px = 0.f, py = 0.f, pz = 0.f, nx = 0.f, ny = 0.f, nz = 1.f;
+        if (in_range) {
+            px = pos3[3 * i]; py = pos3[3 * i + 1]; pz = pos3[3 * i + 2];
+            nx = nrm3[3 * i]; ny = nrm3[3 * i + 1]; nz = nrm3[3 * i + 2];
         }
-        if (lane == 0) scale_out[i * n_lights + light_index] = possible > 0.0f ? sum / possible : 0.0f;
+        float sum = 0.0f, possible = 0.0f;
+        for (int k = 0; k < n_dirs; k++) {
+            const float ax = __ldg(&dirs3[3 * k]), ay = __ldg(&dirs3[3 * k + 1]), az = __ldg(&dirs3[3 * k + 2]);
+            const float dot = dot3(ax, ay, az, nx, ny, nz);
+            const bool want = in_range && dot > kEqualEpsilon;
+            if (!__any_sync(0xffffffffu, want)) continue;
+            if (want) possible = possible + dot;
+            const int vis = segment_visible(S, want, px, py, pz, px + (ax * kMaxTraceLength), py + (ay * kMaxTraceLength),
+                                            pz + (az * kMaxTraceLength), 1);
+            if (want && vis) sum = sum + dot;
+        }
+        if (in_range) scale_out[i * n_lights + light_index] = possible > 0.0f ? sum / possible : 0.0f;
     }
 }
 
@@ -206,7 +201,7 @@ int vrad_direct_light(vrad_env* e, int64_t n_luxels, const float* pos3, const fl
         launches++;
         for (int L = 0; L < n_lights; L++) {
             if (hl[L].type != 5) continue;
-            int64_t b2 = (n_luxels * 32 + 127) / 128;
+            int64_t b2 = (n_luxels + 127) / 128;
             k3_sky_ambient<<<(int)(b2 < cap ? b2 : cap), 128, 0, e->stream>>>(e->scene, n_luxels, n_lights, L, e->n_sky_dirs, e->d_sky_dirs.p,
                                                                            (const float*)d_pos, (const float*)d_nrm, (float*)d_scale);
             launches++;
