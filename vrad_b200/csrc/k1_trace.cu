@@ -64,8 +64,8 @@ k1_trace_rays(DevScene S, int64_t n, const float* __restrict__ ox, const float* 
         const int64_t base = chunk * kRaysPerWarp;
         const int64_t end = base + kRaysPerWarp < n ? base + kRaysPerWarp : n;
         auto fetch = [&](int64_t i, Ray& r, float& t0, float& t1, float& len) {
-            r = Ray{ox[i], oy[i], oz[i], dx[i], dy[i], dz[i]};
-            t0 = tmin ? tmin[i] : 0.0f; t1 = tmax[i]; len = 0.0f;
+            r = Ray{__ldcs(&ox[i]), __ldcs(&oy[i]), __ldcs(&oz[i]), __ldcs(&dx[i]), __ldcs(&dy[i]), __ldcs(&dz[i])};   // streamed once
+            t0 = tmin ? __ldcs(&tmin[i]) : 0.0f; t1 = __ldcs(&tmax[i]); len = 0.0f;
             return true;
         };
         auto retire = [&](int64_t i, int tri, float t, float) {
@@ -98,7 +98,8 @@ k1_test_lines(DevScene S, int64_t n, int64_t stride, const float* __restrict__ a
         auto fetch = [&](int64_t i, Ray& r, float& t0, float& t1, float& len) {
             t0 = 0.0f;
             r = Ray{0.f, 0.f, 0.f, 1.f, 1.f, 1.f}; len = 0.0f;
-            const bool ok = segment_to_ray(a[i], a[stride + i], a[2 * stride + i], b[i], b[stride + i], b[2 * stride + i], r, len);
+            const bool ok = segment_to_ray(__ldcs(&a[i]), __ldcs(&a[stride + i]), __ldcs(&a[2 * stride + i]),
+                                           __ldcs(&b[i]), __ldcs(&b[stride + i]), __ldcs(&b[2 * stride + i]), r, len);   // streamed once
             t1 = len;
             return ok;
         };
