@@ -319,6 +319,46 @@ def run_graft(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
+    # ---------------- C5 side numbers (rank 0, N=1 only; informational, outside every timed region above) ----------------
+    large = None
+    if world == 1 and not args.no_large:
+        try:
+            s3 = scenes.outdoor()
+            env3 = environment_from_scene(s3, device=local_rank, with_patches=False)
+            env3.set_stream(stream)
+            env3.set_async(True)
+            n3 = 1 << 22
+            a3, b3 = scenes.shadow_segments(s3, n3, seed=0xC5)
+            d_a3, d_b3 = torch.from_numpy(a3).to(dev), torch.from_numpy(b3).to(dev)
+            d_bits3 = torch.empty(n3 // 32, dtype=torch.int32, device=dev)
+            for _ in range(2):
+                env3.test_lines(d_a3, d_b3, out=d_bits3)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                env3.test_lines(d_a3, d_b3, out=d_bits3)
+            e1.record(); torch.cuda.synchronize()
+            seg_ms = e0.elapsed_time(e1) / 3
+            dirs = np.loadtxt(os.path.join(ROOT, "vrad_b200", "data", "anorms.txt"), dtype=np.float32)
+            env3.set_sky_dirs(dirs)
+            env3.set_async(False)
+            d_pos, d_nrm = torch.from_numpy(s3.luxel_pos).to(dev), torch.from_numpy(s3.luxel_normal).to(dev)
+            d_rgb = torch.empty((d_pos.shape[0], 3), device=dev)
+            env3.direct_light(d_pos, d_nrm, s3.lights, out=d_rgb)
+            env3.direct_light(d_pos, d_nrm, s3.lights, out=d_rgb)
+            k3_ms, k3_launches = env3.last_timing()
+            up = float((dirs @ s3.luxel_normal[::97].T > 0.001).sum()) / s3.luxel_normal[::97].shape[0]
+            st3 = env3.stats()
+            large = {"workload": "C5: S3 outdoor map (1,026,540 tris, 2,005,056 luxels/patches), informational",
+                     "kd_build_seconds_host": st3["build_seconds"], "kd_nodes": st3["n_nodes"],
+                     "shadow_segments_per_sec": n3 / (seg_ms * 1e-3), "segments": n3,
+                     "direct_light_ms": k3_ms, "direct_light_rays_per_sec": d_pos.shape[0] * (1 + up) / (k3_ms * 1e-3),
+                     "direct_light_lights": "sun (EMIT_SKYLIGHT) + sky ambient over 162 directions"}
+            env3.close()
+            del d_a3, d_b3, d_pos, d_nrm, d_rgb
+        except Exception as exc:   # side numbers must never take the headline down
+            large = {"error": str(exc)}
+
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     cpu_rays_obj, cpu_gather_obj = None, None
     if world == 1 and not args.no_cpu:
@@ -362,6 +402,7 @@ def run_graft(args, rank, local_rank, world):
                              "The HBM-bound kernel of this path is k4_gather: see gather.roofline"},
         "cpu_baseline": cpu_rays_obj,
         "clocks": clocks,
+        "large_scene": large,
         "gather": {
             "metric": "bounce_gather_iters_per_sec", "value": gather_value, "unit": "iters/s", "scaling": "strong",
             "steps": g_steps, "bounces_per_step": N_BOUNCES, "ms_per_iter": gather_ms / iters,
@@ -393,6 +434,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-large", action="store_true", help="skip the informational C5 (S3 map) side numbers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
     rank, local_rank, world = dist_setup(args)

@@ -39,13 +39,6 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
-// A caller pointer staged for device use: device pointers pass through, host pointers are
-// copied into a scratch buffer on the handle's stream.
-struct Staged {
-    const void* dev = nullptr;
-    bool was_host = false;
-};
-
 struct PatchesDev {
     int n = 0;
     DevBuf<float4> origin_area;     // origin.xyz, area
@@ -123,7 +116,6 @@ struct vrad_env {
 
     // scratch for staging host pointers
     std::vector<vrad::DevBuf<unsigned char>> scratch;
-    size_t scratch_used = 0;
 
     vrad::PatchesDev patches;
     vrad::TransfersDev transfers;
@@ -145,6 +137,8 @@ int stage_in(vrad_env* e, int slot, const void* p, size_t bytes, const void** de
 // returns a device pointer to write results into; if `p` is host memory a scratch buffer is used
 int stage_out(vrad_env* e, int slot, void* p, size_t bytes, void** dev_out, bool* was_host);
 int finish_out(vrad_env* e, void* host_p, const void* dev_p, size_t bytes, bool was_host);
+// plain device scratch of `bytes` in slot `slot` (grown on demand, owned by the handle)
+int scratch_get(vrad_env* e, int slot, size_t bytes, void** out);
 void timing_begin(vrad_env* e);
 void timing_end(vrad_env* e, int launches);
 int sync_if_needed(vrad_env* e, bool any_host);

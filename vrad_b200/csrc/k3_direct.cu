@@ -187,9 +187,9 @@ int vrad_direct_light(vrad_env* e, int64_t n_luxels, const float* pos3, const fl
     if ((rc = stage_in(e, 2, hl.data(), sizeof(vrad_light) * hl.size(), &d_l, &h2))) return rc;
     void* d_rgb;
     if ((rc = stage_out(e, 3, rgb_out, (size_t)n_luxels * 12, &d_rgb, &ho))) return rc;
-    void* d_scale; bool hs;
+    void* d_scale;                       // per-(luxel, light) scalar falloff*dot*visibility
     const size_t nscale = (size_t)n_luxels * (n_lights ? n_lights : 1);
-    if ((rc = stage_out(e, 4, (void*)hl.data() /*force scratch*/, nscale * 4, &d_scale, &hs))) return rc;
+    if ((rc = scratch_get(e, 4, nscale * 4, &d_scale))) return rc;
     timing_begin(e);
     int launches = 0;
     if (n_lights) {

@@ -23,7 +23,7 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-static int scratch_get(vrad_env* e, int slot, size_t bytes, void** out) {
+int scratch_get(vrad_env* e, int slot, size_t bytes, void** out) {
     if ((size_t)slot >= e->scratch.size()) e->scratch.resize(slot + 1);
     if (e->scratch[slot].alloc(bytes ? bytes : 1) != 0) { set_error("out of device memory (%zu bytes)", bytes); return VRAD_E_NOMEM; }
     *out = e->scratch[slot].p;
@@ -107,6 +107,8 @@ static int upload_scene(vrad_env* e) {
 
 using namespace vrad;
 
+extern "C" void vrad_comm_destroy_internal(vrad_env*);   // comm.cu
+
 extern "C" {
 
 const char* vrad_last_error(void) { return g_err; }
@@ -149,7 +151,6 @@ void vrad_env_destroy(vrad_env* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
-    extern void vrad_comm_destroy_internal(vrad_env*);
     vrad_comm_destroy_internal(e);
     e->d_nodes.release(); e->d_tri_index.release(); e->d_q0.release(); e->d_q1.release(); e->d_q2.release();
     for (auto& s : e->scratch) s.release();
