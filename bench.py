@@ -354,8 +354,18 @@ def run_graft(args, rank, local_rank, world):
                      "shadow_segments_per_sec": n3 / (seg_ms * 1e-3), "segments": n3,
                      "direct_light_ms": k3_ms, "direct_light_rays_per_sec": d_pos.shape[0] * (1 + up) / (k3_ms * 1e-3),
                      "direct_light_lights": "sun (EMIT_SKYLIGHT) + sky ambient over 162 directions"}
+            env3.patches_upload(s3.patch_origin, s3.patch_normal, s3.patch_plane_dist, s3.patch_area, s3.patch_refl, s3.patch_cluster, s3.patch_flags)
+            t0 = time.perf_counter(); nnz3 = env3.build_transfers(s3.pvs); torch.cuda.synchronize(); k2_s3 = time.perf_counter() - t0
+            e30 = torch.full((s3.n_patches, 3), 100.0, device=dev); o30 = torch.empty_like(e30)
+            env3.set_async(True)
+            env3.bounce(e30, 2, out=o30, want_added=False)
+            e0.record(); env3.bounce(e30, 10, out=o30, want_added=False); e1.record(); torch.cuda.synchronize()
+            k4_ms3 = e0.elapsed_time(e1) / 10
+            large.update({"transfer_build_seconds": k2_s3, "transfers": nnz3, "transfer_bytes": 8 * nnz3,
+                          "gather_ms_per_bounce": k4_ms3, "gather_gbs": (8 * nnz3 + 40 * s3.n_patches) / (k4_ms3 * 1e-3) / 1e9,
+                          "gather_frac_of_hbm_peak": (8 * nnz3 + 40 * s3.n_patches) / (k4_ms3 * 1e-3) / 1e9 / hbm_peak})
             env3.close()
-            del d_a3, d_b3, d_pos, d_nrm, d_rgb
+            del d_a3, d_b3, d_pos, d_nrm, d_rgb, e30, o30
         except Exception as exc:   # side numbers must never take the headline down
             large = {"error": str(exc)}
 

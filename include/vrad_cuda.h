@@ -139,6 +139,10 @@ int  vrad_build_transfers(vrad_env*, int n_clusters, const uint8_t* pvs, int64_t
 int  vrad_transfers_upload(vrad_env*, int64_t row0, int64_t row1, const int64_t* rowptr, const int32_t* col, const float* w);
 int  vrad_transfers_info(vrad_env*, int64_t* row0, int64_t* row1, int64_t* nnz);
 int  vrad_transfers_download(vrad_env*, int64_t* rowptr, int32_t* col, float* w);
+/* rows [row_begin,row_end) of the resident lists (global row numbers, must be owned by this rank): rowptr gets
+ * row_end-row_begin+1 offsets starting at 0; col/w must hold `capacity` entries (VRAD_E_INVALID if too small).
+ * For matrices too large to download whole (C5: 5.7e9 transfers). */
+int  vrad_transfers_download_rows(vrad_env*, int64_t row_begin, int64_t row_end, int64_t* rowptr, int32_t* col, float* w, int64_t capacity);
 /* sky-ambient sample directions (vmath.Anorms, vmath/constants.go:15,21-184) */
 int  vrad_set_sky_dirs(vrad_env*, int n, const float* dirs3);
 /* per-luxel direct lighting with shadow rays (north_star K3; light parameters per vrad_light) */

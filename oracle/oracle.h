@@ -112,6 +112,8 @@ int  orc_patches_set(orc_env*, int n, const float* origin3, const float* normal3
 /* K2: builds CSR transfers.  pvs: n_clusters x n_clusters bytes (nonzero = visible) or NULL. */
 int  orc_build_transfers(orc_env*, int n_clusters, const uint8_t* pvs, int64_t* nnz_out, int threads);
 int  orc_transfers_get(orc_env*, int64_t* rowptr, int32_t* col, float* w);
+/* one row (incl. MakeScales) for spot checks on maps whose full matrix is too large for the CPU; returns the entry count */
+int64_t orc_transfer_row(orc_env*, int row, int n_clusters, const uint8_t* pvs, int32_t* col_out, float* w_out, int64_t cap);
 /* sky-ambient sample directions (the 162 `Anorms`, vmath/constants.go:15,21-184), copied */
 int  orc_set_sky_dirs(int n, const float* dirs3);
 /* K3: direct light per luxel; rgb_out 3 floats per luxel */

@@ -159,6 +159,16 @@ class OracleEnv:
         assert self._l.orc_transfers_get(self._h, _p(rowptr), _p(col), _p(w)) == 0
         return rowptr, col, w
 
+    def transfer_row(self, i, pvs=None, cap=1 << 20):
+        nc = 0
+        if pvs is not None:
+            pvs = np.ascontiguousarray(pvs, np.uint8); nc = pvs.shape[0]
+        col = np.empty(cap, np.int32); w = np.empty(cap, np.float32)
+        self._l.orc_transfer_row.restype = C.c_int64
+        n = self._l.orc_transfer_row(self._h, C.c_int(int(i)), C.c_int(nc), _p(pvs), _p(col), _p(w), C.c_int64(cap))
+        assert n >= 0
+        return col[:n].copy(), w[:n].copy()
+
     def set_sky_dirs(self, dirs3):
         d = _f32(dirs3).reshape(-1, 3)
         assert self._l.orc_set_sky_dirs(C.c_int(d.shape[0]), _p(d)) == 0

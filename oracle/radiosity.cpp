@@ -110,6 +110,31 @@ int orc_build_transfers(orc_env* e, int n_clusters, const uint8_t* pvs, int64_t*
     return 0;
 }
 
+// one row of the transfer matrix (same rule as orc_build_transfers incl. MakeScales), for spot checks on maps whose
+// full matrix is too large for the CPU (C5).  Returns the number of entries, or -1 if `cap` is too small.
+int64_t orc_transfer_row(orc_env* e, int i, int n_clusters, const uint8_t* pvs, int32_t* col_out, float* w_out, int64_t cap) {
+    if (!e || !e->built) return -1;
+    const Patches& P = e->patches;
+    if (i < 0 || i >= P.n) return -1;
+    std::vector<int32_t> cols; std::vector<float> ws;
+    if (!(P.flags[i] & 1)) {
+        for (int j = 0; j < P.n; j++) {
+            if (j == i) continue;
+            if (pvs && !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[j]]) continue;
+            float tr = transfer_weight(P, i, j);
+            if (tr == 0.0f) continue;
+            if (!patches_see(e, i, j)) continue;
+            cols.push_back(j); ws.push_back(tr);
+        }
+        float total = 0.0f;
+        for (float v : ws) total = total + v;
+        if (total > 1.0f) { float s = 1.0f / total; for (float& v : ws) v = v * s; }
+    }
+    if ((int64_t)cols.size() > cap) return -1;
+    std::copy(cols.begin(), cols.end(), col_out); std::copy(ws.begin(), ws.end(), w_out);
+    return (int64_t)cols.size();
+}
+
 int orc_transfers_get(orc_env* e, int64_t* rowptr, int32_t* col, float* w) {
     if (!e || e->rowptr.empty()) return -1;
     if (rowptr) memcpy(rowptr, e->rowptr.data(), e->rowptr.size() * sizeof(int64_t));

@@ -137,3 +137,39 @@ def test_s2_full_transfers_and_bounce_properties():
         ref = pyoracle.gather_rows(0, 1, rp[i:i + 2] - rp[i], col[rp[i]:rp[i + 1]], w[rp[i]:rp[i + 1]], emit0, scene.patch_refl)[0]
         assert np.abs(t1[i] - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6)
     env.close()
+
+
+def test_c5_bake_transfers_and_bounce(s3):
+    """C5 at full size: 2,005,056 patches -> ~5.7e9 transfers built and bounced on one GPU.  The matrix is far
+    too large to download or to build on the CPU, so rows are spot-checked bit-exactly against the oracle's
+    single-row builder and the bounce is checked through properties and a sampled-row recomputation."""
+    from oracle import pyoracle
+    from vrad_b200.environment import environment_from_scene
+    scene, _, orc = s3
+    env = environment_from_scene(scene)                       # with patches
+    nnz = env.build_transfers(scene.pvs)
+    N = scene.n_patches
+    assert nnz > 3_000_000_000
+    r0, r1, n_local = env.transfers_info()
+    assert (r0, r1, n_local) == (0, N, nnz)
+    orc.patches_upload(scene.patch_origin, scene.patch_normal, scene.patch_plane_dist, scene.patch_area, scene.patch_refl,
+                       scene.patch_cluster, scene.patch_flags)
+    rows = [0, 1, 4097, 123456, 1002527, 1500001, N - 1] + [int(x) for x in scenes.SplitMix64(77).integers(17, N)]
+    emit0 = scenes.SplitMix64(0xC5).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
+    t1, added1, _ = env.bounce(emit0, 1)
+    for i in rows:
+        rp, col, w = env.transfers_download_rows(i, i + 1)
+        oc, ow = orc.transfer_row(i, scene.pvs)
+        assert np.array_equal(col, oc) and np.array_equal(w.view(np.uint32), ow.view(np.uint32)), i
+        assert rp[0] == 0 and rp[1] == len(oc)
+        ref = pyoracle.gather_rows(0, 1, rp, col, w, emit0, scene.patch_refl)[0]
+        assert np.abs(t1[i] - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6)
+    # a block of consecutive rows through the range download: ascending columns, PVS honoured, row sums <= 1
+    rp, col, w = env.transfers_download_rows(700000, 700256, capacity=1 << 21)
+    lens = np.diff(rp)
+    rr = np.repeat(np.arange(700000, 700256), lens)
+    assert np.all(scene.pvs[scene.patch_cluster[rr], scene.patch_cluster[col]] == 1) and not np.any(rr == col)
+    assert np.add.reduceat(w.astype(np.float64), rp[:-1][lens > 0]).max() <= 1.0 + 1e-4
+    t4, added4, done = env.bounce(emit0, 100, early_out=True)
+    assert done < 100 and np.all(added4 < 1.0) and np.isfinite(t4).all() and np.all(t4 >= t1 - 1e-3)
+    env.close()

@@ -363,6 +363,37 @@ int vrad_transfers_download(vrad_env* e, int64_t* rowptr, int32_t* col, float* w
     return VRAD_OK;
 }
 
+int vrad_transfers_download_rows(vrad_env* e, int64_t row_begin, int64_t row_end, int64_t* rowptr, int32_t* col, float* w, int64_t capacity) {
+    if (!e || !rowptr) { set_error("vrad_transfers_download_rows: bad arguments"); return VRAD_E_INVALID; }
+    TransfersDev& T = e->transfers;
+    if (!T.ready) { set_error("vrad_transfers_download_rows: no transfers resident"); return VRAD_E_STATE; }
+    if (row_begin < T.row0 || row_end > T.row1 || row_end < row_begin) {
+        set_error("vrad_transfers_download_rows: rows [%lld,%lld) outside this rank's [%lld,%lld)", (long long)row_begin, (long long)row_end, (long long)T.row0, (long long)T.row1);
+        return VRAD_E_INVALID;
+    }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const int64_t a = row_begin - T.row0, n = row_end - row_begin;
+    std::vector<int64_t> prow(n + 1);
+    std::vector<int32_t> rlen(n ? n : 1);
+    VRAD_CUDA_CHECK(cudaMemcpy(prow.data(), T.rowptr.p + a, (n + 1) * 8, cudaMemcpyDeviceToHost));
+    if (n) VRAD_CUDA_CHECK(cudaMemcpy(rlen.data(), T.rowlen.p + a, n * 4, cudaMemcpyDeviceToHost));
+    int64_t need = 0;
+    for (int64_t i = 0; i < n; i++) need += rlen[i];
+    if (need > capacity || (need > 0 && (!col || !w))) { set_error("vrad_transfers_download_rows: %lld entries, capacity %lld", (long long)need, (long long)capacity); return VRAD_E_INVALID; }
+    const int64_t span = prow[n] - prow[0];
+    std::vector<int2> ptr(span ? span : 1);
+    if (span) VRAD_CUDA_CHECK(cudaMemcpy(ptr.data(), T.tr.p + prow[0], span * 8, cudaMemcpyDeviceToHost));
+    int64_t pos = 0;
+    for (int64_t i = 0; i < n; i++) {
+        rowptr[i] = pos;
+        const int64_t base = prow[i] - prow[0];
+        for (int32_t k = 0; k < rlen[i]; k++) { col[pos + k] = ptr[base + k].x; memcpy(&w[pos + k], &ptr[base + k].y, 4); }
+        pos += rlen[i];
+    }
+    rowptr[n] = pos;
+    return VRAD_OK;
+}
+
 int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out,
                 float added_last[3], int* bounces_done) {
     if (!e || !emit0_rgb || n_bounces < 0) { set_error("vrad_bounce: bad arguments"); return VRAD_E_INVALID; }

@@ -213,6 +213,15 @@ class Environment:
         check(self._l.vrad_transfers_download(self._h, ptr(rowptr), ptr(col), ptr(w)))
         return rowptr, col, w
 
+    def transfers_download_rows(self, row_begin, row_end, capacity=None):
+        """Rows [row_begin,row_end) of the resident transfer lists (for matrices too large to download whole)."""
+        if capacity is None:
+            capacity = 1 << 22
+        rowptr = np.empty(row_end - row_begin + 1, np.int64); col = np.empty(capacity, np.int32); w = np.empty(capacity, np.float32)
+        check(self._l.vrad_transfers_download_rows(self._h, C.c_int64(row_begin), C.c_int64(row_end), ptr(rowptr), ptr(col), ptr(w), C.c_int64(capacity)))
+        n = int(rowptr[-1])
+        return rowptr, col[:n].copy(), w[:n].copy()
+
     def set_sky_dirs(self, dirs3):
         d = np.ascontiguousarray(dirs3, np.float32).reshape(-1, 3)
         check(self._l.vrad_set_sky_dirs(self._h, C.c_int(d.shape[0]), ptr(d)))

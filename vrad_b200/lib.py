@@ -22,7 +22,7 @@ SYMBOLS = [
     "vrad_env_last_timing", "vrad_host_alloc", "vrad_host_free", "vrad_env_add_triangles", "vrad_env_build",
     "vrad_env_upload_tree", "vrad_env_stats", "vrad_env_download_tree", "vrad_trace4", "vrad_trace_rays",
     "vrad_test_lines", "vrad_patches_upload", "vrad_build_transfers", "vrad_transfers_upload", "vrad_transfers_info",
-    "vrad_transfers_download", "vrad_set_sky_dirs", "vrad_direct_light", "vrad_bounce", "vrad_comm_unique_id",
+    "vrad_transfers_download", "vrad_transfers_download_rows", "vrad_set_sky_dirs", "vrad_direct_light", "vrad_bounce", "vrad_comm_unique_id",
     "vrad_comm_init", "vrad_version",
 ]
 
