@@ -314,18 +314,22 @@ def run_graft(args, rank, local_rank, world):
     energy_ok = bool(np.isfinite(h_tot).all() and h_tot.min() >= 0.0)
     env2.close()
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---------------- C5 side numbers (rank 0, N=1 only; informational, outside every timed region above) ----------------
+    # ---------------- C5 (S3 outdoor map): informational side numbers, outside every timed region above ----------------
+    # rays + direct light on rank 0 at N=1; transfer build + bounce gather at every N (rows sharded by rank)
     large = None
-    if world == 1 and not args.no_large:
-        try:
-            s3 = scenes.outdoor()
-            env3 = environment_from_scene(s3, device=local_rank, with_patches=False)
-            env3.set_stream(stream)
+    if not args.no_large:
+        s3 = scenes.outdoor()
+        env3 = environment_from_scene(s3, device=local_rank, rank=rank, world=world)
+        env3.set_stream(stream)
+        if world > 1:
+            uid3 = [Environment.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid3, src=0)
+            env3.comm_init(uid3[0])
+        st3 = env3.stats()
+        large = {"workload": "C5: S3 outdoor map (1,026,540 tris, 2,005,056 luxels/patches, 32x32-cell tile PVS), informational",
+                 "kd_build_seconds_host": st3["build_seconds"], "kd_nodes": st3["n_nodes"]}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world == 1:
             env3.set_async(True)
             n3 = 1 << 22
             a3, b3 = scenes.shadow_segments(s3, n3, seed=0xC5)
@@ -333,7 +337,6 @@ def run_graft(args, rank, local_rank, world):
             d_bits3 = torch.empty(n3 // 32, dtype=torch.int32, device=dev)
             for _ in range(2):
                 env3.test_lines(d_a3, d_b3, out=d_bits3)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(3):
                 env3.test_lines(d_a3, d_b3, out=d_bits3)
@@ -346,28 +349,40 @@ def run_graft(args, rank, local_rank, world):
             d_rgb = torch.empty((d_pos.shape[0], 3), device=dev)
             env3.direct_light(d_pos, d_nrm, s3.lights, out=d_rgb)
             env3.direct_light(d_pos, d_nrm, s3.lights, out=d_rgb)
-            k3_ms, k3_launches = env3.last_timing()
+            k3_ms, _ = env3.last_timing()
             up = float((dirs @ s3.luxel_normal[::97].T > 0.001).sum()) / s3.luxel_normal[::97].shape[0]
-            st3 = env3.stats()
-            large = {"workload": "C5: S3 outdoor map (1,026,540 tris, 2,005,056 luxels/patches), informational",
-                     "kd_build_seconds_host": st3["build_seconds"], "kd_nodes": st3["n_nodes"],
-                     "shadow_segments_per_sec": n3 / (seg_ms * 1e-3), "segments": n3,
-                     "direct_light_ms": k3_ms, "direct_light_rays_per_sec": d_pos.shape[0] * (1 + up) / (k3_ms * 1e-3),
-                     "direct_light_lights": "sun (EMIT_SKYLIGHT) + sky ambient over 162 directions"}
-            env3.patches_upload(s3.patch_origin, s3.patch_normal, s3.patch_plane_dist, s3.patch_area, s3.patch_refl, s3.patch_cluster, s3.patch_flags)
-            t0 = time.perf_counter(); nnz3 = env3.build_transfers(s3.pvs); torch.cuda.synchronize(); k2_s3 = time.perf_counter() - t0
-            e30 = torch.full((s3.n_patches, 3), 100.0, device=dev); o30 = torch.empty_like(e30)
-            env3.set_async(True)
-            env3.bounce(e30, 2, out=o30, want_added=False)
-            e0.record(); env3.bounce(e30, 10, out=o30, want_added=False); e1.record(); torch.cuda.synchronize()
-            k4_ms3 = e0.elapsed_time(e1) / 10
-            large.update({"transfer_build_seconds": k2_s3, "transfers": nnz3, "transfer_bytes": 8 * nnz3,
-                          "gather_ms_per_bounce": k4_ms3, "gather_gbs": (8 * nnz3 + 40 * s3.n_patches) / (k4_ms3 * 1e-3) / 1e9,
-                          "gather_frac_of_hbm_peak": (8 * nnz3 + 40 * s3.n_patches) / (k4_ms3 * 1e-3) / 1e9 / hbm_peak})
-            env3.close()
-            del d_a3, d_b3, d_pos, d_nrm, d_rgb, e30, o30
-        except Exception as exc:   # side numbers must never take the headline down
-            large = {"error": str(exc)}
+            large.update({"shadow_segments_per_sec": n3 / (seg_ms * 1e-3), "segments": n3, "direct_light_ms": k3_ms,
+                          "direct_light_rays_per_sec": d_pos.shape[0] * (1 + up) / (k3_ms * 1e-3),
+                          "direct_light_lights": "sun (EMIT_SKYLIGHT) + sky ambient over 162 directions"})
+            del d_a3, d_b3, d_pos, d_nrm, d_rgb
+        env3.set_async(False)
+        barrier()
+        t0 = time.perf_counter(); nnz3_local = env3.build_transfers(s3.pvs); torch.cuda.synchronize()
+        k2_s3 = max_over_ranks(time.perf_counter() - t0)
+        nnz3_t = torch.tensor([nnz3_local], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(nnz3_t)
+        nnz3 = int(nnz3_t.item())
+        N3 = s3.n_patches
+        e30 = torch.full((N3, 3), 100.0, device=dev); o30 = torch.empty_like(e30)
+        env3.set_async(True)
+        env3.bounce(e30, 2, out=o30, want_added=False)
+        barrier()
+        e0.record(); env3.bounce(e30, 20, out=o30, want_added=False); e1.record()
+        barrier()
+        k4_ms3 = max_over_ranks(e0.elapsed_time(e1)) / 20
+        gpu_bytes3 = 8 * nnz3_local + 40 * (N3 // world) + (12 * N3 if world > 1 else 0)
+        large.update({"transfer_build_seconds": k2_s3, "transfers": nnz3, "transfer_bytes": 8 * nnz3,
+                      "gather_ms_per_bounce": k4_ms3, "gather_iters_per_sec": 1e3 / k4_ms3,
+                      "gather_job_gbs": (8 * nnz3 + 40 * N3) / (k4_ms3 * 1e-3) / 1e9,
+                      "gather_frac_of_hbm_peak_per_gpu": gpu_bytes3 / (k4_ms3 * 1e-3) / 1e9 / hbm_peak})
+        env3.close()
+        del e30, o30
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     cpu_rays_obj, cpu_gather_obj = None, None
