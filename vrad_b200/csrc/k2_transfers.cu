@@ -10,8 +10,8 @@
 // MakeScales: rows whose weights sum above 1 are rescaled to sum 1.
 //
 // Rows are independent -> sharded by rank with no collective.  Three device passes:
-//   A  thread per (row, candidate): cheap tests, then the shadow ray; one ballot word per 32 pairs
-//      into a bit matrix (rays are generated on the device -- no per-pair HBM input at all);
+//   A  thread per (row, candidate): cheap tests, then the shadow ray -- one ray per unordered pair where both
+//      rows are local -- into a bit matrix (rays are generated on the device: no per-pair HBM input at all);
 //   B  warp per row: popcount -> row lengths; exclusive scan (cub) over 4-entry padded lengths;
 //   C  warp per row: expand set bits in order into (col, w), sequential row sum, MakeScales.
 // Algorithmic HBM bytes: 8*nnz + 64*N + 4*(N+1).
@@ -53,38 +53,59 @@ __device__ __forceinline__ float transfer_weight(const float4 oi, const float4 n
 }
 
 // Pass A.  One block per local row; threads sweep that row's candidate list.
+//
+// The shadow segment of a pair always runs from the lower to the higher patch index, so visibility is
+// symmetric and ONE ray serves both directions: thread (i, j) with i < j also runs the cheap tests from
+// j's side and, if the segment is clear, sets bit (j, i) in row j as well (position of i in j's candidate
+// list by binary search); thread (j, i) is then skipped.  This halves the ray count.  It applies when row
+// j is built by this rank and lists i (PVS entry [cluster j][cluster i]); otherwise each side traces
+// for itself.  All bit writes are atomicOr (the own-row word is warp-aggregated), so the bit matrix does
+// not depend on scheduling.
 __global__ void __launch_bounds__(256)
 k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __restrict__ cluster,
               const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx,
-              const int64_t* __restrict__ bit_ptr, uint32_t* __restrict__ bits) {
+              const int64_t* __restrict__ bit_ptr, uint32_t* __restrict__ bits,
+              const uint8_t* __restrict__ pvs, int n_clusters) {
     for (int row = blockIdx.x; row < nloc; row += gridDim.x) {
         const int i = (int)(row0 + row);
         const float4 oi = __ldg(&P.origin_area[i]), ni = __ldg(&P.normal_dist[i]);
-        const bool sky_i = __ldg(&P.refl[i]).w != 0.0f;
-        const int c = __ldg(&cluster[i]);
-        const int64_t c0 = __ldg(&cand_ptr[c]);
-        const int K = (int)(__ldg(&cand_ptr[c + 1]) - c0);
+        const float sky_i = __ldg(&P.refl[i]).w;
+        const int ci = __ldg(&cluster[i]);
+        const int64_t c0 = __ldg(&cand_ptr[ci]);
+        const int K = (int)(__ldg(&cand_ptr[ci + 1]) - c0);
         const int Kpad = (K + 31) & ~31;
         uint32_t* out = bits + bit_ptr[row];
         for (int p = threadIdx.x; p < Kpad; p += blockDim.x) {
-            bool need_ray = false;
+            bool need_ray = false, pass_ij = false, pass_ji = false;
+            int j = i, cj = ci;
             float4 a = oi, an = ni, b = oi, bn = ni;
-            if (p < K && !sky_i) {
-                const int j = __ldg(&cand_idx[c0 + p]);
+            if (p < K) {
+                j = __ldg(&cand_idx[c0 + p]);
                 if (j != i) {
-                    const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
-                    const float w = transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w);
-                    if (w != 0.0f) {
-                        need_ray = true;
+                    cj = __ldg(&cluster[j]);
+                    const bool mirror = j >= row0 && j < row0 + nloc && (pvs == nullptr || __ldg(&pvs[(size_t)cj * n_clusters + ci]) != 0);
+                    if (!(mirror && j < i)) {                       // otherwise thread (j, i) covers this pair
+                        const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
+                        const float sky_j = __ldg(&P.refl[j]).w;
+                        pass_ij = sky_i == 0.0f && transfer_weight(oi, ni, oj, nj, sky_j) != 0.0f;
+                        pass_ji = mirror && sky_j == 0.0f && transfer_weight(oj, nj, oi, ni, sky_i) != 0.0f;
+                        need_ray = pass_ij || pass_ji;
                         if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
                     }
                 }
             }
             // warp-synchronous shadow test: every lane calls, lanes without a ray idle inside
-            const int keep = segment_visible(S, need_ray, a.x + an.x, a.y + an.y, a.z + an.z,
-                                             b.x + bn.x, b.y + bn.y, b.z + bn.z, 0) && need_ray;
-            const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            if ((threadIdx.x & 31) == 0) out[p >> 5] = m;
+            const int vis = segment_visible(S, need_ray, a.x + an.x, a.y + an.y, a.z + an.z,
+                                            b.x + bn.x, b.y + bn.y, b.z + bn.z, 0) && need_ray;
+            const uint32_t m = __ballot_sync(0xffffffffu, vis && pass_ij);
+            if ((threadIdx.x & 31) == 0 && m) atomicOr(&out[p >> 5], m);
+            if (vis && pass_ji) {
+                // position of i in row j's candidate list (sorted patch indices of the clusters j sees)
+                const int64_t j0 = __ldg(&cand_ptr[cj]);
+                int lo = 0, hi = (int)(__ldg(&cand_ptr[cj + 1]) - j0);
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&cand_idx[j0 + mid]) < i) lo = mid + 1; else hi = mid; }
+                atomicOr(&bits[bit_ptr[j - row0] + (lo >> 5)], 1u << (lo & 31));
+            }
         }
     }
 }
@@ -186,12 +207,13 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     }
     const int64_t nwords = bit_ptr[nloc];
 
-    DevBuf<int32_t> d_clus, d_cand_idx; DevBuf<int64_t> d_cand_ptr, d_bit_ptr, d_padlen; DevBuf<uint32_t> d_bits; DevBuf<unsigned char> d_tmp;
+    DevBuf<int32_t> d_clus, d_cand_idx; DevBuf<int64_t> d_cand_ptr, d_bit_ptr, d_padlen; DevBuf<uint32_t> d_bits; DevBuf<unsigned char> d_tmp, d_pvs;
     TransfersDev& T = e->transfers;
     T.ready = false;
-    auto cleanup = [&]() { d_clus.release(); d_cand_idx.release(); d_cand_ptr.release(); d_bit_ptr.release(); d_padlen.release(); d_bits.release(); d_tmp.release(); };
+    auto cleanup = [&]() { d_clus.release(); d_cand_idx.release(); d_cand_ptr.release(); d_bit_ptr.release(); d_padlen.release(); d_bits.release(); d_tmp.release(); d_pvs.release(); };
     if (d_clus.alloc(N) || d_cand_idx.alloc(cand_idx.size() + 1) || d_cand_ptr.alloc(C + 1) || d_bit_ptr.alloc(nloc + 1) ||
-        d_padlen.alloc(nloc + 1) || d_bits.alloc(nwords + 1) || T.rowptr.alloc(nloc + 1) || T.rowlen.alloc(nloc + 1)) {
+        d_padlen.alloc(nloc + 1) || d_bits.alloc(nwords + 1) || T.rowptr.alloc(nloc + 1) || T.rowlen.alloc(nloc + 1) ||
+        (pvs && d_pvs.alloc((size_t)C * C))) {
         cleanup(); set_error("out of device memory for transfer build (%lld visibility words)", (long long)nwords); return VRAD_E_NOMEM;
     }
 #define K2_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); return VRAD_E_CUDA; } } while (0)
@@ -200,6 +222,8 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     K2_CHECK(cudaMemcpyAsync(d_cand_ptr.p, cand_ptr.data(), (C + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     K2_CHECK(cudaMemcpyAsync(d_bit_ptr.p, bit_ptr.data(), (nloc + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     K2_CHECK(cudaMemsetAsync(d_padlen.p, 0, (nloc + 1) * 8, e->stream));
+    K2_CHECK(cudaMemsetAsync(d_bits.p, 0, (size_t)(nwords + 1) * 4, e->stream));
+    if (pvs) K2_CHECK(cudaMemcpyAsync(d_pvs.p, pvs, (size_t)C * C, cudaMemcpyHostToDevice, e->stream));
 
     PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p};
     static const bool verbose = getenv("VRAD_TIMING") != nullptr;
@@ -209,7 +233,8 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     int launches = 0;
     if (nloc > 0) {
         if (verbose) cudaEventRecord(tv0, e->stream);
-        k2_visibility<<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p);
+        k2_visibility<<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
+                                                                               pvs ? d_pvs.p : nullptr, C);
         if (verbose) cudaEventRecord(tv1, e->stream);
         launches++;
         const int wblocks = (nloc * 32 + 255) / 256;
