@@ -133,9 +133,13 @@ int  vrad_patches_upload(vrad_env*, int n, const float* origin3, const float* no
                          const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags);
 /* patch-to-patch visibility + form factor -> transfer lists (common/types/transfer.go:3-6;
  * Patch.NumTransfers/Transfers patch.go:60-61).  pvs: n_clusters x n_clusters bytes (non-zero = visible)
- * or NULL.  Builds and keeps resident the CSR rows owned by this rank.  nnz_out = local nnz. */
+ * or NULL (host memory).  Builds and keeps resident the CSR rows owned by this rank.  nnz_out = local nnz.
+ * world > 1: ranks own contiguous row blocks that tile [0,N) in rank order.  If vrad_comm_init was called the
+ * call is COLLECTIVE and the blocks are balanced by estimated transfers (every 16th candidate pair tested, summed
+ * over ranks); otherwise equal blocks of ceil(N/world) rows.  vrad_transfers_info reports the block. */
 int  vrad_build_transfers(vrad_env*, int n_clusters, const uint8_t* pvs, int64_t* nnz_out);
-/* adopt prebuilt transfer rows [row0,row1): rowptr has row1-row0+1 entries starting at 0 */
+/* adopt prebuilt transfer rows [row0,row1): rowptr has row1-row0+1 entries starting at 0.  world > 1: any
+ * contiguous blocks that tile [0,N) in rank order (vrad_bounce verifies this collectively). */
 int  vrad_transfers_upload(vrad_env*, int64_t row0, int64_t row1, const int64_t* rowptr, const int32_t* col, const float* w);
 int  vrad_transfers_info(vrad_env*, int64_t* row0, int64_t* row1, int64_t* nnz);
 int  vrad_transfers_download(vrad_env*, int64_t* rowptr, int32_t* col, float* w);

@@ -53,8 +53,11 @@ def test_two_gpu_bounce_matches_single_and_oracle(tmp_path):
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     scene = scenes.multi_room(nx=3, ny=2)
     N = scene.n_patches
-    parts = row_partition(N, 2)
-    assert (int(r0["row0"]), int(r0["row1"])) == parts[0] and (int(r1["row0"]), int(r1["row1"])) == parts[1]
+    # the row blocks are contiguous, tile [0,N) in rank order and are balanced by (estimated) transfers, not rows
+    parts = [(int(r0["row0"]), int(r0["row1"])), (int(r1["row0"]), int(r1["row1"]))]
+    assert parts[0][0] == 0 and parts[0][1] == parts[1][0] and parts[1][1] == N
+    assert abs(int(r0["nnz"]) - int(r1["nnz"])) < 0.05 * (int(r0["nnz"]) + int(r1["nnz"]))
+    assert len(row_partition(N, 2)) == 2
     o = pyoracle.env_from_scene(scene)
     nnz = o.build_transfers(scene.pvs, threads=8)
     assert int(r0["nnz"]) + int(r1["nnz"]) == nnz

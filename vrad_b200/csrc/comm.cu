@@ -21,15 +21,18 @@ typedef int (*fn_destroy)(nccl_comm_t);
 typedef const char* (*fn_errstr)(int);
 typedef int (*fn_allgather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_bcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
 
 static struct {
     void* h = nullptr;
     fn_get_uid get_uid; fn_init_rank init_rank; fn_destroy destroy; fn_errstr errstr;
-    fn_allgather allgather; fn_allreduce allreduce;
+    fn_allgather allgather; fn_allreduce allreduce; fn_bcast bcast;
 } g_nccl;
 
 constexpr int kNcclFloat = 7;   // ncclFloat32
 constexpr int kNcclSum = 0;     // ncclSum
+constexpr int kNcclInt32 = 2;   // ncclInt32
+constexpr int kNcclInt64 = 4;   // ncclInt64
 
 static int load_nccl() {
     if (g_nccl.h) return 0;
@@ -42,7 +45,8 @@ static int load_nccl() {
     g_nccl.errstr = (fn_errstr)dlsym(h, "ncclGetErrorString");
     g_nccl.allgather = (fn_allgather)dlsym(h, "ncclAllGather");
     g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
-    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.errstr || !g_nccl.allgather || !g_nccl.allreduce) {
+    g_nccl.bcast = (fn_bcast)dlsym(h, "ncclBroadcast");
+    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.errstr || !g_nccl.allgather || !g_nccl.allreduce || !g_nccl.bcast) {
         set_error("libnccl.so.2 lacks a required symbol"); dlclose(h); return VRAD_E_COMM;
     }
     g_nccl.h = h;
@@ -55,11 +59,51 @@ static int load_nccl() {
         if (_r != 0) { set_error("%s failed: %s", #expr, g_nccl.errstr(_r)); return VRAD_E_COMM; } \
     } while (0)
 
-// in-place all-gather: rank r's rows_per_rank float4 rows already sit at buf + r*rows_per_rank
-int comm_allgather_f4(vrad_env* e, float4* buf, size_t rows_per_rank) {
+// Row-indexed all-gather for arbitrary contiguous row blocks: rank r owns rows [bounds[r], bounds[r+1]) of the
+// float4 array `buf` (indexed by global row) and broadcasts them in place.  `world` small broadcasts; used for
+// the final `total` gather and as the exchange when peer mapping is unavailable.
+int comm_allgather_rows(vrad_env* e, float4* buf, const int64_t* bounds) {
     if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
-    const float4* send = buf + (size_t)e->cfg.rank * rows_per_rank;
-    VRAD_NCCL_CHECK(g_nccl.allgather(send, buf, rows_per_rank * 4, kNcclFloat, (nccl_comm_t)e->nccl_comm, e->stream));
+    for (int r = 0; r < e->cfg.world; r++) {
+        const int64_t cnt = bounds[r + 1] - bounds[r];
+        if (cnt <= 0) continue;
+        VRAD_NCCL_CHECK(g_nccl.bcast(buf + bounds[r], buf + bounds[r], (size_t)cnt * 4, kNcclFloat, r, (nccl_comm_t)e->nccl_comm, e->stream));
+    }
+    return 0;
+}
+
+// every rank contributes its [row0,row1); returns the world+1 boundaries, checked to tile [0,n) in rank order
+int comm_exchange_bounds(vrad_env* e, int64_t row0, int64_t row1, int64_t n, int64_t* bounds_out) {
+    if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
+    const int world = e->cfg.world;
+    DevBuf<int64_t> d;
+    if (d.alloc(2 * (size_t)world)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    const int64_t mine[2] = {row0, row1};
+    std::vector<int64_t> all(2 * (size_t)world);
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(d.p + 2 * e->cfg.rank, mine, 16, cudaMemcpyHostToDevice, e->stream));
+    VRAD_NCCL_CHECK(g_nccl.allgather(d.p + 2 * e->cfg.rank, d.p, 2, kNcclInt64, (nccl_comm_t)e->nccl_comm, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(all.data(), d.p, 16 * (size_t)world, cudaMemcpyDeviceToHost, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    d.release();
+    int64_t expect = 0;
+    for (int r = 0; r < world; r++) {
+        if (all[2 * r] != expect || all[2 * r + 1] < all[2 * r]) {
+            set_error("transfer rows of the ranks do not tile [0,%lld): rank %d holds [%lld,%lld), expected start %lld",
+                      (long long)n, r, (long long)all[2 * r], (long long)all[2 * r + 1], (long long)expect);
+            return VRAD_E_STATE;
+        }
+        bounds_out[r] = all[2 * r];
+        expect = all[2 * r + 1];
+    }
+    if (expect != n) { set_error("transfer rows of the ranks end at %lld, not %lld", (long long)expect, (long long)n); return VRAD_E_STATE; }
+    bounds_out[world] = n;
+    return 0;
+}
+
+// in-place sum of an int32 device array over all ranks
+int comm_allreduce_i32(vrad_env* e, int32_t* d, size_t n) {
+    if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
+    VRAD_NCCL_CHECK(g_nccl.allreduce(d, d, n, kNcclInt32, kNcclSum, (nccl_comm_t)e->nccl_comm, e->stream));
     return 0;
 }
 

@@ -22,6 +22,8 @@
 
 namespace vrad {
 
+int comm_allreduce_i32(vrad_env* e, int32_t* d, size_t n);
+
 constexpr float kPlaneTestEpsilon = 0.01f;
 constexpr float kTransEpsilon = 1.0e-7f;
 constexpr float kPiF = 3.14159265358979323846f;
@@ -107,6 +109,51 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
                 atomicOr(&bits[bit_ptr[j - row0] + (lo >> 5)], 1u << (lo & 31));
             }
         }
+    }
+}
+
+// Load estimate for the multi-GPU row partition: per row, the number of transfers it will hold, estimated by
+// running the full pair test (cheap tests + shadow ray) on every 16th candidate (staggered by row).  The
+// per-bounce gather streams exactly these entries, so blocks balanced on this estimate keep the bounce loop --
+// which waits for the fullest rank -- even; costs ~1/16 of pass A.
+constexpr int kEstimateStride = 16;
+
+__global__ void __launch_bounds__(256)
+k2_estimate(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __restrict__ cluster,
+            const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx, int32_t* __restrict__ counts) {
+    __shared__ int total;
+    for (int row = blockIdx.x; row < nloc; row += gridDim.x) {
+        const int i = (int)(row0 + row);
+        if (threadIdx.x == 0) total = 0;
+        __syncthreads();
+        const float4 oi = __ldg(&P.origin_area[i]), ni = __ldg(&P.normal_dist[i]);
+        const bool sky_i = __ldg(&P.refl[i]).w != 0.0f;
+        const int64_t c0 = __ldg(&cand_ptr[__ldg(&cluster[i])]);
+        const int K = (int)(__ldg(&cand_ptr[__ldg(&cluster[i]) + 1]) - c0);
+        const int n_samples = (K + kEstimateStride - 1) / kEstimateStride;
+        int mine = 0;
+        for (int q = threadIdx.x; q < ((n_samples + 31) & ~31); q += blockDim.x) {
+            const int p = q * kEstimateStride + (i & (kEstimateStride - 1));
+            bool need = false;
+            float4 a = oi, an = ni, b = oi, bn = ni;
+            if (q < n_samples && p < K && !sky_i) {
+                const int j = __ldg(&cand_idx[c0 + p]);
+                if (j != i) {
+                    const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
+                    if (transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w) != 0.0f) {
+                        need = true;
+                        if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
+                    }
+                }
+            }
+            mine += segment_visible(S, need, a.x + an.x, a.y + an.y, a.z + an.z, b.x + bn.x, b.y + bn.y, b.z + bn.z, 0) && need;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&total, mine);
+        __syncthreads();
+        if (threadIdx.x == 0) counts[i] = total * kEstimateStride;
+        __syncthreads();
     }
 }
 
@@ -198,7 +245,47 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     }
     const int world = e->cfg.world;
     const int64_t rpr = ((int64_t)N + world - 1) / world;
-    const int64_t row0 = std::min<int64_t>(N, e->cfg.rank * rpr), row1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
+    int64_t row0 = std::min<int64_t>(N, e->cfg.rank * rpr), row1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
+    PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p};
+    static const bool no_balance = [] { const char* v = getenv("VRAD_K2_BALANCE"); return v && v[0] == '0'; }();
+    if (world > 1 && e->nccl_comm && !no_balance) {
+        // Balance the contiguous row blocks by estimated transfers instead of by row count (collective): every
+        // rank estimates the row lengths of its equal block (k2_estimate), the estimates are summed over ranks, and
+        // block r starts at the first row whose prefix reaches r/world of the total -- identical on every rank.
+        DevBuf<int32_t> d_cl, d_ci, d_counts; DevBuf<int64_t> d_cp;
+        auto drop = [&]() { d_cl.release(); d_ci.release(); d_counts.release(); d_cp.release(); };
+        if (d_cl.alloc(N) || d_ci.alloc(cand_idx.size() + 1) || d_cp.alloc(C + 1) || d_counts.alloc(N)) { drop(); set_error("out of device memory (row balance)"); return VRAD_E_NOMEM; }
+        std::vector<int32_t> counts(N);
+        cudaError_t ce = cudaMemcpyAsync(d_cl.p, clus.data(), (size_t)N * 4, cudaMemcpyHostToDevice, e->stream);
+        if (ce == cudaSuccess && !cand_idx.empty()) ce = cudaMemcpyAsync(d_ci.p, cand_idx.data(), cand_idx.size() * 4, cudaMemcpyHostToDevice, e->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_cp.p, cand_ptr.data(), (C + 1) * 8, cudaMemcpyHostToDevice, e->stream);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(d_counts.p, 0, (size_t)N * 4, e->stream);
+        if (ce != cudaSuccess) { drop(); set_error("row balance staging failed: %s", cudaGetErrorString(ce)); return VRAD_E_CUDA; }
+        const int nl0 = (int)(row1 - row0);
+        if (nl0 > 0) k2_estimate<<<std::min(nl0, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nl0, row0, d_cl.p, d_cp.p, d_ci.p, d_counts.p);
+        int rcb = comm_allreduce_i32(e, d_counts.p, (size_t)N);
+        if (rcb) { drop(); return rcb; }
+        ce = cudaMemcpyAsync(counts.data(), d_counts.p, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        drop();
+        if (ce != cudaSuccess) { set_error("row balance failed: %s", cudaGetErrorString(ce)); return VRAD_E_CUDA; }
+        int64_t total = 0;
+        for (int i = 0; i < N; i++) total += counts[i] + 1;                 // +1: every row costs something
+        int64_t bounds[kMaxWorld + 1];
+        bounds[0] = 0; bounds[world] = N;
+        int64_t acc = 0; int r = 1;
+        for (int i = 0; i < N && r < world; i++) {
+            acc += counts[i] + 1;
+            while (r < world && acc >= (total * r) / world) bounds[r++] = i + 1;
+        }
+        while (r < world) bounds[r++] = N;
+        row0 = bounds[e->cfg.rank]; row1 = bounds[e->cfg.rank + 1];
+        if (getenv("VRAD_VERBOSE") && e->cfg.rank == 0) {
+            fprintf(stderr, "[vrad] balanced row blocks:");
+            for (int q = 0; q <= world; q++) fprintf(stderr, " %lld", (long long)bounds[q]);
+            fprintf(stderr, " (equal blocks would be %lld rows)\n", (long long)rpr);
+        }
+    }
     const int nloc = (int)(row1 - row0);
     std::vector<int64_t> bit_ptr(nloc + 1, 0);
     for (int r = 0; r < nloc; r++) {
@@ -225,7 +312,6 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     K2_CHECK(cudaMemsetAsync(d_bits.p, 0, (size_t)(nwords + 1) * 4, e->stream));
     if (pvs) K2_CHECK(cudaMemcpyAsync(d_pvs.p, pvs, (size_t)C * C, cudaMemcpyHostToDevice, e->stream));
 
-    PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p};
     static const bool verbose = getenv("VRAD_TIMING") != nullptr;
     cudaEvent_t tv0 = nullptr, tv1 = nullptr;
     if (verbose) { cudaEventCreate(&tv0); cudaEventCreate(&tv1); }

@@ -19,7 +19,8 @@
 
 namespace vrad {
 
-int comm_allgather_f4(vrad_env* e, float4* buf, size_t rows_per_rank);
+int comm_allgather_rows(vrad_env* e, float4* buf, const int64_t* bounds);
+int comm_exchange_bounds(vrad_env* e, int64_t row0, int64_t row1, int64_t n, int64_t* bounds_out);
 int comm_setup_peers(vrad_env* e, size_t n_pad);
 int comm_allreduce3(vrad_env* e, float* d3);
 
@@ -290,11 +291,7 @@ int vrad_transfers_upload(vrad_env* e, int64_t row0, int64_t row1, const int64_t
     const int64_t N = e->patches.n;
     if (N == 0) { set_error("vrad_transfers_upload: upload patches first"); return VRAD_E_STATE; }
     if (row1 > N) { set_error("vrad_transfers_upload: rows [%lld,%lld) exceed %lld patches", (long long)row0, (long long)row1, (long long)N); return VRAD_E_INVALID; }
-    if (e->cfg.world > 1) {
-        const int64_t rpr = rows_per_rank(e, N);
-        const int64_t want0 = std::min<int64_t>(N, e->cfg.rank * rpr), want1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
-        if (row0 != want0 || row1 != want1) { set_error("vrad_transfers_upload: rank %d owns rows [%lld,%lld)", e->cfg.rank, (long long)want0, (long long)want1); return VRAD_E_INVALID; }
-    }
+    // with several ranks the row blocks must tile [0,N) in rank order; vrad_bounce checks that collectively
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     const int64_t nloc = row1 - row0;
     const int64_t nnz = rowptr[nloc] - rowptr[0];
@@ -404,10 +401,16 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     const int64_t N = e->patches.n;
     const int world = e->cfg.world;
     const int64_t rpr = rows_per_rank(e, N);
-    const int64_t n_pad = rpr * world;
+    const int64_t n_pad = rpr * world;           // >= N; radiance buffers are indexed by global patch number
+    int64_t bounds[kMaxWorld + 1] = {0};
+    if (world > 1) {
+        if (world > kMaxWorld) { set_error("vrad_bounce: world %d > %d", world, kMaxWorld); return VRAD_E_UNSUPPORTED; }
+        int rcb = comm_exchange_bounds(e, T.row0, T.row1, N, bounds);
+        if (rcb) return rcb;
+    }
     const int nloc = (int)(T.row1 - T.row0);
     const int nblocks = std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
-    // `total` is sized for a full gather at the end (rank r's rows live at r*rpr)
+    // `total` is indexed by global row too, so that the final gather is in place
     if (e->d_er[0].alloc(n_pad) || e->d_er[1].alloc(n_pad) || e->d_total.alloc(n_pad) || e->d_partials.alloc(3 * (size_t)nblocks + 8)) {
         set_error("out of device memory for bounce state"); return VRAD_E_NOMEM;
     }
@@ -422,7 +425,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
 
     timing_begin(e);
     int launches = 0;
-    float4* total_local = e->d_total.p + (world > 1 ? e->cfg.rank * rpr : 0);
+    float4* total_local = e->d_total.p + (world > 1 ? T.row0 : 0);
     VRAD_CUDA_CHECK(cudaMemsetAsync(e->d_total.p, 0, (size_t)n_pad * 16, e->stream));
     VRAD_CUDA_CHECK(cudaMemsetAsync(d_added, 0, 12, e->stream));
     k4_init_er<<<(int)((n_pad + 255) / 256), 256, 0, e->stream>>>((int)n_pad, (int)N, (const float*)d_emit0, e->patches.refl.p, e->d_er[0].p);
@@ -448,7 +451,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         pending_wait = false;
         if (probe) cudaEventRecord(pe[n_probe][1], e->stream);
         if (p2p) { k4_peer_signal<<<1, 32, 0, e->stream>>>(d_peers); launches++; pending_wait = true; }
-        else if (world > 1 && (rc = comm_allgather_f4(e, e->d_er[cur ^ 1].p, (size_t)rpr))) return rc;
+        else if (world > 1 && (rc = comm_allgather_rows(e, e->d_er[cur ^ 1].p, bounds))) return rc;
         if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
         cur ^= 1; done++;
         const bool last = (b + 1 == n_bounces);
@@ -464,7 +467,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         }
     }
     if (pending_wait) { k4_peer_wait<<<1, 32, 0, e->stream>>>(d_peers); launches++; }
-    if (world > 1 && (rc = comm_allgather_f4(e, e->d_total.p, (size_t)rpr))) return rc;
+    if (world > 1 && (rc = comm_allgather_rows(e, e->d_total.p, bounds))) return rc;
     if (d_out3) {
         k4_unpack_total<<<(int)((N + 255) / 256), 256, 0, e->stream>>>(N, e->d_total.p, (float*)d_out3);
         launches++;

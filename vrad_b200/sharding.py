@@ -1,10 +1,11 @@
 """Host-side sharding rules for the multi-GPU path (one process per GPU).
 
 Rays / luxels are independent: each rank takes a contiguous range.  Patch rows of the transfer matrix
-are block-partitioned in equal blocks of ceil(N / world) rows -- the same rule libvradcuda applies in
-vrad_build_transfers / vrad_transfers_upload -- so that rank r's rows sit at slot r*rows_per_rank of the
-all-gathered radiance buffer and patch index == buffer index.  The only data-path collective is the
-per-bounce all-gather of the new radiance rows.
+are partitioned in contiguous blocks that tile [0, N) in rank order.  `row_partition` is the default rule (equal
+blocks of ceil(N / world) rows, what vrad_build_transfers uses without a communicator and what callers of
+vrad_transfers_upload typically pass); with a communicator vrad_build_transfers balances the blocks by estimated
+transfers instead.  Radiance buffers are indexed by global patch number, so any such tiling works.  The only
+data-path exchange is the per-bounce hand-over of the new radiance rows.
 """
 from __future__ import annotations
 
