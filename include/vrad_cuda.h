@@ -37,7 +37,7 @@ typedef enum {
     VRAD_E_NOMEM = -3,
     VRAD_E_STATE = -4,       /* e.g. trace before build */
     VRAD_E_COMM = -5,        /* NCCL error */
-    VRAD_E_UNSUPPORTED = -6  /* e.g. FCACHETRI_TRANSPARENT triangles (callback cannot cross into a kernel) */
+    VRAD_E_UNSUPPORTED = -6  /* e.g. a kd tree deeper than the device traversal stack */
 } vrad_status;
 
 /* raytracer/constants.go:5-18 */
@@ -45,6 +45,11 @@ typedef enum {
 #define VRAD_TRACE_ID_OPAQUE     0x02000000
 #define VRAD_TRACE_ID_STATICPROP 0x04000000
 #define VRAD_KDNODE_LEAF 3
+/* triangle flag (TriIntersectData.NFlags, raytracer/cache/triangle/triintersectdata.go:20): upstream
+ * FCACHETRI_TRANSPARENT.  Such a triangle is an ordinary blocker unless the trace runs with texture
+ * shadows (VRAD_TL_TEXTURE_SHADOWS), where it goes through the coverage rule of
+ * raytracer/types/coverageCount.go:16-48 evaluated on the device. */
+#define VRAD_TRI_TRANSPARENT 0x01
 
 typedef struct vrad_env vrad_env;   /* opaque; stands in for raytracer.Environment (raytracer/environment.go:28-39) */
 
@@ -112,7 +117,8 @@ int  vrad_env_download_tree(vrad_env*, int32_t* children, float* split, int32_t*
 /* ---- K1: ray casting --------------------------------------------------------------------- */
 /* Environment.Trace4Rays (raytracer/environment.go:140-145): one FourRays packet
  * (raytracer/types/fourrays.go:8-11) -> RayTracingResult (raytracer/types/result.go:8-12).
- * origin/dir/normal are x[4] y[4] z[4].  Latency path; kept for call-surface fidelity. */
+ * origin/dir/normal are x[4] y[4] z[4].  Latency path; kept for call-surface fidelity.
+ * (callback = nil: transparent triangles block like any other, as upstream does without a callback.) */
 int  vrad_trace4(vrad_env*, const float origin_xyz4[12], const float dir_xyz4[12], const float tmin[4],
                  const float tmax[4], int32_t skip_id, int32_t hit_ids[4], float hit_dist[4], float normal_xyz4[12]);
 /* batched Trace4Rays: n rays SoA.  tmin may be NULL (0).  hit_tri = index into the triangle list or -1,
@@ -122,10 +128,59 @@ int  vrad_trace_rays(vrad_env*, int64_t n, const float* ox, const float* oy, con
                      const float* dx, const float* dy, const float* dz, const float* tmin, const float* tmax,
                      int32_t skip_id, int32_t* hit_tri, int32_t* hit_sid, float* hit_t);
 /* trace.TestLine / trace.TestLineDoesHitSky (raytracer/trace/testline.go:18-94, without the 3D-skybox
- * recursion of :57-89): n segments, SoA blocks x[n] y[n] z[n]; vis_bits bit (i%32) of word i/32, 1 = visible.
+ * recursion of :57-89 -- vrad_test_lines_sky is the complete form): n segments, SoA blocks x[n] y[n] z[n]; vis_bits bit (i%32) of word i/32, 1 = visible.
  * sky_mode 0: any hit occludes; 1: a nearest hit on a TRACE_ID_SKY triangle does not occlude (:46-48). */
 int  vrad_test_lines(vrad_env*, int64_t n, const float* start_xyz_soa, const float* stop_xyz_soa,
                      int sky_mode, uint32_t* vis_bits);
+
+/* Environment.TriangleColors (raytracer/environment.go:61-63, GetTriangleColor :430-432): 3 floats per
+ * triangle, in the order the triangles were added.  colour.X is the coverage CoverageCount adds for a
+ * transparent triangle (coverageCount.go:29).  May be called before or after the build. */
+int  vrad_env_set_triangle_colors(vrad_env*, int n, const float* rgb3);
+
+/* ---- BSP point location, sky cameras, full TestLineDoesHitSky ------ */
+/* The lumps trace.PointLeafnum (raytracer/trace/pointleaf.go:8-33) and clustertable.PointInLeaf
+ * (rad/clustertable/point.go:14-38) walk: Nodes{PlaneNum, Children[2]} (negative child = -1-leaf),
+ * Planes{Normal, Distance, AxisType}, Leafs{Cluster, Area}; n_areas = len(Areas). */
+int  vrad_bsp_upload(vrad_env*, int n_nodes, const int32_t* node_plane, const int32_t* node_children2,
+                     int n_planes, const float* plane_normal3, const float* plane_dist, const int32_t* plane_type,
+                     int n_leafs, const int32_t* leaf_cluster, const int32_t* leaf_area, int n_areas);
+/* trace.PointLeafnum for n points (xyz interleaved) */
+int  vrad_point_leafnum(vrad_env*, int64_t n, const float* pts3, int32_t* leaf_out);
+/* clustertable.ClusterFromPoint (rad/clustertable/point.go:10-12) for n points: TEST_EPSILON-tolerant
+ * descent that prefers the front child unless it ends in a cluster -1 leaf */
+int  vrad_cluster_from_point(vrad_env*, int64_t n, const float* pts3, int32_t* cluster_out);
+/* cameras.ProcessSkyCameras (rad/cameras/skycamera.go:10-49): one entry per sky_camera entity (origin,
+ * scale); cameras with scale <= 0 are dropped; fills cache.skyCameras / areaSkyCameras
+ * (cache/skycameras.go:8-40).  n_kept_out may be NULL.  Needs vrad_bsp_upload first. */
+int  vrad_sky_cameras_set(vrad_env*, int n, const float* origin3, const float* scale, int* n_kept_out);
+/* read back: per kept camera its area and WorldToSky, and areaSkyCameras[n_areas]; pointers may be NULL */
+int  vrad_sky_cameras_get(vrad_env*, int* n_cameras, int32_t* cam_area, float* world_to_sky, int32_t* area_camera);
+
+#define VRAD_TL_CAN_RECURSE      1   /* canRecurse (testline.go:18,58): clip into the 3D sky boxes */
+#define VRAD_TL_TEXTURE_SHADOWS  2   /* textureShadows (testline.go:14,32-34,52-55): transparent-triangle coverage */
+#define VRAD_TL_PACKET_LEAF      4   /* the leaf/area of every group of 4 segments comes from its first
+                                        segment, as the FourVectors form does (start.Vec(0), testline.go:63) */
+/* trace.TestLineDoesHitSky (raytracer/trace/testline.go:18-94), complete: skip id
+ * TRACE_ID_STATICPROP|static_prop_to_skip (:36), sky-id test (:42-51), coverage (:52-55), 3D-skybox
+ * recursion through every sky camera (:57-89), fractionVisible = 1 - clamp(occlusion) (:91-93).
+ * start/stop: SoA blocks x[n] y[n] z[n]; fraction_visible: n floats. */
+int  vrad_test_lines_sky(vrad_env*, int64_t n, const float* start_xyz_soa, const float* stop_xyz_soa, int flags,
+                         int32_t static_prop_to_skip, float* fraction_visible);
+/* lightmap.CanLeafTraceToSky (rad/lightmap/lightmap.go:425-451) for n_leafs BSP leafs: from the centre of
+ * Mins/Maxs (int16 triples) along every sky direction set with vrad_set_sky_dirs (vmath.Anorms), with
+ * recursion; can_out[i] = 1 when any direction has fractionVisible > 0. */
+int  vrad_leafs_trace_to_sky(vrad_env*, int n_leafs, const int16_t* mins3, const int16_t* maxs3, uint8_t* can_out);
+
+/* ---- PVS ------------------------------------------------------------ */
+/* lightmap.DecompressVis (rad/lightmap/vis.go:54-94): one run-length coded PVS row of the visibility
+ * lump -> (n_clusters+7)/8 bytes.  Host-only helper (no device needed).  Returns the number of input
+ * bytes consumed, or a negative vrad_status. */
+int64_t vrad_decompress_vis(const uint8_t* in, int64_t in_len, int n_clusters, uint8_t* out_row);
+/* The whole visibility lump -> the n_clusters x n_clusters byte matrix vrad_build_transfers takes:
+ * byteofs2 = dvis ByteOffset[cluster][DVIS_PVS, DVIS_PAS] (lightmap.GetVisCache, vis.go:9-47); a cluster
+ * with offset -1 sees nothing.  Host-only helper. */
+int  vrad_pvs_from_vis_lump(int n_clusters, const int32_t* byteofs2, const uint8_t* visdata, int64_t vis_len, uint8_t* pvs_out);
 
 /* ---- patches, K2 transfers, K3 direct light, K4 bounce ---------------------------------- */
 /* fields of common/types/patch.go:9-64 the kernels read (leaf patches only) */

@@ -99,18 +99,28 @@ private:
 
 namespace trace {
 
-// TestLineDoesHitSky (raytracer/trace/testline.go:18-94) for one FourVectors pair; the 3D-skybox
-// recursion (:57-89) is a NEXT row: canRecurse is accepted and ignored.
+// package variables of raytracer/trace/testline.go:13-16
+inline bool textureShadows = false;
+inline bool noSkyRecurse = false;
+
+// TestLineDoesHitSky (raytracer/trace/testline.go:18-94) for one FourVectors pair, complete: static-prop skip
+// id (:36), sky-id rule (:42-51), coverage (:52-55), 3D-skybox recursion with the leaf of lane 0 (:57-89).
 inline void TestLineDoesHitSky(const raytracer::Environment& env, const raytracer::FourVectors& start, const raytracer::FourVectors& stop,
-                               raytracer::Flt4x* fractionVisible, bool /*canRecurse*/ = true, int /*staticPropToSkip*/ = -1, bool /*doDebug*/ = false) {
+                               raytracer::Flt4x* fractionVisible, bool canRecurse = true, int staticPropToSkip = -1, bool /*doDebug*/ = false) {
     float a[12], b[12];
     for (int l = 0; l < 4; l++) {
         a[l] = start.X[l]; a[4 + l] = start.Y[l]; a[8 + l] = start.Z[l];
         b[l] = stop.X[l]; b[4 + l] = stop.Y[l]; b[8 + l] = stop.Z[l];
     }
-    uint32_t bits = 0;
-    raytracer::fatal_on(vrad_test_lines(env.handle(), 4, a, b, 1, &bits), "vrad_test_lines");
-    for (int l = 0; l < 4; l++) (*fractionVisible)[l] = ((bits >> l) & 1u) ? 1.0f : 0.0f;
+    const int flags = VRAD_TL_PACKET_LEAF | ((canRecurse && !noSkyRecurse) ? VRAD_TL_CAN_RECURSE : 0) | (textureShadows ? VRAD_TL_TEXTURE_SHADOWS : 0);
+    raytracer::fatal_on(vrad_test_lines_sky(env.handle(), 4, a, b, flags, staticPropToSkip, fractionVisible->data()), "vrad_test_lines_sky");
+}
+
+// PointLeafnum (raytracer/trace/pointleaf.go:8-10); needs the BSP lumps (vrad_bsp_upload)
+inline int PointLeafnum(const raytracer::Environment& env, const raytracer::Vec3& point) {
+    int32_t leaf = -1;
+    raytracer::fatal_on(vrad_point_leafnum(env.handle(), 1, point.data(), &leaf), "vrad_point_leafnum");
+    return leaf;
 }
 
 } // namespace trace

@@ -126,6 +126,32 @@ int  orc_bounce(orc_env*, const float* emit0_rgb, int n_bounces, int early_out,
 int  orc_gather_rows(int64_t row0, int64_t row1, const int64_t* rowptr, const int32_t* col, const float* w,
                      const float* emit_rgb, const float* refl_rgb, float* out_rgb, int threads);
 
+/* ---- full TestLineDoesHitSky call surface (oracle/skytrace.cpp) ---- */
+#define ORC_TL_CAN_RECURSE     1   /* canRecurse, raytracer/trace/testline.go:18,58 */
+#define ORC_TL_TEXTURE_SHADOWS 2   /* textureShadows, testline.go:14,32-34,52-55 */
+#define ORC_TL_PACKET_LEAF     4   /* leaf of every group of 4 segments from its first segment (start.Vec(0), testline.go:63) */
+/* Environment.TriangleColors (raytracer/environment.go:61-63; GetTriangleColor :430-432): 3 floats per triangle */
+int  orc_env_set_triangle_colors(orc_env*, int n, const float* rgb3);
+/* BSP point-location data (bsp Nodes / Planes / Leafs lumps as the reference's cache holds them) */
+int  orc_bsp_set(orc_env*, int n_nodes, const int32_t* node_plane, const int32_t* node_children2, int n_planes,
+                 const float* plane_normal3, const float* plane_dist, const int32_t* plane_type, int n_leafs,
+                 const int32_t* leaf_cluster, const int32_t* leaf_area, int n_areas);
+/* trace.PointLeafnum, raytracer/trace/pointleaf.go:8-33 */
+int  orc_point_leafnum(orc_env*, int64_t n, const float* pts3, int32_t* leaf_out);
+/* clustertable.ClusterFromPoint / PointInLeaf, rad/clustertable/point.go:10-38 */
+int  orc_cluster_from_point(orc_env*, int64_t n, const float* pts3, int32_t* cluster_out);
+/* cameras.ProcessSkyCameras, rad/cameras/skycamera.go:10-49; returns the number of cameras kept */
+int  orc_sky_cameras_set(orc_env*, int n, const float* origin3, const float* scale);
+int  orc_sky_cameras_get(orc_env*, int32_t* cam_area, float* world_to_sky, int32_t* area_camera);
+/* trace.TestLineDoesHitSky per segment, raytracer/trace/testline.go:18-94 */
+int  orc_test_lines_sky(orc_env*, int64_t n, const float* start_soa, const float* stop_soa, int flags,
+                        int32_t static_prop_to_skip, float* fraction_visible, int threads);
+/* lightmap.CanLeafTraceToSky, rad/lightmap/lightmap.go:425-451 (dirs = vmath.Anorms) */
+int  orc_leafs_trace_to_sky(orc_env*, int n_leafs, const int16_t* mins3, const int16_t* maxs3, int n_dirs,
+                            const float* dirs3, uint8_t* can_out, int threads);
+/* lightmap.DecompressVis, rad/lightmap/vis.go:54-94: one PVS row; returns input bytes consumed or <0 */
+int64_t orc_decompress_vis(const uint8_t* in, int64_t in_len, int n_clusters, uint8_t* out_row);
+
 int  orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -34,6 +34,25 @@ struct Patches {
 
 struct Counters { int64_t nodes = 0, tris = 0, leaves = 0; };
 
+// BSP point-location data read by trace.PointLeafnum (raytracer/trace/pointleaf.go:8-33) and
+// clustertable.PointInLeaf (rad/clustertable/point.go:14-38): Nodes{PlaneNum, Children[2]},
+// Planes{Normal, Distance, AxisType}, Leafs{Cluster, Area}, len(Areas).
+struct Bsp {
+    std::vector<int32_t> node_plane, node_children;      // children: 2 per node, negative = -1 - leaf
+    std::vector<float>   plane_normal, plane_dist;
+    std::vector<int32_t> plane_type;
+    std::vector<int32_t> leaf_cluster, leaf_area;
+    int n_areas = 0;
+    bool set = false;
+};
+
+// cache/skycameras.go:8-40 + common/types/skycamera.go (Origin, WorldToSky, SkyToWorld, Area)
+struct SkyCameras {
+    std::vector<float>   origin, world_to_sky, sky_to_world;
+    std::vector<int32_t> area;
+    std::vector<int32_t> area_camera;                    // areaSkyCameras[], -1 = none
+};
+
 } // namespace orc
 
 struct orc_env {
@@ -50,6 +69,9 @@ struct orc_env {
     std::vector<int64_t> rowptr;
     std::vector<int32_t> col;
     std::vector<float>   w;
+    std::vector<float>   tri_color;   // Environment.TriangleColors (raytracer/environment.go:61-63), 3 per triangle
+    orc::Bsp bsp;
+    orc::SkyCameras cams;
 };
 
 namespace orc {
@@ -66,6 +88,11 @@ Hit trace1(const orc_env* e, const float o[3], const float d[3], float tmin, flo
 Hit trace_brute(const orc_env* e, const float o[3], const float d[3], float tmin, float tmax, int32_t skip_id);
 void trace4(const orc_env* e, const float o[3][4], const float d[3][4], const float tmin[4], const float tmax[4],
             int32_t skip_id, int32_t hit_tri[4], float hit_t[4]);
+
+// trace1 with the transparent-triangle rule (coverage != nullptr: CoverageCount semantics,
+// raytracer/types/coverageCount.go:27-37); coverage == nullptr is exactly trace1.
+Hit trace1_coverage(const orc_env* e, const float o[3], const float d[3], float tmin, float tmax,
+                    int32_t skip_id, float* coverage);
 
 // TestLine on one segment: returns 1 if visible.  mode: 0 spec, 2 brute.
 int test_line1(const orc_env* e, const float a[3], const float b[3], int sky_mode, int mode);

@@ -135,6 +135,58 @@ class OracleEnv:
                                       C.c_int(mode), C.c_int(threads)) == 0
         return bits
 
+    # -- full TestLineDoesHitSky surface (oracle/skytrace.cpp) --------------
+    def set_triangle_colors(self, rgb):
+        rgb = _f32(rgb).reshape(-1, 3)
+        assert self._l.orc_env_set_triangle_colors(self._h, C.c_int(rgb.shape[0]), _p(rgb)) == 0
+
+    def bsp_set(self, bsp):
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        npl, nch = i32(bsp.node_plane), i32(bsp.node_children).reshape(-1, 2)
+        pn, pd, pt = _f32(bsp.plane_normal).reshape(-1, 3), _f32(bsp.plane_dist), i32(bsp.plane_type)
+        lc, la = i32(bsp.leaf_cluster), i32(bsp.leaf_area)
+        assert self._l.orc_bsp_set(self._h, C.c_int(npl.shape[0]), _p(npl), _p(nch), C.c_int(pd.shape[0]), _p(pn), _p(pd), _p(pt),
+                                   C.c_int(lc.shape[0]), _p(lc), _p(la), C.c_int(int(bsp.n_areas))) == 0
+        self._n_areas = int(bsp.n_areas)
+
+    def point_leafnum(self, pts):
+        pts = _f32(pts).reshape(-1, 3); out = np.empty(pts.shape[0], np.int32)
+        assert self._l.orc_point_leafnum(self._h, C.c_int64(pts.shape[0]), _p(pts), _p(out)) == 0
+        return out
+
+    def cluster_from_point(self, pts):
+        pts = _f32(pts).reshape(-1, 3); out = np.empty(pts.shape[0], np.int32)
+        assert self._l.orc_cluster_from_point(self._h, C.c_int64(pts.shape[0]), _p(pts), _p(out)) == 0
+        return out
+
+    def process_sky_cameras(self, origins, scales):
+        o = _f32(origins).reshape(-1, 3); s = _f32(scales).reshape(-1)
+        n = self._l.orc_sky_cameras_set(self._h, C.c_int(o.shape[0]), _p(o), _p(s))
+        assert n >= 0
+        return n
+
+    def sky_cameras(self):
+        n = self._l.orc_sky_cameras_get(self._h, None, None, None)
+        cam_area = np.empty(n, np.int32); w2s = np.empty(n, np.float32); area_cam = np.empty(self._n_areas, np.int32)
+        self._l.orc_sky_cameras_get(self._h, _p(cam_area), _p(w2s), _p(area_cam))
+        return cam_area, w2s, area_cam
+
+    def test_lines_sky(self, start_soa, stop_soa, flags=1, static_prop_to_skip=-1, threads=1):
+        s = _f32(start_soa); e = _f32(stop_soa)
+        n = s.shape[1]
+        out = np.empty(n, np.float32)
+        assert self._l.orc_test_lines_sky(self._h, C.c_int64(n), _p(s), _p(e), C.c_int(flags), C.c_int32(static_prop_to_skip),
+                                          _p(out), C.c_int(threads)) == 0
+        return out
+
+    def leafs_trace_to_sky(self, mins, maxs, dirs3, threads=1):
+        mins = np.ascontiguousarray(mins, np.int16).reshape(-1, 3); maxs = np.ascontiguousarray(maxs, np.int16).reshape(-1, 3)
+        d = _f32(dirs3).reshape(-1, 3)
+        out = np.empty(mins.shape[0], np.uint8)
+        assert self._l.orc_leafs_trace_to_sky(self._h, C.c_int(mins.shape[0]), _p(mins), _p(maxs), C.c_int(d.shape[0]), _p(d),
+                                              _p(out), C.c_int(threads)) == 0
+        return out
+
     # -- radiosity ---------------------------------------------------------
     def patches_upload(self, origin, normal, plane_dist, area, refl, cluster=None, flags=None):
         origin = _f32(origin); normal = _f32(normal); plane_dist = _f32(plane_dist); area = _f32(area); refl = _f32(refl)
@@ -197,6 +249,14 @@ def gather_rows(row0, row1, rowptr, col, w, emit, refl, threads=1):
     lib().orc_gather_rows(C.c_int64(row0), C.c_int64(row1), _p(rowptr), _p(col), _p(w), _p(emit), _p(refl),
                           _p(out), C.c_int(threads))
     return out
+
+
+def decompress_vis(data: bytes, n_clusters: int):
+    buf = np.frombuffer(bytes(data), np.uint8)
+    out = np.zeros((n_clusters + 7) // 8, np.uint8)
+    lib().orc_decompress_vis.restype = C.c_int64
+    used = lib().orc_decompress_vis(_p(buf), C.c_int64(buf.shape[0]), C.c_int(n_clusters), _p(out))
+    return out, int(used)
 
 
 def num_threads():

@@ -130,7 +130,7 @@ def test_errors_are_loud(s1_scene):
     with pytest.raises(VradError):
         e.trace_rays(np.zeros((3, 4), np.float32), np.ones((3, 4), np.float32), np.ones(4, np.float32))   # not built
     with pytest.raises(VradError):
-        e.add_triangles(np.array([1], np.int32), np.zeros((1, 9), np.float32), np.array([1], np.uint8))     # transparent
+        e.test_lines(np.zeros((3, 4), np.float32), np.ones((3, 4), np.float32))                             # not built
     e.add_triangles(s1_scene.tri_ids, s1_scene.tri_verts)
     e.setup_acceleration_structure()
     with pytest.raises(VradError):

@@ -26,12 +26,14 @@ constexpr float kFltEpsilon = 1.1920929e-7f;
 //   q0      float4 [n_tris]    nx ny nz d          -- plane, read for every tested triangle
 //   q1      float4 [n_tris]    e0 e1 e2 e3         -- read only when the plane test passes
 //   q2      float4 [n_tris]    e4 e5 id sel|flags  -- id read first for the skip test
+//   tri_cov float  [n_tris]    colour.X of the triangle = its coverage (texture-shadow traces only; may be null)
 struct DevScene {
     const int2*    nodes;
     const int32_t* tri_index;
     const float4*  q0;
     const float4*  q1;
     const float4*  q2;
+    const float*   tri_cov;
     float bmin[3], bmax[3];
     int n_nodes, n_idx, n_tris;
 };
@@ -75,6 +77,31 @@ struct Ray {
 struct TraversalStack {        // lives in local memory (dynamically indexed); kept apart from the
     int   node[kStackMax];     // scalar state so that the scalars stay in registers
     float tmin[kStackMax], tmax[kStackMax];
+};
+
+// CoverageCount state of one ray (raytracer/types/coverageCount.go:16-48): transparent triangles
+// (flag bit 0) add their colour.X to the coverage; the hit is dropped while coverage < 1 and kept once
+// it reaches 1.  A triangle counts once per ray however many leaves hold it (exact list of the counted
+// triangles, 16 entries; a ray that crosses more distinct ones is treated as fully covered) and only
+// when its hit lies before the segment end -- the same rules as oracle/skytrace.cpp.
+// Only the texture-shadow kernels instantiate this.
+constexpr int kCoverList = 16;
+struct Coverage {
+    float cov;
+    int   n;
+    int   counted[kCoverList];
+    __device__ __forceinline__ void reset() { cov = 0.0f; n = 0; }
+    // returns true when the hit is to be kept
+    __device__ __forceinline__ bool visit(const float* __restrict__ tri_cov, int ti) {
+        for (int k = 0; k < n; k++) if (counted[k] == ti) return false;
+        if (n == kCoverList) cov = 1.0f;
+        else {
+            counted[n++] = ti;
+            const float c = tri_cov ? __ldg(&tri_cov[ti]) : 0.0f;
+            cov = min_sel(cov + c, 1.0f);
+        }
+        return cov == 1.0f;
+    }
 };
 
 struct Traversal {
@@ -138,8 +165,9 @@ struct Traversal {
     // phase 2: the leaf's triangles in two converged sub-phases per round -- (A) every lane scans
     // forward to its next triangle whose plane hit is in range (cheap, one 16-B load each), (B) the
     // lanes that found one run the projected edge tests together -- then terminate or pop.
-    template <bool ANY_HIT>
-    __device__ __forceinline__ void leaf(const DevScene& S, TraversalStack& st, int2 nd, int skip_id, float any_len) {
+    template <bool ANY_HIT, bool COVER = false>
+    __device__ __forceinline__ void leaf(const DevScene& S, TraversalStack& st, int2 nd, int skip_id, float any_len,
+                                         Coverage* cv = nullptr) {
         const int start = nd.x >> 2;
         int cnt = active ? (int)__int_as_float(nd.y) : 0;
         int k = 0;
@@ -172,8 +200,12 @@ struct Traversal {
                 const float b1 = ((b.w * c0) + (c.x * c1)) + c.y;
                 const bool inside = (b0 >= 0.0f) && (b1 >= 0.0f) && ((b0 + b1) <= 1.0f);
                 if (inside && __float_as_int(c.z) != skip_id) {
-                    hit_tri = cand; hit_t = tc;
-                    if (ANY_HIT) { active = false; cnt = 0; }
+                    bool keep = true;
+                    if (COVER) { if ((sel >> 16) & 1) keep = (tc < any_len) && cv->visit(S.tri_cov, cand); }   // any_len = the ray's own tmax
+                    if (keep) {
+                        hit_tri = cand; hit_t = tc;
+                        if (ANY_HIT) { active = false; cnt = 0; }
+                    }
                 }
             }
         }
@@ -197,6 +229,21 @@ __device__ __forceinline__ void trace_ray(const DevScene& S, const Ray& r, bool 
         T.leaf<ANY_HIT>(S, st, nd, skip_id, any_len);
     }
     hit_tri = T.hit_tri; hit_t = T.hit_t;
+}
+
+// closest hit with the transparent-triangle coverage rule; cov_out = accumulated coverage of the ray
+__device__ __forceinline__ void trace_ray_cover(const DevScene& S, const Ray& r, bool valid, float tmin, float tmax,
+                                                int skip_id, int& hit_tri, float& hit_t, float& cov_out) {
+    Traversal T;
+    TraversalStack st;
+    Coverage cv;
+    cv.reset();
+    T.begin(S, r, valid, tmin, tmax);
+    while (__any_sync(0xffffffffu, T.active)) {
+        const int2 nd = T.descend(S, st);
+        T.leaf<false, true>(S, st, nd, skip_id, tmax, &cv);
+    }
+    hit_tri = T.hit_tri; hit_t = T.hit_t; cov_out = cv.cov;
 }
 
 // trace.TestLine front end (raytracer/trace/testline.go:22-27): segment -> normalised ray.

@@ -59,6 +59,19 @@ struct TransfersDev {
     bool ready = false;
 };
 
+// BSP point-location data on the device (trace.PointLeafnum, clustertable.PointInLeaf) and the sky cameras.
+//   nodes   int4   [n_nodes]  {plane, child0, child1, plane axis type}  -- one 128-bit load per step
+//   planes  float4 [n_planes] {normal.xyz, dist}
+struct DevBsp {
+    const int4*    nodes;
+    const float4*  planes;
+    const int32_t* leaf_cluster;
+    const int32_t* leaf_area;
+    const int32_t* area_camera;    // areaSkyCameras[n_areas], -1 = none (cache/skycameras.go:10)
+    const float4*  cams;           // {origin.xyz, WorldToSky} per sky camera
+    int n_nodes, n_leafs, n_areas, n_cams;
+};
+
 constexpr int kMaxWorld = 8;
 
 // Peer-memory view of the radiance buffers (multi-GPU K4): pointers into every rank's er[0]/er[1]
@@ -107,7 +120,18 @@ struct vrad_env {
     vrad::DevBuf<int2> d_nodes;
     vrad::DevBuf<int32_t> d_tri_index;
     vrad::DevBuf<float4> d_q0, d_q1, d_q2;
+    vrad::DevBuf<float> d_tri_cov;     // colour.X per triangle (coverage of transparent triangles)
+    std::vector<float> h_colors;       // Environment.TriangleColors, 3 per triangle
     vrad::DevScene scene{};
+
+    // BSP lumps + sky cameras (f2)
+    vrad::DevBuf<int4> d_bsp_nodes;
+    vrad::DevBuf<float4> d_bsp_planes, d_cams;
+    vrad::DevBuf<int32_t> d_leaf_cluster, d_leaf_area, d_area_camera;
+    vrad::DevBsp bsp{};
+    bool bsp_ready = false;
+    std::vector<int32_t> h_cam_area, h_area_camera;
+    std::vector<float> h_cam_w2s;
 
     // second stream + double-buffered staging for the pipelined host-buffer paths
     cudaStream_t copy_stream = nullptr;
@@ -149,5 +173,6 @@ int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, 
                       int32_t* hit_tri, int32_t* hit_sid, float* hit_t, float* normal_soa);
 int launch_test_lines(vrad_env* e, int64_t n, const float* start_soa, const float* stop_soa, int sky_mode, uint32_t* bits);
 int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, int sky_mode, uint32_t* d_bits);
+int upload_triangle_coverage(vrad_env* e);
 
 } // namespace vrad

@@ -99,7 +99,22 @@ static int upload_scene(vrad_env* e) {
     S.nodes = e->d_nodes.p; S.tri_index = e->d_tri_index.p; S.q0 = e->d_q0.p; S.q1 = e->d_q1.p; S.q2 = e->d_q2.p;
     for (int c = 0; c < 3; c++) { S.bmin[c] = T.bmin[c]; S.bmax[c] = T.bmax[c]; }
     S.n_nodes = (int)nn; S.n_idx = (int)ni; S.n_tris = (int)nt;
+    S.tri_cov = nullptr;
     e->built = true;
+    return upload_triangle_coverage(e);
+}
+
+// colour.X per triangle -> device (coverage of transparent triangles, coverageCount.go:29)
+int upload_triangle_coverage(vrad_env* e) {
+    if (!e->built || e->h_colors.empty()) return 0;
+    const size_t nt = e->h_tris.size();
+    if (e->h_colors.size() != 3 * nt) { set_error("triangle colours: %zu given for %zu triangles", e->h_colors.size() / 3, nt); return VRAD_E_INVALID; }
+    if (e->d_tri_cov.alloc(nt ? nt : 1)) { set_error("out of device memory for triangle colours"); return VRAD_E_NOMEM; }
+    std::vector<float> cov(nt);
+    for (size_t i = 0; i < nt; i++) cov[i] = e->h_colors[3 * i];
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(e->d_tri_cov.p, cov.data(), nt * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->scene.tri_cov = e->d_tri_cov.p;
     return 0;
 }
 
@@ -153,6 +168,8 @@ void vrad_env_destroy(vrad_env* e) {
     cudaStreamSynchronize(e->stream);
     vrad_comm_destroy_internal(e);
     e->d_nodes.release(); e->d_tri_index.release(); e->d_q0.release(); e->d_q1.release(); e->d_q2.release();
+    e->d_tri_cov.release(); e->d_bsp_nodes.release(); e->d_bsp_planes.release(); e->d_cams.release();
+    e->d_leaf_cluster.release(); e->d_leaf_area.release(); e->d_area_camera.release();
     for (auto& s : e->scratch) s.release();
     e->patches.origin_area.release(); e->patches.normal_dist.release(); e->patches.refl.release(); e->patches.cluster.release();
     e->transfers.rowptr.release(); e->transfers.rowlen.release(); e->transfers.tr.release();
@@ -203,17 +220,20 @@ void vrad_host_free(void* p) { if (p) cudaFreeHost(p); }
 int vrad_env_add_triangles(vrad_env* e, int n, const int32_t* ids, const float* verts9, const uint8_t* flags) {
     if (!e || n < 0 || (n > 0 && (!ids || !verts9))) { set_error("vrad_env_add_triangles: bad arguments"); return VRAD_E_INVALID; }
     if (e->built) { set_error("vrad_env_add_triangles: acceleration structure already built"); return VRAD_E_STATE; }
-    for (int i = 0; i < n; i++) {
-        uint8_t f = flags ? flags[i] : 0;
-        if (f & 0x01) {   // FCACHETRI_TRANSPARENT needs ITransparentTriangleCallback (raytracer/types/coverageCount.go:11-13)
-            set_error("vrad_env_add_triangles: transparent triangles are not supported (callback cannot run in a kernel)");
-            return VRAD_E_UNSUPPORTED;
-        }
-    }
     e->h_ids.insert(e->h_ids.end(), ids, ids + n);
     e->h_verts.insert(e->h_verts.end(), verts9, verts9 + 9 * (size_t)n);
     if (flags) e->h_flags.insert(e->h_flags.end(), flags, flags + n); else e->h_flags.insert(e->h_flags.end(), n, 0);
     return VRAD_OK;
+}
+
+int vrad_env_set_triangle_colors(vrad_env* e, int n, const float* rgb3) {
+    if (!e || n < 0 || (n > 0 && !rgb3)) { set_error("vrad_env_set_triangle_colors: bad arguments"); return VRAD_E_INVALID; }
+    const size_t have = e->built ? e->h_tris.size() : e->h_ids.size();
+    if ((size_t)n != have) { set_error("vrad_env_set_triangle_colors: %d colours for %zu triangles", n, have); return VRAD_E_INVALID; }
+    e->h_colors.assign(rgb3, rgb3 + 3 * (size_t)n);
+    if (!e->built) return VRAD_OK;
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    return upload_triangle_coverage(e);
 }
 
 int vrad_env_build(vrad_env* e) {

@@ -22,6 +22,8 @@ TRACE_ID_SKY = 0x01000000         # raytracer/constants.go:9-11
 TRACE_ID_OPAQUE = 0x02000000
 TRACE_ID_STATICPROP = 0x04000000
 KDNODE_STATE_LEAF = 3             # raytracer/constants.go:16
+TRI_TRANSPARENT = 0x01            # TriIntersectData.NFlags bit (upstream FCACHETRI_TRANSPARENT)
+TL_CAN_RECURSE, TL_TEXTURE_SHADOWS, TL_PACKET_LEAF = 1, 2, 4   # vrad_test_lines_sky flags
 
 
 def _is_torch(a):
@@ -182,6 +184,68 @@ class Environment:
         check(self._l.vrad_test_lines(self._h, C.c_int64(n), ptr(s), ptr(e), C.c_int(sky_mode), ptr(out)))
         return out
 
+    # ---- full TestLineDoesHitSky surface: colours, BSP lumps, sky cameras (section 8 f2) -----
+    def set_triangle_colors(self, rgb):                                             # environment.go:61-63, :430-432
+        self._flush_pending()
+        rgb = np.ascontiguousarray(rgb, np.float32).reshape(-1, 3)
+        check(self._l.vrad_env_set_triangle_colors(self._h, C.c_int(rgb.shape[0]), ptr(rgb)))
+
+    def bsp_upload(self, bsp):
+        """bsp: scenes.Bsp (Nodes/Planes/Leafs lumps as flat arrays)."""
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        node_plane, node_children = i32(bsp.node_plane), i32(bsp.node_children).reshape(-1, 2)
+        pn, pd, pt = _f32(bsp.plane_normal).reshape(-1, 3), _f32(bsp.plane_dist), i32(bsp.plane_type)
+        lc, la = i32(bsp.leaf_cluster), i32(bsp.leaf_area)
+        check(self._l.vrad_bsp_upload(self._h, C.c_int(node_plane.shape[0]), ptr(node_plane), ptr(node_children),
+                                      C.c_int(pd.shape[0]), ptr(pn), ptr(pd), ptr(pt), C.c_int(lc.shape[0]), ptr(lc), ptr(la),
+                                      C.c_int(int(bsp.n_areas))))
+        self._n_areas = int(bsp.n_areas)
+
+    def point_leafnum(self, pts):                                                   # pointleaf.go:8-33
+        pts = _f32(pts).reshape(-1, 3)
+        out = np.empty(pts.shape[0], np.int32)
+        check(self._l.vrad_point_leafnum(self._h, C.c_int64(pts.shape[0]), ptr(pts), ptr(out)))
+        return out
+
+    def cluster_from_point(self, pts):                                              # clustertable/point.go:10-38
+        pts = _f32(pts).reshape(-1, 3)
+        out = np.empty(pts.shape[0], np.int32)
+        check(self._l.vrad_cluster_from_point(self._h, C.c_int64(pts.shape[0]), ptr(pts), ptr(out)))
+        return out
+
+    def process_sky_cameras(self, origins, scales):                                 # rad/cameras/skycamera.go:10-49
+        o = _f32(origins).reshape(-1, 3); s = _f32(scales).reshape(-1)
+        kept = C.c_int()
+        check(self._l.vrad_sky_cameras_set(self._h, C.c_int(o.shape[0]), ptr(o), ptr(s), C.byref(kept)))
+        return kept.value
+
+    def sky_cameras(self):
+        n = C.c_int()
+        check(self._l.vrad_sky_cameras_get(self._h, C.byref(n), None, None, None))
+        cam_area = np.empty(n.value, np.int32); w2s = np.empty(n.value, np.float32)
+        area_cam = np.empty(getattr(self, "_n_areas", 0), np.int32)
+        check(self._l.vrad_sky_cameras_get(self._h, C.byref(n), ptr(cam_area), ptr(w2s), ptr(area_cam)))
+        return cam_area, w2s, area_cam
+
+    def test_lines_sky(self, start_soa, stop_soa, flags=TL_CAN_RECURSE, static_prop_to_skip=-1, out=None):
+        """Batched, complete TestLineDoesHitSky: [3, n] SoA endpoints -> fractionVisible[n]."""
+        s = _f32(start_soa); e = _f32(stop_soa)
+        n = int(s.shape[1])
+        if out is None:
+            if _is_torch(s):
+                import torch
+                out = torch.empty(n, dtype=torch.float32, device=s.device)
+            else:
+                out = np.empty(n, np.float32)
+        check(self._l.vrad_test_lines_sky(self._h, C.c_int64(n), ptr(s), ptr(e), C.c_int(flags), C.c_int32(static_prop_to_skip), ptr(out)))
+        return out
+
+    def leafs_trace_to_sky(self, mins, maxs):                                       # lightmap.go:425-451
+        mins = np.ascontiguousarray(mins, np.int16).reshape(-1, 3); maxs = np.ascontiguousarray(maxs, np.int16).reshape(-1, 3)
+        out = np.empty(mins.shape[0], np.uint8)
+        check(self._l.vrad_leafs_trace_to_sky(self._h, C.c_int(mins.shape[0]), ptr(mins), ptr(maxs), ptr(out)))
+        return out
+
     # ---- patches / K2 / K3 / K4 --------------------------------------------------------
     def patches_upload(self, origin, normal, plane_dist, area, refl, cluster=None, flags=None):
         origin = _f32(origin); normal = _f32(normal); plane_dist = _f32(plane_dist); area = _f32(area); refl = _f32(refl)
@@ -275,18 +339,37 @@ def environment_from_scene(scene, device=0, rank=0, world=1, with_patches=True) 
     return env
 
 
-def test_line_does_hit_sky(env: Environment, start_xyz4, stop_xyz4, can_recurse=True, static_prop_to_skip=-1, do_debug=False):
+def test_line_does_hit_sky(env: Environment, start_xyz4, stop_xyz4, can_recurse=True, static_prop_to_skip=-1, do_debug=False,
+                           texture_shadows=False):
     """trace.TestLineDoesHitSky for one FourVectors pair (raytracer/trace/testline.go:18-94).
 
-    Returns fractionVisible[4].  The 3D-skybox recursion (:57-89) needs BSP leaf/area data that the
-    synthetic path does not carry; it is a listed NEXT row, so `can_recurse`
-    is accepted and ignored.
+    Returns fractionVisible[4].  As in the reference the leaf that decides the 3D-skybox recursion is
+    the one of lane 0 (`start.Vec(0)`, :63); `texture_shadows` is the package variable of :14.
     """
     s = np.ascontiguousarray(start_xyz4, np.float32).reshape(3, 4)
     e = np.ascontiguousarray(stop_xyz4, np.float32).reshape(3, 4)
-    bits = env.test_lines(s, e, sky_mode=1)
-    word = int(bits[0])
-    return np.array([1.0 if (word >> i) & 1 else 0.0 for i in range(4)], np.float32)
+    flags = TL_PACKET_LEAF | (TL_CAN_RECURSE if can_recurse else 0) | (TL_TEXTURE_SHADOWS if texture_shadows else 0)
+    return env.test_lines_sky(s, e, flags, static_prop_to_skip)
+
+
+def decompress_vis(data: bytes, n_clusters: int):
+    """lightmap.DecompressVis (rad/lightmap/vis.go:54-94): one PVS row -> ((n_clusters+7)//8 bytes, input bytes used)."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    out = np.zeros((n_clusters + 7) // 8, np.uint8)
+    used = _lib.load().vrad_decompress_vis(ptr(buf), C.c_int64(buf.shape[0]), C.c_int(n_clusters), ptr(out))
+    if used < 0:
+        raise VradError(int(used), _lib.load().vrad_last_error().decode("utf-8", "replace"))
+    return out, int(used)
+
+
+def pvs_from_vis_lump(n_clusters: int, byteofs, visdata: bytes):
+    """The visibility lump -> the [C, C] byte matrix `Environment.build_transfers` takes (vis.go:9-47)."""
+    ofs = np.ascontiguousarray(byteofs, np.int32).reshape(-1, 2)
+    assert ofs.shape[0] == n_clusters
+    buf = np.frombuffer(bytes(visdata), np.uint8)
+    out = np.empty((n_clusters, n_clusters), np.uint8)
+    check(_lib.load().vrad_pvs_from_vis_lump(C.c_int(n_clusters), ptr(ofs), ptr(buf), C.c_int64(buf.shape[0]), ptr(out)))
+    return out
 
 
 def row_partition(n_rows: int, world: int):

@@ -24,6 +24,9 @@ SYMBOLS = [
     "vrad_test_lines", "vrad_patches_upload", "vrad_build_transfers", "vrad_transfers_upload", "vrad_transfers_info",
     "vrad_transfers_download", "vrad_transfers_download_rows", "vrad_set_sky_dirs", "vrad_direct_light", "vrad_bounce", "vrad_comm_unique_id",
     "vrad_comm_init", "vrad_version",
+    "vrad_env_set_triangle_colors", "vrad_bsp_upload", "vrad_point_leafnum", "vrad_cluster_from_point",
+    "vrad_sky_cameras_set", "vrad_sky_cameras_get", "vrad_test_lines_sky", "vrad_leafs_trace_to_sky",
+    "vrad_decompress_vis", "vrad_pvs_from_vis_lump",
 ]
 
 
@@ -57,6 +60,7 @@ def load(build_if_missing: bool = True):
     lib.vrad_host_free.argtypes = [C.c_void_p]
     lib.vrad_env_destroy.argtypes = [C.c_void_p]
     lib.vrad_env_destroy.restype = None
+    lib.vrad_decompress_vis.restype = C.c_int64
     _lib = lib
     return lib
 

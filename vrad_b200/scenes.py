@@ -437,3 +437,183 @@ def outdoor(seed: int = 0x5EED0003, cells: int = 708, cell: float = 46.0, n_buil
     lights[1]["type"] = EMIT_SKYAMBIENT; lights[1]["intensity"] = (40.0, 50.0, 70.0)
     return Scene("S3_outdoor", ids, verts, flags, origin, normal, plane_dist, area, refl, cluster, np.zeros(N, np.uint8),
                  nt * nt, pvs, origin, normal, lights, {"seed": seed, "cells": cells, "n_buildings": n_buildings})
+
+
+@dataclass
+class Bsp:
+    """The lumps trace.PointLeafnum (raytracer/trace/pointleaf.go:8-33) and clustertable.PointInLeaf
+    (rad/clustertable/point.go:14-38) walk, as flat arrays: Nodes{PlaneNum, Children[2]} (negative child =
+    -1 - leaf), Planes{Normal, Distance, AxisType}, Leafs{Cluster, Area, Mins, Maxs}, len(Areas)."""
+    node_plane: np.ndarray
+    node_children: np.ndarray      # int32 [n_nodes, 2]
+    plane_normal: np.ndarray       # float32 [n_planes, 3]
+    plane_dist: np.ndarray
+    plane_type: np.ndarray         # 0,1,2 = axial x,y,z; >= 3 = general (dot-product path)
+    leaf_cluster: np.ndarray
+    leaf_area: np.ndarray
+    leaf_mins: np.ndarray          # int16 [n_leafs, 3]
+    leaf_maxs: np.ndarray
+    n_areas: int
+
+
+class _BspBuilder:
+    def __init__(self):
+        self.nodes, self.planes, self.leafs = [], [], []
+
+    def plane(self, normal, dist, ptype):
+        self.planes.append((tuple(float(v) for v in normal), float(dist), int(ptype)))
+        return len(self.planes) - 1
+
+    def leaf(self, cluster, area, mins=(0, 0, 0), maxs=(0, 0, 0)):
+        self.leafs.append((int(cluster), int(area), tuple(mins), tuple(maxs)))
+        return -1 - (len(self.leafs) - 1)
+
+    def node(self, plane):
+        """Reserve a node (parents before children, as in a BSP lump); fill with set_children."""
+        self.nodes.append([plane, 0, 0])
+        return len(self.nodes) - 1
+
+    def set_children(self, node, front, back):
+        self.nodes[node][1], self.nodes[node][2] = front, back
+
+    def finish(self, n_areas) -> Bsp:
+        nd = np.asarray(self.nodes, np.int32).reshape(-1, 3)
+        return Bsp(nd[:, 0].copy(), nd[:, 1:3].copy(),
+                   np.asarray([p[0] for p in self.planes], np.float32).reshape(-1, 3),
+                   np.asarray([p[1] for p in self.planes], np.float32), np.asarray([p[2] for p in self.planes], np.int32),
+                   np.asarray([l[0] for l in self.leafs], np.int32), np.asarray([l[1] for l in self.leafs], np.int32),
+                   np.asarray([l[2] for l in self.leafs], np.int16).reshape(-1, 3),
+                   np.asarray([l[3] for l in self.leafs], np.int16).reshape(-1, 3), n_areas)
+
+
+def sky_room(seed: int = 0x5EED0004, n_boxes: int = 40, n_panes: int = 24) -> Scene:
+    """Scene for the complete TestLineDoesHitSky surface: the S1 room with a
+    TRACE_ID_SKY ceiling, a static prop (TRACE_ID_STATICPROP | 7), transparent panes with per-triangle
+    coverage colours, a closed opaque bunker, and two 3D sky boxes far outside the room, each with a
+    sky_camera (scales 16 and 32; a third camera entity has scale 0 and is dropped).  meta carries the BSP
+    lumps (`bsp`), the camera entities and the triangle colours."""
+    rng = SplitMix64(seed)
+    sx, sy, sz = 1024.0, 1024.0, 512.0
+    x0, y0, z0 = -sx / 2, -sy / 2, 0.0
+    g = _Geom()
+    faces = _room_faces(x0, y0, z0, sx, sy, sz)
+    for k, f in enumerate(faces):
+        _face_quad(g, TRACE_ID_SKY if k == 1 else TRACE_ID_OPAQUE, f)          # loadbsp/main.go:255 sky sides
+    mins, maxs = _place_boxes(rng, n_boxes, x0, y0, x0 + sx, y0 + sy, z0)
+    g.add_box_array(TRACE_ID_OPAQUE, mins, maxs)
+    first = len(g.ids)
+    g.add_box(TRACE_ID_STATICPROP | 7, (-60.0, -60.0, 300.0), (60.0, 60.0, 340.0))    # a floating static prop:
+    g.ids[first:] = [TRACE_ID_STATICPROP | 7] * (len(g.ids) - first)                   # every triangle carries the prop id
+    g.add_box(TRACE_ID_OPAQUE, (300.0, 300.0, 100.0), (428.0, 428.0, 228.0))          # bunker (hollow, closed)
+    n_opaque = len(g.ids)
+    # transparent panes: horizontal quads between z=360 and z=480, stacked so a ray can cross several
+    colors = []
+    for k in range(n_panes):
+        p = rng.uniform(5)
+        cx, cy = -400.0 + 800.0 * float(p[0]), -400.0 + 800.0 * float(p[1])
+        w, z = 80.0 + 160.0 * float(p[2]), 360.0 + 120.0 * float(p[3])
+        g.add_quad(TRACE_ID_OPAQUE, (cx - w, cy - w, z), (cx + w, cy - w, z), (cx + w, cy + w, z), (cx - w, cy + w, z))
+        cov = (0.25, 0.5, 0.75, 1.0)[k % 4] if k % 5 else float(np.float32(p[4]))
+        colors += [cov, cov]
+    n_world = len(g.ids)
+    # 3D sky boxes: sky faces outside, opaque "mountains" inside
+    sky = [((8192.0, 0.0, 0.0), 16.0), ((8192.0, 4096.0, 0.0), 32.0)]
+    for (c, scale) in sky:
+        hx, hz = 256.0, 160.0
+        g.add_box(TRACE_ID_SKY, (c[0] - hx, c[1] - hx, c[2] - 16.0), (c[0] + hx, c[1] + hx, c[2] + hz))
+        for m in range(6):
+            q = rng.uniform(4)
+            mx_, my_ = c[0] - 200.0 + 400.0 * float(q[0]), c[1] - 200.0 + 400.0 * float(q[1])
+            if abs(mx_ - c[0]) < 48.0 and abs(my_ - c[1]) < 48.0:
+                mx_ += 96.0
+            s_ = 20.0 + 40.0 * float(q[2]); h_ = 60.0 + 90.0 * float(q[3])
+            g.add_box(TRACE_ID_OPAQUE, (mx_ - s_, my_ - s_, c[2] - 16.0), (mx_ + s_, my_ + s_, c[2] + h_))
+    ids, verts, flags = g.arrays()
+    flags[n_opaque:n_world] = 1                                                # transparent panes
+    tri_colors = np.zeros((ids.shape[0], 3), np.float32)
+    tri_colors[:, :] = 1.0
+    tri_colors[n_opaque:n_world, 0] = np.asarray(colors, np.float32)
+
+    # BSP: root splits world | sky boxes; world side: solid below the floor (cluster -1), then x/y quadrants
+    # with one general (non-axial) plane; sky side: one leaf per sky box.  Areas: 0 solid, 1 world, 2/3 sky boxes.
+    b = _BspBuilder()
+    n_root = b.node(b.plane((1, 0, 0), 4096.0, 0))
+    n_sky = b.node(b.plane((0, 1, 0), 2048.0, 1))
+    n_floor = b.node(b.plane((0, 0, 1), 0.0, 2))
+    b.set_children(n_root, n_sky, n_floor)
+    b.set_children(n_sky, b.leaf(5, 3, (7936, 3840, -16), (8448, 4352, 160)), b.leaf(4, 2, (7936, -256, -16), (8448, 256, 160)))
+    n_x = b.node(b.plane((1, 0, 0), 0.0, 0))
+    b.set_children(n_floor, n_x, b.leaf(-1, 0, (-512, -512, -64), (512, 512, 0)))
+    n_diag = b.node(b.plane((0.6, 0.8, 0.0), 100.0, 3))                        # general plane: dot-product path
+    n_y = b.node(b.plane((0, 1, 0), 0.0, 1))
+    b.set_children(n_x, n_diag, n_y)
+    b.set_children(n_diag, b.leaf(0, 1, (0, -512, 0), (512, 512, 512)), b.leaf(1, 1, (0, -512, 0), (300, 200, 512)))
+    b.set_children(n_y, b.leaf(2, 1, (-512, 0, 0), (0, 512, 512)), b.leaf(3, 1, (-512, -512, 0), (0, 0, 512)))
+    bsp = b.finish(4)
+
+    cams_origin = np.asarray([[8192.0, 0.0, 24.0], [0.0, 0.0, 100.0], [8192.0, 4096.0, 24.0]], np.float32)
+    cams_scale = np.asarray([16.0, 0.0, 32.0], np.float32)                     # the second entity is dropped (scale <= 0)
+    # "leafs" for CanLeafTraceToSky: BSP leaf bounds + probe boxes (inside the bunker, under a wide pane, ...)
+    probe_mins = np.asarray([[332, 332, 132], [-400, -400, 10], [8100, -60, 0], [-64, -64, 200]], np.int16)
+    probe_maxs = np.asarray([[396, 396, 196], [-300, -300, 90], [8160, 60, 60], [64, 64, 280]], np.int16)
+    meta = {"seed": seed, "bsp": bsp, "cams_origin": cams_origin, "cams_scale": cams_scale, "tri_colors": tri_colors,
+            "n_opaque": n_opaque, "n_world": n_world,
+            "probe_mins": np.concatenate([bsp.leaf_mins, probe_mins]), "probe_maxs": np.concatenate([bsp.leaf_maxs, probe_maxs])}
+    return Scene("S4_sky_room", ids, verts, flags, meta=meta)
+
+
+def sky_segments(scene: Scene, n: int, seed: int = 0x5C1) -> tuple[np.ndarray, np.ndarray]:
+    """Segments for the sky test: starts inside the room (some inside a sky box, some below the floor), stops far
+    along mostly-upward directions; every 97th segment has zero length."""
+    rng = SplitMix64(seed)
+    a = np.stack([rng.uniform(n, -500, 500), rng.uniform(n, -500, 500), rng.uniform(n, 4, 500)])
+    z = rng.uniform(n, 0.05, 1.0).astype(np.float64)
+    side = rng.integers(n, 8)
+    z[side == 0] *= -1.0                                                      # some point down / sideways
+    phi = rng.uniform(n, 0.0, 2.0 * math.pi).astype(np.float64)
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    d = np.stack([r * np.cos(phi), r * np.sin(phi), z])
+    ln = rng.uniform(n, 50.0, 30000.0).astype(np.float64)
+    insky = side == 1                                                         # start inside sky box 0 (its area has a camera)
+    a[0, insky] = 8192.0 + a[0, insky] * 0.4; a[1, insky] *= 0.4; a[2, insky] = 2.0 + a[2, insky] * 0.25
+    below = side == 2
+    a[2, below] = -10.0                                                       # solid leaf (area 0 has no camera either)
+    b = (a.astype(np.float64) + d * ln).astype(np.float32)
+    zero = (np.arange(n) % 97) == 5
+    b[:, zero] = a[:, zero]
+    return np.ascontiguousarray(a.astype(np.float32)), np.ascontiguousarray(b)
+
+
+def mini_sky_scene():
+    """Hand-made scene for known answers: floor, TRACE_ID_SKY ceiling at z=512, a static prop (id 7) at z=300 over
+    the origin, and three transparent panes over x in [100,200] (the third only over [150,200]) with coverages
+    0.25, 0.5, 0.5 at z = 400, 420, 440."""
+    ids, verts, flags, cols = [], [], [], []
+
+    def quad(tid, x0, x1, y0, y1, z, flag=0, cov=1.0):
+        for tri in (((x0, y0, z), (x1, y0, z), (x1, y1, z)), ((x0, y0, z), (x1, y1, z), (x0, y1, z))):
+            ids.append(tid); verts.append([c for v in tri for c in v]); flags.append(flag); cols.append([cov, 0.0, 0.0])
+    quad(TRACE_ID_OPAQUE, -512, 512, -512, 512, 0)
+    quad(TRACE_ID_SKY, -512, 512, -512, 512, 512)
+    quad(TRACE_ID_STATICPROP | 7, -60, 60, -60, 60, 300)
+    quad(TRACE_ID_OPAQUE, 100, 200, -50, 50, 400, 1, 0.25)
+    quad(TRACE_ID_OPAQUE, 100, 200, -50, 50, 420, 1, 0.5)
+    quad(TRACE_ID_OPAQUE, 150, 200, -50, 50, 440, 1, 0.5)
+    return (np.asarray(ids, np.int32), np.asarray(verts, np.float32), np.asarray(flags, np.uint8), np.asarray(cols, np.float32))
+
+
+MINI_SKY_CASES = [
+    # start, stop, flags, prop to skip, expected fractionVisible
+    ((0, 0, 100), (0, 0, 5000), 0, -1, 0.0),        # the prop blocks
+    ((0, 0, 100), (0, 0, 5000), 0, 7, 1.0),         # prop 7 skipped (testline.go:36); the ceiling is sky (:46-48)
+    ((0, 0, 100), (0, 0, 5000), 0, 8, 0.0),         # another prop id does not help
+    ((0, 0, 100), (0, 0, 250), 0, -1, 1.0),         # ends below the prop
+    ((300, 0, 100), (300, 0, -50), 0, -1, 0.0),     # the floor is an ordinary blocker
+    ((120, 0, 100), (120, 0, 5000), 0, -1, 0.0),    # no callback: a transparent pane blocks like any triangle
+    ((120, 0, 100), (120, 0, 5000), 2, -1, 0.25),   # coverage 0.25 + 0.5 (coverageCount.go:29-30)
+    ((120, 0, 100), (120, 0, 410), 2, -1, 0.75),    # only the first pane lies before the segment end
+    ((170, 0, 100), (170, 0, 5000), 2, -1, 0.0),    # 0.25 + 0.5 + 0.5 clamps to 1: fully covered
+    ((170, 0, 100), (170, 0, 430), 2, -1, 0.25),
+    ((170, 0, 450), (170, 0, 100), 2, -1, 0.0),     # downwards through all three, then the floor is beyond the end
+    ((50, 50, 50), (50, 50, 50), 3, -1, 1.0),       # zero-length segment: visible
+]
