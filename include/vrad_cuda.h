@@ -182,6 +182,30 @@ int64_t vrad_decompress_vis(const uint8_t* in, int64_t in_len, int n_clusters, u
  * with offset -1 sees nothing.  Host-only helper. */
 int  vrad_pvs_from_vis_lump(int n_clusters, const int32_t* byteofs2, const uint8_t* visdata, int64_t vis_len, uint8_t* pvs_out);
 
+/* ---- patch hierarchy --------------------------------------------- */
+/* One face as MakePatchForFace sees it (rad/patches/face.go:29-197). */
+typedef struct {
+    int32_t first_point, n_points;   /* the face winding: points3[3*first_point ...], n_points <= 64 */
+    float   normal[3], plane_dist;   /* patch.Plane (face.go:119-142) */
+    float   lux_scale;               /* patch.LuxScale = mean length of the two lightmap vectors (face.go:83-109); 1/16 by default */
+    float   chop;                    /* patch.Chop = maxChop (face.go:24,111) */
+    uint8_t sky;                     /* patch.Sky = IsSky(f) (face.go:106) */
+    uint8_t no_subdivide;            /* PreventSubdivision (subdivide.go:151-165) or a displacement face (:60) */
+    uint8_t has_base_light;          /* BaseLight != 0: no edge-of-face chop rule (subdivide.go:389-392) */
+    uint8_t pad;
+} vrad_face_patch;                   /* 36 bytes */
+/* patches.MakePatchForFace + SubdividePatches / SubdividePatch / ClipWindingEpsilon / CreateChildPatch /
+ * WindingAreaAndBalancePoint (rad/patches/face.go:29-197, subdivide.go:25-66,167-437).  Host-only helper (no
+ * device needed).  Patches come out in the reference's order: one root per non-degenerate face, then the children
+ * depth first (child1's subtree before child2's).  min_chop = minChop (face.go:25).  Output arrays may be NULL;
+ * *n_patches_out / *n_points_out always receive the sizes; VRAD_E_NOMEM when max_patches / max_points are too
+ * small (call once with 0 capacities to size the buffers). */
+int  vrad_patches_subdivide(int n_faces, const vrad_face_patch* faces, const float* points3, float min_chop,
+                            int max_patches, int max_points, int* n_patches_out, int* n_points_out,
+                            float* origin3, float* normal3, float* plane_dist, float* area, float* mins3, float* maxs3,
+                            float* chop, int32_t* parent, int32_t* child1, int32_t* child2, int32_t* face,
+                            int32_t* wind_first, int32_t* wind_count, float* wind_points3);
+
 /* ---- patches, K2 transfers, K3 direct light, K4 bounce ---------------------------------- */
 /* fields of common/types/patch.go:9-64 the kernels read (leaf patches only) */
 int  vrad_patches_upload(vrad_env*, int n, const float* origin3, const float* normal3, const float* plane_dist,

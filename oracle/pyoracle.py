@@ -251,6 +251,32 @@ def gather_rows(row0, row1, rowptr, col, w, emit, refl, threads=1):
     return out
 
 
+def subdivide_patches(faces, points, min_chop=4.0):
+    """oracle/patches.cpp; faces: structured array with the vrad_face_patch fields."""
+    points = _f32(points).reshape(-1, 3)
+    col = lambda k, t: np.ascontiguousarray(faces[k], t)
+    args_in = [col("first_point", np.int32), col("n_points", np.int32), col("normal", np.float32), col("plane_dist", np.float32),
+               col("lux_scale", np.float32), col("chop", np.float32), col("sky", np.uint8), col("no_subdivide", np.uint8),
+               col("has_base_light", np.uint8)]
+    n_, m_ = C.c_int(), C.c_int()
+    L = lib()
+    rc = L.orc_patches_subdivide(C.c_int(len(faces)), *[_p(a) for a in args_in], _p(points), C.c_float(min_chop),
+                                 C.byref(n_), C.byref(m_), *([None] * 14))
+    assert rc == 0
+    n, m = n_.value, m_.value
+    f3 = lambda: np.empty((n, 3), np.float32)
+    f1 = lambda: np.empty(n, np.float32)
+    i1 = lambda: np.empty(n, np.int32)
+    out = dict(origin=f3(), normal=f3(), plane_dist=f1(), area=f1(), mins=f3(), maxs=f3(), chop=f1(), parent=i1(), child1=i1(),
+               child2=i1(), face=i1(), wind_first=i1(), wind_count=i1(), wind_points=np.empty((m, 3), np.float32))
+    keys = ("origin", "normal", "plane_dist", "area", "mins", "maxs", "chop", "parent", "child1", "child2", "face",
+            "wind_first", "wind_count", "wind_points")
+    rc = L.orc_patches_subdivide(C.c_int(len(faces)), *[_p(a) for a in args_in], _p(points), C.c_float(min_chop),
+                                 C.byref(n_), C.byref(m_), *[_p(out[k]) for k in keys])
+    assert rc == 0
+    return out
+
+
 def decompress_vis(data: bytes, n_clusters: int):
     buf = np.frombuffer(bytes(data), np.uint8)
     out = np.zeros((n_clusters + 7) // 8, np.uint8)

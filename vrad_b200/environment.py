@@ -352,6 +352,32 @@ def test_line_does_hit_sky(env: Environment, start_xyz4, stop_xyz4, can_recurse=
     return env.test_lines_sky(s, e, flags, static_prop_to_skip)
 
 
+PATCH_TREE_FIELDS = ("origin", "normal", "plane_dist", "area", "mins", "maxs", "chop", "parent", "child1", "child2", "face",
+                     "wind_first", "wind_count", "wind_points")
+
+
+def subdivide_patches(faces, points, min_chop=4.0):
+    """patches.MakePatchForFace + SubdividePatches (rad/patches/face.go:29-197, subdivide.go:25-437) on the host.
+    faces: lib.FACE_PATCH_DTYPE records; points: [P, 3] winding points.  Returns a dict of arrays (PATCH_TREE_FIELDS)."""
+    L = _lib.load()
+    faces = np.ascontiguousarray(faces, _lib.FACE_PATCH_DTYPE)
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    np_, npt = C.c_int(), C.c_int()
+    rc = L.vrad_patches_subdivide(C.c_int(faces.shape[0]), ptr(faces), ptr(points), C.c_float(min_chop), C.c_int(0), C.c_int(0),
+                                  C.byref(np_), C.byref(npt), *([None] * 14))
+    if rc not in (0, -3):
+        check(rc)
+    n, m = np_.value, npt.value
+    f3 = lambda: np.empty((n, 3), np.float32)
+    f1 = lambda: np.empty(n, np.float32)
+    i1 = lambda: np.empty(n, np.int32)
+    out = dict(origin=f3(), normal=f3(), plane_dist=f1(), area=f1(), mins=f3(), maxs=f3(), chop=f1(), parent=i1(), child1=i1(),
+               child2=i1(), face=i1(), wind_first=i1(), wind_count=i1(), wind_points=np.empty((m, 3), np.float32))
+    check(L.vrad_patches_subdivide(C.c_int(faces.shape[0]), ptr(faces), ptr(points), C.c_float(min_chop), C.c_int(n), C.c_int(m),
+                                   C.byref(np_), C.byref(npt), *[ptr(out[k]) for k in PATCH_TREE_FIELDS]))
+    return out
+
+
 def decompress_vis(data: bytes, n_clusters: int):
     """lightmap.DecompressVis (rad/lightmap/vis.go:54-94): one PVS row -> ((n_clusters+7)//8 bytes, input bytes used)."""
     buf = np.frombuffer(bytes(data), np.uint8)

@@ -26,8 +26,14 @@ SYMBOLS = [
     "vrad_comm_init", "vrad_version",
     "vrad_env_set_triangle_colors", "vrad_bsp_upload", "vrad_point_leafnum", "vrad_cluster_from_point",
     "vrad_sky_cameras_set", "vrad_sky_cameras_get", "vrad_test_lines_sky", "vrad_leafs_trace_to_sky",
-    "vrad_decompress_vis", "vrad_pvs_from_vis_lump",
+    "vrad_decompress_vis", "vrad_pvs_from_vis_lump", "vrad_patches_subdivide",
 ]
+
+# == vrad_face_patch in include/vrad_cuda.h
+FACE_PATCH_DTYPE = np.dtype([("first_point", "<i4"), ("n_points", "<i4"), ("normal", "<f4", 3), ("plane_dist", "<f4"),
+                             ("lux_scale", "<f4"), ("chop", "<f4"), ("sky", "u1"), ("no_subdivide", "u1"),
+                             ("has_base_light", "u1"), ("pad", "u1")])
+assert FACE_PATCH_DTYPE.itemsize == 36
 
 
 class VradConfig(C.Structure):

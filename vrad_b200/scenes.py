@@ -617,3 +617,75 @@ MINI_SKY_CASES = [
     ((170, 0, 450), (170, 0, 100), 2, -1, 0.0),     # downwards through all three, then the floor is beyond the end
     ((50, 50, 50), (50, 50, 50), 3, -1, 1.0),       # zero-length segment: visible
 ]
+
+
+# ---- hierarchical patches (rad/patches/face.go + subdivide.go) ------------------------------------
+
+FACE_PATCH_DTYPE = np.dtype([("first_point", "<i4"), ("n_points", "<i4"), ("normal", "<f4", 3), ("plane_dist", "<f4"),
+                             ("lux_scale", "<f4"), ("chop", "<f4"), ("sky", "u1"), ("no_subdivide", "u1"),
+                             ("has_base_light", "u1"), ("pad", "u1")])     # == vrad_face_patch (include/vrad_cuda.h)
+
+
+class _FaceList:
+    """Face windings the way the BSP hands them to MakePatchForFace (rad/patches/face.go:29): planar convex polygons."""
+
+    def __init__(self, lux_scale=1.0 / 16.0, chop=4.0):
+        self.points, self.faces, self.lux, self.chop = [], [], lux_scale, chop
+
+    def quad(self, o, u, v, normal, sky=0, no_subdivide=0):
+        o = np.asarray(o, np.float64); u = np.asarray(u, np.float64); v = np.asarray(v, np.float64)
+        first = len(self.points)
+        for p in (o, o + u, o + u + v, o + v):
+            self.points.append(tuple(np.float32(c) for c in p))
+        n = np.asarray(normal, np.float64)
+        self.faces.append((first, 4, tuple(np.float32(c) for c in n), np.float32(float(np.dot(n, o))), np.float32(self.lux),
+                           np.float32(self.chop), sky, no_subdivide, 0, 0))
+
+    def arrays(self):
+        return np.asarray(self.faces, dtype=FACE_PATCH_DTYPE), np.asarray(self.points, np.float32).reshape(-1, 3)
+
+
+def room_faces(nx=3, ny=2, room=512.0, door_w=128.0, door_h=256.0):
+    """The faces of the multi_room geometry (same rooms, shared walls with door openings), one winding each;
+    returns (faces, points, face_room) -- face_room = the room (cluster) the face belongs to."""
+    R = room
+    fl = _FaceList()
+    face_room = []
+    a, b = (R - door_w) / 2, (R + door_w) / 2
+    for i in range(nx):
+        for j in range(ny):
+            x0, y0, k = i * R, j * R, i * ny + j
+            fl.quad((x0, y0, 0), (R, 0, 0), (0, R, 0), (0, 0, 1)); face_room.append(k)            # floor
+            fl.quad((x0, y0, R), (R, 0, 0), (0, R, 0), (0, 0, -1)); face_room.append(k)           # ceiling
+            walls = [((x0, y0, 0), (0, 1, 0), (1, 0, 0), i > 0), ((x0 + R, y0, 0), (0, 1, 0), (-1, 0, 0), i < nx - 1),
+                     ((x0, y0, 0), (1, 0, 0), (0, 1, 0), j > 0), ((x0, y0 + R, 0), (1, 0, 0), (0, -1, 0), j < ny - 1)]
+            for (o, u, nrm, door) in walls:
+                o = np.asarray(o, np.float64); u = np.asarray(u, np.float64)
+                if not door:
+                    fl.quad(o, u * R, (0, 0, R), nrm); face_room.append(k)
+                else:                                                                              # left, right, above the door
+                    fl.quad(o, u * a, (0, 0, R), nrm); face_room.append(k)
+                    fl.quad(o + u * b, u * (R - b), (0, 0, R), nrm); face_room.append(k)
+                    fl.quad(o + u * a + np.array([0, 0, door_h]), u * (b - a), (0, 0, R - door_h), nrm); face_room.append(k)
+    faces, points = fl.arrays()
+    return faces, points, np.asarray(face_room, np.int32)
+
+
+def multi_room_hier(seed: int = 0x5EED0002, nx: int = 3, ny: int = 2, boxes_per_room: int = 30, pvs_radius: int = 2) -> Scene:
+    """The multi_room map with its patches made the reference's way: one root patch per face, subdivided by
+    patches.SubdividePatches (product host code, vrad_patches_subdivide) into Parent/Child1/Child2 trees with
+    4-luxel (64-unit) chop.  Patch arrays hold ALL patches (roots, interior, leaves); meta["tree"] has the links."""
+    from .environment import subdivide_patches
+    base = multi_room(seed, nx, ny, boxes_per_room=boxes_per_room, pvs_radius=pvs_radius)
+    faces, points, face_room = room_faces(nx, ny)
+    t = subdivide_patches(faces, points, min_chop=4.0)
+    N = t["origin"].shape[0]
+    rng = SplitMix64(seed ^ 0xABCDEF)
+    refl_face = np.minimum(rng.uniform(3 * len(faces), 0.2, 0.7).reshape(-1, 3), np.float32(0.99))
+    sc = Scene(base.name + "_hier", base.tri_ids, base.tri_verts, base.tri_flags, t["origin"], t["normal"], t["plane_dist"], t["area"],
+               refl_face[t["face"]].astype(np.float32), face_room[t["face"]].astype(np.int32), np.zeros(N, np.uint8),
+               base.n_clusters, base.pvs, None, None, base.lights, dict(base.meta))
+    sc.meta["tree"] = t
+    sc.meta["faces"] = faces
+    sc.meta["face_points"] = points
+    return sc
