@@ -210,6 +210,14 @@ int  vrad_patches_subdivide(int n_faces, const vrad_face_patch* faces, const flo
 /* fields of common/types/patch.go:9-64 the kernels read (leaf patches only) */
 int  vrad_patches_upload(vrad_env*, int n, const float* origin3, const float* normal3, const float* plane_dist,
                          const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags);
+/* Patch.Parent / Child1 / Child2 / FaceNumber (common/types/patch.go:33,49-51) of the patches uploaded before, as
+ * patches.SubdividePatches leaves them (vrad_patches_subdivide): children after their parent, in pairs, carrying the
+ * parent's reflectivity.  face may be NULL.  Switches the stages to the hierarchical form: vrad_build_transfers builds
+ * rows for leaf patches only and picks emitters by the top-down walk of upstream's TestPatchToPatch (descend while
+ * |origin_i - origin_j|^2 / 16 < area_j; faces other than the receiver's own), and vrad_bounce runs CollectLight for
+ * interior patches (area-weighted average of the two children).  Clusters given to vrad_patches_upload apply to every
+ * patch; the PVS test uses the cluster of an emitter's face root. */
+int  vrad_patches_set_hierarchy(vrad_env*, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face);
 /* patch-to-patch visibility + form factor -> transfer lists (common/types/transfer.go:3-6;
  * Patch.NumTransfers/Transfers patch.go:60-61).  pvs: n_clusters x n_clusters bytes (non-zero = visible)
  * or NULL (host memory).  Builds and keeps resident the CSR rows owned by this rank.  nnz_out = local nnz.

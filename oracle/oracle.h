@@ -109,6 +109,10 @@ int  orc_trace_counters(orc_env*, int64_t* nodes_visited, int64_t* tris_tested, 
 /* ---- radiosity stages ---- */
 int  orc_patches_set(orc_env*, int n, const float* origin3, const float* normal3, const float* plane_dist,
                      const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags);
+/* Patch.Parent / Child1 / Child2 / FaceNumber (common/types/patch.go:33,49-51) for the patches set before: switches
+ * K2 to the hierarchical candidate walk (vismat.cpp TestPatchToPatch) and K4's CollectLight to
+ * the parent/child form (App. B.4).  face may be NULL. */
+int  orc_patches_set_hierarchy(orc_env*, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face);
 /* K2: builds CSR transfers.  pvs: n_clusters x n_clusters bytes (nonzero = visible) or NULL. */
 int  orc_build_transfers(orc_env*, int n_clusters, const uint8_t* pvs, int64_t* nnz_out, int threads);
 int  orc_transfers_get(orc_env*, int64_t* rowptr, int32_t* col, float* w);

@@ -30,6 +30,9 @@ struct Patches {
     std::vector<float> origin, normal, plane_dist, area, refl;
     std::vector<int32_t> cluster;
     std::vector<uint8_t> flags;     // bit0 = sky
+    // Patch.Parent / Child1 / Child2 / FaceNumber (common/types/patch.go:33,49-51); empty = flat (leaf patches only)
+    std::vector<int32_t> parent, child1, child2, face;
+    bool hier() const { return !child1.empty(); }
 };
 
 struct Counters { int64_t nodes = 0, tris = 0, leaves = 0; };

@@ -197,6 +197,11 @@ class OracleEnv:
                                        _p(refl), _p(cluster), _p(flags)) == 0
         self.n_patches = n
 
+    def set_hierarchy(self, parent, child1, child2, face=None):
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, np.int32)
+        parent, child1, child2, face = i32(parent), i32(child1), i32(child2), i32(face)
+        assert self._l.orc_patches_set_hierarchy(self._h, C.c_int(parent.shape[0]), _p(parent), _p(child1), _p(child2), _p(face)) == 0
+
     def build_transfers(self, pvs=None, threads=1):
         nnz = C.c_int64()
         nc = 0

@@ -8,6 +8,7 @@
 // SURVEY.md App. B.2-B.4 (uncited) -- PARITY UNPINNED; analytic known-answer tests are the arbiter.
 #include "oracle_impl.hpp"
 #include <omp.h>
+#include <algorithm>
 
 namespace orc {
 
@@ -53,10 +54,77 @@ static inline int patches_see(const orc_env* e, int i, int j) {
     return test_line1(e, a, b, 0, 0);
 }
 
+// vismat.cpp TestPatchToPatch: descend into the children of an emitter that is large for its
+// distance (|origin_i - origin_j|^2 / 16 < area_j), otherwise the emitter itself is the candidate.
+static void test_patch_to_patch(const Patches& P, int i, int j, std::vector<int32_t>& cand) {
+    if (P.child1[j] != -1) {
+        const float* oi = &P.origin[3 * i]; const float* oj = &P.origin[3 * j];
+        float tmp[3] = {oi[0] - oj[0], oi[1] - oj[1], oi[2] - oj[2]};
+        if (dot3(tmp, tmp) * 0.0625f < P.area[j]) {
+            test_patch_to_patch(P, i, P.child1[j], cand);
+            test_patch_to_patch(P, i, P.child2[j], cand);
+            return;
+        }
+    }
+    cand.push_back(j);
+}
+
+// candidates of receiver i in ascending patch order (MakeScales walks the vis row in patch order)
+static void row_candidates(const Patches& P, int i, int n_clusters, const uint8_t* pvs, std::vector<int32_t>& cand) {
+    cand.clear();
+    if (!P.hier()) {
+        for (int j = 0; j < P.n; j++) {
+            if (j == i) continue;
+            if (pvs && !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[j]]) continue;
+            cand.push_back(j);
+        }
+        return;
+    }
+    if (P.child1[i] != -1) return;                       // only leaf patches gather (BuildVisLeafs walks clusterChildren)
+    for (int r = 0; r < P.n; r++) {
+        if (P.parent[r] != -1) continue;                 // face root patches (faceParents)
+        if (pvs && !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[r]]) continue;
+        if (P.face[i] >= 0 && P.face[r] == P.face[i]) continue;     // "don't check patches on the same face"
+        test_patch_to_patch(P, i, r, cand);
+    }
+    std::sort(cand.begin(), cand.end());
+    cand.erase(std::remove(cand.begin(), cand.end(), i), cand.end());
+}
+
+static void build_row(const orc_env* e, int i, int n_clusters, const uint8_t* pvs, std::vector<int32_t>& cols, std::vector<float>& ws) {
+    const Patches& P = e->patches;
+    cols.clear(); ws.clear();
+    if (P.flags[i] & 1) return;                          // sky patches receive nothing
+    std::vector<int32_t> cand;
+    row_candidates(P, i, n_clusters, pvs, cand);
+    for (int32_t j : cand) {
+        float tr = transfer_weight(P, i, j);
+        if (tr == 0.0f) continue;
+        if (!patches_see(e, i, j)) continue;
+        cols.push_back(j); ws.push_back(tr);
+    }
+    // MakeScales (App. B.3): cap the row sum at 1
+    float total = 0.0f;
+    for (float v : ws) total = total + v;
+    if (total > 1.0f) {
+        float s = 1.0f / total;
+        for (float& v : ws) v = v * s;
+    }
+}
+
 } // namespace orc
 using namespace orc;
 
 extern "C" {
+
+int orc_patches_set_hierarchy(orc_env* e, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face) {
+    if (!e || n != e->patches.n) return -1;
+    Patches& P = e->patches;
+    P.parent.assign(parent, parent + n); P.child1.assign(child1, child1 + n); P.child2.assign(child2, child2 + n);
+    if (face) P.face.assign(face, face + n); else P.face.assign(n, -1);
+    e->rowptr.clear(); e->col.clear(); e->w.clear();
+    return 0;
+}
 
 int orc_patches_set(orc_env* e, int n, const float* origin3, const float* normal3, const float* plane_dist,
                     const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags) {
@@ -70,6 +138,7 @@ int orc_patches_set(orc_env* e, int n, const float* origin3, const float* normal
     P.refl.assign(reflectivity3, reflectivity3 + 3 * (size_t)n);
     if (cluster) P.cluster.assign(cluster, cluster + n); else P.cluster.assign(n, 0);
     if (flags) P.flags.assign(flags, flags + n); else P.flags.assign(n, 0);
+    P.parent.clear(); P.child1.clear(); P.child2.clear(); P.face.clear();
     e->rowptr.clear(); e->col.clear(); e->w.clear();
     return 0;
 }
@@ -81,24 +150,7 @@ int orc_build_transfers(orc_env* e, int n_clusters, const uint8_t* pvs, int64_t*
     std::vector<std::vector<int32_t>> cols(N);
     std::vector<std::vector<float>> ws(N);
 #pragma omp parallel for schedule(dynamic, 8) num_threads(threads > 0 ? threads : 1)
-    for (int i = 0; i < N; i++) {
-        if (P.flags[i] & 1) continue;                    // sky patches receive nothing
-        for (int j = 0; j < N; j++) {
-            if (j == i) continue;
-            if (pvs && !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[j]]) continue;
-            float tr = transfer_weight(P, i, j);
-            if (tr == 0.0f) continue;
-            if (!patches_see(e, i, j)) continue;
-            cols[i].push_back(j); ws[i].push_back(tr);
-        }
-        // MakeScales (App. B.3): cap the row sum at 1
-        float total = 0.0f;
-        for (float v : ws[i]) total = total + v;
-        if (total > 1.0f) {
-            float s = 1.0f / total;
-            for (float& v : ws[i]) v = v * s;
-        }
-    }
+    for (int i = 0; i < N; i++) build_row(e, i, n_clusters, pvs, cols[i], ws[i]);
     e->rowptr.assign(N + 1, 0);
     for (int i = 0; i < N; i++) e->rowptr[i + 1] = e->rowptr[i] + (int64_t)cols[i].size();
     e->col.resize(e->rowptr[N]); e->w.resize(e->rowptr[N]);
@@ -117,19 +169,7 @@ int64_t orc_transfer_row(orc_env* e, int i, int n_clusters, const uint8_t* pvs, 
     const Patches& P = e->patches;
     if (i < 0 || i >= P.n) return -1;
     std::vector<int32_t> cols; std::vector<float> ws;
-    if (!(P.flags[i] & 1)) {
-        for (int j = 0; j < P.n; j++) {
-            if (j == i) continue;
-            if (pvs && !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[j]]) continue;
-            float tr = transfer_weight(P, i, j);
-            if (tr == 0.0f) continue;
-            if (!patches_see(e, i, j)) continue;
-            cols.push_back(j); ws.push_back(tr);
-        }
-        float total = 0.0f;
-        for (float v : ws) total = total + v;
-        if (total > 1.0f) { float s = 1.0f / total; for (float& v : ws) v = v * s; }
-    }
+    build_row(e, i, n_clusters, pvs, cols, ws);
     if ((int64_t)cols.size() > cap) return -1;
     std::copy(cols.begin(), cols.end(), col_out); std::copy(ws.begin(), ws.end(), w_out);
     return (int64_t)cols.size();
@@ -255,14 +295,28 @@ int orc_bounce(orc_env* e, const float* emit0_rgb, int n_bounces, int early_out,
     int done = 0;
     for (int b = 0; b < n_bounces; b++) {
         orc_gather_rows(0, N, e->rowptr.data(), e->col.data(), e->w.data(), emit.data(), P.refl.data(), add.data(), threads);
-        // CollectLight (leaf patches only)
+        // CollectLight (vrad.cpp, App. B.4).  Flat patch sets: forward order (every patch is a leaf).  With a hierarchy:
+        // reverse index order so that children come before their parents; an interior patch takes the
+        // area-weighted average of its two children for both totallight and emitlight.
         added[0] = added[1] = added[2] = 0.0f;
-        for (int i = 0; i < N; i++) {
-            for (int c = 0; c < 3; c++) {
-                if (P.flags[i] & 1) { emit[3 * i + c] = 0.0f; continue; }
-                total[3 * i + c] = total[3 * i + c] + add[3 * i + c];
-                emit[3 * i + c] = add[3 * i + c];
-                added[c] = added[c] + emit[3 * i + c];
+        const bool hier = P.hier();
+        for (int n = 0; n < N; n++) {
+            const int i = hier ? N - 1 - n : n;
+            if (P.flags[i] & 1) { emit[3 * i] = emit[3 * i + 1] = emit[3 * i + 2] = 0.0f; continue; }
+            if (!hier || P.child1[i] == -1) {
+                for (int c = 0; c < 3; c++) {
+                    total[3 * i + c] = total[3 * i + c] + add[3 * i + c];
+                    emit[3 * i + c] = add[3 * i + c];
+                    added[c] = added[c] + emit[3 * i + c];
+                }
+            } else {
+                const int c1 = P.child1[i], c2 = P.child2[i];
+                const float s1 = P.area[c1] / (P.area[c1] + P.area[c2]);
+                const float s2 = P.area[c2] / (P.area[c1] + P.area[c2]);
+                for (int c = 0; c < 3; c++) {
+                    total[3 * i + c] = (total[3 * c1 + c] * s1) + (s2 * total[3 * c2 + c]);      // VectorScale, VectorMA
+                    emit[3 * i + c] = (emit[3 * c1 + c] * s1) + (s2 * emit[3 * c2 + c]);
+                }
             }
         }
         done++;

@@ -47,6 +47,17 @@ struct PatchesDev {
     DevBuf<int32_t> cluster;
     std::vector<int32_t> h_cluster;
     std::vector<uint8_t> h_flags;
+    std::vector<float> h_area, h_refl;          // host copies for the hierarchy checks / collect weights
+    // patch hierarchy (Patch.Parent / Child1 / FaceNumber, common/types/patch.go:33,49-51); empty = flat
+    bool hier = false;
+    DevBuf<int4> tree;                          // {parent, child1, face, cluster of the face root} per patch
+    std::vector<int32_t> h_root_cluster;
+    // CollectLight for interior patches, flattened: interior patch p = sum over the leaves of its subtree of
+    // w(p, leaf) * value(leaf), w = product of the area fractions along the path (vrad.cpp CollectLight, App. B.4)
+    int n_interior = 0;
+    DevBuf<int32_t> collect_ids;                // interior patch numbers
+    DevBuf<int64_t> collect_ptr;                // n_interior + 1 offsets into collect_ent
+    DevBuf<int2>    collect_ent;                // {leaf patch, weight bits}
 };
 
 struct TransfersDev {

@@ -9,6 +9,15 @@
 //   origin+normal of the two patches (always traced from the lower to the higher index) is clear.
 // MakeScales: rows whose weights sum above 1 are rescaled to sum 1.
 //
+// With a patch hierarchy (vrad_patches_set_hierarchy; Patch.Parent/Child1/Child2, common/types/patch.go:33,49-51)
+// only leaf patches gather, and the emitters of receiver i are those the top-down walk of vismat.cpp
+// TestPatchToPatch stops at: from every face root visible from cluster(i) (faces other than i's own), descend
+// into the children while |origin_i - origin_j|^2 / 16 < area_j.  The walk is evaluated per candidate instead:
+// j is an emitter for i iff every ancestor of j descends and j itself does not (or is a leaf) -- the same set,
+// but each (row, candidate) thread decides alone by walking j's parent chain (<= tree depth steps, early out at
+// the first ancestor that is small for its distance), so the candidate list stays a flat sorted array, the
+// bit matrix / count / fill passes are unchanged and the rows come out in ascending patch order.
+//
 // Rows are independent -> sharded by rank with no collective.  Three device passes:
 //   A  thread per (row, candidate): cheap tests, then the shadow ray -- one ray per unordered pair where both
 //      rows are local -- into a bit matrix (rays are generated on the device: no per-pair HBM input at all);
@@ -54,6 +63,22 @@ __device__ __forceinline__ float transfer_weight(const float4 oi, const float4 n
     return trans;
 }
 
+// TestPatchToPatch seen from the emitter (see the header): does the top-down walk for a receiver at `o_recv`
+// stop exactly at patch j?  tree[] = {parent, child1, face, root cluster}.
+__device__ __forceinline__ bool emitter_accepted(const PatchView& P, const int4* __restrict__ tree, const float4 o_recv,
+                                                 const float4 oj, const int4 tj) {
+    float dx = o_recv.x - oj.x, dy = o_recv.y - oj.y, dz = o_recv.z - oj.z;
+    if (tj.y != -1 && (((dx * dx) + (dy * dy)) + (dz * dz)) * 0.0625f < oj.w) return false;     // the walk goes on into j's children
+    int a = tj.x;
+    while (a != -1) {
+        const float4 oa = __ldg(&P.origin_area[a]);
+        dx = o_recv.x - oa.x; dy = o_recv.y - oa.y; dz = o_recv.z - oa.z;
+        if (!((((dx * dx) + (dy * dy)) + (dz * dz)) * 0.0625f < oa.w)) return false;             // the walk stopped above j
+        a = __ldg(&tree[a]).x;
+    }
+    return true;
+}
+
 // Pass A.  One block per local row; threads sweep that row's candidate list.
 //
 // The shadow segment of a pair always runs from the lower to the higher patch index, so visibility is
@@ -63,16 +88,19 @@ __device__ __forceinline__ float transfer_weight(const float4 oi, const float4 n
 // j is built by this rank and lists i (PVS entry [cluster j][cluster i]); otherwise each side traces
 // for itself.  All bit writes are atomicOr (the own-row word is warp-aggregated), so the bit matrix does
 // not depend on scheduling.
+template <bool HIER>
 __global__ void __launch_bounds__(256)
 k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __restrict__ cluster,
               const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx,
               const int64_t* __restrict__ bit_ptr, uint32_t* __restrict__ bits,
-              const uint8_t* __restrict__ pvs, int n_clusters) {
+              const uint8_t* __restrict__ pvs, int n_clusters, const int4* __restrict__ tree) {
     for (int row = blockIdx.x; row < nloc; row += gridDim.x) {
         const int i = (int)(row0 + row);
         const float4 oi = __ldg(&P.origin_area[i]), ni = __ldg(&P.normal_dist[i]);
         const float sky_i = __ldg(&P.refl[i]).w;
         const int ci = __ldg(&cluster[i]);
+        int4 ti = make_int4(-1, -1, -1, ci);
+        if (HIER) ti = __ldg(&tree[i]);
         const int64_t c0 = __ldg(&cand_ptr[ci]);
         const int K = (int)(__ldg(&cand_ptr[ci + 1]) - c0);
         const int Kpad = (K + 31) & ~31;
@@ -85,12 +113,20 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
                 j = __ldg(&cand_idx[c0 + p]);
                 if (j != i) {
                     cj = __ldg(&cluster[j]);
-                    const bool mirror = j >= row0 && j < row0 + nloc && (pvs == nullptr || __ldg(&pvs[(size_t)cj * n_clusters + ci]) != 0);
+                    // row j lists i when the cluster of i's face root is visible from j's cluster (ti.w == ci when flat)
+                    const bool mirror = j >= row0 && j < row0 + nloc && (pvs == nullptr || __ldg(&pvs[(size_t)cj * n_clusters + ti.w]) != 0);
                     if (!(mirror && j < i)) {                       // otherwise thread (j, i) covers this pair
                         const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
                         const float sky_j = __ldg(&P.refl[j]).w;
-                        pass_ij = sky_i == 0.0f && transfer_weight(oi, ni, oj, nj, sky_j) != 0.0f;
-                        pass_ji = mirror && sky_j == 0.0f && transfer_weight(oj, nj, oi, ni, sky_i) != 0.0f;
+                        bool acc_ij = true, acc_ji = true;
+                        if (HIER) {
+                            const int4 tj = __ldg(&tree[j]);
+                            const bool other_face = !(ti.z >= 0 && ti.z == tj.z);       // "don't check patches on the same face"
+                            acc_ij = ti.y == -1 && other_face && emitter_accepted(P, tree, oi, oj, tj);
+                            acc_ji = mirror && tj.y == -1 && other_face && emitter_accepted(P, tree, oj, oi, ti);
+                        }
+                        pass_ij = acc_ij && sky_i == 0.0f && transfer_weight(oi, ni, oj, nj, sky_j) != 0.0f;
+                        pass_ji = acc_ji && mirror && sky_j == 0.0f && transfer_weight(oj, nj, oi, ni, sky_i) != 0.0f;
                         need_ray = pass_ij || pass_ji;
                         if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
                     }
@@ -118,16 +154,20 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
 // which waits for the fullest rank -- even; costs ~1/16 of pass A.
 constexpr int kEstimateStride = 16;
 
+template <bool HIER>
 __global__ void __launch_bounds__(256)
 k2_estimate(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __restrict__ cluster,
-            const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx, int32_t* __restrict__ counts) {
+            const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx, int32_t* __restrict__ counts,
+            const int4* __restrict__ tree) {
     __shared__ int total;
     for (int row = blockIdx.x; row < nloc; row += gridDim.x) {
         const int i = (int)(row0 + row);
         if (threadIdx.x == 0) total = 0;
         __syncthreads();
         const float4 oi = __ldg(&P.origin_area[i]), ni = __ldg(&P.normal_dist[i]);
-        const bool sky_i = __ldg(&P.refl[i]).w != 0.0f;
+        int4 ti = make_int4(-1, -1, -1, 0);
+        if (HIER) ti = __ldg(&tree[i]);
+        const bool sky_i = __ldg(&P.refl[i]).w != 0.0f || ti.y != -1;      // interior patches gather nothing
         const int64_t c0 = __ldg(&cand_ptr[__ldg(&cluster[i])]);
         const int K = (int)(__ldg(&cand_ptr[__ldg(&cluster[i]) + 1]) - c0);
         const int n_samples = (K + kEstimateStride - 1) / kEstimateStride;
@@ -140,7 +180,12 @@ k2_estimate(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __re
                 const int j = __ldg(&cand_idx[c0 + p]);
                 if (j != i) {
                     const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
-                    if (transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w) != 0.0f) {
+                    bool acc = true;
+                    if (HIER) {
+                        const int4 tj = __ldg(&tree[j]);
+                        acc = !(ti.z >= 0 && ti.z == tj.z) && emitter_accepted(P, tree, oi, oj, tj);
+                    }
+                    if (acc && transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w) != 0.0f) {
                         need = true;
                         if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
                     }
@@ -232,8 +277,19 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
             clus[i] = c;
         }
     }
+    // candidates of a cluster = every patch (with a hierarchy: of any tree level) whose face root lies in a visible cluster
+    const bool hier = P.hier;
+    const int4* d_tree = hier ? P.tree.p : nullptr;
+    std::vector<int32_t> rclus(clus);
+    if (hier && pvs) {
+        for (int i = 0; i < N; i++) {
+            int c = P.h_root_cluster[i];
+            if (c < 0 || c >= C) { set_error("vrad_build_transfers: the face root of patch %d has cluster %d outside [0,%d)", i, c, C); return VRAD_E_INVALID; }
+            rclus[i] = c;
+        }
+    }
     std::vector<std::vector<int32_t>> members(C);
-    for (int i = 0; i < N; i++) members[clus[i]].push_back(i);
+    for (int i = 0; i < N; i++) members[rclus[i]].push_back(i);
     std::vector<int64_t> cand_ptr(C + 1, 0);
     std::vector<int32_t> cand_idx;
     for (int c = 0; c < C; c++) {
@@ -262,7 +318,10 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
         if (ce == cudaSuccess) ce = cudaMemsetAsync(d_counts.p, 0, (size_t)N * 4, e->stream);
         if (ce != cudaSuccess) { drop(); set_error("row balance staging failed: %s", cudaGetErrorString(ce)); return VRAD_E_CUDA; }
         const int nl0 = (int)(row1 - row0);
-        if (nl0 > 0) k2_estimate<<<std::min(nl0, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nl0, row0, d_cl.p, d_cp.p, d_ci.p, d_counts.p);
+        if (nl0 > 0) {
+            if (hier) k2_estimate<true><<<std::min(nl0, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nl0, row0, d_cl.p, d_cp.p, d_ci.p, d_counts.p, d_tree);
+            else k2_estimate<false><<<std::min(nl0, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nl0, row0, d_cl.p, d_cp.p, d_ci.p, d_counts.p, nullptr);
+        }
         int rcb = comm_allreduce_i32(e, d_counts.p, (size_t)N);
         if (rcb) { drop(); return rcb; }
         ce = cudaMemcpyAsync(counts.data(), d_counts.p, (size_t)N * 4, cudaMemcpyDeviceToHost, e->stream);
@@ -319,8 +378,10 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     int launches = 0;
     if (nloc > 0) {
         if (verbose) cudaEventRecord(tv0, e->stream);
-        k2_visibility<<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
-                                                                               pvs ? d_pvs.p : nullptr, C);
+        if (hier) k2_visibility<true><<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
+                                                                                             pvs ? d_pvs.p : nullptr, C, d_tree);
+        else k2_visibility<false><<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
+                                                                                           pvs ? d_pvs.p : nullptr, C, nullptr);
         if (verbose) cudaEventRecord(tv1, e->stream);
         launches++;
         const int wblocks = (nloc * 32 + 255) / 256;

@@ -255,6 +255,30 @@ __global__ void k4_unpack_total(int64_t n, const float4* __restrict__ total, flo
 
 static inline int64_t rows_per_rank(const vrad_env* e, int64_t n) { return (n + e->cfg.world - 1) / e->cfg.world; }
 
+// CollectLight for interior patches (vrad.cpp CollectLight): an interior patch holds the
+// area-weighted average of its two children.  Flattened over the subtree: one warp per interior patch sums
+// w(p, leaf) * buf[leaf] over its leaves (children inherit the face's reflectivity -- CreateChildPatch copies the
+// parent, rad/patches/subdivide.go:360 -- so averaging emit*refl equals averaging emit and then reflecting).
+__global__ void __launch_bounds__(256)
+k4_collect_parents(int n_interior, const int32_t* __restrict__ ids, const int64_t* __restrict__ cptr,
+                   const int2* __restrict__ ent, float4* __restrict__ buf) {
+    const int lane = threadIdx.x & 31;
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (w >= n_interior) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int64_t k = cptr[w] + lane; k < cptr[w + 1]; k += 32) {
+        const int2 en = __ldg(&ent[k]);
+        const float4 v = buf[en.x];
+        const float wt = __int_as_float(en.y);
+        s0 += wt * v.x; s1 += wt * v.y; s2 += wt * v.z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) buf[ids[w]] = make_float4(s0, s1, s2, 0.f);
+}
+
 } // namespace vrad
 using namespace vrad;
 
@@ -268,6 +292,8 @@ int vrad_patches_upload(vrad_env* e, int n, const float* origin3, const float* n
     if (P.origin_area.alloc(n) || P.normal_dist.alloc(n) || P.refl.alloc(n) || P.cluster.alloc(n)) { set_error("out of device memory for patches"); return VRAD_E_NOMEM; }
     std::vector<float4> oa(n), nd(n), rf(n);
     P.h_cluster.assign(n, 0); P.h_flags.assign(n, 0);
+    P.h_area.assign(area, area + n); P.h_refl.assign(reflectivity3, reflectivity3 + 3 * (size_t)n);
+    P.hier = false; P.n_interior = 0; P.h_root_cluster.clear();
     for (int i = 0; i < n; i++) {
         oa[i] = make_float4(origin3[3 * i], origin3[3 * i + 1], origin3[3 * i + 2], area[i]);
         nd[i] = make_float4(normal3[3 * i], normal3[3 * i + 1], normal3[3 * i + 2], plane_dist[i]);
@@ -282,6 +308,63 @@ int vrad_patches_upload(vrad_env* e, int n, const float* origin3, const float* n
     VRAD_CUDA_CHECK(cudaMemcpyAsync(P.cluster.p, P.h_cluster.data(), (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     P.n = n;
+    e->transfers.ready = false;
+    return VRAD_OK;
+}
+
+int vrad_patches_set_hierarchy(vrad_env* e, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face) {
+    if (!e || !parent || !child1 || !child2) { set_error("vrad_patches_set_hierarchy: bad arguments"); return VRAD_E_INVALID; }
+    PatchesDev& P = e->patches;
+    if (P.n == 0 || n != P.n) { set_error("vrad_patches_set_hierarchy: %d links for %d uploaded patches", n, P.n); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    // the links of a SubdividePatches result: children are appended after their parent (subdivide.go:352-355), in pairs
+    for (int i = 0; i < n; i++) {
+        const int c1 = child1[i], c2 = child2[i];
+        if ((c1 == -1) != (c2 == -1)) { set_error("vrad_patches_set_hierarchy: patch %d has one child", i); return VRAD_E_INVALID; }
+        if (c1 != -1) {
+            if (c1 <= i || c2 <= i || c1 >= n || c2 >= n || c1 == c2 || parent[c1] != i || parent[c2] != i) { set_error("vrad_patches_set_hierarchy: bad children of patch %d", i); return VRAD_E_INVALID; }
+            for (int k = 0; k < 2; k++) {
+                const int c = k ? c2 : c1;
+                if (memcmp(&P.h_refl[3 * (size_t)c], &P.h_refl[3 * (size_t)i], 12) != 0 || (P.h_flags[c] & 1) != (P.h_flags[i] & 1)) {
+                    set_error("vrad_patches_set_hierarchy: child %d does not carry its parent's reflectivity / sky flag (CreateChildPatch copies the parent)", c);
+                    return VRAD_E_INVALID;
+                }
+            }
+        }
+        if (parent[i] != -1 && (parent[i] < 0 || parent[i] >= i || (child1[parent[i]] != i && child2[parent[i]] != i))) { set_error("vrad_patches_set_hierarchy: bad parent of patch %d", i); return VRAD_E_INVALID; }
+    }
+    std::vector<int4> tree(n);
+    P.h_root_cluster.assign(n, 0);
+    for (int i = 0; i < n; i++) {                            // parents precede children: one forward pass
+        P.h_root_cluster[i] = parent[i] == -1 ? P.h_cluster[i] : P.h_root_cluster[parent[i]];
+        tree[i] = make_int4(parent[i], child1[i], face ? face[i] : -1, P.h_root_cluster[i]);
+    }
+    // flattened CollectLight rows: weights top-down, s = area_child / (area_child1 + area_child2)
+    std::vector<int32_t> ids; std::vector<int64_t> cptr(1, 0); std::vector<int2> ent;
+    std::vector<std::pair<int, float>> work;
+    for (int p = 0; p < n; p++) {
+        if (child1[p] == -1) continue;
+        ids.push_back(p);
+        work.assign(1, std::make_pair(p, 1.0f));
+        while (!work.empty()) {
+            const auto [q, wq] = work.back(); work.pop_back();
+            if (child1[q] == -1) { int2 v; v.x = q; memcpy(&v.y, &wq, 4); ent.push_back(v); continue; }
+            const float a1 = P.h_area[child1[q]], a2 = P.h_area[child2[q]];
+            work.push_back(std::make_pair(child2[q], wq * (a2 / (a1 + a2))));
+            work.push_back(std::make_pair(child1[q], wq * (a1 / (a1 + a2))));
+        }
+        cptr.push_back((int64_t)ent.size());
+    }
+    if (P.tree.alloc(n) || P.collect_ids.alloc(ids.size() + 1) || P.collect_ptr.alloc(cptr.size()) || P.collect_ent.alloc(ent.size() + 1)) {
+        set_error("out of device memory for the patch hierarchy"); return VRAD_E_NOMEM;
+    }
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(P.tree.p, tree.data(), (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
+    if (!ids.empty()) VRAD_CUDA_CHECK(cudaMemcpyAsync(P.collect_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(P.collect_ptr.p, cptr.data(), cptr.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    if (!ent.empty()) VRAD_CUDA_CHECK(cudaMemcpyAsync(P.collect_ent.p, ent.data(), ent.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    P.n_interior = (int)ids.size();
+    P.hier = true;
     e->transfers.ready = false;
     return VRAD_OK;
 }
@@ -419,8 +502,13 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     void* d_out3;
     if ((rc = stage_out(e, 1, total_rgb_out, (size_t)N * 12, &d_out3, &h_out))) return rc;
     float* d_added = e->d_partials.p + 3 * (size_t)nblocks;       // 3 floats after the partials
-    if (world > 1 && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
-    const bool p2p = world > 1 && e->peers.ready;
+    // with a patch hierarchy the interior patches are recomputed from the exchanged leaf rows on every rank, which
+    // needs the complete buffer before the next gather starts: the fused peer-store exchange is not used then
+    const PatchesDev& PD = e->patches;
+    const bool hier = PD.hier && PD.n_interior > 0;
+    const int collect_blocks = (PD.n_interior * 32 + 255) / 256;
+    if (world > 1 && !hier && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
+    const bool p2p = world > 1 && !hier && e->peers.ready;
     const PeerTable* d_peers = p2p ? e->peers.d_table.p : nullptr;
 
     timing_begin(e);
@@ -452,6 +540,10 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         if (probe) cudaEventRecord(pe[n_probe][1], e->stream);
         if (p2p) { k4_peer_signal<<<1, 32, 0, e->stream>>>(d_peers); launches++; pending_wait = true; }
         else if (world > 1 && (rc = comm_allgather_rows(e, e->d_er[cur ^ 1].p, bounds))) return rc;
+        if (hier) {     // CollectLight, interior patches: emit of a parent = area-weighted average of its children
+            k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_er[cur ^ 1].p);
+            launches++;
+        }
         if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
         cur ^= 1; done++;
         const bool last = (b + 1 == n_bounces);
@@ -468,6 +560,10 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     }
     if (pending_wait) { k4_peer_wait<<<1, 32, 0, e->stream>>>(d_peers); launches++; }
     if (world > 1 && (rc = comm_allgather_rows(e, e->d_total.p, bounds))) return rc;
+    if (hier) {         // totallight of the interior patches, from the leaves' totals
+        k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_total.p);
+        launches++;
+    }
     if (d_out3) {
         k4_unpack_total<<<(int)((N + 255) / 256), 256, 0, e->stream>>>(N, e->d_total.p, (float*)d_out3);
         launches++;

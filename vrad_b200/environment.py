@@ -255,6 +255,12 @@ class Environment:
         check(self._l.vrad_patches_upload(self._h, C.c_int(n), ptr(origin), ptr(normal), ptr(plane_dist), ptr(area), ptr(refl), ptr(cluster), ptr(flags)))
         self.n_patches = n
 
+    def set_hierarchy(self, parent, child1, child2, face=None):
+        """Patch.Parent / Child1 / Child2 / FaceNumber for the uploaded patches (common/types/patch.go:33,49-51)."""
+        i32 = lambda a: None if a is None else np.ascontiguousarray(a, np.int32)
+        parent, child1, child2, face = i32(parent), i32(child1), i32(child2), i32(face)
+        check(self._l.vrad_patches_set_hierarchy(self._h, C.c_int(parent.shape[0]), ptr(parent), ptr(child1), ptr(child2), ptr(face)))
+
     def build_transfers(self, pvs=None):
         nnz = C.c_int64(); nc = 0
         if pvs is not None:
