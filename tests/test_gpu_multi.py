@@ -34,6 +34,23 @@ rp, col, w = env.transfers_download()
 np.savez(os.path.join(os.environ["VRAD_OUT"], f"rank{rank}.npz"), total=total, added=added, done=done, total_eo=total_eo,
          done_eo=done_eo, row0=row0, row1=row1, nnz=nnz, rp=rp, col=col, w=w)
 env.close()
+# the same map with its patch hierarchy (SubdividePatches trees): rows sharded, interior patches recomputed on every rank
+hs = scenes.multi_room_hier(nx=3, ny=2)
+t = hs.meta["tree"]
+henv = environment_from_scene(hs, device=lr, rank=rank, world=world)
+henv.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
+uid2 = [Environment.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid2, src=0)
+henv.comm_init(uid2[0])
+hnnz = henv.build_transfers(hs.pvs)
+hrow0, hrow1, _ = henv.transfers_info()
+hN = hs.n_patches
+hemit0 = scenes.SplitMix64(11).uniform(3 * hN, 0.0, 200.0).reshape(hN, 3)
+htotal, hadded, hdone = henv.bounce(hemit0, 6)
+hrp, hcol, hw = henv.transfers_download()
+np.savez(os.path.join(os.environ["VRAD_OUT"], f"hier{rank}.npz"), total=htotal, added=hadded, row0=hrow0, row1=hrow1, nnz=hnnz,
+         rp=hrp, col=hcol, w=hw)
+henv.close()
 dist.destroy_process_group()
 '''
 
@@ -74,3 +91,24 @@ def test_two_gpu_bounce_matches_single_and_oracle(tmp_path):
     te, ae, de = o.bounce(emit0, 100, early_out=True, threads=8)
     assert int(r0["done_eo"]) == int(r1["done_eo"]) == de
     assert np.abs(r0["total_eo"] - te).max() <= 1e-4 * np.abs(te).max()
+
+    # hierarchical run of the same processes: rows bit-exact per rank, bounced light incl. the interior patches
+    h0, h1 = np.load(tmp_path / "hier0.npz"), np.load(tmp_path / "hier1.npz")
+    hs = scenes.multi_room_hier(nx=3, ny=2)
+    t = hs.meta["tree"]
+    ho = pyoracle.env_from_scene(hs)
+    ho.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
+    hnnz = ho.build_transfers(hs.pvs, threads=8)
+    assert int(h0["nnz"]) + int(h1["nnz"]) == hnnz
+    hrp, hcol, hw = ho.transfers()
+    hparts = [(int(h0["row0"]), int(h0["row1"])), (int(h1["row0"]), int(h1["row1"]))]
+    assert hparts[0][0] == 0 and hparts[0][1] == hparts[1][0] and hparts[1][1] == hs.n_patches
+    for r, (a, b) in zip((h0, h1), hparts):
+        assert np.array_equal(r["rp"], hrp[a:b + 1] - hrp[a])
+        assert np.array_equal(r["col"], hcol[hrp[a]:hrp[b]]) and np.array_equal(r["w"], hw[hrp[a]:hrp[b]])
+    hemit0 = scenes.SplitMix64(11).uniform(3 * hs.n_patches, 0.0, 200.0).reshape(hs.n_patches, 3)
+    hto, hao, _ = ho.bounce(hemit0, 6, threads=8)
+    for r in (h0, h1):
+        assert np.abs(r["total"] - hto).max() <= 1e-4 * np.abs(hto).max()
+        assert np.allclose(r["added"], hao, rtol=1e-4)
+    assert np.array_equal(h0["total"], h1["total"])

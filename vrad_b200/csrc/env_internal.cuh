@@ -54,10 +54,14 @@ struct PatchesDev {
     std::vector<int32_t> h_root_cluster;
     // CollectLight for interior patches, flattened: interior patch p = sum over the leaves of its subtree of
     // w(p, leaf) * value(leaf), w = product of the area fractions along the path (vrad.cpp CollectLight, App. B.4)
-    int n_interior = 0;
+    int n_interior = 0, n_collect_long = 0;     // collect rows are ordered long (>= 128 leaves) first
     DevBuf<int32_t> collect_ids;                // interior patch numbers
     DevBuf<int64_t> collect_ptr;                // n_interior + 1 offsets into collect_ent
     DevBuf<int2>    collect_ent;                // {leaf patch, weight bits}
+    std::vector<int32_t> h_child1;
+    DevBuf<int32_t> leaf_rows;                  // local row numbers of the leaf patches in [leaf_rows_row0, leaf_rows_row1)
+    int n_leaf_rows = 0;
+    int64_t leaf_rows_row0 = -1, leaf_rows_row1 = -1;
 };
 
 struct TransfersDev {

@@ -118,15 +118,14 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
                     if (!(mirror && j < i)) {                       // otherwise thread (j, i) covers this pair
                         const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
                         const float sky_j = __ldg(&P.refl[j]).w;
-                        bool acc_ij = true, acc_ji = true;
-                        if (HIER) {
+                        pass_ij = sky_i == 0.0f && transfer_weight(oi, ni, oj, nj, sky_j) != 0.0f;
+                        pass_ji = mirror && sky_j == 0.0f && transfer_weight(oj, nj, oi, ni, sky_i) != 0.0f;
+                        if (HIER && (pass_ij || pass_ji)) {           // cheap tests first: the parent-chain walk runs only for pairs that could transfer
                             const int4 tj = __ldg(&tree[j]);
                             const bool other_face = !(ti.z >= 0 && ti.z == tj.z);       // "don't check patches on the same face"
-                            acc_ij = ti.y == -1 && other_face && emitter_accepted(P, tree, oi, oj, tj);
-                            acc_ji = mirror && tj.y == -1 && other_face && emitter_accepted(P, tree, oj, oi, ti);
+                            pass_ij = pass_ij && ti.y == -1 && other_face && emitter_accepted(P, tree, oi, oj, tj);
+                            pass_ji = pass_ji && tj.y == -1 && other_face && emitter_accepted(P, tree, oj, oi, ti);
                         }
-                        pass_ij = acc_ij && sky_i == 0.0f && transfer_weight(oi, ni, oj, nj, sky_j) != 0.0f;
-                        pass_ji = acc_ji && mirror && sky_j == 0.0f && transfer_weight(oj, nj, oi, ni, sky_i) != 0.0f;
                         need_ray = pass_ij || pass_ji;
                         if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
                     }
@@ -180,12 +179,12 @@ k2_estimate(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __re
                 const int j = __ldg(&cand_idx[c0 + p]);
                 if (j != i) {
                     const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
-                    bool acc = true;
-                    if (HIER) {
+                    bool ok = transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w) != 0.0f;
+                    if (HIER && ok) {
                         const int4 tj = __ldg(&tree[j]);
-                        acc = !(ti.z >= 0 && ti.z == tj.z) && emitter_accepted(P, tree, oi, oj, tj);
+                        ok = !(ti.z >= 0 && ti.z == tj.z) && emitter_accepted(P, tree, oi, oj, tj);
                     }
-                    if (acc && transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w) != 0.0f) {
+                    if (ok) {
                         need = true;
                         if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
                     }

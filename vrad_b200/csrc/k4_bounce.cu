@@ -112,6 +112,78 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
     }
 }
 
+// Short-row form (patch hierarchy: rows average ~150 transfers instead of ~1000+).  With one warp per row such a
+// row is a single partial step and the kernel is a chain of dependent latencies (rowptr -> {col,w} -> er[col] ->
+// epilogue) with only 40 rows in flight per SM: measured 1.3 TB/s on the hierarchical S2 matrix.  Here 8 lanes
+// own a row (4 rows per warp, lanes on consecutive entries so the gathers of a row still coalesce), 4 entries in
+// flight per lane with the next {col,w} loads issued ahead of the gathers, and the register budget is capped at 40
+// so that 48 warps = 192 rows stay resident per SM (at 32 registers the loop spills and is slower: 76 vs 64 us).  `rows` (optional) lists the local rows to process -- with a
+// hierarchy only the leaf patches gather, the interior rows are rewritten by k4_collect_parents.
+constexpr int kShortUnroll = 4;
+
+template <int kShortLanes, int kMinBlocks>
+__global__ void __launch_bounds__(kGatherBlock, kMinBlocks)
+k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const int64_t* __restrict__ rowptr,
+                const int2* __restrict__ tr, const float4* __restrict__ er, const float4* __restrict__ refl,
+                float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
+    constexpr int kShortRowsPerBlock = kGatherBlock / kShortLanes;
+    const int sub = threadIdx.x & (kShortLanes - 1), grp = threadIdx.x / kShortLanes;
+    const int r = blockIdx.x * kShortRowsPerBlock + grp;
+    const bool valid = r < nrows;
+    const int row = valid ? (rows ? __ldg(&rows[r]) : r) : 0;
+    const int64_t k0 = valid ? rowptr[row] : 0, k1 = valid ? rowptr[row + 1] : 0;
+    const int2 zero = make_int2(0, 0);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    int2 cur[kShortUnroll], nxt[kShortUnroll];
+    int64_t k = k0 + sub;
+#pragma unroll
+    for (int j = 0; j < kShortUnroll; j++) cur[j] = k + kShortLanes * j < k1 ? __ldcs(&tr[k + kShortLanes * j]) : zero;
+    for (; k < k1; k += kShortLanes * kShortUnroll) {
+#pragma unroll
+        for (int j = 0; j < kShortUnroll; j++)
+            nxt[j] = k + kShortLanes * (kShortUnroll + j) < k1 ? __ldcs(&tr[k + kShortLanes * (kShortUnroll + j)]) : zero;
+        float4 x[kShortUnroll];
+#pragma unroll
+        for (int j = 0; j < kShortUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
+#pragma unroll
+        for (int j = 0; j < kShortUnroll; j++) {
+            const float w = __int_as_float(cur[j].y);
+            s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
+        }
+#pragma unroll
+        for (int j = 0; j < kShortUnroll; j++) cur[j] = nxt[j];
+    }
+#pragma unroll
+    for (int o = kShortLanes / 2; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    if (valid && sub == 0) {
+        const float4 rf = refl[row0 + row];
+        if (rf.w == 0.0f) {                                              // CollectLight, leaf patch
+            float4 t = total[row];
+            t.x += s0; t.y += s1; t.z += s2;
+            total[row] = t;
+            er_next[row0 + row] = make_float4(s0 * rf.x, s1 * rf.y, s2 * rf.z, 0.f);
+            e0 = s0; e1 = s1; e2 = s2;
+        } else {
+            er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);      // sky: emit = 0
+        }
+    }
+    // deterministic per-block partial of `added`
+    __shared__ float sm[kShortRowsPerBlock][3];
+    if (sub == 0) { sm[grp][0] = e0; sm[grp][1] = e1; sm[grp][2] = e2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < kShortRowsPerBlock; q++) a += sm[q][threadIdx.x];
+        partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    }
+}
+
 // out of line on purpose: keeps the peer-table loads out of the gather loop's register allocation
 __device__ __noinline__ void store_row_to_peers(const PeerTable* __restrict__ peers, int next_buf, int64_t row, float x, float y, float z) {
     const int lane = threadIdx.x & 31;
@@ -259,24 +331,50 @@ static inline int64_t rows_per_rank(const vrad_env* e, int64_t n) { return (n + 
 // area-weighted average of its two children.  Flattened over the subtree: one warp per interior patch sums
 // w(p, leaf) * buf[leaf] over its leaves (children inherit the face's reflectivity -- CreateChildPatch copies the
 // parent, rad/patches/subdivide.go:360 -- so averaging emit*refl equals averaging emit and then reflecting).
-__global__ void __launch_bounds__(256)
-k4_collect_parents(int n_interior, const int32_t* __restrict__ ids, const int64_t* __restrict__ cptr,
-                   const int2* __restrict__ ent, float4* __restrict__ buf) {
-    const int lane = threadIdx.x & 31;
-    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (w >= n_interior) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int64_t k = cptr[w] + lane; k < cptr[w + 1]; k += 32) {
-        const int2 en = __ldg(&ent[k]);
-        const float4 v = buf[en.x];
-        const float wt = __int_as_float(en.y);
-        s0 += wt * v.x; s1 += wt * v.y; s2 += wt * v.z;
+// Rows are ordered long first (host side): blocks [0, long_blocks) give a whole warp to each of the n_long rows
+// with >= kCollectLong leaves (face roots and their first levels: up to 1000+ entries), the other blocks give 8
+// lanes to each remaining row (half of all interior patches have 2 leaves).  Loads are issued kCollectUnroll deep:
+// one warp walking a root row entry by entry was a 28 us tail per bounce.
+constexpr int kCollectLong = 128;
+constexpr int kCollectUnroll = 4;
+
+template <int LANES>
+__device__ __forceinline__ void collect_row(int64_t k0, int64_t k1, int sub, const int2* __restrict__ ent, const float4* buf,
+                                            float& s0, float& s1, float& s2) {
+    const int2 zero = make_int2(0, 0);
+    for (int64_t k = k0 + sub; k < k1; k += LANES * kCollectUnroll) {
+        int2 en[kCollectUnroll]; float4 v[kCollectUnroll];
+#pragma unroll
+        for (int j = 0; j < kCollectUnroll; j++) en[j] = k + LANES * j < k1 ? __ldg(&ent[k + LANES * j]) : zero;
+#pragma unroll
+        for (int j = 0; j < kCollectUnroll; j++) v[j] = buf[en[j].x];
+#pragma unroll
+        for (int j = 0; j < kCollectUnroll; j++) {
+            const float wt = __int_as_float(en[j].y);
+            s0 += wt * v[j].x; s1 += wt * v[j].y; s2 += wt * v[j].z;
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = LANES / 2; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0) buf[ids[w]] = make_float4(s0, s1, s2, 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+k4_collect_parents(int n_interior, int n_long, int long_blocks, const int32_t* __restrict__ ids, const int64_t* __restrict__ cptr,
+                   const int2* __restrict__ ent, float4* __restrict__ buf) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if ((int)blockIdx.x < long_blocks) {
+        const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+        const bool valid = w < n_long;
+        collect_row<32>(valid ? cptr[w] : 0, valid ? cptr[w + 1] : 0, lane, ent, buf, s0, s1, s2);
+        if (valid && lane == 0) buf[ids[w]] = make_float4(s0, s1, s2, 0.f);
+    } else {
+        const int w = n_long + ((int)blockIdx.x - long_blocks) * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+        const bool valid = w < n_interior;
+        collect_row<8>(valid ? cptr[w] : 0, valid ? cptr[w + 1] : 0, sub, ent, buf, s0, s1, s2);
+        if (valid && sub == 0) buf[ids[w]] = make_float4(s0, s1, s2, 0.f);
+    }
 }
 
 } // namespace vrad
@@ -340,10 +438,18 @@ int vrad_patches_set_hierarchy(vrad_env* e, int n, const int32_t* parent, const 
         tree[i] = make_int4(parent[i], child1[i], face ? face[i] : -1, P.h_root_cluster[i]);
     }
     // flattened CollectLight rows: weights top-down, s = area_child / (area_child1 + area_child2)
+    // subtree leaf counts (children follow their parents: one backward pass), then the interior patches long rows first
+    std::vector<int32_t> n_leaves(n, 1);
+    for (int i = n - 1; i >= 0; i--) if (child1[i] != -1) n_leaves[i] = n_leaves[child1[i]] + n_leaves[child2[i]];
+    std::vector<int32_t> order;
+    for (int pass = 0; pass < 2; pass++)
+        for (int p = 0; p < n; p++)
+            if (child1[p] != -1 && (n_leaves[p] >= kCollectLong) == (pass == 0)) order.push_back(p);
+    int n_long = 0;
+    for (int p : order) n_long += n_leaves[p] >= kCollectLong;
     std::vector<int32_t> ids; std::vector<int64_t> cptr(1, 0); std::vector<int2> ent;
     std::vector<std::pair<int, float>> work;
-    for (int p = 0; p < n; p++) {
-        if (child1[p] == -1) continue;
+    for (int p : order) {
         ids.push_back(p);
         work.assign(1, std::make_pair(p, 1.0f));
         while (!work.empty()) {
@@ -364,6 +470,9 @@ int vrad_patches_set_hierarchy(vrad_env* e, int n, const int32_t* parent, const 
     if (!ent.empty()) VRAD_CUDA_CHECK(cudaMemcpyAsync(P.collect_ent.p, ent.data(), ent.size() * 8, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     P.n_interior = (int)ids.size();
+    P.n_collect_long = n_long;
+    P.h_child1.assign(child1, child1 + n);
+    P.leaf_rows_row0 = P.leaf_rows_row1 = -1;
     P.hier = true;
     e->transfers.ready = false;
     return VRAD_OK;
@@ -506,9 +615,31 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     // needs the complete buffer before the next gather starts: the fused peer-store exchange is not used then
     const PatchesDev& PD = e->patches;
     const bool hier = PD.hier && PD.n_interior > 0;
-    const int collect_blocks = (PD.n_interior * 32 + 255) / 256;
+    const int collect_long_blocks = (PD.n_collect_long + 7) / 8;
+    const int collect_blocks = collect_long_blocks + (PD.n_interior - PD.n_collect_long + 31) / 32;
     if (world > 1 && !hier && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
     const bool p2p = world > 1 && !hier && e->peers.ready;
+    // short-row form: chosen by the average row length of the rows that gather (env VRAD_K4_SHORT=0/1 forces it)
+    int n_short = nloc;
+    const int32_t* d_rows = nullptr;
+    if (hier) {     // local leaf rows only; the list is rebuilt when the row block changed
+        if (PD.leaf_rows_row0 != T.row0 || PD.leaf_rows_row1 != T.row1) {
+            std::vector<int32_t> lr;
+            for (int64_t i = T.row0; i < T.row1; i++) if (PD.h_child1[i] == -1) lr.push_back((int32_t)(i - T.row0));
+            PatchesDev& PM = e->patches;
+            if (PM.leaf_rows.alloc(lr.size() + 1)) { set_error("out of device memory (leaf row list)"); return VRAD_E_NOMEM; }
+            if (!lr.empty()) VRAD_CUDA_CHECK(cudaMemcpyAsync(PM.leaf_rows.p, lr.data(), lr.size() * 4, cudaMemcpyHostToDevice, e->stream));
+            VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            PM.n_leaf_rows = (int)lr.size(); PM.leaf_rows_row0 = T.row0; PM.leaf_rows_row1 = T.row1;
+        }
+        n_short = PD.n_leaf_rows; d_rows = PD.leaf_rows.p;
+    }
+    static const int force_short = [] { const char* v = getenv("VRAD_K4_SHORT"); return v ? atoi(v) : -1; }();
+    const bool use_short = !p2p && (force_short >= 0 ? force_short != 0 : (T.nnz < (int64_t)400 * std::max(1, n_short)));
+    static const int short_cfg = [] { const char* v = getenv("VRAD_K4_SHORT_CFG"); return v ? atoi(v) : 86; }();   // lanes*10 + min blocks (experiments)
+    const int short_lanes = short_cfg / 10 == 16 ? 16 : (short_cfg / 10 == 4 ? 4 : 8);
+    const int short_rpb = kGatherBlock / short_lanes;
+    const int short_blocks = std::max(1, (n_short + short_rpb - 1) / short_rpb);
     const PeerTable* d_peers = p2p ? e->peers.d_table.p : nullptr;
 
     timing_begin(e);
@@ -532,6 +663,19 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         if (p2p)    // pending_wait false: nothing outstanding, the buffer read was initialised locally
             k4_gather_multi<true><<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
                                                                    e->d_er[cur ^ 1].p, total_local, e->d_partials.p, d_peers, cur ^ 1, pending_wait ? world : 0);
+        else if (use_short) {
+#define VRAD_SHORT(L, B) k4_gather_short<L, B><<<short_blocks, kGatherBlock, 0, e->stream>>>(n_short, d_rows, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, \
+                                                                 e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p)
+            switch (short_cfg) {
+                case 88: VRAD_SHORT(8, 8); break;
+                case 168: VRAD_SHORT(16, 8); break;
+                case 166: VRAD_SHORT(16, 6); break;
+                case 48: VRAD_SHORT(4, 8); break;
+                case 46: VRAD_SHORT(4, 6); break;
+                default: VRAD_SHORT(8, 6); break;
+            }
+#undef VRAD_SHORT
+        }
         else
             k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
                                                              e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
@@ -541,14 +685,14 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         if (p2p) { k4_peer_signal<<<1, 32, 0, e->stream>>>(d_peers); launches++; pending_wait = true; }
         else if (world > 1 && (rc = comm_allgather_rows(e, e->d_er[cur ^ 1].p, bounds))) return rc;
         if (hier) {     // CollectLight, interior patches: emit of a parent = area-weighted average of its children
-            k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_er[cur ^ 1].p);
+            k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_er[cur ^ 1].p);
             launches++;
         }
         if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
         cur ^= 1; done++;
         const bool last = (b + 1 == n_bounces);
         if (early_out || last) {
-            k4_reduce_added<<<1, 256, 0, e->stream>>>(nblocks, e->d_partials.p, d_added);
+            k4_reduce_added<<<1, 256, 0, e->stream>>>(use_short ? short_blocks : nblocks, e->d_partials.p, d_added);
             launches++;
             if (world > 1 && (rc = comm_allreduce3(e, d_added))) return rc;
         }
@@ -561,7 +705,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     if (pending_wait) { k4_peer_wait<<<1, 32, 0, e->stream>>>(d_peers); launches++; }
     if (world > 1 && (rc = comm_allgather_rows(e, e->d_total.p, bounds))) return rc;
     if (hier) {         // totallight of the interior patches, from the leaves' totals
-        k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_total.p);
+        k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_total.p);
         launches++;
     }
     if (d_out3) {
