@@ -379,6 +379,54 @@ def run_graft(args, rank, local_rank, world):
         env3.close()
         del e30, o30
 
+    # ---------------- widened rows, N=1 only, informational, outside every timed region above ----------------
+    widened = None
+    if world == 1 and not args.no_large:
+        try:
+            widened = {}
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # complete TestLineDoesHitSky: static-prop skip, transparent coverage, 3D-skybox recursion
+            sk = scenes.sky_room(); m = sk.meta
+            g = Environment(local_rank); g.add_triangles(sk.tri_ids, sk.tri_verts, sk.tri_flags); g.set_triangle_colors(m["tri_colors"])
+            g.setup_acceleration_structure(); g.bsp_upload(m["bsp"]); g.process_sky_cameras(m["cams_origin"], m["cams_scale"])
+            g.set_stream(stream); g.set_async(True)
+            ns = 1 << 23
+            sa, sb = scenes.sky_segments(sk, ns)
+            d_sa, d_sb = torch.from_numpy(sa).to(dev), torch.from_numpy(sb).to(dev)
+            d_fv = torch.empty(ns, dtype=torch.float32, device=dev)
+            sky = {"workload": "S4 sky room (732 tris, 48 transparent, 2 sky cameras), 2^23 segments via vrad_test_lines_sky", "segments": ns}
+            for flags, name in ((0, "sky_id_only"), (1, "with_skybox_recursion"), (3, "recursion_and_texture_shadows")):
+                for _ in range(2):
+                    g.test_lines_sky(d_sa, d_sb, flags, 7, out=d_fv)
+                e0.record()
+                for _ in range(3):
+                    g.test_lines_sky(d_sa, d_sb, flags, 7, out=d_fv)
+                e1.record(); torch.cuda.synchronize()
+                sky[name + "_segments_per_sec"] = ns / (e0.elapsed_time(e1) / 3 * 1e-3)
+            g.close(); del d_sa, d_sb, d_fv
+            widened["test_line_does_hit_sky"] = sky
+            # patch hierarchy: the C4 map with SubdividePatches trees, hierarchical transfers + CollectLight
+            hs = scenes.multi_room_hier(nx=12, ny=11); tr = hs.meta["tree"]
+            h = environment_from_scene(hs, device=local_rank)
+            h.set_hierarchy(tr["parent"], tr["child1"], tr["child2"], tr["face"])
+            h.set_stream(stream)
+            h.build_transfers(hs.pvs)
+            t0 = time.perf_counter(); hn = h.build_transfers(hs.pvs); torch.cuda.synchronize(); hk2 = time.perf_counter() - t0
+            hN = hs.n_patches
+            he = torch.full((hN, 3), 100.0, device=dev); ho = torch.empty_like(he)
+            h.set_async(True)
+            h.bounce(he, 10, out=ho, want_added=False)
+            e0.record(); h.bounce(he, 100, out=ho, want_added=False); e1.record(); torch.cuda.synchronize()
+            hms = e0.elapsed_time(e1) / 100
+            widened["patch_hierarchy"] = {
+                "workload": "C4 map, patches from vrad_patches_subdivide (roots + interior + leaves), hierarchical vrad_build_transfers, vrad_bounce with CollectLight",
+                "patches": hN, "leaf_patches": int((tr["child1"] == -1).sum()), "transfers": hn, "transfer_build_seconds": hk2,
+                "ms_per_bounce": hms, "iters_per_sec": 1e3 / hms, "gbs": (8 * hn + 40 * hN) / (hms * 1e-3) / 1e9,
+                "flat_map_transfers": nnz, "flat_map_ms_per_bounce": gather_ms / iters}
+            h.close(); del he, ho
+        except Exception as exc:  # informational only: never take the bench line down
+            widened = {"error": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -428,6 +476,7 @@ def run_graft(args, rank, local_rank, world):
         "cpu_baseline": cpu_rays_obj,
         "clocks": clocks,
         "large_scene": large,
+        "widened": widened,
         "gather": {
             "metric": "bounce_gather_iters_per_sec", "value": gather_value, "unit": "iters/s", "scaling": "strong",
             "steps": g_steps, "bounces_per_step": N_BOUNCES, "ms_per_iter": gather_ms / iters,

@@ -14,6 +14,21 @@ if what in ("k1", "k1s3"):
     for _ in range(4): env.test_lines(ta, tb, out=out)
     r = scenes.random_rays(s, 1 << 22)
     env.trace_rays(torch.from_numpy(r["o"]).cuda(), torch.from_numpy(r["d"]).cuda(), torch.from_numpy(r["tmax"]).cuda())
+elif what == "sky":
+    from vrad_b200.environment import Environment
+    s = scenes.sky_room(); m = s.meta
+    env = Environment(); env.add_triangles(s.tri_ids, s.tri_verts, s.tri_flags); env.set_triangle_colors(m["tri_colors"])
+    env.setup_acceleration_structure(); env.bsp_upload(m["bsp"]); env.process_sky_cameras(m["cams_origin"], m["cams_scale"])
+    a, b = scenes.sky_segments(s, 1 << 23)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.empty(1 << 23, dtype=torch.float32, device="cuda")
+    for _ in range(2): env.test_lines_sky(ta, tb, 3, 7, out=out)
+elif what == "hier":
+    s = scenes.multi_room_hier(nx=12, ny=11); t = s.meta["tree"]; env = environment_from_scene(s)
+    env.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
+    env.build_transfers(s.pvs)
+    e0 = torch.full((s.n_patches, 3), 100.0, device="cuda")
+    env.bounce(e0, 4)
 else:
     s = scenes.multi_room(); env = environment_from_scene(s)
     nnz = env.build_transfers(s.pvs)
