@@ -39,6 +39,9 @@ func check(rc C.int, what string) {
 	}
 }
 
+// CudaHandle exposes the handle to the sibling packages' shims (raytracer/trace, rad/patches, rad).
+func (environment *Environment) CudaHandle() unsafe.Pointer { return unsafe.Pointer(environment.cuda.h) }
+
 func newCudaEnv(device int) *cudaEnv {
 	cfg := C.vrad_config{device: C.int(device), rank: 0, world: 1, flags: 0}
 	var h *C.vrad_env
