@@ -236,6 +236,12 @@ int  vrad_transfers_download(vrad_env*, int64_t* rowptr, int32_t* col, float* w)
 int  vrad_transfers_download_rows(vrad_env*, int64_t row_begin, int64_t row_end, int64_t* rowptr, int32_t* col, float* w, int64_t capacity);
 /* sky-ambient sample directions (vmath.Anorms, vmath/constants.go:15,21-184) */
 int  vrad_set_sky_dirs(vrad_env*, int n, const float* dirs3);
+/* How K3's light rays are tested: 0 (default) = binary TestLine, sky lights with the sky-id rule only;
+ * VRAD_TL_CAN_RECURSE = sky lights go through the 3D-skybox recursion (canRecurse = true, as
+ * lightmap.CanLeafTraceToSky calls it, rad/lightmap/lightmap.go:444; needs vrad_bsp_upload + vrad_sky_cameras_set);
+ * VRAD_TL_TEXTURE_SHADOWS = every light ray accumulates transparent-triangle coverage (testline.go:14,32-34,52-55)
+ * and contributes dot * fractionVisible. */
+int  vrad_set_light_trace_flags(vrad_env*, int flags);
 /* per-luxel direct lighting with shadow rays (north_star K3; light parameters per vrad_light) */
 int  vrad_direct_light(vrad_env*, int64_t n_luxels, const float* pos3, const float* normal3,
                        int n_lights, const vrad_light* lights, float* rgb_out);

@@ -120,6 +120,8 @@ int  orc_transfers_get(orc_env*, int64_t* rowptr, int32_t* col, float* w);
 int64_t orc_transfer_row(orc_env*, int row, int n_clusters, const uint8_t* pvs, int32_t* col_out, float* w_out, int64_t cap);
 /* sky-ambient sample directions (the 162 `Anorms`, vmath/constants.go:15,21-184), copied */
 int  orc_set_sky_dirs(int n, const float* dirs3);
+/* light rays of orc_direct_light: 0 = binary TestLine; ORC_TL_CAN_RECURSE / ORC_TL_TEXTURE_SHADOWS = complete form */
+int  orc_env_set_light_trace_flags(orc_env*, int flags);
 /* K3: direct light per luxel; rgb_out 3 floats per luxel */
 int  orc_direct_light(orc_env*, int64_t n_luxels, const float* pos3, const float* normal3,
                       int n_lights, const orc_light* lights, float* rgb_out, int threads);

@@ -75,6 +75,7 @@ struct orc_env {
     std::vector<float>   tri_color;   // Environment.TriangleColors (raytracer/environment.go:61-63), 3 per triangle
     orc::Bsp bsp;
     orc::SkyCameras cams;
+    int light_trace_flags = 0;        // ORC_TL_CAN_RECURSE | ORC_TL_TEXTURE_SHADOWS for the light rays of orc_direct_light
 };
 
 namespace orc {
@@ -96,6 +97,10 @@ void trace4(const orc_env* e, const float o[3][4], const float d[3][4], const fl
 // raytracer/types/coverageCount.go:27-37); coverage == nullptr is exactly trace1.
 Hit trace1_coverage(const orc_env* e, const float o[3], const float d[3], float tmin, float tmax,
                     int32_t skip_id, float* coverage);
+
+// complete TestLineDoesHitSky on one segment (oracle/skytrace.cpp); leaf_point decides the recursion
+float test_line_sky1(const orc_env* e, const float a[3], const float b[3], const float leaf_point[3], int flags, int32_t skip_id);
+float test_line_fraction(const orc_env* e, const float a[3], const float b[3], int flags, int32_t skip_id);
 
 // TestLine on one segment: returns 1 if visible.  mode: 0 spec, 2 brute.
 int test_line1(const orc_env* e, const float a[3], const float b[3], int sky_mode, int mode);

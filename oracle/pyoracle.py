@@ -230,6 +230,9 @@ class OracleEnv:
         d = _f32(dirs3).reshape(-1, 3)
         assert self._l.orc_set_sky_dirs(C.c_int(d.shape[0]), _p(d)) == 0
 
+    def set_light_trace_flags(self, flags):
+        assert self._l.orc_env_set_light_trace_flags(self._h, C.c_int(flags)) == 0
+
     def direct_light(self, pos, normal, lights, threads=1):
         pos = _f32(pos); normal = _f32(normal)
         lights = np.ascontiguousarray(lights)

@@ -187,6 +187,8 @@ int orc_transfers_get(orc_env* e, int64_t* rowptr, int32_t* col, float* w) {
 static std::vector<float> g_sky_dirs; static int g_n_sky_dirs = 0;
 int orc_set_sky_dirs(int n, const float* dirs3) { g_sky_dirs.assign(dirs3, dirs3 + 3 * (size_t)n); g_n_sky_dirs = n; return 0; }
 
+int orc_env_set_light_trace_flags(orc_env* e, int flags) { if (!e) return -1; e->light_trace_flags = flags; return 0; }
+
 int orc_direct_light(orc_env* e, int64_t n_luxels, const float* pos3, const float* normal3, int n_lights,
                      const orc_light* lights, float* rgb_out, int threads) {
     if (!e || !e->built) return -1;
@@ -235,15 +237,27 @@ int orc_direct_light(orc_env* e, int64_t n_luxels, const float* pos3, const floa
                     float s = 1.0f - ((t * t) * (3.0f - (2.0f * t)));
                     falloff = falloff * s;
                 }
-                if (!test_line1(e, pos, dl.origin, 0, 0)) continue;
-                scale = falloff * dot;
+                if (e->light_trace_flags == 0) {
+                    if (!test_line1(e, pos, dl.origin, 0, 0)) continue;
+                    scale = falloff * dot;
+                } else {                                                 // App. B.2: dot *= fractionVisible
+                    float fv = test_line_fraction(e, pos, dl.origin, e->light_trace_flags, ORC_TRACE_ID_STATICPROP | -1);
+                    if (!(fv > 0.0f)) continue;
+                    scale = (falloff * dot) * fv;
+                }
             } else if (dl.type == 3) {                                  // skylight (sun)
                 float dot = -dot3(dl.normal, n);
                 if (!(dot > 0.0f)) continue;
                 float stop[3] = {pos[0] - (dl.normal[0] * MAX_TRACE_LENGTH), pos[1] - (dl.normal[1] * MAX_TRACE_LENGTH),
                                  pos[2] - (dl.normal[2] * MAX_TRACE_LENGTH)};
-                if (!test_line1(e, pos, stop, 1, 0)) continue;
-                scale = dot;
+                if (e->light_trace_flags == 0) {
+                    if (!test_line1(e, pos, stop, 1, 0)) continue;
+                    scale = dot;
+                } else {
+                    float fv = test_line_sky1(e, pos, stop, pos, e->light_trace_flags, ORC_TRACE_ID_STATICPROP | -1);
+                    if (!(fv > 0.0f)) continue;
+                    scale = dot * fv;
+                }
             } else if (dl.type == 5) {                                  // sky ambient
                 float sum = 0.0f, possible = 0.0f;
                 for (int k = 0; k < g_n_sky_dirs; k++) {
@@ -253,7 +267,12 @@ int orc_direct_light(orc_env* e, int64_t n_luxels, const float* pos3, const floa
                     possible = possible + dot;
                     float stop[3] = {pos[0] + (a[0] * MAX_TRACE_LENGTH), pos[1] + (a[1] * MAX_TRACE_LENGTH),
                                      pos[2] + (a[2] * MAX_TRACE_LENGTH)};
-                    if (test_line1(e, pos, stop, 1, 0)) sum = sum + dot;
+                    if (e->light_trace_flags == 0) {
+                        if (test_line1(e, pos, stop, 1, 0)) sum = sum + dot;
+                    } else {
+                        float fv = test_line_sky1(e, pos, stop, pos, e->light_trace_flags, ORC_TRACE_ID_STATICPROP | -1);
+                        if (fv > 0.0f) sum = sum + (dot * fv);
+                    }
                 }
                 if (!(possible > 0.0f)) continue;
                 scale = sum / possible;

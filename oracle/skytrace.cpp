@@ -172,14 +172,15 @@ static inline bool segment_to_ray(const float a[3], const float b[3], float d[3]
 }
 
 // testline.go:22-55: occlusion of one lane before the recursion
-static float primary_occlusion(const orc_env* e, const float a[3], const float b[3], int flags, int32_t skip_id, bool* degenerate) {
+static float primary_occlusion(const orc_env* e, const float a[3], const float b[3], int flags, int32_t skip_id, bool* degenerate,
+                               bool sky_rule = true) {
     float d[3], len;
     *degenerate = false;
     if (!segment_to_ray(a, b, d, len)) { *degenerate = true; return 0.0f; }
     float cov = 0.0f;
     Hit h = trace1_coverage(e, a, d, 0.0f, len, skip_id, (flags & ORC_TL_TEXTURE_SHADOWS) ? &cov : nullptr);
     float occ = 0.0f;
-    if (h.tri != -1 && h.t < len && (e->tris[h.tri].id & ORC_TRACE_ID_SKY) == 0) occ = 1.0f;
+    if (h.tri != -1 && h.t < len && (!sky_rule || (e->tris[h.tri].id & ORC_TRACE_ID_SKY) == 0)) occ = 1.0f;
     if (flags & ORC_TL_TEXTURE_SHADOWS) occ = max_sel(occ, cov);
     return occ;
 }
@@ -191,7 +192,14 @@ static inline float finish(float occ) {                  // testline.go:91-93
 }
 
 // leaf_point: the point whose leaf/area decides the recursion (own start, or lane 0's with ORC_TL_PACKET_LEAF)
-static float test_line_sky1(const orc_env* e, const float a[3], const float b[3], const float leaf_point[3], int flags, int32_t skip_id) {
+// trace.TestLine as a fraction (App. B.1: no sky rule, no recursion), with coverage when ORC_TL_TEXTURE_SHADOWS is set
+float test_line_fraction(const orc_env* e, const float a[3], const float b[3], int flags, int32_t skip_id) {
+    bool degenerate;
+    float occ = primary_occlusion(e, a, b, flags, skip_id, &degenerate, false);
+    return degenerate ? 1.0f : finish(occ);
+}
+
+float test_line_sky1(const orc_env* e, const float a[3], const float b[3], const float leaf_point[3], int flags, int32_t skip_id) {
     bool degenerate;
     float occ = primary_occlusion(e, a, b, flags, skip_id, &degenerate);
     if (degenerate) return 1.0f;

@@ -160,3 +160,46 @@ def test_errors_are_loud(sky_scene):
     a, b = scenes.sky_segments(sky_scene, 100, seed=1)
     assert np.array_equal(e.test_lines_sky(a, b, 1, -1), e.test_lines_sky(a, b, 0, -1))
     e.close()
+
+
+def _floor_luxels_and_lights():
+    xs = np.arange(-496, 512, 32, dtype=np.float32)
+    gx, gy = np.meshgrid(xs, xs, indexing="ij")
+    pos = np.stack([gx.ravel(), gy.ravel(), np.full(gx.size, 1.0, np.float32)], axis=1)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (pos.shape[0], 1))
+    L = np.zeros(4, dtype=scenes.LIGHT_DTYPE)
+    L["start_fade"], L["end_fade"], L["cap_dist"] = 0.0, -1.0, 1.0e22
+    sun = np.array([-0.4, -0.3, -0.87]); sun /= np.linalg.norm(sun)
+    L[0]["type"] = scenes.EMIT_SKYLIGHT; L[0]["normal"] = sun; L[0]["intensity"] = (300, 280, 250)
+    L[1]["type"] = scenes.EMIT_SKYAMBIENT; L[1]["intensity"] = (40, 50, 70)
+    L[2]["type"] = scenes.EMIT_POINT; L[2]["origin"] = (100, 50, 500); L[2]["quadratic_attn"] = 1.0; L[2]["intensity"] = (4e6, 4e6, 4e6)
+    L[3]["type"] = scenes.EMIT_SPOTLIGHT; L[3]["origin"] = (-200, -100, 505); L[3]["normal"] = (0, 0, -1)
+    L[3]["stopdot"], L[3]["stopdot2"], L[3]["exponent"] = 0.8, 0.6, 1.0
+    L[3]["quadratic_attn"] = 1.0; L[3]["intensity"] = (3e6, 2e6, 1e6)
+    return pos, nrm, L
+
+
+def test_direct_light_with_complete_sky_test(sky_scene, sky_pair):
+    """K3 light rays through the complete TestLineDoesHitSky (vrad_set_light_trace_flags): sun + sky ambient with the
+    3D-skybox recursion, every light with transparent-triangle coverage (dot *= fractionVisible).  Exponent 1 and no
+    powf anywhere -> bit-exact against the oracle."""
+    g, o = sky_pair
+    dirs = np.loadtxt(os.path.join(os.path.dirname(__file__), "..", "vrad_b200", "data", "anorms.txt"), dtype=np.float32)
+    g.set_sky_dirs(dirs); o.set_sky_dirs(dirs)
+    pos, nrm, L = _floor_luxels_and_lights()
+    res = {}
+    try:
+        for flags in (0, 1, 2, 3):
+            g.set_light_trace_flags(flags); o.set_light_trace_flags(flags)
+            gl = g.direct_light(pos, nrm, L)
+            ol = o.direct_light(pos, nrm, L, threads=8)
+            assert _same_bits(gl, ol), flags
+            res[flags] = gl
+    finally:
+        g.set_light_trace_flags(0); o.set_light_trace_flags(0)
+    assert (res[0] != res[1]).any(axis=1).sum() > 50          # the sky boxes take light away
+    assert np.all(res[1].sum(axis=1) <= res[0].sum(axis=1) + 1e-3)
+    assert (res[2].sum(axis=1) >= res[0].sum(axis=1) - 1e-3).all() and res[2].mean() > 2 * res[0].mean()   # panes stop being hard blockers
+    from vrad_b200.environment import VradError
+    with pytest.raises(VradError):
+        g.set_light_trace_flags(4)                            # PACKET_LEAF has no meaning for light rays

@@ -159,6 +159,7 @@ struct vrad_env {
     vrad::PatchesDev patches;
     vrad::TransfersDev transfers;
     vrad::DevBuf<float> d_sky_dirs; int n_sky_dirs = 0;
+    int light_trace_flags = 0;         // VRAD_TL_CAN_RECURSE | VRAD_TL_TEXTURE_SHADOWS for the light rays of K3
 
     // bounce state
     vrad::DevBuf<float4> d_er[2];      // emit*refl (rgb, pad), full N (padded to world*rows_per_rank)

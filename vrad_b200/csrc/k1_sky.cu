@@ -16,50 +16,11 @@
 // subset).  HBM traffic: 24 B in + 4 B out per segment for the primary pass; the recursion pass re-reads
 // 24 B + 4 B and rewrites 4 B for the segments of warps that recurse.
 #include "env_internal.cuh"
+#include "sky.cuh"
 
 namespace vrad {
 
 constexpr int kSkyBlock = 128;
-constexpr float kMaxTraceLength = (float)(1.732050807569 * 32768.0);   // common/constants/constants.go:15-19
-constexpr float kTestEpsilon = 0.03125f;                               // vmath/constants.go:7
-constexpr int   kPilStack = 64;
-
-// raytracer/trace/pointleaf.go:8-33
-__device__ __forceinline__ int point_leafnum(const DevBsp& B, float px, float py, float pz) {
-    if (B.n_nodes == 0) return 0;
-    int node = 0;
-    while (node >= 0) {
-        const int4 nd = __ldg(&B.nodes[node]);
-        const float4 pl = __ldg(&B.planes[nd.x]);
-        float dist;
-        if (nd.w < 3) dist = pick3(nd.w, px, py, pz) - pl.w;
-        else dist = (((pl.x * px) + (pl.y * py)) + (pl.z * pz)) - pl.w;
-        node = (dist < 0.0f) ? nd.z : nd.y;
-    }
-    return -1 - node;
-}
-
-// rad/clustertable/point.go:14-38, the recursion unrolled into a stack of pending back children:
-// the front branch wins unless it ends in a cluster -1 leaf
-__device__ __forceinline__ int point_in_leaf(const DevBsp& B, float px, float py, float pz) {
-    if (B.n_nodes == 0) return 0;
-    int pending[kPilStack];
-    int sp = 0;
-    int node = 0;
-    for (;;) {
-        while (node >= 0) {
-            const int4 nd = __ldg(&B.nodes[node]);
-            const float4 pl = __ldg(&B.planes[nd.x]);
-            const float dist = (((px * pl.x) + (py * pl.y)) + (pz * pl.z)) - pl.w;
-            if (dist > kTestEpsilon) node = nd.y;
-            else if (dist < -kTestEpsilon) node = nd.z;
-            else { if (sp < kPilStack) pending[sp++] = nd.z; node = nd.y; }
-        }
-        const int leaf = -1 - node;
-        if (sp == 0 || __ldg(&B.leaf_cluster[leaf]) != -1) return leaf;
-        node = pending[--sp];
-    }
-}
 
 __global__ void __launch_bounds__(256)
 k_point_leafnum(DevBsp B, int64_t n, const float* __restrict__ pts, int32_t* __restrict__ out, int want_cluster) {
@@ -68,31 +29,6 @@ k_point_leafnum(DevBsp B, int64_t n, const float* __restrict__ pts, int32_t* __r
     const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
     if (want_cluster) out[i] = __ldg(&B.leaf_cluster[point_in_leaf(B, x, y, z)]);
     else out[i] = point_leafnum(B, x, y, z);
-}
-
-// testline.go:22-55 for one lane: occlusion before the recursion.  Warp-synchronous.
-template <bool COVER>
-__device__ __forceinline__ float primary_occlusion(const DevScene& S, bool valid, float ax, float ay, float az,
-                                                   float bx, float by, float bz, int skip_id, bool& degenerate) {
-    Ray r; float len = 0.0f;
-    r.ox = r.oy = r.oz = 0.0f; r.dx = r.dy = r.dz = 1.0f;
-    const bool ok = segment_to_ray(ax, ay, az, bx, by, bz, r, len);
-    degenerate = !ok;
-    int tri; float t; float cov = 0.0f;
-    if (COVER) trace_ray_cover(S, r, valid && ok, 0.0f, len, skip_id, tri, t, cov);
-    else trace_ray<false>(S, r, valid && ok, 0.0f, len, skip_id, 0.0f, tri, t);
-    float occ = 0.0f;
-    if (valid && ok) {
-        if (tri != -1 && t < len && (__float_as_int(__ldg(&S.q2[tri]).z) & 0x01000000) == 0) occ = 1.0f;
-        if (COVER) occ = max_sel(occ, cov);
-    }
-    return occ;
-}
-
-__device__ __forceinline__ float finish_fraction(float occ) {     // testline.go:91-93
-    occ = max_sel(occ, 0.0f);
-    occ = min_sel(occ, 1.0f);
-    return 1.0f - occ;
 }
 
 // pass 1: occlusion of every segment (final fraction when no recursion pass follows)

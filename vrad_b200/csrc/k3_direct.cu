@@ -11,11 +11,31 @@
 // directions together (parallel rays per round); a final pass accumulates RGB per luxel in light
 // order, which keeps the sum bit-identical to the sequential CPU formulation.
 #include "env_internal.cuh"
+#include "sky.cuh"
 
 namespace vrad {
 
 constexpr float kEqualEpsilon = 0.001f;                              // vmath/constants.go:9
-constexpr float kMaxTraceLength = 1.732050807569f * 32768.0f;        // common/constants/constants.go:15-19
+// (kMaxTraceLength: sky.cuh; common/constants/constants.go:15-19)
+
+// Visibility of a light ray.  MODE 0: the binary TestLine / sky-id TestLine of the base path (any-hit traversal for
+// point lights).  MODE 1 / 2: the complete form of raytracer/trace/testline.go:18-94 selected with
+// vrad_set_light_trace_flags -- sky lights go through the 3D-skybox recursion; with MODE 2 (texture shadows)
+// every light ray accumulates transparent-triangle coverage and the result is a fraction (App. B.2: dot *= fractionVisible).
+template <int MODE>
+__device__ __forceinline__ float light_ray_fraction(const DevScene& S, const DevBsp& B, bool ok, float px, float py, float pz,
+                                                    float sx, float sy, float sz, bool sky_light, bool can_recurse) {
+    if (MODE == 0) return (float)(segment_visible(S, ok, px, py, pz, sx, sy, sz, sky_light ? 1 : 0) && ok);
+    if (sky_light) {       // warp-uniform (light type)
+        const float fv = MODE == 2 ? sky_fraction<true>(S, B, ok, px, py, pz, sx, sy, sz, can_recurse, px, py, pz, VRAD_TRACE_ID_STATICPROP | -1)
+                                   : sky_fraction<false>(S, B, ok, px, py, pz, sx, sy, sz, can_recurse, px, py, pz, VRAD_TRACE_ID_STATICPROP | -1);
+        return ok ? fv : 0.0f;
+    }
+    bool degenerate;
+    const float occ = MODE == 2 ? primary_occlusion<true, false>(S, ok, px, py, pz, sx, sy, sz, VRAD_TRACE_ID_STATICPROP | -1, degenerate)
+                                : primary_occlusion<false, false>(S, ok, px, py, pz, sx, sy, sz, VRAD_TRACE_ID_STATICPROP | -1, degenerate);
+    return ok ? finish_fraction(occ) : 0.0f;
+}
 
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
     return ((ax * bx) + (ay * by)) + (az * bz);
@@ -24,8 +44,9 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 // Pair index space is light-major and padded to whole warps: a warp holds 32 consecutive luxels of
 // ONE light, so its rays share an end point (coherent traversal) and the light type / sky mode is
 // warp-uniform.  The shadow test is warp-synchronous: every lane calls segment_visible once.
+template <int MODE>
 __global__ void __launch_bounds__(128)
-k3_pair_scale(DevScene S, int64_t n_luxels, int n_lights, const float* __restrict__ pos3,
+k3_pair_scale(DevScene S, DevBsp B, int can_recurse, int64_t n_luxels, int n_lights, const float* __restrict__ pos3,
               const float* __restrict__ nrm3, const vrad_light* __restrict__ lights, float* __restrict__ scale_out) {
     const int64_t n_pad = (n_luxels + 31) & ~(int64_t)31;
     const int64_t total = n_pad * n_lights;
@@ -97,8 +118,13 @@ k3_pair_scale(DevScene S, int64_t n_luxels, int n_lights, const float* __restric
             sx = px - (dl.normal[0] * kMaxTraceLength); sy = py - (dl.normal[1] * kMaxTraceLength);
             sz = pz - (dl.normal[2] * kMaxTraceLength);
         }
-        const int vis = segment_visible(S, ok, px, py, pz, sx, sy, sz, type == 3 ? 1 : 0);
-        if (in_range) scale_out[i * n_lights + L] = (ok && vis) ? value : 0.0f;
+        if (MODE == 0) {
+            const int vis = segment_visible(S, ok, px, py, pz, sx, sy, sz, type == 3 ? 1 : 0);
+            if (in_range) scale_out[i * n_lights + L] = (ok && vis) ? value : 0.0f;
+        } else {
+            const float fv = light_ray_fraction<MODE>(S, B, ok, px, py, pz, sx, sy, sz, type == 3, can_recurse != 0);
+            if (in_range) scale_out[i * n_lights + L] = (ok && fv > 0.0f) ? value * fv : 0.0f;
+        }
     }
 }
 
@@ -107,8 +133,9 @@ k3_pair_scale(DevScene S, int64_t n_luxels, int n_lights, const float* __restric
 // with lanes over the 162 directions fans out over the whole hemisphere and ran at 0.8 G rays/s on the
 // 1 M-triangle map against 3.2 G rays/s for the parallel sun rays).  Each lane accumulates its own luxel
 // in direction order, i.e. exactly the sequential CPU sum.
+template <int MODE>
 __global__ void __launch_bounds__(128)
-k3_sky_ambient(DevScene S, int64_t n_luxels, int n_lights, int light_index, int n_dirs, const float* __restrict__ dirs3,
+k3_sky_ambient(DevScene S, DevBsp B, int can_recurse, int64_t n_luxels, int n_lights, int light_index, int n_dirs, const float* __restrict__ dirs3,
                const float* __restrict__ pos3, const float* __restrict__ nrm3, float* __restrict__ scale_out) {
     const int64_t n_pad = (n_luxels + 31) & ~(int64_t)31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -126,9 +153,15 @@ k3_sky_ambient(DevScene S, int64_t n_luxels, int n_lights, int light_index, int 
             const bool want = in_range && dot > kEqualEpsilon;
             if (!__any_sync(0xffffffffu, want)) continue;
             if (want) possible = possible + dot;
-            const int vis = segment_visible(S, want, px, py, pz, px + (ax * kMaxTraceLength), py + (ay * kMaxTraceLength),
-                                            pz + (az * kMaxTraceLength), 1);
-            if (want && vis) sum = sum + dot;
+            if (MODE == 0) {
+                const int vis = segment_visible(S, want, px, py, pz, px + (ax * kMaxTraceLength), py + (ay * kMaxTraceLength),
+                                                pz + (az * kMaxTraceLength), 1);
+                if (want && vis) sum = sum + dot;
+            } else {
+                const float fv = light_ray_fraction<MODE>(S, B, want, px, py, pz, px + (ax * kMaxTraceLength), py + (ay * kMaxTraceLength),
+                                                          pz + (az * kMaxTraceLength), true, can_recurse != 0);
+                if (want && fv > 0.0f) sum = sum + (dot * fv);
+            }
         }
         if (in_range) scale_out[i * n_lights + light_index] = possible > 0.0f ? sum / possible : 0.0f;
     }
@@ -165,6 +198,12 @@ int vrad_set_sky_dirs(vrad_env* e, int n, const float* dirs3) {
     return VRAD_OK;
 }
 
+int vrad_set_light_trace_flags(vrad_env* e, int flags) {
+    if (!e || (flags & ~(VRAD_TL_CAN_RECURSE | VRAD_TL_TEXTURE_SHADOWS))) { set_error("vrad_set_light_trace_flags: bad arguments"); return VRAD_E_INVALID; }
+    e->light_trace_flags = flags;
+    return VRAD_OK;
+}
+
 int vrad_direct_light(vrad_env* e, int64_t n_luxels, const float* pos3, const float* normal3, int n_lights,
                       const vrad_light* lights, float* rgb_out) {
     if (!e || n_luxels < 0 || n_lights < 0 || (n_luxels > 0 && (!pos3 || !normal3 || !rgb_out)) || (n_lights > 0 && !lights)) {
@@ -196,14 +235,25 @@ int vrad_direct_light(vrad_env* e, int64_t n_luxels, const float* pos3, const fl
         VRAD_CUDA_CHECK(cudaMemsetAsync(d_scale, 0, nscale * 4, e->stream));
         const int64_t total = ((n_luxels + 31) & ~(int64_t)31) * n_lights;
         int64_t blocks = (total + 127) / 128, cap = (int64_t)e->sm_count * 64;
-        k3_pair_scale<<<(int)(blocks < cap ? blocks : cap), 128, 0, e->stream>>>(e->scene, n_luxels, n_lights, (const float*)d_pos,
-                                                                               (const float*)d_nrm, (const vrad_light*)d_l, (float*)d_scale);
+        // light_trace_flags (vrad_set_light_trace_flags): 0 = base path; recursion and/or texture shadows = complete TestLineDoesHitSky
+        const int mode = (e->light_trace_flags & VRAD_TL_TEXTURE_SHADOWS) ? 2 : ((e->light_trace_flags & VRAD_TL_CAN_RECURSE) ? 1 : 0);
+        const int rec = (e->light_trace_flags & VRAD_TL_CAN_RECURSE) && e->bsp_ready ? 1 : 0;
+        const int grid1 = (int)(blocks < cap ? blocks : cap);
+#define K3_ARGS e->scene, e->bsp, rec, n_luxels, n_lights, (const float*)d_pos, (const float*)d_nrm, (const vrad_light*)d_l, (float*)d_scale
+        if (mode == 0) k3_pair_scale<0><<<grid1, 128, 0, e->stream>>>(K3_ARGS);
+        else if (mode == 1) k3_pair_scale<1><<<grid1, 128, 0, e->stream>>>(K3_ARGS);
+        else k3_pair_scale<2><<<grid1, 128, 0, e->stream>>>(K3_ARGS);
+#undef K3_ARGS
         launches++;
         for (int L = 0; L < n_lights; L++) {
             if (hl[L].type != 5) continue;
             int64_t b2 = (n_luxels + 127) / 128;
-            k3_sky_ambient<<<(int)(b2 < cap ? b2 : cap), 128, 0, e->stream>>>(e->scene, n_luxels, n_lights, L, e->n_sky_dirs, e->d_sky_dirs.p,
-                                                                           (const float*)d_pos, (const float*)d_nrm, (float*)d_scale);
+            const int grid2 = (int)(b2 < cap ? b2 : cap);
+#define K3_ARGS e->scene, e->bsp, rec, n_luxels, n_lights, L, e->n_sky_dirs, e->d_sky_dirs.p, (const float*)d_pos, (const float*)d_nrm, (float*)d_scale
+            if (mode == 0) k3_sky_ambient<0><<<grid2, 128, 0, e->stream>>>(K3_ARGS);
+            else if (mode == 1) k3_sky_ambient<1><<<grid2, 128, 0, e->stream>>>(K3_ARGS);
+            else k3_sky_ambient<2><<<grid2, 128, 0, e->stream>>>(K3_ARGS);
+#undef K3_ARGS
             launches++;
         }
     }

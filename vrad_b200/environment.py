@@ -296,6 +296,10 @@ class Environment:
         d = np.ascontiguousarray(dirs3, np.float32).reshape(-1, 3)
         check(self._l.vrad_set_sky_dirs(self._h, C.c_int(d.shape[0]), ptr(d)))
 
+    def set_light_trace_flags(self, flags: int):
+        """TL_CAN_RECURSE / TL_TEXTURE_SHADOWS for the light rays of direct_light (0 = binary TestLine)."""
+        check(self._l.vrad_set_light_trace_flags(self._h, C.c_int(flags)))
+
     def direct_light(self, pos, normal, lights, out=None):
         pos = _f32(pos); normal = _f32(normal)
         lights = np.ascontiguousarray(lights)
