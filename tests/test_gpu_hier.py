@@ -104,3 +104,25 @@ def test_hierarchy_validation(hier_scene):
     with pytest.raises(VradError):
         e.set_hierarchy(t["parent"], t["child1"], t["child2"])                  # a child with its own reflectivity
     e.close()
+
+
+def test_per_candidate_form_gives_the_same_rows(hier_scene, hier_pair, tmp_path):
+    """The top-down kernel (default) and the per-candidate kernel (fallback when a shared-memory list overflows;
+    forced with VRAD_K2_TOPDOWN=0, read once per process) must produce identical transfer lists."""
+    import hashlib, os, subprocess, sys
+    g = hier_pair[0]
+    rg, cg, wg = g.transfers_download()
+    want = hashlib.sha256(rg.tobytes() + cg.tobytes() + wg.tobytes()).hexdigest()
+    code = (
+        "import sys, hashlib; sys.path.insert(0, %r)\n"
+        "from vrad_b200 import scenes\n"
+        "from vrad_b200.environment import environment_from_scene\n"
+        "s = scenes.multi_room_hier(nx=3, ny=2); t = s.meta['tree']\n"
+        "e = environment_from_scene(s); e.set_hierarchy(t['parent'], t['child1'], t['child2'], t['face'])\n"
+        "e.build_transfers(s.pvs); r, c, w = e.transfers_download()\n"
+        "print('HASH', hashlib.sha256(r.tobytes() + c.tobytes() + w.tobytes()).hexdigest())\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VRAD_K2_TOPDOWN="0"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = [l.split()[1] for l in out.stdout.splitlines() if l.startswith("HASH")][0]
+    assert got == want

@@ -58,7 +58,8 @@ struct PatchesDev {
     DevBuf<int32_t> collect_ids;                // interior patch numbers
     DevBuf<int64_t> collect_ptr;                // n_interior + 1 offsets into collect_ent
     DevBuf<int2>    collect_ent;                // {leaf patch, weight bits}
-    std::vector<int32_t> h_child1;
+    std::vector<int32_t> h_child1, h_parent;
+    DevBuf<int32_t> child2;
     DevBuf<int32_t> leaf_rows;                  // local row numbers of the leaf patches in [leaf_rows_row0, leaf_rows_row1)
     int n_leaf_rows = 0;
     int64_t leaf_rows_row0 = -1, leaf_rows_row1 = -1;

@@ -147,6 +147,101 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
     }
 }
 
+// Pass A, hierarchical form, top down (the walk as upstream runs it).  The per-candidate kernel above evaluates every
+// patch of every visible face tree for every row (5.8e9 (row, candidate) pairs on the full S2 map for 23.5 M kept
+// transfers); here a block expands receiver i's emitter set level by level from the face roots its cluster sees:
+// a frontier in shared memory, each thread takes a node, pushes its two children when the node is large for its
+// distance, otherwise appends it to the accepted list; then the accepted emitters run the cheap tests and the shadow
+// ray warp-synchronously.  A kept emitter sets the bit at its position in the row's sorted candidate list (binary
+// search), so the bit matrix, the count/scan/fill passes and the row order are the same as before -- and so is the
+// result, bit for bit.  Receivers are the local leaf rows; no pair sharing (rows of ~150 emitters make rays cheap).
+// The accepted list is flushed (tested and traced) whenever the next level could overflow it; if a frontier
+// overflows its shared-memory capacity the host reruns the row block with the per-candidate kernel.
+constexpr int kTdThreads = 128;
+constexpr int kTdFrontier = 1024;       // a level's frontier is ~50 nodes per nearby face plane whatever the level (|d|^2 < 16 area)
+constexpr int kTdAccepted = 2048;       // flushed (tested + traced) whenever the next level could overflow it
+
+__global__ void __launch_bounds__(kTdThreads)
+k2_visibility_topdown(DevScene S, PatchView P, int n_rows, const int32_t* __restrict__ rows, int64_t row0,
+                      const int32_t* __restrict__ cluster, const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx,
+                      const int64_t* __restrict__ root_ptr, const int32_t* __restrict__ root_idx,
+                      const int64_t* __restrict__ bit_ptr, uint32_t* __restrict__ bits,
+                      const int4* __restrict__ tree, const int32_t* __restrict__ child2, int* __restrict__ overflow) {
+    __shared__ int fr[2][kTdFrontier];
+    __shared__ int acc[kTdAccepted];
+    __shared__ int n_fr[2], n_acc;
+    const int tid = threadIdx.x;
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const int row = __ldg(&rows[r]);
+        const int i = (int)(row0 + row);
+        const float4 oi = __ldg(&P.origin_area[i]), ni = __ldg(&P.normal_dist[i]);
+        if (__ldg(&P.refl[i]).w != 0.0f) continue;                      // sky patches receive nothing (block-uniform)
+        const int ci = __ldg(&cluster[i]);
+        const int face_i = __ldg(&tree[i]).z;
+        const int64_t c0 = __ldg(&cand_ptr[ci]);
+        const int K = (int)(__ldg(&cand_ptr[ci + 1]) - c0);
+        uint32_t* out = bits + bit_ptr[row];
+        // the accepted emitters so far: cheap tests, shadow ray (warp-synchronous), bit at the emitter's list position
+        auto flush = [&]() {
+            const int na = min(n_acc, kTdAccepted);
+            for (int p = tid; p < ((na + 31) & ~31); p += kTdThreads) {
+                bool need = false;
+                int j = i;
+                float4 a = oi, an = ni, b = oi, bn = ni;
+                if (p < na) {
+                    j = acc[p];
+                    if (j != i) {
+                        const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
+                        need = transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w) != 0.0f;
+                        if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
+                    }
+                }
+                const int vis = segment_visible(S, need, a.x + an.x, a.y + an.y, a.z + an.z, b.x + bn.x, b.y + bn.y, b.z + bn.z, 0) && need;
+                if (vis) {
+                    int lo = 0, hi = K;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&cand_idx[c0 + mid]) < j) lo = mid + 1; else hi = mid; }
+                    atomicOr(&out[lo >> 5], 1u << (lo & 31));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) n_acc = 0;
+            __syncthreads();
+        };
+        if (tid == 0) { n_fr[0] = 0; n_fr[1] = 0; n_acc = 0; }
+        __syncthreads();
+        for (int64_t k = __ldg(&root_ptr[ci]) + tid; k < __ldg(&root_ptr[ci + 1]); k += kTdThreads) {
+            const int rt = __ldg(&root_idx[k]);
+            if (face_i >= 0 && __ldg(&tree[rt]).z == face_i) continue;  // "don't check patches on the same face"
+            const int pos = atomicAdd(&n_fr[0], 1);
+            if (pos < kTdFrontier) fr[0][pos] = rt; else *overflow = 1;
+        }
+        __syncthreads();
+        int cur = 0;
+        for (;;) {
+            const int n = min(n_fr[cur], kTdFrontier);
+            if (n == 0) break;
+            if (n_acc + n > kTdAccepted) flush();                       // block-uniform: both counts are shared
+            for (int k = tid; k < n; k += kTdThreads) {
+                const int j = fr[cur][k];
+                const int c1 = __ldg(&tree[j]).y;
+                const float4 oj = __ldg(&P.origin_area[j]);
+                const float dx = oi.x - oj.x, dy = oi.y - oj.y, dz = oi.z - oj.z;
+                if (c1 != -1 && (((dx * dx) + (dy * dy)) + (dz * dz)) * 0.0625f < oj.w) {
+                    const int pos = atomicAdd(&n_fr[cur ^ 1], 2);
+                    if (pos + 1 < kTdFrontier) { fr[cur ^ 1][pos] = c1; fr[cur ^ 1][pos + 1] = __ldg(&child2[j]); } else *overflow = 1;
+                } else {
+                    acc[atomicAdd(&n_acc, 1)] = j;                      // room was made above
+                }
+            }
+            __syncthreads();
+            if (tid == 0) n_fr[cur] = 0;
+            cur ^= 1;
+            __syncthreads();
+        }
+        flush();
+    }
+}
+
 // Load estimate for the multi-GPU row partition: per row, the number of transfers it will hold, estimated by
 // running the full pair test (cheap tests + shadow ray) on every 16th candidate (staggered by row).  The
 // per-bounce gather streams exactly these entries, so blocks balanced on this estimate keep the bounce loop --
@@ -298,6 +393,18 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
         std::sort(cand_idx.begin() + start, cand_idx.end());
         cand_ptr[c + 1] = (int64_t)cand_idx.size();
     }
+    // hierarchical top-down form: per cluster, the face roots (patches without a parent) of the clusters it sees
+    std::vector<int64_t> root_ptr(C + 1, 0);
+    std::vector<int32_t> root_idx;
+    if (hier) {
+        std::vector<std::vector<int32_t>> roots(C);
+        for (int i = 0; i < N; i++) if (P.h_parent[i] == -1) roots[rclus[i]].push_back(i);
+        for (int c = 0; c < C; c++) {
+            for (int c2 = 0; c2 < C; c2++)
+                if (!pvs || pvs[(size_t)c * C + c2]) root_idx.insert(root_idx.end(), roots[c2].begin(), roots[c2].end());
+            root_ptr[c + 1] = (int64_t)root_idx.size();
+        }
+    }
     const int world = e->cfg.world;
     const int64_t rpr = ((int64_t)N + world - 1) / world;
     int64_t row0 = std::min<int64_t>(N, e->cfg.rank * rpr), row1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
@@ -377,7 +484,35 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     int launches = 0;
     if (nloc > 0) {
         if (verbose) cudaEventRecord(tv0, e->stream);
-        if (hier) k2_visibility<true><<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
+        static const bool topdown_off = [] { const char* v = getenv("VRAD_K2_TOPDOWN"); return v && v[0] == '0'; }();
+        bool done = false;
+        if (hier && !topdown_off) {
+            std::vector<int32_t> lrows;
+            for (int64_t i = row0; i < row1; i++) if (P.h_child1[i] == -1) lrows.push_back((int32_t)(i - row0));
+            DevBuf<int32_t> d_rows, d_root_idx; DevBuf<int64_t> d_root_ptr; DevBuf<int> d_ovf;
+            auto drop = [&]() { d_rows.release(); d_root_idx.release(); d_root_ptr.release(); d_ovf.release(); };
+            if (d_rows.alloc(lrows.size() + 1) || d_root_idx.alloc(root_idx.size() + 1) || d_root_ptr.alloc(C + 1) || d_ovf.alloc(1)) {
+                drop(); cleanup(); set_error("out of device memory (top-down transfer build)"); return VRAD_E_NOMEM;
+            }
+            int ovf = 0;
+            cudaError_t ce = cudaSuccess;
+            if (!lrows.empty()) ce = cudaMemcpyAsync(d_rows.p, lrows.data(), lrows.size() * 4, cudaMemcpyHostToDevice, e->stream);
+            if (ce == cudaSuccess && !root_idx.empty()) ce = cudaMemcpyAsync(d_root_idx.p, root_idx.data(), root_idx.size() * 4, cudaMemcpyHostToDevice, e->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_root_ptr.p, root_ptr.data(), (C + 1) * 8, cudaMemcpyHostToDevice, e->stream);
+            if (ce == cudaSuccess) ce = cudaMemsetAsync(d_ovf.p, 0, sizeof(int), e->stream);
+            if (ce == cudaSuccess && !lrows.empty())
+                k2_visibility_topdown<<<std::min((int)lrows.size(), e->sm_count * 16), kTdThreads, 0, e->stream>>>(
+                    e->scene, pv, (int)lrows.size(), d_rows.p, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_root_ptr.p, d_root_idx.p,
+                    d_bit_ptr.p, d_bits.p, d_tree, P.child2.p, d_ovf.p);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(&ovf, d_ovf.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);     // host buffers above must outlive their copies
+            drop();
+            if (ce != cudaSuccess) { cleanup(); set_error("top-down transfer build failed: %s", cudaGetErrorString(ce)); return VRAD_E_CUDA; }
+            done = ovf == 0;
+            if (!done) K2_CHECK(cudaMemsetAsync(d_bits.p, 0, (size_t)(nwords + 1) * 4, e->stream));   // a list overflowed: per-candidate form
+        }
+        if (done) { }
+        else if (hier) k2_visibility<true><<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
                                                                                              pvs ? d_pvs.p : nullptr, C, d_tree);
         else k2_visibility<false><<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
                                                                                            pvs ? d_pvs.p : nullptr, C, nullptr);

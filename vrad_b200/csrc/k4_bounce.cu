@@ -472,6 +472,9 @@ int vrad_patches_set_hierarchy(vrad_env* e, int n, const int32_t* parent, const 
     P.n_interior = (int)ids.size();
     P.n_collect_long = n_long;
     P.h_child1.assign(child1, child1 + n);
+    P.h_parent.assign(parent, parent + n);
+    if (P.child2.alloc(n)) { set_error("out of device memory for the patch hierarchy"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemcpy(P.child2.p, child2, (size_t)n * 4, cudaMemcpyHostToDevice));
     P.leaf_rows_row0 = P.leaf_rows_row1 = -1;
     P.hier = true;
     e->transfers.ready = false;
