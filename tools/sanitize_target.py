@@ -26,3 +26,26 @@ L[2]["type"] = 5; L[2]["intensity"] = (10, 10, 10)
 env.direct_light(s.patch_origin[::9], s.patch_normal[::9], L)
 env.close()
 print("sanitize target done, nnz", nnz)
+# ---- widened rows: complete TestLineDoesHitSky, BSP point queries, K3 with trace flags, patch hierarchy ----
+from vrad_b200.environment import Environment
+sk = scenes.sky_room(n_boxes=8); m = sk.meta
+g = Environment(); g.add_triangles(sk.tri_ids, sk.tri_verts, sk.tri_flags); g.set_triangle_colors(m["tri_colors"])
+g.setup_acceleration_structure(); g.bsp_upload(m["bsp"]); g.process_sky_cameras(m["cams_origin"], m["cams_scale"])
+sa, sb = scenes.sky_segments(sk, 5003)
+for flags in (0, 1, 3, 7):
+    g.test_lines_sky(sa, sb, flags, 7)
+pts = np.ascontiguousarray(sa.T)
+g.point_leafnum(pts); g.cluster_from_point(pts)
+g.set_sky_dirs(dirs)
+g.leafs_trace_to_sky(m["probe_mins"], m["probe_maxs"])
+for flags in (1, 3):
+    g.set_light_trace_flags(flags)
+    g.direct_light(np.ascontiguousarray(pts[:999] * np.float32([1, 1, 0]) + np.float32([0, 0, 1])), np.tile(np.float32([0, 0, 1]), (999, 1)), L)
+g.close()
+hs = scenes.multi_room_hier(nx=2, ny=1, boxes_per_room=8); t = hs.meta["tree"]
+h = environment_from_scene(hs)
+h.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
+hn = h.build_transfers(hs.pvs)
+h.bounce(np.full((hs.n_patches, 3), 50.0, np.float32), 3)
+h.close()
+print("sanitize target (widened rows) done, hier nnz", hn)
