@@ -30,5 +30,46 @@ int main() {
     raytracer::Flt4x vis;
     trace::TestLineDoesHitSky(env, a, b, &vis);
     std::printf("vis %g %g %g %g\n", vis[0], vis[1], vis[2], vis[3]);
+
+    // second scenario: the hand-made sky scene of vrad_b200/scenes.py (mini_sky_scene): floor, TRACE_ID_SKY ceiling, a static prop
+    // (id 7) and three transparent panes with coverage colours, traced with textureShadows on through the FourVectors mirror
+    {
+        raytracer::Environment sky;
+        auto quad = [&](int32_t id, float x0, float x1, float y0, float y1, float z, uint16_t flags, float cov) {
+            sky.AddTriangleWithMaterial(id, {x0, y0, z}, {x1, y0, z}, {x1, y1, z}, {cov, 0, 0}, flags, 0);
+            sky.AddTriangleWithMaterial(id, {x0, y0, z}, {x1, y1, z}, {x0, y1, z}, {cov, 0, 0}, flags, 0);
+        };
+        quad(raytracer::TRACE_ID_OPAQUE, -512, 512, -512, 512, 0, 0, 1);
+        quad(raytracer::TRACE_ID_SKY, -512, 512, -512, 512, 512, 0, 1);
+        quad(raytracer::TRACE_ID_STATICPROP | 7, -60, 60, -60, 60, 300, 0, 1);
+        quad(raytracer::TRACE_ID_OPAQUE, 100, 200, -50, 50, 400, VRAD_TRI_TRANSPARENT, 0.25f);
+        quad(raytracer::TRACE_ID_OPAQUE, 100, 200, -50, 50, 420, VRAD_TRI_TRANSPARENT, 0.5f);
+        quad(raytracer::TRACE_ID_OPAQUE, 150, 200, -50, 50, 440, VRAD_TRI_TRANSPARENT, 0.5f);
+        sky.SetupAccelerationStructure();
+        struct Case { float a[3], b[3]; bool shadows; int prop; };
+        const Case cases[] = {{{0, 0, 100}, {0, 0, 5000}, false, -1}, {{0, 0, 100}, {0, 0, 5000}, false, 7}, {{120, 0, 100}, {120, 0, 5000}, false, -1},
+                              {{120, 0, 100}, {120, 0, 5000}, true, -1}, {{120, 0, 100}, {120, 0, 410}, true, -1}, {{170, 0, 100}, {170, 0, 5000}, true, -1},
+                              {{170, 0, 100}, {170, 0, 430}, true, -1}};
+        for (const Case& c : cases) {
+            raytracer::FourVectors s4, e4;
+            for (int l = 0; l < 4; l++) { s4.X[l] = c.a[0]; s4.Y[l] = c.a[1]; s4.Z[l] = c.a[2]; e4.X[l] = c.b[0]; e4.Y[l] = c.b[1]; e4.Z[l] = c.b[2]; }
+            trace::textureShadows = c.shadows;
+            raytracer::Flt4x fv;
+            trace::TestLineDoesHitSky(sky, s4, e4, &fv, true, c.prop);
+            std::printf("sky %.9g %.9g %.9g %.9g\n", fv[0], fv[1], fv[2], fv[3]);
+        }
+        raytracer::Vec3 col = sky.GetTriangleColor(6);
+        std::printf("colour %g\n", col[0]);
+    }
+    // third scenario (host only): MakePatchForFace + SubdividePatches on one 256 x 128 face, 16 units per luxel, chop 4
+    {
+        std::vector<float> pts = {0, 0, 0, 256, 0, 0, 256, 128, 0, 0, 128, 0};
+        vrad_face_patch f{};
+        f.first_point = 0; f.n_points = 4; f.normal[2] = 1.0f; f.plane_dist = 0.0f; f.lux_scale = 1.0f / 16.0f; f.chop = 4.0f;
+        patches::PatchTree t = patches::SubdividePatches({f}, pts);
+        int leaves = 0; float leaf_area = 0;
+        for (int i = 0; i < t.size(); i++) if (t.child1[i] == -1) { leaves++; leaf_area += t.area[i]; }
+        std::printf("patches %d leaves %d leaf_area %g child1 %d child2 %d\n", t.size(), leaves, leaf_area, t.child1[0], t.child2[0]);
+    }
     return 0;
 }

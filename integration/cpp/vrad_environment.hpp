@@ -11,8 +11,11 @@
 //     SetupAccelerationStructure      :119-138
 //     Trace4Rays                      :140-145   (FourRays raytracer/types/fourrays.go:8-11,
 //                                                 RayTracingResult raytracer/types/result.go:8-12)
-//     GetTriangle                     :422-424
-//   trace::TestLineDoesHitSky         raytracer/trace/testline.go:18-94
+//     GetTriangle / GetTriangleColor  :422-424, :430-432
+//   trace::TestLineDoesHitSky         raytracer/trace/testline.go:18-94   (textureShadows / noSkyRecurse :13-16)
+//   trace::PointLeafnum               raytracer/trace/pointleaf.go:8-10
+//   cameras::ProcessSkyCameras        rad/cameras/skycamera.go:10-49
+//   patches::SubdividePatches         rad/patches/subdivide.go:25-145 (+ MakePatchForFace, rad/patches/face.go:29-197)
 #pragma once
 #include <array>
 #include <cstdio>
@@ -49,11 +52,13 @@ public:
     void AddTriangle(int32_t id, const Vec3& v1, const Vec3& v2, const Vec3& v3, const Vec3& colour = {1, 0, 0}) {
         AddTriangleWithMaterial(id, v1, v2, v3, colour, 0, 0);
     }
-    void AddTriangleWithMaterial(int32_t id, const Vec3& v1, const Vec3& v2, const Vec3& v3, const Vec3&, uint16_t flags, int) {
+    void AddTriangleWithMaterial(int32_t id, const Vec3& v1, const Vec3& v2, const Vec3& v3, const Vec3& colour, uint16_t flags, int) {
         ids_.push_back(id);
         for (const Vec3* v : {&v1, &v2, &v3}) for (float c : *v) verts_.push_back(c);
         flags_.push_back(static_cast<uint8_t>(flags));
+        for (float c : colour) colours_.push_back(c);                  // TriangleColors (:61-63)
     }
+    Vec3 GetTriangleColor(int index) const { return {colours_[3 * index], colours_[3 * index + 1], colours_[3 * index + 2]}; }   // :430-432
     void AddQuad(int32_t id, const Vec3& v1, const Vec3& v2, const Vec3& v3, const Vec3& v4, const Vec3& colour = {1, 0, 0}) {
         AddTriangle(id, v1, v2, v3, colour);
         AddTriangle(id + 1, v1, v3, v4, colour);
@@ -69,6 +74,7 @@ public:
     void SetupAccelerationStructure() {
         fatal_on(vrad_env_add_triangles(h_, static_cast<int>(ids_.size()), ids_.data(), verts_.data(), flags_.data()), "vrad_env_add_triangles");
         fatal_on(vrad_env_build(h_), "vrad_env_build");
+        fatal_on(vrad_env_set_triangle_colors(h_, static_cast<int>(ids_.size()), colours_.data()), "vrad_env_set_triangle_colors");
     }
     void Trace4Rays(const FourRays& rays, const Flt4x& TMin, const Flt4x& TMax, RayTracingResult* resultOut, int skipId = -1) const {
         float o[12], d[12], n[12];
@@ -93,6 +99,7 @@ private:
     std::vector<int32_t> ids_;
     std::vector<float> verts_;
     std::vector<uint8_t> flags_;
+    std::vector<float> colours_;
 };
 
 } // namespace raytracer
@@ -124,3 +131,41 @@ inline int PointLeafnum(const raytracer::Environment& env, const raytracer::Vec3
 }
 
 } // namespace trace
+
+namespace cameras {
+
+// ProcessSkyCameras (rad/cameras/skycamera.go:10-49): origin and scale of every sky_camera entity; returns the cameras kept
+inline int ProcessSkyCameras(const raytracer::Environment& env, const std::vector<raytracer::Vec3>& origins, const std::vector<float>& scales) {
+    int kept = 0;
+    raytracer::fatal_on(vrad_sky_cameras_set(env.handle(), static_cast<int>(scales.size()), origins.empty() ? nullptr : origins[0].data(),
+                                             scales.data(), &kept), "vrad_sky_cameras_set");
+    return kept;
+}
+
+} // namespace cameras
+
+namespace patches {
+
+struct PatchTree {              // the fields of common/types/patch.go:9-64 this stage produces, one entry per patch
+    std::vector<float> origin, normal, plane_dist, area, mins, maxs, chop, wind_points;
+    std::vector<int32_t> parent, child1, child2, face, wind_first, wind_count;
+    int size() const { return static_cast<int>(area.size()); }
+};
+
+// MakePatchForFace for every face + SubdividePatches (rad/patches/face.go:29-197, subdivide.go:25-437)
+inline PatchTree SubdividePatches(const std::vector<vrad_face_patch>& faces, const std::vector<float>& points3, float minChop = 4.0f) {
+    int n = 0, np = 0;
+    vrad_patches_subdivide(static_cast<int>(faces.size()), faces.data(), points3.data(), minChop, 0, 0, &n, &np,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    PatchTree t;
+    t.origin.resize(3 * n); t.normal.resize(3 * n); t.mins.resize(3 * n); t.maxs.resize(3 * n); t.wind_points.resize(3 * np);
+    t.plane_dist.resize(n); t.area.resize(n); t.chop.resize(n);
+    t.parent.resize(n); t.child1.resize(n); t.child2.resize(n); t.face.resize(n); t.wind_first.resize(n); t.wind_count.resize(n);
+    raytracer::fatal_on(vrad_patches_subdivide(static_cast<int>(faces.size()), faces.data(), points3.data(), minChop, n, np, &n, &np,
+                                               t.origin.data(), t.normal.data(), t.plane_dist.data(), t.area.data(), t.mins.data(), t.maxs.data(),
+                                               t.chop.data(), t.parent.data(), t.child1.data(), t.child2.data(), t.face.data(),
+                                               t.wind_first.data(), t.wind_count.data(), t.wind_points.data()), "vrad_patches_subdivide");
+    return t;
+}
+
+} // namespace patches

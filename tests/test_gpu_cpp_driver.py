@@ -22,6 +22,13 @@ def test_cpp_driver_matches_oracle():
     ids, verts, flags = g.arrays()
     o = pyoracle.OracleEnv(); o.add_triangles(ids, verts, flags); o.build()
     dirs = np.array([[0.6, 0.0, -0.8], [-0.6, 0.48, -0.64], [0.0, 1.0, 0.0], [0.36, 0.48, 0.8]], np.float32)
+    # the sky scenario: hand-derived fractions (same scene and cases as scenes.MINI_SKY_CASES), all four lanes alike
+    sky = [[float(x) for x in l.split()[1:]] for l in out if l.startswith("sky ")]
+    assert sky == [[v] * 4 for v in (0.0, 1.0, 0.0, 0.25, 0.75, 0.0, 0.25)]
+    assert [l for l in out if l.startswith("colour")] == ["colour 0.25"]
+    # the host-only subdivision scenario: 256 x 128 face -> 8 x 4 leaves of 32 x 32, numbered depth first
+    assert [l for l in out if l.startswith("patches")] == ["patches 63 leaves 32 leaf_area 32768 child1 1 child2 2"]
+    out = [l for l in out if not l.startswith(("sky ", "colour", "patches"))]
     lines = [l.split() for l in out if not l.startswith("vis")]
     assert len(lines) == 16
     for p in range(4):
