@@ -203,3 +203,16 @@ def test_direct_light_with_complete_sky_test(sky_scene, sky_pair):
     from vrad_b200.environment import VradError
     with pytest.raises(VradError):
         g.set_light_trace_flags(4)                            # PACKET_LEAF has no meaning for light rays
+
+
+def test_empty_inputs(sky_scene, sky_pair):
+    g, _ = sky_pair
+    z = np.zeros((3, 0), np.float32)
+    assert g.test_lines_sky(z, z, 3, 7).shape == (0,)
+    assert g.point_leafnum(np.zeros((0, 3), np.float32)).shape == (0,)
+    assert g.cluster_from_point(np.zeros((0, 3), np.float32)).shape == (0,)
+    assert g.leafs_trace_to_sky(np.zeros((0, 3), np.int16), np.zeros((0, 3), np.int16)).shape == (0,)
+    assert g.process_sky_cameras(np.zeros((0, 3), np.float32), np.zeros(0, np.float32)) == 0      # no cameras: recursion becomes a no-op
+    a = np.array([[0.0], [0.0], [100.0]], np.float32); b = np.array([[0.0], [0.0], [5000.0]], np.float32)
+    assert g.test_lines_sky(a, b, 1, 7)[0] == g.test_lines_sky(a, b, 0, 7)[0]
+    assert g.process_sky_cameras(sky_scene.meta["cams_origin"], sky_scene.meta["cams_scale"]) == 2   # restore the module fixture
