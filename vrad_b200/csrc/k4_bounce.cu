@@ -116,12 +116,11 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
 // row is a single partial step and the kernel is a chain of dependent latencies (rowptr -> {col,w} -> er[col] ->
 // epilogue) with only 40 rows in flight per SM: measured 1.3 TB/s on the hierarchical S2 matrix.  Here 8 lanes
 // own a row (4 rows per warp, lanes on consecutive entries so the gathers of a row still coalesce), 4 entries in
-// flight per lane with the next {col,w} loads issued ahead of the gathers, and the register budget is capped at 40
-// so that 48 warps = 192 rows stay resident per SM (at 32 registers the loop spills and is slower: 76 vs 64 us).  `rows` (optional) lists the local rows to process -- with a
+// flight per lane and the register budget capped at 32 so that 64 warps = 256 rows stay resident per SM: 61.9 us per
+// bounce; with the one-step {col,w} prefetch of the long-row kernel the loop needs 40 registers (48 warps): 64.1 us,
+// and squeezed into 32 it spills: 76 us.  `rows` (optional) lists the local rows to process -- with a
 // hierarchy only the leaf patches gather, the interior rows are rewritten by k4_collect_parents.
-constexpr int kShortUnroll = 4;
-
-template <int kShortLanes, int kMinBlocks>
+template <int kShortLanes, int kMinBlocks, int kShortUnroll = 4, bool kPrefetch = true>
 __global__ void __launch_bounds__(kGatherBlock, kMinBlocks)
 k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const int64_t* __restrict__ rowptr,
                 const int2* __restrict__ tr, const float4* __restrict__ er, const float4* __restrict__ refl,
@@ -134,24 +133,39 @@ k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const
     const int64_t k0 = valid ? rowptr[row] : 0, k1 = valid ? rowptr[row + 1] : 0;
     const int2 zero = make_int2(0, 0);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    int2 cur[kShortUnroll], nxt[kShortUnroll];
     int64_t k = k0 + sub;
+    if (kPrefetch) {
+        int2 cur[kShortUnroll], nxt[kShortUnroll];
 #pragma unroll
-    for (int j = 0; j < kShortUnroll; j++) cur[j] = k + kShortLanes * j < k1 ? __ldcs(&tr[k + kShortLanes * j]) : zero;
-    for (; k < k1; k += kShortLanes * kShortUnroll) {
+        for (int j = 0; j < kShortUnroll; j++) cur[j] = k + kShortLanes * j < k1 ? __ldcs(&tr[k + kShortLanes * j]) : zero;
+        for (; k < k1; k += kShortLanes * kShortUnroll) {
 #pragma unroll
-        for (int j = 0; j < kShortUnroll; j++)
-            nxt[j] = k + kShortLanes * (kShortUnroll + j) < k1 ? __ldcs(&tr[k + kShortLanes * (kShortUnroll + j)]) : zero;
-        float4 x[kShortUnroll];
+            for (int j = 0; j < kShortUnroll; j++)
+                nxt[j] = k + kShortLanes * (kShortUnroll + j) < k1 ? __ldcs(&tr[k + kShortLanes * (kShortUnroll + j)]) : zero;
+            float4 x[kShortUnroll];
 #pragma unroll
-        for (int j = 0; j < kShortUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
+            for (int j = 0; j < kShortUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
 #pragma unroll
-        for (int j = 0; j < kShortUnroll; j++) {
-            const float w = __int_as_float(cur[j].y);
-            s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
+            for (int j = 0; j < kShortUnroll; j++) {
+                const float w = __int_as_float(cur[j].y);
+                s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
+            }
+#pragma unroll
+            for (int j = 0; j < kShortUnroll; j++) cur[j] = nxt[j];
         }
+    } else {
+        for (; k < k1; k += kShortLanes * kShortUnroll) {
+            int2 cur[kShortUnroll]; float4 x[kShortUnroll];
 #pragma unroll
-        for (int j = 0; j < kShortUnroll; j++) cur[j] = nxt[j];
+            for (int j = 0; j < kShortUnroll; j++) cur[j] = k + kShortLanes * j < k1 ? __ldcs(&tr[k + kShortLanes * j]) : zero;
+#pragma unroll
+            for (int j = 0; j < kShortUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
+#pragma unroll
+            for (int j = 0; j < kShortUnroll; j++) {
+                const float w = __int_as_float(cur[j].y);
+                s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
+            }
+        }
     }
 #pragma unroll
     for (int o = kShortLanes / 2; o > 0; o >>= 1) {
@@ -639,7 +653,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     }
     static const int force_short = [] { const char* v = getenv("VRAD_K4_SHORT"); return v ? atoi(v) : -1; }();
     const bool use_short = !p2p && (force_short >= 0 ? force_short != 0 : (T.nnz < (int64_t)400 * std::max(1, n_short)));
-    static const int short_cfg = [] { const char* v = getenv("VRAD_K4_SHORT_CFG"); return v ? atoi(v) : 86; }();   // lanes*10 + min blocks (experiments)
+    static const int short_cfg = [] { const char* v = getenv("VRAD_K4_SHORT_CFG"); return v ? atoi(v) : 884; }();   // experiments; see the switch below
     const int short_lanes = short_cfg / 10 == 16 ? 16 : (short_cfg / 10 == 4 ? 4 : 8);
     const int short_rpb = kGatherBlock / short_lanes;
     const int short_blocks = std::max(1, (n_short + short_rpb - 1) / short_rpb);
@@ -667,15 +681,13 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             k4_gather_multi<true><<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
                                                                    e->d_er[cur ^ 1].p, total_local, e->d_partials.p, d_peers, cur ^ 1, pending_wait ? world : 0);
         else if (use_short) {
-#define VRAD_SHORT(L, B) k4_gather_short<L, B><<<short_blocks, kGatherBlock, 0, e->stream>>>(n_short, d_rows, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, \
+#define VRAD_SHORT(L, B, ...) k4_gather_short<L, B, ##__VA_ARGS__><<<short_blocks, kGatherBlock, 0, e->stream>>>(n_short, d_rows, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, \
                                                                  e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p)
-            switch (short_cfg) {
-                case 88: VRAD_SHORT(8, 8); break;
-                case 168: VRAD_SHORT(16, 8); break;
-                case 166: VRAD_SHORT(16, 6); break;
-                case 48: VRAD_SHORT(4, 8); break;
-                case 46: VRAD_SHORT(4, 6); break;
-                default: VRAD_SHORT(8, 6); break;
+            switch (short_cfg) {                                  // lanes per row, min blocks/SM[, unroll, prefetch]: measured on the hierarchical S2 matrix
+                case 86: VRAD_SHORT(8, 6); break;                 // 64.1 us (40 registers, one-step prefetch)
+                case 168: VRAD_SHORT(16, 8); break;               // 77 us
+                case 48: VRAD_SHORT(4, 8); break;                 // 82 us
+                default: VRAD_SHORT(8, 8, 4, false); break;       // 61.9 us: no prefetch, 32 registers, 64 warps per SM
             }
 #undef VRAD_SHORT
         }
