@@ -689,3 +689,47 @@ def multi_room_hier(seed: int = 0x5EED0002, nx: int = 3, ny: int = 2, boxes_per_
     sc.meta["faces"] = faces
     sc.meta["face_points"] = points
     return sc
+
+
+def room_grid_bsp(nx=3, ny=2, room=512.0) -> Bsp:
+    """BSP lumps for the multi_room grid: axial splits at the room boundaries, one leaf (cluster = i*ny + j, area 1) per room."""
+    b = _BspBuilder()
+
+    def build(i0, i1, j0, j1):
+        if i1 - i0 == 1 and j1 - j0 == 1:
+            return b.leaf(i0 * ny + j0, 1, (int(i0 * room), int(j0 * room), 0), (int(i1 * room), int(j1 * room), int(room)))
+        if i1 - i0 >= j1 - j0:
+            m = (i0 + i1) // 2
+            n = b.node(b.plane((1, 0, 0), m * room, 0))
+            front, back = build(m, i1, j0, j1), build(i0, m, j0, j1)
+        else:
+            m = (j0 + j1) // 2
+            n = b.node(b.plane((0, 1, 0), m * room, 1))
+            front, back = build(i0, i1, m, j1), build(i0, i1, j0, m)
+        b.set_children(n, front, back)
+        return n
+    build(0, nx, 0, ny)
+    return b.finish(2)
+
+
+def compress_vis_rows(pvs) -> tuple[bytes, np.ndarray]:
+    """The visibility lump a BSP compiler would write for a [C, C] 0/1 matrix: each row bit-packed (cluster k = bit k&7 of
+    byte k>>3) and run-length coded (zero runs -> 0, count); returns (lump bytes, ByteOffset[C][2] with PAS = -1)."""
+    pvs = np.asarray(pvs)
+    lump = bytearray()
+    ofs = np.full((pvs.shape[0], 2), -1, np.int32)
+    for c in range(pvs.shape[0]):
+        row = np.packbits(pvs[c].astype(bool), bitorder="little").tobytes()
+        ofs[c, 0] = len(lump)
+        j = 0
+        while j < len(row):
+            lump.append(row[j])
+            if row[j]:
+                j += 1
+                continue
+            rep = 1
+            j += 1
+            while j < len(row) and row[j] == 0 and rep < 255:
+                rep += 1; j += 1
+            lump.append(rep)
+    return bytes(lump), ofs
