@@ -236,6 +236,33 @@ int  vrad_transfers_download(vrad_env*, int64_t* rowptr, int32_t* col, float* w)
 int  vrad_transfers_download_rows(vrad_env*, int64_t row_begin, int64_t row_end, int64_t* rowptr, int32_t* col, float* w, int64_t capacity);
 /* sky-ambient sample directions (vmath.Anorms, vmath/constants.go:15,21-184) */
 int  vrad_set_sky_dirs(vrad_env*, int n, const float* dirs3);
+/* ---- light records from entities and patches (host-only; the producers of vrad_direct_light's inputs) -------- */
+/* Entity.LightForString (common/types/entity.go:103-158): "r g b [scale]" (or one number, or two 4-tuples LDR HDR) ->
+ * linear RGB intensity.  VRAD_E_INVALID for negative components or an unknown form (rgb_out = 0). */
+int  vrad_light_for_string(const char* value, float rgb_out[3]);
+/* The key-values the light parsers read, already converted the way Entity.FloatForKey / VectorForKey / LightForKey do. */
+typedef struct {
+    int32_t classname;                 /* 0 "light", 1 "light_spot", 2 "light_environment" (lights.go:98-112) */
+    float   origin[3];
+    int32_t light_ok; float light[3];  /* LightForKey("_light") */
+    int32_t has_target; float target_origin[3];     /* "target" -> FindTargetEntity(...).origin (lights.go:184-194) */
+    float   angles[3], pitch, angle;   /* "angles" (pitch yaw roll), "pitch", "angle" (-1 up, -2 down) */
+    float   inner_cone, cone, exponent;             /* "_inner_cone", "_cone", "_exponent" (degrees) */
+    float   fifty_percent_distance, zero_percent_distance; int32_t hardfalloff;
+    float   constant_attn, linear_attn, quadratic_attn, distance;
+    int32_t ambient_ok; float ambient[3];           /* light_environment: LightForKey("_ambient") */
+} vrad_light_entity;                   /* 124 bytes */
+/* CreateDirectLights, entity part (rad/lightmap/lights.go:90-113): ParseLightPoint / ParseLightSpot / ParseLightEnvironment
+ * + ParseLightGeneric, SetLightFalloffParams, SetupLightNormalFromProps (:173-426) and the quadratic fit of
+ * vmath/quadratic/solver.go.  One record per light / light_spot, two (sky + sky ambient) for the first light_environment,
+ * in entity order.  *n_out = number of lights; VRAD_E_NOMEM when max_out is too small. */
+int  vrad_lights_from_entities(int n, const vrad_light_entity* ents, int max_out, vrad_light* out, int* n_out);
+/* CreateDirectLights, surface part (lights.go:49-82): one EMIT_SURFACE light per leaf patch whose average BaseLight
+ * reaches light_threshold (lightThreshold, :25); scale2 = Patch.Scale[2]; child1 may be NULL (all leaves). */
+int  vrad_lights_from_patches(int n, const float* origin3, const float* normal3, const float* base_light3, const float* area,
+                              const float* scale2, const float* base_area, const int32_t* child1, float light_threshold,
+                              int max_out, vrad_light* out, int* n_out);
+
 /* How K3's light rays are tested: 0 (default) = binary TestLine, sky lights with the sky-id rule only;
  * VRAD_TL_CAN_RECURSE = sky lights go through the 3D-skybox recursion (canRecurse = true, as
  * lightmap.CanLeafTraceToSky calls it, rad/lightmap/lightmap.go:444; needs vrad_bsp_upload + vrad_sky_cameras_set);

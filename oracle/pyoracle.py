@@ -285,6 +285,32 @@ def subdivide_patches(faces, points, min_chop=4.0):
     return out
 
 
+def light_for_string(value: str):
+    out = np.zeros(3, np.float32)
+    rc = lib().orc_light_for_string(C.c_char_p(value.encode()), _p(out))
+    return out, rc
+
+
+def lights_from_entities(ents, light_dtype):
+    ents = np.ascontiguousarray(ents)
+    assert ents.dtype.itemsize == 124
+    out = np.zeros(2 * max(1, ents.shape[0]), light_dtype)
+    n = lib().orc_lights_from_entities(C.c_int(ents.shape[0]), _p(ents), C.c_int(out.shape[0]), _p(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def lights_from_patches(origin, normal, base_light, area, scale2, base_area, child1, light_threshold, light_dtype):
+    origin = _f32(origin).reshape(-1, 3); normal = _f32(normal).reshape(-1, 3); base_light = _f32(base_light).reshape(-1, 3)
+    area = _f32(area); scale2 = _f32(scale2).reshape(-1, 2); base_area = _f32(base_area)
+    child1 = None if child1 is None else np.ascontiguousarray(child1, np.int32)
+    out = np.zeros(max(1, origin.shape[0]), light_dtype)
+    n = lib().orc_lights_from_patches(C.c_int(origin.shape[0]), _p(origin), _p(normal), _p(base_light), _p(area), _p(scale2), _p(base_area),
+                                      _p(child1), C.c_float(light_threshold), C.c_int(out.shape[0]), _p(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
 def decompress_vis(data: bytes, n_clusters: int):
     buf = np.frombuffer(bytes(data), np.uint8)
     out = np.zeros((n_clusters + 7) // 8, np.uint8)

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libvradcuda.so")
 
-SOURCES = ["vrad_env.cu", "k1_trace.cu", "k1_sky.cu", "k2_transfers.cu", "k3_direct.cu", "k4_bounce.cu", "comm.cu", "kd_builder.cpp", "patch_subdivide.cpp"]
+SOURCES = ["vrad_env.cu", "k1_trace.cu", "k1_sky.cu", "k2_transfers.cu", "k3_direct.cu", "k4_bounce.cu", "comm.cu", "kd_builder.cpp", "patch_subdivide.cpp", "light_setup.cpp"]
 
 
 def _nvcc() -> str:

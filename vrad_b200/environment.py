@@ -388,6 +388,37 @@ def subdivide_patches(faces, points, min_chop=4.0):
     return out
 
 
+def light_for_string(value: str):
+    """Entity.LightForString (common/types/entity.go:103-158): "r g b [scale]" -> linear RGB intensity (raises on a bad value)."""
+    out = np.zeros(3, np.float32)
+    check(_lib.load().vrad_light_for_string(C.c_char_p(value.encode()), ptr(out)))
+    return out
+
+
+def lights_from_entities(ents):
+    """CreateDirectLights, entity part (rad/lightmap/lights.go:90-426): lib.LIGHT_ENTITY_DTYPE records -> scenes.LIGHT_DTYPE records."""
+    from .scenes import LIGHT_DTYPE
+    ents = np.ascontiguousarray(ents, _lib.LIGHT_ENTITY_DTYPE)
+    out = np.zeros(2 * max(1, ents.shape[0]), LIGHT_DTYPE)
+    n = C.c_int()
+    check(_lib.load().vrad_lights_from_entities(C.c_int(ents.shape[0]), ptr(ents), C.c_int(out.shape[0]), ptr(out), C.byref(n)))
+    return out[: n.value].copy()
+
+
+def lights_from_patches(origin, normal, base_light, area, scale2, base_area, child1=None, light_threshold=0.1):
+    """CreateDirectLights, surface part (lights.go:49-82): EMIT_SURFACE lights of the emitting leaf patches."""
+    from .scenes import LIGHT_DTYPE
+    origin = _f32(origin).reshape(-1, 3); normal = _f32(normal).reshape(-1, 3); base_light = _f32(base_light).reshape(-1, 3)
+    area = _f32(area); scale2 = _f32(scale2).reshape(-1, 2); base_area = _f32(base_area)
+    child1 = None if child1 is None else np.ascontiguousarray(child1, np.int32)
+    n_p = origin.shape[0]
+    out = np.zeros(max(1, n_p), LIGHT_DTYPE)
+    n = C.c_int()
+    check(_lib.load().vrad_lights_from_patches(C.c_int(n_p), ptr(origin), ptr(normal), ptr(base_light), ptr(area), ptr(scale2), ptr(base_area),
+                                               ptr(child1), C.c_float(light_threshold), C.c_int(out.shape[0]), ptr(out), C.byref(n)))
+    return out[: n.value].copy()
+
+
 def decompress_vis(data: bytes, n_clusters: int):
     """lightmap.DecompressVis (rad/lightmap/vis.go:54-94): one PVS row -> ((n_clusters+7)//8 bytes, input bytes used)."""
     buf = np.frombuffer(bytes(data), np.uint8)

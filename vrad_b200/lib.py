@@ -27,6 +27,7 @@ SYMBOLS = [
     "vrad_env_set_triangle_colors", "vrad_bsp_upload", "vrad_point_leafnum", "vrad_cluster_from_point",
     "vrad_sky_cameras_set", "vrad_sky_cameras_get", "vrad_test_lines_sky", "vrad_leafs_trace_to_sky",
     "vrad_decompress_vis", "vrad_pvs_from_vis_lump", "vrad_patches_subdivide", "vrad_patches_set_hierarchy", "vrad_set_light_trace_flags",
+    "vrad_light_for_string", "vrad_lights_from_entities", "vrad_lights_from_patches",
 ]
 
 # == vrad_face_patch in include/vrad_cuda.h
@@ -34,6 +35,15 @@ FACE_PATCH_DTYPE = np.dtype([("first_point", "<i4"), ("n_points", "<i4"), ("norm
                              ("lux_scale", "<f4"), ("chop", "<f4"), ("sky", "u1"), ("no_subdivide", "u1"),
                              ("has_base_light", "u1"), ("pad", "u1")])
 assert FACE_PATCH_DTYPE.itemsize == 36
+
+# == vrad_light_entity in include/vrad_cuda.h
+LIGHT_ENTITY_DTYPE = np.dtype([("classname", "<i4"), ("origin", "<f4", 3), ("light_ok", "<i4"), ("light", "<f4", 3),
+                               ("has_target", "<i4"), ("target_origin", "<f4", 3), ("angles", "<f4", 3), ("pitch", "<f4"), ("angle", "<f4"),
+                               ("inner_cone", "<f4"), ("cone", "<f4"), ("exponent", "<f4"),
+                               ("fifty_percent_distance", "<f4"), ("zero_percent_distance", "<f4"), ("hardfalloff", "<i4"),
+                               ("constant_attn", "<f4"), ("linear_attn", "<f4"), ("quadratic_attn", "<f4"), ("distance", "<f4"),
+                               ("ambient_ok", "<i4"), ("ambient", "<f4", 3)])
+assert LIGHT_ENTITY_DTYPE.itemsize == 124
 
 
 class VradConfig(C.Structure):
