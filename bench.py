@@ -149,7 +149,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C1: S1 box room (996 tris), shadow-segment visibility; bounded sample per step", "segments_per_step": n_sample},
+        "config": {"workload": "C1: S1 box room (996 tris, 1325 kd nodes), 2^24 shadow segments per step per GPU via vrad_test_lines (K1)",
+                   "segments_per_step_per_gpu": N_SEGMENTS, "reference_arm_sample_per_step": n_sample,
+                   "note": "same workload as the graft arm; each reference step traces a bounded sample of it (cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gather": {"metric": "bounce_gather_iters_per_sec", "value": 20 / dt, "unit": "iters/s",
