@@ -120,3 +120,89 @@ def test_hierarchical_solution_tracks_the_flat_one():
     assert np.median(np.abs(th[leaf] - tf) / np.maximum(tf, 1e-3)) < 0.05
     # energy bound of a closed scene with reflectivity <= 0.7: bounced light below E * rho / (1 - rho)
     assert th[leaf].max() < 100.0 * 0.7 / 0.3
+
+
+def test_hierarchical_candidates_against_a_python_walk():
+    """The emitters of a receiver row, re-derived with an independent Python restatement of upstream's TestPatchToPatch walk
+    (descend while |origin_i - origin_j|^2 / 16 < area_j; roots of visible clusters; not the receiver's own face), the
+    MakeTransfer form factor in float64, and the oracle's own TestLine for the shadow segment."""
+    sc = scenes.multi_room_hier(nx=2, ny=1, boxes_per_room=6)
+    t = sc.meta["tree"]
+    o = pyoracle.env_from_scene(sc)
+    o.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
+    o.build_transfers(sc.pvs, threads=4)
+    rowptr, col, w = o.transfers()
+    O, Nn, A, D = sc.patch_origin.astype(np.float64), sc.patch_normal.astype(np.float64), sc.patch_area.astype(np.float64), sc.patch_plane_dist.astype(np.float64)
+    roots = np.nonzero(t["parent"] == -1)[0]
+
+    def walk(i, j, out):
+        if t["child1"][j] != -1:
+            d = sc.patch_origin[i] - sc.patch_origin[j]                       # fp32 like the oracle: the test sits on a threshold
+            d2 = np.float32(np.float32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+            if np.float32(d2 * np.float32(0.0625)) < sc.patch_area[j]:
+                walk(i, t["child1"][j], out); walk(i, t["child2"][j], out)
+                return
+        out.append(j)
+
+    leaves = np.nonzero(t["child1"] == -1)[0]
+    checked = 0
+    for i in leaves[:: max(1, len(leaves) // 25)]:
+        cand = []
+        for r in roots:
+            if sc.pvs[sc.patch_cluster[i], sc.patch_cluster[r]] and t["face"][r] != t["face"][i]:
+                walk(i, r, cand)
+        cand = sorted(c for c in cand if c != i)
+        # form factor (float64) and the plane test; pairs within 1e-6 of a threshold are left to the oracle
+        keep, fuzzy = [], set()
+        for j in cand:
+            side = O[j] @ Nn[i] - D[i] - 0.01
+            dl = O[i] - O[j]; ln = np.linalg.norm(dl)
+            if ln == 0:
+                continue
+            dl /= ln
+            scale = -(dl @ Nn[i]) * (dl @ Nn[j]) / (np.pi * ln * ln)
+            trans = A[j] * scale
+            if abs(side) < 1e-4 or abs(trans - 1e-7) < 1e-9 or abs(scale) < 1e-12:
+                fuzzy.add(j)
+            if side > 0 and scale > 0 and trans > 1e-7:
+                keep.append(j)
+        row = col[rowptr[i]:rowptr[i + 1]]
+        assert set(row) - fuzzy <= set(keep), i                                # nothing outside the walk's emitter set
+        missing = [j for j in keep if j not in set(row) and j not in fuzzy]
+        if missing:                                                             # every missing emitter must be shadowed
+            a = np.stack([(sc.patch_origin[min(i, j)] + sc.patch_normal[min(i, j)]) for j in missing]).T.astype(np.float32)
+            b = np.stack([(sc.patch_origin[max(i, j)] + sc.patch_normal[max(i, j)]) for j in missing]).T.astype(np.float32)
+            bits = o.test_lines(np.ascontiguousarray(a), np.ascontiguousarray(b), mode=2)      # brute-force tracer
+            vis = np.unpackbits(bits.view(np.uint8), bitorder="little")[: len(missing)]
+            assert not vis.any(), (i, missing)
+        checked += 1
+    assert checked >= 20
+
+
+def test_collect_light_hand_example():
+    """One bounce on a hand-made hierarchy: receiver plate R (a root with two leaf children of areas 3 and 1, facing +z)
+    under an emitter E (single leaf, facing -z).  Leaves gather area_E * cos*cos / (pi d^2); the root holds the
+    area-weighted mean of its children (vrad.cpp CollectLight, App. B.4)."""
+    o = pyoracle.OracleEnv()
+    o.add_triangles([scenes.TRACE_ID_OPAQUE], np.array([[9000, 9000, 9000, 9001, 9000, 9000, 9000, 9001, 9000]], np.float32)); o.build()
+    origin = np.array([[0, 0, 0], [-1, 0, 0], [3, 0, 0], [0, 0, 6]], np.float32)         # root, child1, child2, emitter (36/16 < area 4: the walk descends)
+    normal = np.array([[0, 0, 1], [0, 0, 1], [0, 0, 1], [0, 0, -1]], np.float32)
+    pdist = np.array([0, 0, 0, -6], np.float32)
+    area = np.array([4, 3, 1, 2], np.float32)
+    refl = np.full((4, 3), 0.5, np.float32)
+    o.patches_upload(origin, normal, pdist, area, refl, np.zeros(4, np.int32))
+    o.set_hierarchy([-1, 0, 0, -1], [1, -1, -1, -1], [2, -1, -1, -1], [0, 0, 0, 1])
+    assert o.build_transfers(None) == 4                                                  # E <- both children, each child <- E
+    rowptr, col, w = o.transfers()
+    assert list(np.diff(rowptr)) == [0, 1, 1, 2] and list(col) == [3, 3, 1, 2]          # the root gathers nothing; E sees the two LEAVES (near root)
+
+    def ff(i, j):
+        d = origin[i].astype(np.float64) - origin[j]; ln = np.linalg.norm(d); d /= ln
+        return area[j] * (-(d @ normal[i]) * (d @ normal[j])) / (np.pi * ln * ln)
+    assert np.allclose(w, [ff(1, 3), ff(2, 3), ff(3, 1), ff(3, 2)], rtol=1e-6)
+    emit = np.zeros((4, 3), np.float32); emit[3] = 100.0
+    tot, added, done = o.bounce(emit, 1)
+    t1, t2 = ff(1, 3) * 100 * 0.5, ff(2, 3) * 100 * 0.5
+    assert np.allclose(tot[1], t1, rtol=1e-6) and np.allclose(tot[2], t2, rtol=1e-6) and np.allclose(tot[3], 0)
+    assert np.allclose(tot[0], 0.75 * t1 + 0.25 * t2, rtol=1e-6)                         # CollectLight: area-weighted mean of the children
+    assert np.allclose(added, t1 + t2, rtol=1e-6)                                        # only leaves count towards `added`
