@@ -218,6 +218,16 @@ int  vrad_patches_upload(vrad_env*, int n, const float* origin3, const float* no
  * interior patches (area-weighted average of the two children).  Clusters given to vrad_patches_upload apply to every
  * patch; the PVS test uses the cluster of an emitter's face root. */
 int  vrad_patches_set_hierarchy(vrad_env*, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face);
+/* Bump-mapped patches (Patch.NeedsBumpMap, common/types/patch.go:23; BumpLights = NUM_BUMP_VECTS + 1 light values per patch,
+ * common/types/bumpLights.go:8-10, common/constants/constants.go:33).  vrad_bump_normals is upstream's GetBumpNormals for one
+ * face (texture S/T vectors, flat and phong normal -> the three bump-basis normals; host-only).  After vrad_patches_set_bump
+ * (flag + 9 floats per patch; normals[0] is the patch normal) vrad_bounce also accumulates TotalLight.Light[1..3] for the
+ * bump-mapped leaf patches -- each transfer projected on the bump normals as upstream's GatherLight does -- read back with
+ * vrad_bounce_bump_totals (9 floats per patch: Light[1], Light[2], Light[3]; zero for other patches).  Light[0] (the flat
+ * value, which is what a patch re-emits) is vrad_bounce's total_rgb_out.  Single GPU only for now. */
+int  vrad_bump_normals(const float s_vect[3], const float t_vect[3], const float flat_normal[3], const float phong_normal[3], float out9[9]);
+int  vrad_patches_set_bump(vrad_env*, int n, const uint8_t* needs_bump, const float* bump_normals9);
+int  vrad_bounce_bump_totals(vrad_env*, float* out9);
 /* patch-to-patch visibility + form factor -> transfer lists (common/types/transfer.go:3-6;
  * Patch.NumTransfers/Transfers patch.go:60-61).  pvs: n_clusters x n_clusters bytes (non-zero = visible)
  * or NULL (host memory).  Builds and keeps resident the CSR rows owned by this rank.  nnz_out = local nnz.

@@ -125,6 +125,12 @@ int  orc_env_set_light_trace_flags(orc_env*, int flags);
 /* K3: direct light per luxel; rgb_out 3 floats per luxel */
 int  orc_direct_light(orc_env*, int64_t n_luxels, const float* pos3, const float* normal3,
                       int n_lights, const orc_light* lights, float* rgb_out, int threads);
+/* upstream GetBumpNormals: the three bump-basis normals of a face (texture S/T vectors, flat and phong normal) */
+int  orc_bump_normals(const float s_vect[3], const float t_vect[3], const float flat_normal[3], const float phong_normal[3], float out9[9]);
+/* Patch.NeedsBumpMap (common/types/patch.go:23) + the bump normals; orc_bounce then also accumulates TotalLight.Light[1..3]
+ * (common/types/bumpLights.go:8-10) for the bump-mapped leaf patches, read back with orc_bounce_bump_totals (9 floats per patch) */
+int  orc_patches_set_bump(orc_env*, int n, const uint8_t* needs_bump, const float* bump_normals9);
+int  orc_bounce_bump_totals(orc_env*, float* out9);
 /* K4: bounce.  emit0_rgb: N*3.  total_rgb_out: N*3 (accumulated bounced light, excludes emit0). */
 int  orc_bounce(orc_env*, const float* emit0_rgb, int n_bounces, int early_out,
                 float* total_rgb_out, float added_last[3], int* bounces_done, int threads);

@@ -33,6 +33,11 @@ struct Patches {
     // Patch.Parent / Child1 / Child2 / FaceNumber (common/types/patch.go:33,49-51); empty = flat (leaf patches only)
     std::vector<int32_t> parent, child1, child2, face;
     bool hier() const { return !child1.empty(); }
+    // Patch.NeedsBumpMap (common/types/patch.go:23) and the three bump normals of such a patch (normals[1..3]; normals[0] is
+    // the flat patch normal); empty = no bump-mapped patches
+    std::vector<uint8_t> needs_bump;
+    std::vector<float> bump_normals;            // 9 per patch
+    std::vector<float> total_bump;              // TotalLight.Light[1..3] (common/types/bumpLights.go:8-10), 9 per patch, from the last bounce call
 };
 
 struct Counters { int64_t nodes = 0, tris = 0, leaves = 0; };

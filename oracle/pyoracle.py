@@ -242,6 +242,15 @@ class OracleEnv:
                                         C.c_int(lights.shape[0]), _p(lights), _p(out), C.c_int(threads)) == 0
         return out
 
+    def set_bump(self, needs_bump, bump_normals):
+        nb = np.ascontiguousarray(needs_bump, np.uint8); bn = _f32(bump_normals).reshape(-1, 9)
+        assert self._l.orc_patches_set_bump(self._h, C.c_int(nb.shape[0]), _p(nb), _p(bn)) == 0
+
+    def bump_totals(self):
+        out = np.empty((self.n_patches, 3, 3), np.float32)
+        assert self._l.orc_bounce_bump_totals(self._h, _p(out)) == 0
+        return out
+
     def bounce(self, emit0, n_bounces, early_out=False, threads=1):
         emit0 = _f32(emit0)
         total = np.empty_like(emit0); added = np.empty(3, np.float32); done = C.c_int()
@@ -282,6 +291,12 @@ def subdivide_patches(faces, points, min_chop=4.0):
     rc = L.orc_patches_subdivide(C.c_int(len(faces)), *[_p(a) for a in args_in], _p(points), C.c_float(min_chop),
                                  C.byref(n_), C.byref(m_), *[_p(out[k]) for k in keys])
     assert rc == 0
+    return out
+
+
+def bump_normals(s_vect, t_vect, flat_normal, phong_normal):
+    out = np.empty((3, 3), np.float32)
+    lib().orc_bump_normals(_p(_f32(s_vect)), _p(_f32(t_vect)), _p(_f32(flat_normal)), _p(_f32(phong_normal)), _p(out))
     return out
 
 

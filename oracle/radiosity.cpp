@@ -304,6 +304,66 @@ int orc_gather_rows(int64_t row0, int64_t row1, const int64_t* rowptr, const int
     return 0;
 }
 
+// Upstream GetBumpNormals (SURVEY App. B.4 mentions the 4-normal variant; constants NUM_BUMP_VECTS = 3,
+// common/constants/constants.go:33): a basis around the phong normal from the texture S vector, mirrored for left-handed
+// texture axes, then the fixed tangent-space basis g_localBumpBasis rotated into world space.
+int orc_bump_normals(const float s_vect[3], const float t_vect[3], const float flat_normal[3], const float phong_normal[3], float out9[9]) {
+    static const float OO_SQRT_2 = 0.70710676908493042f, OO_SQRT_3 = 0.57735025882720947f, OO_SQRT_6 = 0.40824821591377258f,
+                       OO_SQRT_2_OVER_3 = 0.81649661064147949f;
+    static const float basis[3][3] = {{OO_SQRT_2_OVER_3, 0.0f, OO_SQRT_3}, {-OO_SQRT_6, OO_SQRT_2, OO_SQRT_3}, {-OO_SQRT_6, -OO_SQRT_2, OO_SQRT_3}};
+    auto cross = [](const float* a, const float* b, float* o) {
+        o[0] = (a[1] * b[2]) - (a[2] * b[1]); o[1] = (a[2] * b[0]) - (a[0] * b[2]); o[2] = (a[0] * b[1]) - (a[1] * b[0]);
+    };
+    auto normalize = [](float* v) {
+        float len = sqrtf(dot3(v, v));
+        if (len != 0.0f) { float r = 1.0f / len; v[0] = v[0] * r; v[1] = v[1] * r; v[2] = v[2] * r; }
+    };
+    float tmp[3];
+    cross(s_vect, t_vect, tmp);
+    bool left_handed = dot3(flat_normal, tmp) < 0.0f;
+    float sb[3][3];
+    cross(phong_normal, s_vect, sb[1]); normalize(sb[1]);
+    cross(sb[1], phong_normal, sb[0]); normalize(sb[0]);
+    for (int k = 0; k < 3; k++) sb[2][k] = phong_normal[k];
+    if (left_handed) for (int k = 0; k < 3; k++) sb[1][k] = -sb[1][k];
+    for (int i = 0; i < 3; i++)                                   // VectorIRotate: in.x * row0 + in.y * row1 + in.z * row2
+        for (int k = 0; k < 3; k++) out9[3 * i + k] = ((basis[i][0] * sb[0][k]) + (basis[i][1] * sb[1][k])) + (basis[i][2] * sb[2][k]);
+    return 0;
+}
+
+int orc_patches_set_bump(orc_env* e, int n, const uint8_t* needs_bump, const float* bump_normals9) {
+    if (!e || n != e->patches.n) return -1;
+    e->patches.needs_bump.assign(needs_bump, needs_bump + n);
+    e->patches.bump_normals.assign(bump_normals9, bump_normals9 + 9 * (size_t)n);
+    return 0;
+}
+
+int orc_bounce_bump_totals(orc_env* e, float* out9) {
+    if (!e || e->patches.total_bump.empty()) return -1;
+    memcpy(out9, e->patches.total_bump.data(), e->patches.total_bump.size() * sizeof(float));
+    return 0;
+}
+
+// upstream GatherLight, bump-mapped branch, for one patch: the three bump sums (the flat sum stays with orc_gather_rows)
+static void gather_bump_row(const Patches& P, int i, const int64_t* rowptr, const int32_t* col, const float* w, const float* emit, float sum9[9]) {
+    for (int k = 0; k < 9; k++) sum9[k] = 0.0f;
+    const float* oi = &P.origin[3 * i]; const float* ni = &P.normal[3 * i];
+    for (int64_t k = rowptr[i]; k < rowptr[i + 1]; k++) {
+        int32_t j = col[k];
+        float delta[3] = {P.origin[3 * j] - oi[0], P.origin[3 * j + 1] - oi[1], P.origin[3 * j + 2] - oi[2]};   // towards the emitter
+        float len = sqrtf(dot3(delta, delta));
+        if (len != 0.0f) { float r = 1.0f / len; delta[0] = delta[0] * r; delta[1] = delta[1] * r; delta[2] = delta[2] * r; }
+        float scale = 1.0f / dot3(delta, ni);                       // "remove normal already factored into transfer steradian"
+        float ws = w[k] * scale;
+        float v[3] = {(emit[3 * j] * P.refl[3 * j]) * ws, (emit[3 * j + 1] * P.refl[3 * j + 1]) * ws, (emit[3 * j + 2] * P.refl[3 * j + 2]) * ws};
+        for (int b = 0; b < 3; b++) {
+            float d = dot3(delta, &P.bump_normals[9 * (size_t)i + 3 * b]);
+            if (d <= 0.0f) continue;
+            sum9[3 * b] = sum9[3 * b] + (v[0] * d); sum9[3 * b + 1] = sum9[3 * b + 1] + (v[1] * d); sum9[3 * b + 2] = sum9[3 * b + 2] + (v[2] * d);
+        }
+    }
+}
+
 int orc_bounce(orc_env* e, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out,
                float added_last[3], int* bounces_done, int threads) {
     if (!e || e->rowptr.empty()) return -1;
@@ -312,8 +372,19 @@ int orc_bounce(orc_env* e, const float* emit0_rgb, int n_bounces, int early_out,
     std::vector<float> emit(emit0_rgb, emit0_rgb + 3 * (size_t)N), add(3 * (size_t)N), total(3 * (size_t)N, 0.0f);
     float added[3] = {0, 0, 0};
     int done = 0;
+    const bool bump = !P.needs_bump.empty();
+    Patches& PW = e->patches;
+    if (bump) PW.total_bump.assign(9 * (size_t)N, 0.0f); else PW.total_bump.clear();
     for (int b = 0; b < n_bounces; b++) {
         orc_gather_rows(0, N, e->rowptr.data(), e->col.data(), e->w.data(), emit.data(), P.refl.data(), add.data(), threads);
+        if (bump) {                                        // GatherLight, bump branch; CollectLight adds it to TotalLight.Light[1..3] of leaf patches
+            for (int i = 0; i < N; i++) {
+                if (!P.needs_bump[i] || (P.flags[i] & 1) || (P.hier() && P.child1[i] != -1)) continue;
+                float s9[9];
+                gather_bump_row(P, i, e->rowptr.data(), e->col.data(), e->w.data(), emit.data(), s9);
+                for (int k = 0; k < 9; k++) PW.total_bump[9 * (size_t)i + k] = PW.total_bump[9 * (size_t)i + k] + s9[k];
+            }
+        }
         // CollectLight (vrad.cpp, App. B.4).  Flat patch sets: forward order (every patch is a leaf).  With a hierarchy:
         // reverse index order so that children come before their parents; an interior patch takes the
         // area-weighted average of its two children for both totallight and emitlight.

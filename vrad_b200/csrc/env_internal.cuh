@@ -59,6 +59,15 @@ struct PatchesDev {
     DevBuf<int64_t> collect_ptr;                // n_interior + 1 offsets into collect_ent
     DevBuf<int2>    collect_ent;                // {leaf patch, weight bits}
     std::vector<int32_t> h_child1, h_parent;
+    // bump-mapped patches (Patch.NeedsBumpMap, common/types/patch.go:23): flags, normals[1..3] as three float4 per patch, the
+    // local rows that gather bump sums, and TotalLight.Light[1..3] (common/types/bumpLights.go:8-10) indexed by global patch
+    bool bump = false;
+    std::vector<uint8_t> h_needs_bump;
+    DevBuf<float4> bump_normals;                // [N][3]
+    DevBuf<float4> total_bump[3];
+    DevBuf<int32_t> bump_rows;
+    int n_bump_rows = 0;
+    int64_t bump_rows_row0 = -1, bump_rows_row1 = -1;
     DevBuf<int32_t> child2;
     DevBuf<int32_t> leaf_rows;                  // local row numbers of the leaf patches in [leaf_rows_row0, leaf_rows_row1)
     int n_leaf_rows = 0;

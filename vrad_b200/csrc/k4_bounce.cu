@@ -112,6 +112,57 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
     }
 }
 
+// GatherLight, bump-mapped branch (upstream vrad.cpp; the reference carries the types: Patch.NeedsBumpMap
+// common/types/patch.go:23, BumpLights common/types/bumpLights.go:8-10, NUM_BUMP_VECTS common/constants/constants.go:33).
+// For a bump-mapped patch the light of every transfer is also projected on the three bump-basis normals:
+//   delta = normalize(origin_j - origin_i); v = emit_j * refl_j * transfer / (delta . n_i)   ("remove normal already factored
+//   into transfer steradian"); sum_b += v * (delta . normal_b) for delta . normal_b > 0.
+// The flat sum (Light[0], which is what the patch re-emits) stays with the gather kernels above; this kernel runs over the
+// bump-mapped leaf rows only, one warp per row, and re-reads their {col,w} entries plus the emitters' origins.
+__global__ void __launch_bounds__(256)
+k4_gather_bump(int n_rows, const int32_t* __restrict__ rows, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
+               const float4* __restrict__ er, const float4* __restrict__ origin_area, const float4* __restrict__ normal_dist,
+               const float4* __restrict__ bump_normals, float4* __restrict__ tb0, float4* __restrict__ tb1, float4* __restrict__ tb2) {
+    const int lane = threadIdx.x & 31;
+    const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_rows) return;
+    const int row = __ldg(&rows[r]);
+    const int64_t i = row0 + row;
+    const float4 oi = __ldg(&origin_area[i]), ni = __ldg(&normal_dist[i]);
+    const float4 n1 = __ldg(&bump_normals[3 * i]), n2 = __ldg(&bump_normals[3 * i + 1]), n3 = __ldg(&bump_normals[3 * i + 2]);
+    float s[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) s[k] = 0.f;
+    for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) {
+        const int2 en = __ldcs(&tr[k]);
+        const float w = __int_as_float(en.y);
+        if (w == 0.0f) continue;                                   // row padding
+        const float4 oj = __ldg(&origin_area[en.x]);
+        const float4 v = __ldg(&er[en.x]);
+        float dx = oj.x - oi.x, dy = oj.y - oi.y, dz = oj.z - oi.z;
+        const float len = sqrtf(((dx * dx) + (dy * dy)) + (dz * dz));
+        if (len != 0.0f) { const float rl = 1.0f / len; dx = dx * rl; dy = dy * rl; dz = dz * rl; }
+        const float ws = w * (1.0f / (((dx * ni.x) + (dy * ni.y)) + (dz * ni.z)));
+        const float vx = v.x * ws, vy = v.y * ws, vz = v.z * ws;
+        const float d1 = ((dx * n1.x) + (dy * n1.y)) + (dz * n1.z);
+        const float d2 = ((dx * n2.x) + (dy * n2.y)) + (dz * n2.z);
+        const float d3 = ((dx * n3.x) + (dy * n3.y)) + (dz * n3.z);
+        if (d1 > 0.0f) { s[0] += vx * d1; s[1] += vy * d1; s[2] += vz * d1; }
+        if (d2 > 0.0f) { s[3] += vx * d2; s[4] += vy * d2; s[5] += vz * d2; }
+        if (d3 > 0.0f) { s[6] += vx * d3; s[7] += vy * d3; s[8] += vz * d3; }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    }
+    if (lane == 0) {                                               // CollectLight: TotalLight.Light[b] += addlight.light[b] (leaf patches)
+        float4 t = tb0[i]; t.x += s[0]; t.y += s[1]; t.z += s[2]; tb0[i] = t;
+        t = tb1[i]; t.x += s[3]; t.y += s[4]; t.z += s[5]; tb1[i] = t;
+        t = tb2[i]; t.x += s[6]; t.y += s[7]; t.z += s[8]; tb2[i] = t;
+    }
+}
+
 // Short-row form (patch hierarchy: rows average ~150 transfers instead of ~1000+).  With one warp per row such a
 // row is a single partial step and the kernel is a chain of dependent latencies (rowptr -> {col,w} -> er[col] ->
 // epilogue) with only 40 rows in flight per SM: measured 1.3 TB/s on the hierarchical S2 matrix.  Here 8 lanes
@@ -406,6 +457,7 @@ int vrad_patches_upload(vrad_env* e, int n, const float* origin3, const float* n
     P.h_cluster.assign(n, 0); P.h_flags.assign(n, 0);
     P.h_area.assign(area, area + n); P.h_refl.assign(reflectivity3, reflectivity3 + 3 * (size_t)n);
     P.hier = false; P.n_interior = 0; P.h_root_cluster.clear();
+    P.bump = false; P.h_needs_bump.clear();
     for (int i = 0; i < n; i++) {
         oa[i] = make_float4(origin3[3 * i], origin3[3 * i + 1], origin3[3 * i + 2], area[i]);
         nd[i] = make_float4(normal3[3 * i], normal3[3 * i + 1], normal3[3 * i + 2], plane_dist[i]);
@@ -492,6 +544,60 @@ int vrad_patches_set_hierarchy(vrad_env* e, int n, const int32_t* parent, const 
     P.leaf_rows_row0 = P.leaf_rows_row1 = -1;
     P.hier = true;
     e->transfers.ready = false;
+    return VRAD_OK;
+}
+
+// upstream GetBumpNormals (host-only): basis around the phong normal from the texture S vector, mirrored for left-handed
+// texture axes, then the fixed tangent-space bump basis rotated into world space
+int vrad_bump_normals(const float s_vect[3], const float t_vect[3], const float flat_normal[3], const float phong_normal[3], float out9[9]) {
+    if (!s_vect || !t_vect || !flat_normal || !phong_normal || !out9) { set_error("vrad_bump_normals: bad arguments"); return VRAD_E_INVALID; }
+    const float kBasis[3][3] = {{0.81649661064147949f, 0.0f, 0.57735025882720947f},
+                                {-0.40824821591377258f, 0.70710676908493042f, 0.57735025882720947f},
+                                {-0.40824821591377258f, -0.70710676908493042f, 0.57735025882720947f}};
+    struct V { float x, y, z; };
+    auto cross = [](V a, V b) { return V{(a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x)}; };
+    auto dot = [](V a, V b) { return ((a.x * b.x) + (a.y * b.y)) + (a.z * b.z); };
+    auto unit = [&](V a) { const float len = sqrtf(dot(a, a)); if (len != 0.0f) { const float r = 1.0f / len; a = V{a.x * r, a.y * r, a.z * r}; } return a; };
+    const V sv{s_vect[0], s_vect[1], s_vect[2]}, tv{t_vect[0], t_vect[1], t_vect[2]};
+    const V flat{flat_normal[0], flat_normal[1], flat_normal[2]}, phong{phong_normal[0], phong_normal[1], phong_normal[2]};
+    const bool left_handed = dot(flat, cross(sv, tv)) < 0.0f;
+    V by = unit(cross(phong, sv));
+    const V bx = unit(cross(by, phong));
+    if (left_handed) by = V{-by.x, -by.y, -by.z};
+    for (int b = 0; b < 3; b++) {
+        out9[3 * b] = ((kBasis[b][0] * bx.x) + (kBasis[b][1] * by.x)) + (kBasis[b][2] * phong.x);
+        out9[3 * b + 1] = ((kBasis[b][0] * bx.y) + (kBasis[b][1] * by.y)) + (kBasis[b][2] * phong.y);
+        out9[3 * b + 2] = ((kBasis[b][0] * bx.z) + (kBasis[b][1] * by.z)) + (kBasis[b][2] * phong.z);
+    }
+    return VRAD_OK;
+}
+
+int vrad_patches_set_bump(vrad_env* e, int n, const uint8_t* needs_bump, const float* bump_normals9) {
+    if (!e || !needs_bump || !bump_normals9) { set_error("vrad_patches_set_bump: bad arguments"); return VRAD_E_INVALID; }
+    PatchesDev& P = e->patches;
+    if (P.n == 0 || n != P.n) { set_error("vrad_patches_set_bump: %d entries for %d uploaded patches", n, P.n); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    std::vector<float4> bn(3 * (size_t)n);
+    for (size_t i = 0; i < 3 * (size_t)n; i++) bn[i] = make_float4(bump_normals9[3 * i], bump_normals9[3 * i + 1], bump_normals9[3 * i + 2], 0.f);
+    if (P.bump_normals.alloc(3 * (size_t)n)) { set_error("out of device memory for bump normals"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemcpy(P.bump_normals.p, bn.data(), bn.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    P.h_needs_bump.assign(needs_bump, needs_bump + n);
+    P.bump_rows_row0 = P.bump_rows_row1 = -1;
+    P.bump = true;
+    return VRAD_OK;
+}
+
+int vrad_bounce_bump_totals(vrad_env* e, float* out9) {
+    if (!e || !out9) { set_error("vrad_bounce_bump_totals: bad arguments"); return VRAD_E_INVALID; }
+    PatchesDev& P = e->patches;
+    if (!P.bump || P.total_bump[0].n < (size_t)P.n) { set_error("vrad_bounce_bump_totals: no bump-mapped bounce has run (vrad_patches_set_bump, vrad_bounce)"); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    std::vector<float4> t((size_t)P.n);
+    for (int b = 0; b < 3; b++) {
+        VRAD_CUDA_CHECK(cudaMemcpy(t.data(), P.total_bump[b].p, (size_t)P.n * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < P.n; i++) { out9[9 * (size_t)i + 3 * b] = t[i].x; out9[9 * (size_t)i + 3 * b + 1] = t[i].y; out9[9 * (size_t)i + 3 * b + 2] = t[i].z; }
+    }
     return VRAD_OK;
 }
 
@@ -651,6 +757,25 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         }
         n_short = PD.n_leaf_rows; d_rows = PD.leaf_rows.p;
     }
+    // bump-mapped leaf rows of this rank (TotalLight.Light[1..3] accumulate next to the flat gather)
+    const bool bump = PD.bump;
+    if (bump) {
+        if (world > 1) { set_error("vrad_bounce: bump-mapped patches are not supported with world > 1 yet"); return VRAD_E_UNSUPPORTED; }
+        PatchesDev& PM = e->patches;
+        if (PM.bump_rows_row0 != T.row0 || PM.bump_rows_row1 != T.row1) {
+            std::vector<int32_t> br;
+            for (int64_t i = T.row0; i < T.row1; i++)
+                if (PM.h_needs_bump[i] && !(PM.h_flags[i] & 1) && (!PM.hier || PM.h_child1[i] == -1)) br.push_back((int32_t)(i - T.row0));
+            if (PM.bump_rows.alloc(br.size() + 1)) { set_error("out of device memory (bump row list)"); return VRAD_E_NOMEM; }
+            if (!br.empty()) VRAD_CUDA_CHECK(cudaMemcpyAsync(PM.bump_rows.p, br.data(), br.size() * 4, cudaMemcpyHostToDevice, e->stream));
+            VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            PM.n_bump_rows = (int)br.size(); PM.bump_rows_row0 = T.row0; PM.bump_rows_row1 = T.row1;
+        }
+        for (int b = 0; b < 3; b++) {
+            if (PM.total_bump[b].alloc((size_t)n_pad)) { set_error("out of device memory for bump totals"); return VRAD_E_NOMEM; }
+            VRAD_CUDA_CHECK(cudaMemsetAsync(PM.total_bump[b].p, 0, (size_t)n_pad * 16, e->stream));
+        }
+    }
     static const int force_short = [] { const char* v = getenv("VRAD_K4_SHORT"); return v ? atoi(v) : -1; }();
     const bool use_short = !p2p && (force_short >= 0 ? force_short != 0 : (T.nnz < (int64_t)400 * std::max(1, n_short)));
     static const int short_cfg = [] { const char* v = getenv("VRAD_K4_SHORT_CFG"); return v ? atoi(v) : 884; }();   // experiments; see the switch below
@@ -696,6 +821,12 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
                                                              e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
         launches++;
         pending_wait = false;
+        if (bump && PD.n_bump_rows > 0) {       // same emitters as the gather above (er[cur]), bump-mapped rows only
+            k4_gather_bump<<<(PD.n_bump_rows * 32 + 255) / 256, 256, 0, e->stream>>>(PD.n_bump_rows, PD.bump_rows.p, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p,
+                                                                                  PD.origin_area.p, PD.normal_dist.p, PD.bump_normals.p,
+                                                                                  PD.total_bump[0].p, PD.total_bump[1].p, PD.total_bump[2].p);
+            launches++;
+        }
         if (probe) cudaEventRecord(pe[n_probe][1], e->stream);
         if (p2p) { k4_peer_signal<<<1, 32, 0, e->stream>>>(d_peers); launches++; pending_wait = true; }
         else if (world > 1 && (rc = comm_allgather_rows(e, e->d_er[cur ^ 1].p, bounds))) return rc;

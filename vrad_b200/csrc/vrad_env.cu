@@ -173,6 +173,7 @@ void vrad_env_destroy(vrad_env* e) {
     for (auto& s : e->scratch) s.release();
     e->patches.origin_area.release(); e->patches.normal_dist.release(); e->patches.refl.release(); e->patches.cluster.release();
     e->patches.tree.release(); e->patches.collect_ids.release(); e->patches.collect_ptr.release(); e->patches.collect_ent.release(); e->patches.leaf_rows.release(); e->patches.child2.release();
+    e->patches.bump_normals.release(); e->patches.bump_rows.release(); for (int b = 0; b < 3; b++) e->patches.total_bump[b].release();
     e->transfers.rowptr.release(); e->transfers.rowlen.release(); e->transfers.tr.release();
     e->d_sky_dirs.release(); e->d_er[0].release(); e->d_er[1].release(); e->d_total.release(); e->d_partials.release();
     for (int s = 0; s < 2; s++) {

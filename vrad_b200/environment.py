@@ -261,6 +261,16 @@ class Environment:
         parent, child1, child2, face = i32(parent), i32(child1), i32(child2), i32(face)
         check(self._l.vrad_patches_set_hierarchy(self._h, C.c_int(parent.shape[0]), ptr(parent), ptr(child1), ptr(child2), ptr(face)))
 
+    def set_bump(self, needs_bump, bump_normals):
+        """Patch.NeedsBumpMap + the three bump normals per patch ([N, 3, 3]); bounce() then accumulates TotalLight.Light[1..3]."""
+        nb = np.ascontiguousarray(needs_bump, np.uint8); bn = np.ascontiguousarray(bump_normals, np.float32).reshape(-1, 9)
+        check(self._l.vrad_patches_set_bump(self._h, C.c_int(nb.shape[0]), ptr(nb), ptr(bn)))
+
+    def bump_totals(self):
+        out = np.empty((self.n_patches, 3, 3), np.float32)
+        check(self._l.vrad_bounce_bump_totals(self._h, ptr(out)))
+        return out
+
     def build_transfers(self, pvs=None):
         nnz = C.c_int64(); nc = 0
         if pvs is not None:
@@ -385,6 +395,13 @@ def subdivide_patches(faces, points, min_chop=4.0):
                child2=i1(), face=i1(), wind_first=i1(), wind_count=i1(), wind_points=np.empty((m, 3), np.float32))
     check(L.vrad_patches_subdivide(C.c_int(faces.shape[0]), ptr(faces), ptr(points), C.c_float(min_chop), C.c_int(n), C.c_int(m),
                                    C.byref(np_), C.byref(npt), *[ptr(out[k]) for k in PATCH_TREE_FIELDS]))
+    return out
+
+
+def bump_normals(s_vect, t_vect, flat_normal, phong_normal):
+    """upstream GetBumpNormals for one face -> [3, 3] bump-basis normals (host-only)."""
+    out = np.empty((3, 3), np.float32)
+    check(_lib.load().vrad_bump_normals(ptr(_f32(s_vect)), ptr(_f32(t_vect)), ptr(_f32(flat_normal)), ptr(_f32(phong_normal)), ptr(out)))
     return out
 
 
