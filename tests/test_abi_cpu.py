@@ -10,8 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "vrad_cuda.h")).read()
+def _declared_symbols(header="vrad_cuda.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(vrad_[a-z0-9_]+)\s*\(", src)))
 
@@ -25,6 +25,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, sym), f"libvradcuda.so does not export {sym}"
     assert sorted(lib.SYMBOLS) == declared
     assert b"sm_100a" in handle.vrad_version()
+    # the BSP side of the boundary (include/vrad_bsp.h)
+    from vrad_b200 import bspfile
+    declared_bsp = _declared_symbols("vrad_bsp.h")
+    assert len(declared_bsp) >= 20 and sorted(bspfile.SYMBOLS) == declared_bsp
+    for sym in declared_bsp:
+        assert hasattr(handle, sym), f"libvradcuda.so does not export {sym}"
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["vrad_bsp.h", "vrad_cuda.h"]
 
 
 def test_struct_sizes_match_header():

@@ -1,0 +1,485 @@
+"""CPU tests of the BSP side of the path (include/vrad_bsp.h): the .bsp container, lumps -> triangles / face patches /
+extents / tree tables / sky vis / smoothing normals / luxels, and the lighting lump write-back.  The product (host code in
+libvradcuda.so, called through the C-ABI) is compared bit for bit with the oracle's function-by-function restatement
+(oracle/bspside.py) on a synthetic BSP v20 map, and with hand-derived answers."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import bspside as O
+from vrad_b200 import bspfile as B
+from vrad_b200.lib import VradError
+
+
+@pytest.fixture(scope="module")
+def smap():
+    return B.synthetic_map(3, 2, boxes_per_room=5, sky_rooms=(1,), bump_rooms=(0,))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _cube_map(side=64.0, contents=B.CONTENTS_SOLID, sky_side=None):
+    """One leaf, one node, one axis-aligned cube brush [0, side]^3 (planes stored in +/- pairs)."""
+    planes, sides = [], []
+    for axis in range(3):
+        n = [0.0, 0.0, 0.0]; n[axis] = 1.0
+        planes.append((n, side, axis)); planes.append(([-c for c in n], -side, axis))        # +axis at `side`
+        planes.append((n, 0.0, axis)); planes.append(([-c for c in n], -0.0, axis))          # pair for the face at 0
+    P = np.zeros(len(planes), B.DPLANE)
+    for k, (n, d, t) in enumerate(planes):
+        P[k] = (n, d, t)
+    tex = np.zeros(2, B.TEXINFO); tex[1]["flags"] = B.SURF_SKY
+    for axis in range(3):
+        sides.append((4 * axis, 0, 0, 0))          # +axis side, outward normal +axis at dist side
+        sides.append((4 * axis + 3, 0, 0, 0))      # -axis side, outward normal -axis at dist 0
+    S = np.zeros(6, B.DBRUSHSIDE)
+    for k, t in enumerate(sides):
+        S[k] = t
+    if sky_side is not None:
+        S[sky_side]["texinfo"] = 1
+    br = np.zeros(1, B.DBRUSH); br[0] = (0, 6, contents)
+    leafs = np.zeros(2, B.DLEAF); leafs[1]["numleafbrushes"] = 1; leafs[0]["cluster"] = -1
+    nodes = np.zeros(1, B.DNODE); nodes[0]["planenum"] = 0; nodes[0]["children"] = (-1 - 1, -1 - 0)
+    models = np.zeros(1, B.DMODEL)
+    return B.Lumps(planes=P, texinfo=tex, texdata=np.zeros(1, B.DTEXDATA), brushsides=S, brushes=br, leafs=leafs, nodes=nodes, models=models,
+                   leafbrushes=np.zeros(1, "<u2"))
+
+
+# ---- container ---------------------------------------------------------------------------------------------------------
+def test_bspfile_round_trip(smap, tmp_path):
+    L, meta = smap
+    path = str(tmp_path / "m.bsp")
+    B.write_bsp(path, L, meta)
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"VBSP" and struct.unpack_from("<i", raw, 4)[0] == 20
+    for i in range(64):                                           # directory: aligned, in bounds, leaf lump version 1
+        ofs, ln, ver, _ = struct.unpack_from("<iii4s", raw, 8 + 16 * i)
+        assert ofs % 4 == 0 and ofs + ln <= len(raw) and (ln == 0 or ofs >= 1036)
+        assert ver == (1 if i == B.LUMP["LEAFS"] else 0)
+    f = B.BspFile(path)
+    L2 = f.lumps()
+    for k in L.a:
+        assert np.array_equal(L.a[k], L2.a[k]), k
+    assert L2.visdata.tobytes() == L.visdata.tobytes() and L2.n_areas == 2 and L2.n_clusters == 6
+    assert f.get(B.LUMP["ENTITIES"])[0].rstrip(b"\0").decode() == meta["entities"]
+    # replace a lump, save, reopen: every other lump is untouched
+    f.set(B.LUMP["LIGHTING"], bytes(range(200)), version=1)
+    path2 = str(tmp_path / "m2.bsp")
+    f.save(path2); f.close()
+    g = B.BspFile(path2)
+    assert g.get(B.LUMP["LIGHTING"]) == (bytes(range(200)), 1)
+    for k in L.a:
+        assert np.array_equal(L.a[k], g.lumps().a[k]), k
+    g.close()
+
+
+def test_bspfile_rejects_bad_files(smap, tmp_path):
+    L, meta = smap
+    good = str(tmp_path / "g.bsp")
+    B.write_bsp(good, L, meta)
+    raw = bytearray(open(good, "rb").read())
+
+    def opens(data):
+        p = str(tmp_path / "bad.bsp")
+        open(p, "wb").write(bytes(data))
+        return B.BspFile(p)
+    with pytest.raises(VradError):
+        B.BspFile(str(tmp_path / "missing.bsp"))
+    with pytest.raises(VradError):
+        opens(raw[:500])                                          # shorter than a header
+    bad = bytearray(raw); bad[:4] = b"IBSP"
+    with pytest.raises(VradError):
+        opens(bad)
+    bad = bytearray(raw); struct.pack_into("<i", bad, 4, 17)
+    with pytest.raises(VradError):
+        opens(bad)                                                # unsupported version
+    bad = bytearray(raw); struct.pack_into("<i", bad, 8 + 16 * B.LUMP["FACES"] + 4, len(raw))
+    with pytest.raises(VradError):
+        opens(bad)                                                # lump runs past the end
+    f = opens(raw)
+    faces = L.faces.copy(); faces[3]["texinfo"] = 999
+    f.set(B.LUMP["FACES"], faces)
+    with pytest.raises(VradError):
+        f.lumps()                                                 # index outside another lump
+    f.set(B.LUMP["FACES"], L.faces.tobytes()[:-3])
+    with pytest.raises(VradError):
+        f.lumps()                                                 # not a multiple of the record size
+    f.set(B.LUMP["FACES"], L.faces); f.set(B.LUMP["LEAFS"], L.leafs, version=0)
+    with pytest.raises(VradError):
+        f.lumps()                                                 # 56-byte (version 0) leafs are not read
+    f.close()
+
+
+# ---- lumps -> triangles ------------------------------------------------------------------------------------------------
+def test_raytrace_triangles_match_oracle(smap):
+    L, meta = smap
+    e = meta["brush_entity"]
+    ids, verts = B.raytrace_triangles(L, [e["model"]], [e["origin"]], [e["angles"]])
+    oids, overts = O.raytrace_triangles(L, [(e["model"], e["origin"], e["angles"])])
+    assert np.array_equal(ids, oids) and np.array_equal(_bits(verts), _bits(overts))
+    # 69 world brushes + the entity brush, 12 triangles each, minus the sky side of room 1's roof slab; 1 sky face
+    assert (ids == B.TRACE_ID_OPAQUE).sum() == 12 * (L.brushes.shape[0]) - 2 and (ids == B.TRACE_ID_SKY).sum() == 2
+    assert np.all(ids[-2:] == B.TRACE_ID_SKY)                     # sky faces come last (main.go:296-339)
+    # the caster comes first, rotated 30 degrees about z and moved to its origin: its 8 corners
+    c = verts[:12].reshape(-1, 3)
+    ang = np.deg2rad(30.0)
+    rot = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    corners = np.array([[x, y, z] for x in (-32, 32) for y in (-8, 8) for z in (0, 96)]) @ rot.T + e["origin"]
+    for p in c:
+        assert np.abs(corners - p).sum(axis=1).min() < 1e-3
+    # without casters the world triangles are the same, 12 fewer
+    ids0, verts0 = B.raytrace_triangles(L)
+    assert np.array_equal(ids0, ids[12:]) and np.array_equal(verts0, verts[12:])
+    # model indices outside (0, n_models) are ignored as brushmodelForEntity does
+    ids1, _ = B.raytrace_triangles(L, [0, 7], [e["origin"]] * 2, [e["angles"]] * 2)
+    assert np.array_equal(ids1, ids0)
+
+
+def test_cube_brush_known_answer():
+    side = 64.0
+    ids, verts = B.raytrace_triangles(_cube_map(side))
+    assert ids.shape[0] == 12 and np.all(ids == B.TRACE_ID_OPAQUE)
+    assert set(np.unique(verts).tolist()) == {0.0, side}         # chopped at the axial planes without round-off (winding.go:153-157)
+    a, b, c = verts[:, 0].astype(np.float64), verts[:, 1].astype(np.float64), verts[:, 2].astype(np.float64)
+    n = np.cross(b - a, c - a)
+    assert np.isclose(0.5 * np.linalg.norm(n, axis=1).sum(), 6 * side * side)
+    centre = np.full(3, side / 2)
+    assert np.all(np.einsum("ij,ij->i", n, (a + b + c) / 3 - centre) != 0)
+    out = np.sign(np.einsum("ij,ij->i", n, (a + b + c) / 3 - centre))
+    assert np.all(out == out[0])                                  # one consistent winding for the whole brush
+    # a sky-textured side is not added; a non-opaque brush adds nothing (main.go:238-240,255)
+    ids, verts = B.raytrace_triangles(_cube_map(side, sky_side=2))
+    assert ids.shape[0] == 10 and not np.any(np.all(verts[:, :, 1] == side, axis=1))
+    assert B.raytrace_triangles(_cube_map(side, contents=B.CONTENTS_WINDOW))[0].shape[0] == 0
+    o_ids, o_verts = O.raytrace_triangles(_cube_map(side, sky_side=2))
+    assert np.array_equal(ids, o_ids) and np.array_equal(_bits(verts), _bits(o_verts))
+
+
+def test_oblique_brush_matches_oracle():
+    """A wedge: the cube cut by an oblique plane -- general (non-axial) chops, where the interpolation arithmetic matters."""
+    L = _cube_map(64.0)
+    n = np.float32([0.6, 0.0, 0.8]); d = np.float32(70.0)
+    P = np.concatenate([L.planes, np.zeros(2, B.DPLANE)])
+    P[-2] = (n, d, 3); P[-1] = (-n, -d, 3)
+    S = np.concatenate([L.brushsides, np.zeros(1, B.DBRUSHSIDE)]); S[-1] = (len(P) - 2, 0, 0, 0)
+    br = L.brushes.copy(); br[0]["numsides"] = 7
+    L2 = L.replace(planes=P, brushsides=S, brushes=br)
+    ids, verts = B.raytrace_triangles(L2)
+    o_ids, o_verts = O.raytrace_triangles(L2)
+    assert ids.shape[0] > 12 and np.array_equal(ids, o_ids) and np.array_equal(_bits(verts), _bits(o_verts))
+    assert np.all(verts.reshape(-1, 3).astype(np.float64) @ n.astype(np.float64) <= float(d) + 1e-2)     # everything behind the cut
+    # bevel sides do not cut the other sides (main.go:264-266): the six cube faces come out whole again
+    S2 = S.copy(); S2[-1]["bevel"] = 1
+    _, vb = B.raytrace_triangles(L.replace(planes=P, brushsides=S2, brushes=br))
+    whole = np.all(np.isin(vb.reshape(len(vb), -1), np.float32([0.0, 64.0])), axis=1)
+    assert whole.sum() == 12 and np.all(whole[:12])
+
+
+# ---- lumps -> face patches -----------------------------------------------------------------------------------------------
+def test_face_patches_match_oracle(smap):
+    L, meta = smap
+    origins = np.zeros((2, 3), np.float32); origins[1] = meta["brush_entity"]["origin"]
+    g = B.face_patches(L, origins)
+    o = O.face_patches(L, origins)
+    nf = len(o["windings"])
+    assert g["faces"].shape[0] == nf == L.faces.shape[0]
+    assert np.array_equal(g["face_number"], np.asarray(o["face_number"], np.int32))
+    opts = np.asarray([p for w in o["windings"] for p in w], np.float32)
+    assert np.array_equal(_bits(g["points"]), _bits(opts))
+    assert np.array_equal(g["faces"]["n_points"], [len(w) for w in o["windings"]])
+    assert np.array_equal(_bits(g["faces"]["normal"]), _bits(np.asarray(o["normal"], np.float32)))
+    assert np.array_equal(_bits(g["faces"]["plane_dist"]), _bits(np.asarray(o["plane_dist"], np.float32)))
+    assert np.array_equal(_bits(g["faces"]["lux_scale"]), _bits(np.asarray(o["lux_scale"], np.float32)))
+    assert np.array_equal(g["faces"]["sky"], o["sky"]) and np.array_equal(g["faces"]["no_subdivide"], o["no_subdivide"])
+    assert np.array_equal(_bits(g["reflectivity"]), _bits(np.asarray(o["reflectivity"], np.float32)))
+    assert np.array_equal(g["needs_bump"], o["needs_bump"]) and np.array_equal(_bits(g["scale"]), _bits(np.asarray(o["scale"], np.float32)))
+    assert np.all(g["base_area"] == 512 * 512)
+    # hand-derived: luxel scale 1/16, texture scale 1/4; one sky face (NOLIGHT without LIGHT: no subdivision); room 0's floor is bumped
+    assert np.all(g["faces"]["lux_scale"] == np.float32(1 / 16)) and np.all(g["scale"] == np.float32(0.25))
+    assert g["faces"]["sky"].sum() == 1 and g["faces"]["no_subdivide"].sum() == 1 and g["needs_bump"].sum() == 1 and g["needs_bump"][0] == 1
+    # the brush entity's faces are moved by the entity origin, and so are their planes (face.go:122-144)
+    e = meta["brush_entity"]
+    sel = np.isin(g["face_number"], np.arange(e["first_face"], e["first_face"] + e["n_faces"]))
+    top = g["faces"][sel][0]
+    assert np.allclose(top["normal"], (0, 0, 1)) and top["plane_dist"] == np.float32(96.0 + e["origin"][2])
+    pts = g["points"][top["first_point"]:top["first_point"] + top["n_points"]]
+    assert np.allclose(pts.mean(axis=0), (e["origin"][0], e["origin"][1], 96.0))
+
+
+def test_face_patches_feed_subdivision(smap):
+    from vrad_b200.environment import subdivide_patches
+    L, _ = smap
+    g = B.face_patches(L, None)
+    t = subdivide_patches(g["faces"], g["points"], min_chop=4.0)
+    leaves = t["child1"] == -1
+    roots = t["parent"] == -1
+    assert roots.sum() == L.faces.shape[0]
+    # area is conserved from the face windings down to the leaf patches
+    area_faces = sum(float(O.winding_area([O.vec(p) for p in g["points"][f["first_point"]:f["first_point"] + f["n_points"]]])) for f in g["faces"])
+    assert np.isclose(t["area"][leaves].sum(dtype=np.float64), area_faces, rtol=1e-5)
+    assert np.isclose(t["area"][roots].sum(dtype=np.float64), area_faces, rtol=1e-6)
+
+
+def test_colinear_points_are_removed():
+    """A square face with a redundant vertex in the middle of one edge (point.go:20-31)."""
+    b = B._MapBuilder()
+    ti = 0
+    b.face([(0, 0, 0), (32, 0, 0), (64, 0, 0), (64, 64, 0), (0, 64, 0)], (0, 0, 1), ti)
+    faces = np.zeros(1, B.DFACE); f = b.faces[0]
+    faces[0]["planenum"] = f["planenum"]; faces[0]["firstedge"] = f["firstedge"]; faces[0]["numedges"] = 5; faces[0]["dispinfo"] = -1
+    planes = np.zeros(len(b.planes), B.DPLANE)
+    for k, (n, d, t) in enumerate(b.planes):
+        planes[k] = (n, d, t)
+    models = np.zeros(1, B.DMODEL); models[0]["numfaces"] = 1
+    tex = np.zeros(1, B.TEXINFO); tex[0]["lightmap_vecs"][0][0] = 1 / 16; tex[0]["lightmap_vecs"][1][1] = 1 / 16
+    L = B.Lumps(planes=planes, vertexes3=np.asarray(b.verts, np.float32), edges=np.asarray(b.edges, "<u2").view(B.DEDGE).reshape(-1),
+                surfedges=np.asarray(b.surfedges, "<i4"), faces=faces, texinfo=tex, texdata=np.zeros(1, B.DTEXDATA), models=models)
+    g = B.face_patches(L)
+    assert g["faces"][0]["n_points"] == 4
+    assert np.array_equal(g["points"], np.float32([(0, 0, 0), (64, 0, 0), (64, 64, 0), (0, 64, 0)]))
+    o = O.face_patches(L)
+    assert np.array_equal(g["points"], np.asarray(o["windings"][0], np.float32))
+
+
+# ---- extents, tree tables ------------------------------------------------------------------------------------------------
+def test_face_extents(smap):
+    L, _ = smap
+    mins, size, over = B.face_extents(L)
+    omins, osize = O.face_extents(L)
+    assert np.array_equal(mins, omins) and np.array_equal(size, osize) and over == 0
+    # room 0's floor spans x 0..504, y 0..504 at 1/16 luxel per unit: mins 0, size ceil(31.5) = 32
+    assert tuple(mins[0]) == (0, 0) and tuple(size[0]) == (32, 32)
+    # the sky face keeps what the file stores (start.go:104-106)
+    sky = int(np.nonzero(L.texinfo["flags"][L.faces["texinfo"]] & B.SURF_SKY)[0][0])
+    assert tuple(size[sky]) == (0, 0)
+    # denser luxels overflow the 126-luxel limit and are counted (face.go:66-87)
+    t = L.texinfo.copy(); t["lightmap_vecs"][:, :, :3] *= 8
+    assert B.face_extents(L.replace(texinfo=t))[2] > 0
+    # the luxel-density rescale (start.go:21-64) brings them back
+    t2 = B.rescale_lightmap_vecs(t, 1.0 / 16)
+    assert np.array_equal(_bits(t2["lightmap_vecs"]), _bits(O.rescale_lightmap_vecs(t, 1.0 / 16)["lightmap_vecs"]))
+    assert np.allclose(np.linalg.norm(t2["lightmap_vecs"][:, :, :3], axis=2), 1 / 16)
+    assert np.array_equal(B.rescale_lightmap_vecs(t, 1.0)["lightmap_vecs"], t["lightmap_vecs"])        # no-op at density >= 1
+    m2, s2, over2 = B.face_extents(L.replace(texinfo=t2))
+    assert over2 == 0 and np.array_equal(s2, size)
+
+
+def test_parents_and_cluster_table(smap):
+    L, _ = smap
+    npar, lpar = B.make_parents(L)
+    onp, olp = O.make_parents(L)
+    assert np.array_equal(npar, onp) and np.array_equal(lpar, olp)
+    assert npar[0] == -1 and np.all(npar[1:] >= 0) and lpar[0] == -1 and np.all(lpar[1:7] >= 0)          # leaf 0 (solid) hangs nowhere
+    for leaf in range(1, 7):                                      # walking up from every room leaf ends at the root
+        n = lpar[leaf]
+        assert (-1 - leaf) in L.nodes[n]["children"]
+        while npar[n] != -1:
+            assert n in L.nodes[npar[n]]["children"]; n = npar[n]
+        assert n == 0
+    first, leafs = B.cluster_table(L, L.n_clusters)
+    table = O.build_cluster_table(L, L.n_clusters)
+    assert [list(leafs[first[c]:first[c + 1]]) for c in range(L.n_clusters)] == table == [[1 + c] for c in range(6)]
+    # a tree whose node is reached twice is refused
+    bad = L.nodes.copy(); bad[1]["children"] = (2, 2)
+    with pytest.raises(VradError):
+        B.make_parents(L.replace(nodes=bad))
+
+
+# ---- sky vis ---------------------------------------------------------------------------------------------------------------
+def test_vis_for_light_environment(smap):
+    L, meta = smap
+    flags, pvs = B.vis_for_light_environment(L)
+    oflags, opvs = O.build_vis_for_light_environment(L)
+    assert np.array_equal(flags, oflags) and pvs.tobytes() == opvs
+    # room 1 = (i 0, j 1) holds the sky face; its PVS row is the sky lights' PVS: rooms 0 (same column) and 3 (same row) + itself
+    want = meta["pvs"][1]
+    assert np.array_equal(np.unpackbits(pvs, bitorder="little")[:6], want)
+    sees = np.nonzero(want)[0]
+    for k in range(6):
+        assert flags[1 + k] == (B.LEAF_FLAGS_SKY if k in sees else 0), k
+    assert flags[0] == 0                                          # the solid leaf is never marked (lightmap.go:327-329)
+    # no sky anywhere: no flags, no PVS
+    L0, _ = B.synthetic_map(2, 1, boxes_per_room=1, with_brush_entity=False)
+    f0, p0 = B.vis_for_light_environment(L0)
+    assert not f0.any() and p0 is None and O.build_vis_for_light_environment(L0)[1] is None
+    # a 2D-sky face marks SKY2D instead
+    t = L.texinfo.copy(); t["flags"][t["flags"] & B.SURF_SKY != 0] |= B.SURF_SKY2D
+    f2, _ = B.vis_for_light_environment(L.replace(texinfo=t))
+    assert np.array_equal(f2, O.build_vis_for_light_environment(L.replace(texinfo=t))[0])
+    assert f2[2] == B.LEAF_FLAGS_SKY2D and all(f2[1 + k] == B.LEAF_FLAGS_SKY2D for k in sees)
+    # without vis data every leaf sees every sky leaf (GetVisCache, vis.go:11-20)
+    fa, pa = B.vis_for_light_environment(L.replace(visdata=b""))
+    assert np.all(fa[1:7] == B.LEAF_FLAGS_SKY) and pa is None
+
+
+def test_radial_leafs_need_an_environment():
+    """LEAF_FLAGS_RADIAL leafs that see no sky leaf go through CanLeafTraceToSky on the device (lightmap.go:373-381): without an
+    environment that is an error, not a silent CPU path; radial leafs that already see sky need no trace."""
+    L, _ = B.synthetic_map(3, 2, boxes_per_room=1, sky_rooms=(1,), radial_rooms=(4,), with_brush_entity=False)
+    with pytest.raises(VradError) as ei:
+        B.vis_for_light_environment(L)
+    assert ei.value.status == -4
+    L2, _ = B.synthetic_map(3, 2, boxes_per_room=1, sky_rooms=(1,), radial_rooms=(0,), with_brush_entity=False)
+    f, _ = B.vis_for_light_environment(L2)
+    assert f[1] == (B.LEAF_FLAGS_SKY | B.LEAF_FLAGS_RADIAL)
+    # the oracle takes the trace as a callback
+    fo, _ = O.build_vis_for_light_environment(L, can_leaf_trace_to_sky=lambda leaf: leaf == 5)
+    assert fo[5] == (B.LEAF_FLAGS_SKY | B.LEAF_FLAGS_RADIAL)
+
+
+# ---- smoothing normals ------------------------------------------------------------------------------------------------------
+def test_pair_edges_match_oracle(smap):
+    L, _ = smap
+    for thr in (0.7071067, -1.0):
+        vn, first, nb = B.pair_edges(L, thr)
+        on, onb = O.pair_edges(L, thr)
+        assert np.array_equal(_bits(vn), _bits(np.asarray([v for fn in on for v in fn], np.float32)))
+        assert [list(nb[first[i]:first[i + 1]]) for i in range(L.faces.shape[0])] == onb
+        normals, idx = B.save_vertex_normals(vn)
+        onormals, oidx = O.save_vertex_normals(on)
+        assert np.array_equal(_bits(normals), _bits(onormals)) and np.array_equal(idx, oidx)
+        assert np.allclose(normals[idx], vn, atol=4e-3)           # equal within the 1e-5 squared-distance merge
+        assert np.allclose(np.linalg.norm(vn, axis=1), 1, atol=1e-6)
+
+
+def test_pair_edges_known_answers(smap):
+    L, meta = smap
+    # at the default 45-degree crease nothing in the axis-aligned map smooths across an edge: vertex normals = face normals,
+    # but coplanar faces sharing vertices (wall pieces around a door) are neighbours
+    vn, first, nb = B.pair_edges(L, 0.7071067)
+    fn = L.planes["normal"][L.faces["planenum"]]
+    plain = np.repeat(L.faces["smoothing_groups"] == 0, L.faces["numedges"])
+    assert np.array_equal(vn[plain], np.repeat(fn, L.faces["numedges"], axis=0)[plain])
+    for i in range(L.faces.shape[0]):
+        for o in nb[first[i]:first[i + 1]]:
+            assert np.dot(fn[i], fn[o]) > 0.7 or (L.faces[i]["smoothing_groups"] & L.faces[o]["smoothing_groups"])
+    # with the threshold at -1 every face at a box corner joins in: the top face of an occluder box gets (+-1, +-1, 1)/sqrt(3)
+    vn2, _, _ = B.pair_edges(L, -1.0)
+    box_top = next(i for i in range(L.faces.shape[0]) if L.texinfo[L.faces[i]["texinfo"]]["texdata"] == 2 and fn[i][2] == 1)
+    ofs = int(L.faces["numedges"][:box_top].sum())
+    assert np.allclose(np.abs(vn2[ofs:ofs + 4]), 1 / np.sqrt(3), atol=1e-6) and np.all(vn2[ofs:ofs + 4, 2] > 0)
+    # smoothing groups: solid walls of one room carry group 1 and meet at right angles -> smoothed whatever the threshold;
+    # a hard-edge bit in common stops it (lightmap.go:160-172)
+    wall = next(i for i in range(L.faces.shape[0]) if L.faces[i]["smoothing_groups"] == 1)
+    o0 = int(L.faces["numedges"][:wall].sum())
+    assert not np.array_equal(vn[o0:o0 + 4], np.repeat(fn[wall][None], 4, axis=0))
+    hard = L.faces.copy(); hard["smoothing_groups"][hard["smoothing_groups"] == 1] = 0xff000001
+    vh, _, _ = B.pair_edges(L.replace(faces=hard), 0.7071067)
+    assert np.array_equal(vh[o0:o0 + 4], np.repeat(fn[wall][None], 4, axis=0))
+
+
+def test_phong_normals(smap):
+    L, _ = smap
+    vn, _, _ = B.pair_edges(L, -1.0)
+    on, _ = O.pair_edges(L, -1.0)
+    g = B.face_patches(L)
+    centroids = np.zeros((L.faces.shape[0], 3), np.float32)
+    for k, f in enumerate(g["faces"]):
+        centroids[g["face_number"][k]] = g["points"][f["first_point"]:f["first_point"] + f["n_points"]].astype(np.float64).mean(axis=0)
+    rng = np.random.default_rng(5)
+    faces = rng.integers(0, L.faces.shape[0], 300).astype(np.int32)
+    pts = np.zeros((300, 3), np.float32)
+    for k, fi in enumerate(faces):
+        f = g["faces"][fi]
+        w = g["points"][f["first_point"]:f["first_point"] + f["n_points"]].astype(np.float64)
+        bary = rng.dirichlet(np.ones(len(w)))
+        pts[k] = bary @ w
+    out = B.phong_normals(L, vn, centroids, faces, pts, -1.0)
+    want = np.asarray([O.get_phong_normal(L, on, centroids, int(fi), p, -1.0) for fi, p in zip(faces, pts)], np.float32)
+    assert np.array_equal(_bits(out), _bits(want))
+    assert np.allclose(np.linalg.norm(out, axis=1), 1, atol=1e-5)
+    # known answers: at a face vertex the phong normal is that vertex's smoothed normal; threshold 1 turns smoothing off
+    fi = 0
+    ofs = 0
+    v0 = L.vertexes3[O.edge_vertex(L, L.faces[fi], 0)]
+    got = B.phong_normals(L, vn, centroids, [fi], [v0], -1.0)[0]
+    assert np.allclose(got, vn[ofs], atol=1e-6)
+    flat = B.phong_normals(L, vn, centroids, faces, pts, 1.0)
+    assert np.array_equal(flat, L.planes["normal"][L.faces["planenum"][faces]])
+    with pytest.raises(VradError):
+        B.phong_normals(L, vn, centroids, [9999], [v0])
+
+
+# ---- luxels and the lighting lump ------------------------------------------------------------------------------------------
+def test_face_luxels_and_lighting_layout(smap, tmp_path):
+    L, meta = smap
+    mins, size, _ = B.face_extents(L)
+    faces, first, nbytes = B.layout_lighting(L, mins, size)
+    flags = L.texinfo["flags"][L.faces["texinfo"]]
+    lit = (flags & (B.SURF_SKY | B.SURF_NOLIGHT)) == 0
+    per_face = (size[:, 0] + 1) * (size[:, 1] + 1) * np.where(flags & B.SURF_BUMPLIGHT, 4, 1) * lit
+    assert np.array_equal(np.diff(first), per_face) and nbytes == 4 * per_face.sum() + 4 * lit.sum()
+    assert np.all(faces["lightofs"][~lit] == -1) and np.all(faces["styles"][~lit] == 255)
+    assert np.all(faces["styles"][lit] == (0, 255, 255, 255)) and np.array_equal(faces["lm_size"], size)
+    ofs = faces["lightofs"][lit]
+    assert ofs[0] == 4 and np.array_equal(np.diff(ofs), 4 * per_face[lit][:-1] + 4)                   # average colour before each block
+    L3 = L.replace(faces=faces)
+    pos, nrm, lface = B.face_luxels(L3, mins, size, first)
+    assert pos.shape[0] == first[-1] and np.array_equal(np.repeat(np.arange(L.faces.shape[0]), per_face), lface)
+    # flat blocks equal the oracle's restatement bit for bit
+    opos, onrm, oface = O.face_luxels(L3, mins, size)
+    flat_sel = np.ones(pos.shape[0], bool)
+    bump_face = int(np.nonzero(flags & B.SURF_BUMPLIGHT)[0][0])
+    n_flat = (size[bump_face, 0] + 1) * (size[bump_face, 1] + 1)
+    flat_sel[first[bump_face] + n_flat:first[bump_face + 1]] = False
+    assert np.array_equal(_bits(pos[flat_sel]), _bits(opos)) and np.array_equal(_bits(nrm[flat_sel]), _bits(onrm)) and np.array_equal(lface[flat_sel], oface)
+    # every sample is one unit in front of its face and maps back to integer lightmap coordinates mins + (s, t)
+    pl = L.planes[L.faces["planenum"][lface]]
+    assert np.allclose(np.einsum("ij,ij->i", pos.astype(np.float64), pl["normal"].astype(np.float64)) - pl["dist"], 1.0, atol=1e-3)
+    lv = L.texinfo["lightmap_vecs"][L.faces["texinfo"][lface]].astype(np.float64)
+    st = np.einsum("ijk,ik->ij", lv[:, :, :3], pos.astype(np.float64) - pl["normal"]) + lv[:, :, 3]
+    assert np.allclose(st, np.round(st), atol=1e-4)
+    k = first[5]
+    w5 = size[5, 0] + 1
+    assert np.allclose(st[k], mins[5]) and np.allclose(st[k + 1], mins[5] + (1, 0)) and np.allclose(st[k + w5], mins[5] + (0, 1))       # t major, s minor
+    # the bump-mapped floor: 4 blocks, same positions, block 0 = the face normal, blocks 1..3 = the bump basis (sum = sqrt(3) n)
+    blocks_p = pos[first[bump_face]:first[bump_face + 1]].reshape(4, n_flat, 3)
+    blocks_n = nrm[first[bump_face]:first[bump_face + 1]].reshape(4, n_flat, 3)
+    assert np.array_equal(blocks_p[0], blocks_p[1]) and np.array_equal(blocks_p[0], blocks_p[3])
+    assert np.allclose(blocks_n[1:].sum(axis=0), np.sqrt(3) * blocks_n[0], atol=1e-5)
+    # pack: colours land at lightofs, the average colour right before, and the file carries the lump
+    rng = np.random.default_rng(11)
+    rgb = rng.uniform(0, 400, (pos.shape[0], 3)).astype(np.float32)
+    colors = B.color_to_rgbexp32(rgb)
+    lump = B.pack_lighting(L3, first, colors, nbytes)
+    assert len(lump) == nbytes
+    for fi in (0, 5, bump_face, int(np.nonzero(lit)[0][-1])):
+        o = int(faces["lightofs"][fi]); n = int(per_face[fi])
+        assert lump[o:o + 4 * n] == colors[first[fi]:first[fi] + n].tobytes()
+        flat_n = n // 4 if fi == bump_face else n
+        avg = B.color_from_rgbexp32(colors[first[fi]:first[fi] + flat_n]).mean(axis=0, dtype=np.float64)
+        got = B.color_from_rgbexp32(np.frombuffer(lump[o - 4:o], B.RGBEXP32))[0]
+        assert np.allclose(got, avg, rtol=2e-2)
+    path = str(tmp_path / "lit.bsp")
+    B.write_bsp(path, L3, meta, lighting=lump)
+    f = B.BspFile(path)
+    assert f.get(B.LUMP["LIGHTING"])[0] == lump and np.array_equal(f.lumps().faces, faces)
+    f.close()
+    with pytest.raises(VradError):
+        B.pack_lighting(L3, first, colors, nbytes - 8)           # the last face would not fit
+
+
+def test_rgbexp32():
+    rng = np.random.default_rng(3)
+    mags = np.float32(2.0) ** rng.integers(-40, 40, (4000, 1)).astype(np.float32)
+    rgb = (rng.uniform(0, 1, (4000, 3)).astype(np.float32) * mags).astype(np.float32)
+    rgb[::17, 1] = 0; rgb[::29] = 0
+    got = B.color_to_rgbexp32(rgb)
+    want = np.asarray([O.pack_rgbexp32(c) for c in rgb], dtype=np.int64)
+    assert np.array_equal(np.stack([got["r"], got["g"], got["b"], got["exponent"]], axis=1).astype(np.int64), want)
+    back = B.color_from_rgbexp32(got)
+    mx = rgb.max(axis=1)
+    nz = mx > 0
+    assert np.all(got[nz].view(np.uint8).reshape(-1, 4)[:, :3].max(axis=1) >= 128)                     # the largest mantissa is normalised
+    assert np.all(back <= rgb * (1 + 1e-6)) and np.all(rgb[nz] - back[nz] <= (mx[nz] / 128)[:, None])   # truncation, one part in 128 of the largest
+    # hand-derived: (1,2,3) -> largest 3 doubles 6 times to 192: exponent -6, mantissas 64,128,192
+    c = B.color_to_rgbexp32([[1, 2, 3], [300, 200, 100], [255.5, 1, 1], [0, 0, 0], [-5, 4, np.nan], [np.inf, 1, 1], [1e-37, 0, 0], [256, 0, 0]])
+    rows = [tuple(int(v) for v in (x["r"], x["g"], x["b"], x["exponent"])) for x in c]
+    assert rows[0] == (64, 128, 192, -6) and rows[1] == (150, 100, 50, 1) and rows[2] == (255, 1, 1, 0) and rows[3] == (0, 0, 0, 0)
+    assert rows[4] == (0, 128, 0, -5)                             # negative and NaN components count as zero
+    assert rows[5][0] == 255 and rows[5][3] > 100 and rows[6] == (0, 0, 0, 0) and rows[7] == (128, 0, 0, 1)
+    assert np.array_equal(B.color_from_rgbexp32(c[:2]), np.float32([[1, 2, 3], [300, 200, 100]]))

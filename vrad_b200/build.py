@@ -16,7 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libvradcuda.so")
 
-SOURCES = ["vrad_env.cu", "k1_trace.cu", "k1_sky.cu", "k2_transfers.cu", "k3_direct.cu", "k4_bounce.cu", "comm.cu", "kd_builder.cpp", "patch_subdivide.cpp", "light_setup.cpp"]
+SOURCES = ["vrad_env.cu", "k1_trace.cu", "k1_sky.cu", "k2_transfers.cu", "k3_direct.cu", "k4_bounce.cu", "comm.cu", "kd_builder.cpp", "patch_subdivide.cpp", "light_setup.cpp",
+           "bsp_file.cpp", "bsp_input.cpp", "bsp_light.cpp", "k5_finalize.cu"]
 
 
 def _nvcc() -> str:
@@ -30,7 +31,8 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "vrad_cuda.h"), __file__]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "vrad_cuda.h"),
+                                                               os.path.join(HERE, "..", "include", "vrad_bsp.h"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

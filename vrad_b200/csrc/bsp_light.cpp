@@ -1,0 +1,319 @@
+// bsp_light.cpp -- smoothing normals, luxel sample points and the lighting lump: what sits
+// between the BSP faces and K3's luxel arrays on the way in, and between the baked light and the .bsp on the way out.
+// Pure host code.
+//
+// Reference map
+//   rad/lightmap/lightmap.go:37-216      PairEdges: faces per vertex, neighbour lists, smoothed vertex normals
+//   rad/lightmap/lightmap.go:218-265     SaveVertexNormals
+//   rad/lightmap/lightmap.go:267-282     EdgeVertex
+//   rad/lightmap/normallist.go:12-49     NormalList.FindOrAddNormal (8x8x8 grid over [-1,1]^3)
+//   rad/lightmap/normallist.go:52-143    GetPhongNormal
+//   common/types/face.go:5-13            FaceNeighbour
+//   vmath/polygon/face.go:5-17           ValidDispFace
+// Intent adopted where the literal text is defective: lightmap.go:74 walks len(Edges) instead of the face's edges;
+// normallist.go:40 compares pointers and :47 returns the length after the append -- equal means
+// squared distance < 1e-5 and the index of the new element is returned; lightmap.go:258-264 `make(..., len)` then append
+// doubles the list -- the lump holds each unique normal once.
+// UNCITED (absent from the reference): luxel sample points (upstream InitLightinfo / CalcPoints without the
+// off-face sample nudging) and the lighting lump layout (upstream PrecompLightmapOffsets / FinalLightFace).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../include/vrad_bsp.h"
+#include "rgbexp.cuh"
+
+namespace vrad { void set_error(const char* fmt, ...); }
+
+namespace {
+
+constexpr uint32_t kSmoothingGroupHardEdge = 0xff000000u;     // lightmap.go:23
+constexpr int kMaxNeighbours = 64;                            // lightmap.go:41
+
+struct V3 { float v[3]; float& operator[](int i) { return v[i]; } float operator[](int i) const { return v[i]; } };
+inline V3 sub(const V3& a, const V3& b) { return {{a[0] - b[0], a[1] - b[1], a[2] - b[2]}}; }
+inline V3 add(const V3& a, const V3& b) { return {{a[0] + b[0], a[1] + b[1], a[2] + b[2]}}; }
+inline V3 scale(const V3& a, float s) { return {{a[0] * s, a[1] * s, a[2] * s}}; }
+inline float dot(const V3& a, const V3& b) { return ((a[0] * b[0]) + (a[1] * b[1])) + (a[2] * b[2]); }
+inline V3 cross(const V3& a, const V3& b) { return {{(a[1] * b[2]) - (a[2] * b[1]), (a[2] * b[0]) - (a[0] * b[2]), (a[0] * b[1]) - (a[1] * b[0])}}; }
+inline float len(const V3& a) { return (float)std::sqrt((double)(((a[0] * a[0]) + (a[1] * a[1])) + (a[2] * a[2]))); }
+inline V3 normalize(const V3& a) { const float l = 1.0f / len(a); return {{a[0] * l, a[1] * l, a[2] * l}}; }
+inline V3 load3(const float* p) { return {{p[0], p[1], p[2]}}; }
+
+inline int face_vertex(const vrad_bsp_lumps& L, const vrad_dface& f, int k) {    // EdgeVertex, lightmap.go:267-282
+    const int n = f.numedges;
+    if (k < 0) k += n; else if (k >= n) k %= n;
+    const int32_t se = L.surfedges[f.firstedge + k];
+    return se < 0 ? L.edges[-(int64_t)se].v[1] : L.edges[se].v[0];
+}
+inline bool valid_disp_face(const vrad_dface& f) { return f.dispinfo != -1 && f.numedges == 4; }
+
+inline bool face_is_lit(const vrad_bsp_lumps& L, const vrad_dface& f) {
+    return !(L.texinfo[f.texinfo].flags & (VRAD_SURF_SKY | VRAD_SURF_NOLIGHT));
+}
+inline bool face_is_bumped(const vrad_bsp_lumps& L, const vrad_dface& f) { return (L.texinfo[f.texinfo].flags & VRAD_SURF_BUMPLIGHT) != 0; }
+
+}  // namespace
+
+extern "C" int vrad_bsp_pair_edges(const vrad_bsp_lumps* Lp, float smoothing_threshold, float* vertex_normals3,
+                                   int32_t* neighbour_first, int32_t* neighbours, int max_neighbours) {
+    if (!Lp || !vertex_normals3 || !neighbour_first) { vrad::set_error("vrad_bsp_pair_edges: bad arguments"); return VRAD_E_INVALID; }
+    const vrad_bsp_lumps& L = *Lp;
+    // faces per vertex, each face once, in face order (lightmap.go:48-87) -- as CSR
+    std::vector<int32_t> vfirst((size_t)L.n_vertexes + 1, 0);
+    std::vector<int32_t> last_face((size_t)L.n_vertexes, -1);
+    for (int i = 0; i < L.n_faces; i++)
+        for (int j = 0; j < L.faces[i].numedges; j++) { const int v = face_vertex(L, L.faces[i], j); if (last_face[v] != i) { last_face[v] = i; vfirst[v + 1]++; } }
+    for (int v = 0; v < L.n_vertexes; v++) vfirst[v + 1] += vfirst[v];
+    std::vector<int32_t> vfaces((size_t)vfirst[L.n_vertexes]), fill(vfirst.begin(), vfirst.end() - 1);
+    std::fill(last_face.begin(), last_face.end(), -1);
+    for (int i = 0; i < L.n_faces; i++)
+        for (int j = 0; j < L.faces[i].numedges; j++) { const int v = face_vertex(L, L.faces[i], j); if (last_face[v] != i) { last_face[v] = i; vfaces[fill[v]++] = i; } }
+
+    size_t out = 0;
+    int32_t nn_total = 0;
+    for (int i = 0; i < L.n_faces; i++) {
+        const vrad_dface& f = L.faces[i];
+        const V3 face_normal = load3(L.planes[f.planenum].normal);          // :96
+        const bool has_disp = valid_disp_face(f);
+        int tmp[kMaxNeighbours], nn = 0;
+        neighbour_first[i] = nn_total;
+        for (int j = 0; j < f.numedges; j++) {
+            V3 acc = {{0, 0, 0}};
+            const int v = face_vertex(L, f, j);
+            for (int32_t k = vfirst[v]; k < vfirst[v + 1]; k++) {
+                const int o = vfaces[k];
+                if (o == i) continue;                                        // skip self
+                const vrad_dface& of = L.faces[o];
+                if (!has_disp && valid_disp_face(of)) continue;              // :138-140
+                const V3 nb = load3(L.planes[of.planenum].normal);
+                const float cos_angle = dot(nb, face_normal);
+                if (has_disp) acc = add(acc, nb);                            // always smooth with and against a displacement
+                else if (f.smoothing_groups == 0 && of.smoothing_groups == 0) {
+                    if (cos_angle >= smoothing_threshold) acc = add(acc, nb); else continue;
+                } else {
+                    const uint32_t g = f.smoothing_groups & of.smoothing_groups;
+                    if (g & kSmoothingGroupHardEdge) continue;
+                    if (g != 0) acc = add(acc, nb); else continue;
+                }
+                int m = 0;
+                for (; m < nn; m++) if (tmp[m] == o) break;
+                if (m >= nn) {
+                    if (nn >= kMaxNeighbours) { vrad::set_error("Stack overflow in neighbors (face %d)", i); return VRAD_E_INVALID; }
+                    tmp[nn++] = o;
+                }
+            }
+            acc = normalize(add(acc, face_normal));                          // fixup (:209-213)
+            for (int k = 0; k < 3; k++) vertex_normals3[3 * out + k] = acc[k];
+            out++;
+        }
+        if (neighbours) {
+            if (nn_total + nn > max_neighbours) { vrad::set_error("vrad_bsp_pair_edges: more than %d neighbour entries", max_neighbours); return VRAD_E_NOMEM; }
+            for (int m = 0; m < nn; m++) neighbours[nn_total + m] = tmp[m];
+        }
+        nn_total += nn;
+    }
+    neighbour_first[L.n_faces] = nn_total;
+    return VRAD_OK;
+}
+
+extern "C" int vrad_bsp_save_vertex_normals(int n_face_vertices, const float* vertex_normals3, int max_normals,
+                                            float* normals3, uint16_t* indices, int* n_normals_out) {
+    if (n_face_vertices < 0 || (n_face_vertices && !vertex_normals3) || !n_normals_out) { vrad::set_error("vrad_bsp_save_vertex_normals: bad arguments"); return VRAD_E_INVALID; }
+    constexpr int kSub = 8;                                                  // numSubDivs, normallist.go:11
+    std::vector<int32_t> grid[kSub][kSub][kSub];
+    std::vector<V3> list;
+    for (int i = 0; i < n_face_vertices; i++) {
+        const V3 nv = load3(vertex_normals3 + 3 * (size_t)i);
+        int gi[3];
+        for (int d = 0; d < 3; d++) {
+            // (int)(((n + 1) * 0.5) * numSubDivs - 0.000001): Go evaluates the untyped constants in fp32 here
+            int g = (int)(((nv[d] + 1.0f) * 0.5f) * (float)kSub - 0.000001f);
+            g = g < kSub - 1 ? g : kSub - 1;                                 // math.Min(g, numSubDivs) would index out of range at 8
+            g = g > 0 ? g : 0;
+            gi[d] = g;
+        }
+        std::vector<int32_t>& cell = grid[gi[0]][gi[1]][gi[2]];
+        int found = -1;
+        for (int32_t idx : cell) {
+            const V3 d = sub(list[idx], nv);
+            if (dot(d, d) < 0.00001f) { found = idx; break; }
+        }
+        if (found < 0) { found = (int)list.size(); cell.push_back(found); list.push_back(nv); }
+        if (found > 0xffff) { vrad::set_error("g_numvertnormals > MAX_MAP_VERTNORMALS"); return VRAD_E_INVALID; }
+        if (indices) indices[i] = (uint16_t)found;
+    }
+    *n_normals_out = (int)list.size();
+    if (normals3) {
+        if ((int)list.size() > max_normals) { vrad::set_error("vrad_bsp_save_vertex_normals: %zu normals, room for %d", list.size(), max_normals); return VRAD_E_NOMEM; }
+        for (size_t i = 0; i < list.size(); i++) for (int k = 0; k < 3; k++) normals3[3 * i + k] = list[i][k];
+    }
+    return VRAD_OK;
+}
+
+extern "C" int vrad_bsp_phong_normals(const vrad_bsp_lumps* Lp, float smoothing_threshold, const float* vertex_normals3, const float* centroids3,
+                                      int64_t n, const int32_t* face, const float* points3, float* normals3_out) {
+    if (!Lp || !vertex_normals3 || !centroids3 || n < 0 || (n && (!face || !points3 || !normals3_out))) { vrad::set_error("vrad_bsp_phong_normals: bad arguments"); return VRAD_E_INVALID; }
+    const vrad_bsp_lumps& L = *Lp;
+    std::vector<int64_t> first((size_t)L.n_faces + 1, 0);                   // offset of each face's block in vertex_normals3
+    for (int i = 0; i < L.n_faces; i++) first[i + 1] = first[i] + L.faces[i].numedges;
+    for (int64_t p = 0; p < n; p++) {
+        const int fn = face[p];
+        if (fn < 0 || fn >= L.n_faces) { vrad::set_error("vrad_bsp_phong_normals: point %lld names face %d of %d", (long long)p, fn, L.n_faces); return VRAD_E_INVALID; }
+        const vrad_dface& f = L.faces[fn];
+        const V3 face_normal = load3(L.planes[f.planenum].normal);
+        V3 result = face_normal;
+        if (smoothing_threshold != 1.0f) {
+            const V3 centre = load3(centroids3 + 3 * (size_t)fn), spot = load3(points3 + 3 * p);
+            const float* vn = vertex_normals3 + 3 * first[fn];
+            for (int j = 0; j < f.numedges; j++) {
+                const V3 n1 = load3(vn + 3 * j), n2 = load3(vn + 3 * ((j + 1) % f.numedges));
+                const V3 p1 = load3(L.vertexes3 + 3 * (size_t)face_vertex(L, f, j)), p2 = load3(L.vertexes3 + 3 * (size_t)face_vertex(L, f, j + 1));
+                const V3 v1 = sub(p1, centre), v2 = sub(p2, centre), vspot = sub(spot, centre);
+                const float aa = dot(v1, v1), bb = dot(v2, v2), ab = dot(v1, v2);
+                const float a1 = (bb * dot(v1, vspot) - ab * dot(vspot, v2)) / (aa * bb - ab * ab);
+                const float a2 = (dot(vspot, v2) - a1 * ab) / bb;
+                if (a1 >= 0.0f && a2 >= 0.0f) {                              // inside the wedge centre-p1-p2
+                    const float s = (1.0f - a1) - a2;                        // Go: the untyped 1.0 takes a1's type
+                    V3 ph = scale(face_normal, s);
+                    ph = add(ph, scale(n1, a1));
+                    ph = add(ph, scale(n2, a2));
+                    if (1.0e-20f > len(ph)) { vrad::set_error("Phong normal length out of bounds (face %d)", fn); return VRAD_E_INVALID; }
+                    result = normalize(ph);
+                    break;
+                }
+            }
+        }
+        for (int k = 0; k < 3; k++) normals3_out[3 * p + k] = result[k];
+    }
+    return VRAD_OK;
+}
+
+extern "C" int vrad_bsp_layout_lighting(const vrad_bsp_lumps* Lp, const int32_t* mins2, const int32_t* size2, vrad_dface* faces_out,
+                                        int64_t* luxel_first, int64_t* lump_bytes) {
+    if (!Lp || !mins2 || !size2 || !luxel_first || !lump_bytes) { vrad::set_error("vrad_bsp_layout_lighting: bad arguments"); return VRAD_E_INVALID; }
+    const vrad_bsp_lumps& L = *Lp;
+    int64_t lux = 0, bytes = 0;
+    for (int i = 0; i < L.n_faces; i++) {
+        const vrad_dface& f = L.faces[i];
+        luxel_first[i] = lux;
+        vrad_dface o = f;
+        for (int k = 0; k < 2; k++) { o.lm_mins[k] = mins2[2 * (size_t)i + k]; o.lm_size[k] = size2[2 * (size_t)i + k]; }
+        if (!face_is_lit(L, f) || size2[2 * (size_t)i] < 0 || size2[2 * (size_t)i + 1] < 0) {
+            o.lightofs = -1;
+            for (int k = 0; k < 4; k++) o.styles[k] = 255;
+        } else {
+            const int64_t samples = (int64_t)(size2[2 * (size_t)i] + 1) * (size2[2 * (size_t)i + 1] + 1) * (face_is_bumped(L, f) ? 4 : 1);
+            bytes += 4;                                                      // the style's average colour sits right before the samples
+            if (bytes + samples * 4 > INT32_MAX) { vrad::set_error("vrad_bsp_layout_lighting: lighting lump would exceed 2 GiB at face %d", i); return VRAD_E_INVALID; }
+            o.lightofs = (int32_t)bytes;
+            o.styles[0] = 0; o.styles[1] = o.styles[2] = o.styles[3] = 255;
+            bytes += samples * 4;
+            lux += samples;
+        }
+        if (faces_out) faces_out[i] = o;
+    }
+    luxel_first[L.n_faces] = lux;
+    *lump_bytes = bytes;
+    return VRAD_OK;
+}
+
+extern "C" int vrad_bsp_face_luxels(const vrad_bsp_lumps* Lp, const int32_t* mins2, const int32_t* size2, const float* face_origins3,
+                                    const int64_t* luxel_first, float* pos3, float* normal3, int32_t* luxel_face) {
+    if (!Lp || !mins2 || !size2 || !luxel_first || !pos3 || !normal3) { vrad::set_error("vrad_bsp_face_luxels: bad arguments"); return VRAD_E_INVALID; }
+    const vrad_bsp_lumps& L = *Lp;
+    for (int i = 0; i < L.n_faces; i++) {
+        const int64_t count = luxel_first[i + 1] - luxel_first[i];
+        if (count == 0) continue;
+        const vrad_dface& f = L.faces[i];
+        const vrad_texinfo& tx = L.texinfo[f.texinfo];
+        const int w = size2[2 * (size_t)i] + 1, h = size2[2 * (size_t)i + 1] + 1;
+        const int blocks = face_is_bumped(L, f) ? 4 : 1;
+        if (count != (int64_t)w * h * blocks) { vrad::set_error("vrad_bsp_face_luxels: face %d has %lld luxels laid out, extents say %lld", i, (long long)count, (long long)w * h * blocks); return VRAD_E_INVALID; }
+        const vrad_dplane& pl = L.planes[f.planenum];
+        const V3 nrm = load3(pl.normal);
+        const float dist = pl.dist;
+        const V3 lv0 = load3(tx.lightmap_vecs[0]), lv1 = load3(tx.lightmap_vecs[1]);
+        // a normal to the texture axes: points move along it without changing their (s,t); flipped towards the face normal
+        V3 texnormal = normalize(cross(lv1, lv0));
+        float distscale = dot(texnormal, nrm);
+        if (distscale == 0.0f || distscale != distscale) { vrad::set_error("Texture axis perpendicular to face %d", i); return VRAD_E_INVALID; }
+        if (distscale < 0.0f) { distscale = -distscale; texnormal = {{-texnormal[0], -texnormal[1], -texnormal[2]}}; }
+        distscale = 1.0f / distscale;
+        V3 l2w[2];
+        l2w[0] = cross(lv1, nrm); l2w[0] = scale(l2w[0], 1.0f / dot(l2w[0], lv0));
+        l2w[1] = cross(lv0, nrm); l2w[1] = scale(l2w[1], 1.0f / dot(l2w[1], lv1));
+        V3 org;
+        for (int k = 0; k < 3; k++) org[k] = (-(tx.lightmap_vecs[0][3] * l2w[0][k])) - (tx.lightmap_vecs[1][3] * l2w[1][k]);
+        float d = dot(org, nrm) - dist;
+        d *= distscale;
+        for (int k = 0; k < 3; k++) org[k] = org[k] + ((-d) * texnormal[k]);
+        if (face_origins3) org = add(org, load3(face_origins3 + 3 * (size_t)i));
+        float bump9[9];
+        if (blocks == 4) {
+            const int rc = vrad_bump_normals(tx.texture_vecs[0], tx.texture_vecs[1], nrm.v, nrm.v, bump9);
+            if (rc) return rc;
+        }
+        int64_t o = luxel_first[i];
+        for (int b = 0; b < blocks; b++) {
+            const V3 bn = b == 0 ? nrm : load3(bump9 + 3 * (b - 1));
+            for (int t = 0; t < h; t++)
+                for (int s = 0; s < w; s++, o++) {
+                    const float us = (float)(mins2[2 * (size_t)i] + s), ut = (float)(mins2[2 * (size_t)i + 1] + t);
+                    for (int k = 0; k < 3; k++) {
+                        const float surf = (org[k] + (us * l2w[0][k])) + (ut * l2w[1][k]);
+                        pos3[3 * o + k] = surf + nrm[k];                    // one unit off the surface
+                        normal3[3 * o + k] = bn[k];
+                    }
+                    if (luxel_face) luxel_face[o] = i;
+                }
+        }
+    }
+    return VRAD_OK;
+}
+
+extern "C" int vrad_color_to_rgbexp32(int64_t n, const float* rgb3, vrad_color_rgbexp32* out) {
+    if (n < 0 || (n && (!rgb3 || !out))) { vrad::set_error("vrad_color_to_rgbexp32: bad arguments"); return VRAD_E_INVALID; }
+    for (int64_t i = 0; i < n; i++) {
+        const vrad::RgbExp c = vrad::pack_rgbexp32(rgb3[3 * i], rgb3[3 * i + 1], rgb3[3 * i + 2]);
+        out[i].r = c.r; out[i].g = c.g; out[i].b = c.b; out[i].exponent = c.e;
+    }
+    return VRAD_OK;
+}
+
+extern "C" int vrad_color_from_rgbexp32(int64_t n, const vrad_color_rgbexp32* in, float* rgb3) {
+    if (n < 0 || (n && (!in || !rgb3))) { vrad::set_error("vrad_color_from_rgbexp32: bad arguments"); return VRAD_E_INVALID; }
+    for (int64_t i = 0; i < n; i++) {
+        const vrad::RgbExp c = {in[i].r, in[i].g, in[i].b, in[i].exponent};
+        vrad::unpack_rgbexp32(c, rgb3[3 * i], rgb3[3 * i + 1], rgb3[3 * i + 2]);
+    }
+    return VRAD_OK;
+}
+
+extern "C" int vrad_bsp_pack_lighting(const vrad_bsp_lumps* Lp, const int64_t* luxel_first, const vrad_color_rgbexp32* colors,
+                                      uint8_t* lump_out, int64_t lump_bytes) {
+    if (!Lp || !luxel_first || !colors || (lump_bytes && !lump_out) || lump_bytes < 0) { vrad::set_error("vrad_bsp_pack_lighting: bad arguments"); return VRAD_E_INVALID; }
+    const vrad_bsp_lumps& L = *Lp;
+    std::memset(lump_out, 0, (size_t)lump_bytes);
+    for (int i = 0; i < L.n_faces; i++) {
+        const int64_t count = luxel_first[i + 1] - luxel_first[i];
+        const vrad_dface& f = L.faces[i];
+        if (count == 0 || f.lightofs < 0) continue;
+        if (f.lightofs < 4 || (int64_t)f.lightofs + count * 4 > lump_bytes) { vrad::set_error("vrad_bsp_pack_lighting: face %d (%lld luxels at %d) does not fit the %lld-byte lump", i, (long long)count, f.lightofs, (long long)lump_bytes); return VRAD_E_INVALID; }
+        std::memcpy(lump_out + f.lightofs, colors + luxel_first[i], (size_t)count * 4);
+        // average colour of the flat block (the first (w+1)(h+1) samples), stored before the samples
+        const int64_t flat = face_is_bumped(L, f) ? count / 4 : count;
+        float sum[3] = {0, 0, 0};
+        for (int64_t k = 0; k < flat; k++) {
+            const vrad_color_rgbexp32& c = colors[luxel_first[i] + k];
+            float r, g, b;
+            vrad::unpack_rgbexp32({c.r, c.g, c.b, c.exponent}, r, g, b);
+            sum[0] += r; sum[1] += g; sum[2] += b;
+        }
+        const float inv = 1.0f / (float)flat;
+        const vrad::RgbExp avg = vrad::pack_rgbexp32(sum[0] * inv, sum[1] * inv, sum[2] * inv);
+        uint8_t* a = lump_out + f.lightofs - 4;
+        a[0] = avg.r; a[1] = avg.g; a[2] = avg.b; a[3] = (uint8_t)avg.e;
+    }
+    return VRAD_OK;
+}
