@@ -207,6 +207,16 @@ int  vrad_color_from_rgbexp32(int64_t n, const vrad_color_rgbexp32* in, float* r
 /* K5 -- final light per luxel on the device (upstream FinalLightFace, UNCITED): out = RGBExp32(direct + indirect), negative
  * components clamped to zero.  indirect3 may be NULL.  Pointers may be host or device memory. */
 int  vrad_lightmap_finalize(vrad_env*, int64_t n, const float* direct3, const float* indirect3, vrad_color_rgbexp32* out);
+/* Which patch lights which luxel: the leaf patch (child1[i] == -1; child1 NULL = all patches are leaves) of the luxel's own face
+ * whose origin is nearest to the sample point; -1 when the face has no patch.  Own rule -- upstream's FinalLightFace filters the
+ * patch lights of a face and its neighbours through a radial kernel (BuildPatchRadial / SampleRadial, UNCITED and not restated);
+ * the nearest-patch lookup is the piecewise-constant form of it.  Host-only. */
+int  vrad_luxel_nearest_patch(int64_t n, const int32_t* luxel_face, const float* pos3, int n_patches, const int32_t* patch_face,
+                              const int32_t* child1, const float* origin3, int32_t* patch_out);
+/* K5 with the bounced light looked up per luxel: out = RGBExp32(direct + patch_total[luxel_patch]) (luxel_patch -1: direct only).
+ * patch_total3 = the N x 3 totals vrad_bounce returns.  Device pointers must be 16-byte aligned. */
+int  vrad_lightmap_finalize_patches(vrad_env*, int64_t n, const float* direct3, const int32_t* luxel_patch, int n_patches,
+                                    const float* patch_total3, vrad_color_rgbexp32* out);
 /* Scatter the packed luxels into the lighting lump laid out by vrad_bsp_layout_lighting (lumps->faces must be the faces_out
  * of that call) and fill each face's average colour from its flat block. */
 int  vrad_bsp_pack_lighting(const vrad_bsp_lumps*, const int64_t* luxel_first, const vrad_color_rgbexp32* colors,

@@ -483,3 +483,49 @@ def test_rgbexp32():
     assert rows[4] == (0, 128, 0, -5)                             # negative and NaN components count as zero
     assert rows[5][0] == 255 and rows[5][3] > 100 and rows[6] == (0, 0, 0, 0) and rows[7] == (128, 0, 0, 1)
     assert np.array_equal(B.color_from_rgbexp32(c[:2]), np.float32([[1, 2, 3], [300, 200, 100]]))
+
+
+# ---- the file-driven bake, host side ------------------------------------------------------------------------------------
+def test_luxel_nearest_patch():
+    rng = np.random.default_rng(9)
+    npatch, n = 60, 500
+    patch_face = rng.integers(0, 5, npatch).astype(np.int32)
+    child1 = np.where(rng.integers(0, 3, npatch) == 0, 1, -1).astype(np.int32)      # a third are interior patches
+    origin = rng.uniform(0, 100, (npatch, 3)).astype(np.float32)
+    lface = rng.integers(-1, 7, n).astype(np.int32)                                 # faces 5, 6 have no patch; -1 is no face
+    pos = rng.uniform(0, 100, (n, 3)).astype(np.float32)
+    got = B.luxel_nearest_patch(lface, pos, patch_face, origin, child1)
+    for l in range(n):
+        cand = [i for i in range(npatch) if patch_face[i] == lface[l] and child1[i] == -1]
+        if not cand:
+            assert got[l] == -1
+            continue
+        d = [float(np.sum((origin[i] - pos[l]).astype(np.float32) ** 2, dtype=np.float32)) for i in cand]
+        assert got[l] in cand and np.isclose(float(np.sum((origin[got[l]] - pos[l]) ** 2)), min(d), rtol=1e-6)
+    assert np.all(B.luxel_nearest_patch(lface, pos, patch_face, origin)[lface == 2] >= 0)      # child1 None: every patch is a leaf
+
+
+def test_bake_prepare_host_pipeline(smap):
+    from vrad_b200 import bake
+    L, meta = smap
+    ents = bake.parse_entities(meta["entities"])
+    assert [e["classname"] for e in ents][:2] == ["worldspawn", "func_brush"] and sum(e["classname"] == "light" for e in ents) == 6
+    cm, co, ca = bake.shadow_casters(ents)
+    assert list(cm) == [1] and np.allclose(co[0], meta["brush_entity"]["origin"]) and np.allclose(ca[0], meta["brush_entity"]["angles"])
+    prep = bake.prepare(L, meta["entities"])
+    t = prep["tree"]
+    N = t["origin"].shape[0]
+    assert prep["tri_ids"].shape[0] == 12 * L.brushes.shape[0] - 2 + 2
+    assert prep["lights"].shape[0] == 6 + 2 and list(prep["lights"]["type"][-2:]) == [3, 5]          # 6 point lights, sun + sky ambient
+    assert prep["refl"].shape == (N, 3) and prep["cluster"].shape == (N,) and prep["cluster"].min() >= 0 and prep["cluster"].max() == 5
+    # a patch's cluster is its room: the room its origin lies in
+    room = (np.clip(t["origin"][:, 0] // 512, 0, 2) * 2 + np.clip(t["origin"][:, 1] // 512, 0, 1)).astype(np.int32)
+    world = prep["face_of_patch"] < L.models[0]["numfaces"]
+    assert np.array_equal(prep["cluster"][world], room[world])
+    assert np.array_equal(prep["pvs"], meta["pvs"])
+    # every luxel found a leaf patch on its own face, within that patch's reach (chop 4 luxels = 64 units -> < 64 away)
+    lp = prep["lux_patch"]
+    assert lp.min() >= 0 and np.all(t["child1"][lp] == -1) and np.array_equal(prep["face_of_patch"][lp], prep["lux_face"])
+    assert np.linalg.norm(t["origin"][lp] - prep["lux_pos"], axis=1).max() < 64.0
+    assert prep["flags"].sum() > 0 and np.all(prep["flags"][prep["face_of_patch"] != np.nonzero(L.texinfo["flags"][L.faces["texinfo"]] & B.SURF_SKY)[0][0]] == 0)
+    assert prep["lump_bytes"] == 4 * prep["lux_pos"].shape[0] + 4 * (np.diff(prep["luxel_first"]) > 0).sum()

@@ -1,0 +1,209 @@
+"""File-driven bake: .bsp in -> lit .bsp out, every step through the C-ABI of libvradcuda.so.
+
+This is the Python mirror of the sequence the reference's tasks run (cmd/tasks/loadbsp/main.go:38-160 ->
+rad.Start, rad/start.go:21-98 -> cmd/tasks/computerad/main.go:5-10 -> cmd/tasks/finish/main.go:8-40), with the reference's stubbed
+or absent stages (tracer, transfers, direct light, bounces, lightmap write-back) replaced by the library:
+
+    load        vrad_bspfile_open / _lumps                       loadBSP, cache.BuildLumpCache
+    geometry    vrad_env_add_bsp, vrad_env_build                 ExtractBrushEntityShadowCasters, addBrushesForRayTrace, SetupAccelerationStructure
+    patches     vrad_bsp_face_patches, vrad_patches_subdivide    patches.MakePatches, SubdividePatches
+    vis         vrad_pvs_from_vis_lump                           lightmap.GetVisCache / DecompressVis
+    lights      vrad_lights_from_entities                        lightmap.CreateDirectLights
+    luxels      vrad_bsp_face_extents / _layout_lighting / _face_luxels
+    K3          vrad_direct_light (luxels, then patch origins -> emit0)
+    K2, K4      vrad_build_transfers, vrad_bounce
+    K5          vrad_luxel_nearest_patch, vrad_lightmap_finalize_patches
+    write       vrad_bsp_pack_lighting, vrad_bspfile_set_lump / _save
+
+`prepare` and `finish` are host-side and GPU-side product code; `light` only needs the Environment call surface, so the GPU
+tests run it a second time on the CPU oracle's environment to check the device stages end to end.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import bspfile as B
+from .environment import lights_from_entities, light_for_string, pvs_from_vis_lump, subdivide_patches
+from .lib import LIGHT_ENTITY_DTYPE, VradError
+
+
+def anorms() -> np.ndarray:
+    """vmath.Anorms (vmath/constants.go:15,21-184): the 162 sky-ambient sample directions."""
+    import os
+    return np.loadtxt(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "anorms.txt"), dtype=np.float32)
+
+
+def parse_entities(text: str) -> list[dict]:
+    """The entity lump as a list of key -> value dicts (`{ "key" "value" ... }` blocks; what vmf.NewReader(...).Read() yields in
+    loadbsp/main.go:176-181).  Later duplicates of a key win, as Entity.ValueForKey's linear search from the list head does."""
+    ents, cur, i, n = [], None, 0, len(text)
+    while i < n:
+        c = text[i]
+        if c == "{":
+            cur = {}; i += 1
+        elif c == "}":
+            if cur is not None:
+                ents.append(cur)
+            cur = None; i += 1
+        elif c == '"':
+            j = text.index('"', i + 1)
+            k0 = text.index('"', j + 1); k1 = text.index('"', k0 + 1)
+            if cur is not None:
+                cur[text[i + 1:j]] = text[k0 + 1:k1]
+            i = k1 + 1
+        else:
+            i += 1
+    return ents
+
+
+def _floats(s: str, n: int):
+    v = [float(x) for x in s.split()[:n]] if s else []
+    return v + [0.0] * (n - len(v))
+
+
+def light_entities(ents: list[dict]) -> np.ndarray:
+    """light / light_spot / light_environment entities -> vrad_light_entity records (the conversions Entity.FloatForKey /
+    VectorForKey / LightForKey do, common/types/entity.go:60-101)."""
+    classes = {"light": 0, "light_spot": 1, "light_environment": 2}
+    by_name = {e.get("targetname"): e for e in ents if e.get("targetname")}
+    out = []
+    for e in ents:
+        if e.get("classname") not in classes:
+            continue
+        r = np.zeros(1, LIGHT_ENTITY_DTYPE)[0]
+        r["classname"] = classes[e["classname"]]
+        r["origin"] = _floats(e.get("origin", ""), 3)
+        for key, ok, dst in (("_light", "light_ok", "light"), ("_ambient", "ambient_ok", "ambient")):
+            try:
+                r[dst] = light_for_string(e[key]); r[ok] = 1
+            except (KeyError, VradError):
+                r[ok] = 0
+        tgt = by_name.get(e.get("target"))
+        if tgt is not None:
+            r["has_target"] = 1; r["target_origin"] = _floats(tgt.get("origin", ""), 3)
+        r["angles"] = _floats(e.get("angles", ""), 3)
+        for key, dst in (("pitch", "pitch"), ("angle", "angle"), ("_inner_cone", "inner_cone"), ("_cone", "cone"), ("_exponent", "exponent"),
+                         ("_fifty_percent_distance", "fifty_percent_distance"), ("_zero_percent_distance", "zero_percent_distance"),
+                         ("_constant_attn", "constant_attn"), ("_linear_attn", "linear_attn"), ("_quadratic_attn", "quadratic_attn"),
+                         ("_distance", "distance")):
+            r[dst] = _floats(e.get(key, ""), 1)[0]
+        r["hardfalloff"] = int(_floats(e.get("_hardfalloff", ""), 1)[0])
+        out.append(r)
+    return np.asarray(out, LIGHT_ENTITY_DTYPE) if out else np.zeros(0, LIGHT_ENTITY_DTYPE)
+
+
+def shadow_casters(ents: list[dict]):
+    """Brush entities with vrad_brush_cast_shadows (ExtractBrushEntityShadowCasters, loadbsp/main.go:186-211): model "*N" -> N."""
+    model, origin, angles = [], [], []
+    for e in ents:
+        if "vrad_brush_cast_shadows" in e and e.get("model", "").startswith("*"):
+            model.append(int(e["model"][1:])); origin.append(_floats(e.get("origin", ""), 3)); angles.append(_floats(e.get("angles", ""), 3))
+    return np.asarray(model, np.int32), np.asarray(origin, np.float32).reshape(-1, 3), np.asarray(angles, np.float32).reshape(-1, 3)
+
+
+def model_origins(L: B.Lumps, ents: list[dict]) -> np.ndarray:
+    """The "origin" key of each brush model's entity (patches.MakePatches, rad/patches/build.go:38-45); the world's is zero."""
+    out = np.zeros((L.models.shape[0], 3), np.float32)
+    for e in ents:
+        m = e.get("model", "")
+        if m.startswith("*") and m[1:].isdigit() and int(m[1:]) < out.shape[0]:
+            out[int(m[1:])] = _floats(e.get("origin", ""), 3)
+    return out
+
+
+def _point_cluster(L: B.Lumps, p) -> int:
+    """trace.PointLeafnum (raytracer/trace/pointleaf.go:8-33) on the host, for the handful of per-model lookups."""
+    node = int(L.models[0]["headnode"])
+    while node >= 0:
+        nd = L.nodes[node]; pl = L.planes[int(nd["planenum"])]
+        t = int(pl["type"])
+        d = (np.float32(p[t]) - pl["dist"]) if t < 3 else (np.float32(np.dot(pl["normal"], np.asarray(p, np.float32))) - pl["dist"])
+        node = int(nd["children"][1 if d < 0 else 0])
+    return int(L.leafs[-1 - node]["cluster"])
+
+
+def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float = 4.0) -> dict:
+    """Everything the device stages take, from the lumps (host code in the library; no GPU needed)."""
+    ents = parse_entities(entity_text)
+    cm, co, ca = shadow_casters(ents)
+    tri_ids, tri_verts = B.raytrace_triangles(L, cm, co, ca)
+    origins = model_origins(L, ents)
+    fp = B.face_patches(L, origins, max_chop)
+    tree = subdivide_patches(fp["faces"], fp["points"], min_chop=min_chop)
+    face_of_patch = fp["face_number"][tree["face"]]                       # face lump index of every patch
+    # cluster of a face = cluster of the leaf that lists it (leaffaces); faces of brush models: the leaf their model origin is in
+    n_faces = L.faces.shape[0]
+    face_cluster = np.full(n_faces, -1, np.int32)
+    for lf in L.leafs:
+        for k in range(int(lf["numleaffaces"])):
+            f = int(L.leaffaces[int(lf["firstleafface"]) + k])
+            if face_cluster[f] < 0:
+                face_cluster[f] = lf["cluster"]
+    for m in range(1, L.models.shape[0]):
+        mod = L.models[m]
+        centre = origins[m] + 0.5 * (mod["mins"] + mod["maxs"])
+        face_cluster[int(mod["firstface"]):int(mod["firstface"]) + int(mod["numfaces"])] = _point_cluster(L, centre)
+    nc = L.n_clusters
+    pvs = None
+    if nc:
+        ofs = np.frombuffer(L.visdata[4:4 + 8 * nc].tobytes(), "<i4").reshape(nc, 2)
+        pvs = pvs_from_vis_lump(nc, ofs, L.visdata.tobytes())
+    mins, size, oversize = B.face_extents(L)
+    faces_lit, luxel_first, lump_bytes = B.layout_lighting(L, mins, size)
+    face_origin = np.zeros((n_faces, 3), np.float32)
+    for m in range(L.models.shape[0]):
+        face_origin[int(L.models[m]["firstface"]):int(L.models[m]["firstface"]) + int(L.models[m]["numfaces"])] = origins[m]
+    Llit = L.replace(faces=faces_lit)
+    lux_pos, lux_normal, lux_face = B.face_luxels(Llit, mins, size, luxel_first, face_origin)
+    lux_patch = B.luxel_nearest_patch(lux_face, lux_pos, face_of_patch, tree["origin"], tree["child1"])
+    sky = fp["faces"]["sky"][tree["face"]].astype(np.uint8)
+    return dict(ents=ents, tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
+                cluster=face_cluster[face_of_patch].astype(np.int32), flags=sky, pvs=pvs, lights=lights_from_entities(light_entities(ents)),
+                lumps=Llit, luxel_first=luxel_first, lump_bytes=lump_bytes, lux_pos=lux_pos, lux_normal=lux_normal, lux_face=lux_face,
+                lux_patch=lux_patch, oversize=oversize, face_of_patch=face_of_patch)
+
+
+def light(env, prep: dict, bounces: int = 8, early_out: bool = True) -> dict:
+    """The device stages, on any object with the Environment call surface: geometry + kd build (K1), transfers (K2), direct
+    light on the luxels and on the patches (K3; the patch value is Patch.DirectLight, what the first bounce emits), bounces (K4)."""
+    t = prep["tree"]
+    env.add_triangles(prep["tri_ids"], prep["tri_verts"].reshape(-1, 9), np.zeros(prep["tri_ids"].shape[0], np.uint8))
+    env.setup_acceleration_structure() if hasattr(env, "setup_acceleration_structure") else env.build()
+    env.patches_upload(t["origin"], t["normal"], t["plane_dist"], t["area"], prep["refl"], prep["cluster"], prep["flags"])
+    env.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
+    nnz = env.build_transfers(prep["pvs"])
+    if np.any(prep["lights"]["type"] == 5):                            # EMIT_SKYAMBIENT samples the sky along vmath.Anorms
+        env.set_sky_dirs(anorms())
+    direct = np.asarray(env.direct_light(prep["lux_pos"], prep["lux_normal"], prep["lights"]))
+    lifted = (t["origin"] + t["normal"]).astype(np.float32)            # one unit off the surface, like the luxel samples
+    emit0 = np.asarray(env.direct_light(lifted, t["normal"], prep["lights"]))
+    total, _, done = env.bounce(emit0, bounces, early_out)
+    return dict(nnz=int(nnz), direct=direct, emit0=emit0, total=np.asarray(total), bounces_done=int(done))
+
+
+def finish(env, prep: dict, lit: dict) -> tuple[bytes, np.ndarray]:
+    """K5 on the device + the lighting lump: returns (lump bytes, packed luxel colours)."""
+    colors = B.lightmap_finalize_patches(env, lit["direct"], prep["lux_patch"], lit["total"])
+    return B.pack_lighting(prep["lumps"], prep["luxel_first"], colors, prep["lump_bytes"]), colors
+
+
+def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8) -> dict:
+    """The whole job: read a .bsp, light it on the GPU, write it back with LUMP_LIGHTING and the face lump replaced."""
+    from .environment import Environment
+    f = B.BspFile(path_in)
+    try:
+        L = f.lumps()
+        text = f.get(B.LUMP["ENTITIES"])[0].rstrip(b"\0").decode("utf-8", "replace")
+        prep = prepare(L, text)
+        env = Environment(device)
+        try:
+            lit = light(env, prep, bounces)
+            lump, colors = finish(env, prep, lit)
+        finally:
+            env.close()
+        f.set(B.LUMP["LIGHTING"], lump, version=1)
+        f.set(B.LUMP["FACES"], prep["lumps"].faces)
+        f.save(path_out)
+    finally:
+        f.close()
+    return dict(prep=prep, lit=lit, lump=lump, colors=colors)

@@ -53,7 +53,7 @@ SYMBOLS = [
     "vrad_bsp_rescale_lightmap_vecs", "vrad_bsp_face_extents", "vrad_bsp_make_parents", "vrad_bsp_cluster_table",
     "vrad_bsp_vis_for_light_environment", "vrad_bsp_pair_edges", "vrad_bsp_save_vertex_normals", "vrad_bsp_phong_normals",
     "vrad_bsp_layout_lighting", "vrad_bsp_face_luxels", "vrad_color_to_rgbexp32", "vrad_color_from_rgbexp32",
-    "vrad_lightmap_finalize", "vrad_bsp_pack_lighting",
+    "vrad_lightmap_finalize", "vrad_bsp_pack_lighting", "vrad_luxel_nearest_patch", "vrad_lightmap_finalize_patches",
 ]
 
 
@@ -320,6 +320,26 @@ def lightmap_finalize(env, direct, indirect=None) -> np.ndarray:
     i = None if indirect is None else np.ascontiguousarray(indirect, np.float32).reshape(-1, 3)
     out = np.zeros(d.shape[0], RGBEXP32)
     _check(_lib.load().vrad_lightmap_finalize(env._h, C.c_int64(d.shape[0]), _ptr(d), _ptr(i), _ptr(out)), "vrad_lightmap_finalize")
+    return out
+
+
+def luxel_nearest_patch(luxel_face, pos, patch_face, origin, child1=None) -> np.ndarray:
+    lf = np.ascontiguousarray(luxel_face, np.int32); p = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    pf = np.ascontiguousarray(patch_face, np.int32); o = np.ascontiguousarray(origin, np.float32).reshape(-1, 3)
+    c1 = None if child1 is None else np.ascontiguousarray(child1, np.int32)
+    out = np.zeros(lf.shape[0], np.int32)
+    _check(_lib.load().vrad_luxel_nearest_patch(C.c_int64(lf.shape[0]), _ptr(lf), _ptr(p), C.c_int(pf.shape[0]), _ptr(pf), _ptr(c1), _ptr(o), _ptr(out)),
+           "vrad_luxel_nearest_patch")
+    return out
+
+
+def lightmap_finalize_patches(env, direct, luxel_patch, patch_total) -> np.ndarray:
+    """K5 on the device with the bounced light of each luxel's patch."""
+    d = np.ascontiguousarray(direct, np.float32).reshape(-1, 3); ix = np.ascontiguousarray(luxel_patch, np.int32)
+    t = np.ascontiguousarray(patch_total, np.float32).reshape(-1, 3)
+    out = np.zeros(d.shape[0], RGBEXP32)
+    _check(_lib.load().vrad_lightmap_finalize_patches(env._h, C.c_int64(d.shape[0]), _ptr(d), _ptr(ix), C.c_int(t.shape[0]), _ptr(t), _ptr(out)),
+           "vrad_lightmap_finalize_patches")
     return out
 
 

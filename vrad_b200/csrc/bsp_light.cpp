@@ -317,3 +317,34 @@ extern "C" int vrad_bsp_pack_lighting(const vrad_bsp_lumps* Lp, const int64_t* l
     }
     return VRAD_OK;
 }
+
+extern "C" int vrad_luxel_nearest_patch(int64_t n, const int32_t* luxel_face, const float* pos3, int n_patches, const int32_t* patch_face,
+                                        const int32_t* child1, const float* origin3, int32_t* patch_out) {
+    if (n < 0 || n_patches < 0 || (n && (!luxel_face || !pos3 || !patch_out)) || (n_patches && (!patch_face || !origin3))) {
+        vrad::set_error("vrad_luxel_nearest_patch: bad arguments"); return VRAD_E_INVALID;
+    }
+    int32_t max_face = -1;
+    for (int i = 0; i < n_patches; i++) if (patch_face[i] > max_face) max_face = patch_face[i];
+    // leaf patches per face, CSR, ascending patch index
+    std::vector<int32_t> first((size_t)max_face + 2, 0), list;
+    for (int i = 0; i < n_patches; i++) if (patch_face[i] >= 0 && (!child1 || child1[i] == -1)) first[patch_face[i] + 1]++;
+    for (int f = 0; f <= max_face; f++) first[f + 1] += first[f];
+    list.resize((size_t)first[max_face + 1]);
+    std::vector<int32_t> fill(first.begin(), first.end() - 1);
+    for (int i = 0; i < n_patches; i++) if (patch_face[i] >= 0 && (!child1 || child1[i] == -1)) list[fill[patch_face[i]]++] = i;
+    for (int64_t l = 0; l < n; l++) {
+        const int f = luxel_face[l];
+        int32_t best = -1;
+        float best_d = 0.0f;
+        if (f >= 0 && f <= max_face) {
+            const V3 p = load3(pos3 + 3 * l);
+            for (int32_t k = first[f]; k < first[f + 1]; k++) {
+                const V3 d = sub(load3(origin3 + 3 * (size_t)list[k]), p);
+                const float dd = dot(d, d);
+                if (best < 0 || dd < best_d) { best = list[k]; best_d = dd; }      // the first of equally near patches wins
+            }
+        }
+        patch_out[l] = best;
+    }
+    return VRAD_OK;
+}
