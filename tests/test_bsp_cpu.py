@@ -529,3 +529,23 @@ def test_bake_prepare_host_pipeline(smap):
     assert np.linalg.norm(t["origin"][lp] - prep["lux_pos"], axis=1).max() < 64.0
     assert prep["flags"].sum() > 0 and np.all(prep["flags"][prep["face_of_patch"] != np.nonzero(L.texinfo["flags"][L.faces["texinfo"]] & B.SURF_SKY)[0][0]] == 0)
     assert prep["lump_bytes"] == 4 * prep["lux_pos"].shape[0] + 4 * (np.diff(prep["luxel_first"]) > 0).sum()
+
+
+def test_cpp_driver_reads_the_same_file(smap, tmp_path):
+    """The compiled C++ host mirror (integration/cpp/drive --bsp) goes through the same C-ABI entry points from a .bsp file and
+    arrives at the same counts as the Python mirror -- no GPU involved."""
+    import subprocess
+    from vrad_b200 import bake
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L, meta = smap
+    path = str(tmp_path / "m.bsp")
+    B.write_bsp(path, L, meta)
+    subprocess.run(["make", "-C", os.path.join(root, "integration", "cpp")], check=True, capture_output=True)
+    out = subprocess.run([os.path.join(root, "integration", "cpp", "drive"), "--bsp", path], check=True, capture_output=True, text=True).stdout.split()
+    got = {out[i]: int(out[i + 1]) for i in range(1, len(out), 2)}
+    prep = bake.prepare(L, meta["entities"])
+    t = prep["tree"]
+    assert got == dict(faces=L.faces.shape[0], brushes=L.brushes.shape[0], triangles=prep["tri_ids"].shape[0] - 12, patches=t["origin"].shape[0],
+                       leaves=int((t["child1"] == -1).sum()), luxels=prep["lux_pos"].shape[0], lighting_bytes=prep["lump_bytes"], oversize=0)
+    bad = subprocess.run([os.path.join(root, "integration", "cpp", "drive"), "--bsp", str(tmp_path / "nope.bsp")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "cannot open" in bad.stderr
