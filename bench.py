@@ -475,6 +475,30 @@ def run_graft(args, rank, local_rank, world):
                                      "faces": int(Lm.faces.shape[0]), "triangles": int(res["prep"]["tri_ids"].shape[0]), "patches": int(res["prep"]["tree"]["origin"].shape[0]),
                                      "luxels": int(res["prep"]["lux_pos"].shape[0]), "transfers": res["lit"]["nnz"], "bounces": res["lit"]["bounces_done"],
                                      "wall_seconds": wall, "lighting_lump_bytes": len(res["lump"]), "file_bytes": out_size}
+            # binned-SAH kd build on the device (RTE_FLAGS_FAST_TREE_GENERATION) against the exact host builder, and K1 on both trees
+            kd = {}
+            for name, scn, nseg in (("C1_box_room", s1, 1 << 24), ("C5_outdoor", scenes.outdoor(), 1 << 22)):
+                sa, sb = scenes.shadow_segments(scn, nseg)
+                d_sa, d_sb = torch.from_numpy(sa).to(dev), torch.from_numpy(sb).to(dev)
+                d_bits = torch.empty((nseg + 31) // 32, dtype=torch.int32, device=dev)
+                row = {"triangles": scn.n_tris, "segments": nseg}
+                for kind in ("exact_host", "binned_device"):
+                    ek = Environment(local_rank); ek.add_triangles(scn.tri_ids, scn.tri_verts, scn.tri_flags)
+                    secs = ek.setup_acceleration_structure() if kind == "exact_host" else ek.build_fast()
+                    st = ek.stats()
+                    ek.set_stream(stream); ek.set_async(True)
+                    for _ in range(2):
+                        ek.test_lines(d_sa, d_sb, out=d_bits)
+                    e0.record()
+                    for _ in range(5):
+                        ek.test_lines(d_sa, d_sb, out=d_bits)
+                    e1.record(); torch.cuda.synchronize()
+                    row[kind] = {"build_seconds": secs, "nodes": st["n_nodes"], "index_entries": st["n_idx"], "max_depth": st["max_depth"],
+                                 "segments_per_sec": nseg / (e0.elapsed_time(e1) / 5 * 1e-3), "visible": int(np.unpackbits(d_bits.cpu().numpy().view(np.uint8)).sum())}
+                    ek.close()
+                kd[name] = row
+                del d_sa, d_sb, d_bits
+            bsp_side["kd_build_fast"] = kd
         except Exception as exc:  # informational only: never take the bench line down
             bsp_side = {"error": repr(exc), "partial": bsp_side}
 

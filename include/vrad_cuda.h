@@ -104,6 +104,19 @@ int  vrad_env_add_triangles(vrad_env*, int n, const int32_t* ids, const float* v
  * (RefineNode :238-387, CalculateCostsOfSplit :181-236), ChangeIntoIntersectionFormat
  * (raytracer/cache/optimisedtriangle.go:30-78), upload */
 int  vrad_env_build(vrad_env*);
+/* RTE_FLAGS_FAST_TREE_GENERATION (raytracer/constants.go:5 -- declared by the reference, read nowhere): the binned-SAH builder.
+ * Same cost model, leaf rules, depth limit and packed output as vrad_env_build, split candidates from 32 bins per axis of the
+ * node's box instead of every triSkip-th vertex; built level by level on the device (where = VRAD_BUILD_ON_DEVICE: one thread per
+ * triangle reference / per node, integer atomics and stable scans, so the tree does not depend on scheduling) or with the same
+ * code on the host's cores (VRAD_BUILD_ON_HOST).  The tree differs from vrad_env_build's; closest hits and visibility do not
+ * (ties resolve by triangle index).  The finished tree is validated like an uploaded one before any kernel walks it. */
+#define VRAD_BUILD_ON_DEVICE 0
+#define VRAD_BUILD_ON_HOST   1
+int  vrad_env_build_fast(vrad_env*, int where);
+/* the same builder without an environment (host-only helper; no device needed): arrays in reference layout.  children / split /
+ * tri_index may be NULL to size the buffers (*n_nodes, *n_idx); aabb and max_depth may be NULL. */
+int  vrad_kd_build_binned_host(int n, const float* verts9, int max_nodes, int max_idx, int32_t* children, float* split, int32_t* tri_index,
+                               int* n_nodes, int* n_idx, float aabb[6], int* max_depth);
 /* adopt a tree built elsewhere, in the reference's own layouts (OptimisedKDNode, TriangleIndexList, TriIntersectData) */
 int  vrad_env_upload_tree(vrad_env*, int n_nodes, const int32_t* children, const float* split,
                           int n_idx, const int32_t* tri_index, int n_tris, const vrad_tri48* tris,

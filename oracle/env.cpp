@@ -48,6 +48,17 @@ int orc_env_export(orc_env* e, int32_t* children, float* split, int32_t* tri_ind
     return 0;
 }
 
+// adopt a foreign tree over the same triangles (reference layout): lets the tests show that what a ray hits does not depend on which
+// valid kd tree is walked.  The triangle records stay the oracle's own.
+int orc_env_replace_tree(orc_env* e, int n_nodes, const int32_t* children, const float* split, int n_idx, const int32_t* tri_index, const float aabb[6]) {
+    if (!e || !e->built || n_nodes <= 0 || !children || !split || (n_idx > 0 && !tri_index) || !aabb) return -1;
+    e->nodes.resize((size_t)n_nodes);
+    for (int i = 0; i < n_nodes; i++) { e->nodes[i].children = children[i]; e->nodes[i].split = split[i]; }
+    e->tri_index.assign(tri_index, tri_index + n_idx);
+    for (int c = 0; c < 3; c++) { e->bmin[c] = aabb[c]; e->bmax[c] = aabb[3 + c]; }
+    return 0;
+}
+
 double orc_env_build_seconds(orc_env* e) { return e ? e->build_seconds : 0.0; }
 
 } // extern "C"

@@ -76,6 +76,7 @@ int  orc_env_add_triangles(orc_env*, int n, const int32_t* ids, const float* ver
 int  orc_env_build(orc_env*);
 int  orc_env_sizes(orc_env*, int* n_nodes, int* n_idx, int* n_tris, int* max_depth, int* n_leaves);
 int  orc_env_export(orc_env*, int32_t* children, float* split, int32_t* tri_index, orc_tri48* tris, float aabb[6]);
+int  orc_env_replace_tree(orc_env*, int n_nodes, const int32_t* children, const float* split, int n_idx, const int32_t* tri_index, const float aabb[6]);
 double orc_env_build_seconds(orc_env*);
 
 /* nearest hit over ALL triangles (ground truth; O(n_tris) per ray) */

@@ -94,6 +94,12 @@ class OracleEnv:
         assert self._l.orc_env_export(self._h, _p(children), _p(split), _p(tri_index), _p(tris), _p(aabb)) == 0
         return {"children": children, "split": split, "tri_index": tri_index, "tris": tris, "aabb": aabb}
 
+    def replace_tree(self, children, split, tri_index, aabb):
+        """Walk a foreign kd tree (reference layout) over the same triangles."""
+        c = np.ascontiguousarray(children, np.int32); s = np.ascontiguousarray(split, np.float32)
+        t = np.ascontiguousarray(tri_index, np.int32); a = np.ascontiguousarray(aabb, np.float32)
+        assert self._l.orc_env_replace_tree(self._h, C.c_int(c.shape[0]), _p(c), _p(s), C.c_int(t.shape[0]), _p(t), _p(a)) == 0
+
     # -- tracing -----------------------------------------------------------
     def _trace(self, fn, o, d, tmax, tmin=None, skip_id=-1, threads=1):
         o = _f32(o); d = _f32(d); tmax = _f32(tmax)

@@ -200,5 +200,7 @@ int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, 
 int launch_test_lines(vrad_env* e, int64_t n, const float* start_soa, const float* stop_soa, int sky_mode, uint32_t* bits);
 int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, int sky_mode, uint32_t* d_bits);
 int upload_triangle_coverage(vrad_env* e);
+struct KdTree;
+int build_kd_tree_binned_device(cudaStream_t stream, const float* verts9, int n, KdTree& out, int* launches, const char** why);
 
 } // namespace vrad

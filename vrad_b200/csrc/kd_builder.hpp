@@ -24,6 +24,11 @@ struct KdTree {
 // depend on the number of host threads used.
 void build_kd_tree(const float* verts9, int n, KdTree& out);
 
+// Binned-SAH level-by-level builder (kd_fast.cu): same cost model, limits and output layout, candidates from 32 bins per axis.
+// One source, two execution policies: the host's cores, or the device (stream = cudaStream_t as void*).  Returns a vrad_status;
+// *why points at a static message on failure.
+int build_kd_tree_binned_host(const float* verts9, int n, KdTree& out, const char** why);
+
 // Triangle -> 48-byte intersection record (plane + two projected, normalised edge equations).
 void make_intersection_records(const int32_t* ids, const float* verts9, const uint8_t* flags, int n, vrad_tri48* out);
 

@@ -252,6 +252,52 @@ int vrad_env_build(vrad_env* e) {
     return upload_scene(e);
 }
 
+int vrad_env_build_fast(vrad_env* e, int where) {
+    if (!e || (where != VRAD_BUILD_ON_DEVICE && where != VRAD_BUILD_ON_HOST)) { set_error("vrad_env_build_fast: bad arguments"); return VRAD_E_INVALID; }
+    if (e->built) { set_error("vrad_env_build_fast: already built"); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    auto t0 = std::chrono::steady_clock::now();
+    const int n = (int)e->h_ids.size();
+    const char* why = "";
+    int launches = 0;
+    int rc = where == VRAD_BUILD_ON_HOST ? build_kd_tree_binned_host(e->h_verts.data(), n, e->tree, &why)
+                                         : build_kd_tree_binned_device(e->stream, e->h_verts.data(), n, e->tree, &launches, &why);
+    if (rc) { set_error("vrad_env_build_fast: %s", why); return rc; }
+    // the tree came from kernels: check it like a foreign tree before any traversal kernel walks it
+    int leaves = 0;
+    const int depth = validate_kd_tree((int)e->tree.children.size(), e->tree.children.data(), e->tree.split.data(), (int)e->tree.tri_index.size(),
+                                       e->tree.tri_index.data(), n, &leaves, &why);
+    if (depth < 0) { set_error("vrad_env_build_fast: built tree is not valid: %s", why); return VRAD_E_UNSUPPORTED; }
+    e->tree.max_depth = depth; e->tree.n_leaves = leaves;
+    e->h_tris.resize(n);
+    make_intersection_records(e->h_ids.data(), e->h_verts.data(), e->h_flags.data(), n, e->h_tris.data());
+    e->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    e->last_launches = launches;
+    if (e->tree.max_depth >= kStackMax) { set_error("vrad_env_build_fast: tree depth %d exceeds %d", e->tree.max_depth, kStackMax - 1); return VRAD_E_UNSUPPORTED; }
+    return upload_scene(e);
+}
+
+int vrad_kd_build_binned_host(int n, const float* verts9, int max_nodes, int max_idx, int32_t* children, float* split, int32_t* tri_index,
+                              int* n_nodes, int* n_idx, float aabb[6], int* max_depth) {
+    if (n < 0 || (n > 0 && !verts9) || !n_nodes || !n_idx) { set_error("vrad_kd_build_binned_host: bad arguments"); return VRAD_E_INVALID; }
+    KdTree t;
+    const char* why = "";
+    int rc = build_kd_tree_binned_host(verts9, n, t, &why);
+    if (rc) { set_error("vrad_kd_build_binned_host: %s", why); return rc; }
+    int leaves = 0;
+    const int depth = validate_kd_tree((int)t.children.size(), t.children.data(), t.split.data(), (int)t.tri_index.size(), t.tri_index.data(), n, &leaves, &why);
+    if (depth < 0) { set_error("vrad_kd_build_binned_host: built tree is not valid: %s", why); return VRAD_E_UNSUPPORTED; }
+    *n_nodes = (int)t.children.size(); *n_idx = (int)t.tri_index.size();
+    if (max_depth) *max_depth = depth;
+    if (aabb) for (int c = 0; c < 3; c++) { aabb[c] = t.bmin[c]; aabb[3 + c] = t.bmax[c]; }
+    if (children && split && tri_index) {
+        if (*n_nodes > max_nodes || *n_idx > max_idx) { set_error("vrad_kd_build_binned_host: %d nodes / %d indices, room for %d / %d", *n_nodes, *n_idx, max_nodes, max_idx); return VRAD_E_NOMEM; }
+        memcpy(children, t.children.data(), 4 * t.children.size()); memcpy(split, t.split.data(), 4 * t.split.size());
+        if (!t.tri_index.empty()) memcpy(tri_index, t.tri_index.data(), 4 * t.tri_index.size());
+    }
+    return VRAD_OK;
+}
+
 int vrad_env_upload_tree(vrad_env* e, int n_nodes, const int32_t* children, const float* split, int n_idx,
                          const int32_t* tri_index, int n_tris, const vrad_tri48* tris, const float aabb[6]) {
     if (!e || !children || !split || (n_idx > 0 && !tri_index) || (n_tris > 0 && !tris) || !aabb) { set_error("vrad_env_upload_tree: bad arguments"); return VRAD_E_INVALID; }

@@ -119,6 +119,12 @@ class Environment:
         check(self._l.vrad_env_build(self._h))
         return self.stats()["build_seconds"]
 
+    def build_fast(self, on_host: bool = False):
+        """RTE_FLAGS_FAST_TREE_GENERATION (raytracer/constants.go:5): the binned-SAH builder, on the device or on the host's cores."""
+        self._flush_pending()
+        check(self._l.vrad_env_build_fast(self._h, C.c_int(1 if on_host else 0)))
+        return self.stats()["build_seconds"]
+
     def upload_tree(self, children, split, tri_index, tris, aabb):
         children = np.ascontiguousarray(children, np.int32); split = np.ascontiguousarray(split, np.float32)
         tri_index = np.ascontiguousarray(tri_index, np.int32); tris = np.ascontiguousarray(tris)
@@ -454,6 +460,19 @@ def pvs_from_vis_lump(n_clusters: int, byteofs, visdata: bytes):
     out = np.empty((n_clusters, n_clusters), np.uint8)
     check(_lib.load().vrad_pvs_from_vis_lump(C.c_int(n_clusters), ptr(ofs), ptr(buf), C.c_int64(buf.shape[0]), ptr(out)))
     return out
+
+
+def kd_build_binned_host(verts9):
+    """The binned-SAH builder run on the host's cores, without an environment: the tree in reference layout."""
+    v = np.ascontiguousarray(verts9, np.float32).reshape(-1, 9)
+    l = _lib.load()
+    nn, ni, depth = C.c_int(), C.c_int(), C.c_int()
+    aabb = np.zeros(6, np.float32)
+    check(l.vrad_kd_build_binned_host(C.c_int(v.shape[0]), ptr(v), C.c_int(0), C.c_int(0), None, None, None, C.byref(nn), C.byref(ni), ptr(aabb), C.byref(depth)))
+    children = np.zeros(nn.value, np.int32); split = np.zeros(nn.value, np.float32); tri_index = np.zeros(max(ni.value, 1), np.int32)
+    check(l.vrad_kd_build_binned_host(C.c_int(v.shape[0]), ptr(v), C.c_int(nn.value), C.c_int(ni.value), ptr(children), ptr(split), ptr(tri_index),
+                                      C.byref(nn), C.byref(ni), ptr(aabb), C.byref(depth)))
+    return {"children": children, "split": split, "tri_index": tri_index[:ni.value], "aabb": aabb, "max_depth": depth.value}
 
 
 def row_partition(n_rows: int, world: int):

@@ -29,6 +29,7 @@ SYMBOLS = [
     "vrad_decompress_vis", "vrad_pvs_from_vis_lump", "vrad_patches_subdivide", "vrad_patches_set_hierarchy", "vrad_set_light_trace_flags",
     "vrad_light_for_string", "vrad_lights_from_entities", "vrad_lights_from_patches",
     "vrad_bump_normals", "vrad_patches_set_bump", "vrad_bounce_bump_totals",
+    "vrad_env_build_fast", "vrad_kd_build_binned_host",
 ]
 
 # == vrad_face_patch in include/vrad_cuda.h
