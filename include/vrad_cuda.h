@@ -109,7 +109,8 @@ int  vrad_env_build(vrad_env*);
  * node's box instead of every triSkip-th vertex; built level by level on the device (where = VRAD_BUILD_ON_DEVICE: one thread per
  * triangle reference / per node, integer atomics and stable scans, so the tree does not depend on scheduling) or with the same
  * code on the host's cores (VRAD_BUILD_ON_HOST).  The tree differs from vrad_env_build's; closest hits and visibility do not
- * (ties resolve by triangle index).  The finished tree is validated like an uploaded one before any kernel walks it. */
+ * (ties resolve by triangle index), except for rays that graze a triangle edge lying in a split plane, where any kd tracer's answer
+ * depends on the planes.  The finished tree is validated like an uploaded one before any kernel walks it. */
 #define VRAD_BUILD_ON_DEVICE 0
 #define VRAD_BUILD_ON_HOST   1
 int  vrad_env_build_fast(vrad_env*, int where);

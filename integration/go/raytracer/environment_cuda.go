@@ -51,6 +51,13 @@ func newCudaEnv(device int) *cudaEnv {
 
 // AddTriangleWithMaterial (environment.go:45-69) keeps appending to OptimizedTriangleList on the Go
 // side; the triangles are handed to the library in one batch when the tree is built.
+// SetupAccelerationStructureFastCUDA is SetupAccelerationStructure with RTE_FLAGS_FAST_TREE_GENERATION (raytracer/constants.go:5) set in
+// environment.Flags: the binned-SAH tree is built on the GPU from the triangles already handed over with vrad_env_add_triangles /
+// vrad_env_add_bsp (vrad_env_build_fast, include/vrad_cuda.h).
+func (environment *Environment) SetupAccelerationStructureFastCUDA() {
+	check(C.vrad_env_build_fast(environment.cuda.h, C.VRAD_BUILD_ON_DEVICE), "vrad_env_build_fast")
+}
+
 func (environment *Environment) SetupAccelerationStructureCUDA() {
 	n := len(environment.OptimizedTriangleList)
 	ids := make([]C.int32_t, n)

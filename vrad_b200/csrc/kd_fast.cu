@@ -9,8 +9,10 @@
 // depth > MAX_TREE_DEPTH = 21 (constants.go:28), left child gets left + both, right child gets both + right (:381-385), on-plane
 // triangles go right (optimisedtriangle.go:99-101) -- but takes its candidates from 32 equal bins per axis of the node's box and
 // counts triangles by their (clipped) bounding boxes.  Output is the reference's packed layout (OptimisedKDNode, TriangleIndexList),
-// so the traversal kernels run on it unchanged; the closest hit of a ray does not depend on which valid tree is walked
-// (ties resolve by triangle index), so K1 stays bit-exact against the oracle -- that is the parity test.
+// so the traversal kernels run on it unchanged.  Away from knife edges the closest hit of a ray does not depend on which valid
+// tree is walked (ties resolve by triangle index); a ray grazing a triangle edge that lies in a split plane touches a leaf in one
+// point and may or may not visit it.  Parity therefore: K1 on this tree is bit-exact against the oracle's tracer walking THIS tree
+// (OracleEnv.replace_tree), and equal to the exact tree's results except on such rays (tests/test_kd_fast_cpu.py).
 //
 // Formulation: breadth first.  A level holds its active nodes (box, output node index, range of triangle references) and one
 // flat array of references grouped by node.  Per level: (1) thread per reference adds its clipped box to the 3 x 32 start / end
