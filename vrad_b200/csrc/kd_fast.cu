@@ -308,13 +308,23 @@ int build(Exec& ex, const float* verts9_exec /* in the policy's memory */, int n
     int rc = VRAD_OK;
     auto fail = [&](int code, const char* msg) { rc = code; *why = msg; };
 
+    bool have_all = true;
+    for (const void* p : {(const void*)tmin, (const void*)tmax, (const void*)ref_tri[0], (const void*)ref_tri[1], (const void*)ref_slot[0], (const void*)ref_slot[1],
+                          (const void*)flag_l, (const void*)flag_r, (const void*)scan_l, (const void*)scan_r, (const void*)level[0], (const void*)level[1],
+                          (const void*)split, (const void*)is_split, (const void*)leaf_refs, (const void*)child_refs, (const void*)pair_index,
+                          (const void*)leaf_ofs, (const void*)child_ofs, (const void*)out_children, (const void*)out_split, (const void*)out_idx})
+        have_all = have_all && p != nullptr;
+    if (!have_all || ex.err != cudaSuccess) { fail(VRAD_E_NOMEM, "binned kd build: out of memory for the level buffers"); }   // no kernel runs on a null buffer
+
+    if (rc == VRAD_OK) {
     ex.for_each(n, TriBounds{verts9_exec, tmin, tmax});
     ex.for_each(n, InitRefs{ref_tri[0], ref_slot[0]});
     LevelNode root;
     for (int a = 0; a < 3; a++) { root.lo[a] = scene_lo[a]; root.hi[a] = scene_hi[a]; }
     root.node = 0; root.ref_begin = 0; root.ref_end = n; root.depth = 0;
     ex.upload(level[0], &root, sizeof root);
-    int64_t n_active = 1, n_refs = n, n_nodes = 1, n_idx = 0;
+    }
+    int64_t n_active = rc == VRAD_OK ? 1 : 0, n_refs = n, n_nodes = 1, n_idx = 0;
     int cur = 0, max_depth = 0, n_leaves = 0;
     for (int depth = 0; n_active > 0 && rc == VRAD_OK; depth++) {
         if (depth > kMaxDepth + 2) { fail(VRAD_E_UNSUPPORTED, "binned kd build: level loop did not terminate"); break; }
@@ -322,6 +332,7 @@ int build(Exec& ex, const float* verts9_exec /* in the policy's memory */, int n
             ex.free(bin_lo); ex.free(bin_hi);
             bin_cap = n_active * 3 * kBins;
             bin_lo = (int32_t*)A(4 * (size_t)bin_cap); bin_hi = (int32_t*)A(4 * (size_t)bin_cap);
+            if (!bin_lo || !bin_hi || ex.err != cudaSuccess) { fail(VRAD_E_NOMEM, "binned kd build: out of memory for the bins"); break; }
         }
         int32_t totals[3] = {0, 0, 0};                                            // split nodes, leaf references, child references
         for (int force_leaf = 0; force_leaf < 2; force_leaf++) {
