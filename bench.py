@@ -435,72 +435,18 @@ def run_graft(args, rank, local_rank, world):
         except Exception as exc:  # informational only: never take the bench line down
             widened = {"error": repr(exc)}
 
-    # ---------------- BSP side: K5 final light -> RGBExp32 and the file-driven bake; N=1, informational, own guard ----------------
+    # ---------------- BSP side: K5, the file-driven bake, the binned kd build; N=1, informational ----------------
+    # Runs in a child process (tools/bsp_side_bench.py): these paths had not yet run on a GPU when this was written, so nothing they do
+    # -- an exception, a sticky CUDA error, a crash, a hang -- may touch the numbers above.
     bsp_side = None
     if world == 1 and not args.no_large:
         try:
-            import ctypes as C
-            import tempfile
-            from vrad_b200 import bake, bspfile, lib as vlib
-            bsp_side = {}
-            k5 = Environment(local_rank); k5.set_stream(stream); k5.set_async(True)
-            nl = 1 << 24                                             # 16.8 M luxels: 201 MB + 201 MB in, 67 MB out > 126 MB L2
-            d_dir = torch.rand((nl, 3), device=dev) * 400.0
-            d_ind = torch.rand((nl, 3), device=dev) * 100.0
-            d_out = torch.empty(nl, dtype=torch.int32, device=dev)
-            l5 = vlib.load()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for _ in range(3):
-                vlib.check(l5.vrad_lightmap_finalize(k5._h, C.c_int64(nl), vlib.ptr(d_dir), vlib.ptr(d_ind), vlib.ptr(d_out)))
-            e0.record()
-            for _ in range(10):
-                vlib.check(l5.vrad_lightmap_finalize(k5._h, C.c_int64(nl), vlib.ptr(d_dir), vlib.ptr(d_ind), vlib.ptr(d_out)))
-            e1.record(); torch.cuda.synchronize()
-            k5_ms = e0.elapsed_time(e1) / 10
-            sample = slice(0, 1 << 16)
-            want = bspfile.color_to_rgbexp32((d_dir[sample] + d_ind[sample]).cpu().numpy())
-            k5_ok = bool(np.array_equal(d_out[sample].cpu().numpy().view(bspfile.RGBEXP32), want))
-            bsp_side["k5_finalize"] = {"workload": "2^24 luxels, direct + indirect resident in HBM, vrad_lightmap_finalize", "luxels": nl, "ms": k5_ms,
-                                       "luxels_per_sec": nl / (k5_ms * 1e-3), "gbs": 28.0 * nl / (k5_ms * 1e-3) / 1e9,
-                                       "frac_of_hbm_peak": 28.0 * nl / (k5_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_luxel": 28,
-                                       "matches_host_function": k5_ok}
-            k5.close(); del d_dir, d_ind, d_out
-            Lm, meta = bspfile.synthetic_map(4, 3, boxes_per_room=12, sky_rooms=(1, 6), bump_rooms=(0,))
-            with tempfile.TemporaryDirectory() as td:
-                src, dst = os.path.join(td, "in.bsp"), os.path.join(td, "out.bsp")
-                bspfile.write_bsp(src, Lm, meta)
-                t0 = time.perf_counter(); res = bake.bake_file(src, dst, device=local_rank, bounces=8); wall = time.perf_counter() - t0
-                out_size = os.path.getsize(dst)
-            bsp_side["bake_file"] = {"workload": "synthetic BSP v20 map, 4 x 3 rooms, .bsp in -> lit .bsp out through vrad_b200.bake (first call, includes kd build and all host stages)",
-                                     "faces": int(Lm.faces.shape[0]), "triangles": int(res["prep"]["tri_ids"].shape[0]), "patches": int(res["prep"]["tree"]["origin"].shape[0]),
-                                     "luxels": int(res["prep"]["lux_pos"].shape[0]), "transfers": res["lit"]["nnz"], "bounces": res["lit"]["bounces_done"],
-                                     "wall_seconds": wall, "lighting_lump_bytes": len(res["lump"]), "file_bytes": out_size}
-            # binned-SAH kd build on the device (RTE_FLAGS_FAST_TREE_GENERATION) against the exact host builder, and K1 on both trees
-            kd = {}
-            for name, scn, nseg in (("C1_box_room", s1, 1 << 24), ("C5_outdoor", scenes.outdoor(), 1 << 22)):
-                sa, sb = scenes.shadow_segments(scn, nseg)
-                d_sa, d_sb = torch.from_numpy(sa).to(dev), torch.from_numpy(sb).to(dev)
-                d_bits = torch.empty((nseg + 31) // 32, dtype=torch.int32, device=dev)
-                row = {"triangles": scn.n_tris, "segments": nseg}
-                for kind in ("exact_host", "binned_device"):
-                    ek = Environment(local_rank); ek.add_triangles(scn.tri_ids, scn.tri_verts, scn.tri_flags)
-                    secs = ek.setup_acceleration_structure() if kind == "exact_host" else ek.build_fast()
-                    st = ek.stats()
-                    ek.set_stream(stream); ek.set_async(True)
-                    for _ in range(2):
-                        ek.test_lines(d_sa, d_sb, out=d_bits)
-                    e0.record()
-                    for _ in range(5):
-                        ek.test_lines(d_sa, d_sb, out=d_bits)
-                    e1.record(); torch.cuda.synchronize()
-                    row[kind] = {"build_seconds": secs, "nodes": st["n_nodes"], "index_entries": st["n_idx"], "max_depth": st["max_depth"],
-                                 "segments_per_sec": nseg / (e0.elapsed_time(e1) / 5 * 1e-3), "visible": int(np.unpackbits(d_bits.cpu().numpy().view(np.uint8)).sum())}
-                    ek.close()
-                kd[name] = row
-                del d_sa, d_sb, d_bits
-            bsp_side["kd_build_fast"] = kd
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bsp_side_bench.py"), "--device", str(local_rank), "--hbm-peak", str(hbm_peak)],
+                               capture_output=True, text=True, timeout=420)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            bsp_side = json.loads(lines[-1]) if lines else {"error": f"exit {r.returncode}", "stderr": r.stderr[-800:]}
         except Exception as exc:  # informational only: never take the bench line down
-            bsp_side = {"error": repr(exc), "partial": bsp_side}
+            bsp_side = {"error": repr(exc)}
 
     if rank != 0:
         if world > 1:
