@@ -62,6 +62,30 @@ def compute():
     pins["hier_2x1_bounce4_single_thread"] = digest(oh.bounce(emit0, 4, threads=1)[0])
     row, used = pyoracle.decompress_vis(bytes([0xFF, 0x00, 0x03, 0x81]), 40)
     pins["decompress_vis_kat"] = [[int(x) for x in row], used]
+    # BSP side (oracle/bspside.py on the synthetic BSP v20 map of vrad_b200/bspfile.py) and the binned kd builder's tree
+    from oracle import bspside
+    from vrad_b200 import bspfile
+    from vrad_b200.environment import kd_build_binned_host
+    L, meta = bspfile.synthetic_map(3, 2, boxes_per_room=5, sky_rooms=(1,), bump_rooms=(0,))
+    e = meta["brush_entity"]
+    pins["bsp_map_lumps"] = digest(*[L.a[k] for k in sorted(L.a)], L.visdata)
+    ids, verts = bspside.raytrace_triangles(L, [(e["model"], e["origin"], e["angles"])])
+    pins["bsp_raytrace_triangles"] = digest(ids, verts)
+    fp = bspside.face_patches(L)
+    pins["bsp_face_windings"] = digest(np.asarray([q for w in fp["windings"] for q in w], np.float32), np.asarray(fp["plane_dist"], np.float32))
+    mins, size = bspside.face_extents(L)
+    pins["bsp_face_extents"] = digest(mins, size)
+    flags, pvs = bspside.build_vis_for_light_environment(L)
+    pins["bsp_sky_vis"] = [int(x) for x in flags] + list(pvs)
+    normals, nbs = bspside.pair_edges(L, -1.0)
+    pins["bsp_pair_edges_all_smooth"] = digest(np.asarray([v for fn in normals for v in fn], np.float32), np.asarray([x for l in nbs for x in l], np.int32))
+    un, ui = bspside.save_vertex_normals(normals)
+    pins["bsp_vertex_normal_lumps"] = digest(un, ui)
+    pos, nrm, lf = bspside.face_luxels(L, mins, size)
+    pins["bsp_luxels"] = digest(pos, nrm, lf)
+    pins["rgbexp32_kat"] = [list(bspside.pack_rgbexp32(c)) for c in ((1, 2, 3), (300, 200, 100), (255.5, 1, 1), (0, 0, 0), (1e-3, 2e-3, 5e-4))]
+    kt = kd_build_binned_host(s1.tri_verts)
+    pins["s1_binned_kd_tree"] = digest(kt["children"], kt["split"], kt["tri_index"])
     return pins
 
 
