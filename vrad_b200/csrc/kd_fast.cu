@@ -53,6 +53,32 @@ KD_HD void atomic_inc(int32_t* p) {
 #endif
 }
 
+// order-preserving map float -> uint32, so that the largest coordinate of a set is an integer atomicMax (order independent)
+KD_HD uint32_t float_key(float f) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u; std::memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+KD_HD float key_float(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; std::memcpy(&f, &u, 4); return f;
+#endif
+}
+KD_HD void atomic_max_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    uint32_t cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (cur < v && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+#endif
+}
+
 struct LevelNode {
     float lo[3], hi[3];
     int32_t node;                 // index in the output node arrays
@@ -90,15 +116,18 @@ KD_HD int bin_of(float x, float lo, float inv) {
 struct BinRefs {
     const LevelNode* nodes; const int32_t* ref_tri; const int32_t* ref_slot; const float* tmin; const float* tmax;
     int32_t* bin_lo; int32_t* bin_hi;          // [slot][axis][bin]
+    uint32_t* bin_end_max;                     // float_key of the largest (clipped) end coordinate among the references ending in the bin; 0 = none
     KD_HD void operator()(int64_t r) const {
         const int slot = ref_slot[r], t = ref_tri[r];
         const LevelNode& nd = nodes[slot];
         for (int a = 0; a < 3; a++) {
             const float w = nd.hi[a] - nd.lo[a];
             int b0 = 0, b1 = 0;
+            float mx = nd.hi[a];
             if (w > 0.0f) {
                 const float inv = (float)kBins / w;
-                float mn = tmin[3 * (int64_t)t + a], mx = tmax[3 * (int64_t)t + a];
+                float mn = tmin[3 * (int64_t)t + a];
+                mx = tmax[3 * (int64_t)t + a];
                 if (mn < nd.lo[a]) mn = nd.lo[a];
                 if (mx > nd.hi[a]) mx = nd.hi[a];
                 b0 = bin_of(mn, nd.lo[a], inv); b1 = bin_of(mx, nd.lo[a], inv);
@@ -106,6 +135,7 @@ struct BinRefs {
             }
             atomic_inc(&bin_lo[((int64_t)slot * 3 + a) * kBins + b0]);
             atomic_inc(&bin_hi[((int64_t)slot * 3 + a) * kBins + b1]);
+            atomic_max_u32(&bin_end_max[((int64_t)slot * 3 + a) * kBins + b1], float_key(mx));
         }
     }
 };
@@ -116,7 +146,7 @@ KD_HD float box_area(const float lo[3], const float hi[3]) {        // polygon.B
 }
 
 struct ChooseSplit {
-    const LevelNode* nodes; const int32_t* bin_lo; const int32_t* bin_hi; Split* split; int force_leaf;
+    const LevelNode* nodes; const int32_t* bin_lo; const int32_t* bin_hi; const uint32_t* bin_end_max; Split* split; int force_leaf;
     KD_HD void operator()(int64_t slot) const {
         const LevelNode& nd = nodes[slot];
         const int n = nd.ref_end - nd.ref_begin;
@@ -131,10 +161,23 @@ struct ChooseSplit {
                     if (!(w > 0.0f)) continue;
                     const int32_t* bl = bin_lo + ((int64_t)slot * 3 + a) * kBins;
                     const int32_t* bh = bin_hi + ((int64_t)slot * 3 + a) * kBins;
+                    const uint32_t* be = bin_end_max + ((int64_t)slot * 3 + a) * kBins;
                     int n_start = 0, n_end = 0;                      // references starting / ending in bins 0..p
+                    uint32_t end_key = 0;                            // largest end coordinate in bins 0..p
                     for (int p = 0; p < kBins - 1; p++) {
                         n_start += bl[p]; n_end += bh[p];
-                        const float pos = nd.lo[a] + w * ((float)(p + 1) / (float)kBins);
+                        if (be[p] > end_key) end_key = be[p];
+                        // The plane after bin p.  Pulled back from the bin boundary to the largest coordinate at which a reference
+                        // of bins 0..p ends, when that lies in bin p: everything counted as "left only" still is (end <= plane), and
+                        // references that start between there and the boundary stop straddling -- on grid-aligned geometry the
+                        // plane lands on the shared vertex coordinates, as the exact builder's vertex candidates do
+                        // (environment.go:265-307).
+                        float pos = nd.lo[a] + w * ((float)(p + 1) / (float)kBins);
+                        if (bh[p] > 0) {
+                            const float snapped = key_float(end_key);
+                            const float bin_floor = nd.lo[a] + w * ((float)p / (float)kBins);
+                            if (snapped > bin_floor && snapped < pos) pos = snapped;
+                        }
                         if (!(pos > nd.lo[a] && pos < nd.hi[a])) continue;
                         const int n_left_only = n_end;               // end before the plane
                         const int n_right_only = n - n_start;        // start after the plane
@@ -300,7 +343,7 @@ int build(Exec& ex, const float* verts9_exec /* in the policy's memory */, int n
     int32_t* scan_l = (int32_t*)A(4 * (cap_refs + 1)); int32_t* scan_r = (int32_t*)A(4 * (cap_refs + 1));
     LevelNode* level[2] = {(LevelNode*)A(sizeof(LevelNode) * cap_level), (LevelNode*)A(sizeof(LevelNode) * cap_level)};
     Split* split = (Split*)A(sizeof(Split) * cap_level);
-    int32_t* bin_lo = nullptr; int32_t* bin_hi = nullptr; int64_t bin_cap = 0;    // grown per level: 3 * 32 counters per active node
+    int32_t* bin_lo = nullptr; int32_t* bin_hi = nullptr; uint32_t* bin_end_max = nullptr; int64_t bin_cap = 0;    // grown per level: 3 * 32 counters per active node
     int32_t* is_split = (int32_t*)A(4 * cap_level); int32_t* leaf_refs = (int32_t*)A(4 * cap_level); int32_t* child_refs = (int32_t*)A(4 * cap_level);
     int32_t* pair_index = (int32_t*)A(4 * (cap_level + 1)); int32_t* leaf_ofs = (int32_t*)A(4 * (cap_level + 1)); int32_t* child_ofs = (int32_t*)A(4 * (cap_level + 1));
     int32_t* out_children = (int32_t*)A(4 * cap_nodes); float* out_split = (float*)A(4 * cap_nodes);
@@ -329,18 +372,19 @@ int build(Exec& ex, const float* verts9_exec /* in the policy's memory */, int n
     for (int depth = 0; n_active > 0 && rc == VRAD_OK; depth++) {
         if (depth > kMaxDepth + 2) { fail(VRAD_E_UNSUPPORTED, "binned kd build: level loop did not terminate"); break; }
         if (n_active * 3 * kBins > bin_cap) {
-            ex.free(bin_lo); ex.free(bin_hi);
+            ex.free(bin_lo); ex.free(bin_hi); ex.free(bin_end_max);
             bin_cap = n_active * 3 * kBins;
-            bin_lo = (int32_t*)A(4 * (size_t)bin_cap); bin_hi = (int32_t*)A(4 * (size_t)bin_cap);
-            if (!bin_lo || !bin_hi || ex.err != cudaSuccess) { fail(VRAD_E_NOMEM, "binned kd build: out of memory for the bins"); break; }
+            bin_lo = (int32_t*)A(4 * (size_t)bin_cap); bin_hi = (int32_t*)A(4 * (size_t)bin_cap); bin_end_max = (uint32_t*)A(4 * (size_t)bin_cap);
+            if (!bin_lo || !bin_hi || !bin_end_max || ex.err != cudaSuccess) { fail(VRAD_E_NOMEM, "binned kd build: out of memory for the bins"); break; }
         }
         int32_t totals[3] = {0, 0, 0};                                            // split nodes, leaf references, child references
         for (int force_leaf = 0; force_leaf < 2; force_leaf++) {
             if (!force_leaf) {
                 ex.zero(bin_lo, 4 * (size_t)n_active * 3 * kBins); ex.zero(bin_hi, 4 * (size_t)n_active * 3 * kBins);
-                ex.for_each(n_refs, BinRefs{level[cur], ref_tri[cur], ref_slot[cur], tmin, tmax, bin_lo, bin_hi});
+                ex.zero(bin_end_max, 4 * (size_t)n_active * 3 * kBins);
+                ex.for_each(n_refs, BinRefs{level[cur], ref_tri[cur], ref_slot[cur], tmin, tmax, bin_lo, bin_hi, bin_end_max});
             }
-            ex.for_each(n_active, ChooseSplit{level[cur], bin_lo, bin_hi, split, force_leaf});
+            ex.for_each(n_active, ChooseSplit{level[cur], bin_lo, bin_hi, bin_end_max, split, force_leaf});
             ex.for_each(n_refs, Classify{level[cur], split, ref_tri[cur], ref_slot[cur], tmin, tmax, flag_l, flag_r});
             ex.scan(flag_l, scan_l, n_refs); ex.scan(flag_r, scan_r, n_refs);
             ex.for_each(n_active, NodeCounts{level[cur], split, scan_l, scan_r, is_split, leaf_refs, child_refs});
@@ -372,7 +416,7 @@ int build(Exec& ex, const float* verts9_exec /* in the policy's memory */, int n
         out.max_depth = max_depth; out.n_leaves = n_leaves;
     }
     for (void* p : {(void*)tmin, (void*)tmax, (void*)ref_tri[0], (void*)ref_tri[1], (void*)ref_slot[0], (void*)ref_slot[1], (void*)flag_l, (void*)flag_r,
-                    (void*)scan_l, (void*)scan_r, (void*)level[0], (void*)level[1], (void*)split, (void*)bin_lo, (void*)bin_hi, (void*)is_split,
+                    (void*)scan_l, (void*)scan_r, (void*)level[0], (void*)level[1], (void*)split, (void*)bin_lo, (void*)bin_hi, (void*)bin_end_max, (void*)is_split,
                     (void*)leaf_refs, (void*)child_refs, (void*)pair_index, (void*)leaf_ofs, (void*)child_ofs, (void*)out_children, (void*)out_split, (void*)out_idx})
         ex.free(p);
     return rc;
