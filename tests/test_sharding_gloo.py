@@ -156,3 +156,47 @@ def test_collect_rows_weights():
     v = np.zeros((5, 3), np.float32); v[2:] = [[8, 8, 8], [2, 2, 2], [5, 5, 5]]
     sharding.apply_collect(v, ids, ptr, leaf, wt)
     assert np.allclose(v[1], 3.0) and np.allclose(v[0], 0.75 * 3 + 0.25 * 8)
+
+
+# ---- the file-driven bake with luxels and patch origins sharded over ranks (vrad_b200/bake.py) -----------------------------------
+def _bake_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pyoracle
+    from vrad_b200 import bake, bspfile
+    L, meta = bspfile.synthetic_map(2, 1, boxes_per_room=3, sky_rooms=(1,))
+    prep = bake.prepare(L, meta["entities"])
+    lit = bake.light(pyoracle.OracleEnv(), prep, bounces=3, rank=rank, world=world)     # K3 ranges per rank, all-gathered over gloo
+    # the K5 leg's exchange (packed colours as int32 blocks of uneven length), with the host pack function standing in for the kernel
+    parts = sharding.range_partition(lit["direct"].shape[0], world)
+    a, b = parts[rank]
+    ind = np.where(prep["lux_patch"][a:b, None] >= 0, lit["total"][np.maximum(prep["lux_patch"][a:b], 0)], np.float32(0)).astype(np.float32)
+    mine = bspfile.color_to_rgbexp32(lit["direct"][a:b] + ind)
+    colors = bake.all_gather_blocks(mine.view(np.int32), parts, rank).view(bspfile.RGBEXP32)
+    if rank == 0:
+        q.put((lit["direct"], lit["emit0"], lit["total"], colors))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_bake_equals_single_process(world):
+    from oracle import pyoracle
+    from vrad_b200 import bake, bspfile
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_bake_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    direct, emit0, total, colors = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    L, meta = bspfile.synthetic_map(2, 1, boxes_per_room=3, sky_rooms=(1,))
+    prep = bake.prepare(L, meta["entities"])
+    ref = bake.light(pyoracle.OracleEnv(), prep, bounces=3)
+    # luxels and patch origins are independent work items: sharding them changes nothing, bit for bit
+    assert np.array_equal(direct, ref["direct"]) and np.array_equal(emit0, ref["emit0"]) and np.array_equal(total, ref["total"])
+    ind = np.where(prep["lux_patch"][:, None] >= 0, ref["total"][np.maximum(prep["lux_patch"], 0)], np.float32(0)).astype(np.float32)
+    assert np.array_equal(colors, bspfile.color_to_rgbexp32(ref["direct"] + ind))
+    assert direct.shape[0] % world != 0 or world == 2                         # uneven blocks are part of the case (world 3)

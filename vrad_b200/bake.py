@@ -163,9 +163,29 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
                 lux_patch=lux_patch, oversize=oversize, face_of_patch=face_of_patch)
 
 
-def light(env, prep: dict, bounces: int = 8, early_out: bool = True) -> dict:
+def all_gather_blocks(local: np.ndarray, parts, rank: int, device=None) -> np.ndarray:
+    """Concatenation over ranks of the contiguous blocks `parts` (range_partition), each rank holding `local` = its own block.
+    torch.distributed.all_gather wants equal shapes, so blocks travel padded to the largest one.  device: None (gloo, host tensors)
+    or a CUDA device (nccl)."""
+    import torch
+    import torch.distributed as dist
+    width = max(b - a for a, b in parts)
+    mine = torch.zeros((width,) + local.shape[1:], dtype=torch.from_numpy(local[:0].copy()).dtype)
+    mine[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local))
+    if device is not None:
+        mine = mine.to(device)
+    bufs = [torch.empty_like(mine) for _ in parts]
+    dist.all_gather(bufs, mine)
+    return np.concatenate([bufs[r][: b - a].cpu().numpy() for r, (a, b) in enumerate(parts)], axis=0)
+
+
+def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int = 0, world: int = 1, device=None) -> dict:
     """The device stages, on any object with the Environment call surface: geometry + kd build (K1), transfers (K2), direct
-    light on the luxels and on the patches (K3; the patch value is Patch.DirectLight, what the first bounce emits), bounces (K4)."""
+    light on the luxels and on the patches (K3; the patch value is Patch.DirectLight, what the first bounce emits), bounces (K4).
+    world > 1 (one process per GPU, torch.distributed initialised): luxels and patch origins are independent work items, each
+    rank lights its contiguous range (sharding.range_partition) and the blocks are all-gathered; the transfer rows and the
+    per-bounce radiance exchange are sharded inside the environment itself (vrad_config.rank / world, vrad_comm_init)."""
+    from .sharding import range_partition
     t = prep["tree"]
     env.add_triangles(prep["tri_ids"], prep["tri_verts"].reshape(-1, 9), np.zeros(prep["tri_ids"].shape[0], np.uint8))
     env.setup_acceleration_structure() if hasattr(env, "setup_acceleration_structure") else env.build()
@@ -174,36 +194,59 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True) -> dict:
     nnz = env.build_transfers(prep["pvs"])
     if np.any(prep["lights"]["type"] == 5):                            # EMIT_SKYAMBIENT samples the sky along vmath.Anorms
         env.set_sky_dirs(anorms())
-    direct = np.asarray(env.direct_light(prep["lux_pos"], prep["lux_normal"], prep["lights"]))
     lifted = (t["origin"] + t["normal"]).astype(np.float32)            # one unit off the surface, like the luxel samples
-    emit0 = np.asarray(env.direct_light(lifted, t["normal"], prep["lights"]))
+
+    def lit_points(pos, nrm):
+        if world == 1:
+            return np.asarray(env.direct_light(pos, nrm, prep["lights"]))
+        parts = range_partition(pos.shape[0], world)
+        a, b = parts[rank]
+        mine = np.asarray(env.direct_light(pos[a:b], nrm[a:b], prep["lights"])) if b > a else np.zeros((0, 3), np.float32)
+        return all_gather_blocks(mine, parts, rank, device)
+    direct = lit_points(prep["lux_pos"], prep["lux_normal"])
+    emit0 = lit_points(lifted, t["normal"])
     total, _, done = env.bounce(emit0, bounces, early_out)
     return dict(nnz=int(nnz), direct=direct, emit0=emit0, total=np.asarray(total), bounces_done=int(done))
 
 
-def finish(env, prep: dict, lit: dict) -> tuple[bytes, np.ndarray]:
-    """K5 on the device + the lighting lump: returns (lump bytes, packed luxel colours)."""
-    colors = B.lightmap_finalize_patches(env, lit["direct"], prep["lux_patch"], lit["total"])
+def finish(env, prep: dict, lit: dict, rank: int = 0, world: int = 1, device=None) -> tuple[bytes, np.ndarray]:
+    """K5 on the device + the lighting lump: returns (lump bytes, packed luxel colours).  world > 1: each rank packs its luxel range."""
+    from .sharding import range_partition
+    if world == 1:
+        colors = B.lightmap_finalize_patches(env, lit["direct"], prep["lux_patch"], lit["total"])
+    else:
+        parts = range_partition(lit["direct"].shape[0], world)
+        a, b = parts[rank]
+        mine = B.lightmap_finalize_patches(env, lit["direct"][a:b], prep["lux_patch"][a:b], lit["total"]) if b > a else np.zeros(0, B.RGBEXP32)
+        colors = all_gather_blocks(mine.view(np.int32), parts, rank, device).view(B.RGBEXP32)
     return B.pack_lighting(prep["lumps"], prep["luxel_first"], colors, prep["lump_bytes"]), colors
 
 
-def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8) -> dict:
-    """The whole job: read a .bsp, light it on the GPU, write it back with LUMP_LIGHTING and the face lump replaced."""
+def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, rank: int = 0, world: int = 1, comm_id: bytes | None = None) -> dict:
+    """The whole job: read a .bsp, light it on the GPU, write it back with LUMP_LIGHTING and the face lump replaced.
+    world > 1: one process per GPU under torch.distributed (nccl); comm_id = the 128 bytes of Environment.comm_unique_id() from rank 0;
+    every rank reads the file and lights its share, rank 0 writes the result."""
     from .environment import Environment
     f = B.BspFile(path_in)
     try:
         L = f.lumps()
         text = f.get(B.LUMP["ENTITIES"])[0].rstrip(b"\0").decode("utf-8", "replace")
         prep = prepare(L, text)
-        env = Environment(device)
+        env = Environment(device, rank, world)
         try:
-            lit = light(env, prep, bounces)
-            lump, colors = finish(env, prep, lit)
+            dev = None
+            if world > 1:
+                import torch
+                dev = torch.device("cuda", device)
+                env.comm_init(comm_id)
+            lit = light(env, prep, bounces, rank=rank, world=world, device=dev)
+            lump, colors = finish(env, prep, lit, rank=rank, world=world, device=dev)
         finally:
             env.close()
-        f.set(B.LUMP["LIGHTING"], lump, version=1)
-        f.set(B.LUMP["FACES"], prep["lumps"].faces)
-        f.save(path_out)
+        if rank == 0:
+            f.set(B.LUMP["LIGHTING"], lump, version=1)
+            f.set(B.LUMP["FACES"], prep["lumps"].faces)
+            f.save(path_out)
     finally:
         f.close()
     return dict(prep=prep, lit=lit, lump=lump, colors=colors)
