@@ -140,6 +140,24 @@ int  vrad_bsp_face_patches(const vrad_bsp_lumps*, const float* model_origins3, f
                            int max_faces, int max_points, int* n_faces_out, int* n_points_out,
                            vrad_face_patch* faces, float* points3, int32_t* face_number, float* reflectivity3,
                            float* base_area, uint8_t* needs_bump, float* scale2);
+/* ---- texture lights (lights.rad) ------------------------------------------------------------ */
+typedef struct { char name[116]; float value[3]; } vrad_texlight;     /* types.TexLight (common/types/texlight.go:5-9); 128 bytes */
+/* lights_rad.Reader.Read + lightForString + forceTextureShadowsOnModel (common/parser/lights-rad/reader.go:19-192): the text of a
+ * lights.rad file -> the texlight table (a later definition of a name overrides an earlier one; at most MAX_TEXLIGHTS = 128) and the
+ * "noshadow" materials / "forcetextureshadow" models, returned as NUL-terminated names back to back in names_out (first the
+ * n_noshadow materials, then the n_forced models; *names_len = bytes used; names_out may be NULL to size).  hdr != 0 keeps "hdr:"
+ * lines and drops "ldr:" lines.  out may be NULL to count. */
+int  vrad_texlights_parse(const char* text, int64_t len, int hdr, int max_out, vrad_texlight* out, int* n_out,
+                          char* names_out, int64_t names_cap, int* n_noshadow, int* n_forced, int64_t* names_len);
+/* patches.BaseLightForFace / LightForTexture (rad/patches/face.go:208-280) for the faces vrad_bsp_face_patches returned (face_number):
+ * the material name of each face (LUMP_TEXDATA_STRING_TABLE / _DATA; cubemap-patched names "maps/<map_name>/<original>_%d_%d_%d" are
+ * reduced to <original>) looked up in the texlight table -> Patch.BaseLight (base_light3_out, zero when the material emits nothing).
+ * faces_inout (may be NULL): emitting faces get has_base_light = 1 and, unless SURF_NOCHOP, may be subdivided (face.go:158-163 sets
+ * SURF_LIGHT on their texinfo).  The result feeds vrad_lights_from_patches. */
+int  vrad_bsp_apply_texlights(const vrad_bsp_lumps*, const int32_t* string_table, int n_strings, const char* string_data, int64_t string_len,
+                              const char* map_name, int n_texlights, const vrad_texlight* texlights,
+                              int n_faces, const int32_t* face_number, vrad_face_patch* faces_inout, float* base_light3_out);
+
 /* rad.Start's luxel-density rescale (rad/start.go:21-64): lightmap vectors longer than luxel_density luxels per unit are
  * shortened to it (in place; no-op for luxel_density >= 1).  Call before vrad_bsp_face_extents, as
  * UpdateAllFaceLightmapExtents (:100-111) does. */

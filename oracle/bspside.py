@@ -594,3 +594,103 @@ def face_luxels(L, mins, size, face_origins=None):
                 pos.append([org[k] + us * l2w0[k] + ut * l2w1[k] + n[k] for k in range(3)])
                 nrm.append(n); faces.append(i)
     return np.asarray(pos, np.float32).reshape(-1, 3), np.asarray(nrm, np.float32).reshape(-1, 3), np.asarray(faces, np.int32)
+
+
+# ---- common/parser/lights-rad: texture lights -----------------------------------------------------------------------------
+def _scan_floats(s, limit=8):
+    """fmt.Sscanf(light, "%e %e ...") into float32: leading numeric tokens, stopping at the first that does not parse"""
+    out = []
+    for tok in s.split()[:limit]:
+        try:
+            out.append(F(float(tok)))
+        except ValueError:
+            break
+    return out
+
+
+def rad_light_for_string(light):
+    """lights_rad.lightForString, reader.go:122-186 (useHDR := true: the second 4-tuple wins when 8 numbers are given).  None = rejected."""
+    v = _scan_floats(light)
+    n = len(v)
+    v = v + [F(0)] * (8 - n)
+    r, g, b, scaler = v[0], v[1], v[2], v[3]
+    if n == 8:
+        r, g, b, scaler = v[4], v[5], v[6], v[7]
+        n = 4
+    if r < 0 or g < 0 or b < 0 or scaler < 0:
+        return None
+    lin = lambda c: F(math.pow(float(c / F(255.0)), 2.2) * 255)
+    if n == 1:
+        x = lin(r)
+        return [x, x, x]
+    if n in (3, 4):
+        out = [lin(r), lin(g), lin(b)]
+        if n == 4:
+            out = [c * (scaler / F(255.0)) for c in out]
+        return out
+    return None
+
+
+def read_lights_rad(text, hdr=False):
+    """lights_rad.Reader.Read, reader.go:19-120 -> (list of (name, value), noshadow materials, forcetextureshadow models).
+    Intent: lines end at newline, empty lines are skipped, "hdr:" / "ldr:" are prefixes."""
+    table, noshadow, forced = [], [], []
+    for line in text.split("\n"):
+        line = line.strip(" \t\r")
+        if not line:
+            continue
+        if line.startswith("hdr:"):
+            if not hdr:
+                continue
+            line = line[4:]
+        if line.startswith("ldr:"):
+            if hdr:
+                continue
+            line = line[4:]
+        parts = line.split(None, 1)
+        if not parts:
+            continue
+        tok, rest = parts[0], (parts[1] if len(parts) > 1 else "")
+        if tok == "noshadow":
+            if rest.split():
+                noshadow.append(rest.split()[0].split(".")[0])
+        elif tok == "forcetextureshadow":
+            if rest.split():
+                name = rest.split()[0]
+                if name.startswith("models/"):
+                    name = name[len("models/"):]
+                if name.endswith(".mdl"):
+                    name = name[:-4]
+                forced.append(name)
+        else:
+            value = rad_light_for_string(rest) if rest.strip() else None
+            if value is None:
+                continue                                          # "ignoring bad texlight"
+            for entry in table:
+                if entry[0] == tok:
+                    entry[1] = value                              # overriding
+                    break
+            else:
+                assert len(table) < 128, "Too many texlights"
+                table.append([tok, value])
+    return table, noshadow, forced
+
+
+def light_for_texture(name, map_name, table):
+    """patches.LightForTexture, rad/patches/face.go:232-280"""
+    prefix = "maps/" + map_name + "/"
+    if map_name and name.startswith(prefix):
+        base = name[len(prefix):]
+        found = True
+        for _ in range(3):
+            us = base.rfind("_")
+            if us == -1:
+                found = False
+                break
+            base = base[:us]
+        if found:
+            name = base
+    for n, value in table:
+        if n == name:
+            return value
+    return [F(0), F(0), F(0)]

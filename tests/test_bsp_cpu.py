@@ -549,3 +549,80 @@ def test_cpp_driver_reads_the_same_file(smap, tmp_path):
                        leaves=int((t["child1"] == -1).sum()), luxels=prep["lux_pos"].shape[0], lighting_bytes=prep["lump_bytes"], oversize=0)
     bad = subprocess.run([os.path.join(root, "integration", "cpp", "drive"), "--bsp", str(tmp_path / "nope.bsp")], capture_output=True, text=True)
     assert bad.returncode == 1 and "cannot open" in bad.stderr
+
+
+# ---- lights.rad -------------------------------------------------------------------------------------------------------------
+LIGHTS_RAD = "\r\n".join([
+    "lights/white001\t255 255 255 200",
+    "",                                                        # the literal reader stops here; the intent is to skip
+    "lights/fluorescentwarm002a 255 240 200 150",
+    "lights/single 128",
+    "lights/rgbonly\t 10 20 30",
+    "hdr:lights/dual 255 255 255 100 255 128 0 800",
+    "ldr:lights/dual 255 255 255 100",
+    "lights/both 255 255 255 100 255 128 0 800",
+    "noshadow tools/toolsnodraw.vmt",
+    "noshadow glass/window01",
+    "forcetextureshadow models/props/fence_d.mdl",
+    "lights/bad -5 10 10 10",
+    "lights/garbage",
+    "lights/white001 255 255 255 400",                         # overrides the first line
+    "metal/box01 200 180 160 50",                              # a material of the synthetic map
+]) + "\r\n"
+
+
+def test_lights_rad_parse():
+    for hdr in (False, True):
+        table, noshadow, forced = B.texlights_parse(LIGHTS_RAD, hdr)
+        otable, onoshadow, oforced = O.read_lights_rad(LIGHTS_RAD, hdr)
+        assert [t["name"].decode() for t in table] == [n for n, _ in otable]
+        assert np.array_equal(_bits(table["value"]), _bits(np.asarray([v for _, v in otable], np.float32)))
+        assert noshadow == onoshadow == ["tools/toolsnodraw", "glass/window01"] and forced == oforced == ["props/fence_d"]
+    table, _, _ = B.texlights_parse(LIGHTS_RAD, False)
+    got = {t["name"].decode(): t["value"] for t in table}
+    assert list(got) == ["lights/white001", "lights/fluorescentwarm002a", "lights/single", "lights/rgbonly", "lights/dual", "lights/both", "metal/box01"]
+    assert np.allclose(got["lights/white001"], 400.0)                                   # white, overridden to brightness 400
+    lin = lambda c: (c / 255.0) ** 2.2 * 255
+    assert np.allclose(got["lights/fluorescentwarm002a"], [lin(255) * 150 / 255, lin(240) * 150 / 255, lin(200) * 150 / 255], rtol=1e-6)
+    assert np.allclose(got["lights/single"], lin(128), rtol=1e-6) and np.allclose(got["lights/rgbonly"], [lin(10), lin(20), lin(30)], rtol=1e-6)
+    assert np.allclose(got["lights/dual"], 100.0)                                       # the ldr: line
+    assert np.allclose(got["lights/both"], [lin(255) * 800 / 255, lin(128) * 800 / 255, 0.0], rtol=1e-6)      # 8 numbers: the second tuple (reader.go:126)
+    hdr_table, _, _ = B.texlights_parse(LIGHTS_RAD, True)
+    hdr_got = {t["name"].decode(): t["value"] for t in hdr_table}
+    assert np.allclose(hdr_got["lights/dual"], [lin(255) * 800 / 255, lin(128) * 800 / 255, 0.0], rtol=1e-6)
+    # an LF-only file parses the same; too many entries are refused (MAX_TEXLIGHTS)
+    t2, _, _ = B.texlights_parse(LIGHTS_RAD.replace("\r\n", "\n"), False)
+    assert np.array_equal(t2, table)
+    with pytest.raises(VradError):
+        B.texlights_parse("\n".join(f"lights/l{i} 255 255 255 {i + 1}" for i in range(129)))
+    assert B.texlights_parse("")[0].shape[0] == 0
+
+
+def test_texlights_give_faces_their_base_light(smap):
+    from vrad_b200.environment import lights_from_patches, subdivide_patches
+    L, meta = smap
+    table, _, _ = B.texlights_parse(LIGHTS_RAD)
+    fp = B.face_patches(L)
+    base, faces = B.apply_texlights(L, meta["string_table"], meta["string_data"], "synth", table, fp["face_number"], fp["faces"])
+    otable, _, _ = O.read_lights_rad(LIGHTS_RAD)
+    names = meta["string_data"].split(b"\0")
+    want = np.asarray([O.light_for_texture(names[int(L.texdata[int(L.texinfo[int(L.faces[fn]["texinfo"])]["texdata"])]["name_id"])].decode(), "synth", otable)
+                       for fn in fp["face_number"]], np.float32)
+    assert np.array_equal(_bits(base), _bits(want))
+    # the occluder boxes use material 2 = "metal/box01": exactly their faces emit
+    is_box = L.texinfo["texdata"][L.faces["texinfo"][fp["face_number"]]] == 2
+    assert is_box.sum() > 0 and np.array_equal(np.any(base != 0, axis=1), is_box) and np.array_equal(faces["has_base_light"] == 1, is_box)
+    assert np.array_equal(faces["no_subdivide"], fp["faces"]["no_subdivide"])            # no NOLIGHT face emits here
+    # a cubemap-patched name resolves to the original material
+    data = meta["string_data"].replace(b"metal/box01", b"maps/synth/metal/box01_12_-40_7")
+    shift = len(b"maps/synth/metal/box01_12_-40_7") - len(b"metal/box01")
+    st = meta["string_table"].copy(); st[3:] += shift
+    base2, _ = B.apply_texlights(L, st, data, "synth", table, fp["face_number"])
+    assert np.array_equal(base2, base)
+    assert not B.apply_texlights(L, st, data, "othermap", table, fp["face_number"])[0].any()
+    # and the patches made from them become surface lights (CreateDirectLights, lights.go:49-82)
+    t = subdivide_patches(faces, fp["points"], min_chop=4.0)
+    leaf = t["child1"] == -1
+    lights = lights_from_patches(t["origin"], t["normal"], base[t["face"]], t["area"], np.repeat(fp["scale"][t["face"]][:, :1], 2, axis=1) * 0 + 1.0,
+                                 fp["base_area"][t["face"]], t["child1"])
+    assert lights.shape[0] == int((leaf & is_box[t["face"]]).sum()) and np.all(lights["type"] == 0)

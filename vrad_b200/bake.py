@@ -23,7 +23,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import bspfile as B
-from .environment import lights_from_entities, light_for_string, pvs_from_vis_lump, subdivide_patches
+from .environment import lights_from_entities, lights_from_patches, light_for_string, pvs_from_vis_lump, subdivide_patches
 from .lib import LIGHT_ENTITY_DTYPE, VradError
 
 
@@ -122,13 +122,20 @@ def _point_cluster(L: B.Lumps, p) -> int:
     return int(L.leafs[-1 - node]["cluster"])
 
 
-def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float = 4.0) -> dict:
-    """Everything the device stages take, from the lumps (host code in the library; no GPU needed)."""
+def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float = 4.0, lights_rad: str | None = None,
+            texdata_strings=None, map_name: str = "") -> dict:
+    """Everything the device stages take, from the lumps (host code in the library; no GPU needed).
+    lights_rad = the text of a lights.rad file, texdata_strings = (LUMP_TEXDATA_STRING_TABLE as int32, LUMP_TEXDATA_STRING_DATA bytes):
+    faces whose material is a texlight get Patch.BaseLight and their leaf patches become EMIT_SURFACE lights (CreateDirectLights)."""
     ents = parse_entities(entity_text)
     cm, co, ca = shadow_casters(ents)
     tri_ids, tri_verts = B.raytrace_triangles(L, cm, co, ca)
     origins = model_origins(L, ents)
     fp = B.face_patches(L, origins, max_chop)
+    base_light = np.zeros((fp["faces"].shape[0], 3), np.float32)
+    if lights_rad is not None and texdata_strings is not None:
+        table, _, _ = B.texlights_parse(lights_rad)
+        base_light, fp["faces"] = B.apply_texlights(L, texdata_strings[0], texdata_strings[1], map_name, table, fp["face_number"], fp["faces"])
     tree = subdivide_patches(fp["faces"], fp["points"], min_chop=min_chop)
     face_of_patch = fp["face_number"][tree["face"]]                       # face lump index of every patch
     # cluster of a face = cluster of the leaf that lists it (leaffaces); faces of brush models: the leaf their model origin is in
@@ -157,8 +164,13 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
     lux_pos, lux_normal, lux_face = B.face_luxels(Llit, mins, size, luxel_first, face_origin)
     lux_patch = B.luxel_nearest_patch(lux_face, lux_pos, face_of_patch, tree["origin"], tree["child1"])
     sky = fp["faces"]["sky"][tree["face"]].astype(np.uint8)
-    return dict(ents=ents, tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
-                cluster=face_cluster[face_of_patch].astype(np.int32), flags=sky, pvs=pvs, lights=lights_from_entities(light_entities(ents)),
+    lights = lights_from_entities(light_entities(ents))
+    if base_light.any():                                              # surface lights first, as CreateDirectLights does (lights.go:49-82, then :90-113)
+        surf = lights_from_patches(tree["origin"], tree["normal"], base_light[tree["face"]], tree["area"], fp["scale"][tree["face"]],
+                                   fp["base_area"][tree["face"]], tree["child1"])
+        lights = np.concatenate([surf, lights])
+    return dict(ents=ents, base_light=base_light[tree["face"]].astype(np.float32), tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
+                cluster=face_cluster[face_of_patch].astype(np.int32), flags=sky, pvs=pvs, lights=lights,
                 lumps=Llit, luxel_first=luxel_first, lump_bytes=lump_bytes, lux_pos=lux_pos, lux_normal=lux_normal, lux_face=lux_face,
                 lux_patch=lux_patch, oversize=oversize, face_of_patch=face_of_patch)
 
@@ -222,7 +234,8 @@ def finish(env, prep: dict, lit: dict, rank: int = 0, world: int = 1, device=Non
     return B.pack_lighting(prep["lumps"], prep["luxel_first"], colors, prep["lump_bytes"]), colors
 
 
-def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, rank: int = 0, world: int = 1, comm_id: bytes | None = None) -> dict:
+def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, rank: int = 0, world: int = 1, comm_id: bytes | None = None,
+              lights_rad_path: str | None = None) -> dict:
     """The whole job: read a .bsp, light it on the GPU, write it back with LUMP_LIGHTING and the face lump replaced.
     world > 1: one process per GPU under torch.distributed (nccl); comm_id = the 128 bytes of Environment.comm_unique_id() from rank 0;
     every rank reads the file and lights its share, rank 0 writes the result."""
@@ -231,7 +244,10 @@ def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, ra
     try:
         L = f.lumps()
         text = f.get(B.LUMP["ENTITIES"])[0].rstrip(b"\0").decode("utf-8", "replace")
-        prep = prepare(L, text)
+        rad = open(lights_rad_path, "r", errors="replace").read() if lights_rad_path else None
+        strings = (np.frombuffer(f.get(B.LUMP["TEXDATA_STRING_TABLE"])[0], "<i4"), f.get(B.LUMP["TEXDATA_STRING_DATA"])[0])
+        import os
+        prep = prepare(L, text, lights_rad=rad, texdata_strings=strings, map_name=os.path.splitext(os.path.basename(path_in))[0])
         env = Environment(device, rank, world)
         try:
             dev = None

@@ -54,6 +54,7 @@ SYMBOLS = [
     "vrad_bsp_vis_for_light_environment", "vrad_bsp_pair_edges", "vrad_bsp_save_vertex_normals", "vrad_bsp_phong_normals",
     "vrad_bsp_layout_lighting", "vrad_bsp_face_luxels", "vrad_color_to_rgbexp32", "vrad_color_from_rgbexp32",
     "vrad_lightmap_finalize", "vrad_bsp_pack_lighting", "vrad_luxel_nearest_patch", "vrad_lightmap_finalize_patches",
+    "vrad_texlights_parse", "vrad_bsp_apply_texlights",
 ]
 
 
@@ -218,6 +219,38 @@ def face_patches(L: Lumps, model_origins=None, max_chop: float = 4.0) -> dict:
                                    _ptr(out["face_number"]), _ptr(out["reflectivity"]), _ptr(out["base_area"]), _ptr(out["needs_bump"]), _ptr(out["scale"])),
            "vrad_bsp_face_patches")
     return out
+
+
+TEXLIGHT = np.dtype([("name", "S116"), ("value", "<f4", 3)])
+assert TEXLIGHT.itemsize == 128
+
+
+def texlights_parse(text: str, hdr: bool = False):
+    """lights.rad text -> (texlight table, noshadow materials, forcetextureshadow models)."""
+    raw = text.encode()
+    l = _lib.load()
+    n, nn, nf, used = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    _check(l.vrad_texlights_parse(raw, C.c_int64(len(raw)), C.c_int(int(hdr)), C.c_int(0), None, C.byref(n), None, C.c_int64(0), C.byref(nn), C.byref(nf), C.byref(used)),
+           "vrad_texlights_parse")
+    table = np.zeros(max(n.value, 1), TEXLIGHT)
+    names = C.create_string_buffer(max(used.value, 1))
+    _check(l.vrad_texlights_parse(raw, C.c_int64(len(raw)), C.c_int(int(hdr)), C.c_int(table.shape[0]), _ptr(table), C.byref(n), names, C.c_int64(used.value),
+                                  C.byref(nn), C.byref(nf), C.byref(used)), "vrad_texlights_parse")
+    parts = names.raw[:used.value].split(b"\0")[:-1] if used.value else []
+    parts = [p.decode() for p in parts]
+    return table[:n.value].copy(), parts[:nn.value], parts[nn.value:nn.value + nf.value]
+
+
+def apply_texlights(L: Lumps, string_table, string_data: bytes, map_name: str, texlights, face_number, faces=None):
+    """BaseLightForFace for the faces of face_patches(): (base_light [n, 3], faces with has_base_light / no_subdivide updated)."""
+    st = np.ascontiguousarray(string_table, np.int32); tl = np.ascontiguousarray(texlights, TEXLIGHT)
+    fnum = np.ascontiguousarray(face_number, np.int32)
+    out = np.zeros((fnum.shape[0], 3), np.float32)
+    fc = None if faces is None else np.ascontiguousarray(faces, FACE_PATCH_DTYPE).copy()
+    _check(_lib.load().vrad_bsp_apply_texlights(L.ref, _ptr(st), C.c_int(st.shape[0]), string_data, C.c_int64(len(string_data)), map_name.encode(),
+                                                C.c_int(tl.shape[0]), _ptr(tl) if tl.shape[0] else None, C.c_int(fnum.shape[0]), _ptr(fnum), _ptr(fc), _ptr(out)),
+           "vrad_bsp_apply_texlights")
+    return out, fc
 
 
 def rescale_lightmap_vecs(texinfo: np.ndarray, luxel_density: float) -> np.ndarray:
