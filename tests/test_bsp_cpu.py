@@ -626,3 +626,36 @@ def test_texlights_give_faces_their_base_light(smap):
     lights = lights_from_patches(t["origin"], t["normal"], base[t["face"]], t["area"], np.repeat(fp["scale"][t["face"]][:, :1], 2, axis=1) * 0 + 1.0,
                                  fp["base_area"][t["face"]], t["child1"])
     assert lights.shape[0] == int((leaf & is_box[t["face"]]).sum()) and np.all(lights["type"] == 0)
+
+
+def test_direct_light_honours_the_light_pvs():
+    """DirectLight.PVS (AllocDLight / SetDLightVis, rad/lightmap/lights.go:118-161; PVSCheck, lightmap.go:413-422): a light reaches only
+    the samples whose cluster its own cluster sees.  Checked on the oracle's environment through the bake's host logic."""
+    from oracle import pyoracle
+    from vrad_b200 import bake
+    L, meta = B.synthetic_map(4, 1, boxes_per_room=3, pvs_radius=1, with_brush_entity=False)
+    # one light per room at door height, in line with the door openings, so that it does shine through two doors in a row
+    ents = "".join('{\n"classname" "light"\n"origin" "%g 256 128"\n"_light" "255 255 255 300"\n}\n' % (512 * r + 200) for r in range(4))
+    prep = bake.prepare(L, ents)
+    assert prep["lights"].shape[0] == 4 and prep["sky_pvs"] is None
+    culled = bake.light(pyoracle.OracleEnv(), prep, bounces=1)
+    full = bake.light(pyoracle.OracleEnv(), prep, bounces=1, use_light_pvs=False)
+    assert np.all(culled["direct"] <= full["direct"]) and np.abs(culled["direct"] - full["direct"]).max() > 1.0     # light does pass two doors in a row
+    # by hand: the samples of room r are lit by the lights of rooms r-1, r, r+1 only
+    o = pyoracle.OracleEnv()
+    o.add_triangles(prep["tri_ids"], prep["tri_verts"].reshape(-1, 9)); o.build()
+    o.bsp_set(prep["bsp"])
+    lux_room = o.cluster_from_point(prep["lux_pos"])                  # ClusterFromPoint of the sample, as upstream's BuildFacelights records it
+    agree = lux_room == meta["face_room"][prep["lux_face"]]           # = the face's room, except for luxels hanging over the face's edge
+    assert agree.mean() > 0.9 and lux_room.min() >= 0
+    want = np.zeros_like(culled["direct"])
+    for r in range(4):
+        sel = np.nonzero(lux_room == r)[0]
+        keep = np.abs(np.arange(4) - r) <= 1                          # light k sits in room k
+        want[sel] = o.direct_light(prep["lux_pos"][sel], prep["lux_normal"][sel], prep["lights"][keep])
+    assert np.array_equal(culled["direct"], want)
+    # a PVS that sees everything changes nothing, bit for bit
+    L2, meta2 = B.synthetic_map(4, 1, boxes_per_room=3, pvs_radius=9, with_brush_entity=False)
+    prep2 = bake.prepare(L2, ents)
+    a = bake.light(pyoracle.OracleEnv(), prep2, bounces=1); b = bake.light(pyoracle.OracleEnv(), prep2, bounces=1, use_light_pvs=False)
+    assert np.array_equal(a["direct"], b["direct"]) and np.array_equal(a["total"], b["total"])

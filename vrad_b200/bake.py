@@ -155,6 +155,8 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
     if nc:
         ofs = np.frombuffer(L.visdata[4:4 + 8 * nc].tobytes(), "<i4").reshape(nc, 2)
         pvs = pvs_from_vis_lump(nc, ofs, L.visdata.tobytes())
+    has_radial = bool(np.any((L.leafs["area_flags"].astype(np.int32) >> 9) & B.LEAF_FLAGS_RADIAL))
+    sky_pvs = None if has_radial else B.vis_for_light_environment(L)[1]       # radial-vis maps: BuildVisForLightEnvironment needs the device
     mins, size, oversize = B.face_extents(L)
     faces_lit, luxel_first, lump_bytes = B.layout_lighting(L, mins, size)
     face_origin = np.zeros((n_faces, 3), np.float32)
@@ -164,12 +166,16 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
     lux_pos, lux_normal, lux_face = B.face_luxels(Llit, mins, size, luxel_first, face_origin)
     lux_patch = B.luxel_nearest_patch(lux_face, lux_pos, face_of_patch, tree["origin"], tree["child1"])
     sky = fp["faces"]["sky"][tree["face"]].astype(np.uint8)
+    from .scenes import Bsp
+    bsp = Bsp(L.nodes["planenum"].astype(np.int32), L.nodes["children"].astype(np.int32), L.planes["normal"].astype(np.float32),
+              L.planes["dist"].astype(np.float32), L.planes["type"].astype(np.int32), L.leafs["cluster"].astype(np.int32),
+              (L.leafs["area_flags"].astype(np.int32) & 0x1ff), L.leafs["mins"].copy(), L.leafs["maxs"].copy(), max(int(L.n_areas), 1))
     lights = lights_from_entities(light_entities(ents))
     if base_light.any():                                              # surface lights first, as CreateDirectLights does (lights.go:49-82, then :90-113)
         surf = lights_from_patches(tree["origin"], tree["normal"], base_light[tree["face"]], tree["area"], fp["scale"][tree["face"]],
                                    fp["base_area"][tree["face"]], tree["child1"])
         lights = np.concatenate([surf, lights])
-    return dict(ents=ents, base_light=base_light[tree["face"]].astype(np.float32), tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
+    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, base_light=base_light[tree["face"]].astype(np.float32), tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
                 cluster=face_cluster[face_of_patch].astype(np.int32), flags=sky, pvs=pvs, lights=lights,
                 lumps=Llit, luxel_first=luxel_first, lump_bytes=lump_bytes, lux_pos=lux_pos, lux_normal=lux_normal, lux_face=lux_face,
                 lux_patch=lux_patch, oversize=oversize, face_of_patch=face_of_patch)
@@ -191,7 +197,7 @@ def all_gather_blocks(local: np.ndarray, parts, rank: int, device=None) -> np.nd
     return np.concatenate([bufs[r][: b - a].cpu().numpy() for r, (a, b) in enumerate(parts)], axis=0)
 
 
-def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int = 0, world: int = 1, device=None) -> dict:
+def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int = 0, world: int = 1, device=None, use_light_pvs: bool = True) -> dict:
     """The device stages, on any object with the Environment call surface: geometry + kd build (K1), transfers (K2), direct
     light on the luxels and on the patches (K3; the patch value is Patch.DirectLight, what the first bounce emits), bounces (K4).
     world > 1 (one process per GPU, torch.distributed initialised): luxels and patch origins are independent work items, each
@@ -208,13 +214,41 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int =
         env.set_sky_dirs(anorms())
     lifted = (t["origin"] + t["normal"]).astype(np.float32)            # one unit off the surface, like the luxel samples
 
+    # DirectLight.PVS (common/types/light.go; AllocDLight + SetDLightVis, rad/lightmap/lights.go:118-161; sky lights: MergeDLightVis,
+    # lightmap.go:399-411): a light only reaches the samples whose cluster is in the PVS of the light's own cluster (PVSCheck,
+    # lightmap.go:413-422: a sample with cluster -1 is lit by everything).  K3 takes one light list for all its luxels, so the samples
+    # go to the device grouped by cluster, each group with the lights that pass.
+    light_sees = None
+    if use_light_pvs and prep["pvs"] is not None and len(prep["lights"]):
+        (env.bsp_upload if hasattr(env, "bsp_upload") else env.bsp_set)(prep["bsp"])
+        nc = prep["pvs"].shape[0]
+        lcl = np.asarray(env.cluster_from_point(np.ascontiguousarray(prep["lights"]["origin"], np.float32)))
+        light_sees = np.ones((len(prep["lights"]), nc), bool)
+        for k, c in enumerate(lcl):
+            if prep["lights"]["type"][k] in (3, 5):                    # sky light / sky ambient: the merged PVS of the sky leafs
+                if prep["sky_pvs"] is not None:
+                    light_sees[k] = np.unpackbits(prep["sky_pvs"], bitorder="little")[:nc].astype(bool)
+            elif 0 <= c < nc:
+                light_sees[k] = prep["pvs"][c] != 0
+
+    def lit_block(pos, nrm):
+        if light_sees is None or pos.shape[0] == 0:
+            return np.asarray(env.direct_light(pos, nrm, prep["lights"])) if pos.shape[0] else np.zeros((0, 3), np.float32)
+        cl = np.asarray(env.cluster_from_point(pos))
+        out = np.zeros((pos.shape[0], 3), np.float32)
+        for c in np.unique(cl):
+            sel = np.nonzero(cl == c)[0]
+            keep = np.ones(len(prep["lights"]), bool) if c < 0 or c >= light_sees.shape[1] else light_sees[:, c]
+            if keep.any():
+                out[sel] = np.asarray(env.direct_light(np.ascontiguousarray(pos[sel]), np.ascontiguousarray(nrm[sel]), prep["lights"][keep]))
+        return out
+
     def lit_points(pos, nrm):
         if world == 1:
-            return np.asarray(env.direct_light(pos, nrm, prep["lights"]))
+            return lit_block(pos, nrm)
         parts = range_partition(pos.shape[0], world)
         a, b = parts[rank]
-        mine = np.asarray(env.direct_light(pos[a:b], nrm[a:b], prep["lights"])) if b > a else np.zeros((0, 3), np.float32)
-        return all_gather_blocks(mine, parts, rank, device)
+        return all_gather_blocks(lit_block(pos[a:b], nrm[a:b]), parts, rank, device)
     direct = lit_points(prep["lux_pos"], prep["lux_normal"])
     emit0 = lit_points(lifted, t["normal"])
     total, _, done = env.bounce(emit0, bounces, early_out)
