@@ -104,6 +104,10 @@ int  vrad_bspfile_get_lump(vrad_bspfile*, int lump, const void** data, int64_t* 
 int  vrad_bspfile_set_lump(vrad_bspfile*, int lump, const void* data, int64_t len, int lump_version);
 int  vrad_bspfile_save(vrad_bspfile*, const char* path);
 void vrad_bspfile_close(vrad_bspfile*);
+/* cache.SetTargetFaces (cmd/tasks/loadbsp/main.go:79-89): which face lump the job lights.  hdr = 0: LUMP_FACES / LUMP_LIGHTING;
+ * hdr != 0: LUMP_FACES_HDR / LUMP_LIGHTING_HDR (an empty HDR face lump is seeded from LUMP_FACES).  vrad_bspfile_lumps views the
+ * chosen lump from then on; the two lump numbers to write the results to come back through the out pointers (may be NULL). */
+int  vrad_bspfile_set_target_faces(vrad_bspfile*, int hdr, int* face_lump_out, int* lighting_lump_out);
 /* typed views of the lumps above; VRAD_E_INVALID when a lump's length is not a multiple of its record size,
  * the leaf lump is not version 1, or an index stored in one lump points outside another. */
 int  vrad_bspfile_lumps(vrad_bspfile*, vrad_bsp_lumps* out);

@@ -59,7 +59,7 @@ def test_bspfile_round_trip(smap, tmp_path):
     for i in range(64):                                           # directory: aligned, in bounds, leaf lump version 1
         ofs, ln, ver, _ = struct.unpack_from("<iii4s", raw, 8 + 16 * i)
         assert ofs % 4 == 0 and ofs + ln <= len(raw) and (ln == 0 or ofs >= 1036)
-        assert ver == (1 if i == B.LUMP["LEAFS"] else 0)
+        assert ver == (1 if i in (B.LUMP["LEAFS"], B.LUMP["FACES"]) else 0)
     f = B.BspFile(path)
     L2 = f.lumps()
     for k in L.a:
@@ -659,3 +659,22 @@ def test_direct_light_honours_the_light_pvs():
     prep2 = bake.prepare(L2, ents)
     a = bake.light(pyoracle.OracleEnv(), prep2, bounces=1); b = bake.light(pyoracle.OracleEnv(), prep2, bounces=1, use_light_pvs=False)
     assert np.array_equal(a["direct"], b["direct"]) and np.array_equal(a["total"], b["total"])
+
+
+def test_target_faces_ldr_and_hdr(smap, tmp_path):
+    """cache.SetTargetFaces (cmd/tasks/loadbsp/main.go:79-89): an HDR job lights LUMP_FACES_HDR (seeded from LUMP_FACES when empty) and
+    writes LUMP_LIGHTING_HDR; the LDR lumps stay as they were."""
+    L, meta = smap
+    path = str(tmp_path / "m.bsp")
+    B.write_bsp(path, L, meta)
+    f = B.BspFile(path)
+    assert f.set_target_faces(False) == (B.LUMP["FACES"], B.LUMP["LIGHTING"])
+    assert f.get(B.LUMP["FACES_HDR"])[0] == b""
+    assert f.set_target_faces(True) == (B.LUMP["FACES_HDR"], B.LUMP["LIGHTING_HDR"])
+    assert f.get(B.LUMP["FACES_HDR"])[0] == L.faces.tobytes()
+    hdr_faces = L.faces.copy(); hdr_faces["lightofs"] = 1234
+    f.set(B.LUMP["FACES_HDR"], hdr_faces)
+    assert np.array_equal(f.lumps().faces, hdr_faces)                 # the views follow the target
+    f.set_target_faces(False)
+    assert np.array_equal(f.lumps().faces, L.faces)
+    f.close()

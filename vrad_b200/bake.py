@@ -123,7 +123,7 @@ def _point_cluster(L: B.Lumps, p) -> int:
 
 
 def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float = 4.0, lights_rad: str | None = None,
-            texdata_strings=None, map_name: str = "") -> dict:
+            texdata_strings=None, map_name: str = "", lights_rad_hdr: bool = False) -> dict:
     """Everything the device stages take, from the lumps (host code in the library; no GPU needed).
     lights_rad = the text of a lights.rad file, texdata_strings = (LUMP_TEXDATA_STRING_TABLE as int32, LUMP_TEXDATA_STRING_DATA bytes):
     faces whose material is a texlight get Patch.BaseLight and their leaf patches become EMIT_SURFACE lights (CreateDirectLights)."""
@@ -134,7 +134,7 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
     fp = B.face_patches(L, origins, max_chop)
     base_light = np.zeros((fp["faces"].shape[0], 3), np.float32)
     if lights_rad is not None and texdata_strings is not None:
-        table, _, _ = B.texlights_parse(lights_rad)
+        table, _, _ = B.texlights_parse(lights_rad, lights_rad_hdr)
         base_light, fp["faces"] = B.apply_texlights(L, texdata_strings[0], texdata_strings[1], map_name, table, fp["face_number"], fp["faces"])
     tree = subdivide_patches(fp["faces"], fp["points"], min_chop=min_chop)
     face_of_patch = fp["face_number"][tree["face"]]                       # face lump index of every patch
@@ -269,19 +269,20 @@ def finish(env, prep: dict, lit: dict, rank: int = 0, world: int = 1, device=Non
 
 
 def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, rank: int = 0, world: int = 1, comm_id: bytes | None = None,
-              lights_rad_path: str | None = None) -> dict:
+              lights_rad_path: str | None = None, hdr: bool = False) -> dict:
     """The whole job: read a .bsp, light it on the GPU, write it back with LUMP_LIGHTING and the face lump replaced.
     world > 1: one process per GPU under torch.distributed (nccl); comm_id = the 128 bytes of Environment.comm_unique_id() from rank 0;
     every rank reads the file and lights its share, rank 0 writes the result."""
     from .environment import Environment
     f = B.BspFile(path_in)
     try:
+        face_lump, lighting_lump = f.set_target_faces(hdr)            # cache.SetTargetFaces (loadbsp/main.go:79-89)
         L = f.lumps()
         text = f.get(B.LUMP["ENTITIES"])[0].rstrip(b"\0").decode("utf-8", "replace")
         rad = open(lights_rad_path, "r", errors="replace").read() if lights_rad_path else None
         strings = (np.frombuffer(f.get(B.LUMP["TEXDATA_STRING_TABLE"])[0], "<i4"), f.get(B.LUMP["TEXDATA_STRING_DATA"])[0])
         import os
-        prep = prepare(L, text, lights_rad=rad, texdata_strings=strings, map_name=os.path.splitext(os.path.basename(path_in))[0])
+        prep = prepare(L, text, lights_rad=rad, lights_rad_hdr=hdr, texdata_strings=strings, map_name=os.path.splitext(os.path.basename(path_in))[0])
         env = Environment(device, rank, world)
         try:
             dev = None
@@ -294,8 +295,8 @@ def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, ra
         finally:
             env.close()
         if rank == 0:
-            f.set(B.LUMP["LIGHTING"], lump, version=1)
-            f.set(B.LUMP["FACES"], prep["lumps"].faces)
+            f.set(lighting_lump, lump, version=1)
+            f.set(face_lump, prep["lumps"].faces, version=1)
             f.save(path_out)
     finally:
         f.close()

@@ -54,7 +54,7 @@ SYMBOLS = [
     "vrad_bsp_vis_for_light_environment", "vrad_bsp_pair_edges", "vrad_bsp_save_vertex_normals", "vrad_bsp_phong_normals",
     "vrad_bsp_layout_lighting", "vrad_bsp_face_luxels", "vrad_color_to_rgbexp32", "vrad_color_from_rgbexp32",
     "vrad_lightmap_finalize", "vrad_bsp_pack_lighting", "vrad_luxel_nearest_patch", "vrad_lightmap_finalize_patches",
-    "vrad_texlights_parse", "vrad_bsp_apply_texlights",
+    "vrad_texlights_parse", "vrad_bsp_apply_texlights", "vrad_bspfile_set_target_faces",
 ]
 
 
@@ -164,6 +164,12 @@ class BspFile:
     def save(self, path: str):
         _check(self._l.vrad_bspfile_save(self._h, path.encode()), "vrad_bspfile_save")
 
+    def set_target_faces(self, hdr: bool):
+        """cache.SetTargetFaces: returns (face lump, lighting lump) the job reads / writes."""
+        a, b = C.c_int(), C.c_int()
+        _check(self._l.vrad_bspfile_set_target_faces(self._h, C.c_int(int(hdr)), C.byref(a), C.byref(b)), "vrad_bspfile_set_target_faces")
+        return a.value, b.value
+
     def lumps(self) -> Lumps:
         """Typed views (validated by the library), copied into numpy arrays."""
         s = _LumpsStruct()
@@ -181,7 +187,7 @@ class BspFile:
     def set_lumps(self, L: Lumps, entities: str = ""):
         for name, lump in (("planes", 1), ("texdata", 2), ("vertexes3", 3), ("nodes", 5), ("texinfo", 6), ("faces", 7), ("edges", 12),
                            ("surfedges", 13), ("models", 14), ("leaffaces", 16), ("leafbrushes", 17), ("brushes", 18), ("brushsides", 19)):
-            self.set(lump, L.a[name])
+            self.set(lump, L.a[name], version=1 if name == "faces" else 0)      # v20 files carry face lump version 1
         self.set(LUMP["LEAFS"], L.a["leafs"], version=1)
         self.set(LUMP["VISIBILITY"], L.visdata)
         self.set(LUMP["AREAS"], np.zeros(2 * L.n_areas, "<i4"))

@@ -24,6 +24,7 @@ struct vrad_bspfile {
     std::vector<uint8_t> lump[VRAD_HEADER_LUMPS];
     int32_t lump_version[VRAD_HEADER_LUMPS] = {};
     uint8_t fourcc[VRAD_HEADER_LUMPS][4] = {};
+    int face_lump = VRAD_LUMP_FACES;       // cache.SetTargetFaces: LUMP_FACES, or LUMP_FACES_HDR for an HDR compile
 };
 
 namespace {
@@ -146,6 +147,22 @@ extern "C" int vrad_bspfile_save(vrad_bspfile* f, const char* path) {
 
 extern "C" void vrad_bspfile_close(vrad_bspfile* f) { delete f; }
 
+extern "C" int vrad_bspfile_set_target_faces(vrad_bspfile* f, int hdr, int* face_lump_out, int* lighting_lump_out) {
+    if (!f) { vrad::set_error("vrad_bspfile_set_target_faces: bad arguments"); return VRAD_E_INVALID; }
+    // loadbsp.Main (cmd/tasks/loadbsp/main.go:79-89): HDR compiles light LUMP_FACES_HDR; when that lump is empty the LDR faces are
+    // taken over (upstream copies dfaces into dfaces_hdr), so the HDR lump is seeded from LUMP_FACES here.
+    if (hdr) {
+        if (f->lump[VRAD_LUMP_FACES_HDR].empty()) {
+            f->lump[VRAD_LUMP_FACES_HDR] = f->lump[VRAD_LUMP_FACES];
+            f->lump_version[VRAD_LUMP_FACES_HDR] = f->lump_version[VRAD_LUMP_FACES];
+        }
+        f->face_lump = VRAD_LUMP_FACES_HDR;
+    } else f->face_lump = VRAD_LUMP_FACES;
+    if (face_lump_out) *face_lump_out = f->face_lump;
+    if (lighting_lump_out) *lighting_lump_out = hdr ? VRAD_LUMP_LIGHTING_HDR : VRAD_LUMP_LIGHTING;
+    return VRAD_OK;
+}
+
 extern "C" int vrad_bspfile_lumps(vrad_bspfile* f, vrad_bsp_lumps* L) {
     if (!f || !L) { vrad::set_error("vrad_bspfile_lumps: bad arguments"); return VRAD_E_INVALID; }
     std::memset(L, 0, sizeof *L);
@@ -159,7 +176,7 @@ extern "C" int vrad_bspfile_lumps(vrad_bspfile* f, vrad_bsp_lumps* L) {
     L->vertexes3 = vx.empty() ? nullptr : reinterpret_cast<const float*>(vx.data());
     int32_t n_area_recs = 0; const uint8_t (*areas)[8] = nullptr;
     if (!view(f, VRAD_LUMP_PLANES, "plane", &L->n_planes, &L->planes) || !view(f, VRAD_LUMP_EDGES, "edge", &L->n_edges, &L->edges) ||
-        !view(f, VRAD_LUMP_SURFEDGES, "surfedge", &L->n_surfedges, &L->surfedges) || !view(f, VRAD_LUMP_FACES, "face", &L->n_faces, &L->faces) ||
+        !view(f, VRAD_LUMP_SURFEDGES, "surfedge", &L->n_surfedges, &L->surfedges) || !view(f, f->face_lump, "face", &L->n_faces, &L->faces) ||
         !view(f, VRAD_LUMP_TEXINFO, "texinfo", &L->n_texinfo, &L->texinfo) || !view(f, VRAD_LUMP_TEXDATA, "texdata", &L->n_texdata, &L->texdata) ||
         !view(f, VRAD_LUMP_MODELS, "model", &L->n_models, &L->models) || !view(f, VRAD_LUMP_NODES, "node", &L->n_nodes, &L->nodes) ||
         !view(f, VRAD_LUMP_LEAFS, "leaf", &L->n_leafs, &L->leafs) || !view(f, VRAD_LUMP_LEAFFACES, "leafface", &L->n_leaffaces, &L->leaffaces) ||
