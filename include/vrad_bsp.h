@@ -112,6 +112,11 @@ int  vrad_bspfile_set_target_faces(vrad_bspfile*, int hdr, int* face_lump_out, i
  * the leaf lump is not version 1, or an index stored in one lump points outside another. */
 int  vrad_bspfile_lumps(vrad_bspfile*, vrad_bsp_lumps* out);
 
+/* The checks vrad_bspfile_lumps runs, for lumps that come from elsewhere (the Go loader's cache.LumpCache): every index one lump
+ * stores into another is in range, counts have data, the node lump is a forest under the models' head nodes.  The functions below
+ * assume lumps that passed. */
+int  vrad_bsp_validate(const vrad_bsp_lumps*);
+
 /* ---- lumps -> K1 triangles ----------------------------------------------------------------- */
 /* addBrushesForRayTrace + addBrushToRaytraceEnvironment + brush.GetBrushRecursive
  * (cmd/tasks/loadbsp/main.go:233-340, cmd/tasks/loadbsp/brush/brush.go:7-36) with polygon.BaseWindingForPlane /

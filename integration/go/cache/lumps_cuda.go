@@ -191,5 +191,8 @@ func BuildCLumps() *CLumps {
 		L.visdata = (*C.uint8_t)(C.CBytes(lc.VisDataRaw))
 		c.bufs = append(c.bufs, unsafe.Pointer(L.visdata))
 	}
+	if rc := C.vrad_bsp_validate(L); rc != 0 { // every cross-lump index, once; the library's input functions assume it passed
+		panic("vrad_bsp_validate: " + C.GoString(C.vrad_last_error()))
+	}
 	return c
 }

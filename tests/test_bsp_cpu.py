@@ -678,3 +678,22 @@ def test_target_faces_ldr_and_hdr(smap, tmp_path):
     f.set_target_faces(False)
     assert np.array_equal(f.lumps().faces, L.faces)
     f.close()
+
+
+def test_lumps_from_elsewhere_are_validated(smap):
+    """vrad_bsp_validate: the checks of vrad_bspfile_lumps for lumps that did not come through the container (the Go loader's cache)."""
+    L, _ = smap
+    L.validate()
+    for name, field, value in (("faces", "planenum", 60000), ("faces", "texinfo", -1), ("texinfo", "texdata", 99), ("brushsides", "planenum", 65535),
+                               ("leafs", "numleaffaces", 60000), ("brushes", "numsides", 100000), ("models", "numfaces", 100000)):
+        arr = L.a[name].copy(); arr[field][0] = value
+        with pytest.raises(VradError):
+            L.replace(**{name: arr}).validate()
+    se = L.surfedges.copy(); se[5] = -(L.edges.shape[0] + 3)
+    with pytest.raises(VradError):
+        L.replace(surfedges=se).validate()
+    nodes = L.nodes.copy(); nodes[2]["children"] = (1, 1)              # a cycle / shared child: GetBrushRecursive would not terminate
+    with pytest.raises(VradError):
+        L.replace(nodes=nodes).validate()
+    with pytest.raises(VradError):
+        L.replace(visdata=np.int32(50).tobytes() + b"\0" * 16).validate()

@@ -54,7 +54,7 @@ SYMBOLS = [
     "vrad_bsp_vis_for_light_environment", "vrad_bsp_pair_edges", "vrad_bsp_save_vertex_normals", "vrad_bsp_phong_normals",
     "vrad_bsp_layout_lighting", "vrad_bsp_face_luxels", "vrad_color_to_rgbexp32", "vrad_color_from_rgbexp32",
     "vrad_lightmap_finalize", "vrad_bsp_pack_lighting", "vrad_luxel_nearest_patch", "vrad_lightmap_finalize_patches",
-    "vrad_texlights_parse", "vrad_bsp_apply_texlights", "vrad_bspfile_set_target_faces",
+    "vrad_texlights_parse", "vrad_bsp_apply_texlights", "vrad_bspfile_set_target_faces", "vrad_bsp_validate",
 ]
 
 
@@ -127,6 +127,10 @@ class Lumps:
     @property
     def ref(self):
         return C.byref(self.s)
+
+    def validate(self):
+        """vrad_bsp_validate: raises VradError when an index stored in one lump points outside another."""
+        _check(_lib.load().vrad_bsp_validate(self.ref), "vrad_bsp_validate")
 
 
 class BspFile:

@@ -147,47 +147,15 @@ extern "C" int vrad_bspfile_save(vrad_bspfile* f, const char* path) {
 
 extern "C" void vrad_bspfile_close(vrad_bspfile* f) { delete f; }
 
-extern "C" int vrad_bspfile_set_target_faces(vrad_bspfile* f, int hdr, int* face_lump_out, int* lighting_lump_out) {
-    if (!f) { vrad::set_error("vrad_bspfile_set_target_faces: bad arguments"); return VRAD_E_INVALID; }
-    // loadbsp.Main (cmd/tasks/loadbsp/main.go:79-89): HDR compiles light LUMP_FACES_HDR; when that lump is empty the LDR faces are
-    // taken over (upstream copies dfaces into dfaces_hdr), so the HDR lump is seeded from LUMP_FACES here.
-    if (hdr) {
-        if (f->lump[VRAD_LUMP_FACES_HDR].empty()) {
-            f->lump[VRAD_LUMP_FACES_HDR] = f->lump[VRAD_LUMP_FACES];
-            f->lump_version[VRAD_LUMP_FACES_HDR] = f->lump_version[VRAD_LUMP_FACES];
-        }
-        f->face_lump = VRAD_LUMP_FACES_HDR;
-    } else f->face_lump = VRAD_LUMP_FACES;
-    if (face_lump_out) *face_lump_out = f->face_lump;
-    if (lighting_lump_out) *lighting_lump_out = hdr ? VRAD_LUMP_LIGHTING_HDR : VRAD_LUMP_LIGHTING;
-    return VRAD_OK;
-}
-
-extern "C" int vrad_bspfile_lumps(vrad_bspfile* f, vrad_bsp_lumps* L) {
-    if (!f || !L) { vrad::set_error("vrad_bspfile_lumps: bad arguments"); return VRAD_E_INVALID; }
-    std::memset(L, 0, sizeof *L);
-    if (!f->lump[VRAD_LUMP_LEAFS].empty() && f->lump_version[VRAD_LUMP_LEAFS] != 1) {
-        vrad::set_error("bsp: leaf lump version %d (only version 1, 32-byte leafs, is read)", f->lump_version[VRAD_LUMP_LEAFS]);
-        return VRAD_E_UNSUPPORTED;
+// cross-lump indices: everything the input code (bsp_input.cpp, bsp_light.cpp, texlights.cpp) dereferences is checked once, here
+extern "C" int vrad_bsp_validate(const vrad_bsp_lumps* L) {
+    if (!L) { vrad::set_error("vrad_bsp_validate: bad arguments"); return VRAD_E_INVALID; }
+    if ((L->n_planes && !L->planes) || (L->n_vertexes && !L->vertexes3) || (L->n_edges && !L->edges) || (L->n_surfedges && !L->surfedges) ||
+        (L->n_faces && !L->faces) || (L->n_texinfo && !L->texinfo) || (L->n_texdata && !L->texdata) || (L->n_models && !L->models) ||
+        (L->n_nodes && !L->nodes) || (L->n_leafs && !L->leafs) || (L->n_leaffaces && !L->leaffaces) || (L->n_leafbrushes && !L->leafbrushes) ||
+        (L->n_brushes && !L->brushes) || (L->n_brushsides && !L->brushsides) || (L->vis_len && !L->visdata)) {
+        vrad::set_error("bsp: a lump has a count but no data"); return VRAD_E_INVALID;
     }
-    const std::vector<uint8_t>& vx = f->lump[VRAD_LUMP_VERTEXES];
-    if (vx.size() % 12) { vrad::set_error("bsp: vertex lump is %zu bytes, not a multiple of 12", vx.size()); return VRAD_E_INVALID; }
-    L->n_vertexes = (int32_t)(vx.size() / 12);
-    L->vertexes3 = vx.empty() ? nullptr : reinterpret_cast<const float*>(vx.data());
-    int32_t n_area_recs = 0; const uint8_t (*areas)[8] = nullptr;
-    if (!view(f, VRAD_LUMP_PLANES, "plane", &L->n_planes, &L->planes) || !view(f, VRAD_LUMP_EDGES, "edge", &L->n_edges, &L->edges) ||
-        !view(f, VRAD_LUMP_SURFEDGES, "surfedge", &L->n_surfedges, &L->surfedges) || !view(f, f->face_lump, "face", &L->n_faces, &L->faces) ||
-        !view(f, VRAD_LUMP_TEXINFO, "texinfo", &L->n_texinfo, &L->texinfo) || !view(f, VRAD_LUMP_TEXDATA, "texdata", &L->n_texdata, &L->texdata) ||
-        !view(f, VRAD_LUMP_MODELS, "model", &L->n_models, &L->models) || !view(f, VRAD_LUMP_NODES, "node", &L->n_nodes, &L->nodes) ||
-        !view(f, VRAD_LUMP_LEAFS, "leaf", &L->n_leafs, &L->leafs) || !view(f, VRAD_LUMP_LEAFFACES, "leafface", &L->n_leaffaces, &L->leaffaces) ||
-        !view(f, VRAD_LUMP_LEAFBRUSHES, "leafbrush", &L->n_leafbrushes, &L->leafbrushes) || !view(f, VRAD_LUMP_BRUSHES, "brush", &L->n_brushes, &L->brushes) ||
-        !view(f, VRAD_LUMP_BRUSHSIDES, "brushside", &L->n_brushsides, &L->brushsides) || !view(f, VRAD_LUMP_AREAS, "area", &n_area_recs, &areas))
-        return VRAD_E_INVALID;
-    L->n_areas = n_area_recs;
-    L->vis_len = (int64_t)f->lump[VRAD_LUMP_VISIBILITY].size();
-    L->visdata = f->lump[VRAD_LUMP_VISIBILITY].empty() ? nullptr : f->lump[VRAD_LUMP_VISIBILITY].data();
-
-    // cross-lump indices: everything the input code dereferences is checked once, here
     auto bad = [](const char* what, int i, long v, long n) { vrad::set_error("bsp: %s %d refers to %ld, outside [0,%ld)", what, i, v, n); return VRAD_E_INVALID; };
     for (int i = 0; i < L->n_faces; i++) {
         const vrad_dface& fc = L->faces[i];
@@ -237,5 +205,60 @@ extern "C" int vrad_bspfile_lumps(vrad_bspfile* f, vrad_bsp_lumps* L) {
         int32_t nc; std::memcpy(&nc, L->visdata, 4);
         if (nc < 0 || 4 + (int64_t)nc * 8 > L->vis_len) { vrad::set_error("bsp: visibility lump names %d clusters but holds %lld bytes", nc, (long long)L->vis_len); return VRAD_E_INVALID; }
     }
+    // the node lump must be a tree under every model's head node: GetBrushRecursive and MakeParents recurse without a visited set
+    std::vector<uint8_t> seen((size_t)L->n_nodes, 0);
+    for (int m = 0; m < L->n_models; m++) {
+        std::vector<int32_t> stack;
+        if (L->models[m].headnode >= 0) stack.push_back(L->models[m].headnode);
+        while (!stack.empty()) {
+            const int32_t n = stack.back(); stack.pop_back();
+            if (seen[n]) { vrad::set_error("bsp: node %d is reached twice (the node lump is not a forest)", n); return VRAD_E_INVALID; }
+            seen[n] = 1;
+            for (int k = 0; k < 2; k++) if (L->nodes[n].children[k] >= 0) stack.push_back(L->nodes[n].children[k]);
+        }
+    }
     return VRAD_OK;
+}
+
+extern "C" int vrad_bspfile_set_target_faces(vrad_bspfile* f, int hdr, int* face_lump_out, int* lighting_lump_out) {
+    if (!f) { vrad::set_error("vrad_bspfile_set_target_faces: bad arguments"); return VRAD_E_INVALID; }
+    // loadbsp.Main (cmd/tasks/loadbsp/main.go:79-89): HDR compiles light LUMP_FACES_HDR; when that lump is empty the LDR faces are
+    // taken over (upstream copies dfaces into dfaces_hdr), so the HDR lump is seeded from LUMP_FACES here.
+    if (hdr) {
+        if (f->lump[VRAD_LUMP_FACES_HDR].empty()) {
+            f->lump[VRAD_LUMP_FACES_HDR] = f->lump[VRAD_LUMP_FACES];
+            f->lump_version[VRAD_LUMP_FACES_HDR] = f->lump_version[VRAD_LUMP_FACES];
+        }
+        f->face_lump = VRAD_LUMP_FACES_HDR;
+    } else f->face_lump = VRAD_LUMP_FACES;
+    if (face_lump_out) *face_lump_out = f->face_lump;
+    if (lighting_lump_out) *lighting_lump_out = hdr ? VRAD_LUMP_LIGHTING_HDR : VRAD_LUMP_LIGHTING;
+    return VRAD_OK;
+}
+
+extern "C" int vrad_bspfile_lumps(vrad_bspfile* f, vrad_bsp_lumps* L) {
+    if (!f || !L) { vrad::set_error("vrad_bspfile_lumps: bad arguments"); return VRAD_E_INVALID; }
+    std::memset(L, 0, sizeof *L);
+    if (!f->lump[VRAD_LUMP_LEAFS].empty() && f->lump_version[VRAD_LUMP_LEAFS] != 1) {
+        vrad::set_error("bsp: leaf lump version %d (only version 1, 32-byte leafs, is read)", f->lump_version[VRAD_LUMP_LEAFS]);
+        return VRAD_E_UNSUPPORTED;
+    }
+    const std::vector<uint8_t>& vx = f->lump[VRAD_LUMP_VERTEXES];
+    if (vx.size() % 12) { vrad::set_error("bsp: vertex lump is %zu bytes, not a multiple of 12", vx.size()); return VRAD_E_INVALID; }
+    L->n_vertexes = (int32_t)(vx.size() / 12);
+    L->vertexes3 = vx.empty() ? nullptr : reinterpret_cast<const float*>(vx.data());
+    int32_t n_area_recs = 0; const uint8_t (*areas)[8] = nullptr;
+    if (!view(f, VRAD_LUMP_PLANES, "plane", &L->n_planes, &L->planes) || !view(f, VRAD_LUMP_EDGES, "edge", &L->n_edges, &L->edges) ||
+        !view(f, VRAD_LUMP_SURFEDGES, "surfedge", &L->n_surfedges, &L->surfedges) || !view(f, f->face_lump, "face", &L->n_faces, &L->faces) ||
+        !view(f, VRAD_LUMP_TEXINFO, "texinfo", &L->n_texinfo, &L->texinfo) || !view(f, VRAD_LUMP_TEXDATA, "texdata", &L->n_texdata, &L->texdata) ||
+        !view(f, VRAD_LUMP_MODELS, "model", &L->n_models, &L->models) || !view(f, VRAD_LUMP_NODES, "node", &L->n_nodes, &L->nodes) ||
+        !view(f, VRAD_LUMP_LEAFS, "leaf", &L->n_leafs, &L->leafs) || !view(f, VRAD_LUMP_LEAFFACES, "leafface", &L->n_leaffaces, &L->leaffaces) ||
+        !view(f, VRAD_LUMP_LEAFBRUSHES, "leafbrush", &L->n_leafbrushes, &L->leafbrushes) || !view(f, VRAD_LUMP_BRUSHES, "brush", &L->n_brushes, &L->brushes) ||
+        !view(f, VRAD_LUMP_BRUSHSIDES, "brushside", &L->n_brushsides, &L->brushsides) || !view(f, VRAD_LUMP_AREAS, "area", &n_area_recs, &areas))
+        return VRAD_E_INVALID;
+    L->n_areas = n_area_recs;
+    L->vis_len = (int64_t)f->lump[VRAD_LUMP_VISIBILITY].size();
+    L->visdata = f->lump[VRAD_LUMP_VISIBILITY].empty() ? nullptr : f->lump[VRAD_LUMP_VISIBILITY].data();
+
+    return vrad_bsp_validate(L);
 }
