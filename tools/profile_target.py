@@ -1,4 +1,4 @@
-"""Short workload for `ncu --set full` captures: a few K1 and K4 launches at bench sizes."""
+"""Short workload for `ncu --set full` captures: a few launches at bench sizes (k1, k1s3, sky, hier, k5, kdfast, default = K2/K3/K4)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -23,6 +23,29 @@ elif what == "sky":
     ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     out = torch.empty(1 << 23, dtype=torch.float32, device="cuda")
     for _ in range(2): env.test_lines_sky(ta, tb, 3, 7, out=out)
+elif what == "k5":
+    import ctypes as C
+    from vrad_b200 import lib as vlib
+    from vrad_b200.environment import Environment
+    env = Environment()
+    n = 1 << 24
+    d_dir = torch.rand((n, 3), device="cuda") * 400.0; d_ind = torch.rand((n, 3), device="cuda") * 100.0
+    d_idx = torch.randint(0, 200000, (n,), device="cuda", dtype=torch.int32).sort().values      # neighbouring luxels share a patch
+    d_tot = torch.rand((200000, 3), device="cuda") * 100.0
+    d_out = torch.empty(n, dtype=torch.int32, device="cuda")
+    l = vlib.load()
+    for _ in range(3):
+        vlib.check(l.vrad_lightmap_finalize(env._h, C.c_int64(n), vlib.ptr(d_dir), vlib.ptr(d_ind), vlib.ptr(d_out)))
+        vlib.check(l.vrad_lightmap_finalize_patches(env._h, C.c_int64(n), vlib.ptr(d_dir), vlib.ptr(d_idx), C.c_int(200000), vlib.ptr(d_tot), vlib.ptr(d_out)))
+elif what == "kdfast":
+    from vrad_b200.environment import Environment
+    s = scenes.outdoor()
+    env = Environment(); env.add_triangles(s.tri_ids, s.tri_verts, s.tri_flags)
+    print("binned device build seconds", env.build_fast(), env.stats())
+    a, b = scenes.shadow_segments(s, 1 << 22)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.empty((1 << 22) // 32, dtype=torch.int32, device="cuda")
+    for _ in range(2): env.test_lines(ta, tb, out=out)
 elif what == "hier":
     s = scenes.multi_room_hier(nx=12, ny=11); t = s.meta["tree"]; env = environment_from_scene(s)
     env.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
