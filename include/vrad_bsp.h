@@ -240,6 +240,26 @@ int  vrad_lightmap_finalize(vrad_env*, int64_t n, const float* direct3, const fl
  * the nearest-patch lookup is the piecewise-constant form of it.  Host-only. */
 int  vrad_luxel_nearest_patch(int64_t n, const int32_t* luxel_face, const float* pos3, int n_patches, const int32_t* patch_face,
                               const int32_t* child1, const float* origin3, int32_t* patch_out);
+/* Bounced light per luxel by upstream's radial filter (radial.cpp: BuildPatchRadial / AddBouncedToRadial / SampleRadial; UNCITED,
+ * absent from the reference).  vrad_bsp_radial_entries (host) lists, per lit face, the leaf patches of the face and of its
+ * smoothing neighbours (vrad_bsp_pair_edges; NULL = own patches only) with their position and extent in that face's luxel space
+ * (relative to the lightmap mins; extents at least one luxel, stored as reciprocals).  vrad_luxel_radial_light (device) then gives
+ * every luxel sum(r * TotalLight(patch)) / sum(r) with r = 2 - ((cs-s)/ds)^2 - ((ct-t)/dt)^2 over the entries with r > 0 (zero when no
+ * patch reaches it); the extra blocks of a bump-mapped face take patch_bump9 (vrad_bounce_bump_totals; NULL = the flat totals).
+ * luxel_first / size2 / entry_first are host arrays; the rest may be host or device memory.  _host runs the same code on the
+ * host's cores (no device needed). */
+typedef struct { int32_t patch; float s, t, inv_ds, inv_dt; } vrad_radial_entry;      /* 20 bytes */
+int  vrad_bsp_radial_entries(const vrad_bsp_lumps*, const int32_t* mins2, const float* face_origins3,
+                             int n_patches, const int32_t* patch_face, const int32_t* child1, const float* origin3,
+                             const int32_t* wind_first, const int32_t* wind_count, const float* wind_points3,
+                             const int32_t* neighbour_first, const int32_t* neighbours,
+                             int64_t max_entries, int64_t* entry_first, vrad_radial_entry* entries, int64_t* n_entries_out);
+int  vrad_luxel_radial_light(vrad_env*, int64_t n, const int32_t* luxel_face, int n_faces, const int64_t* luxel_first, const int32_t* size2,
+                             const int64_t* entry_first, const vrad_radial_entry* entries, int n_patches, const float* patch_total3,
+                             const float* patch_bump9, float* indirect3_out);
+int  vrad_luxel_radial_light_host(int64_t n, const int32_t* luxel_face, int n_faces, const int64_t* luxel_first, const int32_t* size2,
+                                  const int64_t* entry_first, const vrad_radial_entry* entries, int n_patches, const float* patch_total3,
+                                  const float* patch_bump9, float* indirect3_out);
 /* K5 with the bounced light looked up per luxel: out = RGBExp32(direct + patch_total[luxel_patch]) (luxel_patch -1: direct only).
  * patch_total3 = the N x 3 totals vrad_bounce returns.  Device pointers must be 16-byte aligned. */
 int  vrad_lightmap_finalize_patches(vrad_env*, int64_t n, const float* direct3, const int32_t* luxel_patch, int n_patches,

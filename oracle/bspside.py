@@ -694,3 +694,46 @@ def light_for_texture(name, map_name, table):
         if n == name:
             return value
     return [F(0), F(0), F(0)]
+
+
+# ---- bounced light per luxel: upstream radial.cpp (UNCITED, see include/vrad_bsp.h) ---------------------------------------
+def world_to_luxel(tx, p, offset=None):
+    """WorldToLuxelSpace"""
+    q = vec(p) if offset is None else vsub(vec(p), vec(offset))
+    return [q[0] * F(tx["lightmap_vecs"][k][0]) + q[1] * F(tx["lightmap_vecs"][k][1]) + q[2] * F(tx["lightmap_vecs"][k][2]) + F(tx["lightmap_vecs"][k][3]) for k in range(2)]
+
+
+def build_patch_radial(L, f, mins, size, patch_lists, tree, totals, neighbours=None, face_origins=None):
+    """BuildPatchRadial + AddBouncedToRadial for face f, the way upstream does it: every patch SCATTERS r * light into the luxels it
+    reaches; then SampleRadial = light / weight per luxel.  patch_lists[face] = leaf patches of that face (ascending).  Returns
+    [(size[1]+1) * (size[0]+1), 3] in luxel order (t major)."""
+    tx = L.texinfo[int(L.faces[f]["texinfo"])]
+    w, h = int(size[f][0]) + 1, int(size[f][1]) + 1
+    light = [[F(0), F(0), F(0)] for _ in range(w * h)]
+    weight = [F(0)] * (w * h)
+    off = None if face_origins is None else face_origins[f]
+    sources = [f] + ([] if neighbours is None else list(neighbours[f]))
+    for src in sources:
+        for p in patch_lists[src]:
+            pts = tree["wind_points"][tree["wind_first"][p]:tree["wind_first"][p] + tree["wind_count"][p]]
+            st = [world_to_luxel(tx, q, off) for q in pts]
+            st = [[c[0] - F(int(mins[f][0])), c[1] - F(int(mins[f][1]))] for c in st]
+            mn = [min(c[k] for c in st) for k in range(2)]; mx = [max(c[k] for c in st) for k in range(2)]
+            c = world_to_luxel(tx, tree["origin"][p], off)
+            c = [c[0] - F(int(mins[f][0])), c[1] - F(int(mins[f][1]))]
+            dists, distt = max(F(1.0), mx[0] - mn[0]), max(F(1.0), mx[1] - mn[1])
+            inv_s, inv_t = F(1.0) / dists, F(1.0) / distt
+            for t in range(h):
+                for s in range(w):
+                    ds, dt = (c[0] - F(s)) * inv_s, (c[1] - F(t)) * inv_t
+                    r = F(2.0) - (ds * ds + dt * dt)
+                    if r > 0:
+                        i = s + t * w
+                        light[i] = [light[i][k] + F(totals[p][k]) * r for k in range(3)]
+                        weight[i] = weight[i] + r
+    out = np.zeros((w * h, 3), np.float32)
+    for i in range(w * h):
+        if weight[i] > F(0.00001):
+            inv = F(1.0) / weight[i]
+            out[i] = [light[i][k] * inv for k in range(3)]
+    return out

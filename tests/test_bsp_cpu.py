@@ -697,3 +697,82 @@ def test_lumps_from_elsewhere_are_validated(smap):
         L.replace(nodes=nodes).validate()
     with pytest.raises(VradError):
         L.replace(visdata=np.int32(50).tobytes() + b"\0" * 16).validate()
+
+
+# ---- bounced light per luxel: the radial filter -------------------------------------------------------------------------------
+def test_radial_filter_matches_the_scatter_form(smap):
+    """The gather kernel's functor (host policy) against the oracle's restatement of upstream's scatter (BuildPatchRadial /
+    AddBouncedToRadial / SampleRadial): same sums in the same patch order, so bit for bit."""
+    from vrad_b200 import bake
+    L, meta = smap
+    prep = bake.prepare(L, meta["entities"])
+    t = prep["tree"]
+    N = t["origin"].shape[0]
+    rng = np.random.default_rng(12)
+    totals = rng.uniform(0, 200, (N, 3)).astype(np.float32)
+    mins, size, _ = B.face_extents(prep["lumps"])
+    vn, nb_first, nb = B.pair_edges(L, 0.7071067)
+    first, entries = B.radial_entries(prep["lumps"], mins, t, prep["face_of_patch"], prep["face_origin"], nb_first, nb)
+    assert np.array_equal(first, prep["radial_first"]) and np.array_equal(entries, prep["radial_entries"])          # what the bake uses
+    got = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], size, first, entries, totals)
+    patch_lists = [[] for _ in range(L.faces.shape[0])]
+    for p in range(N):
+        if t["child1"][p] == -1:
+            patch_lists[prep["face_of_patch"][p]].append(p)
+    nbs = [list(nb[nb_first[f]:nb_first[f + 1]]) for f in range(L.faces.shape[0])]
+    lit_faces = np.nonzero(np.diff(prep["luxel_first"]) > 0)[0]
+    bump_face = int(np.nonzero(L.texinfo["flags"][L.faces["texinfo"]] & B.SURF_BUMPLIGHT)[0][0])
+    ent_face = meta["brush_entity"]["first_face"]                         # a face of the brush model: its patches live at the entity's origin
+    for f in [int(lit_faces[0]), int(lit_faces[7]), int(lit_faces[-1]), bump_face, ent_face] + [int(x) for x in lit_faces[20:24]]:
+        want = O.build_patch_radial(L, f, mins, size, patch_lists, t, totals, nbs, prep["face_origin"])
+        a = int(prep["luxel_first"][f])
+        assert np.array_equal(_bits(got[a:a + want.shape[0]]), _bits(want)), f
+        if f == bump_face:                                                 # without bump totals the three extra blocks repeat the flat one
+            for b in range(1, 4):
+                assert np.array_equal(got[a + b * want.shape[0]:a + (b + 1) * want.shape[0]], got[a:a + want.shape[0]])
+    # with bump totals block b takes Light[b]
+    bump = rng.uniform(0, 200, (N, 3, 3)).astype(np.float32)
+    gotb = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], size, first, entries, totals, bump)
+    nflat = (size[bump_face, 0] + 1) * (size[bump_face, 1] + 1)
+    a = int(prep["luxel_first"][bump_face])
+    for b in range(1, 4):
+        want = O.build_patch_radial(L, bump_face, mins, size, patch_lists, t, bump[:, b - 1], nbs, prep["face_origin"])
+        assert np.array_equal(_bits(gotb[a + b * nflat:a + (b + 1) * nflat]), _bits(want))
+    assert np.array_equal(gotb[a:a + nflat], got[a:a + nflat])
+
+
+def test_radial_filter_properties(smap):
+    from vrad_b200 import bake
+    L, meta = smap
+    prep = bake.prepare(L, meta["entities"])
+    t = prep["tree"]
+    N = t["origin"].shape[0]
+    mins, size, _ = B.face_extents(prep["lumps"])
+    first, entries = B.radial_entries(prep["lumps"], mins, t, prep["face_of_patch"], prep["face_origin"])
+    # entries: only leaf patches, each on its own face (no neighbours given), centre inside the face's luxel rectangle
+    assert np.all(t["child1"][entries["patch"]] == -1)
+    per_face = np.repeat(np.arange(L.faces.shape[0]), np.diff(first))
+    assert np.array_equal(prep["face_of_patch"][entries["patch"]], per_face)
+    assert np.all(entries["s"] > -0.01) and np.all(entries["s"] < size[per_face, 0] + 1.01) and np.all(entries["inv_ds"] <= 1.0) and np.all(entries["inv_dt"] <= 1.0)
+    # a constant patch light comes back as the same constant on every luxel a patch reaches (weights normalise), zero elsewhere
+    const = np.tile(np.float32([7.0, 11.0, 13.0]), (N, 1))
+    out = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], size, first, entries, const)
+    reached = out.any(axis=1)
+    assert reached.mean() > 0.99 and np.allclose(out[reached], [7.0, 11.0, 13.0], rtol=1e-5)
+    # the filter interpolates: every luxel lies between the smallest and the largest patch light of its face (+ neighbours)
+    rng = np.random.default_rng(3)
+    totals = rng.uniform(10, 20, (N, 3)).astype(np.float32)
+    out = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], size, first, entries, totals)
+    assert out[reached].min() >= 10.0 - 1e-3 and out[reached].max() <= 20.0 + 1e-3
+    # and it follows the light: luxels next to a bright patch are brighter than those next to a dark one
+    f = int(np.nonzero(np.diff(prep["luxel_first"]) > 500)[0][0])
+    on_face = np.nonzero((prep["face_of_patch"] == f) & (t["child1"] == -1))[0]
+    ramp = np.zeros((N, 3), np.float32)
+    ramp[on_face] = (t["origin"][on_face, :1] - t["origin"][on_face, :1].min()) + (t["origin"][on_face, 1:2] - t["origin"][on_face, 1:2].min())
+    out = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], size, first, entries, ramp)
+    a, b = int(prep["luxel_first"][f]), int(prep["luxel_first"][f + 1])
+    near = B.luxel_nearest_patch(prep["lux_face"][a:b], prep["lux_pos"][a:b], prep["face_of_patch"], t["origin"], t["child1"])
+    assert np.corrcoef(out[a:b, 0], ramp[near, 0])[0, 1] > 0.98
+    with pytest.raises(VradError):
+        bad = entries.copy(); bad["patch"][0] = N
+        B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], size, first, bad, totals)

@@ -75,6 +75,28 @@ def test_k5_with_patch_lookup(env, n):
         B.lightmap_finalize_patches(env, direct, bad, total)
 
 
+def test_radial_filter_device_equals_host_policy(env):
+    """vrad_luxel_radial_light: the gather functor as a CUDA kernel against the same functor on the host's cores (which the CPU tests
+    compare with the oracle's scatter form) -- bit for bit, flat and bump-mapped blocks, host and device inputs."""
+    from vrad_b200 import bake
+    L, meta = B.synthetic_map(3, 2, boxes_per_room=5, sky_rooms=(1,), bump_rooms=(0,))
+    prep = bake.prepare(L, meta["entities"])
+    N = prep["tree"]["origin"].shape[0]
+    rng = np.random.default_rng(8)
+    totals = rng.uniform(0, 300, (N, 3)).astype(np.float32)
+    bump = rng.uniform(0, 300, (N, 3, 3)).astype(np.float32)
+    args = (prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"])
+    for bp in (None, bump):
+        want = B.luxel_radial_light(None, *args, totals, bp)
+        got = B.luxel_radial_light(env, *args, totals, bp)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (want != 0).any(axis=1).mean() > 0.95
+    # a sub-range of luxels (what a rank of a sharded bake computes): offsets shifted, same values
+    a, b = 1000, 1000 + 12345
+    part = B.luxel_radial_light(env, prep["lux_face"][a:b], prep["luxel_first"] - a, prep["lm_size"], prep["radial_first"], prep["radial_entries"], totals, bump)
+    assert np.array_equal(part, want[a:b])
+
+
 def test_env_add_bsp_traces_like_the_oracle():
     """vrad_env_add_bsp (brush entity + world brushes + sky faces) then K1: visibility bits and closest hits equal the oracle's on
     the same triangles."""
@@ -118,12 +140,13 @@ def test_bsp_file_bake(tmp_path):
     for key in ("direct", "emit0", "total"):
         assert np.abs(lit[key] - ref[key]).max() <= RTOL * float(np.abs(ref[key]).max()), key
     assert lit["direct"].max() > 1 and lit["total"].max() > 1
-    # K5 == the host function on the GPU's own inputs, and the lump is what pack_lighting makes of it
-    ind = np.where(prep["lux_patch"][:, None] >= 0, lit["total"][np.maximum(prep["lux_patch"], 0)], np.float32(0)).astype(np.float32)
+    # radial filter + K5 == the same functor on the host's cores + the host pack function, on the GPU's own inputs; the lump is what
+    # pack_lighting makes of it
+    ind = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"])
     assert np.array_equal(_rows(res["colors"]), _rows(B.color_to_rgbexp32(lit["direct"] + ind)))
     assert res["lump"] == B.pack_lighting(prep["lumps"], prep["luxel_first"], res["colors"], prep["lump_bytes"])
     # against the oracle's light the decoded luxels agree to the 8-bit truncation step (one part in 128 of the largest component)
-    ind_ref = np.where(prep["lux_patch"][:, None] >= 0, ref["total"][np.maximum(prep["lux_patch"], 0)], np.float32(0)).astype(np.float32)
+    ind_ref = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], ref["total"])
     want = ref["direct"] + ind_ref
     got = B.color_from_rgbexp32(res["colors"])
     step = np.maximum(want.max(axis=1, keepdims=True), 1e-3) / 64

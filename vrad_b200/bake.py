@@ -175,7 +175,10 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
         surf = lights_from_patches(tree["origin"], tree["normal"], base_light[tree["face"]], tree["area"], fp["scale"][tree["face"]],
                                    fp["base_area"][tree["face"]], tree["child1"])
         lights = np.concatenate([surf, lights])
-    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, base_light=base_light[tree["face"]].astype(np.float32), tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
+    vn, nb_first, nb = B.pair_edges(L)                                # lightmap.PairEdges: the smoothing neighbours of every face
+    entry_first, entries = B.radial_entries(Llit, mins, tree, face_of_patch, face_origin, nb_first, nb)
+    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, face_origin=face_origin, lm_mins=mins, lm_size=size, vertex_normals=vn,
+                radial_first=entry_first, radial_entries=entries, base_light=base_light[tree["face"]].astype(np.float32), tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
                 cluster=face_cluster[face_of_patch].astype(np.int32), flags=sky, pvs=pvs, lights=lights,
                 lumps=Llit, luxel_first=luxel_first, lump_bytes=lump_bytes, lux_pos=lux_pos, lux_normal=lux_normal, lux_face=lux_face,
                 lux_patch=lux_patch, oversize=oversize, face_of_patch=face_of_patch)
@@ -255,16 +258,21 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int =
     return dict(nnz=int(nnz), direct=direct, emit0=emit0, total=np.asarray(total), bounces_done=int(done))
 
 
-def finish(env, prep: dict, lit: dict, rank: int = 0, world: int = 1, device=None) -> tuple[bytes, np.ndarray]:
-    """K5 on the device + the lighting lump: returns (lump bytes, packed luxel colours).  world > 1: each rank packs its luxel range."""
+def finish(env, prep: dict, lit: dict, rank: int = 0, world: int = 1, device=None, indirect: str = "radial") -> tuple[bytes, np.ndarray]:
+    """K5 on the device + the lighting lump: returns (lump bytes, packed luxel colours).  indirect = "radial": the bounced light of a
+    luxel is upstream's radial filter over the patch lights of its face and the face's smoothing neighbours (vrad_luxel_radial_light);
+    "nearest": the light of the nearest leaf patch of the face (vrad_lightmap_finalize_patches).  world > 1: each rank packs its range."""
     from .sharding import range_partition
-    if world == 1:
-        colors = B.lightmap_finalize_patches(env, lit["direct"], prep["lux_patch"], lit["total"])
+    parts = range_partition(lit["direct"].shape[0], world)
+    a, b = parts[rank]
+    if b > a and indirect == "radial":
+        ind = B.luxel_radial_light(env, prep["lux_face"][a:b], prep["luxel_first"] - a, prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"])
+        mine = B.lightmap_finalize(env, lit["direct"][a:b], ind)
+    elif b > a:
+        mine = B.lightmap_finalize_patches(env, lit["direct"][a:b], prep["lux_patch"][a:b], lit["total"])
     else:
-        parts = range_partition(lit["direct"].shape[0], world)
-        a, b = parts[rank]
-        mine = B.lightmap_finalize_patches(env, lit["direct"][a:b], prep["lux_patch"][a:b], lit["total"]) if b > a else np.zeros(0, B.RGBEXP32)
-        colors = all_gather_blocks(mine.view(np.int32), parts, rank, device).view(B.RGBEXP32)
+        mine = np.zeros(0, B.RGBEXP32)
+    colors = mine if world == 1 else all_gather_blocks(mine.view(np.int32), parts, rank, device).view(B.RGBEXP32)
     return B.pack_lighting(prep["lumps"], prep["luxel_first"], colors, prep["lump_bytes"]), colors
 
 

@@ -55,6 +55,7 @@ SYMBOLS = [
     "vrad_bsp_layout_lighting", "vrad_bsp_face_luxels", "vrad_color_to_rgbexp32", "vrad_color_from_rgbexp32",
     "vrad_lightmap_finalize", "vrad_bsp_pack_lighting", "vrad_luxel_nearest_patch", "vrad_lightmap_finalize_patches",
     "vrad_texlights_parse", "vrad_bsp_apply_texlights", "vrad_bspfile_set_target_faces", "vrad_bsp_validate",
+    "vrad_bsp_radial_entries", "vrad_luxel_radial_light", "vrad_luxel_radial_light_host",
 ]
 
 
@@ -383,6 +384,49 @@ def lightmap_finalize_patches(env, direct, luxel_patch, patch_total) -> np.ndarr
     out = np.zeros(d.shape[0], RGBEXP32)
     _check(_lib.load().vrad_lightmap_finalize_patches(env._h, C.c_int64(d.shape[0]), _ptr(d), _ptr(ix), C.c_int(t.shape[0]), _ptr(t), _ptr(out)),
            "vrad_lightmap_finalize_patches")
+    return out
+
+
+RADIAL_ENTRY = np.dtype([("patch", "<i4"), ("s", "<f4"), ("t", "<f4"), ("inv_ds", "<f4"), ("inv_dt", "<f4")])
+assert RADIAL_ENTRY.itemsize == 20
+
+
+def radial_entries(L: Lumps, mins, tree: dict, patch_face, face_origins=None, neighbour_first=None, neighbours=None):
+    """Per lit face the leaf patches (own + smoothing neighbours) in the face's luxel space: (entry_first [n_faces + 1], entries)."""
+    mins = np.ascontiguousarray(mins, np.int32)
+    pf = np.ascontiguousarray(patch_face, np.int32); c1 = np.ascontiguousarray(tree["child1"], np.int32)
+    org = np.ascontiguousarray(tree["origin"], np.float32)
+    wf = np.ascontiguousarray(tree["wind_first"], np.int32); wc = np.ascontiguousarray(tree["wind_count"], np.int32)
+    wp = np.ascontiguousarray(tree["wind_points"], np.float32)
+    fo = None if face_origins is None else np.ascontiguousarray(face_origins, np.float32)
+    nbf = None if neighbour_first is None else np.ascontiguousarray(neighbour_first, np.int32)
+    nb = None if neighbours is None else np.ascontiguousarray(neighbours, np.int32)
+    if nb is not None and nb.shape[0] == 0:
+        nb = np.zeros(1, np.int32)
+    first = np.zeros(L.faces.shape[0] + 1, np.int64); n = C.c_int64()
+    l = _lib.load()
+    args = (L.ref, _ptr(mins), _ptr(fo), C.c_int(pf.shape[0]), _ptr(pf), _ptr(c1), _ptr(org), _ptr(wf), _ptr(wc), _ptr(wp), _ptr(nbf), _ptr(nb))
+    _check(l.vrad_bsp_radial_entries(*args, C.c_int64(0), _ptr(first), None, C.byref(n)), "vrad_bsp_radial_entries")
+    entries = np.zeros(max(n.value, 1), RADIAL_ENTRY)
+    _check(l.vrad_bsp_radial_entries(*args, C.c_int64(entries.shape[0]), _ptr(first), _ptr(entries), C.byref(n)), "vrad_bsp_radial_entries")
+    return first, entries[:n.value]
+
+
+def luxel_radial_light(env, luxel_face, luxel_first, size, entry_first, entries, patch_total, patch_bump=None) -> np.ndarray:
+    """Bounced light per luxel by the radial filter; env = an Environment (device) or None (the same code on the host's cores)."""
+    lf = np.ascontiguousarray(luxel_face, np.int32); first = np.ascontiguousarray(luxel_first, np.int64); size = np.ascontiguousarray(size, np.int32)
+    ef = np.ascontiguousarray(entry_first, np.int64); en = np.ascontiguousarray(entries, RADIAL_ENTRY)
+    if en.shape[0] == 0:
+        en = np.zeros(1, RADIAL_ENTRY)
+    tot = np.ascontiguousarray(patch_total, np.float32).reshape(-1, 3)
+    bump = None if patch_bump is None else np.ascontiguousarray(patch_bump, np.float32).reshape(-1, 9)
+    out = np.zeros((lf.shape[0], 3), np.float32)
+    l = _lib.load()
+    tail = (C.c_int64(lf.shape[0]), _ptr(lf), C.c_int(size.shape[0]), _ptr(first), _ptr(size), _ptr(ef), _ptr(en), C.c_int(tot.shape[0]), _ptr(tot), _ptr(bump), _ptr(out))
+    if env is None:
+        _check(l.vrad_luxel_radial_light_host(*tail), "vrad_luxel_radial_light_host")
+    else:
+        _check(l.vrad_luxel_radial_light(env._h, *tail), "vrad_luxel_radial_light")
     return out
 
 
