@@ -15,5 +15,5 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_th
 timeout 200 ncu --metrics $M --clock-control none -k regex:'k5_finalize' -c 6 --csv --page raw --log-file gpurun_out/r02a_k5.csv python tools/profile_target.py k5 > gpurun_out/r02a_k5.log 2>&1; tail -2 gpurun_out/r02a_k5.log; wc -c gpurun_out/r02a_k5.csv
 timeout 300 ncu --metrics $M --clock-control none -k regex:'k_for_each|DeviceScan' -c 400 --csv --page raw --log-file gpurun_out/r02a_kdfast.csv python tools/profile_target.py kdfast > gpurun_out/r02a_kdfast.log 2>&1; tail -2 gpurun_out/r02a_kdfast.log; wc -c gpurun_out/r02a_kdfast.csv
 # 4. compute-sanitizer on the new kernels (small sizes through the tests)
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_zz_bsp_bake.py -q -k "k5 or add_bsp" 2>&1 | tail -6 > gpurun_out/r02a_sanitizer_k5.txt; tail -3 gpurun_out/r02a_sanitizer_k5.txt
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_zz_bsp_bake.py -q -k "k5 or add_bsp or radial" 2>&1 | tail -6 > gpurun_out/r02a_sanitizer_k5.txt; tail -3 gpurun_out/r02a_sanitizer_k5.txt
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_zz_kd_fast.py -q -k "device_tree or same_tree" 2>&1 | tail -6 > gpurun_out/r02a_sanitizer_kdfast.txt; tail -3 gpurun_out/r02a_sanitizer_kdfast.txt
