@@ -776,3 +776,40 @@ def test_radial_filter_properties(smap):
     with pytest.raises(VradError):
         bad = entries.copy(); bad["patch"][0] = N
         B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], size, first, bad, totals)
+
+
+def test_bake_gives_child_patches_and_luxels_their_phong_normals(smap):
+    """CreateChildPatch -> lightmap.GetPhongNormal (rad/patches/subdivide.go:385): children carry the smoothed normal at their origin,
+    root patches the plane normal (face.go:152); luxel samples get the same treatment."""
+    from vrad_b200 import bake
+    L, meta = smap
+    prep = bake.prepare(L, meta["entities"])
+    t = prep["tree"]
+    fop = prep["face_of_patch"]
+    plane_n = L.planes["normal"][L.faces["planenum"][fop]]
+    roots = t["parent"] == -1
+    assert np.array_equal(t["normal"][roots], plane_n[roots])
+    assert np.allclose(np.linalg.norm(t["normal"], axis=1), 1.0, atol=1e-5)
+    smooth_face = L.faces["smoothing_groups"][fop] != 0                 # the doorless walls carry smoothing group 1 and meet at right angles
+    bent = np.any(t["normal"] != plane_n, axis=1)
+    assert not bent[~smooth_face].any() and bent[smooth_face & ~roots].mean() > 0.4
+    on, _ = O.pair_edges(L, 0.7071067)
+    kids = np.nonzero(smooth_face & ~roots)[0][::37]
+    want = np.asarray([O.get_phong_normal(L, on, prep["face_centroids"], int(fop[p]), t["origin"][p] - prep["face_origin"][fop[p]]) for p in kids], np.float32)
+    assert np.array_equal(_bits(t["normal"][kids]), _bits(want))
+    # near a corner the normal leans towards the adjoining wall: a positive component along that wall's normal
+    wall = int(np.nonzero((L.faces["smoothing_groups"] != 0))[0][0])
+    on_wall = np.nonzero((fop == wall) & (t["child1"] == -1))[0]
+    lean = np.abs(t["normal"][on_wall] - plane_n[on_wall]).max(axis=1)
+    dist_to_centre = np.linalg.norm(t["origin"][on_wall] - prep["face_centroids"][wall], axis=1)
+    assert lean[np.argmin(dist_to_centre)] < 0.1 and lean.max() > 0.2    # flat at the face centre, bent towards a smoothed corner
+    # luxels: same normals as GetPhongNormal at the on-surface point
+    lf = prep["lux_face"]
+    sm_lux = np.nonzero(L.faces["smoothing_groups"][lf] != 0)[0][::211]
+    flat_n = L.planes["normal"][L.faces["planenum"][lf]]
+    pts = prep["lux_pos"][sm_lux] - flat_n[sm_lux]
+    want = np.asarray([O.get_phong_normal(L, on, prep["face_centroids"], int(lf[i]), p) for i, p in zip(sm_lux, pts)], np.float32)
+    assert np.allclose(prep["lux_normal"][sm_lux], want, atol=2e-6)
+    plain = L.faces["smoothing_groups"][lf] == 0
+    bump_extra = (L.texinfo["flags"][L.faces["texinfo"][lf]] & B.SURF_BUMPLIGHT) != 0
+    assert np.array_equal(prep["lux_normal"][plain & ~bump_extra], flat_n[plain & ~bump_extra])

@@ -123,7 +123,7 @@ def _point_cluster(L: B.Lumps, p) -> int:
 
 
 def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float = 4.0, lights_rad: str | None = None,
-            texdata_strings=None, map_name: str = "", lights_rad_hdr: bool = False) -> dict:
+            texdata_strings=None, map_name: str = "", lights_rad_hdr: bool = False, smoothing_threshold: float = 0.7071067) -> dict:
     """Everything the device stages take, from the lumps (host code in the library; no GPU needed).
     lights_rad = the text of a lights.rad file, texdata_strings = (LUMP_TEXDATA_STRING_TABLE as int32, LUMP_TEXDATA_STRING_DATA bytes):
     faces whose material is a texlight get Patch.BaseLight and their leaf patches become EMIT_SURFACE lights (CreateDirectLights)."""
@@ -138,8 +138,21 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
         base_light, fp["faces"] = B.apply_texlights(L, texdata_strings[0], texdata_strings[1], map_name, table, fp["face_number"], fp["faces"])
     tree = subdivide_patches(fp["faces"], fp["points"], min_chop=min_chop)
     face_of_patch = fp["face_number"][tree["face"]]                       # face lump index of every patch
-    # cluster of a face = cluster of the leaf that lists it (leaffaces); faces of brush models: the leaf their model origin is in
+    # lightmap.PairEdges (rad/start.go:66-79) -> smoothed vertex normals; CreateChildPatch gives every child patch the phong normal at its
+    # origin (lightmap.GetPhongNormal, rad/patches/subdivide.go:385); root patches keep the plane normal (rad/patches/face.go:152).
+    # cache.faceCentroids[fn] = root origin - face offset (face.go:151); the lookup runs in the face's model space.
+    vn, nb_first, nb = B.pair_edges(L, smoothing_threshold)
     n_faces = L.faces.shape[0]
+    face_origin = np.zeros((n_faces, 3), np.float32)
+    for m in range(L.models.shape[0]):
+        face_origin[int(L.models[m]["firstface"]):int(L.models[m]["firstface"]) + int(L.models[m]["numfaces"])] = origins[m]
+    centroids = np.zeros((n_faces, 3), np.float32)
+    roots = tree["parent"] == -1
+    centroids[face_of_patch[roots]] = tree["origin"][roots] - face_origin[face_of_patch[roots]]
+    kids = np.nonzero(~roots)[0]
+    if kids.size:
+        tree["normal"][kids] = B.phong_normals(L, vn, centroids, face_of_patch[kids], tree["origin"][kids] - face_origin[face_of_patch[kids]], smoothing_threshold)
+    # cluster of a face = cluster of the leaf that lists it (leaffaces); faces of brush models: the leaf their model origin is in
     face_cluster = np.full(n_faces, -1, np.int32)
     for lf in L.leafs:
         for k in range(int(lf["numleaffaces"])):
@@ -159,11 +172,17 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
     sky_pvs = None if has_radial else B.vis_for_light_environment(L)[1]       # radial-vis maps: BuildVisForLightEnvironment needs the device
     mins, size, oversize = B.face_extents(L)
     faces_lit, luxel_first, lump_bytes = B.layout_lighting(L, mins, size)
-    face_origin = np.zeros((n_faces, 3), np.float32)
-    for m in range(L.models.shape[0]):
-        face_origin[int(L.models[m]["firstface"]):int(L.models[m]["firstface"]) + int(L.models[m]["numfaces"])] = origins[m]
     Llit = L.replace(faces=faces_lit)
     lux_pos, lux_normal, lux_face = B.face_luxels(Llit, mins, size, luxel_first, face_origin)
+    # the sample normal is the phong normal at the sample (upstream BuildFacelights; same GetPhongNormal).  The three extra blocks of a
+    # bump-mapped face keep the bump basis face_luxels built around the flat normal.
+    flags_of_lux = L.texinfo["flags"][L.faces["texinfo"][lux_face]]
+    k_in_face = np.arange(lux_face.shape[0]) - luxel_first[lux_face]
+    per_block = (size[lux_face, 0] + 1).astype(np.int64) * (size[lux_face, 1] + 1)
+    flat_block = np.nonzero(((flags_of_lux & B.SURF_BUMPLIGHT) == 0) | (k_in_face < per_block))[0]
+    if flat_block.size:
+        on_surface = lux_pos[flat_block] - lux_normal[flat_block] - face_origin[lux_face[flat_block]]
+        lux_normal[flat_block] = B.phong_normals(L, vn, centroids, lux_face[flat_block], on_surface, smoothing_threshold)
     lux_patch = B.luxel_nearest_patch(lux_face, lux_pos, face_of_patch, tree["origin"], tree["child1"])
     sky = fp["faces"]["sky"][tree["face"]].astype(np.uint8)
     from .scenes import Bsp
@@ -175,9 +194,8 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
         surf = lights_from_patches(tree["origin"], tree["normal"], base_light[tree["face"]], tree["area"], fp["scale"][tree["face"]],
                                    fp["base_area"][tree["face"]], tree["child1"])
         lights = np.concatenate([surf, lights])
-    vn, nb_first, nb = B.pair_edges(L)                                # lightmap.PairEdges: the smoothing neighbours of every face
     entry_first, entries = B.radial_entries(Llit, mins, tree, face_of_patch, face_origin, nb_first, nb)
-    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, face_origin=face_origin, lm_mins=mins, lm_size=size, vertex_normals=vn,
+    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, face_origin=face_origin, face_centroids=centroids, lm_mins=mins, lm_size=size, vertex_normals=vn,
                 radial_first=entry_first, radial_entries=entries, base_light=base_light[tree["face"]].astype(np.float32), tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
                 cluster=face_cluster[face_of_patch].astype(np.int32), flags=sky, pvs=pvs, lights=lights,
                 lumps=Llit, luxel_first=luxel_first, lump_bytes=lump_bytes, lux_pos=lux_pos, lux_normal=lux_normal, lux_face=lux_face,

@@ -14,7 +14,7 @@
 //   vmath/polygon/winding.go:217-260  WindingArea, WindingCenter, WindingBounds
 // App. A intents applied: #16 (WindingCenter divides by a float point count and writes its result),
 // #22 (WindingAreaAndBalancePoint writes the caller's centre).  GetPhongNormal (subdivide.go:385) is the
-// plane normal here: phong smoothing needs the face-neighbour tables, which stay with the Go driver.
+// plane normal here: the caller overwrites the children's normals with vrad_bsp_phong_normals (include/vrad_bsp.h) once PairEdges has run, as vrad_b200/bake.py does.
 //
 // Formulation: flat point/patch arrays and an explicit work stack instead of the reference's recursion over
 // heap windings; child indices come out in the same order (child1's whole subtree before child2's).
