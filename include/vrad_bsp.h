@@ -225,6 +225,14 @@ int  vrad_bsp_layout_lighting(const vrad_bsp_lumps*, const int32_t* mins2, const
  * the block gives the light on that basis vector.  face_origins3 = cache.faceOffsets (the model origin per face) or NULL. */
 int  vrad_bsp_face_luxels(const vrad_bsp_lumps*, const int32_t* mins2, const int32_t* size2, const float* face_origins3,
                           const int64_t* luxel_first, float* pos3, float* normal3, int32_t* luxel_face);
+/* Move every sample of vrad_bsp_face_luxels onto its face (own rule; upstream's BuildFacesamples chops the face winding into
+ * luxel-sized pieces and lights their centres, UNCITED): the sample of luxel (s,t) becomes the centroid of the part of the face that
+ * lies in the luxel's cell [s-1/2, s+1/2] x [t-1/2, t+1/2]; a luxel whose cell misses the face takes the nearest point of the face
+ * outline.  Grid points that hang over the face's edge would otherwise sit inside the neighbouring brush and come out black.
+ * pos3_inout = the positions of vrad_bsp_face_luxels (moved in place, still one unit off the surface; the blocks of a bump-mapped
+ * face move alike); luxel_st2_out (may be NULL) = the sample's lightmap coordinates relative to the mins. */
+int  vrad_bsp_place_samples(const vrad_bsp_lumps*, const int32_t* mins2, const int32_t* size2, const float* face_origins3,
+                            const int64_t* luxel_first, float* pos3_inout, float* luxel_st2_out);
 /* upstream VectorToColorRGBExp32 (UNCITED): linear RGB -> 8-bit mantissas with a shared power-of-two exponent (largest
  * component brought into [128,255]).  Host-only; the device kernel behind vrad_lightmap_finalize runs the same inline
  * function (vrad_b200/csrc/rgbexp.cuh).  Negative / NaN components count as 0; below 2^-120 everything encodes as 0. */

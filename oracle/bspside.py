@@ -737,3 +737,44 @@ def build_patch_radial(L, f, mins, size, patch_lists, tree, totals, neighbours=N
             inv = F(1.0) / weight[i]
             out[i] = [light[i][k] * inv for k in range(3)]
     return out
+
+
+# ---- samples inside the face (own rule, see include/vrad_bsp.h: vrad_bsp_place_samples) --------------------------------------
+def place_sample(poly, s, t):
+    """The sample of luxel (s, t): centroid of face-polygon ∩ cell, else the nearest outline point.  float64 geometry -- an independent
+    computation, compared with a tolerance (the product works in float32)."""
+    cell = [(s - 0.5, t - 0.5), (s + 0.5, t - 0.5), (s + 0.5, t + 0.5), (s - 0.5, t + 0.5)]
+    pts = [(float(a), float(b)) for a, b in poly]
+
+    def clip(points, axis, bound, keep_greater):
+        out = []
+        for i in range(len(points)):
+            a, b = points[i], points[(i + 1) % len(points)]
+            ina = a[axis] >= bound if keep_greater else a[axis] <= bound
+            inb = b[axis] >= bound if keep_greater else b[axis] <= bound
+            if ina:
+                out.append(a)
+            if ina != inb:
+                u = (bound - a[axis]) / (b[axis] - a[axis])
+                out.append((a[0] + u * (b[0] - a[0]), a[1] + u * (b[1] - a[1])))
+        return out
+    c = clip(clip(clip(clip(pts, 0, s - 0.5, True), 0, s + 0.5, False), 1, t - 0.5, True), 1, t + 0.5, False)
+    if len(c) >= 3:
+        a2 = cx = cy = 0.0
+        for i in range(1, len(c) - 1):
+            cr = (c[i][0] - c[0][0]) * (c[i + 1][1] - c[0][1]) - (c[i][1] - c[0][1]) * (c[i + 1][0] - c[0][0])
+            a2 += cr; cx += cr * (c[0][0] + c[i][0] + c[i + 1][0]); cy += cr * (c[0][1] + c[i][1] + c[i + 1][1])
+        if abs(a2) > 1e-6:
+            return cx / (3 * a2), cy / (3 * a2), abs(a2) / 2
+    best, best_d = pts[0], 1e30
+    for i in range(len(pts)):
+        a, b = pts[i], pts[(i + 1) % len(pts)]
+        ex, ey = b[0] - a[0], b[1] - a[1]
+        l2 = ex * ex + ey * ey
+        u = ((s - a[0]) * ex + (t - a[1]) * ey) / l2 if l2 > 0 else 0.0
+        u = min(max(u, 0.0), 1.0)
+        x = (a[0] + u * ex, a[1] + u * ey)
+        d = (x[0] - s) ** 2 + (x[1] - t) ** 2
+        if d < best_d:
+            best, best_d = x, d
+    return best[0], best[1], 0.0

@@ -813,3 +813,48 @@ def test_bake_gives_child_patches_and_luxels_their_phong_normals(smap):
     plain = L.faces["smoothing_groups"][lf] == 0
     bump_extra = (L.texinfo["flags"][L.faces["texinfo"][lf]] & B.SURF_BUMPLIGHT) != 0
     assert np.array_equal(prep["lux_normal"][plain & ~bump_extra], flat_n[plain & ~bump_extra])
+
+
+def test_samples_are_placed_on_their_faces(smap):
+    L, meta = smap
+    mins, size, _ = B.face_extents(L)
+    faces, first, _ = B.layout_lighting(L, mins, size)
+    L3 = L.replace(faces=faces)
+    pos, nrm, lf = B.face_luxels(L3, mins, size, first)
+    placed, st = B.place_samples(L3, mins, size, first, pos)
+    moved = np.linalg.norm(placed - pos, axis=1) > 0
+    assert 0.1 < moved.mean() < 0.4                                       # the luxels along the faces' edges
+    # still one unit in front of the face plane
+    pl = L.planes[L.faces["planenum"][lf]]
+    assert np.allclose(np.einsum("ij,ij->i", placed.astype(np.float64), pl["normal"].astype(np.float64)) - pl["dist"], 1.0, atol=1e-3)
+    # the returned lightmap coordinates are those of the new position
+    lv = L.texinfo["lightmap_vecs"][L.faces["texinfo"][lf]].astype(np.float64)
+    st_world = np.einsum("ijk,ik->ij", lv[:, :, :3], placed.astype(np.float64) - pl["normal"]) + lv[:, :, 3] - mins[lf]
+    assert np.allclose(st_world, st, atol=2e-3)
+    # every sample lies on its face (inside the winding, up to rounding) and within half a luxel of its grid point unless the cell misses the face
+    checked = 0
+    for f in np.nonzero(np.diff(first) > 0)[0][::9]:
+        fc = L.faces[f]
+        verts = np.asarray([L.vertexes3[O.edge_vertex(L, fc, k)] for k in range(int(fc["numedges"]))], np.float64)
+        tx = L.texinfo[int(fc["texinfo"])]["lightmap_vecs"].astype(np.float64)
+        poly = verts @ tx[:, :3].T + tx[:, 3] - mins[f]
+        w = size[f, 0] + 1
+        for k in range(int(first[f]), int(first[f]) + (size[f, 0] + 1) * (size[f, 1] + 1), 7):
+            s, t = (k - int(first[f])) % w, (k - int(first[f])) // w
+            cs, ct, area = O.place_sample(poly, s, t)
+            assert abs(st[k, 0] - cs) < 1e-3 and abs(st[k, 1] - ct) < 1e-3, (f, s, t)
+            # inside the convex outline: all cross products of one sign (or zero)
+            e = np.roll(poly, -1, axis=0) - poly
+            cr = e[:, 0] * (st[k, 1] - poly[:, 1]) - e[:, 1] * (st[k, 0] - poly[:, 0])
+            assert (cr >= -1e-3).all() or (cr <= 1e-3).all()
+            if area > 0:
+                assert abs(st[k, 0] - s) <= 0.5 + 1e-4 and abs(st[k, 1] - t) <= 0.5 + 1e-4
+            if area > 1 - 1e-9:
+                assert not moved[k]                                        # a cell wholly inside the face keeps its grid point, bit for bit
+            checked += 1
+    assert checked > 500
+    # bump-mapped faces: the four blocks move alike
+    bump_face = int(np.nonzero(L.texinfo["flags"][L.faces["texinfo"]] & B.SURF_BUMPLIGHT)[0][0])
+    n_flat = (size[bump_face, 0] + 1) * (size[bump_face, 1] + 1)
+    blocks = placed[first[bump_face]:first[bump_face + 1]].reshape(4, n_flat, 3)
+    assert np.array_equal(blocks[0], blocks[1]) and np.array_equal(blocks[0], blocks[3])

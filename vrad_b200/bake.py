@@ -123,7 +123,8 @@ def _point_cluster(L: B.Lumps, p) -> int:
 
 
 def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float = 4.0, lights_rad: str | None = None,
-            texdata_strings=None, map_name: str = "", lights_rad_hdr: bool = False, smoothing_threshold: float = 0.7071067) -> dict:
+            texdata_strings=None, map_name: str = "", lights_rad_hdr: bool = False, smoothing_threshold: float = 0.7071067,
+            place_samples: bool = True) -> dict:
     """Everything the device stages take, from the lumps (host code in the library; no GPU needed).
     lights_rad = the text of a lights.rad file, texdata_strings = (LUMP_TEXDATA_STRING_TABLE as int32, LUMP_TEXDATA_STRING_DATA bytes):
     faces whose material is a texlight get Patch.BaseLight and their leaf patches become EMIT_SURFACE lights (CreateDirectLights)."""
@@ -174,6 +175,9 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
     faces_lit, luxel_first, lump_bytes = B.layout_lighting(L, mins, size)
     Llit = L.replace(faces=faces_lit)
     lux_pos, lux_normal, lux_face = B.face_luxels(Llit, mins, size, luxel_first, face_origin)
+    grid_pos = lux_pos
+    if place_samples:                                                 # grid points that hang over a face's edge sit inside the next brush
+        lux_pos, _ = B.place_samples(Llit, mins, size, luxel_first, lux_pos, face_origin)
     # the sample normal is the phong normal at the sample (upstream BuildFacelights; same GetPhongNormal).  The three extra blocks of a
     # bump-mapped face keep the bump basis face_luxels built around the flat normal.
     flags_of_lux = L.texinfo["flags"][L.faces["texinfo"][lux_face]]
@@ -195,7 +199,7 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
                                    fp["base_area"][tree["face"]], tree["child1"])
         lights = np.concatenate([surf, lights])
     entry_first, entries = B.radial_entries(Llit, mins, tree, face_of_patch, face_origin, nb_first, nb)
-    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, face_origin=face_origin, face_centroids=centroids, lm_mins=mins, lm_size=size, vertex_normals=vn,
+    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, face_origin=face_origin, face_centroids=centroids, lux_grid_pos=grid_pos, lm_mins=mins, lm_size=size, vertex_normals=vn,
                 radial_first=entry_first, radial_entries=entries, base_light=base_light[tree["face"]].astype(np.float32), tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
                 cluster=face_cluster[face_of_patch].astype(np.int32), flags=sky, pvs=pvs, lights=lights,
                 lumps=Llit, luxel_first=luxel_first, lump_bytes=lump_bytes, lux_pos=lux_pos, lux_normal=lux_normal, lux_face=lux_face,

@@ -55,7 +55,7 @@ SYMBOLS = [
     "vrad_bsp_layout_lighting", "vrad_bsp_face_luxels", "vrad_color_to_rgbexp32", "vrad_color_from_rgbexp32",
     "vrad_lightmap_finalize", "vrad_bsp_pack_lighting", "vrad_luxel_nearest_patch", "vrad_lightmap_finalize_patches",
     "vrad_texlights_parse", "vrad_bsp_apply_texlights", "vrad_bspfile_set_target_faces", "vrad_bsp_validate",
-    "vrad_bsp_radial_entries", "vrad_luxel_radial_light", "vrad_luxel_radial_light_host",
+    "vrad_bsp_radial_entries", "vrad_luxel_radial_light", "vrad_luxel_radial_light_host", "vrad_bsp_place_samples",
 ]
 
 
@@ -342,6 +342,16 @@ def face_luxels(L: Lumps, mins, size, luxel_first, face_origins=None):
     fo = None if face_origins is None else np.ascontiguousarray(face_origins, np.float32)
     _check(_lib.load().vrad_bsp_face_luxels(L.ref, _ptr(mins), _ptr(size), _ptr(fo), _ptr(first), _ptr(pos), _ptr(nrm), _ptr(lf)), "vrad_bsp_face_luxels")
     return pos, nrm, lf
+
+
+def place_samples(L: Lumps, mins, size, luxel_first, pos, face_origins=None):
+    """Samples moved onto their faces: (new positions, sample lightmap coordinates relative to the mins)."""
+    mins = np.ascontiguousarray(mins, np.int32); size = np.ascontiguousarray(size, np.int32); first = np.ascontiguousarray(luxel_first, np.int64)
+    p = np.ascontiguousarray(pos, np.float32).copy()
+    st = np.zeros((p.shape[0], 2), np.float32)
+    fo = None if face_origins is None else np.ascontiguousarray(face_origins, np.float32)
+    _check(_lib.load().vrad_bsp_place_samples(L.ref, _ptr(mins), _ptr(size), _ptr(fo), _ptr(first), _ptr(p), _ptr(st)), "vrad_bsp_place_samples")
+    return p, st
 
 
 def color_to_rgbexp32(rgb) -> np.ndarray:

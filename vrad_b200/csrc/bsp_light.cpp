@@ -272,6 +272,127 @@ extern "C" int vrad_bsp_face_luxels(const vrad_bsp_lumps* Lp, const int32_t* min
     return VRAD_OK;
 }
 
+// ---- samples inside the face ----------------------------------------------------------------------------------------------------
+namespace {
+
+struct P2 { float s, t; };
+
+// Sutherland-Hodgman against one axis-aligned half-plane: keep coord(axis) >= bound (keep_greater) or <= bound
+int clip_axis(const P2* in, int n, int axis, float bound, bool keep_greater, P2* out) {
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const P2 a = in[i], b = in[(i + 1) % n];
+        const float ca = axis ? a.t : a.s, cb = axis ? b.t : b.s;
+        const bool ina = keep_greater ? ca >= bound : ca <= bound, inb = keep_greater ? cb >= bound : cb <= bound;
+        if (ina) out[m++] = a;
+        if (ina != inb) {
+            const float u = (bound - ca) / (cb - ca);
+            P2 x = {a.s + (u * (b.s - a.s)), a.t + (u * (b.t - a.t))};
+            if (axis) x.t = bound; else x.s = bound;
+            out[m++] = x;
+        }
+    }
+    return m;
+}
+
+// area-weighted centroid of a polygon (fan from point 0); false when the polygon has no area
+bool polygon_centroid(const P2* p, int n, P2& c) {
+    float area2 = 0.0f, cs = 0.0f, ct = 0.0f;
+    for (int i = 1; i + 1 < n; i++) {
+        const float ax = p[i].s - p[0].s, ay = p[i].t - p[0].t, bx = p[i + 1].s - p[0].s, by = p[i + 1].t - p[0].t;
+        const float cr = (ax * by) - (ay * bx);                              // twice the signed area of the fan triangle
+        area2 += cr;
+        cs += cr * ((p[0].s + p[i].s) + p[i + 1].s);
+        ct += cr * ((p[0].t + p[i].t) + p[i + 1].t);
+    }
+    if (!(std::fabs(area2) > 1e-6f)) return false;
+    c.s = cs / (3.0f * area2); c.t = ct / (3.0f * area2);
+    return true;
+}
+
+P2 nearest_on_polygon(const P2* p, int n, P2 q) {
+    P2 best = p[0];
+    float best_d = 3.0e38f;
+    for (int i = 0; i < n; i++) {
+        const P2 a = p[i], b = p[(i + 1) % n];
+        const float ex = b.s - a.s, ey = b.t - a.t;
+        const float len2 = (ex * ex) + (ey * ey);
+        float u = len2 > 0.0f ? (((q.s - a.s) * ex) + ((q.t - a.t) * ey)) / len2 : 0.0f;
+        u = u < 0.0f ? 0.0f : (u > 1.0f ? 1.0f : u);
+        const P2 x = {a.s + (u * ex), a.t + (u * ey)};
+        const float d = ((x.s - q.s) * (x.s - q.s)) + ((x.t - q.t) * (x.t - q.t));
+        if (d < best_d) { best_d = d; best = x; }
+    }
+    return best;
+}
+
+}  // namespace
+
+extern "C" int vrad_bsp_place_samples(const vrad_bsp_lumps* Lp, const int32_t* mins2, const int32_t* size2, const float* face_origins3,
+                                      const int64_t* luxel_first, float* pos3_inout, float* luxel_st2_out) {
+    if (!Lp || !mins2 || !size2 || !luxel_first || !pos3_inout) { vrad::set_error("vrad_bsp_place_samples: bad arguments"); return VRAD_E_INVALID; }
+    const vrad_bsp_lumps& L = *Lp;
+    for (int i = 0; i < L.n_faces; i++) {
+        const int64_t count = luxel_first[i + 1] - luxel_first[i];
+        if (count == 0) continue;
+        const vrad_dface& f = L.faces[i];
+        const vrad_texinfo& tx = L.texinfo[f.texinfo];
+        const int w = size2[2 * (size_t)i] + 1, h = size2[2 * (size_t)i + 1] + 1;
+        const int blocks = face_is_bumped(L, f) ? 4 : 1;
+        if (count != (int64_t)w * h * blocks) { vrad::set_error("vrad_bsp_place_samples: face %d has %lld luxels laid out, extents say %lld", i, (long long)count, (long long)w * h * blocks); return VRAD_E_INVALID; }
+        if (f.numedges < 3 || f.numedges > 64) { vrad::set_error("vrad_bsp_place_samples: face %d has %d edges", i, f.numedges); return VRAD_E_INVALID; }
+        // the face winding in luxel space, relative to the lightmap mins
+        P2 poly[64];
+        for (int k = 0; k < f.numedges; k++) {
+            const float* v = L.vertexes3 + 3 * (size_t)face_vertex(L, f, k);
+            float st[2];
+            for (int a = 0; a < 2; a++) {
+                const float* lv = tx.lightmap_vecs[a];
+                st[a] = ((((v[0] * lv[0]) + (v[1] * lv[1])) + (v[2] * lv[2])) + lv[3]) - (float)mins2[2 * (size_t)i + a];
+            }
+            poly[k] = {st[0], st[1]};
+        }
+        // luxel -> world, as vrad_bsp_face_luxels builds it
+        const V3 nrm = load3(L.planes[f.planenum].normal);
+        const V3 lv0 = load3(tx.lightmap_vecs[0]), lv1 = load3(tx.lightmap_vecs[1]);
+        V3 l2w[2];
+        l2w[0] = cross(lv1, nrm); l2w[0] = scale(l2w[0], 1.0f / dot(l2w[0], lv0));
+        l2w[1] = cross(lv0, nrm); l2w[1] = scale(l2w[1], 1.0f / dot(l2w[1], lv1));
+        for (int t = 0; t < h; t++)
+            for (int s = 0; s < w; s++) {
+                P2 a[72], b[72];
+                // a cell that lies wholly inside the (convex) face keeps its grid point exactly
+                bool whole = true;
+                for (int cx = 0; cx < 2 && whole; cx++)
+                    for (int cy = 0; cy < 2 && whole; cy++) {
+                        const P2 q = {(float)s + (cx ? 0.5f : -0.5f), (float)t + (cy ? 0.5f : -0.5f)};
+                        bool pos_side = false, neg_side = false;
+                        for (int k = 0; k < f.numedges; k++) {
+                            const P2 e0 = poly[k], e1 = poly[(k + 1) % f.numedges];
+                            const float cr = ((e1.s - e0.s) * (q.t - e0.t)) - ((e1.t - e0.t) * (q.s - e0.s));
+                            if (cr > 0.0f) pos_side = true; else if (cr < 0.0f) neg_side = true;
+                        }
+                        if (pos_side && neg_side) whole = false;
+                    }
+                if (whole) { if (luxel_st2_out) for (int blk = 0; blk < blocks; blk++) { const int64_t o = luxel_first[i] + (int64_t)blk * w * h + (int64_t)t * w + s; luxel_st2_out[2 * o] = (float)s; luxel_st2_out[2 * o + 1] = (float)t; } continue; }
+                int n = clip_axis(poly, f.numedges, 0, (float)s - 0.5f, true, a);
+                n = clip_axis(a, n, 0, (float)s + 0.5f, false, b);
+                n = clip_axis(b, n, 1, (float)t - 0.5f, true, a);
+                n = clip_axis(a, n, 1, (float)t + 0.5f, false, b);
+                P2 c;
+                if (n < 3 || !polygon_centroid(b, n, c)) c = nearest_on_polygon(poly, f.numedges, P2{(float)s, (float)t});
+                const float ds = c.s - (float)s, dt = c.t - (float)t;      // how far the sample moved off the grid point, in luxels
+                for (int blk = 0; blk < blocks; blk++) {
+                    const int64_t o = luxel_first[i] + (int64_t)blk * w * h + (int64_t)t * w + s;
+                    for (int k = 0; k < 3; k++) pos3_inout[3 * o + k] = (pos3_inout[3 * o + k] + (ds * l2w[0][k])) + (dt * l2w[1][k]);
+                    if (luxel_st2_out) { luxel_st2_out[2 * o] = c.s; luxel_st2_out[2 * o + 1] = c.t; }
+                }
+            }
+    }
+    (void)face_origins3;
+    return VRAD_OK;
+}
+
 extern "C" int vrad_color_to_rgbexp32(int64_t n, const float* rgb3, vrad_color_rgbexp32* out) {
     if (n < 0 || (n && (!rgb3 || !out))) { vrad::set_error("vrad_color_to_rgbexp32: bad arguments"); return VRAD_E_INVALID; }
     for (int64_t i = 0; i < n; i++) {
