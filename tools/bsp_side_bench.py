@@ -48,17 +48,37 @@ def k5_part(dev, device, stream, hbm_peak):
 
 
 def bake_part(device):
+    """The file-driven bake at the C3/C4 map size (12 x 11 rooms, 30 occluders each), stage by stage."""
     from vrad_b200 import bake, bspfile
-    Lm, meta = bspfile.synthetic_map(4, 3, boxes_per_room=12, sky_rooms=(1, 6), bump_rooms=(0,))
+    from vrad_b200.environment import Environment
+    Lm, meta = bspfile.synthetic_map(12, 11, boxes_per_room=30, sky_rooms=(5, 60), bump_rooms=(0,))
     with tempfile.TemporaryDirectory() as td:
         src, dst = os.path.join(td, "in.bsp"), os.path.join(td, "out.bsp")
         bspfile.write_bsp(src, Lm, meta)
-        t0 = time.perf_counter(); res = bake.bake_file(src, dst, device=device, bounces=8); wall = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        f = bspfile.BspFile(src)
+        face_lump, lighting_lump = f.set_target_faces(False)
+        L = f.lumps()
+        text = f.get(bspfile.LUMP["ENTITIES"])[0].rstrip(b"\0").decode()
+        t1 = time.perf_counter()
+        prep = bake.prepare(L, text)
+        t2 = time.perf_counter()
+        env = Environment(device)
+        lit = bake.light(env, prep, bounces=8)
+        t3 = time.perf_counter()
+        lump, colors = bake.finish(env, prep, lit)
+        env.close()
+        t4 = time.perf_counter()
+        f.set(lighting_lump, lump, version=1); f.set(face_lump, prep["lumps"].faces, version=1); f.save(dst); f.close()
+        t5 = time.perf_counter()
         out_size = os.path.getsize(dst)
-    return {"workload": "synthetic BSP v20 map, 4 x 3 rooms, .bsp in -> lit .bsp out through vrad_b200.bake (first call, includes kd build and all host stages)",
-            "faces": int(Lm.faces.shape[0]), "triangles": int(res["prep"]["tri_ids"].shape[0]), "patches": int(res["prep"]["tree"]["origin"].shape[0]),
-            "luxels": int(res["prep"]["lux_pos"].shape[0]), "transfers": res["lit"]["nnz"], "bounces": res["lit"]["bounces_done"],
-            "wall_seconds": wall, "lighting_lump_bytes": len(res["lump"]), "file_bytes": out_size}
+    return {"workload": "synthetic BSP v20 map at the C3/C4 size (12 x 11 rooms), .bsp in -> lit .bsp out through vrad_b200.bake; first call of every stage",
+            "faces": int(Lm.faces.shape[0]), "triangles": int(prep["tri_ids"].shape[0]), "patches": int(prep["tree"]["origin"].shape[0]),
+            "leaf_patches": int((prep["tree"]["child1"] == -1).sum()), "luxels": int(prep["lux_pos"].shape[0]), "lights": int(prep["lights"].shape[0]),
+            "transfers": lit["nnz"], "bounces": lit["bounces_done"],
+            "seconds": {"read": t1 - t0, "prepare_host": t2 - t1, "light_k1_k2_k3_k4": t3 - t2, "radial_k5_pack": t4 - t3, "write": t5 - t4, "total": t5 - t0},
+            "lit_luxel_fraction": float((colors.view(np.uint8).reshape(-1, 4)[:, :3].max(axis=1) > 0).mean()),
+            "lighting_lump_bytes": len(lump), "file_bytes": out_size}
 
 
 def kd_part(dev, device, stream):
