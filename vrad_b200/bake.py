@@ -261,10 +261,16 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int =
             return np.asarray(env.direct_light(pos, nrm, prep["lights"])) if pos.shape[0] else np.zeros((0, 3), np.float32)
         cl = np.asarray(env.cluster_from_point(pos))
         out = np.zeros((pos.shape[0], 3), np.float32)
-        for c in np.unique(cl):
-            sel = np.nonzero(cl == c)[0]
-            keep = np.ones(len(prep["lights"]), bool) if c < 0 or c >= light_sees.shape[1] else light_sees[:, c]
+        # one K3 call per distinct light subset: clusters that see the same lights go to the device together
+        nc = light_sees.shape[1]
+        masks = np.concatenate([light_sees.T, np.ones((1, light_sees.shape[0]), bool)])      # row nc = "sees every light" (cluster -1)
+        row = np.where((cl >= 0) & (cl < nc), cl, nc)
+        uniq, inverse = np.unique(masks, axis=0, return_inverse=True)
+        group = inverse.reshape(-1)[row]
+        for g in np.unique(group):
+            keep = uniq[g]
             if keep.any():
+                sel = np.nonzero(group == g)[0]
                 out[sel] = np.asarray(env.direct_light(np.ascontiguousarray(pos[sel]), np.ascontiguousarray(nrm[sel]), prep["lights"][keep]))
         return out
 
