@@ -11,32 +11,27 @@
 // rad/start.go:66-98): read the lumps, make the ray-trace triangles, the face patches and their subdivision, the face extents
 // and the lighting-lump layout, and print the counts.  Needs no GPU; tests/test_bsp_cpu.py checks the numbers.
 static int bsp_summary(const char* path) {
-    vrad_bspfile* f = nullptr;
-    vrad_bsp_lumps L;
-    if (vrad_bspfile_open(path, &f) || vrad_bspfile_lumps(f, &L)) { std::fprintf(stderr, "%s\n", vrad_last_error()); return 1; }
-    int n_tris = 0, n_faces = 0, n_points = 0, oversize = 0;
-    if (vrad_bsp_raytrace_triangles(&L, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, &n_tris) ||
-        vrad_bsp_face_patches(&L, nullptr, 4.0f, 0, 0, &n_faces, &n_points, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) {
-        std::fprintf(stderr, "%s\n", vrad_last_error()); return 1;
-    }
-    std::vector<vrad_face_patch> faces(n_faces);
-    std::vector<float> points(3 * (size_t)n_points);
-    if (vrad_bsp_face_patches(&L, nullptr, 4.0f, n_faces, n_points, &n_faces, &n_points, faces.data(), points.data(), nullptr, nullptr, nullptr, nullptr, nullptr)) {
-        std::fprintf(stderr, "%s\n", vrad_last_error()); return 1;
-    }
-    patches::PatchTree t = patches::SubdividePatches(faces, points);
+    vrad_bspfile* probe = nullptr;
+    if (vrad_bspfile_open(path, &probe)) { std::fprintf(stderr, "%s\n", vrad_last_error()); return 1; }     // a missing file is an error message, not an abort
+    vrad_bspfile_close(probe);
+    loadbsp::Bsp bsp(path);
+    const vrad_bsp_lumps& L = bsp.lumps;
+    const loadbsp::RayTraceTriangles tris = loadbsp::BrushesForRayTrace(L);
+    const patches::FacePatches fp = patches::MakePatches(L);
+    patches::PatchTree t = patches::SubdividePatches(fp.faces, fp.points3);
     int leaves = 0;
     for (int i = 0; i < t.size(); i++) leaves += t.child1[i] == -1;
+    const lightmap::FaceNeighbours fn = lightmap::PairEdges(L);
     std::vector<int32_t> mins(2 * (size_t)L.n_faces), size(2 * (size_t)L.n_faces);
     std::vector<int64_t> first((size_t)L.n_faces + 1);
     int64_t lump_bytes = 0;
+    int oversize = 0;
     if (vrad_bsp_face_extents(&L, mins.data(), size.data(), &oversize) ||
         vrad_bsp_layout_lighting(&L, mins.data(), size.data(), nullptr, first.data(), &lump_bytes)) {
         std::fprintf(stderr, "%s\n", vrad_last_error()); return 1;
     }
-    std::printf("bsp faces %d brushes %d triangles %d patches %d leaves %d luxels %lld lighting_bytes %lld oversize %d\n",
-                L.n_faces, L.n_brushes, n_tris, t.size(), leaves, (long long)first[L.n_faces], (long long)lump_bytes, oversize);
-    vrad_bspfile_close(f);
+    std::printf("bsp faces %d brushes %d triangles %d patches %d leaves %d luxels %lld lighting_bytes %lld oversize %d neighbours %d\n",
+                L.n_faces, L.n_brushes, (int)tris.ids.size(), t.size(), leaves, (long long)first[L.n_faces], (long long)lump_bytes, oversize, (int)fn.neighbours.size());
     return 0;
 }
 

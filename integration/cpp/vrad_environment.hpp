@@ -16,12 +16,16 @@
 //   trace::PointLeafnum               raytracer/trace/pointleaf.go:8-10
 //   cameras::ProcessSkyCameras        rad/cameras/skycamera.go:10-49
 //   patches::SubdividePatches         rad/patches/subdivide.go:25-145 (+ MakePatchForFace, rad/patches/face.go:29-197)
+//   loadbsp::LoadBSP / AddBrushesForRayTrace   cmd/tasks/loadbsp/main.go:163-170, 186-340
+//   patches::MakePatches              rad/patches/build.go:21-65
+//   lightmap::PairEdges               rad/lightmap/lightmap.go:37-216
 #pragma once
 #include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include "vrad_cuda.h"
+#include "vrad_bsp.h"
 
 namespace raytracer {
 
@@ -169,3 +173,73 @@ inline PatchTree SubdividePatches(const std::vector<vrad_face_patch>& faces, con
 }
 
 } // namespace patches
+
+// ---- the BSP side (include/vrad_bsp.h) ------------------------------------------------------------------------------------------
+namespace loadbsp {
+
+// loadBSP + cache.BuildLumpCache (cmd/tasks/loadbsp/main.go:163-170, cache/bsp.go:51-91): the file and typed views of its lumps
+struct Bsp {
+    vrad_bspfile* file = nullptr;
+    vrad_bsp_lumps lumps{};
+    explicit Bsp(const char* path) {
+        raytracer::fatal_on(vrad_bspfile_open(path, &file), "vrad_bspfile_open");
+        raytracer::fatal_on(vrad_bspfile_lumps(file, &lumps), "vrad_bspfile_lumps");
+    }
+    ~Bsp() { vrad_bspfile_close(file); }
+    Bsp(const Bsp&) = delete;
+    Bsp& operator=(const Bsp&) = delete;
+};
+
+// ExtractBrushEntityShadowCasters + addBrushesForRayTrace (main.go:186-340): ids and vertices of the triangles, in the reference's order
+struct RayTraceTriangles { std::vector<int32_t> ids; std::vector<float> verts9; };
+inline RayTraceTriangles BrushesForRayTrace(const vrad_bsp_lumps& L, const std::vector<int32_t>& casterModel = {}, const std::vector<float>& casterOrigin3 = {},
+                                            const std::vector<float>& casterAngles3 = {}) {
+    const int nc = static_cast<int>(casterModel.size());
+    int n = 0;
+    raytracer::fatal_on(vrad_bsp_raytrace_triangles(&L, nc, casterModel.data(), casterOrigin3.data(), casterAngles3.data(), 0, nullptr, nullptr, &n), "vrad_bsp_raytrace_triangles");
+    RayTraceTriangles t;
+    t.ids.resize(n); t.verts9.resize(9 * static_cast<size_t>(n));
+    raytracer::fatal_on(vrad_bsp_raytrace_triangles(&L, nc, casterModel.data(), casterOrigin3.data(), casterAngles3.data(), n, t.ids.data(), t.verts9.data(), &n), "vrad_bsp_raytrace_triangles");
+    return t;
+}
+// the same, straight into the environment ("Setup ray tracer", main.go:132-150); SetupAccelerationStructure is the caller's next step
+inline int AddBrushesForRayTrace(raytracer::Environment& env, const vrad_bsp_lumps& L) {
+    int n = 0;
+    raytracer::fatal_on(vrad_env_add_bsp(env.handle(), &L, 0, nullptr, nullptr, nullptr, &n), "vrad_env_add_bsp");
+    return n;
+}
+
+}  // namespace loadbsp
+
+namespace patches {
+
+// MakePatches (rad/patches/build.go:21-65): one record per non-displacement face, ready for SubdividePatches
+struct FacePatches { std::vector<vrad_face_patch> faces; std::vector<float> points3; std::vector<int32_t> faceNumber; std::vector<float> reflectivity3; };
+inline FacePatches MakePatches(const vrad_bsp_lumps& L, const std::vector<float>& modelOrigins3 = {}, float maxChop = 4.0f) {
+    const float* mo = modelOrigins3.empty() ? nullptr : modelOrigins3.data();
+    int nf = 0, np = 0;
+    raytracer::fatal_on(vrad_bsp_face_patches(&L, mo, maxChop, 0, 0, &nf, &np, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr), "vrad_bsp_face_patches");
+    FacePatches f;
+    f.faces.resize(nf); f.points3.resize(3 * static_cast<size_t>(np)); f.faceNumber.resize(nf); f.reflectivity3.resize(3 * static_cast<size_t>(nf));
+    raytracer::fatal_on(vrad_bsp_face_patches(&L, mo, maxChop, nf, np, &nf, &np, f.faces.data(), f.points3.data(), f.faceNumber.data(), f.reflectivity3.data(),
+                                              nullptr, nullptr, nullptr), "vrad_bsp_face_patches");
+    return f;
+}
+
+}  // namespace patches
+
+namespace lightmap {
+
+// PairEdges (rad/lightmap/lightmap.go:37-216): smoothed normals per face-vertex + neighbour lists
+struct FaceNeighbours { std::vector<float> vertexNormals3; std::vector<int32_t> first, neighbours; };
+inline FaceNeighbours PairEdges(const vrad_bsp_lumps& L, float smoothingThreshold = 0.7071067f) {
+    size_t nfv = 0;
+    for (int i = 0; i < L.n_faces; i++) nfv += static_cast<size_t>(L.faces[i].numedges);
+    FaceNeighbours fn;
+    fn.vertexNormals3.resize(3 * nfv + 3); fn.first.resize(static_cast<size_t>(L.n_faces) + 1); fn.neighbours.resize(64 * static_cast<size_t>(L.n_faces) + 1);
+    raytracer::fatal_on(vrad_bsp_pair_edges(&L, smoothingThreshold, fn.vertexNormals3.data(), fn.first.data(), fn.neighbours.data(), static_cast<int>(fn.neighbours.size())), "vrad_bsp_pair_edges");
+    fn.neighbours.resize(static_cast<size_t>(fn.first[L.n_faces]));
+    return fn;
+}
+
+}  // namespace lightmap

@@ -546,7 +546,8 @@ def test_cpp_driver_reads_the_same_file(smap, tmp_path):
     prep = bake.prepare(L, meta["entities"])
     t = prep["tree"]
     assert got == dict(faces=L.faces.shape[0], brushes=L.brushes.shape[0], triangles=prep["tri_ids"].shape[0] - 12, patches=t["origin"].shape[0],
-                       leaves=int((t["child1"] == -1).sum()), luxels=prep["lux_pos"].shape[0], lighting_bytes=prep["lump_bytes"], oversize=0)
+                       leaves=int((t["child1"] == -1).sum()), luxels=prep["lux_pos"].shape[0], lighting_bytes=prep["lump_bytes"], oversize=0,
+                       neighbours=int(B.pair_edges(L)[2].shape[0]))
     bad = subprocess.run([os.path.join(root, "integration", "cpp", "drive"), "--bsp", str(tmp_path / "nope.bsp")], capture_output=True, text=True)
     assert bad.returncode == 1 and "cannot open" in bad.stderr
 
