@@ -6,6 +6,7 @@
 #include <vector>
 #include "vrad_environment.hpp"
 #include "vrad_bsp.h"
+#include "vrad_bake.hpp"
 
 // `drive --bsp map.bsp`: the host-only half of loadbsp.Main + rad.Start on a real file (cmd/tasks/loadbsp/main.go:56-150,
 // rad/start.go:66-98): read the lumps, make the ray-trace triangles, the face patches and their subdivision, the face extents
@@ -35,8 +36,49 @@ static int bsp_summary(const char* path) {
     return 0;
 }
 
+// `drive --prepare map.bsp`: the host half of the bake (bake::Prepare) with a checksum per array; tests/test_bsp_cpu.py compares them with
+// what vrad_b200/bake.py prepares from the same file.  No GPU.
+static int bake_prepare(const char* path) {
+    vrad_bspfile* probe = nullptr;
+    if (vrad_bspfile_open(path, &probe)) { std::fprintf(stderr, "%s\n", vrad_last_error()); return 1; }
+    vrad_bspfile_close(probe);
+    loadbsp::Bsp bsp(path);
+    const void* ent = nullptr; int64_t len = 0;
+    vrad_bspfile_get_lump(bsp.file, VRAD_LUMP_ENTITIES, &ent, &len, nullptr);
+    std::string text(static_cast<const char*>(ent), static_cast<size_t>(len));
+    while (!text.empty() && text.back() == '\0') text.pop_back();
+    bake::Prepared P;
+    bake::Prepare(bsp.lumps, text, P);
+    auto line = [](const char* name, uint64_t sum, size_t count) { std::printf("%s %llu %zu\n", name, (unsigned long long)sum, count); };
+    line("tri_ids", bake::Checksum(P.tris.ids), P.tris.ids.size()); line("tri_verts", bake::Checksum(P.tris.verts9), P.tris.verts9.size());
+    line("origin", bake::Checksum(P.tree.origin), P.tree.origin.size()); line("normal", bake::Checksum(P.tree.normal), P.tree.normal.size());
+    line("plane_dist", bake::Checksum(P.tree.plane_dist), P.tree.plane_dist.size()); line("area", bake::Checksum(P.tree.area), P.tree.area.size());
+    line("parent", bake::Checksum(P.tree.parent), P.tree.parent.size()); line("child1", bake::Checksum(P.tree.child1), P.tree.child1.size());
+    line("face_of_patch", bake::Checksum(P.face_of_patch), P.face_of_patch.size()); line("cluster", bake::Checksum(P.cluster), P.cluster.size());
+    line("flags", bake::Checksum(P.flags), P.flags.size()); line("refl", bake::Checksum(P.refl3), P.refl3.size());
+    line("pvs", bake::Checksum(P.pvs), P.pvs.size()); line("sky_pvs", bake::Checksum(P.sky_pvs), P.sky_pvs.size());
+    line("lights", bake::Checksum(P.lights), P.lights.size());
+    line("lm_mins", bake::Checksum(P.mins2), P.mins2.size()); line("lm_size", bake::Checksum(P.size2), P.size2.size());
+    line("lit_faces", bake::Checksum(P.lit_faces), P.lit_faces.size()); line("luxel_first", bake::Checksum(P.luxel_first), P.luxel_first.size());
+    line("lux_pos", bake::Checksum(P.lux_pos3), P.lux_pos3.size()); line("lux_normal", bake::Checksum(P.lux_normal3), P.lux_normal3.size());
+    line("lux_face", bake::Checksum(P.lux_face), P.lux_face.size());
+    line("radial_first", bake::Checksum(P.radial_first), P.radial_first.size()); line("radial_entries", bake::Checksum(P.radial), P.radial.size());
+    std::printf("lump_bytes %lld\n", (long long)P.lump_bytes);
+    return 0;
+}
+
+// `drive --bake in.bsp out.bsp anorms.txt`: the whole job on the GPU (bake::BakeFile); prints what tests/test_gpu_zz_bsp_bake.py checks
+static int bake_file(const char* in, const char* out, const char* anorms) {
+    const bake::Lit lit = bake::BakeFile(in, out, anorms);
+    std::printf("baked transfers %lld bounces %d direct %llu emit %llu total %llu\n", (long long)lit.nnz, lit.bounces,
+                (unsigned long long)bake::Checksum(lit.direct3), (unsigned long long)bake::Checksum(lit.emit3), (unsigned long long)bake::Checksum(lit.total3));
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc == 3 && !std::strcmp(argv[1], "--bsp")) return bsp_summary(argv[2]);
+    if (argc == 3 && !std::strcmp(argv[1], "--prepare")) return bake_prepare(argv[2]);
+    if (argc == 5 && !std::strcmp(argv[1], "--bake")) return bake_file(argv[2], argv[3], argv[4]);
     raytracer::Environment env;
     // a 256^3 room (6 inward quads) with two box occluders, ids as loadbsp assigns them
     env.AddAxisAlignedRectangularSolid(raytracer::TRACE_ID_OPAQUE, {0, 0, 0}, {256, 256, 256});

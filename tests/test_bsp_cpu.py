@@ -859,3 +859,39 @@ def test_samples_are_placed_on_their_faces(smap):
     n_flat = (size[bump_face, 0] + 1) * (size[bump_face, 1] + 1)
     blocks = placed[first[bump_face]:first[bump_face + 1]].reshape(4, n_flat, 3)
     assert np.array_equal(blocks[0], blocks[1]) and np.array_equal(blocks[0], blocks[3])
+
+
+def _word_checksum(a) -> int:
+    """bake::Checksum of integration/cpp/vrad_bake.hpp: sum of word_i * (2654435761 * i + 1) over the 32-bit words, wrapping at 2^64."""
+    b = np.ascontiguousarray(a).tobytes()
+    b += b"\0" * (-len(b) % 4)
+    w = np.frombuffer(b, "<u4").astype(np.uint64)
+    with np.errstate(over="ignore"):
+        return int(np.sum(w * (np.uint64(2654435761) * np.arange(w.shape[0], dtype=np.uint64) + np.uint64(1)), dtype=np.uint64))
+
+
+def test_cpp_bake_prepares_what_the_python_mirror_prepares(smap, tmp_path):
+    """integration/cpp/vrad_bake.hpp (the C++ stand-in for the reference's Go host side) against vrad_b200/bake.py: every array the
+    device stages take -- triangles, patch tree with phong normals, clusters, PVS, lights, luxel samples, radial entries, the laid-out
+    face lump -- byte for byte, from the same .bsp file.  No GPU."""
+    import subprocess
+    from vrad_b200 import bake
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L, meta = smap
+    path = str(tmp_path / "m.bsp")
+    B.write_bsp(path, L, meta)
+    subprocess.run(["make", "-C", os.path.join(root, "integration", "cpp")], check=True, capture_output=True)
+    out = subprocess.run([os.path.join(root, "integration", "cpp", "drive"), "--prepare", path], check=True, capture_output=True, text=True).stdout
+    got = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out.splitlines()}
+    prep = bake.prepare(L, meta["entities"])
+    t = prep["tree"]
+    mine = dict(tri_ids=prep["tri_ids"], tri_verts=prep["tri_verts"], origin=t["origin"], normal=t["normal"], plane_dist=t["plane_dist"], area=t["area"],
+                parent=t["parent"], child1=t["child1"], face_of_patch=prep["face_of_patch"], cluster=prep["cluster"], flags=prep["flags"], refl=prep["refl"],
+                pvs=prep["pvs"], sky_pvs=prep["sky_pvs"], lights=prep["lights"], lm_mins=prep["lm_mins"], lm_size=prep["lm_size"], lit_faces=prep["lumps"].faces,
+                luxel_first=prep["luxel_first"], lux_pos=prep["lux_pos"], lux_normal=prep["lux_normal"], lux_face=prep["lux_face"],
+                radial_first=prep["radial_first"], radial_entries=prep["radial_entries"])
+    assert sorted(got) == sorted(list(mine) + ["lump_bytes"])
+    for k, v in mine.items():
+        assert got[k][0] == _word_checksum(v), k
+        assert got[k][1] == np.asarray(v).size if v.dtype.names is None else got[k][1] == v.shape[0], k
+    assert got["lump_bytes"] == [prep["lump_bytes"]]
