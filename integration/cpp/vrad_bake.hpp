@@ -333,8 +333,14 @@ inline std::vector<uint8_t> Finish(raytracer::Environment& env, const Prepared& 
 inline std::vector<float> ReadSkyDirs(const std::string& path) {             // vmath.Anorms as text: 162 lines of x y z
     std::vector<float> d;
     std::ifstream in(path);
-    float v;
-    while (in >> v) d.push_back(v);
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty() || line[0] == '#') continue;                      // comment lines, as numpy.loadtxt skips them
+        std::istringstream ls(line);
+        float v;
+        while (ls >> v) d.push_back(v);
+    }
+    if (d.size() % 3 != 0 || d.empty()) { std::fprintf(stderr, "ReadSkyDirs: %s holds %zu numbers, expected triples\n", path.c_str(), d.size()); std::abort(); }
     return d;
 }
 
