@@ -36,9 +36,9 @@ static int bsp_summary(const char* path) {
     return 0;
 }
 
-// `drive --prepare map.bsp`: the host half of the bake (bake::Prepare) with a checksum per array; tests/test_bsp_cpu.py compares them with
+// `drive --prepare map.bsp [lights.rad]`: the host half of the bake (bake::Prepare) with a checksum per array; tests/test_bsp_cpu.py compares them with
 // what vrad_b200/bake.py prepares from the same file.  No GPU.
-static int bake_prepare(const char* path) {
+static int bake_prepare(const char* path, const char* lights_rad = nullptr) {
     vrad_bspfile* probe = nullptr;
     if (vrad_bspfile_open(path, &probe)) { std::fprintf(stderr, "%s\n", vrad_last_error()); return 1; }
     vrad_bspfile_close(probe);
@@ -48,7 +48,9 @@ static int bake_prepare(const char* path) {
     std::string text(static_cast<const char*>(ent), static_cast<size_t>(len));
     while (!text.empty() && text.back() == '\0') text.pop_back();
     bake::Prepared P;
-    bake::Prepare(bsp.lumps, text, P);
+    bake::TexLights tex;
+    if (lights_rad) bake::LoadTexLights(bsp, path, lights_rad, tex);
+    bake::Prepare(bsp.lumps, text, P, lights_rad ? &tex : nullptr);
     auto line = [](const char* name, uint64_t sum, size_t count) { std::printf("%s %llu %zu\n", name, (unsigned long long)sum, count); };
     line("tri_ids", bake::Checksum(P.tris.ids), P.tris.ids.size()); line("tri_verts", bake::Checksum(P.tris.verts9), P.tris.verts9.size());
     line("origin", bake::Checksum(P.tree.origin), P.tree.origin.size()); line("normal", bake::Checksum(P.tree.normal), P.tree.normal.size());
@@ -67,9 +69,9 @@ static int bake_prepare(const char* path) {
     return 0;
 }
 
-// `drive --bake in.bsp out.bsp anorms.txt`: the whole job on the GPU (bake::BakeFile); prints what tests/test_gpu_zz_bsp_bake.py checks
-static int bake_file(const char* in, const char* out, const char* anorms) {
-    const bake::Lit lit = bake::BakeFile(in, out, anorms);
+// `drive --bake in.bsp out.bsp anorms.txt [lights.rad]`: the whole job on the GPU (bake::BakeFile); prints what tests/test_gpu_zz_bsp_bake.py checks
+static int bake_file(const char* in, const char* out, const char* anorms, const char* lights_rad) {
+    const bake::Lit lit = bake::BakeFile(in, out, anorms, 0, 8, lights_rad);
     std::printf("baked transfers %lld bounces %d direct %llu emit %llu total %llu\n", (long long)lit.nnz, lit.bounces,
                 (unsigned long long)bake::Checksum(lit.direct3), (unsigned long long)bake::Checksum(lit.emit3), (unsigned long long)bake::Checksum(lit.total3));
     return 0;
@@ -77,8 +79,8 @@ static int bake_file(const char* in, const char* out, const char* anorms) {
 
 int main(int argc, char** argv) {
     if (argc == 3 && !std::strcmp(argv[1], "--bsp")) return bsp_summary(argv[2]);
-    if (argc == 3 && !std::strcmp(argv[1], "--prepare")) return bake_prepare(argv[2]);
-    if (argc == 5 && !std::strcmp(argv[1], "--bake")) return bake_file(argv[2], argv[3], argv[4]);
+    if ((argc == 3 || argc == 4) && !std::strcmp(argv[1], "--prepare")) return bake_prepare(argv[2], argc == 4 ? argv[3] : nullptr);
+    if ((argc == 5 || argc == 6) && !std::strcmp(argv[1], "--bake")) return bake_file(argv[2], argv[3], argv[4], argc == 6 ? argv[5] : nullptr);
     raytracer::Environment env;
     // a 256^3 room (6 inward quads) with two box occluders, ids as loadbsp assigns them
     env.AddAxisAlignedRectangularSolid(raytracer::TRACE_ID_OPAQUE, {0, 0, 0}, {256, 256, 256});

@@ -121,7 +121,11 @@ inline int PointCluster(const vrad_bsp_lumps& L, const float p[3]) {
 }
 
 // everything the device stages take, from the lumps (host code of the library; no GPU needed)
-inline void Prepare(const vrad_bsp_lumps& L, const std::string& entityText, Prepared& P, float minChop = 4.0f, float maxChop = 4.0f, float smoothing = 0.7071067f) {
+// texlights: the text of a lights.rad file plus the texdata string lumps (LUMP_TEXDATA_STRING_TABLE / _DATA) and the map's name
+struct TexLights { std::string radText, mapName; const int32_t* stringTable = nullptr; int nStrings = 0; const char* stringData = nullptr; int64_t stringLen = 0; bool hdr = false; };
+
+inline void Prepare(const vrad_bsp_lumps& L, const std::string& entityText, Prepared& P, const TexLights* tex = nullptr,
+                    float minChop = 4.0f, float maxChop = 4.0f, float smoothing = 0.7071067f) {
     P.ents = ParseEntities(entityText);
     // ExtractBrushEntityShadowCasters (main.go:186-211) + the "origin" of every brush model's entity (MakePatches, build.go:38-45)
     std::vector<int32_t> casterModel; std::vector<float> casterOrigin, casterAngles, modelOrigins(3 * static_cast<size_t>(L.n_models), 0.0f);
@@ -136,6 +140,16 @@ inline void Prepare(const vrad_bsp_lumps& L, const std::string& entityText, Prep
     }
     P.tris = loadbsp::BrushesForRayTrace(L, casterModel, casterOrigin, casterAngles);
     patches::FacePatches fp = patches::MakePatches(L, modelOrigins, maxChop);
+    // BaseLightForFace (rad/patches/face.go:208-280): faces whose material is a texlight emit, and are not edge-chopped
+    std::vector<float> faceBaseLight(3 * fp.faces.size(), 0.0f);
+    if (tex) {
+        int nt = 0;
+        fatal_on(vrad_texlights_parse(tex->radText.data(), static_cast<int64_t>(tex->radText.size()), tex->hdr, 0, nullptr, &nt, nullptr, 0, nullptr, nullptr, nullptr), "vrad_texlights_parse");
+        std::vector<vrad_texlight> table(static_cast<size_t>(nt) + 1);
+        fatal_on(vrad_texlights_parse(tex->radText.data(), static_cast<int64_t>(tex->radText.size()), tex->hdr, nt, table.data(), &nt, nullptr, 0, nullptr, nullptr, nullptr), "vrad_texlights_parse");
+        fatal_on(vrad_bsp_apply_texlights(&L, tex->stringTable, tex->nStrings, tex->stringData, tex->stringLen, tex->mapName.c_str(), nt, table.data(),
+                                          static_cast<int>(fp.faces.size()), fp.faceNumber.data(), fp.faces.data(), faceBaseLight.data()), "vrad_bsp_apply_texlights");
+    }
     P.tree = patches::SubdividePatches(fp.faces, fp.points3, minChop);
     const int N = P.tree.size(), nf = L.n_faces;
     P.face_of_patch.resize(N); P.refl3.resize(3 * static_cast<size_t>(N)); P.flags.resize(N);
@@ -236,6 +250,25 @@ inline void Prepare(const vrad_bsp_lumps& L, const std::string& entityText, Prep
     int nLights = 0;
     fatal_on(vrad_lights_from_entities(static_cast<int>(le.size()), le.data(), static_cast<int>(P.lights.size()), P.lights.data(), &nLights), "vrad_lights_from_entities");
     P.lights.resize(nLights);
+    // ... and the surface part (lights.go:49-82), which comes first in the list
+    bool emits = false;
+    for (float v : faceBaseLight) emits = emits || v != 0.0f;
+    if (emits) {
+        std::vector<float> base(3 * static_cast<size_t>(N)), scale(2 * static_cast<size_t>(N)), baseArea(N);
+        for (int p = 0; p < N; p++) {
+            const int f = P.tree.face[p];
+            for (int k = 0; k < 3; k++) base[3 * static_cast<size_t>(p) + k] = faceBaseLight[3 * static_cast<size_t>(f) + k];
+            scale[2 * static_cast<size_t>(p)] = fp.scale2[2 * static_cast<size_t>(f)]; scale[2 * static_cast<size_t>(p) + 1] = fp.scale2[2 * static_cast<size_t>(f) + 1];
+            baseArea[p] = fp.baseArea[f];
+        }
+        std::vector<vrad_light> surf(static_cast<size_t>(N) + 1);
+        int ns = 0;
+        fatal_on(vrad_lights_from_patches(N, P.tree.origin.data(), P.tree.normal.data(), base.data(), P.tree.area.data(), scale.data(), baseArea.data(), P.tree.child1.data(),
+                                          0.1f, static_cast<int>(surf.size()), surf.data(), &ns), "vrad_lights_from_patches");
+        surf.resize(ns);
+        surf.insert(surf.end(), P.lights.begin(), P.lights.end());
+        P.lights.swap(surf);
+    }
 }
 
 struct Lit { int64_t nnz = 0; int bounces = 0; std::vector<float> direct3, emit3, total3; };
@@ -345,14 +378,32 @@ inline std::vector<float> ReadSkyDirs(const std::string& path) {             // 
 }
 
 // .bsp in -> lit .bsp out
-inline Lit BakeFile(const char* pathIn, const char* pathOut, const std::string& skyDirsPath, int device = 0, int bounces = 8) {
+inline std::string ReadText(const std::string& path) { std::ifstream in(path, std::ios::binary); std::stringstream ss; ss << in.rdbuf(); return ss.str(); }
+inline std::string MapName(const std::string& path) {
+    const size_t slash = path.find_last_of("/\\"), dot = path.rfind('.');
+    const size_t a = slash == std::string::npos ? 0 : slash + 1;
+    return path.substr(a, (dot == std::string::npos || dot < a) ? std::string::npos : dot - a);
+}
+// fills `tex` from the file's string lumps and a lights.rad path; the pointers stay valid while `bsp` lives
+inline void LoadTexLights(const loadbsp::Bsp& bsp, const std::string& bspPath, const std::string& radPath, TexLights& tex) {
+    const void* p = nullptr; int64_t n = 0;
+    fatal_on(vrad_bspfile_get_lump(bsp.file, VRAD_LUMP_TEXDATA_STRING_TABLE, &p, &n, nullptr), "vrad_bspfile_get_lump");
+    tex.stringTable = static_cast<const int32_t*>(p); tex.nStrings = static_cast<int>(n / 4);
+    fatal_on(vrad_bspfile_get_lump(bsp.file, VRAD_LUMP_TEXDATA_STRING_DATA, &p, &n, nullptr), "vrad_bspfile_get_lump");
+    tex.stringData = static_cast<const char*>(p); tex.stringLen = n;
+    tex.radText = ReadText(radPath); tex.mapName = MapName(bspPath);
+}
+
+inline Lit BakeFile(const char* pathIn, const char* pathOut, const std::string& skyDirsPath, int device = 0, int bounces = 8, const char* lightsRadPath = nullptr) {
     loadbsp::Bsp bsp(pathIn);
     const void* ent = nullptr; int64_t entLen = 0;
     fatal_on(vrad_bspfile_get_lump(bsp.file, VRAD_LUMP_ENTITIES, &ent, &entLen, nullptr), "vrad_bspfile_get_lump");
     std::string text(static_cast<const char*>(ent), static_cast<size_t>(entLen));
     while (!text.empty() && text.back() == '\0') text.pop_back();
     Prepared P;
-    Prepare(bsp.lumps, text, P);
+    TexLights tex;
+    if (lightsRadPath) LoadTexLights(bsp, pathIn, lightsRadPath, tex);
+    Prepare(bsp.lumps, text, P, lightsRadPath ? &tex : nullptr);
     raytracer::Environment env(device);
     const Lit lit = Light(env, P, ReadSkyDirs(skyDirsPath), bounces);
     const std::vector<uint8_t> lump = Finish(env, P, lit);

@@ -214,15 +214,19 @@ inline int AddBrushesForRayTrace(raytracer::Environment& env, const vrad_bsp_lum
 namespace patches {
 
 // MakePatches (rad/patches/build.go:21-65): one record per non-displacement face, ready for SubdividePatches
-struct FacePatches { std::vector<vrad_face_patch> faces; std::vector<float> points3; std::vector<int32_t> faceNumber; std::vector<float> reflectivity3; };
+struct FacePatches {
+    std::vector<vrad_face_patch> faces; std::vector<float> points3; std::vector<int32_t> faceNumber;
+    std::vector<float> reflectivity3, baseArea, scale2; std::vector<uint8_t> needsBump;
+};
 inline FacePatches MakePatches(const vrad_bsp_lumps& L, const std::vector<float>& modelOrigins3 = {}, float maxChop = 4.0f) {
     const float* mo = modelOrigins3.empty() ? nullptr : modelOrigins3.data();
     int nf = 0, np = 0;
     raytracer::fatal_on(vrad_bsp_face_patches(&L, mo, maxChop, 0, 0, &nf, &np, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr), "vrad_bsp_face_patches");
     FacePatches f;
     f.faces.resize(nf); f.points3.resize(3 * static_cast<size_t>(np)); f.faceNumber.resize(nf); f.reflectivity3.resize(3 * static_cast<size_t>(nf));
+    f.baseArea.resize(nf); f.scale2.resize(2 * static_cast<size_t>(nf)); f.needsBump.resize(nf);
     raytracer::fatal_on(vrad_bsp_face_patches(&L, mo, maxChop, nf, np, &nf, &np, f.faces.data(), f.points3.data(), f.faceNumber.data(), f.reflectivity3.data(),
-                                              nullptr, nullptr, nullptr), "vrad_bsp_face_patches");
+                                              f.baseArea.data(), f.needsBump.data(), f.scale2.data()), "vrad_bsp_face_patches");
     return f;
 }
 

@@ -881,9 +881,24 @@ def test_cpp_bake_prepares_what_the_python_mirror_prepares(smap, tmp_path):
     path = str(tmp_path / "m.bsp")
     B.write_bsp(path, L, meta)
     subprocess.run(["make", "-C", os.path.join(root, "integration", "cpp")], check=True, capture_output=True)
-    out = subprocess.run([os.path.join(root, "integration", "cpp", "drive"), "--prepare", path], check=True, capture_output=True, text=True).stdout
+    for with_rad in (False, True):
+        _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path)
+
+
+def _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path):
+    import subprocess
+    from vrad_b200 import bake
+    cmd = [os.path.join(root, "integration", "cpp", "drive"), "--prepare", path]
+    kw = {}
+    if with_rad:
+        rad = str(tmp_path / "lights.rad")
+        open(rad, "w", newline="").write(LIGHTS_RAD)
+        cmd.append(rad)
+        kw = dict(lights_rad=LIGHTS_RAD, texdata_strings=(meta["string_table"], meta["string_data"]), map_name="m")
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
     got = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out.splitlines()}
-    prep = bake.prepare(L, meta["entities"])
+    prep = bake.prepare(L, meta["entities"], **kw)
+    assert (prep["lights"]["type"] == 0).any() == with_rad             # surface lights only with the texlight table
     t = prep["tree"]
     mine = dict(tri_ids=prep["tri_ids"], tri_verts=prep["tri_verts"], origin=t["origin"], normal=t["normal"], plane_dist=t["plane_dist"], area=t["area"],
                 parent=t["parent"], child1=t["child1"], face_of_patch=prep["face_of_patch"], cluster=prep["cluster"], flags=prep["flags"], refl=prep["refl"],
