@@ -910,3 +910,41 @@ def _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path):
         assert got[k][0] == _word_checksum(v), k
         assert got[k][1] == np.asarray(v).size if v.dtype.names is None else got[k][1] == v.shape[0], k
     assert got["lump_bytes"] == [prep["lump_bytes"]]
+
+
+def test_cpp_bake_end_to_end_on_the_oracle(smap, tmp_path):
+    """bake::BakeFile (integration/cpp/vrad_bake.hpp) run WITHOUT a GPU: the test binary links tests/helpers/oracle_device_shim.cpp, which puts
+    the CPU oracle behind the device entry points the C++ bake calls.  Its lit .bsp must equal what the Python mirror produces with the
+    oracle's environment and the host twins of the radial filter and K5 -- lump for lump.  (On a GPU the same comparison runs against the
+    real kernels: tests/test_gpu_zzz_cpp_bake.py.)"""
+    import subprocess
+    from oracle import pyoracle
+    from vrad_b200 import bake
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pyoracle.build()
+    exe = str(tmp_path / "drive_on_oracle")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-fopenmp", "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "integration", "cpp"), "-o", exe,
+                    os.path.join(root, "integration", "cpp", "drive_main.cpp"), os.path.join(root, "tests", "helpers", "oracle_device_shim.cpp"),
+                    "-L" + os.path.join(root, "vrad_b200", "_lib"), "-lvradcuda", "-L" + os.path.join(root, "oracle", "_build"), "-loracle",
+                    "-Wl,-rpath," + os.path.join(root, "vrad_b200", "_lib"), "-Wl,-rpath," + os.path.join(root, "oracle", "_build")], check=True, capture_output=True)
+    L, meta = B.synthetic_map(2, 2, boxes_per_room=4, sky_rooms=(1,), bump_rooms=(0,))
+    src, dst = str(tmp_path / "in.bsp"), str(tmp_path / "cpp.bsp")
+    B.write_bsp(src, L, meta)
+    anorms = os.path.join(root, "vrad_b200", "data", "anorms.txt")
+    r = subprocess.run([exe, "--bake", src, dst, anorms], check=True, capture_output=True, text=True)
+    words = r.stdout.split()
+    got = {words[i]: int(words[i + 1]) for i in range(1, len(words), 2)}
+    # the Python mirror on the oracle's environment
+    prep = bake.prepare(L, meta["entities"], texdata_strings=(meta["string_table"], meta["string_data"]), map_name="in")
+    lit = bake.light(pyoracle.OracleEnv(), prep, bounces=8)
+    assert got["transfers"] == lit["nnz"] and got["bounces"] == lit["bounces_done"]
+    assert got["direct"] == _word_checksum(lit["direct"]) and got["emit"] == _word_checksum(lit["emit0"]) and got["total"] == _word_checksum(lit["total"])
+    ind = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"])
+    lump = B.pack_lighting(prep["lumps"], prep["luxel_first"], B.color_to_rgbexp32(lit["direct"] + ind), prep["lump_bytes"])
+    f = B.BspFile(dst)
+    assert f.get(B.LUMP["LIGHTING"]) == (lump, 1)
+    assert np.array_equal(f.lumps().faces, prep["lumps"].faces) and f.get(B.LUMP["FACES"])[1] == 1
+    for k in L.a:
+        if k != "faces":
+            assert np.array_equal(L.a[k], f.lumps().a[k]), k
+    f.close()
