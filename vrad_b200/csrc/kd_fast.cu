@@ -313,9 +313,9 @@ struct HostExec {
     cudaError_t err = cudaSuccess;
     void* alloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
     void free(void* p) { std::free(p); }
-    void zero(void* p, size_t bytes) { std::memset(p, 0, bytes); }
-    void upload(void* d, const void* h, size_t bytes) { std::memcpy(d, h, bytes); }
-    void download(void* h, const void* d, size_t bytes) { std::memcpy(h, d, bytes); }
+    void zero(void* p, size_t bytes) { if (bytes) std::memset(p, 0, bytes); }
+    void upload(void* d, const void* h, size_t bytes) { if (bytes) std::memcpy(d, h, bytes); }
+    void download(void* h, const void* d, size_t bytes) { if (bytes) std::memcpy(h, d, bytes); }
     template <class F> void for_each(int64_t n, F f) {
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n; i++) f(i);
