@@ -76,3 +76,25 @@ def test_splitmix64_reference_vector():
     from vrad_b200.scenes import SplitMix64
     got = SplitMix64(1234567).u64(3)
     assert [int(x) for x in got] == [6457827717110365317, 3203168211198807973, 9817491932198370423]
+
+
+def test_bsp_side_entry_points_reject_null_arguments():
+    """Every entry point of include/vrad_bsp.h called with nothing but zeros / NULLs: a status (0 only where 'nothing to do' is a valid
+    request), never a crash.  (x86-64 SysV: surplus integer arguments are ignored by the callee.)"""
+    import ctypes as C
+    from vrad_b200 import bspfile, lib
+    handle = lib.load()
+    zeros = [C.c_void_p(0)] * 14
+    ok_on_empty = {"vrad_bsp_rescale_lightmap_vecs", "vrad_color_to_rgbexp32", "vrad_color_from_rgbexp32", "vrad_luxel_nearest_patch",
+                   "vrad_luxel_radial_light_host"}
+    for sym in bspfile.SYMBOLS:
+        fn = getattr(handle, sym)
+        if sym == "vrad_bspfile_close":
+            fn.restype = None
+            fn(None)
+            continue
+        fn.restype = C.c_int
+        rc = fn(*zeros)
+        assert (rc == 0) if sym in ok_on_empty else (rc < 0), (sym, rc)
+        if rc < 0:
+            assert handle.vrad_last_error()                      # and it says why
