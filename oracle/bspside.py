@@ -272,7 +272,8 @@ def face_patches(L, model_origins=None, max_chop=4.0):
             out["no_subdivide"].append(1 if (fl & SURF_NOCHOP) or ((fl & SURF_NOLIGHT) and not (fl & SURF_LIGHT)) else 0)
             out["face_number"].append(fn)
             out["reflectivity"].append([min(F(td["reflectivity"][k]) * F(1.0), F(0.99)) for k in range(3)])
-            out["base_area"].append(F(int(td["height"]) * int(td["width"])))
+            prod = (int(td["height"]) * int(td["width"]) + 2 ** 31) % 2 ** 32 - 2 ** 31       # Go: int32 product, wrapping
+            out["base_area"].append(F(prod))
             out["needs_bump"].append(1 if fl & SURF_BUMPLIGHT else 0)
             out["scale"].append(scale)
     return out

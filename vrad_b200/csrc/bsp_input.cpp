@@ -309,7 +309,7 @@ extern "C" int vrad_bsp_face_patches(const vrad_bsp_lumps* Lp, const float* mode
                 o.has_base_light = 0;                                       // texlights (lights.rad) stay with the Go driver
                 if (face_number) face_number[nf] = fn;
                 if (reflectivity3) for (int k = 0; k < 3; k++) { const float r = td.reflectivity[k] * 1.0f; reflectivity3[3 * (size_t)nf + k] = r > 0.99f ? 0.99f : r; }
-                if (base_area) base_area[nf] = (float)(td.height * td.width);
+                if (base_area) base_area[nf] = (float)(int32_t)((uint32_t)td.height * (uint32_t)td.width);       // Go's int32 product wraps (face.go:219)
                 if (needs_bump) needs_bump[nf] = (tx.flags & VRAD_SURF_BUMPLIGHT) ? 1 : 0;
                 if (scale2) { scale2[2 * (size_t)nf] = sc[0]; scale2[2 * (size_t)nf + 1] = sc[1]; }
             }
