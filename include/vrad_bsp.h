@@ -215,7 +215,8 @@ int  vrad_bsp_phong_normals(const vrad_bsp_lumps*, float smoothing_threshold, co
  * for SURF_BUMPLIGHT faces.  faces_out (n_faces records, may be NULL) = the face lump with lightofs pointing at the first
  * sample, styles = {0,255,255,255}, lm_mins / lm_size from vrad_bsp_face_extents; SURF_SKY / SURF_NOLIGHT faces get
  * lightofs -1.  luxel_first (n_faces + 1) = offset of each face's samples in the luxel arrays K3 / K5 work on (unlit faces:
- * empty range); *lump_bytes = size of the lump. */
+ * empty range); *lump_bytes = size of the lump.  A lit face larger than 126 luxels on a side (vrad_bsp_face_extents counts them) is an
+ * error here: "Bad surface extents", as upstream has it (the reference logs and goes on, rad/world/face.go:66-87). */
 int  vrad_bsp_layout_lighting(const vrad_bsp_lumps*, const int32_t* mins2, const int32_t* size2, vrad_dface* faces_out,
                               int64_t* luxel_first, int64_t* lump_bytes);
 /* Sample positions for K3 (upstream InitLightinfo / CalcPoints, UNCITED; without upstream's nudging of samples that fall off

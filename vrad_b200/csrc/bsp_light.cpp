@@ -203,6 +203,13 @@ extern "C" int vrad_bsp_layout_lighting(const vrad_bsp_lumps* Lp, const int32_t*
             o.lightofs = -1;
             for (int k = 0; k < 4; k++) o.styles[k] = 255;
         } else {
+            // world.CalcFaceExtents (rad/world/face.go:66-87) logs such a face and carries on with the fatal error commented out; upstream
+            // stops ("Bad surface extents - surface is too big to have a lightmap").  A lightmap larger than the format allows cannot be
+            // laid out, so this is where the job stops here as well.
+            if (size2[2 * (size_t)i] > 126 || size2[2 * (size_t)i + 1] > 126) {
+                vrad::set_error("Bad surface extents - face %d is too big to have a lightmap (%d x %d luxels, limit 126)", i, size2[2 * (size_t)i], size2[2 * (size_t)i + 1]);
+                return VRAD_E_INVALID;
+            }
             const int64_t samples = (int64_t)(size2[2 * (size_t)i] + 1) * (size2[2 * (size_t)i + 1] + 1) * (face_is_bumped(L, f) ? 4 : 1);
             bytes += 4;                                                      // the style's average colour sits right before the samples
             if (bytes + samples * 4 > INT32_MAX) { vrad::set_error("vrad_bsp_layout_lighting: lighting lump would exceed 2 GiB at face %d", i); return VRAD_E_INVALID; }
