@@ -58,6 +58,7 @@ static int bake_prepare(const char* path, const char* lights_rad = nullptr) {
     line("parent", bake::Checksum(P.tree.parent), P.tree.parent.size()); line("child1", bake::Checksum(P.tree.child1), P.tree.child1.size());
     line("face_of_patch", bake::Checksum(P.face_of_patch), P.face_of_patch.size()); line("cluster", bake::Checksum(P.cluster), P.cluster.size());
     line("flags", bake::Checksum(P.flags), P.flags.size()); line("refl", bake::Checksum(P.refl3), P.refl3.size());
+    line("needs_bump", bake::Checksum(P.needs_bump), P.needs_bump.size()); line("bump_basis", bake::Checksum(P.bump_basis9), P.bump_basis9.size());
     line("pvs", bake::Checksum(P.pvs), P.pvs.size()); line("sky_pvs", bake::Checksum(P.sky_pvs), P.sky_pvs.size());
     line("lights", bake::Checksum(P.lights), P.lights.size());
     line("lm_mins", bake::Checksum(P.mins2), P.mins2.size()); line("lm_size", bake::Checksum(P.size2), P.size2.size());
@@ -72,8 +73,9 @@ static int bake_prepare(const char* path, const char* lights_rad = nullptr) {
 // `drive --bake in.bsp out.bsp anorms.txt [lights.rad]`: the whole job on the GPU (bake::BakeFile); prints what tests/test_gpu_zz_bsp_bake.py checks
 static int bake_file(const char* in, const char* out, const char* anorms, const char* lights_rad) {
     const bake::Lit lit = bake::BakeFile(in, out, anorms, 0, 8, lights_rad);
-    std::printf("baked transfers %lld bounces %d direct %llu emit %llu total %llu\n", (long long)lit.nnz, lit.bounces,
-                (unsigned long long)bake::Checksum(lit.direct3), (unsigned long long)bake::Checksum(lit.emit3), (unsigned long long)bake::Checksum(lit.total3));
+    std::printf("baked transfers %lld bounces %d direct %llu emit %llu total %llu bump %llu\n", (long long)lit.nnz, lit.bounces,
+                (unsigned long long)bake::Checksum(lit.direct3), (unsigned long long)bake::Checksum(lit.emit3), (unsigned long long)bake::Checksum(lit.total3),
+                (unsigned long long)bake::Checksum(lit.bump9));
     return 0;
 }
 

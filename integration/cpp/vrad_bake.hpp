@@ -92,6 +92,8 @@ struct Prepared {
     patches::PatchTree tree;
     std::vector<int32_t> face_of_patch, cluster;
     std::vector<uint8_t> flags;                      // bit 0 = sky
+    std::vector<uint8_t> needs_bump;                 // Patch.NeedsBumpMap (SURF_BUMPLIGHT)
+    std::vector<float> bump_basis9;                  // upstream GetBumpNormals per bump-mapped patch (zero elsewhere)
     std::vector<float> refl3, face_origin3, centroids3;
     std::vector<uint8_t> pvs;                        // n_clusters x n_clusters (empty: no vis data)
     int n_clusters = 0;
@@ -175,6 +177,15 @@ inline void Prepare(const vrad_bsp_lumps& L, const std::string& entityText, Prep
         std::vector<float> nrm(kidPoint.size());
         fatal_on(vrad_bsp_phong_normals(&L, smoothing, P.neighbours.vertexNormals3.data(), P.centroids3.data(), static_cast<int64_t>(kids.size()), kidFace.data(), kidPoint.data(), nrm.data()), "vrad_bsp_phong_normals");
         for (size_t i = 0; i < kids.size(); i++) for (int k = 0; k < 3; k++) P.tree.normal[3 * static_cast<size_t>(kids[i]) + k] = nrm[3 * i + k];
+    }
+    // Patch.NeedsBumpMap + the bump basis around the patch's (phong) normal
+    P.needs_bump.assign(N, 0); P.bump_basis9.assign(9 * static_cast<size_t>(N), 0.0f);
+    for (int p = 0; p < N; p++) {
+        if (!fp.needsBump[P.tree.face[p]]) continue;
+        P.needs_bump[p] = 1;
+        const vrad_dface& fc = L.faces[P.face_of_patch[p]];
+        const vrad_texinfo& tx = L.texinfo[fc.texinfo];
+        fatal_on(vrad_bump_normals(tx.texture_vecs[0], tx.texture_vecs[1], L.planes[fc.planenum].normal, &P.tree.normal[3 * static_cast<size_t>(p)], &P.bump_basis9[9 * static_cast<size_t>(p)]), "vrad_bump_normals");
     }
     // cluster of a face = cluster of the first leaf that lists it; faces of brush models: the leaf their model sits in
     std::vector<int32_t> faceCluster(nf, -1);
@@ -271,7 +282,7 @@ inline void Prepare(const vrad_bsp_lumps& L, const std::string& entityText, Prep
     }
 }
 
-struct Lit { int64_t nnz = 0; int bounces = 0; std::vector<float> direct3, emit3, total3; };
+struct Lit { int64_t nnz = 0; int bounces = 0; std::vector<float> direct3, emit3, total3, bump9; };
 
 // K3 for a block of points with DirectLight.PVS honoured: one device call per distinct light subset (see vrad_b200/bake.py)
 inline void DirectLightCulled(raytracer::Environment& env, const Prepared& P, const std::vector<std::vector<uint8_t>>& lightSees, int64_t n, const float* pos3, const float* nrm3, float* out3) {
@@ -309,6 +320,9 @@ inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vect
     fatal_on(vrad_patches_upload(env.handle(), N, P.tree.origin.data(), P.tree.normal.data(), P.tree.plane_dist.data(), P.tree.area.data(), P.refl3.data(), P.cluster.data(), P.flags.data()), "vrad_patches_upload");
     fatal_on(vrad_patches_set_hierarchy(env.handle(), N, P.tree.parent.data(), P.tree.child1.data(), P.tree.child2.data(), P.tree.face.data()), "vrad_patches_set_hierarchy");
     Lit out;
+    bool bumped = false;
+    for (uint8_t b : P.needs_bump) bumped = bumped || b;
+    if (bumped) fatal_on(vrad_patches_set_bump(env.handle(), N, P.needs_bump.data(), P.bump_basis9.data()), "vrad_patches_set_bump");
     fatal_on(vrad_build_transfers(env.handle(), P.n_clusters, P.pvs.empty() ? nullptr : P.pvs.data(), &out.nnz), "vrad_build_transfers");
     bool ambient = false;
     for (const vrad_light& l : P.lights) ambient = ambient || l.type == 5;
@@ -344,6 +358,7 @@ inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vect
     DirectLightCulled(env, P, lightSees, N, lifted.data(), P.tree.normal.data(), out.emit3.data());
     float added[3];
     fatal_on(vrad_bounce(env.handle(), out.emit3.data(), bounces, 1, out.total3.data(), added, &out.bounces), "vrad_bounce");
+    if (bumped) { out.bump9.resize(9 * static_cast<size_t>(N)); fatal_on(vrad_bounce_bump_totals(env.handle(), out.bump9.data()), "vrad_bounce_bump_totals"); }
     return out;
 }
 
@@ -354,7 +369,8 @@ inline std::vector<uint8_t> Finish(raytracer::Environment& env, const Prepared& 
     std::vector<float> indirect(3 * static_cast<size_t>(nl) + 3);
     std::vector<vrad_radial_entry> none(1);
     fatal_on(vrad_luxel_radial_light(env.handle(), nl, P.lux_face.data(), nf, P.luxel_first.data(), P.size2.data(), P.radial_first.data(),
-                                     P.radial.empty() ? none.data() : P.radial.data(), N, lit.total3.data(), nullptr, indirect.data()), "vrad_luxel_radial_light");
+                                     P.radial.empty() ? none.data() : P.radial.data(), N, lit.total3.data(), lit.bump9.empty() ? nullptr : lit.bump9.data(), indirect.data()),
+             "vrad_luxel_radial_light");
     std::vector<vrad_color_rgbexp32> colors(static_cast<size_t>(nl) + 1);
     fatal_on(vrad_lightmap_finalize(env.handle(), nl, lit.direct3.data(), indirect.data(), colors.data()), "vrad_lightmap_finalize");
     std::vector<uint8_t> lump(static_cast<size_t>(P.lump_bytes) + 1);

@@ -39,6 +39,8 @@ int vrad_direct_light(vrad_env* e, int64_t n, const float* pos3, const float* no
 int vrad_bounce(vrad_env* e, const float* emit0, int n_bounces, int early_out, float* total, float added[3], int* done) {
     return orc_bounce(e->o, emit0, n_bounces, early_out, total, added, done, kThreads);
 }
+int vrad_patches_set_bump(vrad_env* e, int n, const uint8_t* needs_bump, const float* bump_normals9) { return orc_patches_set_bump(e->o, n, needs_bump, bump_normals9); }
+int vrad_bounce_bump_totals(vrad_env* e, float* out9) { return orc_bounce_bump_totals(e->o, out9); }
 int vrad_luxel_radial_light(vrad_env*, int64_t n, const int32_t* luxel_face, int n_faces, const int64_t* luxel_first, const int32_t* size2, const int64_t* entry_first,
                             const vrad_radial_entry* entries, int n_patches, const float* patch_total3, const float* patch_bump9, float* out) {
     return vrad_luxel_radial_light_host(n, luxel_face, n_faces, luxel_first, size2, entry_first, entries, n_patches, patch_total3, patch_bump9, out);

@@ -901,7 +901,7 @@ def _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path):
     assert (prep["lights"]["type"] == 0).any() == with_rad             # surface lights only with the texlight table
     t = prep["tree"]
     mine = dict(tri_ids=prep["tri_ids"], tri_verts=prep["tri_verts"], origin=t["origin"], normal=t["normal"], plane_dist=t["plane_dist"], area=t["area"],
-                parent=t["parent"], child1=t["child1"], face_of_patch=prep["face_of_patch"], cluster=prep["cluster"], flags=prep["flags"], refl=prep["refl"],
+                parent=t["parent"], child1=t["child1"], needs_bump=prep["needs_bump"], bump_basis=prep["bump_basis"], face_of_patch=prep["face_of_patch"], cluster=prep["cluster"], flags=prep["flags"], refl=prep["refl"],
                 pvs=prep["pvs"], sky_pvs=prep["sky_pvs"], lights=prep["lights"], lm_mins=prep["lm_mins"], lm_size=prep["lm_size"], lit_faces=prep["lumps"].faces,
                 luxel_first=prep["luxel_first"], lux_pos=prep["lux_pos"], lux_normal=prep["lux_normal"], lux_face=prep["lux_face"],
                 radial_first=prep["radial_first"], radial_entries=prep["radial_entries"])
@@ -939,7 +939,8 @@ def test_cpp_bake_end_to_end_on_the_oracle(smap, tmp_path):
     lit = bake.light(pyoracle.OracleEnv(), prep, bounces=8)
     assert got["transfers"] == lit["nnz"] and got["bounces"] == lit["bounces_done"]
     assert got["direct"] == _word_checksum(lit["direct"]) and got["emit"] == _word_checksum(lit["emit0"]) and got["total"] == _word_checksum(lit["total"])
-    ind = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"])
+    assert lit["bump_totals"].any() and got["bump"] == _word_checksum(lit["bump_totals"])
+    ind = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"], lit["bump_totals"])
     lump = B.pack_lighting(prep["lumps"], prep["luxel_first"], B.color_to_rgbexp32(lit["direct"] + ind), prep["lump_bytes"])
     f = B.BspFile(dst)
     assert f.get(B.LUMP["LIGHTING"]) == (lump, 1)

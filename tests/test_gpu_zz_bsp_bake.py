@@ -137,16 +137,17 @@ def test_bsp_file_bake(tmp_path):
     # the same device stages on the CPU oracle
     ref = bake.light(pyoracle.OracleEnv(), prep, bounces=8)
     assert lit["nnz"] == ref["nnz"] and lit["bounces_done"] == ref["bounces_done"]
-    for key in ("direct", "emit0", "total"):
+    for key in ("direct", "emit0", "total", "bump_totals"):
         assert np.abs(lit[key] - ref[key]).max() <= RTOL * float(np.abs(ref[key]).max()), key
+    assert lit["bump_totals"].any()                                # room 0's floor is SURF_BUMPLIGHT
     assert lit["direct"].max() > 1 and lit["total"].max() > 1
     # radial filter + K5 == the same functor on the host's cores + the host pack function, on the GPU's own inputs; the lump is what
     # pack_lighting makes of it
-    ind = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"])
+    ind = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"], lit["bump_totals"])
     assert np.array_equal(_rows(res["colors"]), _rows(B.color_to_rgbexp32(lit["direct"] + ind)))
     assert res["lump"] == B.pack_lighting(prep["lumps"], prep["luxel_first"], res["colors"], prep["lump_bytes"])
     # against the oracle's light the decoded luxels agree to the 8-bit truncation step (one part in 128 of the largest component)
-    ind_ref = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], ref["total"])
+    ind_ref = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], ref["total"], ref["bump_totals"])
     want = ref["direct"] + ind_ref
     got = B.color_from_rgbexp32(res["colors"])
     step = np.maximum(want.max(axis=1, keepdims=True), 1e-3) / 64

@@ -34,6 +34,7 @@ def test_cpp_driver_bakes_the_same_file(tmp_path):
     lit = res["lit"]
     assert got["transfers"] == lit["nnz"] and got["bounces"] == lit["bounces_done"]
     assert got["direct"] == checksum(lit["direct"]) and got["emit"] == checksum(lit["emit0"]) and got["total"] == checksum(lit["total"])
+    assert got["bump"] == checksum(lit["bump_totals"])
     a, b = B.BspFile(out_py), B.BspFile(out_cpp)
     for lump in range(64):
         assert a.get(lump) == b.get(lump), lump

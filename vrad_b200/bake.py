@@ -23,7 +23,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import bspfile as B
-from .environment import lights_from_entities, lights_from_patches, light_for_string, pvs_from_vis_lump, subdivide_patches
+from .environment import bump_normals, lights_from_entities, lights_from_patches, light_for_string, pvs_from_vis_lump, subdivide_patches
 from .lib import LIGHT_ENTITY_DTYPE, VradError
 
 
@@ -189,6 +189,14 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
         lux_normal[flat_block] = B.phong_normals(L, vn, centroids, lux_face[flat_block], on_surface, smoothing_threshold)
     lux_patch = B.luxel_nearest_patch(lux_face, lux_pos, face_of_patch, tree["origin"], tree["child1"])
     sky = fp["faces"]["sky"][tree["face"]].astype(np.uint8)
+    # Patch.NeedsBumpMap (SURF_BUMPLIGHT, rad/patches/face.go:66-70) and the bump basis of every such patch: upstream GetBumpNormals with the
+    # face's texture vectors, the face normal and the patch's (phong) normal
+    needs_bump = fp["needs_bump"][tree["face"]].astype(np.uint8)
+    bump_basis = np.zeros((tree["origin"].shape[0], 3, 3), np.float32)
+    for p in np.nonzero(needs_bump)[0]:
+        tx = L.texinfo[L.faces["texinfo"][face_of_patch[p]]]
+        flat = L.planes["normal"][L.faces["planenum"][face_of_patch[p]]]
+        bump_basis[p] = bump_normals(tx["texture_vecs"][0][:3], tx["texture_vecs"][1][:3], flat, tree["normal"][p])
     from .scenes import Bsp
     bsp = Bsp(L.nodes["planenum"].astype(np.int32), L.nodes["children"].astype(np.int32), L.planes["normal"].astype(np.float32),
               L.planes["dist"].astype(np.float32), L.planes["type"].astype(np.int32), L.leafs["cluster"].astype(np.int32),
@@ -199,7 +207,7 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
                                    fp["base_area"][tree["face"]], tree["child1"])
         lights = np.concatenate([surf, lights])
     entry_first, entries = B.radial_entries(Llit, mins, tree, face_of_patch, face_origin, nb_first, nb)
-    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, face_origin=face_origin, face_centroids=centroids, lux_grid_pos=grid_pos, lm_mins=mins, lm_size=size, vertex_normals=vn,
+    return dict(ents=ents, bsp=bsp, sky_pvs=sky_pvs, needs_bump=needs_bump, bump_basis=bump_basis, face_origin=face_origin, face_centroids=centroids, lux_grid_pos=grid_pos, lm_mins=mins, lm_size=size, vertex_normals=vn,
                 radial_first=entry_first, radial_entries=entries, base_light=base_light[tree["face"]].astype(np.float32), tri_ids=tri_ids, tri_verts=tri_verts, tree=tree, refl=fp["reflectivity"][tree["face"]].astype(np.float32),
                 cluster=face_cluster[face_of_patch].astype(np.int32), flags=sky, pvs=pvs, lights=lights,
                 lumps=Llit, luxel_first=luxel_first, lump_bytes=lump_bytes, lux_pos=lux_pos, lux_normal=lux_normal, lux_face=lux_face,
@@ -234,6 +242,8 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int =
     env.setup_acceleration_structure() if hasattr(env, "setup_acceleration_structure") else env.build()
     env.patches_upload(t["origin"], t["normal"], t["plane_dist"], t["area"], prep["refl"], prep["cluster"], prep["flags"])
     env.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
+    if prep["needs_bump"].any() and world == 1:                       # TotalLight.Light[1..3] of the bump-mapped leaf patches (single GPU)
+        env.set_bump(prep["needs_bump"], prep["bump_basis"])
     nnz = env.build_transfers(prep["pvs"])
     if np.any(prep["lights"]["type"] == 5):                            # EMIT_SKYAMBIENT samples the sky along vmath.Anorms
         env.set_sky_dirs(anorms())
@@ -283,7 +293,8 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int =
     direct = lit_points(prep["lux_pos"], prep["lux_normal"])
     emit0 = lit_points(lifted, t["normal"])
     total, _, done = env.bounce(emit0, bounces, early_out)
-    return dict(nnz=int(nnz), direct=direct, emit0=emit0, total=np.asarray(total), bounces_done=int(done))
+    bump = np.asarray(env.bump_totals()) if (prep["needs_bump"].any() and world == 1) else None
+    return dict(nnz=int(nnz), direct=direct, emit0=emit0, total=np.asarray(total), bump_totals=bump, bounces_done=int(done))
 
 
 def finish(env, prep: dict, lit: dict, rank: int = 0, world: int = 1, device=None, indirect: str = "radial") -> tuple[bytes, np.ndarray]:
@@ -294,7 +305,8 @@ def finish(env, prep: dict, lit: dict, rank: int = 0, world: int = 1, device=Non
     parts = range_partition(lit["direct"].shape[0], world)
     a, b = parts[rank]
     if b > a and indirect == "radial":
-        ind = B.luxel_radial_light(env, prep["lux_face"][a:b], prep["luxel_first"] - a, prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"])
+        ind = B.luxel_radial_light(env, prep["lux_face"][a:b], prep["luxel_first"] - a, prep["lm_size"], prep["radial_first"], prep["radial_entries"], lit["total"],
+                                   lit.get("bump_totals"))    # the three extra blocks of a bump-mapped face take TotalLight.Light[1..3]
         mine = B.lightmap_finalize(env, lit["direct"][a:b], ind)
     elif b > a:
         mine = B.lightmap_finalize_patches(env, lit["direct"][a:b], prep["lux_patch"][a:b], lit["total"])
