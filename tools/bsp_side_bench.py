@@ -72,13 +72,29 @@ def bake_part(device):
         f.set(lighting_lump, lump, version=1); f.set(face_lump, prep["lumps"].faces, version=1); f.save(dst); f.close()
         t5 = time.perf_counter()
         out_size = os.path.getsize(dst)
+    # cpu_baseline leg: the same device stages on the CPU oracle (the checker, timed beside -- never on the product path), all host threads
+    cpu = None
+    try:
+        from oracle import pyoracle
+
+        class AllThreads(pyoracle.OracleEnv):
+            T = pyoracle.num_threads()
+            def build_transfers(self, pvs=None, threads=None): return super().build_transfers(pvs, threads=self.T)
+            def direct_light(self, pos, normal, lights, threads=None): return super().direct_light(pos, normal, lights, threads=self.T)
+            def bounce(self, emit0, n, early_out=False, threads=None): return super().bounce(emit0, n, early_out, threads=self.T)
+        c0 = time.perf_counter(); ref = bake.light(AllThreads(), prep, bounces=8); c1 = time.perf_counter()
+        worst = max(float(np.abs(lit[k] - ref[k]).max() / max(np.abs(ref[k]).max(), 1e-30)) for k in ("direct", "emit0", "total"))
+        cpu = {"kind": "port", "cores": AllThreads.T, "light_k1_k2_k3_k4_seconds": c1 - c0, "transfers": ref["nnz"], "bounces": ref["bounces_done"],
+               "max_relative_difference_gpu_vs_oracle": worst, "transfers_equal": bool(ref["nnz"] == lit["nnz"])}
+    except Exception as exc:
+        cpu = {"error": repr(exc)}
     return {"workload": "synthetic BSP v20 map at the C3/C4 size (12 x 11 rooms), .bsp in -> lit .bsp out through vrad_b200.bake; first call of every stage",
             "faces": int(Lm.faces.shape[0]), "triangles": int(prep["tri_ids"].shape[0]), "patches": int(prep["tree"]["origin"].shape[0]),
             "leaf_patches": int((prep["tree"]["child1"] == -1).sum()), "luxels": int(prep["lux_pos"].shape[0]), "lights": int(prep["lights"].shape[0]),
             "transfers": lit["nnz"], "bounces": lit["bounces_done"],
             "seconds": {"read": t1 - t0, "prepare_host": t2 - t1, "light_k1_k2_k3_k4": t3 - t2, "radial_k5_pack": t4 - t3, "write": t5 - t4, "total": t5 - t0},
             "lit_luxel_fraction": float((colors.view(np.uint8).reshape(-1, 4)[:, :3].max(axis=1) > 0).mean()),
-            "lighting_lump_bytes": len(lump), "file_bytes": out_size}
+            "lighting_lump_bytes": len(lump), "file_bytes": out_size, "cpu_baseline": cpu}
 
 
 def kd_part(dev, device, stream):
