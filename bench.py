@@ -442,7 +442,7 @@ def run_graft(args, rank, local_rank, world):
     if world == 1 and not args.no_large:
         try:
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bsp_side_bench.py"), "--device", str(local_rank), "--hbm-peak", str(hbm_peak)],
-                               capture_output=True, text=True, timeout=180)
+                               capture_output=True, text=True, timeout=240)
             lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
             bsp_side = json.loads(lines[-1]) if lines else {"error": f"exit {r.returncode}", "stderr": r.stderr[-800:]}
         except Exception as exc:  # informational only: never take the bench line down
