@@ -426,6 +426,15 @@ inline Lit BakeFile(const char* pathIn, const char* pathOut, const std::string& 
     fatal_on(vrad_bspfile_set_lump(bsp.file, VRAD_LUMP_LIGHTING, lump.data(), static_cast<int64_t>(lump.size()), 1), "vrad_bspfile_set_lump");
     // P.lumps.faces points at P.lit_faces (our copy), so replacing the face lump does not pull the rug from under it
     fatal_on(vrad_bspfile_set_lump(bsp.file, VRAD_LUMP_FACES, P.lit_faces.data(), static_cast<int64_t>(P.lit_faces.size() * sizeof(vrad_dface)), 1), "vrad_bspfile_set_lump");
+    {   // lightmap.SaveVertexNormals (rad/start.go:82-85): the vertex-normal lumps, "for use in the engine"
+        const int nfv = static_cast<int>(P.neighbours.vertexNormals3.size() / 3) - 1;       // PairEdges leaves one spare entry
+        std::vector<float> normals(3 * static_cast<size_t>(std::max(nfv, 1)));
+        std::vector<uint16_t> indices(static_cast<size_t>(std::max(nfv, 1)));
+        int nn = 0;
+        fatal_on(vrad_bsp_save_vertex_normals(nfv, P.neighbours.vertexNormals3.data(), std::max(nfv, 1), normals.data(), indices.data(), &nn), "vrad_bsp_save_vertex_normals");
+        fatal_on(vrad_bspfile_set_lump(bsp.file, VRAD_LUMP_VERTNORMALS, normals.data(), static_cast<int64_t>(nn) * 12, 0), "vrad_bspfile_set_lump");
+        fatal_on(vrad_bspfile_set_lump(bsp.file, VRAD_LUMP_VERTNORMALINDICES, indices.data(), static_cast<int64_t>(nfv) * 2, 0), "vrad_bspfile_set_lump");
+    }
     fatal_on(vrad_bspfile_save(bsp.file, pathOut), "vrad_bspfile_save");
     return lit;
 }

@@ -945,6 +945,9 @@ def test_cpp_bake_end_to_end_on_the_oracle(smap, tmp_path):
     f = B.BspFile(dst)
     assert f.get(B.LUMP["LIGHTING"]) == (lump, 1)
     assert np.array_equal(f.lumps().faces, prep["lumps"].faces) and f.get(B.LUMP["FACES"])[1] == 1
+    normals, indices = B.save_vertex_normals(prep["vertex_normals"])                 # SaveVertexNormals' lumps travel with the file
+    assert f.get(B.LUMP["VERTNORMALS"])[0] == normals.tobytes() and f.get(B.LUMP["VERTNORMALINDICES"])[0] == indices.tobytes()
+    assert indices.shape[0] == int(L.faces["numedges"].sum()) and normals.shape[0] < indices.shape[0]
     for k in L.a:
         if k != "faces":
             assert np.array_equal(L.a[k], f.lumps().a[k]), k

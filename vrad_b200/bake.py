@@ -345,6 +345,10 @@ def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, ra
         if rank == 0:
             f.set(lighting_lump, lump, version=1)
             f.set(face_lump, prep["lumps"].faces, version=1)
+            # lightmap.SaveVertexNormals (rad/start.go:82-85): "store the vertex normals calculated in PairEdges so that they can be written
+            # to the bsp file for use in the engine"
+            normals, indices = B.save_vertex_normals(prep["vertex_normals"])
+            f.set(B.LUMP["VERTNORMALS"], normals); f.set(B.LUMP["VERTNORMALINDICES"], indices)
             f.save(path_out)
     finally:
         f.close()
