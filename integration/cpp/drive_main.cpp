@@ -36,21 +36,42 @@ static int bsp_summary(const char* path) {
     return 0;
 }
 
-// `drive --prepare map.bsp [lights.rad]`: the host half of the bake (bake::Prepare) with a checksum per array; tests/test_bsp_cpu.py compares them with
+// `drive --prepare map.bsp [switches]`: the host half of the bake (bake::Prepare) with a checksum per array; tests/test_bsp_cpu.py compares them with
 // what vrad_b200/bake.py prepares from the same file.  No GPU.
-static int bake_prepare(const char* path, const char* lights_rad = nullptr) {
+// trailing switches shared by --prepare and --bake: [-lights f] [-bounce n] [-luxeldensity x] [-smooth deg] [-chop c] [-maxchop c] [-hdr] [-fast] [-textureshadows]
+static bake::Options parse_options(int argc, char** argv, int first) {
+    bake::Options o;
+    for (int i = first; i < argc; i++) {
+        const std::string a = argv[i];
+        auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : "0"; };
+        if (a == "-lights") o.lightsRad = next();
+        else if (a == "-bounce") o.bounce = std::atoi(next());
+        else if (a == "-luxeldensity") o.luxelDensity = static_cast<float>(std::atof(next()));
+        else if (a == "-smooth") o.smoothDegrees = static_cast<float>(std::atof(next()));
+        else if (a == "-chop") o.chop = static_cast<float>(std::atof(next()));
+        else if (a == "-maxchop") o.maxChop = static_cast<float>(std::atof(next()));
+        else if (a == "-hdr") o.hdr = true;
+        else if (a == "-fast") o.fast = true;
+        else if (a == "-textureshadows") o.textureShadows = true;
+        else { std::fprintf(stderr, "unknown switch %s\n", a.c_str()); std::exit(2); }
+    }
+    return o;
+}
+
+static int bake_prepare(const char* path, const bake::Options& opt) {
+    const char* lights_rad = opt.lightsRad.empty() ? nullptr : opt.lightsRad.c_str();
     vrad_bspfile* probe = nullptr;
     if (vrad_bspfile_open(path, &probe)) { std::fprintf(stderr, "%s\n", vrad_last_error()); return 1; }
     vrad_bspfile_close(probe);
-    loadbsp::Bsp bsp(path);
+    loadbsp::Bsp bsp(path, opt.hdr);
     const void* ent = nullptr; int64_t len = 0;
     vrad_bspfile_get_lump(bsp.file, VRAD_LUMP_ENTITIES, &ent, &len, nullptr);
     std::string text(static_cast<const char*>(ent), static_cast<size_t>(len));
     while (!text.empty() && text.back() == '\0') text.pop_back();
     bake::Prepared P;
     bake::TexLights tex;
-    if (lights_rad) bake::LoadTexLights(bsp, path, lights_rad, tex);
-    bake::Prepare(bsp.lumps, text, P, lights_rad ? &tex : nullptr);
+    if (lights_rad) { bake::LoadTexLights(bsp, path, lights_rad, tex); tex.hdr = opt.hdr; }
+    bake::Prepare(bsp.lumps, text, P, lights_rad ? &tex : nullptr, opt.chop, opt.maxChop, opt.SmoothingThreshold(), opt.luxelDensity);
     auto line = [](const char* name, uint64_t sum, size_t count) { std::printf("%s %llu %zu\n", name, (unsigned long long)sum, count); };
     line("tri_ids", bake::Checksum(P.tris.ids), P.tris.ids.size()); line("tri_verts", bake::Checksum(P.tris.verts9), P.tris.verts9.size());
     line("origin", bake::Checksum(P.tree.origin), P.tree.origin.size()); line("normal", bake::Checksum(P.tree.normal), P.tree.normal.size());
@@ -70,9 +91,9 @@ static int bake_prepare(const char* path, const char* lights_rad = nullptr) {
     return 0;
 }
 
-// `drive --bake in.bsp out.bsp anorms.txt [lights.rad]`: the whole job on the GPU (bake::BakeFile); prints what tests/test_gpu_zz_bsp_bake.py checks
-static int bake_file(const char* in, const char* out, const char* anorms, const char* lights_rad) {
-    const bake::Lit lit = bake::BakeFile(in, out, anorms, 0, 8, lights_rad);
+// `drive --bake in.bsp out.bsp anorms.txt [switches]`: the whole job on the GPU (bake::BakeFile); prints what tests/test_gpu_zz_bsp_bake.py checks
+static int bake_file(const char* in, const char* out, const char* anorms, const bake::Options& opt) {
+    const bake::Lit lit = bake::BakeFile(in, out, anorms, 0, opt);
     std::printf("baked transfers %lld bounces %d direct %llu emit %llu total %llu bump %llu\n", (long long)lit.nnz, lit.bounces,
                 (unsigned long long)bake::Checksum(lit.direct3), (unsigned long long)bake::Checksum(lit.emit3), (unsigned long long)bake::Checksum(lit.total3),
                 (unsigned long long)bake::Checksum(lit.bump9));
@@ -81,8 +102,8 @@ static int bake_file(const char* in, const char* out, const char* anorms, const 
 
 int main(int argc, char** argv) {
     if (argc == 3 && !std::strcmp(argv[1], "--bsp")) return bsp_summary(argv[2]);
-    if ((argc == 3 || argc == 4) && !std::strcmp(argv[1], "--prepare")) return bake_prepare(argv[2], argc == 4 ? argv[3] : nullptr);
-    if ((argc == 5 || argc == 6) && !std::strcmp(argv[1], "--bake")) return bake_file(argv[2], argv[3], argv[4], argc == 6 ? argv[5] : nullptr);
+    if (argc >= 3 && !std::strcmp(argv[1], "--prepare")) return bake_prepare(argv[2], parse_options(argc, argv, 3));
+    if (argc >= 5 && !std::strcmp(argv[1], "--bake")) return bake_file(argv[2], argv[3], argv[4], parse_options(argc, argv, 5));
     raytracer::Environment env;
     // a 256^3 room (6 inward quads) with two box occluders, ids as loadbsp assigns them
     env.AddAxisAlignedRectangularSolid(raytracer::TRACE_ID_OPAQUE, {0, 0, 0}, {256, 256, 256});

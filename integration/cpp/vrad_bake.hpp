@@ -8,6 +8,7 @@
 // bounces) -> finish (cmd/tasks/finish/main.go:8-40: the lighting lump and the file).
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -101,6 +102,7 @@ struct Prepared {
     std::vector<vrad_light> lights;
     std::vector<int32_t> mins2, size2;
     std::vector<vrad_dface> lit_faces;
+    std::vector<vrad_texinfo> texinfo;               // the rescaled copy when -luxeldensity < 1 (empty otherwise)
     vrad_bsp_lumps lumps{};                          // the file's lumps with `faces` pointing at lit_faces
     std::vector<int64_t> luxel_first, radial_first;
     int64_t lump_bytes = 0;
@@ -123,11 +125,30 @@ inline int PointCluster(const vrad_bsp_lumps& L, const float p[3]) {
 }
 
 // everything the device stages take, from the lumps (host code of the library; no GPU needed)
+// the command-line switches of the reference that reach this path (cmd/args.go:53-93)
+struct Options {
+    int   bounce = 8;                 // -bounce
+    float luxelDensity = 1.0f;        // -luxeldensity
+    float smoothDegrees = 45.0f;      // -smooth
+    float chop = 4.0f, maxChop = 4.0f;   // -chop, -maxchop
+    bool  hdr = false;                // -hdr
+    bool  fast = false;               // -fast: here the binned kd build (RTE_FLAGS_FAST_TREE_GENERATION)
+    bool  textureShadows = false;     // -textureshadows
+    std::string lightsRad;            // -lights (path of a lights.rad; empty = none)
+    float SmoothingThreshold() const { return smoothDegrees == 45.0f ? 0.7071067f : static_cast<float>(std::cos(static_cast<double>(smoothDegrees) * 3.14159265358979323846 / 180.0)); }
+};
+
 // texlights: the text of a lights.rad file plus the texdata string lumps (LUMP_TEXDATA_STRING_TABLE / _DATA) and the map's name
 struct TexLights { std::string radText, mapName; const int32_t* stringTable = nullptr; int nStrings = 0; const char* stringData = nullptr; int64_t stringLen = 0; bool hdr = false; };
 
-inline void Prepare(const vrad_bsp_lumps& L, const std::string& entityText, Prepared& P, const TexLights* tex = nullptr,
-                    float minChop = 4.0f, float maxChop = 4.0f, float smoothing = 0.7071067f) {
+inline void Prepare(const vrad_bsp_lumps& Lfile, const std::string& entityText, Prepared& P, const TexLights* tex = nullptr,
+                    float minChop = 4.0f, float maxChop = 4.0f, float smoothing = 0.7071067f, float luxelDensity = 1.0f) {
+    vrad_bsp_lumps L = Lfile;
+    if (luxelDensity < 1.0f) {                                            // rad.Start (rad/start.go:21-66): luxels no denser than -luxeldensity
+        P.texinfo.assign(Lfile.texinfo, Lfile.texinfo + Lfile.n_texinfo);
+        fatal_on(vrad_bsp_rescale_lightmap_vecs(Lfile.n_texinfo, P.texinfo.data(), luxelDensity), "vrad_bsp_rescale_lightmap_vecs");
+        L.texinfo = P.texinfo.data();
+    }
     P.ents = ParseEntities(entityText);
     // ExtractBrushEntityShadowCasters (main.go:186-211) + the "origin" of every brush model's entity (MakePatches, build.go:38-45)
     std::vector<int32_t> casterModel; std::vector<float> casterOrigin, casterAngles, modelOrigins(3 * static_cast<size_t>(L.n_models), 0.0f);
@@ -311,12 +332,14 @@ inline void DirectLightCulled(raytracer::Environment& env, const Prepared& P, co
 }
 
 // the device stages: geometry + kd build (K1), transfers (K2), direct light on luxels and patches (K3), bounces (K4)
-inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vector<float>& skyDirs3, int bounces = 8) {
+inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vector<float>& skyDirs3, int bounces = 8, bool fastTree = false, bool textureShadows = false) {
     const vrad_bsp_lumps& L = P.lumps;
     const int N = P.tree.size();
     std::vector<uint8_t> triFlags(P.tris.ids.size(), 0);
     fatal_on(vrad_env_add_triangles(env.handle(), static_cast<int>(P.tris.ids.size()), P.tris.ids.data(), P.tris.verts9.data(), triFlags.data()), "vrad_env_add_triangles");
-    fatal_on(vrad_env_build(env.handle()), "vrad_env_build");
+    if (fastTree) fatal_on(vrad_env_build_fast(env.handle(), VRAD_BUILD_ON_DEVICE), "vrad_env_build_fast");
+    else fatal_on(vrad_env_build(env.handle()), "vrad_env_build");
+    if (textureShadows) fatal_on(vrad_set_light_trace_flags(env.handle(), VRAD_TL_TEXTURE_SHADOWS), "vrad_set_light_trace_flags");
     fatal_on(vrad_patches_upload(env.handle(), N, P.tree.origin.data(), P.tree.normal.data(), P.tree.plane_dist.data(), P.tree.area.data(), P.refl3.data(), P.cluster.data(), P.flags.data()), "vrad_patches_upload");
     fatal_on(vrad_patches_set_hierarchy(env.handle(), N, P.tree.parent.data(), P.tree.child1.data(), P.tree.child2.data(), P.tree.face.data()), "vrad_patches_set_hierarchy");
     Lit out;
@@ -410,22 +433,26 @@ inline void LoadTexLights(const loadbsp::Bsp& bsp, const std::string& bspPath, c
     tex.radText = ReadText(radPath); tex.mapName = MapName(bspPath);
 }
 
-inline Lit BakeFile(const char* pathIn, const char* pathOut, const std::string& skyDirsPath, int device = 0, int bounces = 8, const char* lightsRadPath = nullptr) {
-    loadbsp::Bsp bsp(pathIn);
+inline Lit BakeFile(const char* pathIn, const char* pathOut, const std::string& skyDirsPath, int device = 0, const Options& opt = Options()) {
+    const char* lightsRadPath = opt.lightsRad.empty() ? nullptr : opt.lightsRad.c_str();
+    const int bounces = opt.bounce;
+    loadbsp::Bsp bsp(pathIn, opt.hdr);
     const void* ent = nullptr; int64_t entLen = 0;
     fatal_on(vrad_bspfile_get_lump(bsp.file, VRAD_LUMP_ENTITIES, &ent, &entLen, nullptr), "vrad_bspfile_get_lump");
     std::string text(static_cast<const char*>(ent), static_cast<size_t>(entLen));
     while (!text.empty() && text.back() == '\0') text.pop_back();
     Prepared P;
     TexLights tex;
-    if (lightsRadPath) LoadTexLights(bsp, pathIn, lightsRadPath, tex);
-    Prepare(bsp.lumps, text, P, lightsRadPath ? &tex : nullptr);
+    if (lightsRadPath) { LoadTexLights(bsp, pathIn, lightsRadPath, tex); tex.hdr = opt.hdr; }
+    Prepare(bsp.lumps, text, P, lightsRadPath ? &tex : nullptr, opt.chop, opt.maxChop, opt.SmoothingThreshold(), opt.luxelDensity);
     raytracer::Environment env(device);
-    const Lit lit = Light(env, P, ReadSkyDirs(skyDirsPath), bounces);
+    const Lit lit = Light(env, P, ReadSkyDirs(skyDirsPath), bounces, opt.fast, opt.textureShadows);
     const std::vector<uint8_t> lump = Finish(env, P, lit);
-    fatal_on(vrad_bspfile_set_lump(bsp.file, VRAD_LUMP_LIGHTING, lump.data(), static_cast<int64_t>(lump.size()), 1), "vrad_bspfile_set_lump");
+    fatal_on(vrad_bspfile_set_lump(bsp.file, bsp.lightingLump, lump.data(), static_cast<int64_t>(lump.size()), 1), "vrad_bspfile_set_lump");
     // P.lumps.faces points at P.lit_faces (our copy), so replacing the face lump does not pull the rug from under it
-    fatal_on(vrad_bspfile_set_lump(bsp.file, VRAD_LUMP_FACES, P.lit_faces.data(), static_cast<int64_t>(P.lit_faces.size() * sizeof(vrad_dface)), 1), "vrad_bspfile_set_lump");
+    fatal_on(vrad_bspfile_set_lump(bsp.file, bsp.faceLump, P.lit_faces.data(), static_cast<int64_t>(P.lit_faces.size() * sizeof(vrad_dface)), 1), "vrad_bspfile_set_lump");
+    if (!P.texinfo.empty())                                                   // the rescaled lightmap vectors go back into the file (rad/start.go:48-50)
+        fatal_on(vrad_bspfile_set_lump(bsp.file, VRAD_LUMP_TEXINFO, P.texinfo.data(), static_cast<int64_t>(P.texinfo.size() * sizeof(vrad_texinfo)), 0), "vrad_bspfile_set_lump");
     {   // lightmap.SaveVertexNormals (rad/start.go:82-85): the vertex-normal lumps, "for use in the engine"
         const int nfv = static_cast<int>(P.neighbours.vertexNormals3.size() / 3) - 1;       // PairEdges leaves one spare entry
         std::vector<float> normals(3 * static_cast<size_t>(std::max(nfv, 1)));

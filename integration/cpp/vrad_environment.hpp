@@ -181,8 +181,10 @@ namespace loadbsp {
 struct Bsp {
     vrad_bspfile* file = nullptr;
     vrad_bsp_lumps lumps{};
-    explicit Bsp(const char* path) {
+    int faceLump = VRAD_LUMP_FACES, lightingLump = VRAD_LUMP_LIGHTING;       // cache.SetTargetFaces (main.go:79-89)
+    explicit Bsp(const char* path, bool hdr = false) {
         raytracer::fatal_on(vrad_bspfile_open(path, &file), "vrad_bspfile_open");
+        raytracer::fatal_on(vrad_bspfile_set_target_faces(file, hdr, &faceLump, &lightingLump), "vrad_bspfile_set_target_faces");
         raytracer::fatal_on(vrad_bspfile_lumps(file, &lumps), "vrad_bspfile_lumps");
     }
     ~Bsp() { vrad_bspfile_close(file); }

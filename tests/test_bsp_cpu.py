@@ -881,11 +881,12 @@ def test_cpp_bake_prepares_what_the_python_mirror_prepares(smap, tmp_path):
     path = str(tmp_path / "m.bsp")
     B.write_bsp(path, L, meta)
     subprocess.run(["make", "-C", os.path.join(root, "integration", "cpp")], check=True, capture_output=True)
-    for with_rad in (False, True):
-        _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path)
+    for with_rad, switches in ((False, {}), (True, {}), (False, dict(luxel_density=0.05, smooth_degrees=100.0, chop=2.0, max_chop=8.0))):
+        _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path, switches)
 
 
-def _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path):
+def _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path, switches):
+    import math
     import subprocess
     from vrad_b200 import bake
     cmd = [os.path.join(root, "integration", "cpp", "drive"), "--prepare", path]
@@ -893,8 +894,13 @@ def _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path):
     if with_rad:
         rad = str(tmp_path / "lights.rad")
         open(rad, "w", newline="").write(LIGHTS_RAD)
-        cmd.append(rad)
+        cmd += ["-lights", rad]
         kw = dict(lights_rad=LIGHTS_RAD, texdata_strings=(meta["string_table"], meta["string_data"]), map_name="m")
+    if switches:                                                         # the reference's command-line switches (cmd/args.go:53-93)
+        cmd += ["-luxeldensity", str(switches["luxel_density"]), "-smooth", str(switches["smooth_degrees"]), "-chop", str(switches["chop"]),
+                "-maxchop", str(switches["max_chop"])]
+        kw.update(luxel_density=switches["luxel_density"], min_chop=switches["chop"], max_chop=switches["max_chop"],
+                  smoothing_threshold=float(np.float32(math.cos(math.radians(switches["smooth_degrees"])))))
     out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
     got = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out.splitlines()}
     prep = bake.prepare(L, meta["entities"], **kw)

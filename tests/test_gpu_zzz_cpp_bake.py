@@ -22,7 +22,7 @@ def test_cpp_driver_bakes_the_same_file(tmp_path):
     res = bake.bake_file(src, out_py, device=0, bounces=8)
     subprocess.run(["make", "-C", os.path.join(root, "integration", "cpp")], check=True, capture_output=True)
     anorms = os.path.join(root, "vrad_b200", "data", "anorms.txt")
-    r = subprocess.run([os.path.join(root, "integration", "cpp", "drive"), "--bake", src, out_cpp, anorms], check=True, capture_output=True, text=True)
+    r = subprocess.run([os.path.join(root, "integration", "cpp", "drive"), "--bake", src, out_cpp, anorms, "-bounce", "8"], check=True, capture_output=True, text=True)
     words = r.stdout.split()
     got = {words[i]: int(words[i + 1]) for i in range(1, len(words), 2)}
 

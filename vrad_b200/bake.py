@@ -124,10 +124,12 @@ def _point_cluster(L: B.Lumps, p) -> int:
 
 def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float = 4.0, lights_rad: str | None = None,
             texdata_strings=None, map_name: str = "", lights_rad_hdr: bool = False, smoothing_threshold: float = 0.7071067,
-            place_samples: bool = True) -> dict:
+            place_samples: bool = True, luxel_density: float = 1.0) -> dict:
     """Everything the device stages take, from the lumps (host code in the library; no GPU needed).
     lights_rad = the text of a lights.rad file, texdata_strings = (LUMP_TEXDATA_STRING_TABLE as int32, LUMP_TEXDATA_STRING_DATA bytes):
     faces whose material is a texlight get Patch.BaseLight and their leaf patches become EMIT_SURFACE lights (CreateDirectLights)."""
+    if luxel_density < 1.0:                                           # rad.Start (rad/start.go:21-66): luxels no denser than -luxeldensity
+        L = L.replace(texinfo=B.rescale_lightmap_vecs(L.texinfo, luxel_density))
     ents = parse_entities(entity_text)
     cm, co, ca = shadow_casters(ents)
     tri_ids, tri_verts = B.raytrace_triangles(L, cm, co, ca)
@@ -230,7 +232,8 @@ def all_gather_blocks(local: np.ndarray, parts, rank: int, device=None) -> np.nd
     return np.concatenate([bufs[r][: b - a].cpu().numpy() for r, (a, b) in enumerate(parts)], axis=0)
 
 
-def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int = 0, world: int = 1, device=None, use_light_pvs: bool = True) -> dict:
+def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int = 0, world: int = 1, device=None, use_light_pvs: bool = True,
+          fast_tree: bool = False, texture_shadows: bool = False) -> dict:
     """The device stages, on any object with the Environment call surface: geometry + kd build (K1), transfers (K2), direct
     light on the luxels and on the patches (K3; the patch value is Patch.DirectLight, what the first bounce emits), bounces (K4).
     world > 1 (one process per GPU, torch.distributed initialised): luxels and patch origins are independent work items, each
@@ -239,7 +242,12 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int =
     from .sharding import range_partition
     t = prep["tree"]
     env.add_triangles(prep["tri_ids"], prep["tri_verts"].reshape(-1, 9), np.zeros(prep["tri_ids"].shape[0], np.uint8))
-    env.setup_acceleration_structure() if hasattr(env, "setup_acceleration_structure") else env.build()
+    if fast_tree and hasattr(env, "build_fast"):
+        env.build_fast()                                              # RTE_FLAGS_FAST_TREE_GENERATION: the binned-SAH build on the device
+    else:
+        env.setup_acceleration_structure() if hasattr(env, "setup_acceleration_structure") else env.build()
+    if texture_shadows:
+        env.set_light_trace_flags(2)                                  # VRAD_TL_TEXTURE_SHADOWS (-textureshadows, testline.go:14)
     env.patches_upload(t["origin"], t["normal"], t["plane_dist"], t["area"], prep["refl"], prep["cluster"], prep["flags"])
     env.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
     if prep["needs_bump"].any() and world == 1:                       # TotalLight.Light[1..3] of the bump-mapped leaf patches (single GPU)
@@ -317,10 +325,13 @@ def finish(env, prep: dict, lit: dict, rank: int = 0, world: int = 1, device=Non
 
 
 def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, rank: int = 0, world: int = 1, comm_id: bytes | None = None,
-              lights_rad_path: str | None = None, hdr: bool = False) -> dict:
+              lights_rad_path: str | None = None, hdr: bool = False, luxel_density: float = 1.0, smooth_degrees: float = 45.0, chop: float = 4.0,
+              max_chop: float = 4.0, fast: bool = False, texture_shadows: bool = False) -> dict:
     """The whole job: read a .bsp, light it on the GPU, write it back with LUMP_LIGHTING and the face lump replaced.
     world > 1: one process per GPU under torch.distributed (nccl); comm_id = the 128 bytes of Environment.comm_unique_id() from rank 0;
-    every rank reads the file and lights its share, rank 0 writes the result."""
+    every rank reads the file and lights its share, rank 0 writes the result.
+    The keyword arguments are the command-line switches of the reference that reach this path (cmd/args.go:53-93): -bounce, -lights, -hdr,
+    -luxeldensity, -smooth (degrees), -chop / -maxchop, -fast (here: the binned kd build), -textureshadows."""
     from .environment import Environment
     f = B.BspFile(path_in)
     try:
@@ -330,7 +341,11 @@ def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, ra
         rad = open(lights_rad_path, "r", errors="replace").read() if lights_rad_path else None
         strings = (np.frombuffer(f.get(B.LUMP["TEXDATA_STRING_TABLE"])[0], "<i4"), f.get(B.LUMP["TEXDATA_STRING_DATA"])[0])
         import os
-        prep = prepare(L, text, lights_rad=rad, lights_rad_hdr=hdr, texdata_strings=strings, map_name=os.path.splitext(os.path.basename(path_in))[0])
+        import math
+        prep = prepare(L, text, min_chop=chop, max_chop=max_chop, lights_rad=rad, lights_rad_hdr=hdr, texdata_strings=strings,
+                       map_name=os.path.splitext(os.path.basename(path_in))[0], luxel_density=luxel_density,
+                       smoothing_threshold=0.7071067 if smooth_degrees == 45.0 else float(np.float32(math.cos(math.radians(smooth_degrees)))))
+        # (45 degrees is the reference's default, spelled float32(0.7071067) at rad/lightmap/lightmap.go:29 -- one ulp below cos(45 deg))
         env = Environment(device, rank, world)
         try:
             dev = None
@@ -338,13 +353,15 @@ def bake_file(path_in: str, path_out: str, device: int = 0, bounces: int = 8, ra
                 import torch
                 dev = torch.device("cuda", device)
                 env.comm_init(comm_id)
-            lit = light(env, prep, bounces, rank=rank, world=world, device=dev)
+            lit = light(env, prep, bounces, rank=rank, world=world, device=dev, fast_tree=fast, texture_shadows=texture_shadows)
             lump, colors = finish(env, prep, lit, rank=rank, world=world, device=dev)
         finally:
             env.close()
         if rank == 0:
             f.set(lighting_lump, lump, version=1)
             f.set(face_lump, prep["lumps"].faces, version=1)
+            if luxel_density < 1.0:                                   # the rescaled lightmap vectors go back into the file (rad/start.go:48-50)
+                f.set(B.LUMP["TEXINFO"], prep["lumps"].texinfo)
             # lightmap.SaveVertexNormals (rad/start.go:82-85): "store the vertex normals calculated in PairEdges so that they can be written
             # to the bsp file for use in the engine"
             normals, indices = B.save_vertex_normals(prep["vertex_normals"])
