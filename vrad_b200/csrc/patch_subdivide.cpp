@@ -94,6 +94,7 @@ void clip_winding_axis(const V3* in, int n, int axis, float dist, std::vector<V3
     int sides[kMaxPointsOnWinding + 4];
     int counts[3] = {0, 0, 0};
     front.clear(); back.clear();
+    if (n <= 0) return;                                    // an empty winding has no sides
     for (int i = 0; i < n; i++) {
         float dot = comp(in[i], axis);                     // Points[i].Dot(normal) with a unit axis normal
         // mgl32 Dot = p0*n0 + p1*n1 + p2*n2: the two zero products add +0 and leave the value unchanged
