@@ -4,7 +4,7 @@
 set -x
 mkdir -p gpurun_out
 # 1. the new GPU tests on their own first (a failure here must not hide the state of the rest), then the whole suite
-python -m pytest tests/test_gpu_zz_bsp_bake.py tests/test_gpu_zz_kd_fast.py tests/test_gpu_bump.py -q -s --durations=8 2>&1 | tail -40 > gpurun_out/r02a_pytest_new.log; tail -5 gpurun_out/r02a_pytest_new.log
+python -m pytest tests/test_gpu_zz_bsp_bake.py tests/test_gpu_zz_kd_fast.py tests/test_gpu_zzz_cpp_bake.py tests/test_gpu_bump.py -q -s --durations=8 2>&1 | tail -40 > gpurun_out/r02a_pytest_new.log; tail -5 gpurun_out/r02a_pytest_new.log
 python -m pytest tests -m gpu -q --durations=8 2>&1 | tail -25 > gpurun_out/r02a_pytest_gpu.log; tail -4 gpurun_out/r02a_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 # 2. bench (N=1) incl. the bsp_side child process
