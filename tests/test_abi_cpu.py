@@ -98,3 +98,47 @@ def test_bsp_side_entry_points_reject_null_arguments():
         assert (rc == 0) if sym in ok_on_empty else (rc < 0), (sym, rc)
         if rc < 0:
             assert handle.vrad_last_error()                      # and it says why
+
+
+def _top_level_args(text, start):
+    """Number of top-level comma-separated arguments of the call whose '(' is at text[start]."""
+    depth, args, i, seen = 0, 0, start, False
+    while i < len(text):
+        c = text[i]
+        if c in "([{":
+            depth += 1
+        elif c in ")]}":
+            depth -= 1
+            if depth == 0:
+                return args + (1 if seen else 0)
+        elif c == "," and depth == 1:
+            args += 1
+        elif not c.isspace() and depth >= 1:
+            seen = True
+        i += 1
+    raise AssertionError("unbalanced call")
+
+
+def test_cgo_sources_call_declared_entry_points_with_the_right_arity():
+    """The Go shims cannot be compiled here (no Go toolchain), so at least every C.vrad_* call in integration/go names a function the
+    headers declare and passes as many arguments as the declaration has parameters."""
+    decl = {}
+    for header in ("vrad_cuda.h", "vrad_bsp.h"):
+        src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", header)).read(), flags=re.S)
+        for m in re.finditer(r"\b(vrad_[a-z0-9_]+)\s*\(", src):
+            n = _top_level_args(src, m.end() - 1)
+            params = src[m.end():src.index(")", m.end())].strip()
+            decl[m.group(1)] = 0 if params in ("", "void") else n
+    calls = 0
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "integration", "go")):
+        for f in files:
+            if not f.endswith(".go"):
+                continue
+            text = open(os.path.join(dirpath, f)).read()
+            text = re.sub(r"//[^\n]*", "", text)
+            for m in re.finditer(r"\bC\.(vrad_[a-z0-9_]+)\(", text):
+                name = m.group(1)
+                assert name in decl, f"{f}: C.{name} is not declared in include/"
+                assert _top_level_args(text, m.end() - 1) == decl[name], f"{f}: C.{name} called with the wrong number of arguments"
+                calls += 1
+    assert calls >= 40
