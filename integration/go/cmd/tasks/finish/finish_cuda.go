@@ -29,16 +29,51 @@ func fatal(what string, rc C.int) {
 	}
 }
 
-// WriteLightingCUDA: direct = per-luxel RGB from vrad_direct_light (luxel order of vrad_bsp_face_luxels), luxelPatch from
-// vrad_luxel_nearest_patch, patchTotal = vrad_bounce's totals.  inPath is re-read so that every lump the program never touched
-// goes back byte for byte.
+// RadialIndirectCUDA: the bounced light of every luxel by the radial filter (vrad_bsp_radial_entries on the host, vrad_luxel_radial_light on the
+// GPU).  patchFace / child1 / origin / windFirst / windCount / windPoints describe cache.GetPatches() as rad/radworld_cuda.go uploads them;
+// nbFirst / nb are lightmap.PairEdgesCUDA's neighbour lists; mins / size come from vrad_bsp_face_extents.
+func RadialIndirectCUDA(lumps *cache.CLumps, litFaces []C.vrad_dface, mins, size []C.int32_t, faceOrigins []C.float, luxelFace []C.int32_t, luxelFirst []C.int64_t,
+	patchFace, child1 []C.int32_t, origin []C.float, windFirst, windCount []C.int32_t, windPoints []C.float, nbFirst, nb []C.int32_t,
+	patchTotal []C.float, patchBump []C.float) []C.float {
+	env := (*C.vrad_env)(unsafe.Pointer(raytracer.GetEnvironment().CudaHandle()))
+	view := lumps.L
+	view.faces = &litFaces[0]
+	nFaces, nPatches, n := len(litFaces), len(patchFace), int(luxelFirst[len(luxelFirst)-1])
+	entryFirst := make([]C.int64_t, nFaces+1)
+	var nEntries C.int64_t
+	var pnb *C.int32_t
+	if len(nb) > 0 {
+		pnb = &nb[0]
+	}
+	fatal("vrad_bsp_radial_entries", C.vrad_bsp_radial_entries(&view, &mins[0], &faceOrigins[0], C.int(nPatches), &patchFace[0], &child1[0], &origin[0],
+		&windFirst[0], &windCount[0], &windPoints[0], &nbFirst[0], pnb, 0, &entryFirst[0], nil, &nEntries))
+	entries := make([]C.vrad_radial_entry, int(nEntries)+1)
+	fatal("vrad_bsp_radial_entries", C.vrad_bsp_radial_entries(&view, &mins[0], &faceOrigins[0], C.int(nPatches), &patchFace[0], &child1[0], &origin[0],
+		&windFirst[0], &windCount[0], &windPoints[0], &nbFirst[0], pnb, nEntries, &entryFirst[0], &entries[0], &nEntries))
+	indirect := make([]C.float, 3*n+3)
+	var bump *C.float
+	if len(patchBump) > 0 {
+		bump = &patchBump[0]
+	}
+	fatal("vrad_luxel_radial_light", C.vrad_luxel_radial_light(env, C.int64_t(n), &luxelFace[0], C.int(nFaces), &luxelFirst[0], &size[0], &entryFirst[0], &entries[0],
+		C.int(nPatches), &patchTotal[0], bump, &indirect[0]))
+	return indirect
+}
+
+// WriteLightingCUDA: direct = per-luxel RGB from vrad_direct_light (luxel order of vrad_bsp_face_luxels), indirect = RadialIndirectCUDA's result (or nil:
+// luxelPatch from vrad_luxel_nearest_patch + patchTotal = vrad_bounce's totals, the piecewise-constant form).  inPath is re-read so that every lump the
+// program never touched goes back byte for byte.
 func WriteLightingCUDA(inPath, outPath string, lumps *cache.CLumps, luxelFirst []C.int64_t, litFaces []C.vrad_dface,
-	direct []C.float, luxelPatch []C.int32_t, patchTotal []C.float) {
+	direct []C.float, indirect []C.float, luxelPatch []C.int32_t, patchTotal []C.float) {
 	env := (*C.vrad_env)(unsafe.Pointer(raytracer.GetEnvironment().CudaHandle()))
 	n := int(luxelFirst[len(luxelFirst)-1])
 	colors := make([]C.vrad_color_rgbexp32, n+1)
-	fatal("vrad_lightmap_finalize_patches", C.vrad_lightmap_finalize_patches(env, C.int64_t(n), &direct[0], &luxelPatch[0],
-		C.int(len(patchTotal)/3), &patchTotal[0], &colors[0]))
+	if indirect != nil {
+		fatal("vrad_lightmap_finalize", C.vrad_lightmap_finalize(env, C.int64_t(n), &direct[0], &indirect[0], &colors[0]))
+	} else {
+		fatal("vrad_lightmap_finalize_patches", C.vrad_lightmap_finalize_patches(env, C.int64_t(n), &direct[0], &luxelPatch[0],
+			C.int(len(patchTotal)/3), &patchTotal[0], &colors[0]))
+	}
 
 	view := lumps.L // the face records laid out by vrad_bsp_layout_lighting carry the offsets
 	view.faces = &litFaces[0]
