@@ -883,6 +883,11 @@ def test_cpp_bake_prepares_what_the_python_mirror_prepares(smap, tmp_path):
     subprocess.run(["make", "-C", os.path.join(root, "integration", "cpp")], check=True, capture_output=True)
     for with_rad, switches in ((False, {}), (True, {}), (False, dict(luxel_density=0.05, smooth_degrees=100.0, chop=2.0, max_chop=8.0))):
         _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path, switches)
+    # and on non-axial geometry (wedges), everything smoothed
+    L2, meta2 = B.synthetic_map(2, 2, boxes_per_room=3, ramps=True, sky_rooms=(2,), bump_rooms=(1,))
+    path2 = str(tmp_path / "ramps.bsp")
+    B.write_bsp(path2, L2, meta2)
+    _compare_cpp_prepare(root, path2, L2, meta2, False, tmp_path, dict(luxel_density=1.0, smooth_degrees=170.0, chop=4.0, max_chop=4.0))
 
 
 def _compare_cpp_prepare(root, path, L, meta, with_rad, tmp_path, switches):
@@ -992,3 +997,66 @@ def test_corrupted_files_never_crash_the_host_pipeline(tmp_path):
         except (VradError, ValueError, IndexError, KeyError, OverflowError):
             rejected += 1
     assert survived + rejected == 120 and rejected > 10 and survived > 10
+
+
+def test_non_axial_geometry_through_the_whole_host_pipeline():
+    """The same product-vs-oracle comparisons on a map with wedges: a sloping face whose lightmap axes are WORLD axes (as a BSP compiler
+    projects them), so the texture normal differs from the face normal (InitLightinfo's distscale path), non-axial brush planes in the
+    winding chopper, and smoothing across a 26.6-degree crease."""
+    from vrad_b200 import bake
+    L, meta = B.synthetic_map(2, 1, boxes_per_room=2, ramps=True, with_brush_entity=False)
+    L.validate()
+    slopes = np.nonzero(L.planes["type"][L.faces["planenum"]] == 3)[0]
+    assert len(slopes) == 2                                              # one sloping face per room
+    # triangles: the wedge brush has 5 sides -> 2 + 2 + 2 + 1 + 1 triangles
+    ids, verts = B.raytrace_triangles(L)
+    oids, overts = O.raytrace_triangles(L)
+    assert np.array_equal(ids, oids) and np.array_equal(_bits(verts), _bits(overts))
+    assert ids.shape[0] == 12 * (L.brushes.shape[0] - 2) + 8 * 2
+    # face patches, extents
+    g, o = B.face_patches(L), O.face_patches(L)
+    assert np.array_equal(_bits(g["points"]), _bits(np.asarray([p for w in o["windings"] for p in w], np.float32)))
+    assert np.array_equal(_bits(g["faces"]["plane_dist"]), _bits(np.asarray(o["plane_dist"], np.float32)))
+    mins, size, over = B.face_extents(L)
+    omins, osize = O.face_extents(L)
+    assert np.array_equal(mins, omins) and np.array_equal(size, osize) and over == 0
+    assert tuple(mins[slopes[0]]) == (2, 2) and tuple(size[slopes[0]]) == (9, 5)     # x 40..168, y 40..104 projected on xy at 16 units per luxel
+    # smoothing: at 45 degrees the slope (26.6 degrees off the floor normal ... it meets the wedge's own vertical faces at > 45) stays
+    # flat; at 20 degrees of cosine threshold 0.85 nothing changes; with everything smoothed product == oracle
+    for thr in (0.7071067, -1.0):
+        vn, first, nb = B.pair_edges(L, thr)
+        on, onb = O.pair_edges(L, thr)
+        assert np.array_equal(_bits(vn), _bits(np.asarray([v for fn in on for v in fn], np.float32)))
+        assert [list(nb[first[i]:first[i + 1]]) for i in range(L.faces.shape[0])] == onb
+    # luxels on the slope: on the plane + 1, integer lightmap coordinates, bit-equal to the oracle's frame
+    faces, first, _ = B.layout_lighting(L, mins, size)
+    L3 = L.replace(faces=faces)
+    pos, nrm, lf = B.face_luxels(L3, mins, size, first)
+    opos, onrm, oface = O.face_luxels(L3, mins, size)
+    assert np.array_equal(_bits(pos), _bits(opos)) and np.array_equal(_bits(nrm), _bits(onrm)) and np.array_equal(lf, oface)
+    sel = lf == slopes[0]
+    pl = L.planes[L.faces["planenum"][slopes[0]]]
+    on_plane = pos[sel].astype(np.float64) - pl["normal"].astype(np.float64)
+    assert np.allclose(on_plane @ pl["normal"].astype(np.float64), pl["dist"], atol=1e-3)
+    lv = L.texinfo["lightmap_vecs"][L.faces["texinfo"][slopes[0]]].astype(np.float64)
+    st = on_plane @ lv[:, :3].T + lv[:, 3]
+    assert np.allclose(st, np.round(st), atol=1e-4)
+    assert abs(float(np.dot(np.cross(lv[1, :3], lv[0, :3]) / np.linalg.norm(np.cross(lv[1, :3], lv[0, :3])), pl["normal"]))) < 0.95     # texture normal != face normal
+    # sample placement keeps them on the slope
+    placed, st2 = B.place_samples(L3, mins, size, first, pos)
+    assert np.allclose((placed[sel].astype(np.float64) - pl["normal"]) @ pl["normal"].astype(np.float64), pl["dist"], atol=1e-3)
+    # the whole prepare + the oracle's light run through; the radial gather equals the scatter form on the sloping face
+    prep = bake.prepare(L, meta["entities"])
+    t = prep["tree"]
+    totals = np.random.default_rng(1).uniform(0, 100, (t["origin"].shape[0], 3)).astype(np.float32)
+    got = B.luxel_radial_light(None, prep["lux_face"], prep["luxel_first"], prep["lm_size"], prep["radial_first"], prep["radial_entries"], totals)
+    patch_lists = [[] for _ in range(L.faces.shape[0])]
+    for p in range(t["origin"].shape[0]):
+        if t["child1"][p] == -1:
+            patch_lists[prep["face_of_patch"][p]].append(p)
+    vn, nb_first, nb = B.pair_edges(L)
+    nbs = [list(nb[nb_first[f]:nb_first[f + 1]]) for f in range(L.faces.shape[0])]
+    f = int(slopes[1])
+    want = O.build_patch_radial(L, f, prep["lm_mins"], prep["lm_size"], patch_lists, t, totals, nbs, prep["face_origin"])
+    a = int(prep["luxel_first"][f])
+    assert np.array_equal(_bits(got[a:a + want.shape[0]]), _bits(want))

@@ -519,11 +519,12 @@ def _axes_for(normal):
 
 def synthetic_map(nx: int = 3, ny: int = 2, room: float = 512.0, boxes_per_room: int = 6, seed: int = 0x5EED0B5F, wall: float = 16.0,
                   door_w: float = 128.0, door_h: float = 256.0, sky_rooms=(), bump_rooms=(), radial_rooms=(), pvs_radius: int = 2,
-                  with_brush_entity: bool = True, luxels_per_unit: float = 1.0 / 16.0) -> tuple[Lumps, dict]:
+                  with_brush_entity: bool = True, luxels_per_unit: float = 1.0 / 16.0, ramps: bool = False) -> tuple[Lumps, dict]:
     """A BSP v20 map of the multi-room grid: rooms of `room`^3 separated by `wall`-thick brushes with door openings, box occluder
     brushes, one leaf/cluster per room (+ the solid leaf 0), faces wound from shared vertices, run-length coded PVS.
     sky_rooms: rooms whose ceiling is a SURF_SKY face; bump_rooms: rooms whose floor is SURF_BUMPLIGHT; radial_rooms: leafs
-    flagged LEAF_FLAGS_RADIAL.  Returns (Lumps, meta) -- meta: entity text, per-face room, brush-entity placement."""
+    flagged LEAF_FLAGS_RADIAL; ramps: one wedge per room with a sloping top (a non-axial plane whose lightmap axes are world axes, so the
+    texture normal differs from the face normal).  Returns (Lumps, meta) -- meta: entity text, per-face room, brush-entity placement."""
     from .scenes import SplitMix64, _place_boxes, compress_vis_rows
     rng = SplitMix64(seed)
     b = _MapBuilder()
@@ -596,6 +597,21 @@ def synthetic_map(nx: int = 3, ny: int = 2, room: float = 512.0, boxes_per_room:
                 quad((mx[0], mn[1], mn[2]), (0, d[1], 0), (0, 0, d[2]), (1, 0, 0), texinfo((1, 0, 0), 2, 0), k)
                 quad((mn[0], mn[1], mn[2]), (d[0], 0, 0), (0, 0, d[2]), (0, -1, 0), texinfo((0, -1, 0), 2, 0), k)
                 quad((mn[0], mx[1], mn[2]), (d[0], 0, 0), (0, 0, d[2]), (0, 1, 0), texinfo((0, 1, 0), 2, 0), k)
+            if ramps:                                                   # a wedge: 128 x 64 base, rising 64 units along +x
+                rx0, rx1, ry0, ry1, rh = x0 + 40.0, x0 + 168.0, y0 + 40.0, y0 + 104.0, 64.0
+                n_top = np.array([-rh, 0.0, rx1 - rx0]); n_top /= np.linalg.norm(n_top)
+                first = len(b.brushsides)
+                for (nn, dd) in (((0.0, 0.0, -1.0), 0.0), ((1.0, 0.0, 0.0), rx1), ((0.0, -1.0, 0.0), -ry0), ((0.0, 1.0, 0.0), ry1),
+                                 (tuple(n_top), float(np.dot(n_top, (rx0, ry0, 0.0))))):
+                    b.brushsides.append((b.plane(nn, dd), texinfo((0, 0, 1), 2, 0), 0, 0))
+                b.brushes.append((first, 5, CONTENTS_SOLID))
+                leaf_brushes.setdefault(k, []).append(len(b.brushes) - 1)
+                for pts, nrm in (([(rx0, ry0, 0), (rx1, ry0, rh), (rx1, ry1, rh), (rx0, ry1, 0)], tuple(n_top)),
+                                 ([(rx1, ry0, 0), (rx1, ry1, 0), (rx1, ry1, rh), (rx1, ry0, rh)], (1.0, 0.0, 0.0)),
+                                 ([(rx0, ry0, 0), (rx1, ry0, 0), (rx1, ry0, rh)], (0.0, -1.0, 0.0)),
+                                 ([(rx0, ry1, 0), (rx1, ry1, rh), (rx1, ry1, 0)], (0.0, 1.0, 0.0))):
+                    f = b.face([np.asarray(q, np.float64) for q in pts], nrm, texinfo(nrm, 2, 0))
+                    face_room.append(k); leaf_faces.setdefault(k, []).append(f)
     n_world_faces = len(b.faces)
 
     # structural brushes: outer shell slabs and the interior walls (three pieces around each door)
