@@ -129,7 +129,7 @@ def test_env_add_bsp_traces_like_the_oracle():
 def test_bsp_file_bake(tmp_path):
     from oracle import pyoracle
     from vrad_b200 import bake
-    L, meta = B.synthetic_map(2, 2, boxes_per_room=4, sky_rooms=(1,), bump_rooms=(0,))
+    L, meta = B.synthetic_map(2, 2, boxes_per_room=4, sky_rooms=(1,), bump_rooms=(0,), ramps=True)
     src, dst = str(tmp_path / "in.bsp"), str(tmp_path / "out.bsp")
     B.write_bsp(src, L, meta)
     res = bake.bake_file(src, dst, device=0, bounces=8)

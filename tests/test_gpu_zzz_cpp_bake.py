@@ -16,7 +16,7 @@ def test_cpp_driver_bakes_the_same_file(tmp_path):
     import subprocess
     from vrad_b200 import bake
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    L, meta = B.synthetic_map(2, 2, boxes_per_room=4, sky_rooms=(1,), bump_rooms=(0,))
+    L, meta = B.synthetic_map(2, 2, boxes_per_room=4, sky_rooms=(1,), bump_rooms=(0,), ramps=True)
     src, out_py, out_cpp = str(tmp_path / "in.bsp"), str(tmp_path / "py.bsp"), str(tmp_path / "cpp.bsp")
     B.write_bsp(src, L, meta)
     res = bake.bake_file(src, out_py, device=0, bounces=8)
