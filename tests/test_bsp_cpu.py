@@ -938,7 +938,7 @@ def test_cpp_bake_end_to_end_on_the_oracle(smap, tmp_path):
                     os.path.join(root, "integration", "cpp", "drive_main.cpp"), os.path.join(root, "tests", "helpers", "oracle_device_shim.cpp"),
                     "-L" + os.path.join(root, "vrad_b200", "_lib"), "-lvradcuda", "-L" + os.path.join(root, "oracle", "_build"), "-loracle",
                     "-Wl,-rpath," + os.path.join(root, "vrad_b200", "_lib"), "-Wl,-rpath," + os.path.join(root, "oracle", "_build")], check=True, capture_output=True)
-    L, meta = B.synthetic_map(2, 2, boxes_per_room=4, sky_rooms=(1,), bump_rooms=(0,))
+    L, meta = B.synthetic_map(2, 2, boxes_per_room=4, sky_rooms=(1,), bump_rooms=(0,), ramps=True)
     src, dst = str(tmp_path / "in.bsp"), str(tmp_path / "cpp.bsp")
     B.write_bsp(src, L, meta)
     anorms = os.path.join(root, "vrad_b200", "data", "anorms.txt")
