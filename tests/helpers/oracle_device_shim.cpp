@@ -26,7 +26,13 @@ int vrad_patches_set_hierarchy(vrad_env* e, int n, const int32_t* parent, const 
     return orc_patches_set_hierarchy(e->o, n, parent, child1, child2, face);
 }
 int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_t* nnz_out) { return orc_build_transfers(e->o, n_clusters, pvs, nnz_out, kThreads); }
-int vrad_set_sky_dirs(vrad_env*, int n, const float* dirs3) { return orc_set_sky_dirs(n, dirs3); }
+static std::vector<float> g_sky_dirs;
+int vrad_set_sky_dirs(vrad_env*, int n, const float* dirs3) { g_sky_dirs.assign(dirs3, dirs3 + 3 * static_cast<size_t>(n)); return orc_set_sky_dirs(n, dirs3); }
+// lightmap.CanLeafTraceToSky for a batch of leafs: what vrad_bsp_vis_for_light_environment (host code in libvradcuda.so) calls for
+// LEAF_FLAGS_RADIAL leafs -- the library's call lands here because the executable's definition comes first in symbol lookup
+int vrad_leafs_trace_to_sky(vrad_env* e, int n_leafs, const int16_t* mins3, const int16_t* maxs3, uint8_t* can_out) {
+    return orc_leafs_trace_to_sky(e->o, n_leafs, mins3, maxs3, static_cast<int>(g_sky_dirs.size() / 3), g_sky_dirs.data(), can_out, kThreads);
+}
 int vrad_bsp_upload(vrad_env* e, int n_nodes, const int32_t* node_plane, const int32_t* node_children2, int n_planes, const float* plane_normal3,
                     const float* plane_dist, const int32_t* plane_type, int n_leafs, const int32_t* leaf_cluster, const int32_t* leaf_area, int n_areas) {
     return orc_bsp_set(e->o, n_nodes, node_plane, node_children2, n_planes, plane_normal3, plane_dist, plane_type, n_leafs, leaf_cluster, leaf_area, n_areas);

@@ -1060,3 +1060,37 @@ def test_non_axial_geometry_through_the_whole_host_pipeline():
     want = O.build_patch_radial(L, f, prep["lm_mins"], prep["lm_size"], patch_lists, t, totals, nbs, prep["face_origin"])
     a = int(prep["luxel_first"][f])
     assert np.array_equal(_bits(got[a:a + want.shape[0]]), _bits(want))
+
+
+def test_radial_leafs_are_traced_for_sky(tmp_path):
+    """BuildVisForLightEnvironment's last branch (rad/lightmap/lightmap.go:373-381): a LEAF_FLAGS_RADIAL leaf that sees no sky leaf through
+    its PVS is traced with CanLeafTraceToSky.  The library's host code calls the tracer through vrad_leafs_trace_to_sky; here the oracle
+    stands behind that entry point (tests/helpers/oracle_device_shim.cpp) and the result is compared with the oracle's restatement given
+    the oracle's own CanLeafTraceToSky as the callback."""
+    import subprocess
+    from oracle import pyoracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pyoracle.build()
+    exe = str(tmp_path / "vis_radial")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-fopenmp", "-I" + os.path.join(root, "include"), "-o", exe,
+                    os.path.join(root, "tests", "helpers", "vis_radial_main.cpp"), os.path.join(root, "tests", "helpers", "oracle_device_shim.cpp"),
+                    "-L" + os.path.join(root, "vrad_b200", "_lib"), "-lvradcuda", "-L" + os.path.join(root, "oracle", "_build"), "-loracle",
+                    "-Wl,-rpath," + os.path.join(root, "vrad_b200", "_lib"), "-Wl,-rpath," + os.path.join(root, "oracle", "_build")], check=True, capture_output=True)
+    # room 1 has the sky ceiling; with a PVS radius of 0 no other room sees it through vis; rooms 2 and 3 are radial.  Room 3 = (i 1, j 1) is
+    # next to room 1 = (0, 1) with a tall (480-unit) door in between, so rays from its centre do reach the sky; room 2 = (1, 0) is around the corner.
+    L, meta = B.synthetic_map(2, 2, boxes_per_room=0, sky_rooms=(1,), radial_rooms=(2, 3), pvs_radius=0, with_brush_entity=False, door_h=480.0)
+    path = str(tmp_path / "radial.bsp")
+    B.write_bsp(path, L, meta)
+    anorms = os.path.join(root, "vrad_b200", "data", "anorms.txt")
+    out = subprocess.run([exe, path, anorms], check=True, capture_output=True, text=True).stdout
+    got = np.asarray([int(x) for x in out.split()], np.uint8)
+    # the oracle: its restatement of the function with its own tracer as the callback
+    ids, verts = O.raytrace_triangles(L)
+    o = pyoracle.OracleEnv(); o.add_triangles(ids, verts.reshape(-1, 9)); o.build()
+    dirs = np.loadtxt(anorms, dtype=np.float32)
+    can = lambda leaf: bool(o.leafs_trace_to_sky(L.leafs["mins"][leaf:leaf + 1], L.leafs["maxs"][leaf:leaf + 1], dirs, threads=4)[0])
+    want, _ = O.build_vis_for_light_environment(L, can_leaf_trace_to_sky=can)
+    assert np.array_equal(got, want)
+    assert got[1 + 1] == B.LEAF_FLAGS_SKY and got[1 + 0] == 0                                  # the sky room itself; room 0 is neither radial nor in its PVS
+    assert got[1 + 3] == (B.LEAF_FLAGS_RADIAL | B.LEAF_FLAGS_SKY)                               # traced: sees the sky through the door
+    assert got[1 + 2] == B.LEAF_FLAGS_RADIAL                                                     # traced: no direction finds the sky
