@@ -91,6 +91,18 @@ const char* vrad_last_error(void);
 int  vrad_env_set_stream(vrad_env*, void* cuda_stream);
 /* async != 0: calls whose data pointers are all device memory return without synchronising */
 int  vrad_env_set_async(vrad_env*, int async);
+/* tuning switches, by name (defaults come from the environment variables in parentheses):
+ *   "k1_sort"       (VRAD_K1_SORT)      order segment batches by start cell / direction octant / end cell before tracing:
+ *                                       -1 = batches of >= 65536 segments (default), 0 = never, 1 = always
+ *   "k1_top"        (VRAD_K1_TOP)       stage the top of the kd tree in shared memory: 0 = off (default), n = node budget
+ *   "k4_seg"        (VRAD_K4_SEG)       entries per gather work item; longer transfer rows are split (default 2048)
+ *   "k4_long_first" (VRAD_K4_ORDER=long) gather work items longest first
+ *   "k4_pdl"        (VRAD_K4_PDL)       multi-GPU gather: chain the bounces by programmatic dependent launch (default 1)
+ *   "k4_graph"      (VRAD_K4_GRAPH)     replay the bounce loop as a CUDA graph (default 1)
+ *   "k4_sim_peers"  (VRAD_K4_SIM_PEERS) world > 1 without a communicator: this device stands in for every peer -- timing
+ *                                       of one rank's slice on one GPU; the light is NOT valid (default 0)
+ * Results do not depend on any of them (K4: within its 1e-4 tolerance). */
+int  vrad_env_set_option(vrad_env*, const char* name, int value);
 /* device time (ms, CUDA events on the launching stream) and kernel-launch count of the last call */
 int  vrad_env_last_timing(vrad_env*, float* kernel_ms, int* n_launches);
 /* pinned staging buffers for the batched calls */
@@ -146,6 +158,18 @@ int  vrad_trace_rays(vrad_env*, int64_t n, const float* ox, const float* oy, con
  * sky_mode 0: any hit occludes; 1: a nearest hit on a TRACE_ID_SKY triangle does not occlude (:46-48). */
 int  vrad_test_lines(vrad_env*, int64_t n, const float* start_xyz_soa, const float* stop_xyz_soa,
                      int sky_mode, uint32_t* vis_bits);
+
+/* The same test for segments given as pairs of indices into a point table that is resident on the device -- how the
+ * lighting stages name their shadow segments: patch origin -> light origin, patch -> patch, leaf centre -> sky sample
+ * (rad/lightmap/lightmap.go:435-447 builds its FourVectors from such a fixed start and a table of directions; rad/patches and
+ * rad/lightmap hold the patch origins and light origins the segments run between).  vrad_points_upload copies n_points
+ * xyz triples once (patch origins, light origins, luxel samples ...); vrad_test_lines_indexed then takes 8 bytes per segment
+ * ({int32 start, int32 stop}, interleaved) instead of 24: a host batch is bound by PCIe at 24 B/segment, not by the kernel.
+ * Results are identical to vrad_test_lines on the same coordinates.  An index outside the table is VRAD_E_INVALID (checked
+ * on the host for host buffers; device buffers are checked by a device pass unless the handle is async, where the kernels
+ * clamp the indices instead). */
+int  vrad_points_upload(vrad_env*, int64_t n_points, const float* xyz3);
+int  vrad_test_lines_indexed(vrad_env*, int64_t n, const int32_t* pairs2, int sky_mode, uint32_t* vis_bits);
 
 /* Environment.TriangleColors (raytracer/environment.go:61-63, GetTriangleColor :430-432): 3 floats per
  * triangle, in the order the triangles were added.  colour.X is the coverage CoverageCount adds for a

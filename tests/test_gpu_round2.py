@@ -1,0 +1,207 @@
+"""Round-2 paths on the GPU, through the C-ABI, against the CPU oracle on the same seeded inputs:
+K1 with the coherence pre-pass (sorted order), with index pairs into a resident point table, with the top of the
+kd tree staged in shared memory; K4 with split rows, item order, and the bounce loop replayed as a CUDA graph.
+Visibility bits are bit-exact in every mode; K4 stays within the 1e-4 relative tolerance north_star states."""
+import numpy as np
+import pytest
+
+from vrad_b200 import scenes
+from vrad_b200.lib import VradError
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def s1_env(s1_scene):
+    from vrad_b200.environment import environment_from_scene
+    env = environment_from_scene(s1_scene)
+    yield env
+    env.close()
+
+
+@pytest.mark.parametrize("n", [1, 33, 1000, 65536 + 5, (1 << 19) + 7])
+@pytest.mark.parametrize("sky", [0, 1])
+def test_sorted_order_is_invisible(n, sky, s1_scene, s1_env, s1_oracle):
+    a, b = scenes.shadow_segments(s1_scene, n, seed=100 + n)
+    ref = s1_oracle.test_lines(a, b, sky_mode=sky, threads=8)
+    for mode in (0, 1):                      # never / always order the batch
+        s1_env.set_option("k1_sort", mode)
+        assert np.array_equal(s1_env.test_lines(a, b, sky_mode=sky), ref), f"k1_sort={mode}"
+
+
+def test_sorted_order_device_buffers_and_degenerate_segments(s1_scene, s1_env, s1_oracle):
+    import torch
+    n = (1 << 18) + 3
+    a, b = scenes.shadow_segments(s1_scene, n, seed=5)
+    b[:, ::7] = a[:, ::7]                    # zero-length segments: visible by definition (testline.go:22-27)
+    a[:, 11] = [-1e6, 2e6, 5.0]; b[:, 11] = [3e6, -2e6, 7.0]   # far outside the scene box: clamped cells, still traced
+    ref = s1_oracle.test_lines(a, b, threads=8)
+    s1_env.set_option("k1_sort", 1)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.full(((n + 31) // 32,), -1, dtype=torch.int32, device="cuda")     # stale words must be overwritten, not or-ed into
+    s1_env.test_lines(da, db, out=out)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), ref)
+
+
+@pytest.mark.parametrize("sort", [0, 1])
+def test_indexed_segments_equal_coordinates(sort, s1_scene, s1_env, s1_oracle):
+    n = (1 << 18) + 9
+    pts, pairs = scenes.shadow_segment_indices(s1_scene, n, seed=77)
+    a, b = scenes.shadow_segments(s1_scene, n, seed=77)
+    ref = s1_oracle.test_lines(a, b, threads=8)
+    s1_env.set_option("k1_sort", sort)
+    s1_env.points_upload(pts)
+    assert np.array_equal(s1_env.test_lines_indexed(pairs), ref)
+    import torch
+    dp = torch.from_numpy(pairs).cuda()
+    assert np.array_equal(s1_env.test_lines_indexed(dp).cpu().numpy().view(np.uint32), ref)
+
+
+def test_indexed_segments_host_pipeline_and_errors(s1_scene, s1_env, s1_oracle):
+    n = (1 << 22) + 64                         # >= 2^22 host pairs: chunked H2D overlapped with the traversal
+    pts, pairs = scenes.shadow_segment_indices(s1_scene, n, seed=3)
+    s1_env.points_upload(pts)
+    got = s1_env.test_lines_indexed(pairs)
+    ns = 1 << 16
+    a, b = scenes.shadow_segments(s1_scene, n, seed=3)
+    assert np.array_equal(got[: ns // 32], s1_oracle.test_lines(a[:, :ns].copy(), b[:, :ns].copy(), threads=8))
+    assert np.array_equal(got, s1_env.test_lines(a, b))             # coordinate form on the same segments, all 2^22
+    bad = pairs[:100].copy(); bad[17, 1] = pts.shape[0]
+    with pytest.raises(VradError) as ei:
+        s1_env.test_lines_indexed(bad)
+    assert ei.value.status == -1
+    import torch
+    with pytest.raises(VradError):
+        s1_env.test_lines_indexed(torch.from_numpy(bad).cuda())
+    from vrad_b200.environment import environment_from_scene
+    e2 = environment_from_scene(s1_scene, with_patches=False)
+    with pytest.raises(VradError) as ei:                             # no point table yet
+        e2.test_lines_indexed(pairs[:10])
+    assert ei.value.status == -4
+    e2.close()
+
+
+@pytest.mark.parametrize("budget", [3, 64, 1023, 4000])
+def test_top_levels_in_shared_memory(budget, s1_scene, s1_env, s1_oracle, s2_small_scene, s2_small_oracle):
+    from vrad_b200.environment import environment_from_scene
+    for scene, orc, env in ((s1_scene, s1_oracle, s1_env), (s2_small_scene, s2_small_oracle, None)):
+        own = env is None
+        if own:
+            env = environment_from_scene(scene, with_patches=False)
+        n = (1 << 17) + 1
+        a, b = scenes.shadow_segments(scene, n, seed=budget)
+        ref = orc.test_lines(a, b, threads=8)
+        env.set_option("k1_top", budget)
+        for sort in (0, 1):
+            env.set_option("k1_sort", sort)
+            assert np.array_equal(env.test_lines(a, b), ref), f"budget {budget} sort {sort}"
+        env.set_option("k1_top", 0)
+        assert np.array_equal(env.test_lines(a, b), ref)
+        if own:
+            env.close()
+
+
+def _gather_reference(orc, scene, emit0, n):
+    return orc.bounce(emit0, n, threads=8)
+
+
+@pytest.mark.parametrize("seg,long_first,graph", [(256, 0, 1), (256, 1, 0), (2048, 0, 1), (32768, 0, 0), (512, 1, 1)])
+def test_gather_items_any_plan_same_light(seg, long_first, graph, s2_small_scene, s2_small_oracle):
+    from vrad_b200.environment import environment_from_scene
+    scene = s2_small_scene
+    env = environment_from_scene(scene)
+    env.set_option("k4_seg", seg); env.set_option("k4_long_first", long_first); env.set_option("k4_graph", graph)
+    nnz = env.build_transfers(scene.pvs)
+    assert nnz == s2_small_oracle.build_transfers(scene.pvs, threads=8)
+    N = scene.n_patches
+    emit0 = scenes.SplitMix64(21).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
+    for nb in (1, 7, 8):                       # below and above the graph threshold; odd and even (buffer parity)
+        tg, ag, dg = env.bounce(emit0, nb)
+        to, ao, do = _gather_reference(s2_small_oracle, scene, emit0, nb)
+        assert dg == do == nb
+        assert np.abs(tg - to).max() <= 1e-4 * np.abs(to).max()
+        assert np.allclose(ag, ao, rtol=1e-4)
+    t1, a1, _ = env.bounce(emit0, 8)           # replayed graph: identical bits (the plan fixes the summation order)
+    t2, a2, _ = env.bounce(emit0, 8)
+    assert np.array_equal(t1, t2) and np.array_equal(a1, a2)
+    te, ae, de = env.bounce(emit0, 100, early_out=True)
+    toe, aoe, doe = s2_small_oracle.bounce(emit0, 100, early_out=True, threads=8)
+    assert de == doe and np.abs(te - toe).max() <= 1e-4 * np.abs(toe).max()
+    # re-planning resident rows keeps the light
+    env.set_option("k4_seg", 1024)
+    t3, _, _ = env.bounce(emit0, 8)
+    assert np.abs(t3 - t1).max() <= 1e-4 * np.abs(t1).max()
+    env.close()
+
+
+def test_split_rows_actually_occur(s1_scene, s1_oracle):
+    """S1's rows average ~2000 transfers: with 256-entry items nearly every row is split, and the result must not move."""
+    from vrad_b200.environment import environment_from_scene
+    env = environment_from_scene(s1_scene)
+    sel = slice(0, None, 2)
+    args = (s1_scene.patch_origin[sel], s1_scene.patch_normal[sel], s1_scene.patch_plane_dist[sel], s1_scene.patch_area[sel], s1_scene.patch_refl[sel])
+    env.patches_upload(*args)
+    env.set_option("k4_seg", 256)
+    nnz = env.build_transfers()
+    n = args[0].shape[0]
+    assert nnz / n > 512                         # rows long enough that 256-entry items split them
+    from oracle import pyoracle
+    o = pyoracle.env_from_scene(s1_scene)
+    o.patches_upload(*args)
+    assert o.build_transfers(threads=8) == nnz
+    emit0 = scenes.SplitMix64(2).uniform(3 * n, 0.0, 100.0).reshape(n, 3)
+    tg, ag, _ = env.bounce(emit0, 12)
+    to, ao, _ = o.bounce(emit0, 12, threads=8)
+    assert np.abs(tg - to).max() <= 1e-4 * np.abs(to).max() and np.allclose(ag, ao, rtol=1e-4)
+    env.close()
+
+
+def test_world1_rejects_a_partial_row_block(s2_small_scene, s2_small_oracle):
+    """with world == 1 a transfer block other than [0, N) must be an error, not light on the wrong patches."""
+    from vrad_b200.environment import environment_from_scene
+    scene = s2_small_scene
+    s2_small_oracle.build_transfers(scene.pvs, threads=8)
+    rp, col, w = s2_small_oracle.transfers()
+    N = scene.n_patches
+    env = environment_from_scene(scene)
+    a, b = 100, N - 50
+    env.transfers_upload(a, b, rp[a:b + 1] - rp[a], col[rp[a]:rp[b]], w[rp[a]:rp[b]])
+    with pytest.raises(VradError) as ei:
+        env.bounce(np.ones((N, 3), np.float32), 2)
+    assert ei.value.status == -4
+    env.transfers_upload(0, N, rp, col, w)
+    tg, _, _ = env.bounce(np.full((N, 3), 50.0, np.float32), 3)
+    to, _, _ = s2_small_oracle.bounce(np.full((N, 3), 50.0, np.float32), 3, threads=8)
+    assert np.abs(tg - to).max() <= 1e-4 * np.abs(to).max()
+    env.close()
+
+
+def test_simulated_peers_runs_the_multi_gpu_kernel_on_one_device(s2_small_scene):
+    """k4_sim_peers: the world-4 slice of rank 1 through k4_gather_items<MULTI> (peer stores, in-kernel barrier, PDL chain,
+    graph replay) on ONE device.  The light of the other ranks' rows is never refreshed, so only this rank's FIRST bounce is
+    comparable: total after 1 bounce == the single-GPU rows of the block."""
+    from vrad_b200.environment import Environment, environment_from_scene
+    scene = s2_small_scene
+    N = scene.n_patches
+    emit0 = scenes.SplitMix64(4).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
+    full = environment_from_scene(scene)
+    full.build_transfers(scene.pvs)
+    t_full, _, _ = full.bounce(emit0, 1)
+    full.close()
+    env = environment_from_scene(scene, rank=1, world=4)
+    env.set_option("k4_sim_peers", 1)
+    env.build_transfers(scene.pvs)
+    row0, row1, _ = env.transfers_info()
+    assert 0 < row0 < row1 < N
+    import torch
+    d_emit = torch.from_numpy(emit0).cuda(); d_out = torch.empty_like(d_emit)
+    env.bounce(d_emit, 1, out=d_out, want_added=False)
+    got = d_out.cpu().numpy()
+    assert np.abs(got[row0:row1] - t_full[row0:row1]).max() <= 1e-4 * np.abs(t_full).max()
+    for graph in (0, 1):                           # 40 chained bounces, stream launches and graph replay: must terminate
+        env.set_option("k4_graph", graph)
+        for _ in range(2):
+            env.bounce(d_emit, 40, out=d_out, want_added=False)
+    torch.cuda.synchronize()
+    assert np.isfinite(d_out.cpu().numpy()).all()
+    env.close()

@@ -124,8 +124,8 @@ int comm_setup_peers(vrad_env* e, size_t n_pad) {
     static const bool force_nccl = [] { const char* v = getenv("VRAD_K4_EXCHANGE"); return v && std::string(v) == "nccl"; }();
     if (force_nccl) return 0;
     comm_close_peers(e);
-    if (P.d_flags.alloc(2 * kMaxWorld)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
-    VRAD_CUDA_CHECK(cudaMemsetAsync(P.d_flags.p, 0, 2 * kMaxWorld * sizeof(uint32_t), e->stream));
+    if (P.d_flags.alloc(kFlagWords)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemsetAsync(P.d_flags.p, 0, kFlagWords * sizeof(uint32_t), e->stream));
     struct Handles { cudaIpcMemHandle_t h[3]; int ok; int pad[15]; };
     static_assert(sizeof(Handles) % 4 == 0, "handle record must be a whole number of floats");
     std::vector<Handles> all(world);
@@ -167,7 +167,7 @@ int comm_setup_peers(vrad_env* e, size_t n_pad) {
     tbl.world = world; tbl.rank = rank;
     if (P.d_table.alloc(1)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
     VRAD_CUDA_CHECK(cudaMemcpy(P.d_table.p, &tbl, sizeof(tbl), cudaMemcpyHostToDevice));
-    P.ready = true; P.n_pad = n_pad;
+    P.ready = true; P.simulated = false; P.n_pad = n_pad;
     return 0;
 }
 

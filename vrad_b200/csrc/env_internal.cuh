@@ -82,6 +82,15 @@ struct TransfersDev {
     DevBuf<int32_t> rowlen;         // logical row lengths
     DevBuf<int2>    tr;             // {col, w bits} pairs == the reference's Transfer struct (transfer.go:3-6)
     bool ready = false;
+    // Gather plan (K4): one warp per work item.  A row longer than `seg` entries is cut into parts of `seg` entries
+    // (one item each) so that no warp carries a 30 us row into the tail of a 40 us kernel; the parts' sums meet in
+    // part_sum[] and the part that arrives last (row_ctr) adds them in part order and runs the row's epilogue.
+    //   item int4 = {local row, first entry (relative to the row), entries | n_parts << 16, first part slot of the row}
+    DevBuf<int4>    items;
+    DevBuf<float4>  part_sum;       // one slot per part of a split row
+    DevBuf<int32_t> row_ctr;        // arrivals per local row (split rows only; the finisher resets it)
+    int n_items = 0, n_slots = 0, seg_shift = 11;
+    int64_t plan_serial = 0;        // bumped by every re-plan (invalidates the captured bounce graph)
 };
 
 // BSP point-location data on the device (trace.PointLeafnum, clustertable.PointInLeaf) and the sky cameras.
@@ -99,30 +108,61 @@ struct DevBsp {
 
 constexpr int kMaxWorld = 8;
 
+// the bounce loop of a call, captured as a CUDA graph (k4_bounce.cu); valid while every captured argument is unchanged
+struct GraphCache {
+    cudaGraphExec_t exec = nullptr;
+    int n_bounces = 0, n_items = 0;
+    const void *items = nullptr, *er0 = nullptr, *total = nullptr, *add = nullptr, *tr = nullptr;
+    int64_t row0 = 0, tag = -1;
+    bool p2p = false;
+};
+
 // Peer-memory view of the radiance buffers (multi-GPU K4): pointers into every rank's er[0]/er[1]
 // and flag words, obtained through CUDA IPC (one process per GPU).  Slot `rank` is the local buffer.
 struct PeerTable;
+// flag words of one rank (device memory, mapped by every peer):
+//   [0, kMaxWorld)      arrival words: word p = the last bounce epoch rank p has finished storing into this rank's buffers
+//   [kFlagBase]         epoch of the bounce before the first one of the current vrad_bounce call (written by the owner only)
+//   [kFlagTicket]       blocks of the running gather that have finished (the last one signals and resets it)
+//   [kFlagError]        set when a wait gave up (a peer never signalled): the call returns VRAD_E_COMM instead of hanging
+constexpr int kFlagBase = kMaxWorld, kFlagTicket = kMaxWorld + 1, kFlagError = kMaxWorld + 2, kFlagWords = 2 * kMaxWorld;
 struct PeerLinks {
     bool      ready = false;
+    bool      simulated = false;             // VRAD_K4_SIM_PEERS: every "peer" is this device (single-GPU tuning of the N-rank slice)
     size_t    n_pad = 0;
     float4*   er[2][kMaxWorld] = {};
     uint32_t* flags[kMaxWorld] = {};
     void*     opened[3][kMaxWorld] = {};     // mappings to close
-    DevBuf<uint32_t> d_flags;                // [kMaxWorld] arrival flags + [kMaxWorld] = this rank's epoch counter
+    DevBuf<uint32_t> d_flags;                // kFlagWords words, layout above
+    DevBuf<float4>   d_sink;                 // simulated peers: where the rows "sent" to the other ranks land
     DevBuf<PeerTable> d_table;
 };
 
-// the same pointers as one record in device memory, read by k4_gather<true> and the barrier kernels
+// the same pointers as one record in device memory, read by k4_gather_items<true> and k4_peer_wait
 struct PeerTable {
     float4*   er[2][kMaxWorld];
-    uint32_t* flags[kMaxWorld];              // flags[r][0..kMaxWorld) arrival words, flags[r][kMaxWorld] = rank r's epoch
+    uint32_t* flags[kMaxWorld];              // flags[p][rank] = this rank's arrival word in rank p's flag block
     int world, rank;
 };
 
 } // namespace vrad
 
+namespace vrad {
+// tuning switches of a handle (vrad_env_set_option); the environment variables of the same meaning give the defaults
+struct EnvOptions {
+    int k1_sort = -1;      // VRAD_K1_SORT: order segment batches before tracing; -1 = batches of >= 65536 segments, 0 never, 1 always
+    int k1_top = 0;        // VRAD_K1_TOP: stage the top levels of the kd tree in shared memory (0 = off, else node budget)
+    int k4_seg = 2048;     // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)
+    int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
+    int k4_pdl = 1;        // VRAD_K4_PDL: chain the bounces of the multi-GPU gather with programmatic dependent launch
+    int k4_graph = 1;      // VRAD_K4_GRAPH: replay the bounce loop as a CUDA graph
+    int k4_sim_peers = 0;  // VRAD_K4_SIM_PEERS: single-GPU stand-in for the peers of a multi-GPU handle (timing only)
+};
+} // namespace vrad
+
 struct vrad_env {
     vrad_config cfg{};
+    vrad::EnvOptions opt{};
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     bool async = false;
@@ -146,6 +186,9 @@ struct vrad_env {
     vrad::DevBuf<int32_t> d_tri_index;
     vrad::DevBuf<float4> d_q0, d_q1, d_q2;
     vrad::DevBuf<float> d_tri_cov;     // colour.X per triangle (coverage of transparent triangles)
+    vrad::DevBuf<int2> d_top;          // top tree levels in breadth-first order (DevScene::top)
+    vrad::DevBuf<float4> d_points;     // resident endpoint table of vrad_test_lines_indexed (xyz, pad)
+    int64_t n_points = 0;
     std::vector<float> h_colors;       // Environment.TriangleColors, 3 per triangle
     vrad::DevScene scene{};
 
@@ -175,8 +218,10 @@ struct vrad_env {
     vrad::DevBuf<float4> d_er[2];      // emit*refl (rgb, pad), full N (padded to world*rows_per_rank)
     vrad::DevBuf<float4> d_total;      // accumulated bounced light for local rows
     vrad::DevBuf<float>  d_partials;   // per-block partial sums of `added`
+    vrad::DevBuf<float4> d_add;        // light added per local row by the last gather (deterministic `added` reduction)
     void* nccl_comm = nullptr;         // ncclComm_t
     vrad::PeerLinks peers;             // K4 fused exchange over NVLink peer memory
+    vrad::GraphCache bounce_graph;
 };
 
 namespace vrad {
@@ -198,7 +243,9 @@ int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, 
                       const float* dy, const float* dz, const float* tmin, const float* tmax, int32_t skip_id,
                       int32_t* hit_tri, int32_t* hit_sid, float* hit_t, float* normal_soa);
 int launch_test_lines(vrad_env* e, int64_t n, const float* start_soa, const float* stop_soa, int sky_mode, uint32_t* bits);
-int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, int sky_mode, uint32_t* d_bits);
+int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, const int32_t* h_pairs, int sky_mode, uint32_t* d_bits);
+int launch_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs, int sky_mode, uint32_t* bits);
+int check_pairs_on_device(vrad_env* e, int64_t n, const int32_t* d_pairs, int* bad_out);
 int upload_triangle_coverage(vrad_env* e);
 struct KdTree;
 int build_kd_tree_binned_device(cudaStream_t stream, const float* verts9, int n, KdTree& out, int* launches, const char** why);

@@ -32,6 +32,7 @@
 namespace vrad {
 
 int comm_allreduce_i32(vrad_env* e, int32_t* d, size_t n);
+int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc);
 
 constexpr float kPlaneTestEpsilon = 0.01f;
 constexpr float kTransEpsilon = 1.0e-7f;
@@ -552,8 +553,11 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     }
     int64_t nnz = 0;
     for (int r = 0; r < nloc; r++) nnz += rl[r];
-    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.ready = true;
+    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np;
     cleanup();
+    int rcp = build_gather_plan(e, rl.data(), nloc);
+    if (rcp) return rcp;
+    T.ready = true;
     if (nnz_out) *nnz_out = nnz;
     return VRAD_OK;
 }

@@ -39,77 +39,228 @@ __global__ void k4_init_er(int n_pad, int n, const float* __restrict__ emit0, co
     er[i] = v;
 }
 
-// One warp per row.  Entries are {col, w} pairs -- the reference's Transfer struct
-// (common/types/transfer.go:3-6) -- read as one coalesced 64-bit load per lane with lanes on
-// CONSECUTIVE entries, so the 32 er[] gathers of one instruction hit consecutive patches wherever the
-// row has a run of adjacent columns (avg run length ~16 on the synthetic maps): few L1 wavefronts
-// per gather instead of one per lane (ncu r01: the int4-per-lane mapping was L1TEX-bound at 86%).
-// kGatherUnroll entries per lane are in flight and the {col,w} loads of the NEXT step are issued
-// before the current step's gathers (software pipeline), so the two dependent memory latencies
-// overlap.  The kernel is latency-bound: what matters is bytes in flight per SM = resident warps x
-// entries in flight, so the register budget is capped to keep 5 blocks (40 warps) per SM -- the
-// same loop at 60 registers (4 blocks) ran at 4.1 TB/s, at 48 registers 6.4 TB/s (tools/exp/k4_exp.cu).
+// ---------------------------------------------------------------------------------------------------------
+// The gather.  One warp per WORK ITEM (TransfersDev::items): a whole row, or -- for a row longer than `seg`
+// entries -- one `seg`-entry part of it.  Entries are {col, w} pairs -- the reference's Transfer struct
+// (common/types/transfer.go:3-6) -- read as one coalesced 64-bit load per lane with lanes on CONSECUTIVE
+// entries, so the 32 er[] gathers of one instruction hit consecutive patches wherever the row has a run of
+// adjacent columns (avg run length ~16 on the synthetic maps): few L1 wavefronts per gather instead of one per
+// lane (ncu r01: the int4-per-lane mapping was L1TEX-bound at 86%).  kGatherUnroll entries per lane are in
+// flight and the {col,w} loads of the NEXT step are issued before the current step's gathers (software
+// pipeline), so the two dependent memory latencies overlap.  The kernel is latency-bound: what matters is bytes
+// in flight per SM = resident warps x entries in flight, so the register budget is capped to keep 5 blocks (40
+// warps) per SM -- the same loop at 60 registers (4 blocks) ran at 4.1 TB/s, at 48 registers 6.4 TB/s
+// (tools/exp/k4_exp.cu).
+//
+// Why items: with one warp per row a 4000-entry row is a ~30 us chain of 16 dependent steps; started late it
+// is the whole tail of a kernel that should take 36 us on an 8-rank slice of the C4 matrix (r01 verdict: 54 us
+// per bounce against 36 us of streaming).  Parts bound the longest chain; their sums meet in part_sum[] and the
+// part that arrives last adds them in part order (so the row sum does not depend on scheduling) and runs the
+// row's epilogue.
+//
+// Multi-GPU form (MULTI): the epilogue stores the finished row into every rank's next-bounce buffer (lane p ->
+// rank p; NVLink peer stores), and the inter-bounce barrier lives inside the kernel --
+//   signal: the block that finishes last (ticket) publishes this bounce's epoch in every rank's arrival words;
+//   wait:   each block, after it has issued its first {col,w} loads (which do not depend on the peers), spins
+//           until all ranks' arrival words (its own included) have reached the previous bounce's epoch.
+// Consecutive bounces are therefore ordered by the flags alone, and the next bounce's kernel is launched with
+// programmatic stream serialisation (PDL): its blocks fill the SM slots that the current bounce's tail frees
+// and have their first loads in flight when the last signal arrives.  One launch per bounce, no barrier kernel.
+// Memory model: row stores -> bar.sync -> fence.acq_rel.gpu + ticket atomic (release, gpu scope) -> last block:
+// fence.acq_rel.sys -> st.relaxed.sys arrival words (release, sys scope) -> waiter: ld.acquire.sys -> bar.sync
+// -> plain (ld.global, not ld.global.nc) loads of er[].
 constexpr int kGatherUnroll = 8;
 
-__global__ void __launch_bounds__(kGatherBlock, 5)
-k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
-          const float4* __restrict__ er, const float4* __restrict__ refl,
-          float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = blockIdx.x * kGatherWarps + warp;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
-    if (row < nloc) {
-        const int64_t k0 = rowptr[row], k1 = rowptr[row + 1];      // padded to 4 entries; padding has w = 0
-        const int2 zero = make_int2(0, 0);                          // out-of-row slots: col 0, weight 0
-        int2 cur[kGatherUnroll], nxt[kGatherUnroll];
-        int64_t k = k0 + lane;
-#pragma unroll
-        for (int j = 0; j < kGatherUnroll; j++) cur[j] = k + 32 * j < k1 ? __ldcs(&tr[k + 32 * j]) : zero;
-        for (; k < k1; k += 32 * kGatherUnroll) {
-#pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++)
-                nxt[j] = k + 32 * (kGatherUnroll + j) < k1 ? __ldcs(&tr[k + 32 * (kGatherUnroll + j)]) : zero;
-            float4 x[kGatherUnroll];
-#pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
-#pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++) {
-                const float w = __int_as_float(cur[j].y);
-                s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
-            }
-#pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
+struct GatherAux {                 // rarely used pointers, kept in the parameter bank (no registers until touched)
+    float4* add;                   // light added per local row (written when non-null: last bounce / early-out)
+    float4* part_sum;
+    int32_t* row_ctr;
+    const PeerTable* peers;        // MULTI only
+    uint32_t* flags;               // this rank's flag words (MULTI only)
+    int next_buf;
+    uint32_t wait_rel, signal_rel; // epochs relative to flags[kFlagBase]; wait_rel 0 = nothing to wait for
+    int wait_world;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// wait half of the inter-bounce barrier; block-wide.  Gives up after ~2^30 cycles (about half a second: a peer died) and
+// sets the error word, which makes every later wait return at once -- vrad_bounce then reports VRAD_E_COMM instead of
+// hanging the device.
+__device__ __noinline__ void wait_for_peers(const uint32_t* flags, int wait_world, uint32_t wait_rel) {
+    if ((int)threadIdx.x < wait_world) {
+        const uint32_t epoch = ld_acquire_sys(flags + kFlagBase) + wait_rel;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+            if (*(volatile const uint32_t*)(flags + kFlagError)) break;
+            if (clock64() - t0 > (1LL << 30)) { atomicExch((unsigned int*)flags + kFlagError, 1u); break; }
         }
+    }
+    __syncthreads();
+}
+
+// signal half: called by one thread per block after the block's bar.sync
+__device__ __noinline__ void signal_if_last(const PeerTable* __restrict__ peers, uint32_t* flags, uint32_t signal_rel) {
+    __threadfence();
+    const unsigned int t = atomicAdd((unsigned int*)flags + kFlagTicket, 1u);
+    if (t == gridDim.x - 1) {
+        flags[kFlagTicket] = 0u;
+        const uint32_t epoch = flags[kFlagBase] + signal_rel;
+        __threadfence_system();
+        const int world = peers->world, rank = peers->rank;
+        for (int p = 0; p < world; p++) st_relaxed_sys(peers->flags[p] + rank, epoch);
+    }
+}
+
+// out of line on purpose: keeps the peer-table loads out of the gather loop's register allocation
+__device__ __noinline__ void store_row_to_peers(const PeerTable* __restrict__ peers, int next_buf, int64_t row, float x, float y, float z) {
+    const int lane = threadIdx.x & 31;
+    x = __shfl_sync(0xffffffffu, x, 0); y = __shfl_sync(0xffffffffu, y, 0); z = __shfl_sync(0xffffffffu, z, 0);
+    if (lane < peers->world) peers->er[next_buf][lane][row] = make_float4(x, y, z, 0.f);
+}
+
+// a part of a split row has its sum: publish it, and if it is the last part to arrive add all parts in part order.
+// Warp-uniform; returns true on the finishing warp with the row sums in s0..s2.
+__device__ __noinline__ bool combine_parts(float4* part_sum, int32_t* row_ctr, int row, int slot0, int idx, int n_parts,
+                                           float& s0, float& s1, float& s2) {
+    const int lane = threadIdx.x & 31;
+    int last = 0;
+    if (lane == 0) {
+        __stcg(&part_sum[slot0 + idx], make_float4(s0, s1, s2, 0.f));
+        __threadfence();
+        last = atomicAdd(&row_ctr[row], 1) == n_parts - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return false;
+    __threadfence();
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int p = lane; p < n_parts; p += 32) {          // fixed order: lane-strided, then the xor tree
+        const float4 v = __ldcg(&part_sum[slot0 + p]);
+        a0 += v.x; a1 += v.y; a2 += v.z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) row_ctr[row] = 0;
+    s0 = a0; s1 = a1; s2 = a2;
+    return true;
+}
+
+template <bool MULTI>
+__device__ __forceinline__ float4 load_er(const float4* er, int col) {
+    if (MULTI) return er[col];          // peers store into this buffer between bounces: no read-only (.nc) path
+    return __ldg(&er[col]);
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(kGatherBlock, 5)
+k4_gather_items(int n_items, const int4* __restrict__ items, int seg_shift, int64_t row0, const int64_t* __restrict__ rowptr,
+                const int2* __restrict__ tr, const float4* er, const float4* __restrict__ refl,
+                float4* er_next, float4* __restrict__ total, GatherAux A) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * kGatherWarps + warp;
+    if (MULTI) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next bounce may be scheduled behind this one
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    int4 it = make_int4(0, 0, 0, -1);
+    int64_t k = 0, k1 = 0;
+    if (w < n_items) {
+        it = __ldg(&items[w]);
+        k = rowptr[it.x] + it.y;
+        k1 = k + (it.z & 0xffff);
+        k += lane;
+    }
+    const int2 zero = make_int2(0, 0);                          // out-of-item slots: col 0, weight 0
+    int2 cur[kGatherUnroll], nxt[kGatherUnroll];
+#pragma unroll
+    for (int j = 0; j < kGatherUnroll; j++) cur[j] = k + 32 * j < k1 ? __ldcs(&tr[k + 32 * j]) : zero;
+    if (MULTI) {
+        // the radiance this bounce reads is complete once every rank's previous-bounce epoch has arrived
+        if (A.wait_rel) wait_for_peers(A.flags, A.wait_world, A.wait_rel);
+    }
+    for (; k < k1; k += 32 * kGatherUnroll) {
+#pragma unroll
+        for (int j = 0; j < kGatherUnroll; j++)
+            nxt[j] = k + 32 * (kGatherUnroll + j) < k1 ? __ldcs(&tr[k + 32 * (kGatherUnroll + j)]) : zero;
+        float4 x[kGatherUnroll];
+#pragma unroll
+        for (int j = 0; j < kGatherUnroll; j++) x[j] = load_er<MULTI>(er, cur[j].x);
+#pragma unroll
+        for (int j = 0; j < kGatherUnroll; j++) {
+            const float wt = __int_as_float(cur[j].y);
+            s0 += wt * x[j].x; s1 += wt * x[j].y; s2 += wt * x[j].z;
+        }
+#pragma unroll
+        for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
+    }
+    if (w < n_items) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, o);
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
-        if (lane == 0) {
-            const float4 r = refl[row0 + row];
-            if (r.w == 0.0f) {                                              // CollectLight, leaf patch
-                float4 t = total[row];
-                t.x += s0; t.y += s1; t.z += s2;
-                total[row] = t;
-                er_next[row0 + row] = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
-                e0 = s0; e1 = s1; e2 = s2;
-            } else {
-                er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);     // sky: emit = 0
+        const int n_parts = (int)((unsigned)it.z >> 16);
+        bool fin = true;
+        if (n_parts > 1) fin = combine_parts(A.part_sum, A.row_ctr, it.x, it.w, it.y >> seg_shift, n_parts, s0, s1, s2);
+        if (fin) {
+            const int row = it.x;
+            float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);                    // sky: emit = 0
+            if (lane == 0) {
+                const float4 r = refl[row0 + row];
+                float4 a = nv;
+                if (r.w == 0.0f) {                                          // CollectLight, leaf patch
+                    float4 t = total[row];
+                    t.x += s0; t.y += s1; t.z += s2;
+                    total[row] = t;
+                    nv = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                    a = make_float4(s0, s1, s2, 0.f);
+                }
+                if (A.add) A.add[row] = a;
+                if (!MULTI) er_next[row0 + row] = nv;
             }
+            // fused exchange: lane p stores the finished row straight into rank p's next-bounce buffer
+            // (NVLink peer store; slot `rank` is the local buffer) -- no separate all-gather pass
+            if (MULTI) store_row_to_peers(A.peers, A.next_buf, row0 + row, nv.x, nv.y, nv.z);
         }
     }
-    // deterministic per-block partial of `added`
-    __shared__ float sm[kGatherWarps][3];
-    if (lane == 0) { sm[warp][0] = e0; sm[warp][1] = e1; sm[warp][2] = e2; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < kGatherWarps; k++) a += sm[k][threadIdx.x];
-        partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    if (MULTI) {
+        __syncthreads();
+        if (threadIdx.x == 0) signal_if_last(A.peers, A.flags, A.signal_rel);
     }
+}
+
+// closes the last bounce of a call: every rank's final stores into this rank's buffers have landed (and this
+// rank's final epoch is out) before anything else touches the radiance buffers
+__global__ void k4_peer_wait(uint32_t* flags, int world, uint32_t wait_rel) {
+    wait_for_peers(flags, world, wait_rel);
+    if (threadIdx.x == 0) { flags[kFlagBase] += wait_rel; __threadfence_system(); }
+}
+
+// deterministic `added`: fixed 1024-row blocks -> per-block partial (stage 1), then k4_reduce_added (stage 2)
+__global__ void __launch_bounds__(256) k4_sum_added_rows(int nloc, const float4* __restrict__ add, float* __restrict__ partials) {
+    __shared__ float sm[3][256];
+    const int base = blockIdx.x * 1024;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int r = base + j * 256 + threadIdx.x;
+        if (r < nloc) { const float4 v = add[r]; a0 += v.x; a1 += v.y; a2 += v.z; }
+    }
+    sm[0][threadIdx.x] = a0; sm[1][threadIdx.x] = a1; sm[2][threadIdx.x] = a2;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) for (int c = 0; c < 3; c++) sm[c][threadIdx.x] += sm[c][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) partials[3 * (size_t)blockIdx.x + threadIdx.x] = sm[threadIdx.x][0];
 }
 
 // GatherLight, bump-mapped branch (upstream vrad.cpp; the reference carries the types: Patch.NeedsBumpMap
@@ -249,126 +400,6 @@ k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const
     }
 }
 
-// out of line on purpose: keeps the peer-table loads out of the gather loop's register allocation
-__device__ __noinline__ void store_row_to_peers(const PeerTable* __restrict__ peers, int next_buf, int64_t row, float x, float y, float z) {
-    const int lane = threadIdx.x & 31;
-    x = __shfl_sync(0xffffffffu, x, 0); y = __shfl_sync(0xffffffffu, y, 0); z = __shfl_sync(0xffffffffu, z, 0);
-    if (lane < peers->world) peers->er[next_buf][lane][row] = make_float4(x, y, z, 0.f);
-}
-
-__device__ __noinline__ void wait_for_peers(const PeerTable* __restrict__ peers, int wait_world) {
-    if ((int)threadIdx.x < wait_world) {
-        volatile uint32_t* local = peers->flags[peers->rank];
-        const uint32_t epoch = local[kMaxWorld];
-        while ((int32_t)(local[threadIdx.x] - epoch) < 0) { }
-    }
-    __syncthreads();
-}
-
-// Multi-GPU form of the same kernel: `peers` (device memory) lists every rank's er_next buffer and this
-// rank's flag words; lanes 0..world-1 store the finished row into one rank each (fused exchange), and
-// the prologue is the wait half of the inter-bounce barrier.  Kept as a separate kernel so that the
-// single-GPU instantiation keeps its register allocation (the loop is occupancy-bound).
-template <bool MULTI>
-__global__ void __launch_bounds__(kGatherBlock, 5)
-k4_gather_multi(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
-          const float4* __restrict__ er, const float4* __restrict__ refl,
-          float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials,
-          const PeerTable* __restrict__ peers, int next_buf, int wait_world) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = blockIdx.x * kGatherWarps + warp;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
-    if (MULTI) {
-        // fused-exchange prologue: the radiance this bounce reads is complete once every rank's epoch has
-        // arrived in the local flag words (wait half of the barrier; k4_peer_signal is the other half)
-        if (wait_world > 1) wait_for_peers(peers, wait_world);
-    }
-    if (row < nloc) {
-        const int64_t k0 = rowptr[row], k1 = rowptr[row + 1];      // padded to 4 entries; padding has w = 0
-        const int2 zero = make_int2(0, 0);                          // out-of-row slots: col 0, weight 0
-        int2 cur[kGatherUnroll], nxt[kGatherUnroll];
-        int64_t k = k0 + lane;
-#pragma unroll
-        for (int j = 0; j < kGatherUnroll; j++) cur[j] = k + 32 * j < k1 ? __ldcs(&tr[k + 32 * j]) : zero;
-        for (; k < k1; k += 32 * kGatherUnroll) {
-#pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++)
-                nxt[j] = k + 32 * (kGatherUnroll + j) < k1 ? __ldcs(&tr[k + 32 * (kGatherUnroll + j)]) : zero;
-            float4 x[kGatherUnroll];
-#pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
-#pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++) {
-                const float w = __int_as_float(cur[j].y);
-                s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
-            }
-#pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);                        // sky: emit = 0
-        if (lane == 0) {
-            const float4 r = refl[row0 + row];
-            if (r.w == 0.0f) {                                              // CollectLight, leaf patch
-                float4 t = total[row];
-                t.x += s0; t.y += s1; t.z += s2;
-                total[row] = t;
-                nv = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
-                e0 = s0; e1 = s1; e2 = s2;
-            }
-            if (!MULTI) er_next[row0 + row] = nv;
-        }
-        if (MULTI) {
-            // fused exchange: lane p stores the finished row straight into rank p's next-bounce buffer
-            // (NVLink peer store; slot `rank` is the local buffer) -- no separate all-gather pass
-            store_row_to_peers(peers, next_buf, row0 + row, nv.x, nv.y, nv.z);
-        }
-    }
-    // deterministic per-block partial of `added`
-    __shared__ float sm[kGatherWarps][3];
-    if (lane == 0) { sm[warp][0] = e0; sm[warp][1] = e1; sm[warp][2] = e2; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < kGatherWarps; k++) a += sm[k][threadIdx.x];
-        partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
-    }
-}
-
-// Fused-exchange barrier between bounces, split in two so that no kernel sits spinning between them:
-// k4_peer_signal (one tiny block after each gather) bumps this rank's epoch and stores it into its
-// slot of every peer's flag words -- after a system-scope fence that orders the peer row stores of
-// the gather that just completed -- and the NEXT k4_gather waits in its prologue until all peers'
-// epochs have arrived.  k4_peer_wait closes the last bounce of a call.
-// wait half as a stand-alone kernel: closes the last bounce of a call (no later gather would wait for it)
-__global__ void k4_peer_wait(const PeerTable* __restrict__ peers) {
-    if ((int)threadIdx.x < peers->world) {
-        volatile uint32_t* local = peers->flags[peers->rank];
-        const uint32_t epoch = local[kMaxWorld];
-        while ((int32_t)(local[threadIdx.x] - epoch) < 0) { }
-        __threadfence_system();
-    }
-}
-
-// signal half of the fused-exchange barrier (the wait half is the prologue of k4_gather)
-__global__ void k4_peer_signal(const PeerTable* __restrict__ peers) {
-    __shared__ uint32_t epoch;
-    if (threadIdx.x == 0) epoch = ++peers->flags[peers->rank][kMaxWorld];
-    __syncthreads();
-    if ((int)threadIdx.x < peers->world) {
-        __threadfence_system();
-        volatile uint32_t* dst = peers->flags[threadIdx.x] + peers->rank;
-        *dst = epoch;
-    }
-}
-
 // single block: fixed-order tree reduction of the per-block partials -> added[3]
 __global__ void k4_reduce_added(int nblocks, const float* __restrict__ partials, float* __restrict__ added) {
     __shared__ float sm[3][256];
@@ -440,6 +471,40 @@ k4_collect_parents(int n_interior, int n_long, int long_blocks, const int32_t* _
         collect_row<8>(valid ? cptr[w] : 0, valid ? cptr[w + 1] : 0, sub, ent, buf, s0, s1, s2);
         if (valid && sub == 0) buf[ids[w]] = make_float4(s0, s1, s2, 0.f);
     }
+}
+
+// Work items of the gather for the resident rows (rowlen = logical row lengths, host copy).  Called by
+// vrad_build_transfers and vrad_transfers_upload once the rows are in place.
+int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
+    TransfersDev& T = e->transfers;
+    const int seg_env = e->opt.k4_seg;
+    const bool long_first = e->opt.k4_long_first != 0;
+    int shift = 8;
+    while ((1 << (shift + 1)) <= seg_env && shift < 15) shift++;
+    const int seg = 1 << shift;
+    std::vector<int4> items;
+    items.reserve((size_t)nloc + 1024);
+    int n_slots = 0;
+    for (int64_t r = 0; r < nloc; r++) {
+        const int len = rowlen[r];
+        const int n_parts = len > seg ? (len + seg - 1) / seg : 1;
+        if (n_parts > 0xffff) { set_error("a transfer row of %d entries needs more than 65535 parts of %d", len, seg); return VRAD_E_UNSUPPORTED; }
+        if (n_parts == 1) { items.push_back(make_int4((int)r, 0, len | (1 << 16), -1)); continue; }
+        for (int p = 0; p < n_parts; p++) {
+            const int off = p * seg, l = std::min(seg, len - off);
+            items.push_back(make_int4((int)r, off, l | (n_parts << 16), n_slots));
+        }
+        n_slots += n_parts;
+    }
+    if (long_first) std::stable_sort(items.begin(), items.end(), [](const int4& a, const int4& b) { return (a.z & 0xffff) > (b.z & 0xffff); });
+    if (T.items.alloc(items.size() + 1) || T.part_sum.alloc((size_t)n_slots + 1) || T.row_ctr.alloc((size_t)nloc + 1)) {
+        set_error("out of device memory for the gather plan"); return VRAD_E_NOMEM;
+    }
+    if (!items.empty()) VRAD_CUDA_CHECK(cudaMemcpyAsync(T.items.p, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemsetAsync(T.row_ctr.p, 0, ((size_t)nloc + 1) * 4, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    T.n_items = (int)items.size(); T.n_slots = n_slots; T.seg_shift = shift; T.plan_serial++;
+    return 0;
 }
 
 } // namespace vrad
@@ -637,7 +702,10 @@ int vrad_transfers_upload(vrad_env* e, int64_t row0, int64_t row1, const int64_t
     VRAD_CUDA_CHECK(cudaMemcpyAsync(T.rowlen.p, rlen.data(), rlen.size() * 4, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaMemcpyAsync(T.tr.p, ptr.data(), ptr.size() * 8, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.ready = true;
+    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np;
+    int rcp = build_gather_plan(e, rlen.data(), nloc);
+    if (rcp) return rcp;
+    T.ready = true;
     return VRAD_OK;
 }
 
@@ -706,42 +774,98 @@ int vrad_transfers_download_rows(vrad_env* e, int64_t row_begin, int64_t row_end
     return VRAD_OK;
 }
 
+// One bounce of the flat (non-hierarchical) gather: a single launch.  p2p: the multi-GPU form, chained to the
+// previous bounce by PDL when `chained` (see k4_gather_items).
+static cudaError_t launch_gather_items(vrad_env* e, bool p2p, bool chained, int cur, bool want_add, uint32_t wait_rel, uint32_t signal_rel, float4* total_local) {
+    TransfersDev& T = e->transfers;
+    const int nblocks = std::max(1, (T.n_items + kGatherWarps - 1) / kGatherWarps);
+    GatherAux A{};
+    A.add = want_add ? e->d_add.p : nullptr;
+    A.part_sum = T.part_sum.p; A.row_ctr = T.row_ctr.p;
+    if (!p2p) {
+        k4_gather_items<false><<<nblocks, kGatherBlock, 0, e->stream>>>(T.n_items, T.items.p, T.seg_shift, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p,
+                                                                       e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
+        return cudaGetLastError();
+    }
+    A.peers = e->peers.d_table.p; A.flags = e->peers.d_flags.p; A.next_buf = cur ^ 1;
+    A.wait_rel = wait_rel; A.signal_rel = signal_rel; A.wait_world = e->cfg.world;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(kGatherBlock); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k4_gather_items<true>, T.n_items, (const int4*)T.items.p, T.seg_shift, T.row0, (const int64_t*)T.rowptr.p,
+                              (const int2*)T.tr.p, (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
+}
+
+// VRAD_K4_SIM_PEERS=1 with world > 1 and no communicator: every "peer" is this device -- rows for the other ranks land in a
+// sink buffer and all arrival words are this rank's own -- so that the N-rank slice of a matrix (rows, launches, barrier
+// code path) can be timed and profiled on ONE GPU.  The radiance of the other ranks' rows is never refreshed, so the light
+// is wrong; only the timing is meaningful.  Never used unless the variable is set.
+static int setup_simulated_peers(vrad_env* e, size_t n_pad) {
+    PeerLinks& P = e->peers;
+    if (P.ready && P.simulated && P.n_pad == n_pad) return 0;
+    const int world = e->cfg.world, rank = e->cfg.rank;
+    if (P.d_flags.alloc(kFlagWords) || P.d_sink.alloc(n_pad) || P.d_table.alloc(1)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemsetAsync(P.d_flags.p, 0, kFlagWords * sizeof(uint32_t), e->stream));
+    PeerTable tbl{};
+    for (int r = 0; r < world; r++) {
+        tbl.er[0][r] = r == rank ? e->d_er[0].p : P.d_sink.p;
+        tbl.er[1][r] = r == rank ? e->d_er[1].p : P.d_sink.p;
+        tbl.flags[r] = P.d_flags.p + (r - rank);          // flags[r][rank] == own word r: one signal fills every arrival word
+    }
+    tbl.world = world; tbl.rank = rank;
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(P.d_table.p, &tbl, sizeof(tbl), cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    P.ready = true; P.simulated = true; P.n_pad = n_pad;
+    return 0;
+}
+
 int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out,
                 float added_last[3], int* bounces_done) {
     if (!e || !emit0_rgb || n_bounces < 0) { set_error("vrad_bounce: bad arguments"); return VRAD_E_INVALID; }
     TransfersDev& T = e->transfers;
     if (!T.ready) { set_error("vrad_bounce: no transfers resident (vrad_build_transfers / vrad_transfers_upload first)"); return VRAD_E_STATE; }
-    if (e->cfg.world > 1 && !e->nccl_comm) { set_error("vrad_bounce: world=%d but vrad_comm_init was not called", e->cfg.world); return VRAD_E_STATE; }
+    const bool sim = e->opt.k4_sim_peers && e->cfg.world > 1 && !e->nccl_comm;
+    if (e->cfg.world > 1 && !e->nccl_comm && !sim) { set_error("vrad_bounce: world=%d but vrad_comm_init was not called", e->cfg.world); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     const int64_t N = e->patches.n;
     const int world = e->cfg.world;
     const int64_t rpr = rows_per_rank(e, N);
     const int64_t n_pad = rpr * world;           // >= N; radiance buffers are indexed by global patch number
     int64_t bounds[kMaxWorld + 1] = {0};
-    if (world > 1) {
+    if (world > 1 && !sim) {
         if (world > kMaxWorld) { set_error("vrad_bounce: world %d > %d", world, kMaxWorld); return VRAD_E_UNSUPPORTED; }
         int rcb = comm_exchange_bounds(e, T.row0, T.row1, N, bounds);
         if (rcb) return rcb;
+    } else if (world == 1 && (T.row0 != 0 || T.row1 != N)) {
+        set_error("vrad_bounce: world=1 but the resident transfer rows are [%lld,%lld) of %lld", (long long)T.row0, (long long)T.row1, (long long)N);
+        return VRAD_E_STATE;
     }
     const int nloc = (int)(T.row1 - T.row0);
     const int nblocks = std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
+    const int add_blocks = std::max(1, (nloc + 1023) / 1024);
     // `total` is indexed by global row too, so that the final gather is in place
-    if (e->d_er[0].alloc(n_pad) || e->d_er[1].alloc(n_pad) || e->d_total.alloc(n_pad) || e->d_partials.alloc(3 * (size_t)nblocks + 8)) {
+    if (e->d_er[0].alloc(n_pad) || e->d_er[1].alloc(n_pad) || e->d_total.alloc(n_pad) || e->d_add.alloc((size_t)nloc + 1) ||
+        e->d_partials.alloc(3 * (size_t)std::max(nblocks, add_blocks) + 8)) {
         set_error("out of device memory for bounce state"); return VRAD_E_NOMEM;
     }
     int rc; const void* d_emit0; bool h_in, h_out;
     if ((rc = stage_in(e, 0, emit0_rgb, (size_t)N * 12, &d_emit0, &h_in))) return rc;
     void* d_out3;
     if ((rc = stage_out(e, 1, total_rgb_out, (size_t)N * 12, &d_out3, &h_out))) return rc;
-    float* d_added = e->d_partials.p + 3 * (size_t)nblocks;       // 3 floats after the partials
+    float* d_added = e->d_partials.p + 3 * (size_t)std::max(nblocks, add_blocks);       // 3 floats after the partials
     // with a patch hierarchy the interior patches are recomputed from the exchanged leaf rows on every rank, which
     // needs the complete buffer before the next gather starts: the fused peer-store exchange is not used then
     const PatchesDev& PD = e->patches;
     const bool hier = PD.hier && PD.n_interior > 0;
     const int collect_long_blocks = (PD.n_collect_long + 7) / 8;
     const int collect_blocks = collect_long_blocks + (PD.n_interior - PD.n_collect_long + 31) / 32;
-    if (world > 1 && !hier && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
+    if (sim) { if ((rc = setup_simulated_peers(e, (size_t)n_pad))) return rc; }
+    else if (world > 1 && !hier && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
     const bool p2p = world > 1 && !hier && e->peers.ready;
+    if (sim && !p2p) { set_error("vrad_bounce: VRAD_K4_SIM_PEERS does not cover the patch hierarchy"); return VRAD_E_UNSUPPORTED; }
     // short-row form: chosen by the average row length of the rows that gather (env VRAD_K4_SHORT=0/1 forces it)
     int n_short = nloc;
     const int32_t* d_rows = nullptr;
@@ -777,16 +901,16 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         }
     }
     static const int force_short = [] { const char* v = getenv("VRAD_K4_SHORT"); return v ? atoi(v) : -1; }();
-    const bool use_short = !p2p && (force_short >= 0 ? force_short != 0 : (T.nnz < (int64_t)400 * std::max(1, n_short)));
+    const bool use_short = !p2p && (hier || (force_short >= 0 ? force_short != 0 : (T.nnz < (int64_t)400 * std::max(1, n_short))));
     static const int short_cfg = [] { const char* v = getenv("VRAD_K4_SHORT_CFG"); return v ? atoi(v) : 884; }();   // experiments; see the switch below
     const int short_lanes = short_cfg / 10 == 16 ? 16 : (short_cfg / 10 == 4 ? 4 : 8);
     const int short_rpb = kGatherBlock / short_lanes;
     const int short_blocks = std::max(1, (n_short + short_rpb - 1) / short_rpb);
-    const PeerTable* d_peers = p2p ? e->peers.d_table.p : nullptr;
+    const bool use_pdl = e->opt.k4_pdl != 0, use_graph = e->opt.k4_graph != 0;
 
     timing_begin(e);
     int launches = 0;
-    float4* total_local = e->d_total.p + (world > 1 ? T.row0 : 0);
+    float4* total_local = e->d_total.p + T.row0;
     VRAD_CUDA_CHECK(cudaMemsetAsync(e->d_total.p, 0, (size_t)n_pad * 16, e->stream));
     VRAD_CUDA_CHECK(cudaMemsetAsync(d_added, 0, 12, e->stream));
     k4_init_er<<<(int)((n_pad + 255) / 256), 256, 0, e->stream>>>((int)n_pad, (int)N, (const float*)d_emit0, e->patches.refl.p, e->d_er[0].p);
@@ -795,17 +919,60 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     int cur = 0, done = 0;
     float h_added[3] = {0.f, 0.f, 0.f};
     static const bool verbose = getenv("VRAD_TIMING") != nullptr;
-    bool pending_wait = false;      // a peer signal was sent that no gather prologue has waited for yet
     constexpr int kProbe = 16;
     cudaEvent_t pe[kProbe][3];
     int n_probe = 0;
-    for (int b = 0; b < n_bounces; b++) {
+    // The plain loop of item gathers (no early-out, no hierarchy, no bump, no NCCL exchange) is a fixed sequence of
+    // launches whose arguments depend only on the bounce number: it is captured once per (bounce count, buffers)
+    // as a CUDA graph and replayed, so the host issues one graph launch per call instead of one kernel per bounce.
+    const bool items_only = !use_short && !bump && !hier && (world == 1 || p2p);
+    const bool graphed = items_only && use_graph && !early_out && !verbose && n_bounces >= 4;
+    if (graphed) {
+        GraphCache& G = e->bounce_graph;
+        const int64_t graph_tag = T.plan_serial * 4 + (use_pdl ? 2 : 0) + (p2p ? 1 : 0);
+        const bool hit = G.exec && G.n_bounces == n_bounces && G.items == T.items.p && G.n_items == T.n_items && G.er0 == e->d_er[0].p && G.total == total_local &&
+                         G.p2p == p2p && G.row0 == T.row0 && G.add == e->d_add.p && G.tr == T.tr.p && G.tag == graph_tag;
+        if (!hit) {
+            if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+            // capture on the handle's own stream (the caller's stream may be the legacy default stream, which cannot capture)
+            cudaStream_t user = e->stream;
+            VRAD_CUDA_CHECK(cudaStreamSynchronize(user));
+            e->stream = e->own_stream;
+            cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+            int c = 0;
+            for (int b = 0; b < n_bounces && ce == cudaSuccess; b++) {
+                ce = launch_gather_items(e, p2p, p2p && use_pdl && b > 0, c, b + 1 == n_bounces, p2p ? (uint32_t)b : 0u, (uint32_t)b + 1u, total_local);
+                c ^= 1;
+            }
+            cudaGraph_t g = nullptr;
+            cudaError_t ce2 = cudaStreamEndCapture(e->stream, &g);
+            e->stream = user;
+            if (ce == cudaSuccess) ce = ce2;
+            if (ce == cudaSuccess) ce = cudaGraphInstantiate(&G.exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (ce != cudaSuccess) {       // capture not available here (e.g. a driver without programmatic edges): plain launches from now on
+                G.exec = nullptr; cudaGetLastError();
+                if (getenv("VRAD_VERBOSE")) fprintf(stderr, "[vrad] bounce-loop graph capture failed (%s); using stream launches\n", cudaGetErrorString(ce));
+                e->opt.k4_graph = 0;
+            }
+            G.n_bounces = n_bounces; G.items = T.items.p; G.n_items = T.n_items; G.er0 = e->d_er[0].p; G.total = total_local; G.p2p = p2p; G.row0 = T.row0;
+            G.add = e->d_add.p; G.tr = T.tr.p; G.tag = graph_tag;
+        }
+        if (G.exec) {
+            VRAD_CUDA_CHECK(cudaGraphLaunch(G.exec, e->stream));
+            launches += n_bounces;
+            done = n_bounces; cur = n_bounces & 1;
+            k4_sum_added_rows<<<add_blocks, 256, 0, e->stream>>>(nloc, e->d_add.p, e->d_partials.p);
+            k4_reduce_added<<<1, 256, 0, e->stream>>>(add_blocks, e->d_partials.p, d_added);
+            launches += 2;
+            if (world > 1 && !sim && (rc = comm_allreduce3(e, d_added))) return rc;
+        }
+    }
+    for (int b = 0; b < n_bounces && done < n_bounces; b++) {
         const bool probe = verbose && b >= 4 && n_probe < kProbe;
+        const bool last = (b + 1 == n_bounces);
         if (probe) { for (int k = 0; k < 3; k++) cudaEventCreate(&pe[n_probe][k]); cudaEventRecord(pe[n_probe][0], e->stream); }
-        if (p2p)    // pending_wait false: nothing outstanding, the buffer read was initialised locally
-            k4_gather_multi<true><<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
-                                                                   e->d_er[cur ^ 1].p, total_local, e->d_partials.p, d_peers, cur ^ 1, pending_wait ? world : 0);
-        else if (use_short) {
+        if (use_short) {
 #define VRAD_SHORT(L, B, ...) k4_gather_short<L, B, ##__VA_ARGS__><<<short_blocks, kGatherBlock, 0, e->stream>>>(n_short, d_rows, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, \
                                                                  e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p)
             switch (short_cfg) {                                  // lanes per row, min blocks/SM[, unroll, prefetch]: measured on the hierarchical S2 matrix
@@ -815,12 +982,11 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
                 default: VRAD_SHORT(8, 8, 4, false); break;       // 61.9 us: no prefetch, 32 registers, 64 warps per SM
             }
 #undef VRAD_SHORT
+        } else {
+            // p2p: bounce b waits for every rank's epoch base+b (bounce 0 reads locally initialised radiance) and signals base+b+1
+            VRAD_CUDA_CHECK(launch_gather_items(e, p2p, p2p && use_pdl && b > 0 && !probe, cur, early_out || last, p2p ? (uint32_t)b : 0u, (uint32_t)b + 1u, total_local));
         }
-        else
-            k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
-                                                             e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
         launches++;
-        pending_wait = false;
         if (bump && PD.n_bump_rows > 0) {       // same emitters as the gather above (er[cur]), bump-mapped rows only
             k4_gather_bump<<<(PD.n_bump_rows * 32 + 255) / 256, 256, 0, e->stream>>>(PD.n_bump_rows, PD.bump_rows.p, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p,
                                                                                   PD.origin_area.p, PD.normal_dist.p, PD.bump_normals.p,
@@ -828,19 +994,21 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             launches++;
         }
         if (probe) cudaEventRecord(pe[n_probe][1], e->stream);
-        if (p2p) { k4_peer_signal<<<1, 32, 0, e->stream>>>(d_peers); launches++; pending_wait = true; }
-        else if (world > 1 && (rc = comm_allgather_rows(e, e->d_er[cur ^ 1].p, bounds))) return rc;
+        if (!p2p && world > 1 && (rc = comm_allgather_rows(e, e->d_er[cur ^ 1].p, bounds))) return rc;
         if (hier) {     // CollectLight, interior patches: emit of a parent = area-weighted average of its children
             k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_er[cur ^ 1].p);
             launches++;
         }
         if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
         cur ^= 1; done++;
-        const bool last = (b + 1 == n_bounces);
         if (early_out || last) {
-            k4_reduce_added<<<1, 256, 0, e->stream>>>(use_short ? short_blocks : nblocks, e->d_partials.p, d_added);
-            launches++;
-            if (world > 1 && (rc = comm_allreduce3(e, d_added))) return rc;
+            if (use_short) { k4_reduce_added<<<1, 256, 0, e->stream>>>(short_blocks, e->d_partials.p, d_added); launches++; }
+            else {
+                k4_sum_added_rows<<<add_blocks, 256, 0, e->stream>>>(nloc, e->d_add.p, e->d_partials.p);
+                k4_reduce_added<<<1, 256, 0, e->stream>>>(add_blocks, e->d_partials.p, d_added);
+                launches += 2;
+            }
+            if (world > 1 && !sim && (rc = comm_allreduce3(e, d_added))) return rc;
         }
         if (early_out && !last) {
             VRAD_CUDA_CHECK(cudaMemcpyAsync(h_added, d_added, 12, cudaMemcpyDeviceToHost, e->stream));
@@ -848,8 +1016,8 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             if (h_added[0] < 1.0f && h_added[1] < 1.0f && h_added[2] < 1.0f) break;
         }
     }
-    if (pending_wait) { k4_peer_wait<<<1, 32, 0, e->stream>>>(d_peers); launches++; }
-    if (world > 1 && (rc = comm_allgather_rows(e, e->d_total.p, bounds))) return rc;
+    if (p2p && done > 0) { k4_peer_wait<<<1, 32, 0, e->stream>>>(e->peers.d_flags.p, world, (uint32_t)done); launches++; }
+    if (world > 1 && !sim && (rc = comm_allgather_rows(e, e->d_total.p, bounds))) return rc;
     if (hier) {         // totallight of the interior patches, from the leaves' totals
         k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_total.p);
         launches++;
@@ -869,14 +1037,21 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             g += a; x += c;
             for (int k = 0; k < 3; k++) cudaEventDestroy(pe[i][k]);
         }
-        fprintf(stderr, "[vrad] rank %d k4_gather %.1f us, exchange (%s) %.1f us per bounce (%d probed)\n", e->cfg.rank,
-                1e3f * g / n_probe, p2p ? "peer stores + barrier" : (world > 1 ? "ncclAllGather" : "none"), 1e3f * x / n_probe, n_probe);
+        fprintf(stderr, "[vrad] rank %d gather %.1f us, exchange (%s) %.1f us per bounce (%d probed)\n", e->cfg.rank,
+                1e3f * g / n_probe, p2p ? "peer stores + in-kernel barrier" : (world > 1 ? "ncclAllGather" : "none"), 1e3f * x / n_probe, n_probe);
     }
     if ((rc = finish_out(e, total_rgb_out, d_out3, (size_t)N * 12, h_out))) return rc;
-    const bool need_sync = h_in || h_out || added_last != nullptr;
+    bool need_sync = h_in || h_out || added_last != nullptr;
     if (added_last) VRAD_CUDA_CHECK(cudaMemcpyAsync(added_last, d_added, 12, cudaMemcpyDeviceToHost, e->stream));
     if (bounces_done) *bounces_done = done;
-    return sync_if_needed(e, need_sync);
+    uint32_t h_err = 0;
+    if (p2p && (need_sync || !e->async)) {       // a wait that gave up (dead peer) is an error, not a hang; async callers see it on their next synchronous call
+        VRAD_CUDA_CHECK(cudaMemcpyAsync(&h_err, e->peers.d_flags.p + kFlagError, 4, cudaMemcpyDeviceToHost, e->stream));
+        need_sync = true;
+    }
+    if ((rc = sync_if_needed(e, need_sync))) return rc;
+    if (h_err) { set_error("vrad_bounce: a rank never signalled the end of a bounce (inter-GPU barrier timed out)"); return VRAD_E_COMM; }
+    return VRAD_OK;
 }
 
 } // extern "C"

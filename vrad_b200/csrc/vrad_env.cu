@@ -1,7 +1,9 @@
 // vrad_env.cu -- handle lifetime, geometry/tree management and the K1 entry points of the C-ABI.
 // Reference map per function: see include/vrad_cuda.h.
 #include "env_internal.cuh"
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <new>
 
@@ -68,6 +70,8 @@ int sync_if_needed(vrad_env* e, bool any_host) {
     return 0;
 }
 
+int upload_top_levels(vrad_env* e);
+
 static int upload_scene(vrad_env* e) {
     const KdTree& T = e->tree;
     const size_t nn = T.children.size(), ni = T.tri_index.size(), nt = e->h_tris.size();
@@ -101,6 +105,8 @@ static int upload_scene(vrad_env* e) {
     S.n_nodes = (int)nn; S.n_idx = (int)ni; S.n_tris = (int)nt;
     S.tri_cov = nullptr;
     e->built = true;
+    int rct = upload_top_levels(e);
+    if (rct) return rct;
     return upload_triangle_coverage(e);
 }
 
@@ -118,11 +124,46 @@ int upload_triangle_coverage(vrad_env* e) {
     return 0;
 }
 
+// The top of the tree in breadth-first order for shared-memory staging (DevScene::top): nodes are taken level by level
+// while both children of a node still fit the budget (EnvOptions::k1_top nodes, at most 2047 = 16 KB).  A staged node whose
+// children are staged too points at their slots, flagged with kTopRef; every other word is the node's own.
+int upload_top_levels(vrad_env* e) {
+    DevScene& S = e->scene;
+    S.top = nullptr; S.n_top = 0;
+    const int budget = std::min(e->opt.k1_top, 2047);
+    const KdTree& T = e->tree;
+    if (budget < 3 || T.children.empty()) return 0;
+    std::vector<int> order(1, 0), slot_of;            // order[slot] = tree node
+    std::vector<int2> top;
+    std::vector<int> first_child_slot(1, -1);
+    for (size_t head = 0; head < order.size(); head++) {
+        const int n = order[head], word = T.children[n];
+        if ((word & 3) == 3) continue;                                    // leaf: nothing to expand
+        if ((int)order.size() + 2 > budget) continue;                     // children stay in global memory
+        first_child_slot[head] = (int)order.size();
+        order.push_back(word >> 2); order.push_back((word >> 2) + 1);
+        first_child_slot.push_back(-1); first_child_slot.push_back(-1);
+    }
+    top.resize(order.size());
+    for (size_t k = 0; k < order.size(); k++) {
+        const int n = order[k];
+        int word = T.children[n];
+        if (first_child_slot[k] >= 0) word = ((first_child_slot[k] | kTopRef) << 2) | (word & 3);
+        top[k].x = word; memcpy(&top[k].y, &T.split[n], 4);
+    }
+    if (e->d_top.alloc(top.size())) { set_error("out of device memory for the staged tree levels"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(e->d_top.p, top.data(), top.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    S.top = e->d_top.p; S.n_top = (int)top.size();
+    return 0;
+}
+
 } // namespace vrad
 
 using namespace vrad;
 
 extern "C" void vrad_comm_destroy_internal(vrad_env*);   // comm.cu
+namespace vrad { int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc); int upload_top_levels(vrad_env* e); }
 
 extern "C" {
 
@@ -146,6 +187,14 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
     vrad_env* e = new (std::nothrow) vrad_env();
     if (!e) return VRAD_E_NOMEM;
     e->cfg = c;
+    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    e->opt.k1_sort = env_int("VRAD_K1_SORT", e->opt.k1_sort);
+    e->opt.k1_top = env_int("VRAD_K1_TOP", e->opt.k1_top);
+    e->opt.k4_seg = env_int("VRAD_K4_SEG", e->opt.k4_seg);
+    { const char* v = getenv("VRAD_K4_ORDER"); e->opt.k4_long_first = v && std::string(v) == "long"; }
+    e->opt.k4_pdl = env_int("VRAD_K4_PDL", e->opt.k4_pdl);
+    e->opt.k4_graph = env_int("VRAD_K4_GRAPH", e->opt.k4_graph);
+    e->opt.k4_sim_peers = env_int("VRAD_K4_SIM_PEERS", e->opt.k4_sim_peers);
     cudaDeviceProp prop;
     VRAD_CUDA_CHECK(cudaGetDeviceProperties(&prop, c.device));
     e->sm_count = prop.multiProcessorCount;
@@ -168,14 +217,17 @@ void vrad_env_destroy(vrad_env* e) {
     cudaStreamSynchronize(e->stream);
     vrad_comm_destroy_internal(e);
     e->d_nodes.release(); e->d_tri_index.release(); e->d_q0.release(); e->d_q1.release(); e->d_q2.release();
-    e->d_tri_cov.release(); e->d_bsp_nodes.release(); e->d_bsp_planes.release(); e->d_cams.release();
+    e->d_tri_cov.release(); e->d_top.release(); e->d_points.release(); e->d_bsp_nodes.release(); e->d_bsp_planes.release(); e->d_cams.release();
     e->d_leaf_cluster.release(); e->d_leaf_area.release(); e->d_area_camera.release();
     for (auto& s : e->scratch) s.release();
     e->patches.origin_area.release(); e->patches.normal_dist.release(); e->patches.refl.release(); e->patches.cluster.release();
     e->patches.tree.release(); e->patches.collect_ids.release(); e->patches.collect_ptr.release(); e->patches.collect_ent.release(); e->patches.leaf_rows.release(); e->patches.child2.release();
     e->patches.bump_normals.release(); e->patches.bump_rows.release(); for (int b = 0; b < 3; b++) e->patches.total_bump[b].release();
     e->transfers.rowptr.release(); e->transfers.rowlen.release(); e->transfers.tr.release();
-    e->d_sky_dirs.release(); e->d_er[0].release(); e->d_er[1].release(); e->d_total.release(); e->d_partials.release();
+    e->d_sky_dirs.release(); e->d_er[0].release(); e->d_er[1].release(); e->d_total.release(); e->d_partials.release(); e->d_add.release();
+    if (e->bounce_graph.exec) cudaGraphExecDestroy(e->bounce_graph.exec);
+    e->peers.d_sink.release();
+    e->transfers.items.release(); e->transfers.part_sum.release(); e->transfers.row_ctr.release();
     for (int s = 0; s < 2; s++) {
         e->d_stage[s].release();
         if (e->ev_copied[s]) cudaEventDestroy(e->ev_copied[s]);
@@ -192,6 +244,29 @@ int vrad_env_set_stream(vrad_env* e, void* cuda_stream) {
     if (!e) return VRAD_E_INVALID;
     cudaStreamSynchronize(e->stream);
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return VRAD_OK;
+}
+
+int vrad_env_set_option(vrad_env* e, const char* name, int value) {
+    if (!e || !name) { set_error("vrad_env_set_option: bad arguments"); return VRAD_E_INVALID; }
+    const std::string n(name);
+    EnvOptions& o = e->opt;
+    if (n == "k1_sort") o.k1_sort = value;
+    else if (n == "k1_top") { o.k1_top = value; if (e->built) { VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device)); VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream)); return upload_top_levels(e); } }
+    else if (n == "k4_seg" || n == "k4_long_first") {
+        (n == "k4_seg" ? o.k4_seg : o.k4_long_first) = value;
+        if (e->transfers.ready) {           // re-plan the resident rows
+            VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+            const int64_t nloc = e->transfers.row1 - e->transfers.row0;
+            std::vector<int32_t> rl(nloc ? nloc : 1);
+            if (nloc) VRAD_CUDA_CHECK(cudaMemcpy(rl.data(), e->transfers.rowlen.p, (size_t)nloc * 4, cudaMemcpyDeviceToHost));
+            return build_gather_plan(e, rl.data(), nloc);
+        }
+    }
+    else if (n == "k4_pdl") o.k4_pdl = value;
+    else if (n == "k4_graph") o.k4_graph = value;
+    else if (n == "k4_sim_peers") o.k4_sim_peers = value;
+    else { set_error("vrad_env_set_option: unknown option '%s'", name); return VRAD_E_INVALID; }
     return VRAD_OK;
 }
 
@@ -427,7 +502,7 @@ int vrad_test_lines(vrad_env* e, int64_t n, const float* start_xyz_soa, const fl
         // large host batch: overlap the H2D copies with the traversal
         void* d_o;
         if ((rc = stage_out(e, 2, vis_bits, wb, &d_o, &ho))) return rc;
-        if ((rc = launch_test_lines_pipelined(e, n, start_xyz_soa, stop_xyz_soa, sky_mode, (uint32_t*)d_o))) return rc;
+        if ((rc = launch_test_lines_pipelined(e, n, start_xyz_soa, stop_xyz_soa, nullptr, sky_mode, (uint32_t*)d_o))) return rc;
         if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
         return sync_if_needed(e, true);
     }
@@ -438,6 +513,64 @@ int vrad_test_lines(vrad_env* e, int64_t n, const float* start_xyz_soa, const fl
     if ((rc = launch_test_lines(e, n, (const float*)d_a, (const float*)d_b, sky_mode, (uint32_t*)d_o))) return rc;
     if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
     return sync_if_needed(e, ha | hb | ho);
+}
+
+/* endpoint table for vrad_test_lines_indexed: patch origins, light origins, luxel samples ... (xyz interleaved) */
+int vrad_points_upload(vrad_env* e, int64_t n_points, const float* xyz3) {
+    if (!e || n_points <= 0 || !xyz3) { set_error("vrad_points_upload: bad arguments"); return VRAD_E_INVALID; }
+    if (n_points > 0x7fffffff) { set_error("vrad_points_upload: %lld points exceed the int32 index range", (long long)n_points); return VRAD_E_INVALID; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    if (e->d_points.alloc((size_t)n_points)) { set_error("out of device memory for %lld points", (long long)n_points); return VRAD_E_NOMEM; }
+    std::vector<float> host;
+    const float* src = xyz3;
+    if (is_device_ptr(xyz3)) {
+        host.resize(3 * (size_t)n_points);
+        VRAD_CUDA_CHECK(cudaMemcpy(host.data(), xyz3, host.size() * 4, cudaMemcpyDeviceToHost));
+        src = host.data();
+    }
+    std::vector<float4> p4((size_t)n_points);
+    for (int64_t i = 0; i < n_points; i++) p4[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(e->d_points.p, p4.data(), p4.size() * sizeof(float4), cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->n_points = n_points;
+    return VRAD_OK;
+}
+
+int vrad_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs2, int sky_mode, uint32_t* vis_bits) {
+    if (!e || n < 0 || (n > 0 && (!pairs2 || !vis_bits))) { set_error("vrad_test_lines_indexed: bad arguments"); return VRAD_E_INVALID; }
+    if (!e->built) { set_error("vrad_test_lines_indexed: acceleration structure not built"); return VRAD_E_STATE; }
+    if (e->n_points == 0) { set_error("vrad_test_lines_indexed: no point table (vrad_points_upload first)"); return VRAD_E_STATE; }
+    if (n == 0) return VRAD_OK;
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const size_t b = (size_t)n * 8, wb = (size_t)((n + 31) / 32) * 4;
+    int rc; bool hp, ho; void* d_o;
+    const bool host_pairs = !is_device_ptr(pairs2);
+    // the indices are checked where they are: on the host for host buffers (before anything is enqueued), by a
+    // device pass for device buffers -- a bad index must be an error, not an out-of-bounds read in the kernel
+    if (host_pairs) {
+        const int64_t np = e->n_points;
+        int64_t bad = -1;
+#pragma omp parallel for reduction(max : bad) schedule(static)
+        for (int64_t i = 0; i < 2 * n; i++)
+            if (pairs2[i] < 0 || pairs2[i] >= np) bad = i > bad ? i : bad;
+        if (bad >= 0) { set_error("vrad_test_lines_indexed: segment %lld refers to point %d of %lld", (long long)(bad / 2), pairs2[bad], (long long)np); return VRAD_E_INVALID; }
+    }
+    if ((rc = stage_out(e, 2, vis_bits, wb, &d_o, &ho))) return rc;
+    if (host_pairs && n >= ((int64_t)1 << 22)) {
+        if ((rc = launch_test_lines_pipelined(e, n, nullptr, nullptr, pairs2, sky_mode, (uint32_t*)d_o))) return rc;
+        if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
+        return sync_if_needed(e, true);
+    }
+    const void* d_p;
+    if ((rc = stage_in(e, 0, pairs2, b, &d_p, &hp))) return rc;
+    if (!host_pairs && !e->async) {          // async callers: the kernels clamp the indices (memory-safe), nothing is read back
+        int bad = 0;
+        if ((rc = check_pairs_on_device(e, n, (const int32_t*)d_p, &bad))) return rc;
+        if (bad) { set_error("vrad_test_lines_indexed: %d indices outside the %lld-point table", bad, (long long)e->n_points); return VRAD_E_INVALID; }
+    }
+    if ((rc = launch_test_lines_indexed(e, n, (const int32_t*)d_p, sky_mode, (uint32_t*)d_o))) return rc;
+    if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
+    return sync_if_needed(e, hp | ho);
 }
 
 } // extern "C"

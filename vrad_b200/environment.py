@@ -70,6 +70,10 @@ class Environment:
     def set_async(self, flag: bool):
         check(self._l.vrad_env_set_async(self._h, C.c_int(int(flag))))
 
+    def set_option(self, name: str, value: int):
+        """Tuning switches (include/vrad_cuda.h: vrad_env_set_option): k1_sort, k1_top, k4_seg, k4_long_first, k4_pdl, k4_graph, k4_sim_peers."""
+        check(self._l.vrad_env_set_option(self._h, C.c_char_p(name.encode()), C.c_int(int(value))))
+
     def last_timing(self):
         ms, nl = C.c_float(), C.c_int()
         check(self._l.vrad_env_last_timing(self._h, C.byref(ms), C.byref(nl)))
@@ -188,6 +192,27 @@ class Environment:
             else:
                 out = np.empty(nw, np.uint32)
         check(self._l.vrad_test_lines(self._h, C.c_int64(n), ptr(s), ptr(e), C.c_int(sky_mode), ptr(out)))
+        return out
+
+    def points_upload(self, xyz):
+        """Resident endpoint table for test_lines_indexed: [P, 3] points (patch origins, light origins, luxel samples ...)."""
+        xyz = _f32(xyz).reshape(-1, 3)
+        check(self._l.vrad_points_upload(self._h, C.c_int64(xyz.shape[0]), ptr(xyz)))
+        self.n_points = int(xyz.shape[0])
+
+    def test_lines_indexed(self, pairs, sky_mode=0, out=None):
+        """Batched TestLine over index pairs [n, 2] (int32) into the uploaded point table -> uint32 visibility words."""
+        if not _is_torch(pairs):
+            pairs = np.ascontiguousarray(pairs, np.int32)
+        n = int(pairs.shape[0])
+        nw = (n + 31) // 32
+        if out is None:
+            if _is_torch(pairs):
+                import torch
+                out = torch.empty(nw, dtype=torch.int32, device=pairs.device)
+            else:
+                out = np.empty(nw, np.uint32)
+        check(self._l.vrad_test_lines_indexed(self._h, C.c_int64(n), ptr(pairs), C.c_int(sky_mode), ptr(out)))
         return out
 
     # ---- full TestLineDoesHitSky surface: colours, BSP lumps, sky cameras (section 8 f2) -----

@@ -341,6 +341,24 @@ def shadow_segments(scene: Scene, n: int, seed: int = 0xC0FFEE) -> tuple[np.ndar
     return np.ascontiguousarray(start.T), np.ascontiguousarray(stop.T)
 
 
+def shadow_segment_indices(scene: Scene, n: int, seed: int = 0xC0FFEE) -> tuple[np.ndarray, np.ndarray]:
+    """The segments of `shadow_segments(scene, n, seed)` as the lighting stages name them: a point table
+    (`origin + normal` of every patch, then the light origins) and [n, 2] int32 index pairs (start, stop) into it.
+    points[pairs[:, 0]].T == start and points[pairs[:, 1]].T == stop, bit for bit."""
+    rng = SplitMix64(seed)
+    N = scene.n_patches
+    a = rng.integers(n, N)
+    b = rng.integers(n, N)
+    pts = (scene.patch_origin + scene.patch_normal).astype(np.float32)
+    pairs = np.stack([a, b], axis=1).astype(np.int32)
+    if scene.lights is not None and len(scene.lights):
+        li = rng.integers(n, len(scene.lights))
+        to_light = (np.arange(n) % 2) == 0
+        pairs[to_light, 1] = N + li[to_light]
+        pts = np.concatenate([pts, np.asarray(scene.lights["origin"], np.float32)], axis=0)
+    return np.ascontiguousarray(pts), np.ascontiguousarray(pairs)
+
+
 def random_rays(scene: Scene, n: int, seed: int = 0xBEEF) -> dict:
     """General closest-hit rays: origins inside the scene AABB, uniform directions, tmax = MAX_TRACE_LENGTH."""
     rng = SplitMix64(seed)
