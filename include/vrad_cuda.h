@@ -97,6 +97,9 @@ int  vrad_env_set_async(vrad_env*, int async);
  *   "k1_top"        (VRAD_K1_TOP)       stage the top of the kd tree in shared memory: 0 = off (default), n = node budget
  *   "k4_seg"        (VRAD_K4_SEG)       entries per gather work item; longer transfer rows are split (default 2048)
  *   "k4_long_first" (VRAD_K4_ORDER=long) gather work items longest first
+ *   "k4_persist"    (VRAD_K4_PERSIST)   gather grid = one block per resident slot over equal-work item ranges (default 1);
+ *                                       0 = 8 items per block, as many blocks as that takes
+ *   "k4_block"      (VRAD_K4_BLOCK)     threads per gather block: 256 (5 blocks per SM) or 192 (6 per SM, more registers)
  *   "k4_pdl"        (VRAD_K4_PDL)       multi-GPU gather: chain the bounces by programmatic dependent launch (default 1)
  *   "k4_graph"      (VRAD_K4_GRAPH)     replay the bounce loop as a CUDA graph (default 1)
  *   "k4_sim_peers"  (VRAD_K4_SIM_PEERS) world > 1 without a communicator: this device stands in for every peer -- timing

@@ -105,12 +105,14 @@ def _gather_reference(orc, scene, emit0, n):
     return orc.bounce(emit0, n, threads=8)
 
 
-@pytest.mark.parametrize("seg,long_first,graph", [(256, 0, 1), (256, 1, 0), (2048, 0, 1), (32768, 0, 0), (512, 1, 1)])
-def test_gather_items_any_plan_same_light(seg, long_first, graph, s2_small_scene, s2_small_oracle):
+@pytest.mark.parametrize("seg,long_first,graph,block,persist", [(256, 0, 1, 256, 1), (256, 1, 0, 192, 0), (2048, 0, 1, 192, 1), (32768, 0, 0, 256, 0),
+                                                                (512, 1, 1, 256, 1)])
+def test_gather_items_any_plan_same_light(seg, long_first, graph, block, persist, s2_small_scene, s2_small_oracle):
     from vrad_b200.environment import environment_from_scene
     scene = s2_small_scene
     env = environment_from_scene(scene)
     env.set_option("k4_seg", seg); env.set_option("k4_long_first", long_first); env.set_option("k4_graph", graph)
+    env.set_option("k4_block", block); env.set_option("k4_persist", persist)
     nnz = env.build_transfers(scene.pvs)
     assert nnz == s2_small_oracle.build_transfers(scene.pvs, threads=8)
     N = scene.n_patches

@@ -1,6 +1,8 @@
 """Prints the metrics we track from an `ncu --page raw --csv` dump (one block per profiled launch)."""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
+while rows and (not rows[0] or rows[0][0] != 'ID'):      # ncu's ==PROF== preamble lines
+    rows.pop(0)
 hdr, units = rows[0], rows[1]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'lts__t_sector_hit_rate.pct',

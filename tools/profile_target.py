@@ -14,6 +14,28 @@ if what in ("k1", "k1s3"):
     for _ in range(4): env.test_lines(ta, tb, out=out)
     r = scenes.random_rays(s, 1 << 22)
     env.trace_rays(torch.from_numpy(r["o"]).cuda(), torch.from_numpy(r["d"]).cuda(), torch.from_numpy(r["tmax"]).cuda())
+elif what in ("r2k1", "r2k1s3"):
+    # round 2: sorted / unsorted / top-level-staged visibility kernels on the bench inputs, one launch each after a warm-up
+    big = what == "r2k1s3"
+    s = scenes.outdoor() if big else scenes.box_room(); env = environment_from_scene(s, with_patches=False)
+    n = 1 << (22 if big else 24)
+    a, b = scenes.shadow_segments(s, n, seed=0xC5 if big else 0xC0FFEE)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.empty(n // 32, dtype=torch.int32, device="cuda")
+    for sort, top in ((0, 0), (1, 0), (0, 1023)):
+        env.set_option("k1_sort", sort); env.set_option("k1_top", top)
+        for _ in range(2): env.test_lines(ta, tb, out=out)
+elif what == "r2k4":
+    # round 2: the multi-GPU gather kernel on the rank-3 slice of a simulated world-8 run, and the single-GPU kernel on the whole matrix
+    s = scenes.multi_room()
+    for world, rank in ((8, 3), (1, 0)):
+        env = environment_from_scene(s, rank=rank, world=world)
+        if world > 1: env.set_option("k4_sim_peers", 1)
+        env.set_option("k4_graph", 0)
+        env.build_transfers(s.pvs)
+        e0 = torch.full((s.n_patches, 3), 100.0, device="cuda"); o = torch.empty_like(e0)
+        env.bounce(e0, 6, out=o, want_added=False)
+        env.close()
 elif what == "sky":
     from vrad_b200.environment import Environment
     s = scenes.sky_room(); m = s.meta

@@ -66,7 +66,7 @@ def main():
     k1 = {}
     ref = None
     for sort in (0, 1):
-        for top in (0, 1023, 2047):
+        for top in (0, 1023):
             env.set_option("k1_sort", sort); env.set_option("k1_top", top)
             ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
             got = d_bits.cpu().numpy()
@@ -112,7 +112,7 @@ def main():
         k3 = {"stats": {k: (v if not hasattr(v, "tolist") else v.tolist()) for k, v in env.stats().items()}}
         ref = None
         for sort in (0, 1):
-            for top in (0, 1023, 2047):
+            for top in (0, 1023):
                 env.set_option("k1_sort", sort); env.set_option("k1_top", top)
                 ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
                 got = d_bits.cpu().numpy()
@@ -131,28 +131,42 @@ def main():
         emit0 = scenes.SplitMix64(0xE1).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
         d_emit = torch.from_numpy(emit0).to(dev); d_tot = torch.empty_like(d_emit)
         k4 = {}
-        for world, rank in ((1, 0), (8, 3), (8, 0), (2, 1)):
+        for world, rank in ((1, 0), (8, 3), (2, 1)):
             env = environment_from_scene(s2, rank=rank, world=world)
             env.set_stream(stream)
             if world > 1:
                 env.set_option("k4_sim_peers", 1)
             nnz = env.build_transfers(s2.pvs)
             row0, row1, _ = env.transfers_info()
+            if world == 1:
+                # row-length histogram of the C4 matrix (for DESIGN): from the row pointers of 8 sampled blocks
+                lens = []
+                for r0 in range(0, N, N // 8):
+                    rpb, _, _ = env.transfers_download_rows(r0, min(N, r0 + 2048), 1 << 23)
+                    lens.append(np.diff(rpb))
+                lens = np.concatenate(lens)
+                k4["row_length_sample"] = {"rows": int(lens.size), "mean": float(lens.mean()), "p50": float(np.percentile(lens, 50)), "p90": float(np.percentile(lens, 90)),
+                                           "p99": float(np.percentile(lens, 99)), "max": int(lens.max()), "min": int(lens.min()),
+                                           "frac_gt_2048": float((lens > 2048).mean()), "frac_gt_4096": float((lens > 4096).mean())}
+                print("row lengths", k4["row_length_sample"], flush=True)
             env.set_async(True)
             tag = f"world{world}_rank{rank}"
             k4[tag] = {"nnz_local": nnz, "rows": [row0, row1], "stream_us_at_peak": 8 * nnz / 6455.3e9 * 1e6}
-            sweeps = [(seg, lf, 1, 1) for seg in (512, 1024, 2048, 4096, 32768) for lf in (0, 1)]
+            # (block, persist, pdl, graph, sim)
+            sweeps = [(256, 1, 1, 1, 1), (192, 1, 1, 1, 1), (256, 0, 1, 1, 1), (192, 0, 1, 1, 1)]
             if world > 1:
-                sweeps += [(2048, 0, 0, 1), (2048, 0, 1, 0), (2048, 0, 0, 0), (1024, 0, 0, 0)]
+                sweeps += [(256, 1, 0, 1, 1), (192, 1, 0, 1, 1), (256, 1, 0, 0, 1), (256, 1, 1, 1, 2), (192, 1, 1, 1, 2)]
             else:
-                sweeps += [(2048, 0, 1, 0)]
-            for seg, lf, pdl, graph in sweeps:
-                env.set_option("k4_seg", seg); env.set_option("k4_long_first", lf)
+                sweeps += [(256, 1, 1, 0, 1)]
+            for blk, per, pdl, graph, sim in sweeps:
+                env.set_option("k4_block", blk); env.set_option("k4_persist", per)
                 env.set_option("k4_pdl", pdl); env.set_option("k4_graph", graph)
+                if world > 1:
+                    env.set_option("k4_sim_peers", sim)      # 2 = no barrier wait (timing diagnostic only)
                 ms = timed(lambda: env.bounce(d_emit, 100, out=d_tot, want_added=False), reps=3, warm=1)
                 us = ms * 10.0
-                k4[tag][f"seg{seg}_long{lf}_pdl{pdl}_graph{graph}"] = {"us_per_bounce": us, "gbs": (8 * nnz + 40 * (row1 - row0)) / us / 1e3}
-                print("K4", tag, seg, lf, pdl, graph, us, flush=True)
+                k4[tag][f"block{blk}_persist{per}_pdl{pdl}_graph{graph}_sim{sim}"] = {"us_per_bounce": us, "gbs": (8 * nnz + 40 * (row1 - row0)) / us / 1e3}
+                print("K4", tag, blk, per, pdl, graph, sim, us, flush=True)
             env.close()
             res["k4_s2"] = k4
             flush()

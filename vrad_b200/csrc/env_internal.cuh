@@ -85,11 +85,13 @@ struct TransfersDev {
     // Gather plan (K4): one warp per work item.  A row longer than `seg` entries is cut into parts of `seg` entries
     // (one item each) so that no warp carries a 30 us row into the tail of a 40 us kernel; the parts' sums meet in
     // part_sum[] and the part that arrives last (row_ctr) adds them in part order and runs the row's epilogue.
-    //   item int4 = {local row, first entry (relative to the row), entries | n_parts << 16, first part slot of the row}
+    //   item int4 = {local row, entries | n_parts << 16 | part index << 24, first entry (position in tr) lo, hi}
     DevBuf<int4>    items;
+    DevBuf<int32_t> item_slot;      // per item: first part slot of its row in part_sum (-1: the row is one item)
+    DevBuf<int32_t> block_ptr;      // n_blocks + 1 offsets into items: the items of each block of the gather grid
     DevBuf<float4>  part_sum;       // one slot per part of a split row
     DevBuf<int32_t> row_ctr;        // arrivals per local row (split rows only; the finisher resets it)
-    int n_items = 0, n_slots = 0, seg_shift = 11;
+    int n_items = 0, n_slots = 0, n_blocks = 0, seg_shift = 11, plan_warps = 8;
     int64_t plan_serial = 0;        // bumped by every re-plan (invalidates the captured bounce graph)
 };
 
@@ -154,6 +156,8 @@ struct EnvOptions {
     int k1_top = 0;        // VRAD_K1_TOP: stage the top levels of the kd tree in shared memory (0 = off, else node budget)
     int k4_seg = 2048;     // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
+    int k4_block = 256;    // VRAD_K4_BLOCK: threads per gather block: 256 (5 blocks/SM, 48 registers) or 192 (6 blocks/SM, 56 registers)
+    int k4_persist = 1;    // VRAD_K4_PERSIST: one gather block per resident slot over equal-work item ranges (0 = 8 items per block)
     int k4_pdl = 1;        // VRAD_K4_PDL: chain the bounces of the multi-GPU gather with programmatic dependent launch
     int k4_graph = 1;      // VRAD_K4_GRAPH: replay the bounce loop as a CUDA graph
     int k4_sim_peers = 0;  // VRAD_K4_SIM_PEERS: single-GPU stand-in for the peers of a multi-GPU handle (timing only)
@@ -246,6 +250,7 @@ int launch_test_lines(vrad_env* e, int64_t n, const float* start_soa, const floa
 int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, const int32_t* h_pairs, int sky_mode, uint32_t* d_bits);
 int launch_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs, int sky_mode, uint32_t* bits);
 int check_pairs_on_device(vrad_env* e, int64_t n, const int32_t* d_pairs, int* bad_out);
+int read_bad_index_count(vrad_env* e, int* bad_out);
 int upload_triangle_coverage(vrad_env* e);
 struct KdTree;
 int build_kd_tree_binned_device(cudaStream_t stream, const float* verts9, int n, KdTree& out, int* launches, const char** why);

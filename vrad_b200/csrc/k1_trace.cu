@@ -21,8 +21,14 @@ constexpr int kRaysPerWarp = 512;              // each warp streams a contiguous
 // the next descend/leaf round, so the warp does not idle on the longest ray of a fixed batch of 32
 // (ncu r01 v2: 6.2 threads per instruction with fixed batches; rays average 2.9 leaf visits but a
 // batch needs 9.3 rounds).  Results are per ray, so the order in which lanes pick rays is irrelevant.
-template <typename Fetch, typename Retire, bool ANY_HIT, bool TOP = false>
-__device__ __forceinline__ void stream_rays(const DevScene& S, int64_t base, int64_t end, int skip_id, Fetch fetch, Retire retire, const int2* top_s = nullptr) {
+// `more` (warp-uniform) is asked for another range of rays when the current one is used up and lanes are idle: a
+// warp whose supply comes in many small ranges (the sorted order hands them out through a global counter) never
+// drains -- its lanes go from the last rays of one range straight to the first rays of the next.
+struct NoMoreRays { __device__ __forceinline__ bool operator()(int64_t&, int64_t&) const { return false; } };
+
+template <typename Fetch, typename Retire, bool ANY_HIT, bool TOP = false, typename More = NoMoreRays>
+__device__ __forceinline__ void stream_rays(const DevScene& S, int64_t base, int64_t end, int skip_id, Fetch fetch, Retire retire, const int2* top_s = nullptr,
+                                            More more = More()) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     Traversal T;
@@ -31,9 +37,11 @@ __device__ __forceinline__ void stream_rays(const DevScene& S, int64_t base, int
     int64_t my_ray = -1;
     float my_len = 0.0f;
     int64_t next = base;
+    bool exhausted = false;
     for (;;) {
         if (my_ray >= 0 && !T.active) { retire(my_ray, T.hit_tri, T.hit_t, my_len); my_ray = -1; }
         const unsigned idle = __ballot_sync(0xffffffffu, my_ray < 0);
+        if (idle && next >= end && !exhausted) exhausted = !more(next, end);
         if (idle && next < end) {
             const int64_t idx = next + __popc(idle & lt_mask);
             if (my_ray < 0 && idx < end) {
@@ -45,7 +53,7 @@ __device__ __forceinline__ void stream_rays(const DevScene& S, int64_t base, int
             next += __popc(idle);
         }
         if (!__any_sync(0xffffffffu, T.active)) {
-            if (__all_sync(0xffffffffu, my_ray < 0) && next >= end) break;
+            if (__all_sync(0xffffffffu, my_ray < 0) && next >= end && exhausted) break;
             continue;                                               // only retirements / refills pending
         }
         const int2 nd = T.template descend<TOP>(S, st, top_s);
@@ -188,40 +196,46 @@ k1_sort_keys(int64_t n, SegSource src, SortGrid G, float4* __restrict__ rec, uin
     idx[i] = (uint32_t)i;
 }
 
-// traversal over the sorted order: position j of the order is segment perm[j]
+// traversal over the sorted order: position j of the order is segment perm[j].  Persistent warps draw ranges of
+// kSortedRange positions from a global counter: neighbouring positions cost alike (that is the point of the order), so
+// fixed per-warp chunks would leave the kernel waiting for the warps that drew the expensive corner of the scene
+// (r02, first form: 512-position chunks, S3 map, 2^22 segments: 7.2 ms sorted against 5.2 ms unsorted).
+constexpr int kSortedRange = 128;
 template <bool SKY, bool TOP>
 __global__ void __launch_bounds__(kTraceBlock, TOP ? 8 : 10)
-k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, const float4* __restrict__ rec, uint32_t* __restrict__ bits) {
+k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, const float4* __restrict__ rec, uint32_t* __restrict__ bits,
+                     unsigned long long* __restrict__ counter) {
     extern __shared__ int2 top_s[];
     if (TOP) {
         for (int i = threadIdx.x; i < S.n_top; i += blockDim.x) top_s[i] = __ldg(&S.top[i]);
         __syncthreads();
     }
-    const int64_t n_chunks = (n + kRaysPerWarp - 1) / kRaysPerWarp;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t chunk = warp0; chunk < n_chunks; chunk += nwarps) {
-        const int64_t base = chunk * kRaysPerWarp;
-        const int64_t end = base + kRaysPerWarp < n ? base + kRaysPerWarp : n;
-        // the lane's slot in `my_ray` carries the ORIGINAL segment number once fetched (negative ids never occur: n <= 2^31)
-        auto fetch = [&](int64_t& i, Ray& r, float& t0, float& t1, float& len) {
-            const uint32_t seg = __ldcs(&perm[i]);
-            const float4 q0 = __ldcs(&rec[2 * (int64_t)seg]), q1 = __ldcs(&rec[2 * (int64_t)seg + 1]);
-            i = seg;
-            t0 = 0.0f;
-            r = Ray{0.f, 0.f, 0.f, 1.f, 1.f, 1.f}; len = 0.0f;
-            const bool ok = segment_to_ray(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, len);
-            t1 = len;
-            return ok;
-        };
-        auto retire = [&](int64_t i, int tri, float t, float len) {
-            // occlusion rule of raytracer/trace/testline.go:42-51
-            bool occluded = tri != -1 && t < len;
-            if (SKY && occluded) occluded = (__float_as_int(__ldg(&S.q2[tri]).z) & 0x01000000) == 0;
-            if (!occluded) atomicOr(&bits[i >> 5], 1u << ((int)i & 31));
-        };
-        stream_rays<decltype(fetch), decltype(retire), !SKY, TOP>(S, base, end, -1, fetch, retire, top_s);
-    }
+    // the lane's slot in `my_ray` carries the ORIGINAL segment number once fetched
+    auto fetch = [&](int64_t& i, Ray& r, float& t0, float& t1, float& len) {
+        const uint32_t seg = __ldcs(&perm[i]);
+        const float4 q0 = __ldcs(&rec[2 * (int64_t)seg]), q1 = __ldcs(&rec[2 * (int64_t)seg + 1]);
+        i = seg;
+        t0 = 0.0f;
+        r = Ray{0.f, 0.f, 0.f, 1.f, 1.f, 1.f}; len = 0.0f;
+        const bool ok = segment_to_ray(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, len);
+        t1 = len;
+        return ok;
+    };
+    auto retire = [&](int64_t i, int tri, float t, float len) {
+        // occlusion rule of raytracer/trace/testline.go:42-51
+        bool occluded = tri != -1 && t < len;
+        if (SKY && occluded) occluded = (__float_as_int(__ldg(&S.q2[tri]).z) & 0x01000000) == 0;
+        if (!occluded) atomicOr(&bits[i >> 5], 1u << ((int)i & 31));
+    };
+    auto more = [&](int64_t& next, int64_t& end) {
+        unsigned long long c = 0;
+        if ((threadIdx.x & 31) == 0) c = atomicAdd(counter, (unsigned long long)kSortedRange);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if ((int64_t)c >= n) return false;
+        next = (int64_t)c; end = (int64_t)c + kSortedRange < n ? (int64_t)c + kSortedRange : n;
+        return true;
+    };
+    stream_rays<decltype(fetch), decltype(retire), !SKY, TOP, decltype(more)>(S, 0, 0, -1, fetch, retire, top_s, more);
 }
 
 // unsorted traversal of index pairs (the coordinate form's k1_test_lines with the endpoints fetched from the point table)
@@ -333,18 +347,22 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         SegSource sub = src;
         if (indexed) sub.pairs = src.pairs + c0; else { sub.a = src.a + c0; sub.b = src.b + c0; }
         uint32_t* out = bits + (c0 >> 5);
+        void* d_ctr;
+        if ((rc = scratch_get(e, 19, 8, &d_ctr))) return rc;
+        VRAD_CUDA_CHECK(cudaMemsetAsync(d_ctr, 0, 8, e->stream));
         VRAD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)((m + 31) >> 5) * 4, e->stream));
+        const int sgrid = (int)std::min<int64_t>((int64_t)e->sm_count * 10, (m + kSortedRange * kTraceWarps - 1) / (kSortedRange * kTraceWarps));
         const int kb = (int)((m + 255) / 256);
         if (indexed) k1_sort_keys<true><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
         else k1_sort_keys<false><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
         VRAD_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream));
         const size_t sm = (size_t)e->scene.n_top * sizeof(int2);
         if (sm) {
-            if (sky_mode) k1_test_lines_sorted<true, true><<<stream_grid(e, m), kTraceBlock, sm, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out);
-            else k1_test_lines_sorted<false, true><<<stream_grid(e, m), kTraceBlock, sm, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out);
+            if (sky_mode) k1_test_lines_sorted<true, true><<<sgrid, kTraceBlock, sm, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out, (unsigned long long*)d_ctr);
+            else k1_test_lines_sorted<false, true><<<sgrid, kTraceBlock, sm, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out, (unsigned long long*)d_ctr);
         } else {
-            if (sky_mode) k1_test_lines_sorted<true, false><<<stream_grid(e, m), kTraceBlock, 0, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out);
-            else k1_test_lines_sorted<false, false><<<stream_grid(e, m), kTraceBlock, 0, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out);
+            if (sky_mode) k1_test_lines_sorted<true, false><<<sgrid, kTraceBlock, 0, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out, (unsigned long long*)d_ctr);
+            else k1_test_lines_sorted<false, false><<<sgrid, kTraceBlock, 0, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out, (unsigned long long*)d_ctr);
         }
         *launches += 2 + 5;                    // keys + traversal + cub's histogram / onesweep passes (4 digit passes of 8 bits)
     }
@@ -369,15 +387,23 @@ __global__ void k1_count_bad_indices(int64_t n2, const int32_t* __restrict__ idx
     if (m && (threadIdx.x & 31) == 0) atomicAdd(bad, __popc(m));
 }
 
-// device-resident index pairs: count the indices outside the point table (synchronises the stream)
+// index pairs on the device: count the indices outside the point table (synchronises the stream)
 int check_pairs_on_device(vrad_env* e, int64_t n, const int32_t* d_pairs, int* bad_out) {
     void* d_bad;
     int rc = scratch_get(e, 18, 4, &d_bad);
     if (rc) return rc;
     VRAD_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, 4, e->stream));
     k1_count_bad_indices<<<(int)((2 * n + 255) / 256), 256, 0, e->stream>>>(2 * n, d_pairs, (int)e->n_points, (int*)d_bad);
+    return read_bad_index_count(e, bad_out);
+}
+
+int read_bad_index_count(vrad_env* e, int* bad_out) {
+    void* d_bad;
+    int rc = scratch_get(e, 18, 4, &d_bad);
+    if (rc) return rc;
     VRAD_CUDA_CHECK(cudaMemcpyAsync(bad_out, d_bad, 4, cudaMemcpyDeviceToHost, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    VRAD_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
@@ -400,6 +426,12 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
     constexpr int64_t kChunk = (int64_t)1 << 21;       // segments per chunk: 48 MiB of coordinates / 16 MiB of pairs, multiple of kRaysPerWarp
     for (int s = 0; s < 2; s++)
         if (e->d_stage[s].alloc((size_t)(h_pairs ? 2 : 6) * kChunk)) { set_error("out of device memory for staging"); return VRAD_E_NOMEM; }
+    void* d_bad = nullptr;
+    if (h_pairs) {
+        int rcb = scratch_get(e, 18, 4, &d_bad);
+        if (rcb) return rcb;
+        VRAD_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, 4, e->stream));
+    }
     timing_begin(e);
     int launches = 0;
     // the copy stream must not overwrite staging that earlier work on the main stream may still read
@@ -424,6 +456,7 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
         }
         VRAD_CUDA_CHECK(cudaEventRecord(e->ev_copied[s], e->copy_stream));
         VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_copied[s], 0));
+        if (h_pairs) { k1_count_bad_indices<<<(int)((2 * m + 255) / 256), 256, 0, e->stream>>>(2 * m, (const int32_t*)st, (int)e->n_points, (int*)d_bad); launches++; }
         int rc = enqueue_test_lines(e, m, src, sky_mode, d_bits + (c0 >> 5), &launches);
         if (rc) return rc;
         VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[s], e->stream));

@@ -87,6 +87,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
@@ -96,24 +101,38 @@ __device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
 // hanging the device.
 __device__ __noinline__ void wait_for_peers(const uint32_t* flags, int wait_world, uint32_t wait_rel) {
     if ((int)threadIdx.x < wait_world) {
-        const uint32_t epoch = ld_acquire_sys(flags + kFlagBase) + wait_rel;
+        // poll with relaxed loads -- an acquire per poll would drop this SM's L1 (CCTL.IVALL) under the blocks of the
+        // previous bounce that still gather on it (r02: the PDL chain was 4 us per bounce SLOWER with acquire polls)
+        const uint32_t epoch = ld_relaxed_sys(flags + kFlagBase) + wait_rel;
         const long long t0 = clock64();
-        while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
-            if (*(volatile const uint32_t*)(flags + kFlagError)) break;
+        while ((int32_t)(ld_relaxed_sys(flags + threadIdx.x) - epoch) < 0) {
+            if (ld_relaxed_sys(flags + kFlagError)) break;
             if (clock64() - t0 > (1LL << 30)) { atomicExch((unsigned int*)flags + kFlagError, 1u); break; }
         }
+        (void)ld_acquire_sys(flags + threadIdx.x);       // the acquire that orders the radiance loads after the arrival
     }
     __syncthreads();
 }
 
 // signal half: called by one thread per block after the block's bar.sync
+// An acquire fence makes the SM drop its L1 (CCTL.IVALL) -- paid per caller it wrecks the er[] gathers' L1 hit rate (r02:
+// with a full fence per split-row part, 1024-entry items ran at 445 us per bounce against 280 us).  So arrivals only
+// RELEASE (atom.release: prior writes ordered, nothing invalidated) and the single thread that finds itself last
+// acquires.
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __noinline__ void signal_if_last(const PeerTable* __restrict__ peers, uint32_t* flags, uint32_t signal_rel) {
-    __threadfence();
-    const unsigned int t = atomicAdd((unsigned int*)flags + kFlagTicket, 1u);
+    const unsigned int t = atom_add_release_gpu(flags + kFlagTicket, 1u);
     if (t == gridDim.x - 1) {
         flags[kFlagTicket] = 0u;
         const uint32_t epoch = flags[kFlagBase] + signal_rel;
-        __threadfence_system();
+        fence_acq_rel_sys();
         const int world = peers->world, rank = peers->rank;
         for (int p = 0; p < world; p++) st_relaxed_sys(peers->flags[p] + rank, epoch);
     }
@@ -134,12 +153,11 @@ __device__ __noinline__ bool combine_parts(float4* part_sum, int32_t* row_ctr, i
     int last = 0;
     if (lane == 0) {
         __stcg(&part_sum[slot0 + idx], make_float4(s0, s1, s2, 0.f));
-        __threadfence();
-        last = atomicAdd(&row_ctr[row], 1) == n_parts - 1;
+        last = atom_add_release_gpu((uint32_t*)&row_ctr[row], 1u) == (uint32_t)(n_parts - 1);
     }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return false;
-    __threadfence();
+    fence_acq_rel_gpu();
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int p = lane; p < n_parts; p += 32) {          // fixed order: lane-strided, then the xor tree
         const float4 v = __ldcg(&part_sum[slot0 + p]);
@@ -160,58 +178,110 @@ __device__ __forceinline__ float4 load_er(const float4* er, int col) {
     return __ldg(&er[col]);
 }
 
-template <bool MULTI>
-__global__ void __launch_bounds__(kGatherBlock, 5)
-k4_gather_items(int n_items, const int4* __restrict__ items, int seg_shift, int64_t row0, const int64_t* __restrict__ rowptr,
+// Blocks: block b owns the items [block_ptr[b], block_ptr[b+1]) and its warps take them one at a time through a
+// shared-memory counter.  Two plans (build_gather_plan): "dispatched" -- 8 consecutive items per block, as many blocks
+// as that takes, balanced by the hardware block scheduler -- and "persistent" -- exactly one block per resident slot
+// (5 per SM), the item list cut into contiguous ranges of equal work and each range ordered longest row first, so that
+// every slot runs the whole bounce, finishes within one short row of the others, and -- multi-GPU -- pays the
+// release + ticket once per bounce instead of once per 8 rows.
+//
+// A warp never idles between two items: an item descriptor is self-contained ({row, entries | parts | part index,
+// first entry as int64}: no row-pointer hop), the NEXT item is claimed while the current one streams and its
+// descriptor travels global -> shared memory by cp.async (no registers held across the loop), and the next item's
+// first {col,w} loads are issued BEFORE the current item's reduction and epilogue.  r02 ncu, single-GPU stand-in for
+// the 8-rank slice: an isolated bounce took 53 us for 195 MB where the steady rate of the same loop (5.5 TB/s) needs
+// 35 us -- the difference is start-up chains (claim -> item -> row pointer -> entries -> radiance, once per row per
+// warp) that nothing overlaps at the start and the end of a kernel that short.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// WARPS x blocks per SM: 8 x 5 = 40 resident warps at 48 registers, or 6 x 6 = 36 resident warps at 56 registers
+template <bool MULTI, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 5 : 6)
+k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ items, const int32_t* __restrict__ item_slot, int64_t row0,
                 const int2* __restrict__ tr, const float4* er, const float4* __restrict__ refl,
                 float4* er_next, float4* __restrict__ total, GatherAux A) {
+    __shared__ int next_item;
+    __shared__ int4 desc_s[WARPS], hold_s[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int w = blockIdx.x * kGatherWarps + warp;
     if (MULTI) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next bounce may be scheduled behind this one
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    int4 it = make_int4(0, 0, 0, -1);
-    int64_t k = 0, k1 = 0;
-    if (w < n_items) {
-        it = __ldg(&items[w]);
-        k = rowptr[it.x] + it.y;
-        k1 = k + (it.z & 0xffff);
-        k += lane;
-    }
-    const int2 zero = make_int2(0, 0);                          // out-of-item slots: col 0, weight 0
+    const int item_end = __ldg(&block_ptr[blockIdx.x + 1]);
+    if (threadIdx.x == 0) next_item = __ldg(&block_ptr[blockIdx.x]);
+    __syncthreads();
+    auto claim = [&]() { int c = 0; if (lane == 0) c = atomicAdd(&next_item, 1); return __shfl_sync(0xffffffffu, c, 0); };
+    const int2 zero = make_int2(0, 0);                              // out-of-item slots: col 0, weight 0
+    int w = claim();
+    int4 it = make_int4(0, 0, 0, 0);
+    if (w < item_end) it = __ldg(&items[w]);
     int2 cur[kGatherUnroll], nxt[kGatherUnroll];
+    {
+        const int2* p0 = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
+        const int l0 = it.y & 0xffff;
 #pragma unroll
-    for (int j = 0; j < kGatherUnroll; j++) cur[j] = k + 32 * j < k1 ? __ldcs(&tr[k + 32 * j]) : zero;
+        for (int j = 0; j < kGatherUnroll; j++) cur[j] = lane + 32 * j < l0 ? __ldcs(&p0[lane + 32 * j]) : zero;
+    }
+    int wn = w < item_end ? claim() : 0x7fffffff;
+    if (wn < item_end && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
     if (MULTI) {
-        // the radiance this bounce reads is complete once every rank's previous-bounce epoch has arrived
+        // the radiance this bounce reads is complete once every rank's previous-bounce epoch has arrived; every warp
+        // passes here exactly once, with its first {col,w} loads (which do not depend on the peers) in flight
         if (A.wait_rel) wait_for_peers(A.flags, A.wait_world, A.wait_rel);
     }
-    for (; k < k1; k += 32 * kGatherUnroll) {
+    bool has = w < item_end;
+    while (has) {
+        // warp-uniform bookkeeping sits in shared memory while the item streams: the loop below runs at the register
+        // limit that keeps 5 blocks per SM resident, and anything live across it is paid for in spills inside it
+        if (lane == 0) hold_s[warp] = make_int4(it.x, it.y, w, wn);
+        const int2* p = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
+        const int len = it.y & 0xffff;
+        int off = lane;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (; off < len; off += 32 * kGatherUnroll) {
 #pragma unroll
-        for (int j = 0; j < kGatherUnroll; j++)
-            nxt[j] = k + 32 * (kGatherUnroll + j) < k1 ? __ldcs(&tr[k + 32 * (kGatherUnroll + j)]) : zero;
-        float4 x[kGatherUnroll];
+            for (int j = 0; j < kGatherUnroll; j++)
+                nxt[j] = off + 32 * (kGatherUnroll + j) < len ? __ldcs(&p[off + 32 * (kGatherUnroll + j)]) : zero;
+            float4 x[kGatherUnroll];
 #pragma unroll
-        for (int j = 0; j < kGatherUnroll; j++) x[j] = load_er<MULTI>(er, cur[j].x);
+            for (int j = 0; j < kGatherUnroll; j++) x[j] = load_er<MULTI>(er, cur[j].x);
 #pragma unroll
-        for (int j = 0; j < kGatherUnroll; j++) {
-            const float wt = __int_as_float(cur[j].y);
-            s0 += wt * x[j].x; s1 += wt * x[j].y; s2 += wt * x[j].z;
+            for (int j = 0; j < kGatherUnroll; j++) {
+                const float wt = __int_as_float(cur[j].y);
+                s0 += wt * x[j].x; s1 += wt * x[j].y; s2 += wt * x[j].z;
+            }
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
         }
+        // hand over to the next item before finishing this one: its first loads run under the reduction and epilogue
+        __syncwarp();
+        const int4 hold = hold_s[warp];
+        const int row = hold.x, meta = hold.y, w_done = hold.z;
+        wn = hold.w;
+        const bool has_next = wn < __ldg(&block_ptr[blockIdx.x + 1]);
+        cp_async_wait_all();
+        __syncwarp();
+        it = desc_s[warp];                                          // stale when !has_next: no entries are read from it then
+        __syncwarp();                                               // every lane has its copy before the slots are refilled
+        {
+            const int2* pn = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
+            const int ln = has_next ? (it.y & 0xffff) : 0;
 #pragma unroll
-        for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
-    }
-    if (w < n_items) {
+            for (int j = 0; j < kGatherUnroll; j++) cur[j] = lane + 32 * j < ln ? __ldcs(&pn[lane + 32 * j]) : zero;
+        }
+        w = wn;
+        wn = has_next ? claim() : 0x7fffffff;
+        if (wn < __ldg(&block_ptr[blockIdx.x + 1]) && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, o);
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
-        const int n_parts = (int)((unsigned)it.z >> 16);
+        const int n_parts = (meta >> 16) & 0xff;
         bool fin = true;
-        if (n_parts > 1) fin = combine_parts(A.part_sum, A.row_ctr, it.x, it.w, it.y >> seg_shift, n_parts, s0, s1, s2);
+        if (n_parts > 1) fin = combine_parts(A.part_sum, A.row_ctr, row, __ldg(&item_slot[w_done]), (meta >> 24) & 0xff, n_parts, s0, s1, s2);
         if (fin) {
-            const int row = it.x;
             float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);                    // sky: emit = 0
             if (lane == 0) {
                 const float4 r = refl[row0 + row];
@@ -230,6 +300,7 @@ k4_gather_items(int n_items, const int4* __restrict__ items, int seg_shift, int6
             // (NVLink peer store; slot `rank` is the local buffer) -- no separate all-gather pass
             if (MULTI) store_row_to_peers(A.peers, A.next_buf, row0 + row, nv.x, nv.y, nv.z);
         }
+        has = has_next;
     }
     if (MULTI) {
         __syncthreads();
@@ -477,33 +548,75 @@ k4_collect_parents(int n_interior, int n_long, int long_blocks, const int32_t* _
 // vrad_build_transfers and vrad_transfers_upload once the rows are in place.
 int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     TransfersDev& T = e->transfers;
-    const int seg_env = e->opt.k4_seg;
     const bool long_first = e->opt.k4_long_first != 0;
+    int max_len = 0;
+    for (int64_t r = 0; r < nloc; r++) max_len = std::max(max_len, rowlen[r]);
     int shift = 8;
-    while ((1 << (shift + 1)) <= seg_env && shift < 15) shift++;
+    while ((1 << (shift + 1)) <= e->opt.k4_seg && shift < 15) shift++;
+    while (shift < 15 && ((int64_t)max_len + (1 << shift) - 1) >> shift > 255) shift++;      // at most 255 parts per row
     const int seg = 1 << shift;
+    if (((int64_t)max_len + seg - 1) / seg > 255) { set_error("a transfer row of %d entries needs more than 255 parts of %d", max_len, seg); return VRAD_E_UNSUPPORTED; }
+    // item = {local row, entries | n_parts << 16 | part index << 24, first entry (padded CSR position) lo, hi}; slot = first part slot of its row
     std::vector<int4> items;
-    items.reserve((size_t)nloc + 1024);
+    std::vector<int32_t> slots;
+    items.reserve((size_t)nloc + 1024); slots.reserve((size_t)nloc + 1024);
     int n_slots = 0;
+    int64_t pos = 0;                                       // rows start on 4-entry boundaries (vrad_transfers_upload / k2_fill)
     for (int64_t r = 0; r < nloc; r++) {
         const int len = rowlen[r];
         const int n_parts = len > seg ? (len + seg - 1) / seg : 1;
-        if (n_parts > 0xffff) { set_error("a transfer row of %d entries needs more than 65535 parts of %d", len, seg); return VRAD_E_UNSUPPORTED; }
-        if (n_parts == 1) { items.push_back(make_int4((int)r, 0, len | (1 << 16), -1)); continue; }
         for (int p = 0; p < n_parts; p++) {
-            const int off = p * seg, l = std::min(seg, len - off);
-            items.push_back(make_int4((int)r, off, l | (n_parts << 16), n_slots));
+            const int off = p * seg, l = n_parts == 1 ? len : std::min(seg, len - off);
+            const int64_t start = pos + off;
+            items.push_back(make_int4((int)r, l | (n_parts << 16) | (p << 24), (int)(uint32_t)(start & 0xffffffff), (int)(start >> 32)));
+            slots.push_back(n_parts > 1 ? n_slots : -1);
         }
-        n_slots += n_parts;
+        if (n_parts > 1) n_slots += n_parts;
+        pos += ((int64_t)len + 3) & ~(int64_t)3;
     }
-    if (long_first) std::stable_sort(items.begin(), items.end(), [](const int4& a, const int4& b) { return (a.z & 0xffff) > (b.z & 0xffff); });
-    if (T.items.alloc(items.size() + 1) || T.part_sum.alloc((size_t)n_slots + 1) || T.row_ctr.alloc((size_t)nloc + 1)) {
+    auto sort_desc = [&](int a, int b) {                   // stable, by entries, items and their slots together
+        std::vector<int> ord(b - a);
+        for (int i = 0; i < b - a; i++) ord[i] = a + i;
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return (items[x].y & 0xffff) > (items[y].y & 0xffff); });
+        std::vector<int4> ti(b - a); std::vector<int32_t> ts(b - a);
+        for (int i = 0; i < b - a; i++) { ti[i] = items[ord[i]]; ts[i] = slots[ord[i]]; }
+        std::copy(ti.begin(), ti.end(), items.begin() + a); std::copy(ts.begin(), ts.end(), slots.begin() + a);
+    };
+    if (long_first) sort_desc(0, (int)items.size());
+    // blocks of the gather grid
+    std::vector<int32_t> bp;
+    const int n_it = (int)items.size();
+    const int plan_warps = e->opt.k4_block == 192 ? 6 : 8;
+    const int n_resident = e->sm_count * (plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS>
+    if (e->opt.k4_persist && n_it > n_resident * plan_warps) {
+        // persistent plan: `slots` contiguous ranges of equal work (entries + a per-item constant), longest item first inside each
+        constexpr int64_t kItemCost = 96;                  // a row's fixed work (index loads, reduction, epilogue) in entry equivalents
+        int64_t total = 0;
+        for (const int4& it : items) total += (it.y & 0xffff) + kItemCost;
+        bp.assign(1, 0);
+        int64_t acc = 0;
+        for (int i = 0; i < n_it; i++) {
+            acc += (items[i].y & 0xffff) + kItemCost;
+            while ((int)bp.size() < n_resident && acc * n_resident >= total * (int64_t)bp.size()) bp.push_back(i + 1);
+        }
+        while ((int)bp.size() < n_resident) bp.push_back(n_it);
+        bp.push_back(n_it);
+        for (int b = 0; b < n_resident; b++) sort_desc(bp[b], bp[b + 1]);
+    } else {
+        for (int i = 0; i < n_it; i += plan_warps) bp.push_back(i);
+        if (bp.empty()) bp.push_back(0);
+        bp.push_back(n_it);
+    }
+    if (T.items.alloc(items.size() + 1) || T.item_slot.alloc(slots.size() + 1) || T.block_ptr.alloc(bp.size()) || T.part_sum.alloc((size_t)n_slots + 1) || T.row_ctr.alloc((size_t)nloc + 1)) {
         set_error("out of device memory for the gather plan"); return VRAD_E_NOMEM;
     }
     if (!items.empty()) VRAD_CUDA_CHECK(cudaMemcpyAsync(T.items.p, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
+    if (!slots.empty()) VRAD_CUDA_CHECK(cudaMemcpyAsync(T.item_slot.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(T.block_ptr.p, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaMemsetAsync(T.row_ctr.p, 0, ((size_t)nloc + 1) * 4, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    T.n_items = (int)items.size(); T.n_slots = n_slots; T.seg_shift = shift; T.plan_serial++;
+    T.n_blocks = (int)bp.size() - 1;
+    T.n_items = (int)items.size(); T.n_slots = n_slots; T.seg_shift = shift; T.plan_warps = plan_warps; T.plan_serial++;
     return 0;
 }
 
@@ -778,24 +891,28 @@ int vrad_transfers_download_rows(vrad_env* e, int64_t row_begin, int64_t row_end
 // previous bounce by PDL when `chained` (see k4_gather_items).
 static cudaError_t launch_gather_items(vrad_env* e, bool p2p, bool chained, int cur, bool want_add, uint32_t wait_rel, uint32_t signal_rel, float4* total_local) {
     TransfersDev& T = e->transfers;
-    const int nblocks = std::max(1, (T.n_items + kGatherWarps - 1) / kGatherWarps);
+    const int nblocks = T.n_blocks;
     GatherAux A{};
     A.add = want_add ? e->d_add.p : nullptr;
     A.part_sum = T.part_sum.p; A.row_ctr = T.row_ctr.p;
+    const bool w6 = T.plan_warps == 6;
     if (!p2p) {
-        k4_gather_items<false><<<nblocks, kGatherBlock, 0, e->stream>>>(T.n_items, T.items.p, T.seg_shift, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p,
-                                                                       e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
+        if (w6) k4_gather_items<false, 6><<<nblocks, 192, 0, e->stream>>>(T.block_ptr.p, T.items.p, T.item_slot.p, T.row0, T.tr.p, e->d_er[cur].p,
+                                                                         e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
+        else k4_gather_items<false, 8><<<nblocks, 256, 0, e->stream>>>(T.block_ptr.p, T.items.p, T.item_slot.p, T.row0, T.tr.p, e->d_er[cur].p,
+                                                                      e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
         return cudaGetLastError();
     }
     A.peers = e->peers.d_table.p; A.flags = e->peers.d_flags.p; A.next_buf = cur ^ 1;
-    A.wait_rel = wait_rel; A.signal_rel = signal_rel; A.wait_world = e->cfg.world;
+    A.wait_rel = e->opt.k4_sim_peers == 2 ? 0u : wait_rel;      // sim 2: no barrier wait (timing diagnostic)
+    A.signal_rel = signal_rel; A.wait_world = e->cfg.world;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(kGatherBlock); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
+    cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(w6 ? 192 : 256); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k4_gather_items<true>, T.n_items, (const int4*)T.items.p, T.seg_shift, T.row0, (const int64_t*)T.rowptr.p,
+    return cudaLaunchKernelEx(&cfg, w6 ? k4_gather_items<true, 6> : k4_gather_items<true, 8>, (const int32_t*)T.block_ptr.p, (const int4*)T.items.p, (const int32_t*)T.item_slot.p, T.row0,
                               (const int2*)T.tr.p, (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
 }
 

@@ -192,6 +192,8 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
     e->opt.k1_top = env_int("VRAD_K1_TOP", e->opt.k1_top);
     e->opt.k4_seg = env_int("VRAD_K4_SEG", e->opt.k4_seg);
     { const char* v = getenv("VRAD_K4_ORDER"); e->opt.k4_long_first = v && std::string(v) == "long"; }
+    e->opt.k4_persist = env_int("VRAD_K4_PERSIST", e->opt.k4_persist);
+    e->opt.k4_block = env_int("VRAD_K4_BLOCK", e->opt.k4_block);
     e->opt.k4_pdl = env_int("VRAD_K4_PDL", e->opt.k4_pdl);
     e->opt.k4_graph = env_int("VRAD_K4_GRAPH", e->opt.k4_graph);
     e->opt.k4_sim_peers = env_int("VRAD_K4_SIM_PEERS", e->opt.k4_sim_peers);
@@ -227,7 +229,7 @@ void vrad_env_destroy(vrad_env* e) {
     e->d_sky_dirs.release(); e->d_er[0].release(); e->d_er[1].release(); e->d_total.release(); e->d_partials.release(); e->d_add.release();
     if (e->bounce_graph.exec) cudaGraphExecDestroy(e->bounce_graph.exec);
     e->peers.d_sink.release();
-    e->transfers.items.release(); e->transfers.part_sum.release(); e->transfers.row_ctr.release();
+    e->transfers.items.release(); e->transfers.item_slot.release(); e->transfers.block_ptr.release(); e->transfers.part_sum.release(); e->transfers.row_ctr.release();
     for (int s = 0; s < 2; s++) {
         e->d_stage[s].release();
         if (e->ev_copied[s]) cudaEventDestroy(e->ev_copied[s]);
@@ -253,8 +255,8 @@ int vrad_env_set_option(vrad_env* e, const char* name, int value) {
     EnvOptions& o = e->opt;
     if (n == "k1_sort") o.k1_sort = value;
     else if (n == "k1_top") { o.k1_top = value; if (e->built) { VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device)); VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream)); return upload_top_levels(e); } }
-    else if (n == "k4_seg" || n == "k4_long_first") {
-        (n == "k4_seg" ? o.k4_seg : o.k4_long_first) = value;
+    else if (n == "k4_seg" || n == "k4_long_first" || n == "k4_persist" || n == "k4_block") {
+        (n == "k4_seg" ? o.k4_seg : (n == "k4_persist" ? o.k4_persist : (n == "k4_block" ? o.k4_block : o.k4_long_first))) = value;
         if (e->transfers.ready) {           // re-plan the resident rows
             VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
             const int64_t nloc = e->transfers.row1 - e->transfers.row0;
@@ -545,25 +547,20 @@ int vrad_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs2, int s
     const size_t b = (size_t)n * 8, wb = (size_t)((n + 31) / 32) * 4;
     int rc; bool hp, ho; void* d_o;
     const bool host_pairs = !is_device_ptr(pairs2);
-    // the indices are checked where they are: on the host for host buffers (before anything is enqueued), by a
-    // device pass for device buffers -- a bad index must be an error, not an out-of-bounds read in the kernel
-    if (host_pairs) {
-        const int64_t np = e->n_points;
-        int64_t bad = -1;
-#pragma omp parallel for reduction(max : bad) schedule(static)
-        for (int64_t i = 0; i < 2 * n; i++)
-            if (pairs2[i] < 0 || pairs2[i] >= np) bad = i > bad ? i : bad;
-        if (bad >= 0) { set_error("vrad_test_lines_indexed: segment %lld refers to point %d of %lld", (long long)(bad / 2), pairs2[bad], (long long)np); return VRAD_E_INVALID; }
-    }
+    // Indices are checked on the device, next to the traversal (which clamps them, so a bad index is never an
+    // out-of-bounds read): a host pass over the pairs would cost more than the PCIe copy it precedes.
     if ((rc = stage_out(e, 2, vis_bits, wb, &d_o, &ho))) return rc;
     if (host_pairs && n >= ((int64_t)1 << 22)) {
         if ((rc = launch_test_lines_pipelined(e, n, nullptr, nullptr, pairs2, sky_mode, (uint32_t*)d_o))) return rc;
         if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
-        return sync_if_needed(e, true);
+        int bad = 0;
+        if ((rc = read_bad_index_count(e, &bad))) return rc;         // synchronises
+        if (bad) { set_error("vrad_test_lines_indexed: %d indices outside the %lld-point table", bad, (long long)e->n_points); return VRAD_E_INVALID; }
+        return VRAD_OK;
     }
     const void* d_p;
     if ((rc = stage_in(e, 0, pairs2, b, &d_p, &hp))) return rc;
-    if (!host_pairs && !e->async) {          // async callers: the kernels clamp the indices (memory-safe), nothing is read back
+    if (host_pairs || !e->async) {           // async callers with device buffers: the kernels clamp the indices (memory-safe), nothing is read back
         int bad = 0;
         if ((rc = check_pairs_on_device(e, n, (const int32_t*)d_p, &bad))) return rc;
         if (bad) { set_error("vrad_test_lines_indexed: %d indices outside the %lld-point table", bad, (long long)e->n_points); return VRAD_E_INVALID; }
