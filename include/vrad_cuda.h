@@ -99,6 +99,9 @@ int  vrad_env_set_async(vrad_env*, int async);
  *   "k4_long_first" (VRAD_K4_ORDER=long) gather work items longest first
  *   "k4_persist"    (VRAD_K4_PERSIST)   gather grid = one block per resident slot over equal-work item ranges (default 1);
  *                                       0 = 8 items per block, as many blocks as that takes
+ *   "k4_pool"       (VRAD_K4_POOL)      percent of the gather work kept out of the persistent blocks' ranges, for whoever
+ *                                       finishes its range early (default 12)
+ *   "k4_items"      (VRAD_K4_ITEMS)     run the multi-GPU (work-item) gather kernel on a single-GPU handle too (default 0)
  *   "k4_block"      (VRAD_K4_BLOCK)     threads per gather block: 256 (5 blocks per SM) or 192 (6 per SM, more registers)
  *   "k4_pdl"        (VRAD_K4_PDL)       multi-GPU gather: chain the bounces by programmatic dependent launch (default 1)
  *   "k4_graph"      (VRAD_K4_GRAPH)     replay the bounce loop as a CUDA graph (default 1)

@@ -113,6 +113,8 @@ def test_gather_items_any_plan_same_light(seg, long_first, graph, block, persist
     env = environment_from_scene(scene)
     env.set_option("k4_seg", seg); env.set_option("k4_long_first", long_first); env.set_option("k4_graph", graph)
     env.set_option("k4_block", block); env.set_option("k4_persist", persist)
+    env.set_option("k4_items", 1)              # the multi-GPU (work-item) kernel on this one device: a one-rank peer table, exact results
+    env.set_option("k4_pool", 0 if seg == 512 else 12)
     nnz = env.build_transfers(scene.pvs)
     assert nnz == s2_small_oracle.build_transfers(scene.pvs, threads=8)
     N = scene.n_patches
@@ -143,7 +145,7 @@ def test_split_rows_actually_occur(s1_scene, s1_oracle):
     sel = slice(0, None, 2)
     args = (s1_scene.patch_origin[sel], s1_scene.patch_normal[sel], s1_scene.patch_plane_dist[sel], s1_scene.patch_area[sel], s1_scene.patch_refl[sel])
     env.patches_upload(*args)
-    env.set_option("k4_seg", 256)
+    env.set_option("k4_seg", 256); env.set_option("k4_items", 1)
     nnz = env.build_transfers()
     n = args[0].shape[0]
     assert nnz / n > 512                         # rows long enough that 256-entry items split them

@@ -65,20 +65,21 @@ def main():
     env.points_upload(pts)
     k1 = {}
     ref = None
-    for sort in (0, 1):
-        for top in (0, 1023):
-            env.set_option("k1_sort", sort); env.set_option("k1_top", top)
-            ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
-            got = d_bits.cpu().numpy()
-            if ref is None:
-                ref = got
-            k1[f"coords_sort{sort}_top{top}"] = {"ms": ms, "seg_per_s": n / ms * 1e3, "same_bits": bool(np.array_equal(got, ref))}
-            print("S1", sort, top, ms, flush=True)
+    for sort, key, top in ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0)):
+        env.set_option("k1_sort", sort); env.set_option("k1_top", top); env.set_option("k1_key", key)
+        ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
+        got = d_bits.cpu().numpy()
+        if ref is None:
+            ref = got
+        k1[f"coords_sort{sort}_key{key}_top{top}"] = {"ms": ms, "seg_per_s": n / ms * 1e3, "same_bits": bool(np.array_equal(got, ref))}
+        print("S1", sort, key, top, ms, flush=True)
     env.set_option("k1_top", 0)
-    for sort in (0, 1):
-        env.set_option("k1_sort", sort)
+    for sort, key in ((0, 0), (1, 0), (1, 1), (1, 2)):
+        env.set_option("k1_sort", sort); env.set_option("k1_key", key)
         ms = timed(lambda: env.test_lines_indexed(d_pairs, out=d_bits))
-        k1[f"indexed_sort{sort}"] = {"ms": ms, "seg_per_s": n / ms * 1e3, "same_bits": bool(np.array_equal(d_bits.cpu().numpy(), ref))}
+        k1[f"indexed_sort{sort}_key{key}"] = {"ms": ms, "seg_per_s": n / ms * 1e3, "same_bits": bool(np.array_equal(d_bits.cpu().numpy(), ref))}
+        print("S1 indexed", sort, key, ms, flush=True)
+    env.set_option("k1_key", 0)
     # host-buffer forms (e2e): pinned coordinates (24 B/segment) vs pinned index pairs (8 B/segment)
     env.set_async(False)
     h_a, h_b = PinnedArray((3, n), np.float32), PinnedArray((3, n), np.float32)
@@ -111,15 +112,14 @@ def main():
         d_bits = torch.empty(n3 // 32, dtype=torch.int32, device=dev)
         k3 = {"stats": {k: (v if not hasattr(v, "tolist") else v.tolist()) for k, v in env.stats().items()}}
         ref = None
-        for sort in (0, 1):
-            for top in (0, 1023):
-                env.set_option("k1_sort", sort); env.set_option("k1_top", top)
-                ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
-                got = d_bits.cpu().numpy()
-                if ref is None:
-                    ref = got
-                k3[f"sort{sort}_top{top}"] = {"ms": ms, "seg_per_s": n3 / ms * 1e3, "same_bits": bool(np.array_equal(got, ref))}
-                print("S3", sort, top, ms, flush=True)
+        for sort, key in ((0, 0), (1, 0), (1, 1), (1, 2)):
+            env.set_option("k1_sort", sort); env.set_option("k1_key", key)
+            ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
+            got = d_bits.cpu().numpy()
+            if ref is None:
+                ref = got
+            k3[f"sort{sort}_key{key}"] = {"ms": ms, "seg_per_s": n3 / ms * 1e3, "same_bits": bool(np.array_equal(got, ref))}
+            print("S3", sort, key, ms, flush=True)
         res["k1_s3"] = k3
         env.close(); del d_a, d_b, d_bits
         flush()
@@ -131,7 +131,7 @@ def main():
         emit0 = scenes.SplitMix64(0xE1).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
         d_emit = torch.from_numpy(emit0).to(dev); d_tot = torch.empty_like(d_emit)
         k4 = {}
-        for world, rank in ((1, 0), (8, 3), (2, 1)):
+        for world, rank in ((1, 0), (8, 3), (2, 1), (4, 0)):
             env = environment_from_scene(s2, rank=rank, world=world)
             env.set_stream(stream)
             if world > 1:
@@ -152,21 +152,21 @@ def main():
             env.set_async(True)
             tag = f"world{world}_rank{rank}"
             k4[tag] = {"nnz_local": nnz, "rows": [row0, row1], "stream_us_at_peak": 8 * nnz / 6455.3e9 * 1e6}
-            # (block, persist, pdl, graph, sim)
-            sweeps = [(256, 1, 1, 1, 1), (192, 1, 1, 1, 1), (256, 0, 1, 1, 1), (192, 0, 1, 1, 1)]
-            if world > 1:
-                sweeps += [(256, 1, 0, 1, 1), (192, 1, 0, 1, 1), (256, 1, 0, 0, 1), (256, 1, 1, 1, 2), (192, 1, 1, 1, 2)]
+            # (items kernel, block, persist, pool %, pdl, sim)
+            if world == 1:
+                sweeps = [(0, 192, 1, 12, 1, 0), (1, 192, 1, 12, 1, 0), (1, 192, 1, 0, 1, 0), (1, 192, 1, 25, 1, 0), (1, 192, 0, 0, 1, 0)]
             else:
-                sweeps += [(256, 1, 1, 0, 1)]
-            for blk, per, pdl, graph, sim in sweeps:
-                env.set_option("k4_block", blk); env.set_option("k4_persist", per)
-                env.set_option("k4_pdl", pdl); env.set_option("k4_graph", graph)
+                sweeps = [(1, 192, 1, 12, 1, 1), (1, 192, 1, 0, 1, 1), (1, 192, 1, 6, 1, 1), (1, 192, 1, 25, 1, 1), (1, 256, 1, 12, 1, 1),
+                          (1, 192, 1, 12, 0, 1), (1, 192, 0, 0, 1, 1), (1, 192, 1, 12, 1, 2)]
+            for items, blk, per, pool, pdl, sim in sweeps:
+                env.set_option("k4_items", items); env.set_option("k4_block", blk); env.set_option("k4_persist", per); env.set_option("k4_pool", pool)
+                env.set_option("k4_pdl", pdl)
                 if world > 1:
                     env.set_option("k4_sim_peers", sim)      # 2 = no barrier wait (timing diagnostic only)
                 ms = timed(lambda: env.bounce(d_emit, 100, out=d_tot, want_added=False), reps=3, warm=1)
                 us = ms * 10.0
-                k4[tag][f"block{blk}_persist{per}_pdl{pdl}_graph{graph}_sim{sim}"] = {"us_per_bounce": us, "gbs": (8 * nnz + 40 * (row1 - row0)) / us / 1e3}
-                print("K4", tag, blk, per, pdl, graph, sim, us, flush=True)
+                k4[tag][f"items{items}_block{blk}_persist{per}_pool{pool}_pdl{pdl}_sim{sim}"] = {"us_per_bounce": us, "gbs": (8 * nnz + 40 * (row1 - row0)) / us / 1e3}
+                print("K4", tag, items, blk, per, pool, pdl, sim, us, flush=True)
             env.close()
             res["k4_s2"] = k4
             flush()

@@ -167,7 +167,7 @@ int comm_setup_peers(vrad_env* e, size_t n_pad) {
     tbl.world = world; tbl.rank = rank;
     if (P.d_table.alloc(1)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
     VRAD_CUDA_CHECK(cudaMemcpy(P.d_table.p, &tbl, sizeof(tbl), cudaMemcpyHostToDevice));
-    P.ready = true; P.simulated = false; P.n_pad = n_pad;
+    P.ready = true; P.simulated = false; P.n_pad = n_pad; P.table_world = world;
     return 0;
 }
 

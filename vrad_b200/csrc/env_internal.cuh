@@ -91,7 +91,7 @@ struct TransfersDev {
     DevBuf<int32_t> block_ptr;      // n_blocks + 1 offsets into items: the items of each block of the gather grid
     DevBuf<float4>  part_sum;       // one slot per part of a split row
     DevBuf<int32_t> row_ctr;        // arrivals per local row (split rows only; the finisher resets it)
-    int n_items = 0, n_slots = 0, n_blocks = 0, seg_shift = 11, plan_warps = 8;
+    int n_items = 0, n_slots = 0, n_blocks = 0, seg_shift = 11, plan_warps = 8, pool_begin = 0;
     int64_t plan_serial = 0;        // bumped by every re-plan (invalidates the captured bounce graph)
 };
 
@@ -126,12 +126,14 @@ struct PeerTable;
 //   [0, kMaxWorld)      arrival words: word p = the last bounce epoch rank p has finished storing into this rank's buffers
 //   [kFlagBase]         epoch of the bounce before the first one of the current vrad_bounce call (written by the owner only)
 //   [kFlagTicket]       blocks of the running gather that have finished (the last one signals and resets it)
+//   [kFlagPool]         items of the common pool handed out in the running gather (reset by its last block)
 //   [kFlagError]        set when a wait gave up (a peer never signalled): the call returns VRAD_E_COMM instead of hanging
-constexpr int kFlagBase = kMaxWorld, kFlagTicket = kMaxWorld + 1, kFlagError = kMaxWorld + 2, kFlagWords = 2 * kMaxWorld;
+constexpr int kFlagBase = kMaxWorld, kFlagTicket = kMaxWorld + 1, kFlagError = kMaxWorld + 2, kFlagPool = kMaxWorld + 3, kFlagWords = 2 * kMaxWorld;
 struct PeerLinks {
     bool      ready = false;
     bool      simulated = false;             // VRAD_K4_SIM_PEERS: every "peer" is this device (single-GPU tuning of the N-rank slice)
     size_t    n_pad = 0;
+    int       table_world = 0;               // ranks in the peer table (== cfg.world, or 1 for a single-GPU handle run with k4_items)
     float4*   er[2][kMaxWorld] = {};
     uint32_t* flags[kMaxWorld] = {};
     void*     opened[3][kMaxWorld] = {};     // mappings to close
@@ -153,10 +155,13 @@ namespace vrad {
 // tuning switches of a handle (vrad_env_set_option); the environment variables of the same meaning give the defaults
 struct EnvOptions {
     int k1_sort = -1;      // VRAD_K1_SORT: order segment batches before tracing; -1 = batches of >= 65536 segments, 0 never, 1 always
+    int k1_key = 0;        // VRAD_K1_KEY: layout of the sort key (k1_trace.cu: 0 start-major Morton, 1 6-D Morton, 2 cubic start cells)
     int k1_top = 0;        // VRAD_K1_TOP: stage the top levels of the kd tree in shared memory (0 = off, else node budget)
     int k4_seg = 2048;     // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
-    int k4_block = 256;    // VRAD_K4_BLOCK: threads per gather block: 256 (5 blocks/SM, 48 registers) or 192 (6 blocks/SM, 56 registers)
+    int k4_block = 192;    // VRAD_K4_BLOCK: threads per work-item gather block: 192 (6 blocks/SM, 56 registers) or 256 (5 blocks/SM, 48 registers: spills in the loop)
+    int k4_pool = 12;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early
+    int k4_items = 0;      // VRAD_K4_ITEMS: run the multi-GPU (work-item) gather on a single-GPU handle too (a one-rank peer table)
     int k4_persist = 1;    // VRAD_K4_PERSIST: one gather block per resident slot over equal-work item ranges (0 = 8 items per block)
     int k4_pdl = 1;        // VRAD_K4_PDL: chain the bounces of the multi-GPU gather with programmatic dependent launch
     int k4_graph = 1;      // VRAD_K4_GRAPH: replay the bounce loop as a CUDA graph

@@ -8,6 +8,7 @@
 // (closest hit: 24 in + 8 out), 24.125 B/segment (visibility).
 #include "env_internal.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cmath>
 #include <cstdlib>
 
 namespace vrad {
@@ -158,7 +159,22 @@ __device__ __forceinline__ uint32_t cell_of(float x, float lo, float inv, int ce
     return (uint32_t)c;
 }
 
-struct SortGrid { float lo[3], inv32[3], inv16[3]; };
+// key layouts (EnvOptions::k1_key), all 30 bits:
+//   0  Morton(start cell, 32 per axis) | direction octant | Morton(end cell, 16 per axis)          -- start-major
+//   1  6-D Morton: bits of start x,y,z and end x,y,z interleaved, 5 per coordinate                  -- both ends refine together
+//   2  start cell on a grid of roughly CUBIC cells (up to 128 x 128 x 16, counts from the scene box) | octant | Morton(end, 8 per axis)
+struct SortGrid { float lo[3], inv32[3], inv16[3], invc[3], inv8[3]; int nc[3]; int mode; };
+__device__ __forceinline__ uint32_t spread6(uint32_t v) {        // 5 bits -> every 6th bit
+    v &= 0x1fu;
+    return (v & 1u) | ((v & 2u) << 5) | ((v & 4u) << 10) | ((v & 8u) << 15) | ((v & 16u) << 20);
+}
+__device__ __forceinline__ uint32_t spread2(uint32_t v) {        // 7 bits -> every 2nd bit
+    v &= 0x7fu;
+    v = (v | (v << 4)) & 0x0f0fu;
+    v = (v | (v << 2)) & 0x3333u;
+    v = (v | (v << 1)) & 0x5555u;
+    return v;
+}
 
 // segment i of a batch: coordinates (SoA blocks, stride) or a pair of indices into the resident point table
 struct SegSource {
@@ -185,14 +201,30 @@ k1_sort_keys(int64_t n, SegSource src, SortGrid G, float4* __restrict__ rec, uin
     if (i >= n) return;
     float ax, ay, az, bx, by, bz;
     load_segment<INDEXED>(src, i, ax, ay, az, bx, by, bz);
-    rec[2 * i] = make_float4(ax, ay, az, bx);
-    rec[2 * i + 1] = make_float4(by, bz, 0.f, 0.f);
-    const uint32_t mo = spread3(cell_of(ax, G.lo[0], G.inv32[0], 32)) | (spread3(cell_of(ay, G.lo[1], G.inv32[1], 32)) << 1) |
-                        (spread3(cell_of(az, G.lo[2], G.inv32[2], 32)) << 2);
-    const uint32_t me = spread3(cell_of(bx, G.lo[0], G.inv16[0], 16)) | (spread3(cell_of(by, G.lo[1], G.inv16[1], 16)) << 1) |
-                        (spread3(cell_of(bz, G.lo[2], G.inv16[2], 16)) << 2);
+    if (!INDEXED) {      // index pairs are small enough (8 B, one sector) to be fetched again through the order; coordinates get a 32-byte record
+        rec[2 * i] = make_float4(ax, ay, az, bx);
+        rec[2 * i + 1] = make_float4(by, bz, 0.f, 0.f);
+    }
     const uint32_t oct = (bx < ax ? 1u : 0u) | (by < ay ? 2u : 0u) | (bz < az ? 4u : 0u);
-    keys[i] = (mo << 15) | (oct << 12) | me;
+    uint32_t key;
+    if (G.mode == 1) {
+        key = (spread6(cell_of(ax, G.lo[0], G.inv32[0], 32)) << 5) | (spread6(cell_of(ay, G.lo[1], G.inv32[1], 32)) << 4) |
+              (spread6(cell_of(az, G.lo[2], G.inv32[2], 32)) << 3) | (spread6(cell_of(bx, G.lo[0], G.inv32[0], 32)) << 2) |
+              (spread6(cell_of(by, G.lo[1], G.inv32[1], 32)) << 1) | spread6(cell_of(bz, G.lo[2], G.inv32[2], 32));
+    } else if (G.mode == 2) {
+        const uint32_t cxy = spread2(cell_of(ax, G.lo[0], G.invc[0], G.nc[0])) | (spread2(cell_of(ay, G.lo[1], G.invc[1], G.nc[1])) << 1);
+        const uint32_t cz = cell_of(az, G.lo[2], G.invc[2], G.nc[2]);
+        const uint32_t me = spread3(cell_of(bx, G.lo[0], G.inv8[0], 8)) | (spread3(cell_of(by, G.lo[1], G.inv8[1], 8)) << 1) |
+                            (spread3(cell_of(bz, G.lo[2], G.inv8[2], 8)) << 2);
+        key = (((cxy << 4) | cz) << 12) | (oct << 9) | me;
+    } else {
+        const uint32_t mo = spread3(cell_of(ax, G.lo[0], G.inv32[0], 32)) | (spread3(cell_of(ay, G.lo[1], G.inv32[1], 32)) << 1) |
+                            (spread3(cell_of(az, G.lo[2], G.inv32[2], 32)) << 2);
+        const uint32_t me = spread3(cell_of(bx, G.lo[0], G.inv16[0], 16)) | (spread3(cell_of(by, G.lo[1], G.inv16[1], 16)) << 1) |
+                            (spread3(cell_of(bz, G.lo[2], G.inv16[2], 16)) << 2);
+        key = (mo << 15) | (oct << 12) | me;
+    }
+    keys[i] = key;
     idx[i] = (uint32_t)i;
 }
 
@@ -201,9 +233,9 @@ k1_sort_keys(int64_t n, SegSource src, SortGrid G, float4* __restrict__ rec, uin
 // fixed per-warp chunks would leave the kernel waiting for the warps that drew the expensive corner of the scene
 // (r02, first form: 512-position chunks, S3 map, 2^22 segments: 7.2 ms sorted against 5.2 ms unsorted).
 constexpr int kSortedRange = 128;
-template <bool SKY, bool TOP>
+template <bool SKY, bool TOP, bool INDEXED>
 __global__ void __launch_bounds__(kTraceBlock, TOP ? 8 : 10)
-k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, const float4* __restrict__ rec, uint32_t* __restrict__ bits,
+k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, const float4* __restrict__ rec, SegSource src, uint32_t* __restrict__ bits,
                      unsigned long long* __restrict__ counter) {
     extern __shared__ int2 top_s[];
     if (TOP) {
@@ -213,11 +245,16 @@ k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, c
     // the lane's slot in `my_ray` carries the ORIGINAL segment number once fetched
     auto fetch = [&](int64_t& i, Ray& r, float& t0, float& t1, float& len) {
         const uint32_t seg = __ldcs(&perm[i]);
-        const float4 q0 = __ldcs(&rec[2 * (int64_t)seg]), q1 = __ldcs(&rec[2 * (int64_t)seg + 1]);
+        float ax, ay, az, bx, by, bz;
+        if (INDEXED) load_segment<true>(src, (int64_t)seg, ax, ay, az, bx, by, bz);
+        else {
+            const float4 q0 = __ldcs(&rec[2 * (int64_t)seg]), q1 = __ldcs(&rec[2 * (int64_t)seg + 1]);
+            ax = q0.x; ay = q0.y; az = q0.z; bx = q0.w; by = q1.x; bz = q1.y;
+        }
         i = seg;
         t0 = 0.0f;
         r = Ray{0.f, 0.f, 0.f, 1.f, 1.f, 1.f}; len = 0.0f;
-        const bool ok = segment_to_ray(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, len);
+        const bool ok = segment_to_ray(ax, ay, az, bx, by, bz, r, len);
         t1 = len;
         return ok;
     };
@@ -304,11 +341,19 @@ static bool want_sort(const vrad_env* e, int64_t n) {
 
 static SortGrid sort_grid(const vrad_env* e) {
     SortGrid G;
+    G.mode = e->opt.k1_key;
+    double vol = 1.0;
+    for (int c = 0; c < 3; c++) vol *= std::max(1.0, (double)e->scene.bmax[c] - (double)e->scene.bmin[c]);
+    const double cell = std::cbrt(vol / 262144.0);           // edge of a cubic cell if 2^18 of them filled the box
+    const int cap[3] = {128, 128, 16};
     for (int c = 0; c < 3; c++) {
         const float w = e->scene.bmax[c] - e->scene.bmin[c];
         G.lo[c] = e->scene.bmin[c];
         G.inv32[c] = w > 0.0f ? 32.0f / w : 0.0f;
         G.inv16[c] = w > 0.0f ? 16.0f / w : 0.0f;
+        G.inv8[c] = w > 0.0f ? 8.0f / w : 0.0f;
+        G.nc[c] = std::min(cap[c], std::max(1, (int)std::lround(w / cell)));
+        G.invc[c] = w > 0.0f ? (float)G.nc[c] / w : 0.0f;
     }
     return G;
 }
@@ -339,7 +384,7 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         const int64_t m = std::min(kSortBatch, n - c0);
         void *d_rec, *d_k0, *d_k1, *d_i0, *d_i1, *d_tmp;
         int rc;
-        if ((rc = scratch_get(e, 12, (size_t)m * 32, &d_rec)) || (rc = scratch_get(e, 13, (size_t)m * 4, &d_k0)) || (rc = scratch_get(e, 14, (size_t)m * 4, &d_k1)) ||
+        if ((rc = scratch_get(e, 12, indexed ? 32 : (size_t)m * 32, &d_rec)) || (rc = scratch_get(e, 13, (size_t)m * 4, &d_k0)) || (rc = scratch_get(e, 14, (size_t)m * 4, &d_k1)) ||
             (rc = scratch_get(e, 15, (size_t)m * 4, &d_i0)) || (rc = scratch_get(e, 16, (size_t)m * 4, &d_i1))) return rc;
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream);
@@ -357,13 +402,16 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         else k1_sort_keys<false><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
         VRAD_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream));
         const size_t sm = (size_t)e->scene.n_top * sizeof(int2);
-        if (sm) {
-            if (sky_mode) k1_test_lines_sorted<true, true><<<sgrid, kTraceBlock, sm, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out, (unsigned long long*)d_ctr);
-            else k1_test_lines_sorted<false, true><<<sgrid, kTraceBlock, sm, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out, (unsigned long long*)d_ctr);
+        const uint32_t* pm = (const uint32_t*)d_i1; const float4* rc4 = (const float4*)d_rec; unsigned long long* ctr = (unsigned long long*)d_ctr;
+#define VRAD_SORTED(SKY, TOP, IDX) k1_test_lines_sorted<SKY, TOP, IDX><<<sgrid, kTraceBlock, (TOP) ? sm : 0, e->stream>>>(e->scene, m, pm, rc4, sub, out, ctr)
+        if (indexed) {
+            if (sm) { if (sky_mode) VRAD_SORTED(true, true, true); else VRAD_SORTED(false, true, true); }
+            else { if (sky_mode) VRAD_SORTED(true, false, true); else VRAD_SORTED(false, false, true); }
         } else {
-            if (sky_mode) k1_test_lines_sorted<true, false><<<sgrid, kTraceBlock, 0, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out, (unsigned long long*)d_ctr);
-            else k1_test_lines_sorted<false, false><<<sgrid, kTraceBlock, 0, e->stream>>>(e->scene, m, (const uint32_t*)d_i1, (const float4*)d_rec, out, (unsigned long long*)d_ctr);
+            if (sm) { if (sky_mode) VRAD_SORTED(true, true, false); else VRAD_SORTED(false, true, false); }
+            else { if (sky_mode) VRAD_SORTED(true, false, false); else VRAD_SORTED(false, false, false); }
         }
+#undef VRAD_SORTED
         *launches += 2 + 5;                    // keys + traversal + cub's histogram / onesweep passes (4 digit passes of 8 bits)
     }
     return 0;
@@ -423,9 +471,14 @@ int launch_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs, int 
 // h_a / h_b are host SoA blocks x[n] y[n] z[n] (coordinates), or h_pairs the host index pairs; d_bits is the
 // device result (n bits).
 int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, const int32_t* h_pairs, int sky_mode, uint32_t* d_bits) {
-    constexpr int64_t kChunk = (int64_t)1 << 21;       // segments per chunk: 48 MiB of coordinates / 16 MiB of pairs, multiple of kRaysPerWarp
+    // Chunks grow geometrically from 2^18 to 2^23 segments: the first copy is short (the traversal starts after 2 MB of
+    // pairs / 6 MB of coordinates instead of 16 / 48 MB) and the later launches are long enough that the per-launch tail
+    // (and, in sorted order, the per-batch sort) stops costing (r02: 8 equal chunks of 2^21 left the index-pair form at
+    // 5.06 ms per 2^24 segments with a 3.6 ms kernel and a 2.7 ms copy).
+    constexpr int64_t kChunkMin = (int64_t)1 << 18, kChunk = (int64_t)1 << 23;
+    const int64_t stage_cap = std::min<int64_t>(kChunk, std::max<int64_t>(kChunkMin, n));
     for (int s = 0; s < 2; s++)
-        if (e->d_stage[s].alloc((size_t)(h_pairs ? 2 : 6) * kChunk)) { set_error("out of device memory for staging"); return VRAD_E_NOMEM; }
+        if (e->d_stage[s].alloc((size_t)(h_pairs ? 2 : 6) * stage_cap)) { set_error("out of device memory for staging"); return VRAD_E_NOMEM; }
     void* d_bad = nullptr;
     if (h_pairs) {
         int rcb = scratch_get(e, 18, 4, &d_bad);
@@ -438,9 +491,13 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
     VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[0], e->stream));
     VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[1], e->stream));
     int c = 0;
-    for (int64_t c0 = 0; c0 < n; c0 += kChunk, c++) {
+    int64_t step = kChunkMin;
+    for (int64_t c0 = 0; c0 < n; c++) {
         const int s = c & 1;
-        const int64_t m = n - c0 < kChunk ? n - c0 : kChunk;
+        int64_t m = std::min(step, stage_cap);
+        if (n - c0 - m < kChunkMin) m = n - c0;            // no sliver at the end
+        m = std::min(m, std::min(n - c0, stage_cap));
+        step = std::min(step * 2, kChunk);
         float* st = e->d_stage[s].p;
         VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, e->ev_done[s], 0));
         SegSource src{};
@@ -449,10 +506,10 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
             src.pairs = (const int2*)st; src.pts = e->d_points.p; src.n_pts = (int)e->n_points;
         } else {
             for (int k = 0; k < 3; k++) {
-                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + k * kChunk, h_a + k * n + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
-                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + (3 + k) * kChunk, h_b + k * n + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
+                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + k * stage_cap, h_a + k * n + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
+                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + (3 + k) * stage_cap, h_b + k * n + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
             }
-            src.a = st; src.b = st + 3 * kChunk; src.stride = kChunk;
+            src.a = st; src.b = st + 3 * stage_cap; src.stride = stage_cap;
         }
         VRAD_CUDA_CHECK(cudaEventRecord(e->ev_copied[s], e->copy_stream));
         VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_copied[s], 0));
@@ -460,6 +517,7 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
         int rc = enqueue_test_lines(e, m, src, sky_mode, d_bits + (c0 >> 5), &launches);
         if (rc) return rc;
         VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[s], e->stream));
+        c0 += m;
     }
     timing_end(e, launches);
     VRAD_CUDA_CHECK(cudaGetLastError());

@@ -39,6 +39,83 @@ __global__ void k4_init_er(int n_pad, int n, const float* __restrict__ emit0, co
     er[i] = v;
 }
 
+// Single-GPU form: one warp per row, as many 8-row blocks as that takes, balanced by the hardware block scheduler.
+// (r02: on one GPU this plain form beats every persistent / work-item variant of the loop tried below -- 279 us per
+// bounce on the C4 matrix against 294-331 us -- the scheduler's dynamic balance is worth more than the start-up
+// bubbles it leaves; the work-item form pays off where a barrier follows every bounce, i.e. with several GPUs.)
+// Entries are {col, w} pairs -- the reference's Transfer struct
+// (common/types/transfer.go:3-6) -- read as one coalesced 64-bit load per lane with lanes on
+// CONSECUTIVE entries, so the 32 er[] gathers of one instruction hit consecutive patches wherever the
+// row has a run of adjacent columns (avg run length ~16 on the synthetic maps): few L1 wavefronts
+// per gather instead of one per lane (ncu r01: the int4-per-lane mapping was L1TEX-bound at 86%).
+// kGatherUnroll entries per lane are in flight and the {col,w} loads of the NEXT step are issued
+// before the current step's gathers (software pipeline), so the two dependent memory latencies
+// overlap.  The kernel is latency-bound: what matters is bytes in flight per SM = resident warps x
+// entries in flight, so the register budget is capped to keep 5 blocks (40 warps) per SM -- the
+// same loop at 60 registers (4 blocks) ran at 4.1 TB/s, at 48 registers 6.4 TB/s (tools/exp/k4_exp.cu).
+constexpr int kGatherUnroll = 8;
+
+__global__ void __launch_bounds__(kGatherBlock, 5)
+k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2* __restrict__ tr,
+          const float4* __restrict__ er, const float4* __restrict__ refl,
+          float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * kGatherWarps + warp;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    if (row < nloc) {
+        const int64_t k0 = rowptr[row], k1 = rowptr[row + 1];      // padded to 4 entries; padding has w = 0
+        const int2 zero = make_int2(0, 0);                          // out-of-row slots: col 0, weight 0
+        int2 cur[kGatherUnroll], nxt[kGatherUnroll];
+        int64_t k = k0 + lane;
+#pragma unroll
+        for (int j = 0; j < kGatherUnroll; j++) cur[j] = k + 32 * j < k1 ? __ldcs(&tr[k + 32 * j]) : zero;
+        for (; k < k1; k += 32 * kGatherUnroll) {
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++)
+                nxt[j] = k + 32 * (kGatherUnroll + j) < k1 ? __ldcs(&tr[k + 32 * (kGatherUnroll + j)]) : zero;
+            float4 x[kGatherUnroll];
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) {
+                const float w = __int_as_float(cur[j].y);
+                s0 += w * x[j].x; s1 += w * x[j].y; s2 += w * x[j].z;
+            }
+#pragma unroll
+            for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            const float4 r = refl[row0 + row];
+            if (r.w == 0.0f) {                                              // CollectLight, leaf patch
+                float4 t = total[row];
+                t.x += s0; t.y += s1; t.z += s2;
+                total[row] = t;
+                er_next[row0 + row] = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                e0 = s0; e1 = s1; e2 = s2;
+            } else {
+                er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);     // sky: emit = 0
+            }
+        }
+    }
+    // deterministic per-block partial of `added`
+    __shared__ float sm[kGatherWarps][3];
+    if (lane == 0) { sm[warp][0] = e0; sm[warp][1] = e1; sm[warp][2] = e2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < kGatherWarps; k++) a += sm[k][threadIdx.x];
+        partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // The gather.  One warp per WORK ITEM (TransfersDev::items): a whole row, or -- for a row longer than `seg`
 // entries -- one `seg`-entry part of it.  Entries are {col, w} pairs -- the reference's Transfer struct
@@ -69,7 +146,7 @@ __global__ void k4_init_er(int n_pad, int n, const float* __restrict__ emit0, co
 // Memory model: row stores -> bar.sync -> fence.acq_rel.gpu + ticket atomic (release, gpu scope) -> last block:
 // fence.acq_rel.sys -> st.relaxed.sys arrival words (release, sys scope) -> waiter: ld.acquire.sys -> bar.sync
 // -> plain (ld.global, not ld.global.nc) loads of er[].
-constexpr int kGatherUnroll = 8;
+
 
 struct GatherAux {                 // rarely used pointers, kept in the parameter bank (no registers until touched)
     float4* add;                   // light added per local row (written when non-null: last bounce / early-out)
@@ -80,6 +157,7 @@ struct GatherAux {                 // rarely used pointers, kept in the paramete
     int next_buf;
     uint32_t wait_rel, signal_rel; // epochs relative to flags[kFlagBase]; wait_rel 0 = nothing to wait for
     int wait_world;
+    int pool_begin, n_items;       // items [pool_begin, n_items) belong to no block: whoever runs dry takes them one by one (flags[kFlagPool])
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -131,6 +209,7 @@ __device__ __noinline__ void signal_if_last(const PeerTable* __restrict__ peers,
     const unsigned int t = atom_add_release_gpu(flags + kFlagTicket, 1u);
     if (t == gridDim.x - 1) {
         flags[kFlagTicket] = 0u;
+        flags[kFlagPool] = 0u;
         const uint32_t epoch = flags[kFlagBase] + signal_rel;
         fence_acq_rel_sys();
         const int world = peers->world, rank = peers->rank;
@@ -192,6 +271,7 @@ __device__ __forceinline__ float4 load_er(const float4* er, int col) {
 // the 8-rank slice: an isolated bounce took 53 us for 195 MB where the steady rate of the same loop (5.5 TB/s) needs
 // 35 us -- the difference is start-up chains (claim -> item -> row pointer -> entries -> radiance, once per row per
 // warp) that nothing overlaps at the start and the end of a kernel that short.
+constexpr int kNoItem = 0x7fffffff;
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -207,14 +287,29 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
     __shared__ int4 desc_s[WARPS], hold_s[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (MULTI) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next bounce may be scheduled behind this one
-    const int item_end = __ldg(&block_ptr[blockIdx.x + 1]);
     if (threadIdx.x == 0) next_item = __ldg(&block_ptr[blockIdx.x]);
     __syncthreads();
-    auto claim = [&]() { int c = 0; if (lane == 0) c = atomicAdd(&next_item, 1); return __shfl_sync(0xffffffffu, c, 0); };
+    // next item of this block's range; when the range is used up, of the common pool (global counter) -- equal work is
+    // not equal time (cache hit rates and DRAM conflicts differ from range to range), and with a barrier behind every
+    // bounce the slots that finish early would otherwise idle until the slowest range is done
+    auto claim = [&]() {
+        int c = kNoItem;
+        if (lane == 0) {
+            c = atomicAdd(&next_item, 1);
+            if (c >= __ldg(&block_ptr[blockIdx.x + 1])) {
+                c = kNoItem;
+                if (MULTI && A.pool_begin < A.n_items) {
+                    const int q = A.pool_begin + (int)atomicAdd((unsigned int*)A.flags + kFlagPool, 1u);
+                    if (q < A.n_items) c = q;
+                }
+            }
+        }
+        return __shfl_sync(0xffffffffu, c, 0);
+    };
     const int2 zero = make_int2(0, 0);                              // out-of-item slots: col 0, weight 0
     int w = claim();
     int4 it = make_int4(0, 0, 0, 0);
-    if (w < item_end) it = __ldg(&items[w]);
+    if (w != kNoItem) it = __ldg(&items[w]);
     int2 cur[kGatherUnroll], nxt[kGatherUnroll];
     {
         const int2* p0 = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
@@ -222,14 +317,14 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
 #pragma unroll
         for (int j = 0; j < kGatherUnroll; j++) cur[j] = lane + 32 * j < l0 ? __ldcs(&p0[lane + 32 * j]) : zero;
     }
-    int wn = w < item_end ? claim() : 0x7fffffff;
-    if (wn < item_end && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
+    int wn = w != kNoItem ? claim() : kNoItem;
+    if (wn != kNoItem && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
     if (MULTI) {
         // the radiance this bounce reads is complete once every rank's previous-bounce epoch has arrived; every warp
         // passes here exactly once, with its first {col,w} loads (which do not depend on the peers) in flight
         if (A.wait_rel) wait_for_peers(A.flags, A.wait_world, A.wait_rel);
     }
-    bool has = w < item_end;
+    bool has = w != kNoItem;
     while (has) {
         // warp-uniform bookkeeping sits in shared memory while the item streams: the loop below runs at the register
         // limit that keeps 5 blocks per SM resident, and anything live across it is paid for in spills inside it
@@ -258,7 +353,7 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
         const int4 hold = hold_s[warp];
         const int row = hold.x, meta = hold.y, w_done = hold.z;
         wn = hold.w;
-        const bool has_next = wn < __ldg(&block_ptr[blockIdx.x + 1]);
+        const bool has_next = wn != kNoItem;
         cp_async_wait_all();
         __syncwarp();
         it = desc_s[warp];                                          // stale when !has_next: no entries are read from it then
@@ -270,8 +365,8 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
             for (int j = 0; j < kGatherUnroll; j++) cur[j] = lane + 32 * j < ln ? __ldcs(&pn[lane + 32 * j]) : zero;
         }
         w = wn;
-        wn = has_next ? claim() : 0x7fffffff;
-        if (wn < __ldg(&block_ptr[blockIdx.x + 1]) && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
+        wn = has_next ? claim() : kNoItem;
+        if (wn != kNoItem && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -586,22 +681,28 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     // blocks of the gather grid
     std::vector<int32_t> bp;
     const int n_it = (int)items.size();
+    int pool_begin = n_it;
     const int plan_warps = e->opt.k4_block == 192 ? 6 : 8;
     const int n_resident = e->sm_count * (plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS>
     if (e->opt.k4_persist && n_it > n_resident * plan_warps) {
         // persistent plan: `slots` contiguous ranges of equal work (entries + a per-item constant), longest item first inside each
         constexpr int64_t kItemCost = 96;                  // a row's fixed work (index loads, reduction, epilogue) in entry equivalents
+        int64_t all = 0;
+        for (const int4& it : items) all += (it.y & 0xffff) + kItemCost;
+        // the tail of the list is the common pool: items no range owns
+        const int pool_pct = std::min(std::max(e->opt.k4_pool, 0), 50);
         int64_t total = 0;
-        for (const int4& it : items) total += (it.y & 0xffff) + kItemCost;
+        for (pool_begin = 0; pool_begin < n_it && total * 100 < all * (100 - pool_pct); pool_begin++) total += (items[pool_begin].y & 0xffff) + kItemCost;
         bp.assign(1, 0);
         int64_t acc = 0;
-        for (int i = 0; i < n_it; i++) {
+        for (int i = 0; i < pool_begin; i++) {
             acc += (items[i].y & 0xffff) + kItemCost;
             while ((int)bp.size() < n_resident && acc * n_resident >= total * (int64_t)bp.size()) bp.push_back(i + 1);
         }
-        while ((int)bp.size() < n_resident) bp.push_back(n_it);
-        bp.push_back(n_it);
+        while ((int)bp.size() < n_resident) bp.push_back(pool_begin);
+        bp.push_back(pool_begin);
         for (int b = 0; b < n_resident; b++) sort_desc(bp[b], bp[b + 1]);
+        sort_desc(pool_begin, n_it);
     } else {
         for (int i = 0; i < n_it; i += plan_warps) bp.push_back(i);
         if (bp.empty()) bp.push_back(0);
@@ -616,7 +717,7 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     VRAD_CUDA_CHECK(cudaMemsetAsync(T.row_ctr.p, 0, ((size_t)nloc + 1) * 4, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     T.n_blocks = (int)bp.size() - 1;
-    T.n_items = (int)items.size(); T.n_slots = n_slots; T.seg_shift = shift; T.plan_warps = plan_warps; T.plan_serial++;
+    T.n_items = (int)items.size(); T.n_slots = n_slots; T.seg_shift = shift; T.plan_warps = plan_warps; T.pool_begin = pool_begin; T.plan_serial++;
     return 0;
 }
 
@@ -887,25 +988,26 @@ int vrad_transfers_download_rows(vrad_env* e, int64_t row_begin, int64_t row_end
     return VRAD_OK;
 }
 
-// One bounce of the flat (non-hierarchical) gather: a single launch.  p2p: the multi-GPU form, chained to the
-// previous bounce by PDL when `chained` (see k4_gather_items).
-static cudaError_t launch_gather_items(vrad_env* e, bool p2p, bool chained, int cur, bool want_add, uint32_t wait_rel, uint32_t signal_rel, float4* total_local) {
+// One bounce of the flat (non-hierarchical) gather: a single launch.  p2p: the work-item form with the fused exchange and
+// the in-kernel barrier, chained to the previous bounce by PDL when `chained`; otherwise the plain warp-per-row kernel.
+static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, bool want_add, uint32_t wait_rel, uint32_t signal_rel, float4* total_local) {
     TransfersDev& T = e->transfers;
+    if (!p2p) {
+        const int nloc = (int)(T.row1 - T.row0);
+        const int nblocks = std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
+        k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
+                                                         e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
+        return cudaGetLastError();
+    }
     const int nblocks = T.n_blocks;
     GatherAux A{};
     A.add = want_add ? e->d_add.p : nullptr;
     A.part_sum = T.part_sum.p; A.row_ctr = T.row_ctr.p;
+    A.pool_begin = T.pool_begin; A.n_items = T.n_items;
     const bool w6 = T.plan_warps == 6;
-    if (!p2p) {
-        if (w6) k4_gather_items<false, 6><<<nblocks, 192, 0, e->stream>>>(T.block_ptr.p, T.items.p, T.item_slot.p, T.row0, T.tr.p, e->d_er[cur].p,
-                                                                         e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
-        else k4_gather_items<false, 8><<<nblocks, 256, 0, e->stream>>>(T.block_ptr.p, T.items.p, T.item_slot.p, T.row0, T.tr.p, e->d_er[cur].p,
-                                                                      e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
-        return cudaGetLastError();
-    }
     A.peers = e->peers.d_table.p; A.flags = e->peers.d_flags.p; A.next_buf = cur ^ 1;
     A.wait_rel = e->opt.k4_sim_peers == 2 ? 0u : wait_rel;      // sim 2: no barrier wait (timing diagnostic)
-    A.signal_rel = signal_rel; A.wait_world = e->cfg.world;
+    A.signal_rel = signal_rel; A.wait_world = e->peers.table_world;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(w6 ? 192 : 256); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
     cudaLaunchAttribute attr[1];
@@ -923,7 +1025,7 @@ static cudaError_t launch_gather_items(vrad_env* e, bool p2p, bool chained, int 
 static int setup_simulated_peers(vrad_env* e, size_t n_pad) {
     PeerLinks& P = e->peers;
     if (P.ready && P.simulated && P.n_pad == n_pad) return 0;
-    const int world = e->cfg.world, rank = e->cfg.rank;
+    const int world = e->cfg.world, rank = e->cfg.rank;      // world 1 (k4_items): a one-rank table, every row is this rank's -- results are exact
     if (P.d_flags.alloc(kFlagWords) || P.d_sink.alloc(n_pad) || P.d_table.alloc(1)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
     VRAD_CUDA_CHECK(cudaMemsetAsync(P.d_flags.p, 0, kFlagWords * sizeof(uint32_t), e->stream));
     PeerTable tbl{};
@@ -935,7 +1037,7 @@ static int setup_simulated_peers(vrad_env* e, size_t n_pad) {
     tbl.world = world; tbl.rank = rank;
     VRAD_CUDA_CHECK(cudaMemcpyAsync(P.d_table.p, &tbl, sizeof(tbl), cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    P.ready = true; P.simulated = true; P.n_pad = n_pad;
+    P.ready = true; P.simulated = true; P.n_pad = n_pad; P.table_world = world;
     return 0;
 }
 
@@ -944,7 +1046,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     if (!e || !emit0_rgb || n_bounces < 0) { set_error("vrad_bounce: bad arguments"); return VRAD_E_INVALID; }
     TransfersDev& T = e->transfers;
     if (!T.ready) { set_error("vrad_bounce: no transfers resident (vrad_build_transfers / vrad_transfers_upload first)"); return VRAD_E_STATE; }
-    const bool sim = e->opt.k4_sim_peers && e->cfg.world > 1 && !e->nccl_comm;
+    const bool sim = (e->opt.k4_sim_peers && e->cfg.world > 1 && !e->nccl_comm) || (e->opt.k4_items && e->cfg.world == 1);
     if (e->cfg.world > 1 && !e->nccl_comm && !sim) { set_error("vrad_bounce: world=%d but vrad_comm_init was not called", e->cfg.world); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     const int64_t N = e->patches.n;
@@ -979,10 +1081,10 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     const bool hier = PD.hier && PD.n_interior > 0;
     const int collect_long_blocks = (PD.n_collect_long + 7) / 8;
     const int collect_blocks = collect_long_blocks + (PD.n_interior - PD.n_collect_long + 31) / 32;
-    if (sim) { if ((rc = setup_simulated_peers(e, (size_t)n_pad))) return rc; }
+    if (sim && !hier && !e->patches.bump) { if ((rc = setup_simulated_peers(e, (size_t)n_pad))) return rc; }
     else if (world > 1 && !hier && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
-    const bool p2p = world > 1 && !hier && e->peers.ready;
-    if (sim && !p2p) { set_error("vrad_bounce: VRAD_K4_SIM_PEERS does not cover the patch hierarchy"); return VRAD_E_UNSUPPORTED; }
+    const bool p2p = (world > 1 || sim) && !hier && !e->patches.bump && e->peers.ready;
+    if (sim && world > 1 && !p2p) { set_error("vrad_bounce: VRAD_K4_SIM_PEERS does not cover the patch hierarchy"); return VRAD_E_UNSUPPORTED; }
     // short-row form: chosen by the average row length of the rows that gather (env VRAD_K4_SHORT=0/1 forces it)
     int n_short = nloc;
     const int32_t* d_rows = nullptr;
@@ -1058,7 +1160,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
             int c = 0;
             for (int b = 0; b < n_bounces && ce == cudaSuccess; b++) {
-                ce = launch_gather_items(e, p2p, p2p && use_pdl && b > 0, c, b + 1 == n_bounces, p2p ? (uint32_t)b : 0u, (uint32_t)b + 1u, total_local);
+                ce = launch_gather(e, p2p, p2p && use_pdl && b > 0, c, b + 1 == n_bounces, p2p ? (uint32_t)b : 0u, (uint32_t)b + 1u, total_local);
                 c ^= 1;
             }
             cudaGraph_t g = nullptr;
@@ -1079,9 +1181,11 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             VRAD_CUDA_CHECK(cudaGraphLaunch(G.exec, e->stream));
             launches += n_bounces;
             done = n_bounces; cur = n_bounces & 1;
-            k4_sum_added_rows<<<add_blocks, 256, 0, e->stream>>>(nloc, e->d_add.p, e->d_partials.p);
-            k4_reduce_added<<<1, 256, 0, e->stream>>>(add_blocks, e->d_partials.p, d_added);
-            launches += 2;
+            if (p2p) {
+                k4_sum_added_rows<<<add_blocks, 256, 0, e->stream>>>(nloc, e->d_add.p, e->d_partials.p);
+                k4_reduce_added<<<1, 256, 0, e->stream>>>(add_blocks, e->d_partials.p, d_added);
+                launches += 2;
+            } else { k4_reduce_added<<<1, 256, 0, e->stream>>>(nblocks, e->d_partials.p, d_added); launches++; }
             if (world > 1 && !sim && (rc = comm_allreduce3(e, d_added))) return rc;
         }
     }
@@ -1101,7 +1205,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
 #undef VRAD_SHORT
         } else {
             // p2p: bounce b waits for every rank's epoch base+b (bounce 0 reads locally initialised radiance) and signals base+b+1
-            VRAD_CUDA_CHECK(launch_gather_items(e, p2p, p2p && use_pdl && b > 0 && !probe, cur, early_out || last, p2p ? (uint32_t)b : 0u, (uint32_t)b + 1u, total_local));
+            VRAD_CUDA_CHECK(launch_gather(e, p2p, p2p && use_pdl && b > 0 && !probe, cur, early_out || last, p2p ? (uint32_t)b : 0u, (uint32_t)b + 1u, total_local));
         }
         launches++;
         if (bump && PD.n_bump_rows > 0) {       // same emitters as the gather above (er[cur]), bump-mapped rows only
@@ -1119,7 +1223,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
         cur ^= 1; done++;
         if (early_out || last) {
-            if (use_short) { k4_reduce_added<<<1, 256, 0, e->stream>>>(short_blocks, e->d_partials.p, d_added); launches++; }
+            if (use_short || !p2p) { k4_reduce_added<<<1, 256, 0, e->stream>>>(use_short ? short_blocks : nblocks, e->d_partials.p, d_added); launches++; }
             else {
                 k4_sum_added_rows<<<add_blocks, 256, 0, e->stream>>>(nloc, e->d_add.p, e->d_partials.p);
                 k4_reduce_added<<<1, 256, 0, e->stream>>>(add_blocks, e->d_partials.p, d_added);
@@ -1133,7 +1237,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             if (h_added[0] < 1.0f && h_added[1] < 1.0f && h_added[2] < 1.0f) break;
         }
     }
-    if (p2p && done > 0) { k4_peer_wait<<<1, 32, 0, e->stream>>>(e->peers.d_flags.p, world, (uint32_t)done); launches++; }
+    if (p2p && done > 0) { k4_peer_wait<<<1, 32, 0, e->stream>>>(e->peers.d_flags.p, e->peers.table_world, (uint32_t)done); launches++; }
     if (world > 1 && !sim && (rc = comm_allgather_rows(e, e->d_total.p, bounds))) return rc;
     if (hier) {         // totallight of the interior patches, from the leaves' totals
         k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_total.p);

@@ -190,10 +190,13 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     e->opt.k1_sort = env_int("VRAD_K1_SORT", e->opt.k1_sort);
     e->opt.k1_top = env_int("VRAD_K1_TOP", e->opt.k1_top);
+    e->opt.k1_key = env_int("VRAD_K1_KEY", e->opt.k1_key);
     e->opt.k4_seg = env_int("VRAD_K4_SEG", e->opt.k4_seg);
     { const char* v = getenv("VRAD_K4_ORDER"); e->opt.k4_long_first = v && std::string(v) == "long"; }
     e->opt.k4_persist = env_int("VRAD_K4_PERSIST", e->opt.k4_persist);
     e->opt.k4_block = env_int("VRAD_K4_BLOCK", e->opt.k4_block);
+    e->opt.k4_pool = env_int("VRAD_K4_POOL", e->opt.k4_pool);
+    e->opt.k4_items = env_int("VRAD_K4_ITEMS", e->opt.k4_items);
     e->opt.k4_pdl = env_int("VRAD_K4_PDL", e->opt.k4_pdl);
     e->opt.k4_graph = env_int("VRAD_K4_GRAPH", e->opt.k4_graph);
     e->opt.k4_sim_peers = env_int("VRAD_K4_SIM_PEERS", e->opt.k4_sim_peers);
@@ -254,9 +257,11 @@ int vrad_env_set_option(vrad_env* e, const char* name, int value) {
     const std::string n(name);
     EnvOptions& o = e->opt;
     if (n == "k1_sort") o.k1_sort = value;
+    else if (n == "k1_key") o.k1_key = value;
     else if (n == "k1_top") { o.k1_top = value; if (e->built) { VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device)); VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream)); return upload_top_levels(e); } }
-    else if (n == "k4_seg" || n == "k4_long_first" || n == "k4_persist" || n == "k4_block") {
-        (n == "k4_seg" ? o.k4_seg : (n == "k4_persist" ? o.k4_persist : (n == "k4_block" ? o.k4_block : o.k4_long_first))) = value;
+    else if (n == "k4_items") o.k4_items = value;
+    else if (n == "k4_seg" || n == "k4_long_first" || n == "k4_persist" || n == "k4_block" || n == "k4_pool") {
+        (n == "k4_seg" ? o.k4_seg : (n == "k4_persist" ? o.k4_persist : (n == "k4_block" ? o.k4_block : (n == "k4_pool" ? o.k4_pool : o.k4_long_first)))) = value;
         if (e->transfers.ready) {           // re-plan the resident rows
             VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
             const int64_t nloc = e->transfers.row1 - e->transfers.row0;
