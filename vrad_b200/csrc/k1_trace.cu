@@ -95,7 +95,7 @@ k1_trace_rays(DevScene S, int64_t n, const float* __restrict__ ox, const float* 
 template <bool SKY, bool TOP>
 __global__ void __launch_bounds__(kTraceBlock, TOP ? 8 : 10)
 k1_test_lines(DevScene S, int64_t n, int64_t stride, const float* __restrict__ a, const float* __restrict__ b,
-              uint32_t* __restrict__ bits) {            // a, b: SoA blocks x[stride] y[stride] z[stride]
+              uint32_t* __restrict__ bits, int rpw) {   // a, b: SoA blocks x[stride] y[stride] z[stride]; rpw = rays per warp chunk (multiple of 32, <= kRaysPerWarp)
     __shared__ uint32_t words[kTraceWarps][kRaysPerWarp / 32];
     extern __shared__ int2 top_s[];
     if (TOP) {
@@ -103,12 +103,12 @@ k1_test_lines(DevScene S, int64_t n, int64_t stride, const float* __restrict__ a
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n_chunks = (n + kRaysPerWarp - 1) / kRaysPerWarp;
+    const int64_t n_chunks = (n + rpw - 1) / rpw;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t chunk = warp0; chunk < n_chunks; chunk += nwarps) {
-        const int64_t base = chunk * kRaysPerWarp;
-        const int64_t end = base + kRaysPerWarp < n ? base + kRaysPerWarp : n;
+        const int64_t base = chunk * rpw;
+        const int64_t end = base + rpw < n ? base + rpw : n;
         if (lane < kRaysPerWarp / 32) words[warp][lane] = 0u;
         __syncwarp();
         auto fetch = [&](int64_t& i, Ray& r, float& t0, float& t1, float& len) {
@@ -233,8 +233,9 @@ k1_sort_keys(int64_t n, SegSource src, SortGrid G, float4* __restrict__ rec, uin
 // fixed per-warp chunks would leave the kernel waiting for the warps that drew the expensive corner of the scene
 // (r02, first form: 512-position chunks, S3 map, 2^22 segments: 7.2 ms sorted against 5.2 ms unsorted).
 constexpr int kSortedRange = 128;
+constexpr int kSortedBlocksPerSM = 12;       // 40 registers: 48 resident warps (the traversal waits on memory: on the 1 M-triangle map L1 hits are 44 %)
 template <bool SKY, bool TOP, bool INDEXED>
-__global__ void __launch_bounds__(kTraceBlock, TOP ? 8 : 10)
+__global__ void __launch_bounds__(kTraceBlock, TOP ? 8 : kSortedBlocksPerSM)
 k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, const float4* __restrict__ rec, SegSource src, uint32_t* __restrict__ bits,
                      unsigned long long* __restrict__ counter) {
     extern __shared__ int2 top_s[];
@@ -278,15 +279,15 @@ k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, c
 // unsorted traversal of index pairs (the coordinate form's k1_test_lines with the endpoints fetched from the point table)
 template <bool SKY>
 __global__ void __launch_bounds__(kTraceBlock)
-k1_test_lines_indexed(DevScene S, int64_t n, SegSource src, uint32_t* __restrict__ bits) {
+k1_test_lines_indexed(DevScene S, int64_t n, SegSource src, uint32_t* __restrict__ bits, int rpw) {
     __shared__ uint32_t words[kTraceWarps][kRaysPerWarp / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n_chunks = (n + kRaysPerWarp - 1) / kRaysPerWarp;
+    const int64_t n_chunks = (n + rpw - 1) / rpw;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t chunk = warp0; chunk < n_chunks; chunk += nwarps) {
-        const int64_t base = chunk * kRaysPerWarp;
-        const int64_t end = base + kRaysPerWarp < n ? base + kRaysPerWarp : n;
+        const int64_t base = chunk * rpw;
+        const int64_t end = base + rpw < n ? base + rpw : n;
         if (lane < kRaysPerWarp / 32) words[warp][lane] = 0u;
         __syncwarp();
         auto fetch = [&](int64_t& i, Ray& r, float& t0, float& t1, float& len) {
@@ -312,8 +313,15 @@ k1_test_lines_indexed(DevScene S, int64_t n, SegSource src, uint32_t* __restrict
 }
 
 // one warp per kRaysPerWarp-ray chunk, capped at 64 resident-block waves per SM (grid-stride beyond that)
-static int stream_grid(const vrad_env* e, int64_t n) {
-    int64_t blocks = ((n + kRaysPerWarp - 1) / kRaysPerWarp + kTraceWarps - 1) / kTraceWarps;
+// rays per warp chunk: 512 for big batches; smaller batches take shorter chunks so that there are still about four chunks per
+// resident warp (a 2^21-segment batch in 512-ray chunks is 4096 warps for 5920 warp slots: r02, the chunked host path ran its
+// kernels 30 % below the rate of one 2^24 batch)
+static int rays_per_warp(const vrad_env* e, int64_t n) {
+    const int64_t want = n / ((int64_t)e->sm_count * 40 * 4);
+    return (int)std::min<int64_t>(kRaysPerWarp, std::max<int64_t>(64, want & ~(int64_t)31));
+}
+static int stream_grid(const vrad_env* e, int64_t n, int rpw = kRaysPerWarp) {
+    int64_t blocks = ((n + rpw - 1) / rpw + kTraceWarps - 1) / kTraceWarps;
     const int64_t cap = (int64_t)e->sm_count * 64;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -342,6 +350,11 @@ static bool want_sort(const vrad_env* e, int64_t n) {
 static SortGrid sort_grid(const vrad_env* e) {
     SortGrid G;
     G.mode = e->opt.k1_key;
+    if (G.mode < 0) {        // automatic: cells should be roughly cubic -- a flat world (outdoor map, 16:16:1) takes the cubic-cell layout
+        float wmin = 1e30f, wmax = 0.0f;
+        for (int c = 0; c < 3; c++) { const float w = e->scene.bmax[c] - e->scene.bmin[c]; wmin = std::min(wmin, w); wmax = std::max(wmax, w); }
+        G.mode = wmax > 4.0f * std::max(wmin, 1.0f) ? 2 : 0;
+    }
     double vol = 1.0;
     for (int c = 0; c < 3; c++) vol *= std::max(1.0, (double)e->scene.bmax[c] - (double)e->scene.bmin[c]);
     const double cell = std::cbrt(vol / 262144.0);           // edge of a cubic cell if 2^18 of them filled the box
@@ -363,17 +376,18 @@ static SortGrid sort_grid(const vrad_env* e) {
 static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int sky_mode, uint32_t* bits, int* launches) {
     const bool indexed = src.pairs != nullptr;
     if (!want_sort(e, n)) {
+        const int rpw = rays_per_warp(e, n), g = stream_grid(e, n, rpw);
         if (indexed) {
-            if (sky_mode) k1_test_lines_indexed<true><<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(e->scene, n, src, bits);
-            else k1_test_lines_indexed<false><<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(e->scene, n, src, bits);
+            if (sky_mode) k1_test_lines_indexed<true><<<g, kTraceBlock, 0, e->stream>>>(e->scene, n, src, bits, rpw);
+            else k1_test_lines_indexed<false><<<g, kTraceBlock, 0, e->stream>>>(e->scene, n, src, bits, rpw);
         } else {
             const size_t sm = (size_t)e->scene.n_top * sizeof(int2);
             if (sm) {
-                if (sky_mode) k1_test_lines<true, true><<<stream_grid(e, n), kTraceBlock, sm, e->stream>>>(e->scene, n, src.stride, src.a, src.b, bits);
-                else k1_test_lines<false, true><<<stream_grid(e, n), kTraceBlock, sm, e->stream>>>(e->scene, n, src.stride, src.a, src.b, bits);
+                if (sky_mode) k1_test_lines<true, true><<<g, kTraceBlock, sm, e->stream>>>(e->scene, n, src.stride, src.a, src.b, bits, rpw);
+                else k1_test_lines<false, true><<<g, kTraceBlock, sm, e->stream>>>(e->scene, n, src.stride, src.a, src.b, bits, rpw);
             } else {
-                if (sky_mode) k1_test_lines<true, false><<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(e->scene, n, src.stride, src.a, src.b, bits);
-                else k1_test_lines<false, false><<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(e->scene, n, src.stride, src.a, src.b, bits);
+                if (sky_mode) k1_test_lines<true, false><<<g, kTraceBlock, 0, e->stream>>>(e->scene, n, src.stride, src.a, src.b, bits, rpw);
+                else k1_test_lines<false, false><<<g, kTraceBlock, 0, e->stream>>>(e->scene, n, src.stride, src.a, src.b, bits, rpw);
             }
         }
         (*launches)++;
@@ -396,7 +410,7 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         if ((rc = scratch_get(e, 19, 8, &d_ctr))) return rc;
         VRAD_CUDA_CHECK(cudaMemsetAsync(d_ctr, 0, 8, e->stream));
         VRAD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)((m + 31) >> 5) * 4, e->stream));
-        const int sgrid = (int)std::min<int64_t>((int64_t)e->sm_count * 10, (m + kSortedRange * kTraceWarps - 1) / (kSortedRange * kTraceWarps));
+        const int sgrid = (int)std::min<int64_t>((int64_t)e->sm_count * kSortedBlocksPerSM, (m + kSortedRange * kTraceWarps - 1) / (kSortedRange * kTraceWarps));
         const int kb = (int)((m + 255) / 256);
         if (indexed) k1_sort_keys<true><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
         else k1_sort_keys<false><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
@@ -471,11 +485,11 @@ int launch_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs, int 
 // h_a / h_b are host SoA blocks x[n] y[n] z[n] (coordinates), or h_pairs the host index pairs; d_bits is the
 // device result (n bits).
 int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, const int32_t* h_pairs, int sky_mode, uint32_t* d_bits) {
-    // Chunks grow geometrically from 2^18 to 2^23 segments: the first copy is short (the traversal starts after 2 MB of
-    // pairs / 6 MB of coordinates instead of 16 / 48 MB) and the later launches are long enough that the per-launch tail
-    // (and, in sorted order, the per-batch sort) stops costing (r02: 8 equal chunks of 2^21 left the index-pair form at
-    // 5.06 ms per 2^24 segments with a 3.6 ms kernel and a 2.7 ms copy).
-    constexpr int64_t kChunkMin = (int64_t)1 << 18, kChunk = (int64_t)1 << 23;
+    // A short head chunk (2^19 segments: the traversal starts after 4 MB of pairs / 12 MB of coordinates), then equal chunks of
+    // 2^21.  Whichever side is slower -- PCIe at 24 B per segment, the kernel at 8 -- the call costs that side plus one chunk of
+    // the other.  (r02: chunks doubling up to 2^23 were worse for both forms -- a copy twice as long as the kernel before it
+    // stalls the kernel stream, and a copy-bound call ends with the whole last kernel exposed.)
+    constexpr int64_t kChunkMin = (int64_t)1 << 19, kChunk = (int64_t)1 << 21;
     const int64_t stage_cap = std::min<int64_t>(kChunk, std::max<int64_t>(kChunkMin, n));
     for (int s = 0; s < 2; s++)
         if (e->d_stage[s].alloc((size_t)(h_pairs ? 2 : 6) * stage_cap)) { set_error("out of device memory for staging"); return VRAD_E_NOMEM; }
@@ -494,10 +508,8 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
     int64_t step = kChunkMin;
     for (int64_t c0 = 0; c0 < n; c++) {
         const int s = c & 1;
-        int64_t m = std::min(step, stage_cap);
-        if (n - c0 - m < kChunkMin) m = n - c0;            // no sliver at the end
-        m = std::min(m, std::min(n - c0, stage_cap));
-        step = std::min(step * 2, kChunk);
+        const int64_t m = std::min(std::min(step, stage_cap), n - c0);
+        step = kChunk;
         float* st = e->d_stage[s].p;
         VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, e->ev_done[s], 0));
         SegSource src{};
