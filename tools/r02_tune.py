@@ -65,8 +65,8 @@ def main():
     env.points_upload(pts)
     k1 = {}
     ref = None
-    for sort, key, top in ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0)):
-        env.set_option("k1_sort", sort); env.set_option("k1_top", top); env.set_option("k1_key", key)
+    for sort, key, top in ((0, 0, 0), (0, 0, -1), (1, 0, 0), (1, -1, 0)):
+        env.set_option("k1_sort", sort); env.set_option("k1_top", max(top, 0)); env.set_option("k1_key", key); env.set_option("k1_stream", 0 if top < 0 else 1)
         ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
         got = d_bits.cpu().numpy()
         if ref is None:
@@ -74,7 +74,8 @@ def main():
         k1[f"coords_sort{sort}_key{key}_top{top}"] = {"ms": ms, "seg_per_s": n / ms * 1e3, "same_bits": bool(np.array_equal(got, ref))}
         print("S1", sort, key, top, ms, flush=True)
     env.set_option("k1_top", 0)
-    for sort, key in ((0, 0), (1, 0), (1, 1), (1, 2)):
+    env.set_option("k1_stream", 1)
+    for sort, key in ((0, 0), (1, 0)):
         env.set_option("k1_sort", sort); env.set_option("k1_key", key)
         ms = timed(lambda: env.test_lines_indexed(d_pairs, out=d_bits))
         k1[f"indexed_sort{sort}_key{key}"] = {"ms": ms, "seg_per_s": n / ms * 1e3, "same_bits": bool(np.array_equal(d_bits.cpu().numpy(), ref))}
@@ -85,7 +86,7 @@ def main():
     h_a, h_b = PinnedArray((3, n), np.float32), PinnedArray((3, n), np.float32)
     h_p = PinnedArray((n, 2), np.int32); h_bits = PinnedArray((n // 32,), np.uint32)
     h_a.array[...] = a; h_b.array[...] = b; h_p.array[...] = pairs
-    for sort in (0, 1):
+    for sort in (-1, 0, 1):
         env.set_option("k1_sort", sort)
         for name, fn in (("coords", lambda: env.test_lines(h_a.array, h_b.array, out=h_bits.array)),
                          ("indexed", lambda: env.test_lines_indexed(h_p.array, out=h_bits.array))):
@@ -112,14 +113,14 @@ def main():
         d_bits = torch.empty(n3 // 32, dtype=torch.int32, device=dev)
         k3 = {"stats": {k: (v if not hasattr(v, "tolist") else v.tolist()) for k, v in env.stats().items()}}
         ref = None
-        for sort, key in ((0, 0), (1, 0), (1, 1), (1, 2)):
-            env.set_option("k1_sort", sort); env.set_option("k1_key", key)
+        for sort, key, st in ((0, 0, 0), (0, 0, 1), (1, 0, 1), (1, 2, 1), (1, -1, 1)):
+            env.set_option("k1_sort", sort); env.set_option("k1_key", key); env.set_option("k1_stream", st)
             ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
             got = d_bits.cpu().numpy()
             if ref is None:
                 ref = got
-            k3[f"sort{sort}_key{key}"] = {"ms": ms, "seg_per_s": n3 / ms * 1e3, "same_bits": bool(np.array_equal(got, ref))}
-            print("S3", sort, key, ms, flush=True)
+            k3[f"sort{sort}_key{key}_stream{st}"] = {"ms": ms, "seg_per_s": n3 / ms * 1e3, "same_bits": bool(np.array_equal(got, ref))}
+            print("S3", sort, key, st, ms, flush=True)
         res["k1_s3"] = k3
         env.close(); del d_a, d_b, d_bits
         flush()

@@ -245,9 +245,10 @@ k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, c
     }
     // the lane's slot in `my_ray` carries the ORIGINAL segment number once fetched
     auto fetch = [&](int64_t& i, Ray& r, float& t0, float& t1, float& len) {
-        const uint32_t seg = __ldcs(&perm[i]);
+        const uint32_t seg = perm ? __ldcs(&perm[i]) : (uint32_t)i;        // no order given: the batch as it came, same streaming
         float ax, ay, az, bx, by, bz;
         if (INDEXED) load_segment<true>(src, (int64_t)seg, ax, ay, az, bx, by, bz);
+        else if (!rec) load_segment<false>(src, (int64_t)seg, ax, ay, az, bx, by, bz);
         else {
             const float4 q0 = __ldcs(&rec[2 * (int64_t)seg]), q1 = __ldcs(&rec[2 * (int64_t)seg + 1]);
             ax = q0.x; ay = q0.y; az = q0.z; bx = q0.w; by = q1.x; bz = q1.y;
@@ -373,9 +374,12 @@ static SortGrid sort_grid(const vrad_env* e) {
 
 // Enqueues the traversal of n segments (coordinates or index pairs) on e->stream; `bits` may be written with atomics
 // (sorted order) or whole words.  *launches += kernels enqueued.  n must start on a 32-segment boundary of the output.
-static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int sky_mode, uint32_t* bits, int* launches) {
+static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int sky_mode, uint32_t* bits, int* launches, bool host_chunk = false) {
     const bool indexed = src.pairs != nullptr;
-    if (!want_sort(e, n)) {
+    // chunks of a host batch are traced as they arrive unless ordering is forced: the call is bound by PCIe or close to it, and a
+    // sort per 2^21-segment chunk costs more than it saves (r02: 5.7 ms ordered against 5.0 ms per 2^24 index pairs)
+    const bool sorted = (host_chunk && e->opt.k1_sort < 0) ? false : want_sort(e, n);
+    if (!sorted && !e->opt.k1_stream) {
         const int rpw = rays_per_warp(e, n), g = stream_grid(e, n, rpw);
         if (indexed) {
             if (sky_mode) k1_test_lines_indexed<true><<<g, kTraceBlock, 0, e->stream>>>(e->scene, n, src, bits, rpw);
@@ -396,13 +400,15 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
     const SortGrid G = sort_grid(e);
     for (int64_t c0 = 0; c0 < n; c0 += kSortBatch) {
         const int64_t m = std::min(kSortBatch, n - c0);
-        void *d_rec, *d_k0, *d_k1, *d_i0, *d_i1, *d_tmp;
+        void *d_rec = nullptr, *d_k0 = nullptr, *d_k1 = nullptr, *d_i0 = nullptr, *d_i1 = nullptr, *d_tmp = nullptr;
         int rc;
-        if ((rc = scratch_get(e, 12, indexed ? 32 : (size_t)m * 32, &d_rec)) || (rc = scratch_get(e, 13, (size_t)m * 4, &d_k0)) || (rc = scratch_get(e, 14, (size_t)m * 4, &d_k1)) ||
-            (rc = scratch_get(e, 15, (size_t)m * 4, &d_i0)) || (rc = scratch_get(e, 16, (size_t)m * 4, &d_i1))) return rc;
         size_t tmp_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream);
-        if ((rc = scratch_get(e, 17, tmp_bytes + 16, &d_tmp))) return rc;
+        if (sorted) {
+            if ((rc = scratch_get(e, 12, indexed ? 32 : (size_t)m * 32, &d_rec)) || (rc = scratch_get(e, 13, (size_t)m * 4, &d_k0)) || (rc = scratch_get(e, 14, (size_t)m * 4, &d_k1)) ||
+                (rc = scratch_get(e, 15, (size_t)m * 4, &d_i0)) || (rc = scratch_get(e, 16, (size_t)m * 4, &d_i1))) return rc;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream);
+            if ((rc = scratch_get(e, 17, tmp_bytes + 16, &d_tmp))) return rc;
+        }
         SegSource sub = src;
         if (indexed) sub.pairs = src.pairs + c0; else { sub.a = src.a + c0; sub.b = src.b + c0; }
         uint32_t* out = bits + (c0 >> 5);
@@ -411,12 +417,14 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         VRAD_CUDA_CHECK(cudaMemsetAsync(d_ctr, 0, 8, e->stream));
         VRAD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)((m + 31) >> 5) * 4, e->stream));
         const int sgrid = (int)std::min<int64_t>((int64_t)e->sm_count * kSortedBlocksPerSM, (m + kSortedRange * kTraceWarps - 1) / (kSortedRange * kTraceWarps));
-        const int kb = (int)((m + 255) / 256);
-        if (indexed) k1_sort_keys<true><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
-        else k1_sort_keys<false><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
-        VRAD_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream));
+        if (sorted) {
+            const int kb = (int)((m + 255) / 256);
+            if (indexed) k1_sort_keys<true><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
+            else k1_sort_keys<false><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
+            VRAD_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream));
+        }
         const size_t sm = (size_t)e->scene.n_top * sizeof(int2);
-        const uint32_t* pm = (const uint32_t*)d_i1; const float4* rc4 = (const float4*)d_rec; unsigned long long* ctr = (unsigned long long*)d_ctr;
+        const uint32_t* pm = (const uint32_t*)d_i1; const float4* rc4 = indexed ? nullptr : (const float4*)d_rec; unsigned long long* ctr = (unsigned long long*)d_ctr;
 #define VRAD_SORTED(SKY, TOP, IDX) k1_test_lines_sorted<SKY, TOP, IDX><<<sgrid, kTraceBlock, (TOP) ? sm : 0, e->stream>>>(e->scene, m, pm, rc4, sub, out, ctr)
         if (indexed) {
             if (sm) { if (sky_mode) VRAD_SORTED(true, true, true); else VRAD_SORTED(false, true, true); }
@@ -426,7 +434,7 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
             else { if (sky_mode) VRAD_SORTED(true, false, false); else VRAD_SORTED(false, false, false); }
         }
 #undef VRAD_SORTED
-        *launches += 2 + 5;                    // keys + traversal + cub's histogram / onesweep passes (4 digit passes of 8 bits)
+        *launches += sorted ? 2 + 6 : 1;       // keys + traversal + cub's histogram / scan / onesweep passes (4 digit passes of 8 bits)
     }
     return 0;
 }
@@ -526,7 +534,7 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
         VRAD_CUDA_CHECK(cudaEventRecord(e->ev_copied[s], e->copy_stream));
         VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_copied[s], 0));
         if (h_pairs) { k1_count_bad_indices<<<(int)((2 * m + 255) / 256), 256, 0, e->stream>>>(2 * m, (const int32_t*)st, (int)e->n_points, (int*)d_bad); launches++; }
-        int rc = enqueue_test_lines(e, m, src, sky_mode, d_bits + (c0 >> 5), &launches);
+        int rc = enqueue_test_lines(e, m, src, sky_mode, d_bits + (c0 >> 5), &launches, true);
         if (rc) return rc;
         VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[s], e->stream));
         c0 += m;
