@@ -333,6 +333,26 @@ int  vrad_bounce(vrad_env*, const float* emit0_rgb, int n_bounces, int early_out
                  float added_last[3], int* bounces_done);
 
 /* ---- multi-GPU plumbing ------------------------------------------------------------------ */
+/* ONE handle that drives several GPUs of this process ("multi-GPU is internal to the handle, invisible to Go"):
+ * the reference is a single goroutine behind a package-level singleton (raytracer/environment.go:17-25;
+ * common/constants/constants.go:43), so its driver cannot start one process per GPU.  The handle owns one environment per listed
+ * device and runs every call on one worker thread per device: geometry, patches and the point table are replicated (the kd tree
+ * is built once and adopted by the other devices); vrad_test_lines / _indexed / vrad_trace_rays / vrad_direct_light split their
+ * batch into one contiguous range per device; vrad_build_transfers shards the patch rows (balanced by estimated transfers) and
+ * vrad_bounce exchanges the radiance rows every bounce with the fused peer-store kernel (cudaDeviceEnablePeerAccess; no NCCL, no
+ * IPC), returning the complete result.  Data pointers must be HOST memory on such a handle; calls are synchronous.  Available:
+ * vrad_env_destroy / set_option / last_timing / add_triangles / set_triangle_colors / build / build_fast / upload_tree / stats /
+ * download_tree / vrad_trace4 (device 0), vrad_trace_rays, vrad_test_lines, vrad_points_upload, vrad_test_lines_indexed,
+ * vrad_patches_upload, vrad_patches_set_hierarchy, vrad_build_transfers, vrad_transfers_info / _download, vrad_set_sky_dirs,
+ * vrad_set_light_trace_flags, vrad_direct_light, vrad_bounce; the others return VRAD_E_UNSUPPORTED.  The same device may be
+ * listed twice (tests on a single-GPU box): such ranks exchange radiance by device copies instead of the in-kernel barrier. */
+typedef struct {
+    int n_devices;       /* 1..8 */
+    int devices[8];      /* CUDA device ordinals, in rank order */
+    int flags;           /* VRAD_CFG_* */
+} vrad_multi_config;
+int  vrad_env_create_multi(const vrad_multi_config* cfg, vrad_env** out);
+/* One process per GPU instead (e.g. under torchrun): one handle per process with (rank, world) in vrad_config and a shared id -- */
 /* 128-byte NCCL unique id: rank 0 calls vrad_comm_unique_id, the driver distributes it, every rank
  * calls vrad_comm_init before vrad_bounce. */
 int  vrad_comm_unique_id(void* out128);

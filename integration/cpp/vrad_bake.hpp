@@ -331,6 +331,17 @@ inline void DirectLightCulled(raytracer::Environment& env, const Prepared& P, co
     }
 }
 
+// the Nodes / Planes / Leafs lumps trace.PointLeafnum and clustertable.ClusterFromPoint walk -> the environment
+inline void UploadBsp(raytracer::Environment& env, const vrad_bsp_lumps& L) {
+    std::vector<int32_t> nodePlane(L.n_nodes), nodeChildren(2 * static_cast<size_t>(L.n_nodes)), planeType(L.n_planes), leafCluster(L.n_leafs), leafArea(L.n_leafs);
+    std::vector<float> planeNormal(3 * static_cast<size_t>(L.n_planes)), planeDist(L.n_planes);
+    for (int i = 0; i < L.n_nodes; i++) { nodePlane[i] = L.nodes[i].planenum; nodeChildren[2 * i] = L.nodes[i].children[0]; nodeChildren[2 * i + 1] = L.nodes[i].children[1]; }
+    for (int i = 0; i < L.n_planes; i++) { for (int k = 0; k < 3; k++) planeNormal[3 * i + k] = L.planes[i].normal[k]; planeDist[i] = L.planes[i].dist; planeType[i] = L.planes[i].type; }
+    for (int i = 0; i < L.n_leafs; i++) { leafCluster[i] = L.leafs[i].cluster; leafArea[i] = L.leafs[i].area_flags & 0x1ff; }
+    fatal_on(vrad_bsp_upload(env.handle(), L.n_nodes, nodePlane.data(), nodeChildren.data(), L.n_planes, planeNormal.data(), planeDist.data(), planeType.data(),
+                             L.n_leafs, leafCluster.data(), leafArea.data(), std::max(L.n_areas, 1)), "vrad_bsp_upload");
+}
+
 // the device stages: geometry + kd build (K1), transfers (K2), direct light on luxels and patches (K3), bounces (K4)
 inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vector<float>& skyDirs3, int bounces = 8, bool fastTree = false, bool textureShadows = false) {
     const vrad_bsp_lumps& L = P.lumps;
@@ -340,7 +351,27 @@ inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vect
     if (fastTree) fatal_on(vrad_env_build_fast(env.handle(), VRAD_BUILD_ON_DEVICE), "vrad_env_build_fast");
     else fatal_on(vrad_env_build(env.handle()), "vrad_env_build");
     if (textureShadows) fatal_on(vrad_set_light_trace_flags(env.handle(), VRAD_TL_TEXTURE_SHADOWS), "vrad_set_light_trace_flags");
-    fatal_on(vrad_patches_upload(env.handle(), N, P.tree.origin.data(), P.tree.normal.data(), P.tree.plane_dist.data(), P.tree.area.data(), P.refl3.data(), P.cluster.data(), P.flags.data()), "vrad_patches_upload");
+    const bool haveVis = !P.pvs.empty();
+    if (haveVis) UploadBsp(env, L);
+    // Cluster per patch, AFTER subdivision (rad/patches/subdivide.go:92-116): ClusterFromPoint(patch.Origin) -- faces span leaves, so
+    // the children of one face can sit in different clusters -- and for an origin in solid space (cluster -1) the first winding
+    // point that is not.  A patch that stays at -1 is in no cluster: vrad_build_transfers leaves it out.
+    std::vector<int32_t> cluster(N, 0);
+    if (haveVis && N > 0) {
+        fatal_on(vrad_cluster_from_point(env.handle(), N, P.tree.origin.data(), cluster.data()), "vrad_cluster_from_point");
+        std::vector<float> wp; std::vector<int> owner;
+        for (int p = 0; p < N; p++) if (cluster[p] < 0)
+            for (int j = 0; j < P.tree.wind_count[p]; j++) {
+                for (int k = 0; k < 3; k++) wp.push_back(P.tree.wind_points[3 * static_cast<size_t>(P.tree.wind_first[p] + j) + k]);
+                owner.push_back(p);
+            }
+        if (!owner.empty()) {
+            std::vector<int32_t> wc(owner.size());
+            fatal_on(vrad_cluster_from_point(env.handle(), static_cast<int64_t>(owner.size()), wp.data(), wc.data()), "vrad_cluster_from_point");
+            for (size_t q = 0; q < owner.size(); q++) if (cluster[owner[q]] < 0 && wc[q] >= 0) cluster[owner[q]] = wc[q];
+        }
+    }
+    fatal_on(vrad_patches_upload(env.handle(), N, P.tree.origin.data(), P.tree.normal.data(), P.tree.plane_dist.data(), P.tree.area.data(), P.refl3.data(), cluster.data(), P.flags.data()), "vrad_patches_upload");
     fatal_on(vrad_patches_set_hierarchy(env.handle(), N, P.tree.parent.data(), P.tree.child1.data(), P.tree.child2.data(), P.tree.face.data()), "vrad_patches_set_hierarchy");
     Lit out;
     bool bumped = false;
@@ -353,13 +384,6 @@ inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vect
     // DirectLight.PVS (AllocDLight / SetDLightVis, rad/lightmap/lights.go:118-161)
     std::vector<std::vector<uint8_t>> lightSees;
     if (!P.pvs.empty() && !P.lights.empty()) {
-        std::vector<int32_t> nodePlane(L.n_nodes), nodeChildren(2 * static_cast<size_t>(L.n_nodes)), planeType(L.n_planes), leafCluster(L.n_leafs), leafArea(L.n_leafs);
-        std::vector<float> planeNormal(3 * static_cast<size_t>(L.n_planes)), planeDist(L.n_planes);
-        for (int i = 0; i < L.n_nodes; i++) { nodePlane[i] = L.nodes[i].planenum; nodeChildren[2 * i] = L.nodes[i].children[0]; nodeChildren[2 * i + 1] = L.nodes[i].children[1]; }
-        for (int i = 0; i < L.n_planes; i++) { for (int k = 0; k < 3; k++) planeNormal[3 * i + k] = L.planes[i].normal[k]; planeDist[i] = L.planes[i].dist; planeType[i] = L.planes[i].type; }
-        for (int i = 0; i < L.n_leafs; i++) { leafCluster[i] = L.leafs[i].cluster; leafArea[i] = L.leafs[i].area_flags & 0x1ff; }
-        fatal_on(vrad_bsp_upload(env.handle(), L.n_nodes, nodePlane.data(), nodeChildren.data(), L.n_planes, planeNormal.data(), planeDist.data(), planeType.data(),
-                                 L.n_leafs, leafCluster.data(), leafArea.data(), std::max(L.n_areas, 1)), "vrad_bsp_upload");
         const int nLights = static_cast<int>(P.lights.size());
         std::vector<float> lo(3 * static_cast<size_t>(nLights));
         for (int k = 0; k < nLights; k++) for (int a = 0; a < 3; a++) lo[3 * k + a] = P.lights[k].origin[a];

@@ -49,6 +49,14 @@ public:
         vrad_config cfg{device, 0, 1, 0};
         fatal_on(vrad_env_create(&cfg, &h_), "vrad_env_create");
     }
+    // one Environment over several GPUs of this process (vrad_env_create_multi): the singleton the reference's single-goroutine
+    // driver holds (raytracer/environment.go:17-25) reaches every device through it -- batches are split and transfer rows sharded inside
+    explicit Environment(const std::vector<int>& devices) {
+        vrad_multi_config cfg{};
+        cfg.n_devices = static_cast<int>(devices.size());
+        for (int i = 0; i < cfg.n_devices && i < 8; i++) cfg.devices[i] = devices[i];
+        fatal_on(vrad_env_create_multi(&cfg, &h_), "vrad_env_create_multi");
+    }
     ~Environment() { vrad_env_destroy(h_); }
     Environment(const Environment&) = delete;
     Environment& operator=(const Environment&) = delete;

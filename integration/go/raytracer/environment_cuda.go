@@ -20,6 +20,9 @@ import "C"
 
 import (
 	"log"
+	"os"
+	"strconv"
+	"strings"
 	"unsafe"
 
 	"github.com/galaco/vrad/raytracer/types"
@@ -42,11 +45,44 @@ func check(rc C.int, what string) {
 // CudaHandle exposes the handle to the sibling packages' shims (raytracer/trace, rad/patches, rad).
 func (environment *Environment) CudaHandle() unsafe.Pointer { return unsafe.Pointer(environment.cuda.h) }
 
-func newCudaEnv(device int) *cudaEnv {
-	cfg := C.vrad_config{device: C.int(device), rank: 0, world: 1, flags: 0}
+// newCudaEnv makes ONE handle over every GPU in `devices` (vrad_env_create_multi): the driver is a single goroutine behind a
+// package-level singleton (environment.go:17-25; common/constants/constants.go:43), so the devices live inside the handle --
+// batches are split and the patch rows sharded there, and every call on it takes Go (host) memory and returns when it is done.
+// One device: the plain single-GPU handle.  VRAD_DEVICES="0,1,2,3" selects the devices; the default is device 0.
+func newCudaEnv(devices []int) *cudaEnv {
 	var h *C.vrad_env
-	check(C.vrad_env_create(&cfg, &h), "vrad_env_create")
+	if len(devices) <= 1 {
+		d := 0
+		if len(devices) == 1 {
+			d = devices[0]
+		}
+		cfg := C.vrad_config{device: C.int(d), rank: 0, world: 1, flags: 0}
+		check(C.vrad_env_create(&cfg, &h), "vrad_env_create")
+		return &cudaEnv{h: h}
+	}
+	var cfg C.vrad_multi_config
+	cfg.n_devices = C.int(len(devices))
+	for i, d := range devices {
+		if i < 8 {
+			cfg.devices[i] = C.int(d)
+		}
+	}
+	check(C.vrad_env_create_multi(&cfg, &h), "vrad_env_create_multi")
 	return &cudaEnv{h: h}
+}
+
+// devicesFromEnv parses VRAD_DEVICES ("0,1,2,3"); empty or unset = device 0.
+func devicesFromEnv() []int {
+	var out []int
+	for _, f := range strings.Split(os.Getenv("VRAD_DEVICES"), ",") {
+		if d, err := strconv.Atoi(strings.TrimSpace(f)); err == nil {
+			out = append(out, d)
+		}
+	}
+	if len(out) == 0 {
+		out = []int{0}
+	}
+	return out
 }
 
 // AddTriangleWithMaterial (environment.go:45-69) keeps appending to OptimizedTriangleList on the Go
@@ -71,7 +107,7 @@ func (environment *Environment) SetupAccelerationStructureCUDA() {
 		}
 		flags[i] = C.uint8_t(g.NFlags)
 	}
-	environment.cuda = newCudaEnv(0)
+	environment.cuda = newCudaEnv(devicesFromEnv())
 	check(C.vrad_env_add_triangles(environment.cuda.h, C.int(n), &ids[0], &verts[0], &flags[0]), "vrad_env_add_triangles")
 	// replaces RefineNode/CalculateCostsOfSplit/ChangeIntoIntersectionFormat (environment.go:119-138)
 	check(C.vrad_env_build(environment.cuda.h), "vrad_env_build")

@@ -72,10 +72,13 @@ static void test_patch_to_patch(const Patches& P, int i, int j, std::vector<int3
 // candidates of receiver i in ascending patch order (MakeScales walks the vis row in patch order)
 static void row_candidates(const Patches& P, int i, int n_clusters, const uint8_t* pvs, std::vector<int32_t>& cand) {
     cand.clear();
+    // a patch whose cluster is -1 (origin and winding in solid space, rad/patches/subdivide.go:100-116) is in no cluster's
+    // child list (clusterChildren): it neither gathers nor is gathered from
+    if (pvs && P.cluster[i] < 0) return;
     if (!P.hier()) {
         for (int j = 0; j < P.n; j++) {
             if (j == i) continue;
-            if (pvs && !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[j]]) continue;
+            if (pvs && (P.cluster[j] < 0 || !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[j]])) continue;
             cand.push_back(j);
         }
         return;
@@ -83,7 +86,7 @@ static void row_candidates(const Patches& P, int i, int n_clusters, const uint8_
     if (P.child1[i] != -1) return;                       // only leaf patches gather (BuildVisLeafs walks clusterChildren)
     for (int r = 0; r < P.n; r++) {
         if (P.parent[r] != -1) continue;                 // face root patches (faceParents)
-        if (pvs && !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[r]]) continue;
+        if (pvs && (P.cluster[r] < 0 || !pvs[(size_t)P.cluster[i] * n_clusters + P.cluster[r]])) continue;
         if (P.face[i] >= 0 && P.face[r] == P.face[i]) continue;     // "don't check patches on the same face"
         test_patch_to_patch(P, i, r, cand);
     }

@@ -1,0 +1,107 @@
+"""The in-process multi-GPU handle (vrad_env_create_multi): ONE handle, one child environment per listed device, every call on
+one worker thread per child -- what the reference's single-goroutine driver needs to reach several GPUs.
+On a single-GPU box the same device is listed twice: partitioning, row balance, block bounds, the radiance exchange (device copies
+between the ranks' buffers) and the result gathering all run; with two or more GPUs the fused peer-store exchange runs as well.
+Everything is compared with the CPU oracle and with a single-device handle."""
+import numpy as np
+import pytest
+
+from vrad_b200 import scenes
+from vrad_b200.lib import VradError
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_lists():
+    import torch
+    n = torch.cuda.device_count()
+    lists = [[0, 0], [0, 0, 0]]
+    if n >= 2:
+        lists += [[0, 1]]
+    if n >= 4:
+        lists += [[0, 1, 2, 3]]
+    return lists
+
+
+@pytest.fixture(scope="module", params=range(4))
+def devices(request):
+    lists = _device_lists()
+    if request.param >= len(lists):
+        pytest.skip("not enough GPUs for this device list")
+    return lists[request.param]
+
+
+def test_rays_split_over_the_devices(devices, s1_scene, s1_oracle):
+    from vrad_b200.environment import environment_from_scene
+    env = environment_from_scene(s1_scene, devices=devices, with_patches=False)
+    for n in (1, 33, 1000, (1 << 19) + 77):
+        a, b = scenes.shadow_segments(s1_scene, n, seed=n)
+        assert np.array_equal(env.test_lines(a, b), s1_oracle.test_lines(a, b, threads=8)), n
+    n = (1 << 18) + 5
+    pts, pairs = scenes.shadow_segment_indices(s1_scene, n, seed=9)
+    a, b = scenes.shadow_segments(s1_scene, n, seed=9)
+    env.points_upload(pts)
+    assert np.array_equal(env.test_lines_indexed(pairs), s1_oracle.test_lines(a, b, threads=8))
+    r = scenes.random_rays(s1_scene, 100003, seed=3)
+    g = env.trace_rays(r["o"], r["d"], r["tmax"])
+    o = s1_oracle.trace1(r["o"], r["d"], r["tmax"], threads=8)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2].view(np.uint32), o[2].view(np.uint32))
+    ids, dist, _ = env.trace4_rays(r["o"][:, :4], r["d"][:, :4], np.zeros(4, np.float32), r["tmax"][:4])
+    assert np.array_equal(ids, o[0][:4])
+    st = env.stats()
+    assert st["n_tris"] == s1_scene.n_tris
+    # a device buffer belongs to one device: rejected, with a status
+    import torch
+    with pytest.raises(VradError) as ei:
+        env.test_lines(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    assert ei.value.status == -1
+    with pytest.raises(VradError) as ei:           # not offered on a multi-GPU handle
+        env.test_lines_sky(a, b)
+    assert ei.value.status == -6
+    env.close()
+
+
+def test_transfers_and_bounce_sharded_inside_the_handle(devices, s2_small_scene, s2_small_oracle):
+    from vrad_b200.environment import environment_from_scene
+    scene = s2_small_scene
+    env = environment_from_scene(scene, devices=devices)
+    nnz = env.build_transfers(scene.pvs)
+    assert nnz == s2_small_oracle.build_transfers(scene.pvs, threads=8)
+    row0, row1, total_nnz = env.transfers_info()
+    assert (row0, row1, total_nnz) == (0, scene.n_patches, nnz)
+    rp, col, w = env.transfers_download()
+    orp, ocol, ow = s2_small_oracle.transfers()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.array_equal(w.view(np.uint32), ow.view(np.uint32))
+    N = scene.n_patches
+    emit0 = scenes.SplitMix64(7).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
+    tg, ag, dg = env.bounce(emit0, 6)
+    to, ao, do = s2_small_oracle.bounce(emit0, 6, threads=8)
+    assert dg == 6 and np.abs(tg - to).max() <= 1e-4 * np.abs(to).max() and np.allclose(ag, ao, rtol=1e-4)
+    te, ae, de = env.bounce(emit0, 100, early_out=True)
+    toe, _, doe = s2_small_oracle.bounce(emit0, 100, early_out=True, threads=8)
+    assert de == doe and np.abs(te - toe).max() <= 1e-4 * np.abs(toe).max()
+    t40a, _, _ = env.bounce(emit0, 40)               # long enough for the captured loop; twice: same bits
+    t40b, _, _ = env.bounce(emit0, 40)
+    assert np.array_equal(t40a, t40b)
+    single = environment_from_scene(scene)
+    single.build_transfers(scene.pvs)
+    t40s, _, _ = single.bounce(emit0, 40)
+    single.close()
+    assert np.abs(t40a - t40s).max() <= 1e-4 * np.abs(t40s).max()
+    # direct light: luxels split over the devices, same light per luxel as one device
+    pos, nrm = scene.patch_origin[::3], scene.patch_normal[::3]
+    if scene.lights is not None and len(scene.lights):
+        gl = env.direct_light(pos, nrm, scene.lights)
+        ol = s2_small_oracle.direct_light(pos, nrm, scene.lights, threads=8)
+        assert np.abs(gl - ol).max() <= 1e-4 * max(float(np.abs(ol).max()), 1e-30)
+    env.close()
+
+
+def test_a_failing_rank_is_an_error_not_a_hang(devices, s2_small_scene):
+    """bounce before the transfers exist: every rank fails the same way; the handle reports it with the device and rank."""
+    from vrad_b200.environment import environment_from_scene
+    env = environment_from_scene(s2_small_scene, devices=devices)
+    with pytest.raises(VradError) as ei:
+        env.bounce(np.ones((s2_small_scene.n_patches, 3), np.float32), 2)
+    assert ei.value.status == -4 and "rank" in str(ei.value)
+    env.close()

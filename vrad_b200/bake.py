@@ -216,6 +216,30 @@ def prepare(L: B.Lumps, entity_text: str, min_chop: float = 4.0, max_chop: float
                 lux_patch=lux_patch, oversize=oversize, face_of_patch=face_of_patch)
 
 
+def patch_clusters(env, prep) -> np.ndarray:
+    """Patch.ClusterNumber, assigned AFTER subdivision as the reference does (rad/patches/subdivide.go:92-116): faces span leaves, so
+    every patch -- children included -- asks ClusterFromPoint for its own origin; an origin in solid space (cluster -1: detail and
+    displacement surfaces) takes the cluster of the first winding point that is not.  A patch that stays at -1 is in no cluster's
+    child list: vrad_build_transfers leaves it out, as receiver and as emitter."""
+    t = prep["tree"]
+    n = t["origin"].shape[0]
+    if prep["pvs"] is None or n == 0:
+        return np.zeros(n, np.int32)
+    (env.bsp_upload if hasattr(env, "bsp_upload") else env.bsp_set)(prep["bsp"])
+    cl = np.asarray(env.cluster_from_point(np.ascontiguousarray(t["origin"], np.float32))).astype(np.int32)
+    bad = np.nonzero(cl < 0)[0]
+    if bad.size:
+        first, count = t["wind_first"][bad].astype(np.int64), t["wind_count"][bad].astype(np.int64)
+        owner = np.repeat(bad, count)
+        idx = np.concatenate([np.arange(f, f + c) for f, c in zip(first, count)]) if owner.size else np.zeros(0, np.int64)
+        if idx.size:
+            wc = np.asarray(env.cluster_from_point(np.ascontiguousarray(t["wind_points"][idx], np.float32)))
+            for p, c in zip(owner, wc):                # first winding point with a cluster wins
+                if cl[p] < 0 and c >= 0:
+                    cl[p] = c
+    return cl
+
+
 def all_gather_blocks(local: np.ndarray, parts, rank: int, device=None) -> np.ndarray:
     """Concatenation over ranks of the contiguous blocks `parts` (range_partition), each rank holding `local` = its own block.
     torch.distributed.all_gather wants equal shapes, so blocks travel padded to the largest one.  device: None (gloo, host tensors)
@@ -248,7 +272,8 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int =
         env.setup_acceleration_structure() if hasattr(env, "setup_acceleration_structure") else env.build()
     if texture_shadows:
         env.set_light_trace_flags(2)                                  # VRAD_TL_TEXTURE_SHADOWS (-textureshadows, testline.go:14)
-    env.patches_upload(t["origin"], t["normal"], t["plane_dist"], t["area"], prep["refl"], prep["cluster"], prep["flags"])
+    cluster = patch_clusters(env, prep)
+    env.patches_upload(t["origin"], t["normal"], t["plane_dist"], t["area"], prep["refl"], cluster, prep["flags"])
     env.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
     if prep["needs_bump"].any() and world == 1:                       # TotalLight.Light[1..3] of the bump-mapped leaf patches (single GPU)
         env.set_bump(prep["needs_bump"], prep["bump_basis"])

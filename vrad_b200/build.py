@@ -17,7 +17,7 @@ OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libvradcuda.so")
 
 SOURCES = ["vrad_env.cu", "k1_trace.cu", "k1_sky.cu", "k2_transfers.cu", "k3_direct.cu", "k4_bounce.cu", "comm.cu", "kd_builder.cpp", "patch_subdivide.cpp", "light_setup.cpp",
-           "bsp_file.cpp", "bsp_input.cpp", "bsp_light.cpp", "k5_finalize.cu", "kd_fast.cu", "texlights.cpp", "radial.cu"]
+           "bsp_file.cpp", "bsp_input.cpp", "bsp_light.cpp", "k5_finalize.cu", "kd_fast.cu", "texlights.cpp", "radial.cu", "group.cu"]
 
 
 def _nvcc() -> str:

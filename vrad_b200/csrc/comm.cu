@@ -59,10 +59,107 @@ static int load_nccl() {
         if (_r != 0) { set_error("%s failed: %s", #expr, g_nccl.errstr(_r)); return VRAD_E_COMM; } \
     } while (0)
 
+// ---- collectives of an in-process group (LocalGroup): host memory + a barrier instead of NCCL ------------------------------
+#define VRAD_GROUP_BARRIER(G) do { if (!(G).barrier()) { set_error("a rank of the in-process group failed"); return VRAD_E_COMM; } } while (0)
+
+static int group_allgather_rows(vrad_env* e, float4* buf, const int64_t* bounds) {
+    LocalGroup& G = *e->group;
+    const int rank = e->cfg.rank;
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));        // my rows are in place before anybody reads them
+    G.ptr[rank][0] = buf;
+    VRAD_GROUP_BARRIER(G);
+    for (int r = 0; r < G.world; r++) {
+        const int64_t cnt = bounds[r + 1] - bounds[r];
+        if (r == rank || cnt <= 0) continue;
+        VRAD_CUDA_CHECK(cudaMemcpyPeerAsync(buf + bounds[r], e->cfg.device, (const float4*)G.ptr[r][0] + bounds[r], G.ranks[r]->cfg.device,
+                                            (size_t)cnt * sizeof(float4), e->stream));
+    }
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    VRAD_GROUP_BARRIER(G);                                    // nobody overwrites its rows while a peer still copies them
+    return 0;
+}
+
+static int group_exchange_rows(vrad_env* e, int64_t row0, int64_t row1, int64_t* all2) {
+    LocalGroup& G = *e->group;
+    G.rows[e->cfg.rank][0] = row0; G.rows[e->cfg.rank][1] = row1;
+    VRAD_GROUP_BARRIER(G);
+    for (int r = 0; r < G.world; r++) { all2[2 * r] = G.rows[r][0]; all2[2 * r + 1] = G.rows[r][1]; }
+    VRAD_GROUP_BARRIER(G);
+    return 0;
+}
+
+static int group_allreduce_i32(vrad_env* e, int32_t* d, size_t n) {
+    LocalGroup& G = *e->group;
+    const int rank = e->cfg.rank;
+    G.i32[rank].resize(n);
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(G.i32[rank].data(), d, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    VRAD_GROUP_BARRIER(G);
+    std::vector<int32_t> sum(n, 0);
+    for (int r = 0; r < G.world; r++) for (size_t i = 0; i < n; i++) sum[i] += G.i32[r][i];
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(d, sum.data(), n * 4, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    VRAD_GROUP_BARRIER(G);
+    return 0;
+}
+
+static int group_allreduce3(vrad_env* e, float* d3) {
+    LocalGroup& G = *e->group;
+    const int rank = e->cfg.rank;
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(G.f3[rank], d3, 12, cudaMemcpyDeviceToHost, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    VRAD_GROUP_BARRIER(G);
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int r = 0; r < G.world; r++) for (int c = 0; c < 3; c++) s[c] += G.f3[r][c];        // rank order: the same sum on every rank
+    VRAD_CUDA_CHECK(cudaMemcpyAsync(d3, s, 12, cudaMemcpyHostToDevice, e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    VRAD_GROUP_BARRIER(G);
+    return 0;
+}
+
+// peer buffers of an in-process group: plain pointers once peer access is on.  Ranks that share a device (single-GPU tests) do
+// not use the fused exchange: the in-kernel barrier needs the ranks' kernels to run side by side, which one device does not promise.
+static int group_setup_peers(vrad_env* e, size_t n_pad) {
+    LocalGroup& G = *e->group;
+    PeerLinks& P = e->peers;
+    const int world = G.world, rank = e->cfg.rank;
+    if (P.ready && P.n_pad == n_pad) return 0;
+    if (G.shares_device || world > kMaxWorld) return 0;
+    if (P.d_flags.alloc(kFlagWords)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemsetAsync(P.d_flags.p, 0, kFlagWords * sizeof(uint32_t), e->stream));
+    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    int ok = 1;
+    for (int r = 0; r < world && ok; r++) {
+        if (r == rank) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, e->cfg.device, G.ranks[r]->cfg.device) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+        const cudaError_t ce = cudaDeviceEnablePeerAccess(G.ranks[r]->cfg.device, 0);
+        if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+        cudaGetLastError();
+    }
+    G.ptr[rank][0] = e->d_er[0].p; G.ptr[rank][1] = e->d_er[1].p; G.ptr[rank][2] = P.d_flags.p; G.ok[rank] = ok;
+    VRAD_GROUP_BARRIER(G);
+    bool all_ok = true;
+    for (int r = 0; r < world; r++) all_ok = all_ok && G.ok[r];
+    PeerTable tbl{};
+    for (int r = 0; r < world; r++) {
+        P.er[0][r] = tbl.er[0][r] = (float4*)G.ptr[r][0]; P.er[1][r] = tbl.er[1][r] = (float4*)G.ptr[r][1];
+        P.flags[r] = tbl.flags[r] = (uint32_t*)G.ptr[r][2];
+    }
+    tbl.world = world; tbl.rank = rank;
+    VRAD_GROUP_BARRIER(G);
+    if (!all_ok) { P.ready = false; return 0; }
+    if (P.d_table.alloc(1)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemcpy(P.d_table.p, &tbl, sizeof(tbl), cudaMemcpyHostToDevice));
+    P.ready = true; P.simulated = false; P.n_pad = n_pad; P.table_world = world;
+    return 0;
+}
+
 // Row-indexed all-gather for arbitrary contiguous row blocks: rank r owns rows [bounds[r], bounds[r+1]) of the
 // float4 array `buf` (indexed by global row) and broadcasts them in place.  `world` small broadcasts; used for
 // the final `total` gather and as the exchange when peer mapping is unavailable.
 int comm_allgather_rows(vrad_env* e, float4* buf, const int64_t* bounds) {
+    if (e->group) return group_allgather_rows(e, buf, bounds);
     if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
     for (int r = 0; r < e->cfg.world; r++) {
         const int64_t cnt = bounds[r + 1] - bounds[r];
@@ -74,17 +171,20 @@ int comm_allgather_rows(vrad_env* e, float4* buf, const int64_t* bounds) {
 
 // every rank contributes its [row0,row1); returns the world+1 boundaries, checked to tile [0,n) in rank order
 int comm_exchange_bounds(vrad_env* e, int64_t row0, int64_t row1, int64_t n, int64_t* bounds_out) {
-    if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
     const int world = e->cfg.world;
-    DevBuf<int64_t> d;
-    if (d.alloc(2 * (size_t)world)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
-    const int64_t mine[2] = {row0, row1};
     std::vector<int64_t> all(2 * (size_t)world);
-    VRAD_CUDA_CHECK(cudaMemcpyAsync(d.p + 2 * e->cfg.rank, mine, 16, cudaMemcpyHostToDevice, e->stream));
-    VRAD_NCCL_CHECK(g_nccl.allgather(d.p + 2 * e->cfg.rank, d.p, 2, kNcclInt64, (nccl_comm_t)e->nccl_comm, e->stream));
-    VRAD_CUDA_CHECK(cudaMemcpyAsync(all.data(), d.p, 16 * (size_t)world, cudaMemcpyDeviceToHost, e->stream));
-    VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    d.release();
+    if (e->group) { int rcg = group_exchange_rows(e, row0, row1, all.data()); if (rcg) return rcg; }
+    else {
+        if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
+        DevBuf<int64_t> d;
+        if (d.alloc(2 * (size_t)world)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
+        const int64_t mine[2] = {row0, row1};
+        VRAD_CUDA_CHECK(cudaMemcpyAsync(d.p + 2 * e->cfg.rank, mine, 16, cudaMemcpyHostToDevice, e->stream));
+        VRAD_NCCL_CHECK(g_nccl.allgather(d.p + 2 * e->cfg.rank, d.p, 2, kNcclInt64, (nccl_comm_t)e->nccl_comm, e->stream));
+        VRAD_CUDA_CHECK(cudaMemcpyAsync(all.data(), d.p, 16 * (size_t)world, cudaMemcpyDeviceToHost, e->stream));
+        VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        d.release();
+    }
     int64_t expect = 0;
     for (int r = 0; r < world; r++) {
         if (all[2 * r] != expect || all[2 * r + 1] < all[2 * r]) {
@@ -102,12 +202,14 @@ int comm_exchange_bounds(vrad_env* e, int64_t row0, int64_t row1, int64_t n, int
 
 // in-place sum of an int32 device array over all ranks
 int comm_allreduce_i32(vrad_env* e, int32_t* d, size_t n) {
+    if (e->group) return group_allreduce_i32(e, d, n);
     if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
     VRAD_NCCL_CHECK(g_nccl.allreduce(d, d, n, kNcclInt32, kNcclSum, (nccl_comm_t)e->nccl_comm, e->stream));
     return 0;
 }
 
 int comm_allreduce3(vrad_env* e, float* d3) {
+    if (e->group) return group_allreduce3(e, d3);
     if (!e->nccl_comm) { set_error("communicator not initialised"); return VRAD_E_STATE; }
     VRAD_NCCL_CHECK(g_nccl.allreduce(d3, d3, 3, kNcclFloat, kNcclSum, (nccl_comm_t)e->nccl_comm, e->stream));
     return 0;
@@ -117,6 +219,7 @@ int comm_allreduce3(vrad_env* e, float* d3) {
 // every peer's buffers.  Collective: all ranks call it with the same n_pad.  Returns VRAD_OK with
 // peers.ready == false when peer mapping is unavailable (the caller then keeps the NCCL all-gather).
 int comm_setup_peers(vrad_env* e, size_t n_pad) {
+    if (e->group) return group_setup_peers(e, n_pad);
     PeerLinks& P = e->peers;
     const int world = e->cfg.world, rank = e->cfg.rank;
     if (P.ready && P.n_pad == n_pad) return 0;
@@ -195,6 +298,7 @@ int vrad_comm_unique_id(void* out128) {
 }
 
 int vrad_comm_init(vrad_env* e, const void* unique_id128) {
+    if (e && e->multi) return VRAD_OK;      // an in-process handle needs no communicator id
     if (!e || !unique_id128) return VRAD_E_INVALID;
     if (e->cfg.world == 1) return VRAD_OK;
     if (e->nccl_comm) { set_error("vrad_comm_init: already initialised"); return VRAD_E_STATE; }

@@ -93,6 +93,7 @@ struct TransfersDev {
     DevBuf<int32_t> row_ctr;        // arrivals per local row (split rows only; the finisher resets it)
     int n_items = 0, n_slots = 0, n_blocks = 0, seg_shift = 11, plan_warps = 8, pool_begin = 0;
     int64_t plan_serial = 0;        // bumped by every re-plan (invalidates the captured bounce graph)
+    int64_t rows_serial = 0;        // bumped when the resident rows change (vrad_build_transfers / vrad_transfers_upload: collective calls)
 };
 
 // BSP point-location data on the device (trace.PointLeafnum, clustertable.PointInLeaf) and the sky cameras.
@@ -151,7 +152,40 @@ struct PeerTable {
 
 } // namespace vrad
 
+#include <condition_variable>
+#include <mutex>
 namespace vrad {
+// Ranks that live in ONE process (vrad_env_create_multi): the handle the caller holds owns one child environment per device and
+// runs every collective call on one thread per child.  The children's collectives (row balance, block bounds, the fallback
+// radiance exchange, `added`, peer-buffer discovery) go through this object -- shared host memory, a generation barrier,
+// cudaMemcpyPeerAsync -- instead of NCCL, and peer buffers are plain pointers after cudaDeviceEnablePeerAccess (no IPC).
+struct LocalGroup {
+    int world = 0;
+    std::vector<vrad_env*> ranks;
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0;
+    uint64_t gen = 0;
+    bool failed = false;                 // a rank left a collective call with an error: the others must not wait for it
+    // exchange slots, written by their rank before a barrier and read by the others after it
+    void* ptr[8][4] = {};
+    std::vector<int32_t> i32[8];
+    float f3[8][3] = {};
+    int64_t rows[8][2] = {};
+    int ok[8] = {};
+    bool shares_device = false;          // two ranks on one device (single-GPU tests): no in-kernel barrier between them
+    // returns false when a rank failed
+    bool barrier() {
+        std::unique_lock<std::mutex> lk(m);
+        if (failed) return false;
+        const uint64_t g = gen;
+        if (++arrived == world) { arrived = 0; gen++; cv.notify_all(); return true; }
+        cv.wait(lk, [&] { return gen != g || failed; });
+        return !failed;
+    }
+    void fail() { std::lock_guard<std::mutex> lk(m); failed = true; cv.notify_all(); }
+    void reset() { std::lock_guard<std::mutex> lk(m); failed = false; arrived = 0; }
+};
 // tuning switches of a handle (vrad_env_set_option); the environment variables of the same meaning give the defaults
 struct EnvOptions {
     int k1_sort = -1;      // VRAD_K1_SORT: order segment batches before tracing; -1 = batches of >= 65536 segments, 0 never, 1 always
@@ -230,8 +264,12 @@ struct vrad_env {
     vrad::DevBuf<float>  d_partials;   // per-block partial sums of `added`
     vrad::DevBuf<float4> d_add;        // light added per local row by the last gather (deterministic `added` reduction)
     void* nccl_comm = nullptr;         // ncclComm_t
+    vrad::LocalGroup* group = nullptr; // child of an in-process multi-GPU handle: its collectives go through the group
+    vrad::LocalGroup* multi = nullptr; // the in-process multi-GPU handle itself (owns the group and its children; no device state of its own)
     vrad::PeerLinks peers;             // K4 fused exchange over NVLink peer memory
     vrad::GraphCache bounce_graph;
+    int64_t bounds_serial = -1;        // rows_serial the cached block boundaries belong to
+    int64_t bounds[vrad::kMaxWorld + 1] = {};
 };
 
 namespace vrad {
@@ -247,13 +285,14 @@ int scratch_get(vrad_env* e, int slot, size_t bytes, void** out);
 void timing_begin(vrad_env* e);
 void timing_end(vrad_env* e, int launches);
 int sync_if_needed(vrad_env* e, bool any_host);
+inline bool has_comm(const vrad_env* e) { return e->nccl_comm != nullptr || e->group != nullptr; }
 
 // kernel launchers implemented in the k*.cu files
 int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, const float* oz, const float* dx,
                       const float* dy, const float* dz, const float* tmin, const float* tmax, int32_t skip_id,
                       int32_t* hit_tri, int32_t* hit_sid, float* hit_t, float* normal_soa);
 int launch_test_lines(vrad_env* e, int64_t n, const float* start_soa, const float* stop_soa, int sky_mode, uint32_t* bits);
-int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, const int32_t* h_pairs, int sky_mode, uint32_t* d_bits);
+int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, int64_t host_stride, const int32_t* h_pairs, int sky_mode, uint32_t* d_bits);
 int launch_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs, int sky_mode, uint32_t* bits);
 int check_pairs_on_device(vrad_env* e, int64_t n, const int32_t* d_pairs, int* bad_out);
 int read_bad_index_count(vrad_env* e, int* bad_out);
@@ -262,3 +301,33 @@ struct KdTree;
 int build_kd_tree_binned_device(cudaStream_t stream, const float* verts9, int n, KdTree& out, int* launches, const char** why);
 
 } // namespace vrad
+
+// in-process multi-GPU handle (group.cu): a handle with e->multi set owns one child per device
+namespace vrad {
+int group_destroy(vrad_env* g);
+int group_set_option(vrad_env* g, const char* name, int value);
+int group_add_triangles(vrad_env* g, int n, const int32_t* ids, const float* verts9, const uint8_t* flags);
+int group_build(vrad_env* g, int fast, int where);
+int group_upload_tree(vrad_env* g, int n_nodes, const int32_t* children, const float* split, int n_idx, const int32_t* tri_index, int n_tris, const vrad_tri48* tris, const float aabb[6]);
+int group_set_triangle_colors(vrad_env* g, int n, const float* rgb3);
+int group_points_upload(vrad_env* g, int64_t n, const float* xyz3);
+int group_set_sky_dirs(vrad_env* g, int n, const float* dirs3);
+int group_set_light_trace_flags(vrad_env* g, int flags);
+int group_last_timing(vrad_env* g, float* ms, int* launches);
+int group_test_lines(vrad_env* g, int64_t n, const float* a, const float* b, int sky_mode, uint32_t* bits);
+int group_test_lines_indexed(vrad_env* g, int64_t n, const int32_t* pairs2, int sky_mode, uint32_t* bits);
+int group_trace_rays(vrad_env* g, int64_t n, const float* ox, const float* oy, const float* oz, const float* dx, const float* dy, const float* dz,
+                     const float* tmin, const float* tmax, int32_t skip_id, int32_t* hit_tri, int32_t* hit_sid, float* hit_t);
+int group_patches_upload(vrad_env* g, int n, const float* origin3, const float* normal3, const float* plane_dist, const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags);
+int group_set_hierarchy(vrad_env* g, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face);
+int group_build_transfers(vrad_env* g, int n_clusters, const uint8_t* pvs, int64_t* nnz_out);
+int group_transfers_info(vrad_env* g, int64_t* row0, int64_t* row1, int64_t* nnz);
+int group_transfers_download(vrad_env* g, int64_t* rowptr, int32_t* col, float* w);
+int group_direct_light(vrad_env* g, int64_t n, const float* pos3, const float* normal3, int n_lights, const vrad_light* lights, float* rgb_out);
+int group_bounce(vrad_env* g, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out, float added_last[3], int* bounces_done);
+inline int group_unsupported(const char* what) { set_error("%s is not available on a multi-GPU handle (vrad_env_create_multi)", what); return VRAD_E_UNSUPPORTED; }
+}
+// a multi-GPU handle: forward to the group; queries that any rank can answer go to rank 0
+#define VRAD_MULTI(e, call) do { if ((e) && (e)->multi) return vrad::call; } while (0)
+#define VRAD_MULTI_RANK0(e) do { if ((e) && (e)->multi) { (e) = (e)->multi->ranks[0]; cudaSetDevice((e)->cfg.device); } } while (0)
+#define VRAD_MULTI_UNSUPPORTED(e, name) do { if ((e) && (e)->multi) return vrad::group_unsupported(name); } while (0)

@@ -159,6 +159,7 @@ extern "C" {
 int vrad_bsp_upload(vrad_env* e, int n_nodes, const int32_t* node_plane, const int32_t* node_children2, int n_planes,
                     const float* plane_normal3, const float* plane_dist, const int32_t* plane_type, int n_leafs,
                     const int32_t* leaf_cluster, const int32_t* leaf_area, int n_areas) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_bsp_upload");
     if (!e || n_nodes < 0 || n_planes < 0 || n_leafs < 1 || n_areas < 0 || !leaf_cluster || !leaf_area ||
         (n_nodes > 0 && (!node_plane || !node_children2)) || (n_planes > 0 && (!plane_normal3 || !plane_dist || !plane_type))) {
         set_error("vrad_bsp_upload: bad arguments"); return VRAD_E_INVALID;
@@ -198,14 +199,17 @@ int vrad_bsp_upload(vrad_env* e, int n_nodes, const int32_t* node_plane, const i
 }
 
 int vrad_point_leafnum(vrad_env* e, int64_t n, const float* pts3, int32_t* leaf_out) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_point_leafnum");
     return launch_points(e, n, pts3, leaf_out, 0, "vrad_point_leafnum");
 }
 
 int vrad_cluster_from_point(vrad_env* e, int64_t n, const float* pts3, int32_t* cluster_out) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_cluster_from_point");
     return launch_points(e, n, pts3, cluster_out, 1, "vrad_cluster_from_point");
 }
 
 int vrad_sky_cameras_set(vrad_env* e, int n, const float* origin3, const float* scale, int* n_kept_out) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_sky_cameras_set");
     if (!e || n < 0 || (n > 0 && (!origin3 || !scale))) { set_error("vrad_sky_cameras_set: bad arguments"); return VRAD_E_INVALID; }
     if (!e->bsp_ready) { set_error("vrad_sky_cameras_set: no BSP uploaded (vrad_bsp_upload)"); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -241,6 +245,7 @@ int vrad_sky_cameras_set(vrad_env* e, int n, const float* origin3, const float* 
 }
 
 int vrad_sky_cameras_get(vrad_env* e, int* n_cameras, int32_t* cam_area, float* world_to_sky, int32_t* area_camera) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_sky_cameras_get");
     if (!e) return VRAD_E_INVALID;
     if (!e->bsp_ready) { set_error("vrad_sky_cameras_get: no BSP uploaded"); return VRAD_E_STATE; }
     if (n_cameras) *n_cameras = (int)e->h_cam_area.size();
@@ -254,6 +259,7 @@ int vrad_sky_cameras_get(vrad_env* e, int* n_cameras, int32_t* cam_area, float* 
 
 int vrad_test_lines_sky(vrad_env* e, int64_t n, const float* start_xyz_soa, const float* stop_xyz_soa, int flags,
                         int32_t static_prop_to_skip, float* fraction_visible) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_test_lines_sky");
     if (!e || n < 0 || (n > 0 && (!start_xyz_soa || !stop_xyz_soa || !fraction_visible))) { set_error("vrad_test_lines_sky: bad arguments"); return VRAD_E_INVALID; }
     if (!e->built) { set_error("vrad_test_lines_sky: acceleration structure not built"); return VRAD_E_STATE; }
     if (n == 0) return VRAD_OK;
@@ -275,6 +281,7 @@ int vrad_test_lines_sky(vrad_env* e, int64_t n, const float* start_xyz_soa, cons
 }
 
 int vrad_leafs_trace_to_sky(vrad_env* e, int n_leafs, const int16_t* mins3, const int16_t* maxs3, uint8_t* can_out) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_leafs_trace_to_sky");
     if (!e || n_leafs < 0 || (n_leafs > 0 && (!mins3 || !maxs3 || !can_out))) { set_error("vrad_leafs_trace_to_sky: bad arguments"); return VRAD_E_INVALID; }
     if (!e->built) { set_error("vrad_leafs_trace_to_sky: acceleration structure not built"); return VRAD_E_STATE; }
     if (e->n_sky_dirs <= 0) { set_error("vrad_leafs_trace_to_sky: no sky directions set (vrad_set_sky_dirs)"); return VRAD_E_STATE; }

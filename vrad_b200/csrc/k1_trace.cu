@@ -492,7 +492,8 @@ int launch_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs, int 
 // while the previous chunk is traced, so the call costs max(PCIe, kernel) instead of their sum.
 // h_a / h_b are host SoA blocks x[n] y[n] z[n] (coordinates), or h_pairs the host index pairs; d_bits is the
 // device result (n bits).
-int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, const int32_t* h_pairs, int sky_mode, uint32_t* d_bits) {
+// host_stride: distance between the x, y and z blocks of h_a / h_b (= n unless the batch is a range of a larger one)
+int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const float* h_b, int64_t host_stride, const int32_t* h_pairs, int sky_mode, uint32_t* d_bits) {
     // A short head chunk (2^19 segments: the traversal starts after 4 MB of pairs / 12 MB of coordinates), then equal chunks of
     // 2^21.  Whichever side is slower -- PCIe at 24 B per segment, the kernel at 8 -- the call costs that side plus one chunk of
     // the other.  (r02: chunks doubling up to 2^23 were worse for both forms -- a copy twice as long as the kernel before it
@@ -526,8 +527,8 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
             src.pairs = (const int2*)st; src.pts = e->d_points.p; src.n_pts = (int)e->n_points;
         } else {
             for (int k = 0; k < 3; k++) {
-                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + k * stage_cap, h_a + k * n + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
-                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + (3 + k) * stage_cap, h_b + k * n + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
+                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + k * stage_cap, h_a + k * host_stride + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
+                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + (3 + k) * stage_cap, h_b + k * host_stride + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
             }
             src.a = st; src.b = st + 3 * stage_cap; src.stride = stage_cap;
         }

@@ -115,7 +115,8 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
                 if (j != i) {
                     cj = __ldg(&cluster[j]);
                     // row j lists i when the cluster of i's face root is visible from j's cluster (ti.w == ci when flat)
-                    const bool mirror = j >= row0 && j < row0 + nloc && (pvs == nullptr || __ldg(&pvs[(size_t)cj * n_clusters + ti.w]) != 0);
+                    // (a face root in no cluster, ti.w == -1, is in nobody's list; cj is a real cluster: j came out of a candidate list)
+                    const bool mirror = j >= row0 && j < row0 + nloc && (pvs == nullptr || (ti.w >= 0 && ti.w < n_clusters && __ldg(&pvs[(size_t)cj * n_clusters + ti.w]) != 0));
                     if (!(mirror && j < i)) {                       // otherwise thread (j, i) covers this pair
                         const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
                         const float sky_j = __ldg(&P.refl[j]).w;
@@ -355,6 +356,7 @@ using namespace vrad;
 extern "C" {
 
 int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_t* nnz_out) {
+    VRAD_MULTI(e, group_build_transfers(e, n_clusters, pvs, nnz_out));
     if (!e) return VRAD_E_INVALID;
     if (!e->built) { set_error("vrad_build_transfers: acceleration structure not built"); return VRAD_E_STATE; }
     PatchesDev& P = e->patches;
@@ -363,13 +365,17 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     const int N = P.n;
     const int C = pvs ? n_clusters : 1;
+    // A patch with cluster -1 (origin and winding points all in solid space, rad/patches/subdivide.go:100-116) is in no cluster's
+    // child list upstream: it neither gathers nor is gathered from.  Here it goes to an extra cluster, index C, that sees nothing
+    // and that nothing sees -- its row comes out empty and it is in no candidate list -- so the kernels need no special case.
+    const int Cx = C + 1;
     // host: per-cluster patch lists, then per-cluster sorted candidate lists (PVS-visible clusters)
     std::vector<int32_t> clus(N, 0);
     if (pvs) {
         for (int i = 0; i < N; i++) {
             int c = P.h_cluster[i];
-            if (c < 0 || c >= C) { set_error("vrad_build_transfers: patch %d has cluster %d outside [0,%d)", i, c, C); return VRAD_E_INVALID; }
-            clus[i] = c;
+            if (c < -1 || c >= C) { set_error("vrad_build_transfers: patch %d has cluster %d outside [-1,%d)", i, c, C); return VRAD_E_INVALID; }
+            clus[i] = c < 0 ? C : c;
         }
     }
     // candidates of a cluster = every patch (with a hierarchy: of any tree level) whose face root lies in a visible cluster
@@ -379,13 +385,13 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     if (hier && pvs) {
         for (int i = 0; i < N; i++) {
             int c = P.h_root_cluster[i];
-            if (c < 0 || c >= C) { set_error("vrad_build_transfers: the face root of patch %d has cluster %d outside [0,%d)", i, c, C); return VRAD_E_INVALID; }
-            rclus[i] = c;
+            if (c < -1 || c >= C) { set_error("vrad_build_transfers: the face root of patch %d has cluster %d outside [-1,%d)", i, c, C); return VRAD_E_INVALID; }
+            rclus[i] = c < 0 ? C : c;
         }
     }
-    std::vector<std::vector<int32_t>> members(C);
+    std::vector<std::vector<int32_t>> members(Cx);
     for (int i = 0; i < N; i++) members[rclus[i]].push_back(i);
-    std::vector<int64_t> cand_ptr(C + 1, 0);
+    std::vector<int64_t> cand_ptr(Cx + 1, 0);
     std::vector<int32_t> cand_idx;
     for (int c = 0; c < C; c++) {
         size_t start = cand_idx.size();
@@ -394,34 +400,36 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
         std::sort(cand_idx.begin() + start, cand_idx.end());
         cand_ptr[c + 1] = (int64_t)cand_idx.size();
     }
+    cand_ptr[Cx] = cand_ptr[C];                                                // the extra cluster's list is empty
     // hierarchical top-down form: per cluster, the face roots (patches without a parent) of the clusters it sees
-    std::vector<int64_t> root_ptr(C + 1, 0);
+    std::vector<int64_t> root_ptr(Cx + 1, 0);
     std::vector<int32_t> root_idx;
     if (hier) {
-        std::vector<std::vector<int32_t>> roots(C);
+        std::vector<std::vector<int32_t>> roots(Cx);
         for (int i = 0; i < N; i++) if (P.h_parent[i] == -1) roots[rclus[i]].push_back(i);
         for (int c = 0; c < C; c++) {
             for (int c2 = 0; c2 < C; c2++)
                 if (!pvs || pvs[(size_t)c * C + c2]) root_idx.insert(root_idx.end(), roots[c2].begin(), roots[c2].end());
             root_ptr[c + 1] = (int64_t)root_idx.size();
         }
+        root_ptr[Cx] = root_ptr[C];
     }
     const int world = e->cfg.world;
     const int64_t rpr = ((int64_t)N + world - 1) / world;
     int64_t row0 = std::min<int64_t>(N, e->cfg.rank * rpr), row1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
     PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p};
     static const bool no_balance = [] { const char* v = getenv("VRAD_K2_BALANCE"); return v && v[0] == '0'; }();
-    if (world > 1 && e->nccl_comm && !no_balance) {
+    if (world > 1 && has_comm(e) && !no_balance) {
         // Balance the contiguous row blocks by estimated transfers instead of by row count (collective): every
         // rank estimates the row lengths of its equal block (k2_estimate), the estimates are summed over ranks, and
         // block r starts at the first row whose prefix reaches r/world of the total -- identical on every rank.
         DevBuf<int32_t> d_cl, d_ci, d_counts; DevBuf<int64_t> d_cp;
         auto drop = [&]() { d_cl.release(); d_ci.release(); d_counts.release(); d_cp.release(); };
-        if (d_cl.alloc(N) || d_ci.alloc(cand_idx.size() + 1) || d_cp.alloc(C + 1) || d_counts.alloc(N)) { drop(); set_error("out of device memory (row balance)"); return VRAD_E_NOMEM; }
+        if (d_cl.alloc(N) || d_ci.alloc(cand_idx.size() + 1) || d_cp.alloc(Cx + 1) || d_counts.alloc(N)) { drop(); set_error("out of device memory (row balance)"); return VRAD_E_NOMEM; }
         std::vector<int32_t> counts(N);
         cudaError_t ce = cudaMemcpyAsync(d_cl.p, clus.data(), (size_t)N * 4, cudaMemcpyHostToDevice, e->stream);
         if (ce == cudaSuccess && !cand_idx.empty()) ce = cudaMemcpyAsync(d_ci.p, cand_idx.data(), cand_idx.size() * 4, cudaMemcpyHostToDevice, e->stream);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_cp.p, cand_ptr.data(), (C + 1) * 8, cudaMemcpyHostToDevice, e->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_cp.p, cand_ptr.data(), (Cx + 1) * 8, cudaMemcpyHostToDevice, e->stream);
         if (ce == cudaSuccess) ce = cudaMemsetAsync(d_counts.p, 0, (size_t)N * 4, e->stream);
         if (ce != cudaSuccess) { drop(); set_error("row balance staging failed: %s", cudaGetErrorString(ce)); return VRAD_E_CUDA; }
         const int nl0 = (int)(row1 - row0);
@@ -464,7 +472,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     TransfersDev& T = e->transfers;
     T.ready = false;
     auto cleanup = [&]() { d_clus.release(); d_cand_idx.release(); d_cand_ptr.release(); d_bit_ptr.release(); d_padlen.release(); d_bits.release(); d_tmp.release(); d_pvs.release(); };
-    if (d_clus.alloc(N) || d_cand_idx.alloc(cand_idx.size() + 1) || d_cand_ptr.alloc(C + 1) || d_bit_ptr.alloc(nloc + 1) ||
+    if (d_clus.alloc(N) || d_cand_idx.alloc(cand_idx.size() + 1) || d_cand_ptr.alloc(Cx + 1) || d_bit_ptr.alloc(nloc + 1) ||
         d_padlen.alloc(nloc + 1) || d_bits.alloc(nwords + 1) || T.rowptr.alloc(nloc + 1) || T.rowlen.alloc(nloc + 1) ||
         (pvs && d_pvs.alloc((size_t)C * C))) {
         cleanup(); set_error("out of device memory for transfer build (%lld visibility words)", (long long)nwords); return VRAD_E_NOMEM;
@@ -472,7 +480,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
 #define K2_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); return VRAD_E_CUDA; } } while (0)
     K2_CHECK(cudaMemcpyAsync(d_clus.p, clus.data(), (size_t)N * 4, cudaMemcpyHostToDevice, e->stream));
     if (!cand_idx.empty()) K2_CHECK(cudaMemcpyAsync(d_cand_idx.p, cand_idx.data(), cand_idx.size() * 4, cudaMemcpyHostToDevice, e->stream));
-    K2_CHECK(cudaMemcpyAsync(d_cand_ptr.p, cand_ptr.data(), (C + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    K2_CHECK(cudaMemcpyAsync(d_cand_ptr.p, cand_ptr.data(), (Cx + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     K2_CHECK(cudaMemcpyAsync(d_bit_ptr.p, bit_ptr.data(), (nloc + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     K2_CHECK(cudaMemsetAsync(d_padlen.p, 0, (nloc + 1) * 8, e->stream));
     K2_CHECK(cudaMemsetAsync(d_bits.p, 0, (size_t)(nwords + 1) * 4, e->stream));
@@ -492,14 +500,14 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
             for (int64_t i = row0; i < row1; i++) if (P.h_child1[i] == -1) lrows.push_back((int32_t)(i - row0));
             DevBuf<int32_t> d_rows, d_root_idx; DevBuf<int64_t> d_root_ptr; DevBuf<int> d_ovf;
             auto drop = [&]() { d_rows.release(); d_root_idx.release(); d_root_ptr.release(); d_ovf.release(); };
-            if (d_rows.alloc(lrows.size() + 1) || d_root_idx.alloc(root_idx.size() + 1) || d_root_ptr.alloc(C + 1) || d_ovf.alloc(1)) {
+            if (d_rows.alloc(lrows.size() + 1) || d_root_idx.alloc(root_idx.size() + 1) || d_root_ptr.alloc(Cx + 1) || d_ovf.alloc(1)) {
                 drop(); cleanup(); set_error("out of device memory (top-down transfer build)"); return VRAD_E_NOMEM;
             }
             int ovf = 0;
             cudaError_t ce = cudaSuccess;
             if (!lrows.empty()) ce = cudaMemcpyAsync(d_rows.p, lrows.data(), lrows.size() * 4, cudaMemcpyHostToDevice, e->stream);
             if (ce == cudaSuccess && !root_idx.empty()) ce = cudaMemcpyAsync(d_root_idx.p, root_idx.data(), root_idx.size() * 4, cudaMemcpyHostToDevice, e->stream);
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_root_ptr.p, root_ptr.data(), (C + 1) * 8, cudaMemcpyHostToDevice, e->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_root_ptr.p, root_ptr.data(), (Cx + 1) * 8, cudaMemcpyHostToDevice, e->stream);
             if (ce == cudaSuccess) ce = cudaMemsetAsync(d_ovf.p, 0, sizeof(int), e->stream);
             if (ce == cudaSuccess && !lrows.empty())
                 k2_visibility_topdown<<<std::min((int)lrows.size(), e->sm_count * 16), kTdThreads, 0, e->stream>>>(
@@ -553,7 +561,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     }
     int64_t nnz = 0;
     for (int r = 0; r < nloc; r++) nnz += rl[r];
-    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np;
+    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.rows_serial++;
     cleanup();
     int rcp = build_gather_plan(e, rl.data(), nloc);
     if (rcp) return rcp;

@@ -190,6 +190,7 @@ using namespace vrad;
 extern "C" {
 
 int vrad_set_sky_dirs(vrad_env* e, int n, const float* dirs3) {
+    VRAD_MULTI(e, group_set_sky_dirs(e, n, dirs3));
     if (!e || n < 0 || (n > 0 && !dirs3)) { set_error("vrad_set_sky_dirs: bad arguments"); return VRAD_E_INVALID; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     if (e->d_sky_dirs.alloc(3 * (size_t)n + 1)) { set_error("out of device memory"); return VRAD_E_NOMEM; }
@@ -199,6 +200,7 @@ int vrad_set_sky_dirs(vrad_env* e, int n, const float* dirs3) {
 }
 
 int vrad_set_light_trace_flags(vrad_env* e, int flags) {
+    VRAD_MULTI(e, group_set_light_trace_flags(e, flags));
     if (!e || (flags & ~(VRAD_TL_CAN_RECURSE | VRAD_TL_TEXTURE_SHADOWS))) { set_error("vrad_set_light_trace_flags: bad arguments"); return VRAD_E_INVALID; }
     e->light_trace_flags = flags;
     return VRAD_OK;
@@ -206,6 +208,7 @@ int vrad_set_light_trace_flags(vrad_env* e, int flags) {
 
 int vrad_direct_light(vrad_env* e, int64_t n_luxels, const float* pos3, const float* normal3, int n_lights,
                       const vrad_light* lights, float* rgb_out) {
+    VRAD_MULTI(e, group_direct_light(e, n_luxels, pos3, normal3, n_lights, lights, rgb_out));
     if (!e || n_luxels < 0 || n_lights < 0 || (n_luxels > 0 && (!pos3 || !normal3 || !rgb_out)) || (n_lights > 0 && !lights)) {
         set_error("vrad_direct_light: bad arguments"); return VRAD_E_INVALID;
     }

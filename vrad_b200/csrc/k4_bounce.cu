@@ -728,6 +728,7 @@ extern "C" {
 
 int vrad_patches_upload(vrad_env* e, int n, const float* origin3, const float* normal3, const float* plane_dist,
                         const float* area, const float* reflectivity3, const int32_t* cluster, const uint8_t* flags) {
+    VRAD_MULTI(e, group_patches_upload(e, n, origin3, normal3, plane_dist, area, reflectivity3, cluster, flags));
     if (!e || n <= 0 || !origin3 || !normal3 || !plane_dist || !area || !reflectivity3) { set_error("vrad_patches_upload: bad arguments"); return VRAD_E_INVALID; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     PatchesDev& P = e->patches;
@@ -756,6 +757,7 @@ int vrad_patches_upload(vrad_env* e, int n, const float* origin3, const float* n
 }
 
 int vrad_patches_set_hierarchy(vrad_env* e, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face) {
+    VRAD_MULTI(e, group_set_hierarchy(e, n, parent, child1, child2, face));
     if (!e || !parent || !child1 || !child2) { set_error("vrad_patches_set_hierarchy: bad arguments"); return VRAD_E_INVALID; }
     PatchesDev& P = e->patches;
     if (P.n == 0 || n != P.n) { set_error("vrad_patches_set_hierarchy: %d links for %d uploaded patches", n, P.n); return VRAD_E_STATE; }
@@ -852,6 +854,7 @@ int vrad_bump_normals(const float s_vect[3], const float t_vect[3], const float 
 }
 
 int vrad_patches_set_bump(vrad_env* e, int n, const uint8_t* needs_bump, const float* bump_normals9) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_patches_set_bump");
     if (!e || !needs_bump || !bump_normals9) { set_error("vrad_patches_set_bump: bad arguments"); return VRAD_E_INVALID; }
     PatchesDev& P = e->patches;
     if (P.n == 0 || n != P.n) { set_error("vrad_patches_set_bump: %d entries for %d uploaded patches", n, P.n); return VRAD_E_STATE; }
@@ -867,6 +870,7 @@ int vrad_patches_set_bump(vrad_env* e, int n, const uint8_t* needs_bump, const f
 }
 
 int vrad_bounce_bump_totals(vrad_env* e, float* out9) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_bounce_bump_totals");
     if (!e || !out9) { set_error("vrad_bounce_bump_totals: bad arguments"); return VRAD_E_INVALID; }
     PatchesDev& P = e->patches;
     if (!P.bump || P.total_bump[0].n < (size_t)P.n) { set_error("vrad_bounce_bump_totals: no bump-mapped bounce has run (vrad_patches_set_bump, vrad_bounce)"); return VRAD_E_STATE; }
@@ -881,6 +885,7 @@ int vrad_bounce_bump_totals(vrad_env* e, float* out9) {
 }
 
 int vrad_transfers_upload(vrad_env* e, int64_t row0, int64_t row1, const int64_t* rowptr, const int32_t* col, const float* w) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_transfers_upload");
     if (!e || !rowptr || row0 < 0 || row1 < row0) { set_error("vrad_transfers_upload: bad arguments"); return VRAD_E_INVALID; }
     const int64_t N = e->patches.n;
     if (N == 0) { set_error("vrad_transfers_upload: upload patches first"); return VRAD_E_STATE; }
@@ -916,7 +921,7 @@ int vrad_transfers_upload(vrad_env* e, int64_t row0, int64_t row1, const int64_t
     VRAD_CUDA_CHECK(cudaMemcpyAsync(T.rowlen.p, rlen.data(), rlen.size() * 4, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaMemcpyAsync(T.tr.p, ptr.data(), ptr.size() * 8, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np;
+    T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.rows_serial++;
     int rcp = build_gather_plan(e, rlen.data(), nloc);
     if (rcp) return rcp;
     T.ready = true;
@@ -924,6 +929,7 @@ int vrad_transfers_upload(vrad_env* e, int64_t row0, int64_t row1, const int64_t
 }
 
 int vrad_transfers_info(vrad_env* e, int64_t* row0, int64_t* row1, int64_t* nnz) {
+    VRAD_MULTI(e, group_transfers_info(e, row0, row1, nnz));
     if (!e) return VRAD_E_INVALID;
     if (!e->transfers.ready) { set_error("vrad_transfers_info: no transfers resident"); return VRAD_E_STATE; }
     if (row0) *row0 = e->transfers.row0;
@@ -933,6 +939,7 @@ int vrad_transfers_info(vrad_env* e, int64_t* row0, int64_t* row1, int64_t* nnz)
 }
 
 int vrad_transfers_download(vrad_env* e, int64_t* rowptr, int32_t* col, float* w) {
+    VRAD_MULTI(e, group_transfers_download(e, rowptr, col, w));
     if (!e) return VRAD_E_INVALID;
     TransfersDev& T = e->transfers;
     if (!T.ready) { set_error("vrad_transfers_download: no transfers resident"); return VRAD_E_STATE; }
@@ -958,6 +965,7 @@ int vrad_transfers_download(vrad_env* e, int64_t* rowptr, int32_t* col, float* w
 }
 
 int vrad_transfers_download_rows(vrad_env* e, int64_t row_begin, int64_t row_end, int64_t* rowptr, int32_t* col, float* w, int64_t capacity) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_transfers_download_rows");
     if (!e || !rowptr) { set_error("vrad_transfers_download_rows: bad arguments"); return VRAD_E_INVALID; }
     TransfersDev& T = e->transfers;
     if (!T.ready) { set_error("vrad_transfers_download_rows: no transfers resident"); return VRAD_E_STATE; }
@@ -1043,11 +1051,12 @@ static int setup_simulated_peers(vrad_env* e, size_t n_pad) {
 
 int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out,
                 float added_last[3], int* bounces_done) {
+    VRAD_MULTI(e, group_bounce(e, emit0_rgb, n_bounces, early_out, total_rgb_out, added_last, bounces_done));
     if (!e || !emit0_rgb || n_bounces < 0) { set_error("vrad_bounce: bad arguments"); return VRAD_E_INVALID; }
     TransfersDev& T = e->transfers;
     if (!T.ready) { set_error("vrad_bounce: no transfers resident (vrad_build_transfers / vrad_transfers_upload first)"); return VRAD_E_STATE; }
-    const bool sim = (e->opt.k4_sim_peers && e->cfg.world > 1 && !e->nccl_comm) || (e->opt.k4_items && e->cfg.world == 1);
-    if (e->cfg.world > 1 && !e->nccl_comm && !sim) { set_error("vrad_bounce: world=%d but vrad_comm_init was not called", e->cfg.world); return VRAD_E_STATE; }
+    const bool sim = (e->opt.k4_sim_peers && e->cfg.world > 1 && !has_comm(e)) || (e->opt.k4_items && e->cfg.world == 1);
+    if (e->cfg.world > 1 && !has_comm(e) && !sim) { set_error("vrad_bounce: world=%d but vrad_comm_init was not called", e->cfg.world); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     const int64_t N = e->patches.n;
     const int world = e->cfg.world;
@@ -1056,8 +1065,14 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     int64_t bounds[kMaxWorld + 1] = {0};
     if (world > 1 && !sim) {
         if (world > kMaxWorld) { set_error("vrad_bounce: world %d > %d", world, kMaxWorld); return VRAD_E_UNSUPPORTED; }
-        int rcb = comm_exchange_bounds(e, T.row0, T.row1, N, bounds);
-        if (rcb) return rcb;
+        // the block boundaries change only when the rows do (a collective call on every rank): exchanged and checked once per
+        // set of rows, not once per call -- the exchange is a collective plus a host synchronisation in front of every bounce loop
+        if (e->bounds_serial != T.rows_serial) {
+            int rcb = comm_exchange_bounds(e, T.row0, T.row1, N, e->bounds);
+            if (rcb) return rcb;
+            e->bounds_serial = T.rows_serial;
+        }
+        memcpy(bounds, e->bounds, sizeof(bounds));
     } else if (world == 1 && (T.row0 != 0 || T.row1 != N)) {
         set_error("vrad_bounce: world=1 but the resident transfer rows are [%lld,%lld) of %lld", (long long)T.row0, (long long)T.row1, (long long)N);
         return VRAD_E_STATE;

@@ -108,9 +108,14 @@ struct InitRefs {
     KD_HD void operator()(int64_t r) const { ref_tri[r] = (int32_t)r; ref_slot[r] = 0; }
 };
 
+// Clamped in float BEFORE the conversion: for a denormal box width inv is +inf, the product +inf or NaN, and converting that
+// is undefined on the host (cvttss2si gives INT_MIN -> bin 0) but saturates on the device (bin 31) -- host and device policies
+// would build different trees from the same triangles.  NaN compares false both times and lands in bin 0 everywhere.
 KD_HD int bin_of(float x, float lo, float inv) {
-    int b = (int)((x - lo) * inv);
-    return b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+    const float f = (x - lo) * inv;
+    if (!(f > 0.0f)) return 0;
+    if (f >= (float)(kBins - 1)) return kBins - 1;
+    return (int)f;
 }
 
 struct BinRefs {

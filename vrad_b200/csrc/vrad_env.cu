@@ -186,6 +186,8 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
     VRAD_CUDA_CHECK(cudaSetDevice(c.device));
     vrad_env* e = new (std::nothrow) vrad_env();
     if (!e) return VRAD_E_NOMEM;
+    // any failure below destroys what was created so far (streams, events, the handle) before the status goes back
+    struct Guard { vrad_env* e; ~Guard() { if (e) vrad_env_destroy(e); } } guard{e};
     e->cfg = c;
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     e->opt.k1_sort = env_int("VRAD_K1_SORT", e->opt.k1_sort);
@@ -213,11 +215,13 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
         VRAD_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_copied[s], cudaEventDisableTiming));
         VRAD_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done[s], cudaEventDisableTiming));
     }
+    guard.e = nullptr;
     *out = e;
     return VRAD_OK;
 }
 
 void vrad_env_destroy(vrad_env* e) {
+    if (e && e->multi) { vrad::group_destroy(e); delete e; return; }
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
@@ -247,6 +251,7 @@ void vrad_env_destroy(vrad_env* e) {
 }
 
 int vrad_env_set_stream(vrad_env* e, void* cuda_stream) {
+    VRAD_MULTI_UNSUPPORTED(e, "vrad_env_set_stream");
     if (!e) return VRAD_E_INVALID;
     cudaStreamSynchronize(e->stream);
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
@@ -254,6 +259,7 @@ int vrad_env_set_stream(vrad_env* e, void* cuda_stream) {
 }
 
 int vrad_env_set_option(vrad_env* e, const char* name, int value) {
+    VRAD_MULTI(e, group_set_option(e, name, value));
     if (!e || !name) { set_error("vrad_env_set_option: bad arguments"); return VRAD_E_INVALID; }
     const std::string n(name);
     EnvOptions& o = e->opt;
@@ -280,12 +286,14 @@ int vrad_env_set_option(vrad_env* e, const char* name, int value) {
 }
 
 int vrad_env_set_async(vrad_env* e, int async) {
+    if (e && e->multi) return VRAD_OK;      // calls on a multi-GPU handle take host buffers and are synchronous
     if (!e) return VRAD_E_INVALID;
     e->async = async != 0;
     return VRAD_OK;
 }
 
 int vrad_env_last_timing(vrad_env* e, float* kernel_ms, int* n_launches) {
+    VRAD_MULTI(e, group_last_timing(e, kernel_ms, n_launches));
     if (!e) return VRAD_E_INVALID;
     if (e->last_ms < 0.0f) {
         VRAD_CUDA_CHECK(cudaEventSynchronize(e->ev1));
@@ -304,6 +312,7 @@ void* vrad_host_alloc(size_t bytes) {
 void vrad_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int vrad_env_add_triangles(vrad_env* e, int n, const int32_t* ids, const float* verts9, const uint8_t* flags) {
+    VRAD_MULTI(e, group_add_triangles(e, n, ids, verts9, flags));
     if (!e || n < 0 || (n > 0 && (!ids || !verts9))) { set_error("vrad_env_add_triangles: bad arguments"); return VRAD_E_INVALID; }
     if (e->built) { set_error("vrad_env_add_triangles: acceleration structure already built"); return VRAD_E_STATE; }
     e->h_ids.insert(e->h_ids.end(), ids, ids + n);
@@ -313,6 +322,7 @@ int vrad_env_add_triangles(vrad_env* e, int n, const int32_t* ids, const float* 
 }
 
 int vrad_env_set_triangle_colors(vrad_env* e, int n, const float* rgb3) {
+    VRAD_MULTI(e, group_set_triangle_colors(e, n, rgb3));
     if (!e || n < 0 || (n > 0 && !rgb3)) { set_error("vrad_env_set_triangle_colors: bad arguments"); return VRAD_E_INVALID; }
     const size_t have = e->built ? e->h_tris.size() : e->h_ids.size();
     if ((size_t)n != have) { set_error("vrad_env_set_triangle_colors: %d colours for %zu triangles", n, have); return VRAD_E_INVALID; }
@@ -323,6 +333,7 @@ int vrad_env_set_triangle_colors(vrad_env* e, int n, const float* rgb3) {
 }
 
 int vrad_env_build(vrad_env* e) {
+    VRAD_MULTI(e, group_build(e, 0, 0));
     if (!e) return VRAD_E_INVALID;
     if (e->built) { set_error("vrad_env_build: already built"); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -337,6 +348,7 @@ int vrad_env_build(vrad_env* e) {
 }
 
 int vrad_env_build_fast(vrad_env* e, int where) {
+    VRAD_MULTI(e, group_build(e, 1, where));
     if (!e || (where != VRAD_BUILD_ON_DEVICE && where != VRAD_BUILD_ON_HOST)) { set_error("vrad_env_build_fast: bad arguments"); return VRAD_E_INVALID; }
     if (e->built) { set_error("vrad_env_build_fast: already built"); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -384,6 +396,7 @@ int vrad_kd_build_binned_host(int n, const float* verts9, int max_nodes, int max
 
 int vrad_env_upload_tree(vrad_env* e, int n_nodes, const int32_t* children, const float* split, int n_idx,
                          const int32_t* tri_index, int n_tris, const vrad_tri48* tris, const float aabb[6]) {
+    VRAD_MULTI(e, group_upload_tree(e, n_nodes, children, split, n_idx, tri_index, n_tris, tris, aabb));
     if (!e || !children || !split || (n_idx > 0 && !tri_index) || (n_tris > 0 && !tris) || !aabb) { set_error("vrad_env_upload_tree: bad arguments"); return VRAD_E_INVALID; }
     if (e->built) { set_error("vrad_env_upload_tree: already built"); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -404,6 +417,7 @@ int vrad_env_upload_tree(vrad_env* e, int n_nodes, const int32_t* children, cons
 }
 
 int vrad_env_stats(vrad_env* e, int* n_nodes, int* n_idx, int* n_tris, int* max_depth, int* n_leaves, float aabb[6], double* build_seconds) {
+    VRAD_MULTI_RANK0(e);
     if (!e) return VRAD_E_INVALID;
     if (!e->built) { set_error("vrad_env_stats: not built"); return VRAD_E_STATE; }
     if (n_nodes) *n_nodes = (int)e->tree.children.size();
@@ -417,6 +431,7 @@ int vrad_env_stats(vrad_env* e, int* n_nodes, int* n_idx, int* n_tris, int* max_
 }
 
 int vrad_env_download_tree(vrad_env* e, int32_t* children, float* split, int32_t* tri_index, vrad_tri48* tris) {
+    VRAD_MULTI_RANK0(e);
     if (!e) return VRAD_E_INVALID;
     if (!e->built) { set_error("vrad_env_download_tree: not built"); return VRAD_E_STATE; }
     // read back from the device copy so the test sees what the kernels see
@@ -450,6 +465,7 @@ int vrad_env_download_tree(vrad_env* e, int32_t* children, float* split, int32_t
 int vrad_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, const float* oz, const float* dx,
                     const float* dy, const float* dz, const float* tmin, const float* tmax, int32_t skip_id,
                     int32_t* hit_tri, int32_t* hit_sid, float* hit_t) {
+    VRAD_MULTI(e, group_trace_rays(e, n, ox, oy, oz, dx, dy, dz, tmin, tmax, skip_id, hit_tri, hit_sid, hit_t));
     if (!e || n < 0 || (n > 0 && (!ox || !oy || !oz || !dx || !dy || !dz || !tmax))) { set_error("vrad_trace_rays: bad arguments"); return VRAD_E_INVALID; }
     if (!e->built) { set_error("vrad_trace_rays: acceleration structure not built"); return VRAD_E_STATE; }
     if (n == 0) return VRAD_OK;
@@ -476,6 +492,7 @@ int vrad_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, co
 
 int vrad_trace4(vrad_env* e, const float origin_xyz4[12], const float dir_xyz4[12], const float tmin[4], const float tmax[4],
                 int32_t skip_id, int32_t hit_ids[4], float hit_dist[4], float normal_xyz4[12]) {
+    VRAD_MULTI_RANK0(e);            // one packet: a latency call, any rank answers it
     if (!e || !origin_xyz4 || !dir_xyz4 || !tmin || !tmax || !hit_ids || !hit_dist) { set_error("vrad_trace4: bad arguments"); return VRAD_E_INVALID; }
     if (!e->built) { set_error("vrad_trace4: acceleration structure not built"); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -485,8 +502,10 @@ int vrad_trace4(vrad_env* e, const float origin_xyz4[12], const float dir_xyz4[1
     const void* d_in; bool hh;
     int rc = stage_in(e, 0, h_in, sizeof(h_in), &d_in, &hh);
     if (rc) return rc;
+    // the 80-byte result block (ids, distances, normals) always lands in the handle's scratch: hit_ids is a 16-byte buffer of the
+    // caller's, host or device, and only its own 4 values are written through it
     void* d_out;
-    if ((rc = stage_out(e, 1, hit_ids, 4 * (4 + 4 + 12), &d_out, &hh))) return rc;
+    if ((rc = scratch_get(e, 1, 4 * (4 + 4 + 12), &d_out))) return rc;
     const float* f = (const float*)d_in;
     int32_t* o_tri = (int32_t*)d_out; float* o_t = (float*)d_out + 4; float* o_n = (float*)d_out + 8;
     rc = launch_trace_rays(e, 4, f, f + 4, f + 8, f + 12, f + 16, f + 20, f + 24, f + 28, skip_id, o_tri, nullptr, o_t, o_n);
@@ -494,12 +513,18 @@ int vrad_trace4(vrad_env* e, const float origin_xyz4[12], const float dir_xyz4[1
     float h_out[20];
     VRAD_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-    memcpy(hit_ids, h_out, 16); memcpy(hit_dist, h_out + 4, 16);
-    if (normal_xyz4) memcpy(normal_xyz4, h_out + 8, 48);
+    auto put = [&](void* dst, const float* src, size_t bytes) -> cudaError_t {
+        if (is_device_ptr(dst)) return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+        memcpy(dst, src, bytes); return cudaSuccess;
+    };
+    VRAD_CUDA_CHECK(put(hit_ids, h_out, 16));
+    VRAD_CUDA_CHECK(put(hit_dist, h_out + 4, 16));
+    if (normal_xyz4) VRAD_CUDA_CHECK(put(normal_xyz4, h_out + 8, 48));
     return VRAD_OK;
 }
 
 int vrad_test_lines(vrad_env* e, int64_t n, const float* start_xyz_soa, const float* stop_xyz_soa, int sky_mode, uint32_t* vis_bits) {
+    VRAD_MULTI(e, group_test_lines(e, n, start_xyz_soa, stop_xyz_soa, sky_mode, vis_bits));
     if (!e || n < 0 || (n > 0 && (!start_xyz_soa || !stop_xyz_soa || !vis_bits))) { set_error("vrad_test_lines: bad arguments"); return VRAD_E_INVALID; }
     if (!e->built) { set_error("vrad_test_lines: acceleration structure not built"); return VRAD_E_STATE; }
     if (n == 0) return VRAD_OK;
@@ -511,7 +536,7 @@ int vrad_test_lines(vrad_env* e, int64_t n, const float* start_xyz_soa, const fl
         // large host batch: overlap the H2D copies with the traversal
         void* d_o;
         if ((rc = stage_out(e, 2, vis_bits, wb, &d_o, &ho))) return rc;
-        if ((rc = launch_test_lines_pipelined(e, n, start_xyz_soa, stop_xyz_soa, nullptr, sky_mode, (uint32_t*)d_o))) return rc;
+        if ((rc = launch_test_lines_pipelined(e, n, start_xyz_soa, stop_xyz_soa, n, nullptr, sky_mode, (uint32_t*)d_o))) return rc;
         if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
         return sync_if_needed(e, true);
     }
@@ -526,6 +551,7 @@ int vrad_test_lines(vrad_env* e, int64_t n, const float* start_xyz_soa, const fl
 
 /* endpoint table for vrad_test_lines_indexed: patch origins, light origins, luxel samples ... (xyz interleaved) */
 int vrad_points_upload(vrad_env* e, int64_t n_points, const float* xyz3) {
+    VRAD_MULTI(e, group_points_upload(e, n_points, xyz3));
     if (!e || n_points <= 0 || !xyz3) { set_error("vrad_points_upload: bad arguments"); return VRAD_E_INVALID; }
     if (n_points > 0x7fffffff) { set_error("vrad_points_upload: %lld points exceed the int32 index range", (long long)n_points); return VRAD_E_INVALID; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -546,6 +572,7 @@ int vrad_points_upload(vrad_env* e, int64_t n_points, const float* xyz3) {
 }
 
 int vrad_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs2, int sky_mode, uint32_t* vis_bits) {
+    VRAD_MULTI(e, group_test_lines_indexed(e, n, pairs2, sky_mode, vis_bits));
     if (!e || n < 0 || (n > 0 && (!pairs2 || !vis_bits))) { set_error("vrad_test_lines_indexed: bad arguments"); return VRAD_E_INVALID; }
     if (!e->built) { set_error("vrad_test_lines_indexed: acceleration structure not built"); return VRAD_E_STATE; }
     if (e->n_points == 0) { set_error("vrad_test_lines_indexed: no point table (vrad_points_upload first)"); return VRAD_E_STATE; }
@@ -558,7 +585,7 @@ int vrad_test_lines_indexed(vrad_env* e, int64_t n, const int32_t* pairs2, int s
     // out-of-bounds read): a host pass over the pairs would cost more than the PCIe copy it precedes.
     if ((rc = stage_out(e, 2, vis_bits, wb, &d_o, &ho))) return rc;
     if (host_pairs && n >= ((int64_t)1 << 22)) {
-        if ((rc = launch_test_lines_pipelined(e, n, nullptr, nullptr, pairs2, sky_mode, (uint32_t*)d_o))) return rc;
+        if ((rc = launch_test_lines_pipelined(e, n, nullptr, nullptr, 0, pairs2, sky_mode, (uint32_t*)d_o))) return rc;
         if ((rc = finish_out(e, vis_bits, d_o, wb, ho))) return rc;
         int bad = 0;
         if ((rc = read_bad_index_count(e, &bad))) return rc;         // synchronises

@@ -37,12 +37,20 @@ def _f32(a):
 
 
 class Environment:
-    def __init__(self, device: int = 0, rank: int = 0, world: int = 1):
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, devices=None):
+        """devices = a list of CUDA ordinals: ONE handle that drives them all from this process (vrad_env_create_multi) --
+        host buffers only, calls synchronous; the rank / world arguments are for the one-process-per-GPU form."""
         self._l = _lib.load()
         self._h = C.c_void_p()
-        cfg = VradConfig(device, rank, world, 0)
-        check(self._l.vrad_env_create(C.byref(cfg), C.byref(self._h)))
-        self.device, self.rank, self.world = device, rank, world
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            mc = _lib.VradMultiConfig(len(devices), (C.c_int * 8)(*(devices + [0] * (8 - len(devices)))), 0)
+            check(self._l.vrad_env_create_multi(C.byref(mc), C.byref(self._h)))
+            device, rank, world = devices[0], 0, 1
+        else:
+            cfg = VradConfig(device, rank, world, 0)
+            check(self._l.vrad_env_create(C.byref(cfg), C.byref(self._h)))
+        self.device, self.rank, self.world, self.devices = device, rank, world, devices
         self.n_patches = 0
         self._pending_ids, self._pending_verts, self._pending_flags = [], [], []
 
@@ -380,8 +388,8 @@ class Environment:
         check(self._l.vrad_comm_init(self._h, C.c_char_p(unique_id)))
 
 
-def environment_from_scene(scene, device=0, rank=0, world=1, with_patches=True) -> Environment:
-    env = Environment(device, rank, world)
+def environment_from_scene(scene, device=0, rank=0, world=1, with_patches=True, devices=None) -> Environment:
+    env = Environment(device, rank, world, devices=devices)
     env.add_triangles(scene.tri_ids, scene.tri_verts, scene.tri_flags)
     env.setup_acceleration_structure()
     if with_patches and scene.patch_origin is not None:

@@ -30,7 +30,7 @@ SYMBOLS = [
     "vrad_light_for_string", "vrad_lights_from_entities", "vrad_lights_from_patches",
     "vrad_bump_normals", "vrad_patches_set_bump", "vrad_bounce_bump_totals",
     "vrad_env_build_fast", "vrad_kd_build_binned_host",
-    "vrad_points_upload", "vrad_test_lines_indexed", "vrad_env_set_option",
+    "vrad_points_upload", "vrad_test_lines_indexed", "vrad_env_set_option", "vrad_env_create_multi",
 ]
 
 # == vrad_face_patch in include/vrad_cuda.h
@@ -51,6 +51,10 @@ assert LIGHT_ENTITY_DTYPE.itemsize == 124
 
 class VradConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("flags", C.c_int)]
+
+
+class VradMultiConfig(C.Structure):
+    _fields_ = [("n_devices", C.c_int), ("devices", C.c_int * 8), ("flags", C.c_int)]
 
 
 class VradError(RuntimeError):
