@@ -93,9 +93,12 @@ int  vrad_env_set_stream(vrad_env*, void* cuda_stream);
 int  vrad_env_set_async(vrad_env*, int async);
 /* tuning switches, by name (defaults come from the environment variables in parentheses):
  *   "k1_sort"       (VRAD_K1_SORT)      order segment batches by start cell / direction octant / end cell before tracing:
- *                                       -1 = batches of >= 65536 segments (default), 0 = never, 1 = always
+ *                                       -1 = batches of >= 65536 segments on scenes of at most 4 MB (default), 0 = never, 1 = always
+ *   "k1_key"        (VRAD_K1_KEY)       layout of the 30-bit sort key: -1 by the shape of the scene box (default), 0 start-major Morton,
+ *                                       1 six-dimensional Morton, 2 cubic start cells
+ *   "k1_stream"     (VRAD_K1_STREAM)    unordered batches through the persistent streaming kernel (default 1; 0 = per-chunk kernels)
  *   "k1_top"        (VRAD_K1_TOP)       stage the top of the kd tree in shared memory: 0 = off (default), n = node budget
- *   "k4_seg"        (VRAD_K4_SEG)       entries per gather work item; longer transfer rows are split (default 2048)
+ *   "k4_seg"        (VRAD_K4_SEG)       entries per gather work item; longer transfer rows are split (default 16384)
  *   "k4_long_first" (VRAD_K4_ORDER=long) gather work items longest first
  *   "k4_persist"    (VRAD_K4_PERSIST)   gather grid = one block per resident slot over equal-work item ranges (default 1);
  *                                       0 = 8 items per block, as many blocks as that takes

@@ -125,6 +125,28 @@ def main():
         env.close(); del d_a, d_b, d_bits
         flush()
 
+    # ---------------- K1 on S2 (49,586 tris: 3 MB of nodes and triangles) ----------------
+    s2k = scenes.multi_room()
+    env = environment_from_scene(s2k, with_patches=False)
+    env.set_stream(stream); env.set_async(True)
+    n2 = 1 << 24
+    a2, b2 = scenes.shadow_segments(s2k, n2, seed=0xC2)
+    d_a, d_b = torch.from_numpy(a2).to(dev), torch.from_numpy(b2).to(dev)
+    d_bits = torch.empty(n2 // 32, dtype=torch.int32, device=dev)
+    k2r = {}
+    ref = None
+    for sort in (0, 1, -1):
+        env.set_option("k1_sort", sort)
+        ms = timed(lambda: env.test_lines(d_a, d_b, out=d_bits))
+        got = d_bits.cpu().numpy()
+        if ref is None:
+            ref = got
+        k2r[f"sort{sort}"] = {"ms": ms, "seg_per_s": n2 / ms * 1e3, "same_bits": bool(np.array_equal(got, ref))}
+        print("S2 rays", sort, ms, flush=True)
+    res["k1_s2"] = k2r
+    env.close(); del d_a, d_b, d_bits
+    flush()
+
     # ---------------- K4 on S2 ----------------
     if not args.skip_k4:
         s2 = scenes.multi_room()

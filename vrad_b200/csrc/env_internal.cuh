@@ -192,7 +192,7 @@ struct EnvOptions {
     int k1_key = -1;       // VRAD_K1_KEY: layout of the sort key (k1_trace.cu: -1 by the scene box, 0 start-major Morton, 1 6-D Morton, 2 cubic start cells)
     int k1_stream = 1;     // VRAD_K1_STREAM: unordered batches also go through the persistent streaming kernel (0 = the per-chunk kernels)
     int k1_top = 0;        // VRAD_K1_TOP: stage the top levels of the kd tree in shared memory (0 = off, else node budget)
-    int k4_seg = 2048;     // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)
+    int k4_seg = 16384;    // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
     int k4_block = 192;    // VRAD_K4_BLOCK: threads per work-item gather block: 192 (6 blocks/SM, 56 registers) or 256 (5 blocks/SM, 48 registers: spills in the loop)
     int k4_pool = 12;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early
@@ -249,6 +249,7 @@ struct vrad_env {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     vrad::DevBuf<float> d_stage[2];
+    uint32_t* h_one = nullptr;         // pinned word holding 1: the source of the chunk-arrival flag copies
 
     // scratch for staging host pointers
     std::vector<vrad::DevBuf<unsigned char>> scratch;

@@ -141,7 +141,9 @@ int group_test_lines(vrad_env* g, int64_t n, const float* a, const float* b, int
         // x[n] y[n] z[n] blocks of the whole batch: this rank reads [s0, s1) of each (host stride n)
         if ((rcc = launch_test_lines_pipelined(c, m, a + s0, b + s0, n, nullptr, sky_mode, (uint32_t*)d_o))) return rcc;
         VRAD_CUDA_CHECK(cudaMemcpyAsync(bits + (s0 >> 5), d_o, wb, cudaMemcpyDeviceToHost, c->stream));
-        VRAD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        int bad = 0;
+        if ((rcc = read_bad_index_count(c, &bad))) return rcc;        // synchronises
+        if (bad) { set_error("vrad_test_lines: the segment copy did not arrive on the device"); return (int)VRAD_E_CUDA; }
         return (int)VRAD_OK;
     });
 }

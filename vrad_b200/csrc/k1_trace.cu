@@ -232,12 +232,23 @@ k1_sort_keys(int64_t n, SegSource src, SortGrid G, float4* __restrict__ rec, uin
 // kSortedRange positions from a global counter: neighbouring positions cost alike (that is the point of the order), so
 // fixed per-warp chunks would leave the kernel waiting for the warps that drew the expensive corner of the scene
 // (r02, first form: 512-position chunks, S3 map, 2^22 segments: 7.2 ms sorted against 5.2 ms unsorted).
+// one thread waits until a chunk of a host batch has landed (see `arrive` below); out of line: its registers are not the traversal's
+__device__ __noinline__ void wait_for_chunk(const uint32_t* flag, uint32_t* err) {
+    const long long t0 = clock64();
+    uint32_t v;
+    do {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (!v && clock64() - t0 > (1LL << 31)) { atomicExch(err, 1u); break; }
+    } while (!v);
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+}
+
 constexpr int kSortedRange = 128;
 constexpr int kSortedBlocksPerSM = 12;       // 40 registers: 48 resident warps (the traversal waits on memory: on the 1 M-triangle map L1 hits are 44 %)
 template <bool SKY, bool TOP, bool INDEXED>
 __global__ void __launch_bounds__(kTraceBlock, TOP ? 8 : kSortedBlocksPerSM)
 k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, const float4* __restrict__ rec, SegSource src, uint32_t* __restrict__ bits,
-                     unsigned long long* __restrict__ counter) {
+                     unsigned long long* __restrict__ counter, const uint32_t* arrive, int chunk_shift, uint32_t* arrive_err) {
     extern __shared__ int2 top_s[];
     if (TOP) {
         for (int i = threadIdx.x; i < S.n_top; i += blockDim.x) top_s[i] = __ldg(&S.top[i]);
@@ -266,11 +277,26 @@ k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, c
         if (SKY && occluded) occluded = (__float_as_int(__ldg(&S.q2[tri]).z) & 0x01000000) == 0;
         if (!occluded) atomicOr(&bits[i >> 5], 1u << ((int)i & 31));
     };
+    // `arrive` (host batches): the batch is still on its way over PCIe while this kernel runs -- chunk k of 2^chunk_shift
+    // positions may be read once arrive[k] is set (a 4-byte copy queued behind the chunk's data on the copy stream; chunks land in
+    // order).  ONE launch serves the whole batch: no per-chunk kernel, no per-chunk tail.  arrive[n_chunks] is the error word: a
+    // wait of ~2^31 cycles gives up (the copy stream died) and the entry point reports it.
+    __shared__ int ready_s[kTraceWarps];          // highest chunk this warp has seen arrive (kept out of the traversal's registers)
+    if ((threadIdx.x & 31) == 0) ready_s[threadIdx.x >> 5] = -1;
+    __syncwarp();
     auto more = [&](int64_t& next, int64_t& end) {
         unsigned long long c = 0;
         if ((threadIdx.x & 31) == 0) c = atomicAdd(counter, (unsigned long long)kSortedRange);
         c = __shfl_sync(0xffffffffu, c, 0);
         if ((int64_t)c >= n) return false;
+        if (arrive) {
+            const int ch = (int)(c >> chunk_shift);
+            if (ch > ready_s[threadIdx.x >> 5]) {
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) { wait_for_chunk(arrive + ch, arrive_err); ready_s[threadIdx.x >> 5] = ch; }
+                __syncwarp();
+            }
+        }
         next = (int64_t)c; end = (int64_t)c + kSortedRange < n ? (int64_t)c + kSortedRange : n;
         return true;
     };
@@ -343,9 +369,18 @@ int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, 
 // Order policy: VRAD_K1_SORT=0 never, 1 always, unset = batches of at least kSortMin segments.
 constexpr int64_t kSortMin = (int64_t)1 << 16;
 constexpr int64_t kSortBatch = (int64_t)1 << 24;          // segments ordered at a time (bounds the scratch: 48 B per segment)
+// Automatic rule: order big batches on scenes whose tree and triangles fit one SM's L1 (256 KB).  There the traversal is purely
+// issue-bound and ordering halves the warp instructions (r02, S1 box room, 58 KB: 15.0 instead of 8.7 threads per instruction,
+// 2.66 ms against 3.23 ms per 2^24 segments, sort included).  It stops paying as soon as the scene spills out of L1: on the
+// 49,586-triangle map (3 MB) 2.95 ms ordered against 2.87 ms unordered; on the 1 M-triangle map (56 MB) the traversal waits on
+// memory, the ordered warps still diverge in the leaves (8.0 threads per instruction either way) and the sort is not recovered:
+// 4.28 ms ordered against 3.87 ms unordered per 2^22 segments.
+constexpr size_t kSortSceneBytes = (size_t)256 << 10;
 static bool want_sort(const vrad_env* e, int64_t n) {
     const int mode = e->opt.k1_sort;
-    return mode < 0 ? n >= kSortMin : mode != 0;
+    if (mode >= 0) return mode != 0;
+    const size_t scene_bytes = (size_t)e->scene.n_nodes * 8 + (size_t)e->scene.n_tris * 48 + (size_t)e->scene.n_idx * 4;
+    return n >= kSortMin && scene_bytes <= kSortSceneBytes;
 }
 
 static SortGrid sort_grid(const vrad_env* e) {
@@ -374,7 +409,8 @@ static SortGrid sort_grid(const vrad_env* e) {
 
 // Enqueues the traversal of n segments (coordinates or index pairs) on e->stream; `bits` may be written with atomics
 // (sorted order) or whole words.  *launches += kernels enqueued.  n must start on a 32-segment boundary of the output.
-static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int sky_mode, uint32_t* bits, int* launches, bool host_chunk = false) {
+static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int sky_mode, uint32_t* bits, int* launches, bool host_chunk = false,
+                              const uint32_t* arrive = nullptr, int chunk_shift = 0, uint32_t* arrive_err = nullptr) {
     const bool indexed = src.pairs != nullptr;
     // chunks of a host batch are traced as they arrive unless ordering is forced: the call is bound by PCIe or close to it, and a
     // sort per 2^21-segment chunk costs more than it saves (r02: 5.7 ms ordered against 5.0 ms per 2^24 index pairs)
@@ -425,7 +461,7 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         }
         const size_t sm = (size_t)e->scene.n_top * sizeof(int2);
         const uint32_t* pm = (const uint32_t*)d_i1; const float4* rc4 = indexed ? nullptr : (const float4*)d_rec; unsigned long long* ctr = (unsigned long long*)d_ctr;
-#define VRAD_SORTED(SKY, TOP, IDX) k1_test_lines_sorted<SKY, TOP, IDX><<<sgrid, kTraceBlock, (TOP) ? sm : 0, e->stream>>>(e->scene, m, pm, rc4, sub, out, ctr)
+#define VRAD_SORTED(SKY, TOP, IDX) k1_test_lines_sorted<SKY, TOP, IDX><<<sgrid, kTraceBlock, (TOP) ? sm : 0, e->stream>>>(e->scene, m, pm, rc4, sub, out, ctr, arrive ? arrive + (c0 >> chunk_shift) : nullptr, chunk_shift, arrive_err)
         if (indexed) {
             if (sm) { if (sky_mode) VRAD_SORTED(true, true, true); else VRAD_SORTED(false, true, true); }
             else { if (sky_mode) VRAD_SORTED(true, false, true); else VRAD_SORTED(false, false, true); }
@@ -456,6 +492,9 @@ __global__ void k1_count_bad_indices(int64_t n2, const int32_t* __restrict__ idx
     const unsigned m = __ballot_sync(0xffffffffu, b);
     if (m && (threadIdx.x & 31) == 0) atomicAdd(bad, __popc(m));
 }
+
+// a streaming launch that gave up waiting for its input marks the batch as bad (the index-pair entry point reads the count back)
+__global__ void k1_fold_arrival_error(const uint32_t* __restrict__ err, int* __restrict__ bad) { if (*err && bad) atomicAdd(bad, 1 << 30); }
 
 // index pairs on the device: count the indices outside the point table (synchronises the stream)
 int check_pairs_on_device(vrad_env* e, int64_t n, const int32_t* d_pairs, int* bad_out) {
@@ -498,6 +537,48 @@ int launch_test_lines_pipelined(vrad_env* e, int64_t n, const float* h_a, const 
     // 2^21.  Whichever side is slower -- PCIe at 24 B per segment, the kernel at 8 -- the call costs that side plus one chunk of
     // the other.  (r02: chunks doubling up to 2^23 were worse for both forms -- a copy twice as long as the kernel before it
     // stalls the kernel stream, and a copy-bound call ends with the whole last kernel exposed.)
+    // Unordered batches up to 2^26 segments go through ONE launch of the streaming kernel, which follows the copy stream chunk by
+    // chunk (2^19 segments each) through arrival flags -- see k1_test_lines_sorted.
+    const bool stream_one_launch = e->opt.k1_stream && e->opt.k1_sort <= 0 && n <= ((int64_t)1 << 26) && e->h_one;
+    if (stream_one_launch) {
+        const int kShift = h_pairs ? 19 : 21;          // 4 MB of pairs, 6 x 8 MB of coordinates per chunk: big enough for the copy engine
+        const int64_t chunk = (int64_t)1 << kShift, n_chunks = (n + chunk - 1) >> kShift;
+        void *d_stage, *d_arrive, *d_bad = nullptr;
+        int rc;
+        if ((rc = scratch_get(e, 20, (size_t)(h_pairs ? 8 : 24) * (size_t)n, &d_stage)) || (rc = scratch_get(e, 21, (size_t)(n_chunks + 1) * 4, &d_arrive))) return rc;
+        if ((rc = scratch_get(e, 18, 4, &d_bad))) return rc;
+        timing_begin(e);
+        int launches = 0;
+        VRAD_CUDA_CHECK(cudaMemsetAsync(d_arrive, 0, (size_t)(n_chunks + 1) * 4, e->stream));
+        VRAD_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, 4, e->stream));
+        // the copies may start once earlier work on the main stream is done with the staging buffer and the flags are zero
+        VRAD_CUDA_CHECK(cudaEventRecord(e->ev_done[0], e->stream));
+        VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, e->ev_done[0], 0));
+        float* st = (float*)d_stage;
+        for (int64_t c = 0; c < n_chunks; c++) {
+            const int64_t c0 = c << kShift, m = std::min(chunk, n - c0);
+            if (h_pairs) VRAD_CUDA_CHECK(cudaMemcpyAsync((int32_t*)d_stage + 2 * c0, h_pairs + 2 * c0, (size_t)m * 8, cudaMemcpyHostToDevice, e->copy_stream));
+            else for (int k = 0; k < 3; k++) {
+                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + k * n + c0, h_a + k * host_stride + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
+                VRAD_CUDA_CHECK(cudaMemcpyAsync(st + (3 + k) * n + c0, h_b + k * host_stride + c0, (size_t)m * 4, cudaMemcpyHostToDevice, e->copy_stream));
+            }
+            VRAD_CUDA_CHECK(cudaMemcpyAsync((uint32_t*)d_arrive + c, e->h_one, 4, cudaMemcpyHostToDevice, e->copy_stream));
+        }
+        VRAD_CUDA_CHECK(cudaEventRecord(e->ev_copied[0], e->copy_stream));
+        SegSource src{};
+        if (h_pairs) { src.pairs = (const int2*)d_stage; src.pts = e->d_points.p; src.n_pts = (int)e->n_points; }
+        else { src.a = st; src.b = st + 3 * n; src.stride = n; }
+        rc = enqueue_test_lines(e, n, src, sky_mode, d_bits, &launches, true, (const uint32_t*)d_arrive, kShift, (uint32_t*)d_arrive + n_chunks);
+        if (rc) return rc;
+        // nothing later on the main stream may touch the staging buffer before the last copy is in (it is, once the kernel is done;
+        // the wait makes the stream order say so too)
+        VRAD_CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_copied[0], 0));
+        if (h_pairs) { k1_count_bad_indices<<<(int)((2 * n + 255) / 256), 256, 0, e->stream>>>(2 * n, (const int32_t*)d_stage, (int)e->n_points, (int*)d_bad); launches++; }
+        k1_fold_arrival_error<<<1, 1, 0, e->stream>>>((const uint32_t*)d_arrive + n_chunks, (int*)d_bad);
+        timing_end(e, launches);
+        VRAD_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
     constexpr int64_t kChunkMin = (int64_t)1 << 19, kChunk = (int64_t)1 << 21;
     const int64_t stage_cap = std::min<int64_t>(kChunk, std::max<int64_t>(kChunkMin, n));
     for (int s = 0; s < 2; s++)
