@@ -134,6 +134,7 @@ int  vrad_env_build(vrad_env*);
  * depends on the planes.  The finished tree is validated like an uploaded one before any kernel walks it. */
 #define VRAD_BUILD_ON_DEVICE 0
 #define VRAD_BUILD_ON_HOST   1
+#define VRAD_BUILD_AUTO      2   /* the device from 10,000 triangles up, the host's cores below (where the device build is all launch latency) */
 int  vrad_env_build_fast(vrad_env*, int where);
 /* the same builder without an environment (host-only helper; no device needed): arrays in reference layout.  children / split /
  * tri_index may be NULL to size the buffers (*n_nodes, *n_idx); aabb and max_depth may be NULL. */

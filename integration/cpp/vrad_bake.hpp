@@ -348,7 +348,7 @@ inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vect
     const int N = P.tree.size();
     std::vector<uint8_t> triFlags(P.tris.ids.size(), 0);
     fatal_on(vrad_env_add_triangles(env.handle(), static_cast<int>(P.tris.ids.size()), P.tris.ids.data(), P.tris.verts9.data(), triFlags.data()), "vrad_env_add_triangles");
-    if (fastTree) fatal_on(vrad_env_build_fast(env.handle(), VRAD_BUILD_ON_DEVICE), "vrad_env_build_fast");
+    if (fastTree) fatal_on(vrad_env_build_fast(env.handle(), VRAD_BUILD_AUTO), "vrad_env_build_fast");
     else fatal_on(vrad_env_build(env.handle()), "vrad_env_build");
     if (textureShadows) fatal_on(vrad_set_light_trace_flags(env.handle(), VRAD_TL_TEXTURE_SHADOWS), "vrad_set_light_trace_flags");
     const bool haveVis = !P.pvs.empty();

@@ -91,7 +91,7 @@ func devicesFromEnv() []int {
 // environment.Flags: the binned-SAH tree is built on the GPU from the triangles already handed over with vrad_env_add_triangles /
 // vrad_env_add_bsp (vrad_env_build_fast, include/vrad_cuda.h).
 func (environment *Environment) SetupAccelerationStructureFastCUDA() {
-	check(C.vrad_env_build_fast(environment.cuda.h, C.VRAD_BUILD_ON_DEVICE), "vrad_env_build_fast")
+	check(C.vrad_env_build_fast(environment.cuda.h, C.VRAD_BUILD_AUTO), "vrad_env_build_fast")
 }
 
 func (environment *Environment) SetupAccelerationStructureCUDA() {

@@ -108,9 +108,9 @@ def kd_part(dev, device, stream):
         d_sa, d_sb = torch.from_numpy(sa).to(dev), torch.from_numpy(sb).to(dev)
         d_bits = torch.empty((nseg + 31) // 32, dtype=torch.int32, device=dev)
         row = {"triangles": scn.n_tris, "segments": nseg}
-        for kind in ("exact_host", "binned_device"):
+        for kind in ("exact_host", "binned_device", "binned_auto"):      # auto = VRAD_BUILD_AUTO: the host's cores below 10,000 triangles
             ek = Environment(device); ek.add_triangles(scn.tri_ids, scn.tri_verts, scn.tri_flags)
-            secs = ek.setup_acceleration_structure() if kind == "exact_host" else ek.build_fast()
+            secs = ek.setup_acceleration_structure() if kind == "exact_host" else ek.build_fast(None if kind == "binned_auto" else False)
             st = ek.stats()
             ek.set_stream(stream); ek.set_async(True)
             for _ in range(2):
@@ -119,7 +119,8 @@ def kd_part(dev, device, stream):
             for _ in range(5):
                 ek.test_lines(d_sa, d_sb, out=d_bits)
             e1.record(); torch.cuda.synchronize()
-            row[kind] = {"build_seconds": secs, "nodes": st["n_nodes"], "index_entries": st["n_idx"], "max_depth": st["max_depth"],
+            row[kind] = {"build_seconds": secs, "nodes": st["n_nodes"], "leaves": st["n_leaves"], "index_entries": st["n_idx"], "max_depth": st["max_depth"],
+                         "triangles_per_leaf": st["n_idx"] / max(1, st["n_leaves"]),
                          "segments_per_sec": nseg / (e0.elapsed_time(e1) / 5 * 1e-3), "visible": int(np.unpackbits(d_bits.cpu().numpy().view(np.uint8)).sum())}
             ek.close()
         out[name] = row

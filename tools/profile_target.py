@@ -22,8 +22,8 @@ elif what in ("r2k1", "r2k1s3"):
     a, b = scenes.shadow_segments(s, n, seed=0xC5 if big else 0xC0FFEE)
     ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     out = torch.empty(n // 32, dtype=torch.int32, device="cuda")
-    for sort, top in ((0, 0), (1, 0), (0, 1023)):
-        env.set_option("k1_sort", sort); env.set_option("k1_top", top)
+    for sort, top, st in ((0, 0, 1), (1, 0, 1), (0, 1023, 1), (0, 0, 0)):      # streaming unordered, ordered, top levels staged, round-1 per-chunk kernel
+        env.set_option("k1_sort", sort); env.set_option("k1_top", top); env.set_option("k1_stream", st)
         for _ in range(2): env.test_lines(ta, tb, out=out)
 elif what == "r2k4":
     # round 2: the multi-GPU gather kernel on the rank-3 slice of a simulated world-8 run, and the single-GPU kernel on the whole matrix
@@ -36,6 +36,31 @@ elif what == "r2k4":
         e0 = torch.full((s.n_patches, 3), 100.0, device="cuda"); o = torch.empty_like(e0)
         env.bounce(e0, 6, out=o, want_added=False)
         env.close()
+elif what == "k3":
+    # K3 at both ends: 8 point/spot lights on the S1 luxels (C2), sun + 162-direction sky ambient on the 2 M luxels of S3 (C5)
+    s = scenes.box_room(); env = environment_from_scene(s, with_patches=False)
+    pos, nrm = torch.from_numpy(s.luxel_pos).cuda(), torch.from_numpy(s.luxel_normal).cuda()
+    for _ in range(2): env.direct_light(pos, nrm, s.lights)
+    env.close()
+    s = scenes.outdoor(); env = environment_from_scene(s, with_patches=False)
+    env.set_sky_dirs(np.loadtxt(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vrad_b200", "data", "anorms.txt"), dtype=np.float32))
+    pos, nrm = torch.from_numpy(s.luxel_pos).cuda(), torch.from_numpy(s.luxel_normal).cuda()
+    for _ in range(2): env.direct_light(pos, nrm, s.lights)
+elif what == "bump":
+    # bump-mapped (4-normal) gather on the C4 map: every patch bump-mapped, 4 bounces
+    from vrad_b200.environment import bump_normals
+    s = scenes.multi_room(); env = environment_from_scene(s)
+    N = s.n_patches
+    basis = np.zeros((N, 3, 3), np.float32)
+    for f in np.unique(s.patch_normal, axis=0):
+        sel = np.all(s.patch_normal == f, axis=1)
+        sv = np.array([0, 1, 0], np.float32) if abs(f[0]) > 0.5 else np.array([1, 0, 0], np.float32)
+        tv = np.cross(f, sv).astype(np.float32)
+        basis[sel] = bump_normals(sv, tv, f, f)
+    env.set_bump(np.ones(N, np.uint8), basis)
+    env.build_transfers(s.pvs)
+    e0 = torch.full((N, 3), 100.0, device="cuda")
+    env.bounce(e0, 4)
 elif what == "sky":
     from vrad_b200.environment import Environment
     s = scenes.sky_room(); m = s.meta

@@ -352,7 +352,7 @@ int vrad_env_build(vrad_env* e) {
 
 int vrad_env_build_fast(vrad_env* e, int where) {
     VRAD_MULTI(e, group_build(e, 1, where));
-    if (!e || (where != VRAD_BUILD_ON_DEVICE && where != VRAD_BUILD_ON_HOST)) { set_error("vrad_env_build_fast: bad arguments"); return VRAD_E_INVALID; }
+    if (!e || (where != VRAD_BUILD_ON_DEVICE && where != VRAD_BUILD_ON_HOST && where != VRAD_BUILD_AUTO)) { set_error("vrad_env_build_fast: bad arguments"); return VRAD_E_INVALID; }
     if (e->built) { set_error("vrad_env_build_fast: already built"); return VRAD_E_STATE; }
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     auto t0 = std::chrono::steady_clock::now();
@@ -362,7 +362,7 @@ int vrad_env_build_fast(vrad_env* e, int where) {
     // below ~10k triangles the level-by-level device build is all launch latency (r02: 996 triangles, 8.5 ms on the device against
     // 2.2 ms for the exact builder on the host): the same functors run on the host's cores instead -- the same tree by construction
     constexpr int kDeviceBuildMin = 10000;
-    if (where == VRAD_BUILD_ON_DEVICE && n < kDeviceBuildMin) where = VRAD_BUILD_ON_HOST;
+    if (where == VRAD_BUILD_AUTO) where = n < kDeviceBuildMin ? VRAD_BUILD_ON_HOST : VRAD_BUILD_ON_DEVICE;
     int rc = where == VRAD_BUILD_ON_HOST ? build_kd_tree_binned_host(e->h_verts.data(), n, e->tree, &why)
                                          : build_kd_tree_binned_device(e->stream, e->h_verts.data(), n, e->tree, &launches, &why);
     if (rc) { set_error("vrad_env_build_fast: %s", why); return rc; }

@@ -131,10 +131,11 @@ class Environment:
         check(self._l.vrad_env_build(self._h))
         return self.stats()["build_seconds"]
 
-    def build_fast(self, on_host: bool = False):
-        """RTE_FLAGS_FAST_TREE_GENERATION (raytracer/constants.go:5): the binned-SAH builder, on the device or on the host's cores."""
+    def build_fast(self, on_host: bool | None = False):
+        """RTE_FLAGS_FAST_TREE_GENERATION (raytracer/constants.go:5): the binned-SAH builder, on the device, on the host's cores, or
+        (on_host=None) wherever it is faster for the triangle count."""
         self._flush_pending()
-        check(self._l.vrad_env_build_fast(self._h, C.c_int(1 if on_host else 0)))
+        check(self._l.vrad_env_build_fast(self._h, C.c_int(2 if on_host is None else (1 if on_host else 0))))
         return self.stats()["build_seconds"]
 
     def upload_tree(self, children, split, tri_index, tris, aabb):
