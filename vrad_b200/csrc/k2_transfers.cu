@@ -27,7 +27,9 @@
 #include "env_internal.cuh"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <thread>
 
 namespace vrad {
 
@@ -365,6 +367,10 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     const int N = P.n;
     const int C = pvs ? n_clusters : 1;
+    static const bool phase_timing = getenv("VRAD_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t_begin = now();
     // A patch with cluster -1 (origin and winding points all in solid space, rad/patches/subdivide.go:100-116) is in no cluster's
     // child list upstream: it neither gathers nor is gathered from.  Here it goes to an extra cluster, index C, that sees nothing
     // and that nothing sees -- its row comes out empty and it is in no candidate list -- so the kernels need no special case.
@@ -391,16 +397,26 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     }
     std::vector<std::vector<int32_t>> members(Cx);
     for (int i = 0; i < N; i++) members[rclus[i]].push_back(i);
+    // list sizes first (a C x C pass over the PVS), then every cluster's list filled and sorted on its own -- on as many host
+    // threads as this rank's share of the cores (the lists are the same on every rank; with one thread they were 0.37 s of a
+    // 1.4 s build on the C5 map at 8 ranks, r02)
     std::vector<int64_t> cand_ptr(Cx + 1, 0);
-    std::vector<int32_t> cand_idx;
     for (int c = 0; c < C; c++) {
-        size_t start = cand_idx.size();
-        for (int c2 = 0; c2 < C; c2++)
-            if (!pvs || pvs[(size_t)c * C + c2]) cand_idx.insert(cand_idx.end(), members[c2].begin(), members[c2].end());
-        std::sort(cand_idx.begin() + start, cand_idx.end());
-        cand_ptr[c + 1] = (int64_t)cand_idx.size();
+        int64_t cnt = 0;
+        for (int c2 = 0; c2 < C; c2++) if (!pvs || pvs[(size_t)c * C + c2]) cnt += (int64_t)members[c2].size();
+        cand_ptr[c + 1] = cand_ptr[c] + cnt;
     }
     cand_ptr[Cx] = cand_ptr[C];                                                // the extra cluster's list is empty
+    std::vector<int32_t> cand_idx((size_t)cand_ptr[C]);
+    const int host_threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, e->cfg.world)));
+#pragma omp parallel for schedule(dynamic, 4) num_threads(host_threads)
+    for (int c = 0; c < C; c++) {
+        int32_t* dst = cand_idx.data() + cand_ptr[c];
+        int32_t* p = dst;
+        for (int c2 = 0; c2 < C; c2++)
+            if (!pvs || pvs[(size_t)c * C + c2]) { std::copy(members[c2].begin(), members[c2].end(), p); p += members[c2].size(); }
+        std::sort(dst, p);
+    }
     // hierarchical top-down form: per cluster, the face roots (patches without a parent) of the clusters it sees
     std::vector<int64_t> root_ptr(Cx + 1, 0);
     std::vector<int32_t> root_idx;
@@ -414,6 +430,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
         }
         root_ptr[Cx] = root_ptr[C];
     }
+    const auto t_lists = now();
     const int world = e->cfg.world;
     const int64_t rpr = ((int64_t)N + world - 1) / world;
     int64_t row0 = std::min<int64_t>(N, e->cfg.rank * rpr), row1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
@@ -460,6 +477,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
             fprintf(stderr, " (equal blocks would be %lld rows)\n", (long long)rpr);
         }
     }
+    const auto t_balance = now();
     const int nloc = (int)(row1 - row0);
     std::vector<int64_t> bit_ptr(nloc + 1, 0);
     for (int r = 0; r < nloc; r++) {
@@ -486,6 +504,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     K2_CHECK(cudaMemsetAsync(d_bits.p, 0, (size_t)(nwords + 1) * 4, e->stream));
     if (pvs) K2_CHECK(cudaMemcpyAsync(d_pvs.p, pvs, (size_t)C * C, cudaMemcpyHostToDevice, e->stream));
 
+    const auto t_staged = now();
     static const bool verbose = getenv("VRAD_TIMING") != nullptr;
     cudaEvent_t tv0 = nullptr, tv1 = nullptr;
     if (verbose) { cudaEventCreate(&tv0); cudaEventCreate(&tv1); }
@@ -562,10 +581,15 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     int64_t nnz = 0;
     for (int r = 0; r < nloc; r++) nnz += rl[r];
     T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.rows_serial++;
+    const auto t_kernels = now();
     cleanup();
     int rcp = build_gather_plan(e, rl.data(), nloc);
     if (rcp) return rcp;
     T.ready = true;
+    if (phase_timing)
+        fprintf(stderr, "[vrad] rank %d build_transfers phases: candidate lists (host) %.3f s, row balance %.3f s, staging %.3f s, kernels + readback %.3f s, "
+                        "free + gather plan %.3f s; %zu candidate entries, %lld visibility words\n", e->cfg.rank, secs(t_begin, t_lists), secs(t_lists, t_balance),
+                secs(t_balance, t_staged), secs(t_staged, t_kernels), secs(t_kernels, now()), cand_idx.size(), (long long)nwords);
     if (nnz_out) *nnz_out = nnz;
     return VRAD_OK;
 }
