@@ -50,7 +50,27 @@ htotal, hadded, hdone = henv.bounce(hemit0, 6)
 hrp, hcol, hw = henv.transfers_download()
 np.savez(os.path.join(os.environ["VRAD_OUT"], f"hier{rank}.npz"), total=htotal, added=hadded, row0=hrow0, row1=hrow1, nnz=hnnz,
          rp=hrp, col=hcol, w=hw)
+for flag in (0, 1):          # all-gather pass per bounce, then the fused peer-store exchange of the leaf rows: same light
+    henv.set_option("k4_hier_p2p", flag)
+    ht2, _, _ = henv.bounce(hemit0, 6)
+    np.save(os.path.join(os.environ["VRAD_OUT"], f"hier{rank}_p2p{flag}.npy"), ht2)
 henv.close()
+# bump totals with sharded rows
+from vrad_b200.environment import bump_normals
+bn = np.zeros((N, 3, 3), np.float32)
+for n_ in np.unique(scene.patch_normal, axis=0):
+    s_ = np.cross(n_, [0, 0, 1]) if abs(n_[2]) < 0.9 else np.float32([1, 0, 0])
+    bn[np.all(scene.patch_normal == n_, axis=1)] = bump_normals(s_, np.cross(n_, s_), n_, n_)
+bflags = (np.arange(N) % 3 != 0).astype(np.uint8)
+benv = environment_from_scene(scene, device=lr, rank=rank, world=world)
+uid3 = [Environment.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid3, src=0)
+benv.comm_init(uid3[0])
+benv.set_bump(bflags, bn)
+benv.build_transfers(scene.pvs)
+btotal, _, _ = benv.bounce(emit0, 4)
+np.savez(os.path.join(os.environ["VRAD_OUT"], f"bump{rank}.npz"), total=btotal, bump=benv.bump_totals(), bn=bn, flags=bflags)
+benv.close()
 dist.destroy_process_group()
 '''
 
@@ -112,3 +132,17 @@ def test_two_gpu_bounce_matches_single_and_oracle(tmp_path):
         assert np.abs(r["total"] - hto).max() <= 1e-4 * np.abs(hto).max()
         assert np.allclose(r["added"], hao, rtol=1e-4)
     assert np.array_equal(h0["total"], h1["total"])
+    for r in (0, 1):
+        for flag in (0, 1):
+            t2 = np.load(tmp_path / f"hier{r}_p2p{flag}.npy")
+            assert np.abs(t2 - hto).max() <= 1e-4 * np.abs(hto).max()
+    # bump totals: every rank returns all rows' Light[1..3]
+    b0, b1 = np.load(tmp_path / "bump0.npz"), np.load(tmp_path / "bump1.npz")
+    ob = pyoracle.env_from_scene(scene)
+    ob.set_bump(b0["flags"], b0["bn"])
+    ob.build_transfers(scene.pvs, threads=8)
+    tob, _, _ = ob.bounce(emit0, 4, threads=8)
+    wb = ob.bump_totals()
+    for r in (b0, b1):
+        assert np.abs(r["total"] - tob).max() <= 1e-4 * np.abs(tob).max()
+        assert np.abs(r["bump"] - wb).max() <= 1e-4 * np.abs(wb).max()

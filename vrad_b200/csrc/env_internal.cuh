@@ -195,6 +195,8 @@ struct EnvOptions {
     int k4_seg = 16384;    // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
     int k4_block = 192;    // VRAD_K4_BLOCK: threads per work-item gather block: 192 (6 blocks/SM, 56 registers) or 256 (5 blocks/SM, 48 registers: spills in the loop)
+    int k4_l2_mb = 0;      // VRAD_K4_L2_MB: MB of L2 set aside for the head of the transfer stream of the multi-GPU gather (0 = off)
+    int k4_hier_p2p = 1;   // VRAD_K4_HIER_P2P: patch hierarchy on several GPUs: leaf rows by peer stores (0 = all-gather pass per bounce)
     int k4_pool = 12;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early
     int k4_items = 0;      // VRAD_K4_ITEMS: run the multi-GPU (work-item) gather on a single-GPU handle too (a one-rank peer table)
     int k4_persist = 1;    // VRAD_K4_PERSIST: one gather block per resident slot over equal-work item ranges (0 = 8 items per block)
@@ -269,6 +271,8 @@ struct vrad_env {
     vrad::LocalGroup* multi = nullptr; // the in-process multi-GPU handle itself (owns the group and its children; no device state of its own)
     vrad::PeerLinks peers;             // K4 fused exchange over NVLink peer memory
     vrad::GraphCache bounce_graph;
+    size_t l2_set_aside_req = 0, l2_set_aside = 0, l2_window_max = 0, l2_window_bytes = 0;   // L2 residency of the transfer stream (k4_l2_mb)
+    float l2_hit_ratio = 0.0f;
     int64_t bounds_serial = -1;        // rows_serial the cached block boundaries belong to
     int64_t bounds[vrad::kMaxWorld + 1] = {};
 };
@@ -325,6 +329,7 @@ int group_build_transfers(vrad_env* g, int n_clusters, const uint8_t* pvs, int64
 int group_transfers_info(vrad_env* g, int64_t* row0, int64_t* row1, int64_t* nnz);
 int group_transfers_download(vrad_env* g, int64_t* rowptr, int32_t* col, float* w);
 int group_direct_light(vrad_env* g, int64_t n, const float* pos3, const float* normal3, int n_lights, const vrad_light* lights, float* rgb_out);
+int group_set_bump(vrad_env* g, int n, const uint8_t* needs_bump, const float* bump_normals9);
 int group_bounce(vrad_env* g, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out, float added_last[3], int* bounces_done);
 inline int group_unsupported(const char* what) { set_error("%s is not available on a multi-GPU handle (vrad_env_create_multi)", what); return VRAD_E_UNSUPPORTED; }
 }

@@ -182,6 +182,10 @@ int group_set_hierarchy(vrad_env* g, int n, const int32_t* parent, const int32_t
     return group_all(g, [&](vrad_env* c) -> int { return vrad_patches_set_hierarchy(c, n, parent, child1, child2, face); });
 }
 
+int group_set_bump(vrad_env* g, int n, const uint8_t* needs_bump, const float* bump_normals9) {
+    return group_all(g, [&](vrad_env* c) -> int { return vrad_patches_set_bump(c, n, needs_bump, bump_normals9); });
+}
+
 int group_build_transfers(vrad_env* g, int n_clusters, const uint8_t* pvs, int64_t* nnz_out) {
     std::vector<int64_t> nnz(g->multi->world, 0);
     int rc = group_run(g, [&](vrad_env* c, int r) -> int { return vrad_build_transfers(c, n_clusters, pvs, &nnz[r]); });

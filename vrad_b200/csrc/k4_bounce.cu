@@ -278,7 +278,11 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // WARPS x blocks per SM: 8 x 5 = 40 resident warps at 48 registers, or 6 x 6 = 36 resident warps at 56 registers
-template <bool MULTI, int WARPS>
+// CS: the {col,w} stream is read with ld.global.cs (evict first); without it the loads leave the replacement decision to the L2
+// access-policy window (k4_l2_mb), which keeps the head of the stream resident from bounce to bounce
+template <bool CS> __device__ __forceinline__ int2 load_tr(const int2* p) { return CS ? __ldcs(p) : *p; }
+
+template <bool MULTI, int WARPS, bool CS = true>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 5 : 6)
 k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ items, const int32_t* __restrict__ item_slot, int64_t row0,
                 const int2* __restrict__ tr, const float4* er, const float4* __restrict__ refl,
@@ -315,7 +319,7 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
         const int2* p0 = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
         const int l0 = it.y & 0xffff;
 #pragma unroll
-        for (int j = 0; j < kGatherUnroll; j++) cur[j] = lane + 32 * j < l0 ? __ldcs(&p0[lane + 32 * j]) : zero;
+        for (int j = 0; j < kGatherUnroll; j++) cur[j] = lane + 32 * j < l0 ? load_tr<CS>(&p0[lane + 32 * j]) : zero;
     }
     int wn = w != kNoItem ? claim() : kNoItem;
     if (wn != kNoItem && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
@@ -336,7 +340,7 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
         for (; off < len; off += 32 * kGatherUnroll) {
 #pragma unroll
             for (int j = 0; j < kGatherUnroll; j++)
-                nxt[j] = off + 32 * (kGatherUnroll + j) < len ? __ldcs(&p[off + 32 * (kGatherUnroll + j)]) : zero;
+                nxt[j] = off + 32 * (kGatherUnroll + j) < len ? load_tr<CS>(&p[off + 32 * (kGatherUnroll + j)]) : zero;
             float4 x[kGatherUnroll];
 #pragma unroll
             for (int j = 0; j < kGatherUnroll; j++) x[j] = load_er<MULTI>(er, cur[j].x);
@@ -362,7 +366,7 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
             const int2* pn = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
             const int ln = has_next ? (it.y & 0xffff) : 0;
 #pragma unroll
-            for (int j = 0; j < kGatherUnroll; j++) cur[j] = lane + 32 * j < ln ? __ldcs(&pn[lane + 32 * j]) : zero;
+            for (int j = 0; j < kGatherUnroll; j++) cur[j] = lane + 32 * j < ln ? load_tr<CS>(&pn[lane + 32 * j]) : zero;
         }
         w = wn;
         wn = has_next ? claim() : kNoItem;
@@ -499,11 +503,17 @@ k4_gather_bump(int n_rows, const int32_t* __restrict__ rows, int64_t row0, const
 // bounce; with the one-step {col,w} prefetch of the long-row kernel the loop needs 40 registers (48 warps): 64.1 us,
 // and squeezed into 32 it spills: 76 us.  `rows` (optional) lists the local rows to process -- with a
 // hierarchy only the leaf patches gather, the interior rows are rewritten by k4_collect_parents.
-template <int kShortLanes, int kMinBlocks, int kShortUnroll = 4, bool kPrefetch = true>
+// MULTI (several GPUs, patch hierarchy): the finished leaf row goes to every rank's next-bounce buffer (sub-lane p -> rank p) and
+// the block that finishes last publishes the bounce epoch, as in k4_gather_items; the wait half of the barrier is the prologue of
+// k4_collect_parents, which needs every rank's leaf rows before it averages them into the interior patches.
+struct ShortPeers { const PeerTable* peers; uint32_t* flags; int next_buf; uint32_t signal_rel; };
+
+template <int kShortLanes, int kMinBlocks, int kShortUnroll = 4, bool kPrefetch = true, bool MULTI = false>
 __global__ void __launch_bounds__(kGatherBlock, kMinBlocks)
 k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const int64_t* __restrict__ rowptr,
-                const int2* __restrict__ tr, const float4* __restrict__ er, const float4* __restrict__ refl,
-                float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
+                const int2* __restrict__ tr, const float4* er, const float4* __restrict__ refl,
+                float4* er_next, float4* __restrict__ total, float* __restrict__ partials, ShortPeers SP = ShortPeers{}) {
+    static_assert(!MULTI || kShortLanes == 8, "the fused exchange maps the 8 lanes of a row onto the (at most 8) ranks");
     constexpr int kShortRowsPerBlock = kGatherBlock / kShortLanes;
     const int sub = threadIdx.x & (kShortLanes - 1), grp = threadIdx.x / kShortLanes;
     const int r = blockIdx.x * kShortRowsPerBlock + grp;
@@ -523,7 +533,7 @@ k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const
                 nxt[j] = k + kShortLanes * (kShortUnroll + j) < k1 ? __ldcs(&tr[k + kShortLanes * (kShortUnroll + j)]) : zero;
             float4 x[kShortUnroll];
 #pragma unroll
-            for (int j = 0; j < kShortUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
+            for (int j = 0; j < kShortUnroll; j++) x[j] = load_er<MULTI>(er, cur[j].x);
 #pragma unroll
             for (int j = 0; j < kShortUnroll; j++) {
                 const float w = __int_as_float(cur[j].y);
@@ -538,7 +548,7 @@ k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const
 #pragma unroll
             for (int j = 0; j < kShortUnroll; j++) cur[j] = k + kShortLanes * j < k1 ? __ldcs(&tr[k + kShortLanes * j]) : zero;
 #pragma unroll
-            for (int j = 0; j < kShortUnroll; j++) x[j] = __ldg(&er[cur[j].x]);
+            for (int j = 0; j < kShortUnroll; j++) x[j] = load_er<MULTI>(er, cur[j].x);
 #pragma unroll
             for (int j = 0; j < kShortUnroll; j++) {
                 const float w = __int_as_float(cur[j].y);
@@ -553,17 +563,22 @@ k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
     float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);                        // sky: emit = 0
     if (valid && sub == 0) {
         const float4 rf = refl[row0 + row];
         if (rf.w == 0.0f) {                                              // CollectLight, leaf patch
             float4 t = total[row];
             t.x += s0; t.y += s1; t.z += s2;
             total[row] = t;
-            er_next[row0 + row] = make_float4(s0 * rf.x, s1 * rf.y, s2 * rf.z, 0.f);
+            nv = make_float4(s0 * rf.x, s1 * rf.y, s2 * rf.z, 0.f);
             e0 = s0; e1 = s1; e2 = s2;
-        } else {
-            er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);      // sky: emit = 0
         }
+        if (!MULTI) er_next[row0 + row] = nv;
+    }
+    if (MULTI) {        // sub-lane p of the row's 8 lanes stores the row into rank p's buffer
+        const int src = (threadIdx.x & 31) & ~(kShortLanes - 1);
+        nv.x = __shfl_sync(0xffffffffu, nv.x, src); nv.y = __shfl_sync(0xffffffffu, nv.y, src); nv.z = __shfl_sync(0xffffffffu, nv.z, src);
+        if (valid && sub < SP.peers->world) SP.peers->er[SP.next_buf][sub][row0 + row] = make_float4(nv.x, nv.y, nv.z, 0.f);
     }
     // deterministic per-block partial of `added`
     __shared__ float sm[kShortRowsPerBlock][3];
@@ -574,6 +589,10 @@ k4_gather_short(int nrows, const int32_t* __restrict__ rows, int64_t row0, const
 #pragma unroll
         for (int q = 0; q < kShortRowsPerBlock; q++) a += sm[q][threadIdx.x];
         partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    }
+    if (MULTI) {
+        __syncthreads();
+        if (threadIdx.x == 0) signal_if_last(SP.peers, SP.flags, SP.signal_rel);
     }
 }
 
@@ -635,7 +654,9 @@ __device__ __forceinline__ void collect_row(int64_t k0, int64_t k1, int sub, con
 
 __global__ void __launch_bounds__(256)
 k4_collect_parents(int n_interior, int n_long, int long_blocks, const int32_t* __restrict__ ids, const int64_t* __restrict__ cptr,
-                   const int2* __restrict__ ent, float4* __restrict__ buf) {
+                   const int2* __restrict__ ent, float4* buf, const uint32_t* flags = nullptr, int wait_world = 0, uint32_t wait_rel = 0) {
+    // several GPUs with the fused exchange: the leaf rows of this bounce are complete once every rank's epoch has arrived
+    if (wait_rel) wait_for_peers(flags, wait_world, wait_rel);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if ((int)blockIdx.x < long_blocks) {
         const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -865,7 +886,7 @@ int vrad_bump_normals(const float s_vect[3], const float t_vect[3], const float 
 }
 
 int vrad_patches_set_bump(vrad_env* e, int n, const uint8_t* needs_bump, const float* bump_normals9) {
-    VRAD_MULTI_UNSUPPORTED(e, "vrad_patches_set_bump");
+    VRAD_MULTI(e, group_set_bump(e, n, needs_bump, bump_normals9));
     if (!e || !needs_bump || !bump_normals9) { set_error("vrad_patches_set_bump: bad arguments"); return VRAD_E_INVALID; }
     PatchesDev& P = e->patches;
     if (P.n == 0 || n != P.n) { set_error("vrad_patches_set_bump: %d entries for %d uploaded patches", n, P.n); return VRAD_E_STATE; }
@@ -881,7 +902,7 @@ int vrad_patches_set_bump(vrad_env* e, int n, const uint8_t* needs_bump, const f
 }
 
 int vrad_bounce_bump_totals(vrad_env* e, float* out9) {
-    VRAD_MULTI_UNSUPPORTED(e, "vrad_bounce_bump_totals");
+    VRAD_MULTI_RANK0(e);          // every rank holds the gathered totals
     if (!e || !out9) { set_error("vrad_bounce_bump_totals: bad arguments"); return VRAD_E_INVALID; }
     PatchesDev& P = e->patches;
     if (!P.bump || P.total_bump[0].n < (size_t)P.n) { set_error("vrad_bounce_bump_totals: no bump-mapped bounce has run (vrad_patches_set_bump, vrad_bounce)"); return VRAD_E_STATE; }
@@ -1029,11 +1050,29 @@ static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, b
     A.signal_rel = signal_rel; A.wait_world = e->peers.table_world;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(w6 ? 192 : 256); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, w6 ? k4_gather_items<true, 6> : k4_gather_items<true, 8>, (const int32_t*)T.block_ptr.p, (const int4*)T.items.p, (const int32_t*)T.item_slot.p, T.row0,
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (chained) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    if (e->l2_window_bytes > 0) {
+        // Keep the head of this rank's transfer stream in L2 from bounce to bounce (the per-rank stream of the C4 matrix at 8 ranks
+        // is 192 MB against 126 MB of L2): lines of the window are marked persisting with probability hitRatio (= set-aside / window,
+        // so that the set-aside is not thrashed), everything else streams.
+        attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[na].val.accessPolicyWindow.base_ptr = (void*)T.tr.p;
+        attr[na].val.accessPolicyWindow.num_bytes = e->l2_window_bytes;
+        attr[na].val.accessPolicyWindow.hitRatio = e->l2_hit_ratio;
+        attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        na++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    const bool cs = e->l2_window_bytes == 0 || e->opt.k4_l2_mb < 0;
+    auto kern = w6 ? (cs ? k4_gather_items<true, 6, true> : k4_gather_items<true, 6, false>) : (cs ? k4_gather_items<true, 8, true> : k4_gather_items<true, 8, false>);
+    return cudaLaunchKernelEx(&cfg, kern, (const int32_t*)T.block_ptr.p, (const int4*)T.items.p, (const int32_t*)T.item_slot.p, T.row0,
                               (const int2*)T.tr.p, (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
 }
 
@@ -1108,8 +1147,11 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     const int collect_long_blocks = (PD.n_collect_long + 7) / 8;
     const int collect_blocks = collect_long_blocks + (PD.n_interior - PD.n_collect_long + 31) / 32;
     if (sim && !hier && !e->patches.bump) { if ((rc = setup_simulated_peers(e, (size_t)n_pad))) return rc; }
-    else if (world > 1 && !hier && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
+    else if (world > 1 && !sim && !e->patches.bump && (rc = comm_setup_peers(e, (size_t)n_pad))) return rc;
     const bool p2p = (world > 1 || sim) && !hier && !e->patches.bump && e->peers.ready;
+    // patch hierarchy on several GPUs: the leaf rows travel by peer stores out of the short-row gather, the barrier's wait half is the
+    // prologue of k4_collect_parents (two launches per bounce, no all-gather pass)
+    const bool p2p_hier = world > 1 && !sim && hier && !e->patches.bump && e->peers.ready && e->opt.k4_hier_p2p;
     if (sim && world > 1 && !p2p) { set_error("vrad_bounce: VRAD_K4_SIM_PEERS does not cover the patch hierarchy"); return VRAD_E_UNSUPPORTED; }
     // short-row form: chosen by the average row length of the rows that gather (env VRAD_K4_SHORT=0/1 forces it)
     int n_short = nloc;
@@ -1129,7 +1171,6 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     // bump-mapped leaf rows of this rank (TotalLight.Light[1..3] accumulate next to the flat gather)
     const bool bump = PD.bump;
     if (bump) {
-        if (world > 1) { set_error("vrad_bounce: bump-mapped patches are not supported with world > 1 yet"); return VRAD_E_UNSUPPORTED; }
         PatchesDev& PM = e->patches;
         if (PM.bump_rows_row0 != T.row0 || PM.bump_rows_row1 != T.row1) {
             std::vector<int32_t> br;
@@ -1153,6 +1194,23 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     const int short_blocks = std::max(1, (n_short + short_rpb - 1) / short_rpb);
     const bool use_pdl = e->opt.k4_pdl != 0, use_graph = e->opt.k4_graph != 0;
 
+    // L2 residency of the transfer stream (k4_l2_mb; multi-GPU form)
+    {
+        const size_t want = p2p && e->opt.k4_l2_mb != 0 ? (size_t)std::abs(e->opt.k4_l2_mb) << 20 : 0;      // negative: window with the .cs loads kept (experiment)
+        if (want != e->l2_set_aside_req) {
+            cudaDeviceProp prop;
+            VRAD_CUDA_CHECK(cudaGetDeviceProperties(&prop, e->cfg.device));
+            const size_t set_aside = std::min(want, (size_t)prop.persistingL2CacheMaxSize);
+            VRAD_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+            e->l2_set_aside_req = want; e->l2_set_aside = set_aside;
+            if (getenv("VRAD_VERBOSE")) fprintf(stderr, "[vrad] L2 set-aside %zu MB (max %d MB, window max %d MB)\n", set_aside >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20);
+            e->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+            e->bounce_graph.tag = -1;            // the window is baked into the captured launches
+        }
+        const size_t stream_bytes = (size_t)T.nnz_padded * 8;
+        e->l2_window_bytes = e->l2_set_aside ? std::min(stream_bytes, e->l2_window_max) : 0;
+        e->l2_hit_ratio = e->l2_window_bytes ? std::min(1.0f, (float)((double)e->l2_set_aside / (double)e->l2_window_bytes)) : 0.0f;
+    }
     timing_begin(e);
     int launches = 0;
     float4* total_local = e->d_total.p + T.row0;
@@ -1219,7 +1277,11 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         const bool probe = verbose && b >= 4 && n_probe < kProbe;
         const bool last = (b + 1 == n_bounces);
         if (probe) { for (int k = 0; k < 3; k++) cudaEventCreate(&pe[n_probe][k]); cudaEventRecord(pe[n_probe][0], e->stream); }
-        if (use_short) {
+        if (use_short && p2p_hier) {
+            const ShortPeers SP{e->peers.d_table.p, e->peers.d_flags.p, cur ^ 1, (uint32_t)b + 1u};
+            k4_gather_short<8, 8, 4, false, true><<<short_blocks, kGatherBlock, 0, e->stream>>>(n_short, d_rows, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p,
+                                                                                              e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p, SP);
+        } else if (use_short) {
 #define VRAD_SHORT(L, B, ...) k4_gather_short<L, B, ##__VA_ARGS__><<<short_blocks, kGatherBlock, 0, e->stream>>>(n_short, d_rows, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, \
                                                                  e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p)
             switch (short_cfg) {                                  // lanes per row, min blocks/SM[, unroll, prefetch]: measured on the hierarchical S2 matrix
@@ -1241,9 +1303,10 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             launches++;
         }
         if (probe) cudaEventRecord(pe[n_probe][1], e->stream);
-        if (!p2p && world > 1 && (rc = comm_allgather_rows(e, e->d_er[cur ^ 1].p, bounds))) return rc;
+        if (!p2p && !p2p_hier && world > 1 && !sim && (rc = comm_allgather_rows(e, e->d_er[cur ^ 1].p, bounds))) return rc;
         if (hier) {     // CollectLight, interior patches: emit of a parent = area-weighted average of its children
-            k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_er[cur ^ 1].p);
+            k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_er[cur ^ 1].p,
+                                                                      p2p_hier ? e->peers.d_flags.p : nullptr, e->peers.table_world, p2p_hier ? (uint32_t)b + 1u : 0u);
             launches++;
         }
         if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
@@ -1263,8 +1326,10 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             if (h_added[0] < 1.0f && h_added[1] < 1.0f && h_added[2] < 1.0f) break;
         }
     }
-    if (p2p && done > 0) { k4_peer_wait<<<1, 32, 0, e->stream>>>(e->peers.d_flags.p, e->peers.table_world, (uint32_t)done); launches++; }
+    if ((p2p || p2p_hier) && done > 0) { k4_peer_wait<<<1, 32, 0, e->stream>>>(e->peers.d_flags.p, e->peers.table_world, (uint32_t)done); launches++; }
     if (world > 1 && !sim && (rc = comm_allgather_rows(e, e->d_total.p, bounds))) return rc;
+    if (bump && world > 1 && !sim)          // TotalLight.Light[1..3] of every rank's bump-mapped rows
+        for (int bb = 0; bb < 3; bb++) if ((rc = comm_allgather_rows(e, e->patches.total_bump[bb].p, bounds))) return rc;
     if (hier) {         // totallight of the interior patches, from the leaves' totals
         k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_total.p);
         launches++;
@@ -1292,7 +1357,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     if (added_last) VRAD_CUDA_CHECK(cudaMemcpyAsync(added_last, d_added, 12, cudaMemcpyDeviceToHost, e->stream));
     if (bounces_done) *bounces_done = done;
     uint32_t h_err = 0;
-    if (p2p && (need_sync || !e->async)) {       // a wait that gave up (dead peer) is an error, not a hang; async callers see it on their next synchronous call
+    if ((p2p || p2p_hier) && (need_sync || !e->async)) {       // a wait that gave up (dead peer) is an error, not a hang; async callers see it on their next synchronous call
         VRAD_CUDA_CHECK(cudaMemcpyAsync(&h_err, e->peers.d_flags.p + kFlagError, 4, cudaMemcpyDeviceToHost, e->stream));
         need_sync = true;
     }
