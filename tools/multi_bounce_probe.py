@@ -39,6 +39,30 @@ for blk, per, pool, pdl, graph in ((192, 1, 12, 1, 1), (192, 1, 12, 0, 1), (192,
     res[f"block{blk}_persist{per}_pool{pool}_pdl{pdl}_graph{graph}"] = {"us_per_bounce": float(t.item()), "max_rel_vs_first": float(np.abs(got - ref).max() / np.abs(ref).max())}
     if rank == 0: print(blk, per, pool, pdl, graph, float(t.item()), flush=True)
 env.close()
+# the same map with its patch hierarchy: leaf rows by peer stores (k4_hier_p2p=1) against the all-gather pass per bounce (0)
+hs = scenes.multi_room_hier(nx=12, ny=11); tr = hs.meta["tree"]
+henv = environment_from_scene(hs, device=lr, rank=rank, world=world)
+henv.set_hierarchy(tr["parent"], tr["child1"], tr["child2"], tr["face"])
+henv.set_stream(torch.cuda.current_stream().cuda_stream)
+if world > 1:
+    uid = [Environment.comm_unique_id() if rank == 0 else None]; dist.broadcast_object_list(uid, src=0); henv.comm_init(uid[0])
+hnnz = henv.build_transfers(hs.pvs)
+hN = hs.n_patches
+he = torch.full((hN, 3), 100.0, device=dev); ho = torch.empty_like(he)
+henv.set_async(True)
+for flag in (1, 0):
+    henv.set_option("k4_hier_p2p", flag)
+    henv.bounce(he, 50, out=ho, want_added=False)
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize(); ev0.record()
+    for _ in range(3):
+        henv.bounce(he, 100, out=ho, want_added=False)
+    ev1.record(); torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1) / 300 * 1e3], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res[f"hierarchy_p2p{flag}_us_per_bounce"] = float(t.item())
+    if rank == 0: print("hierarchy", flag, float(t.item()), flush=True)
+henv.close()
 if rank == 0:
     print(json.dumps(res))
     os.makedirs("gpurun_out", exist_ok=True)
