@@ -62,34 +62,39 @@ __device__ __forceinline__ void stream_rays(const DevScene& S, int64_t base, int
     }
 }
 
-__global__ void __launch_bounds__(kTraceBlock)
+// Closest hit (batched Trace4Rays).  Same supply as the visibility kernel below: persistent warps draw ranges of kTraceRange rays from
+// a global counter and refill their lanes across ranges (round 1: a fixed 512-ray chunk per warp, drained at its end).
+constexpr int kTraceRange = 128;
+constexpr int kTraceBlocksPerSM = 10;
+__global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM)
 k1_trace_rays(DevScene S, int64_t n, const float* __restrict__ ox, const float* __restrict__ oy,
               const float* __restrict__ oz, const float* __restrict__ dx, const float* __restrict__ dy,
               const float* __restrict__ dz, const float* __restrict__ tmin, const float* __restrict__ tmax,
               int skip_id, int32_t* __restrict__ hit_tri, int32_t* __restrict__ hit_sid,
-              float* __restrict__ hit_t, float* __restrict__ normal_soa) {
-    const int64_t n_chunks = (n + kRaysPerWarp - 1) / kRaysPerWarp;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t chunk = warp0; chunk < n_chunks; chunk += nwarps) {
-        const int64_t base = chunk * kRaysPerWarp;
-        const int64_t end = base + kRaysPerWarp < n ? base + kRaysPerWarp : n;
-        auto fetch = [&](int64_t& i, Ray& r, float& t0, float& t1, float& len) {
-            r = Ray{__ldcs(&ox[i]), __ldcs(&oy[i]), __ldcs(&oz[i]), __ldcs(&dx[i]), __ldcs(&dy[i]), __ldcs(&dz[i])};   // streamed once
-            t0 = tmin ? __ldcs(&tmin[i]) : 0.0f; t1 = __ldcs(&tmax[i]); len = 0.0f;
-            return true;
-        };
-        auto retire = [&](int64_t i, int tri, float t, float) {
-            if (hit_tri) hit_tri[i] = tri;
-            if (hit_t) hit_t[i] = t;
-            if (hit_sid) hit_sid[i] = tri >= 0 ? __float_as_int(__ldg(&S.q2[tri]).z) : -1;
-            if (normal_soa) {
-                const float4 q = tri >= 0 ? __ldg(&S.q0[tri]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                normal_soa[i] = q.x; normal_soa[n + i] = q.y; normal_soa[2 * n + i] = q.z;
-            }
-        };
-        stream_rays<decltype(fetch), decltype(retire), false>(S, base, end, skip_id, fetch, retire);
-    }
+              float* __restrict__ hit_t, float* __restrict__ normal_soa, unsigned long long* __restrict__ counter) {
+    auto fetch = [&](int64_t& i, Ray& r, float& t0, float& t1, float& len) {
+        r = Ray{__ldcs(&ox[i]), __ldcs(&oy[i]), __ldcs(&oz[i]), __ldcs(&dx[i]), __ldcs(&dy[i]), __ldcs(&dz[i])};   // streamed once
+        t0 = tmin ? __ldcs(&tmin[i]) : 0.0f; t1 = __ldcs(&tmax[i]); len = 0.0f;
+        return true;
+    };
+    auto retire = [&](int64_t i, int tri, float t, float) {
+        if (hit_tri) hit_tri[i] = tri;
+        if (hit_t) hit_t[i] = t;
+        if (hit_sid) hit_sid[i] = tri >= 0 ? __float_as_int(__ldg(&S.q2[tri]).z) : -1;
+        if (normal_soa) {
+            const float4 q = tri >= 0 ? __ldg(&S.q0[tri]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            normal_soa[i] = q.x; normal_soa[n + i] = q.y; normal_soa[2 * n + i] = q.z;
+        }
+    };
+    auto more = [&](int64_t& next, int64_t& end) {
+        unsigned long long c = 0;
+        if ((threadIdx.x & 31) == 0) c = atomicAdd(counter, (unsigned long long)kTraceRange);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if ((int64_t)c >= n) return false;
+        next = (int64_t)c; end = (int64_t)c + kTraceRange < n ? (int64_t)c + kTraceRange : n;
+        return true;
+    };
+    stream_rays<decltype(fetch), decltype(retire), false, false, decltype(more)>(S, 0, 0, skip_id, fetch, retire, nullptr, more);
 }
 
 template <bool SKY, bool TOP>
@@ -358,9 +363,14 @@ static int stream_grid(const vrad_env* e, int64_t n, int rpw = kRaysPerWarp) {
 int launch_trace_rays(vrad_env* e, int64_t n, const float* ox, const float* oy, const float* oz, const float* dx,
                       const float* dy, const float* dz, const float* tmin, const float* tmax, int32_t skip_id,
                       int32_t* hit_tri, int32_t* hit_sid, float* hit_t, float* normal_soa) {
+    void* d_ctr;
+    int rc = scratch_get(e, 19, 8, &d_ctr);
+    if (rc) return rc;
     timing_begin(e);
-    k1_trace_rays<<<stream_grid(e, n), kTraceBlock, 0, e->stream>>>(
-        e->scene, n, ox, oy, oz, dx, dy, dz, tmin, tmax, skip_id, hit_tri, hit_sid, hit_t, normal_soa);
+    VRAD_CUDA_CHECK(cudaMemsetAsync(d_ctr, 0, 8, e->stream));
+    const int grid = (int)std::min<int64_t>((int64_t)e->sm_count * kTraceBlocksPerSM, (n + kTraceRange * kTraceWarps - 1) / (kTraceRange * kTraceWarps));
+    k1_trace_rays<<<std::max(grid, 1), kTraceBlock, 0, e->stream>>>(
+        e->scene, n, ox, oy, oz, dx, dy, dz, tmin, tmax, skip_id, hit_tri, hit_sid, hit_t, normal_soa, (unsigned long long*)d_ctr);
     timing_end(e, 1);
     VRAD_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -1225,15 +1225,35 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     constexpr int kProbe = 16;
     cudaEvent_t pe[kProbe][3];
     int n_probe = 0;
-    // The plain loop of item gathers (no early-out, no hierarchy, no bump, no NCCL exchange) is a fixed sequence of
-    // launches whose arguments depend only on the bounce number: it is captured once per (bounce count, buffers)
-    // as a CUDA graph and replayed, so the host issues one graph launch per call instead of one kernel per bounce.
-    const bool items_only = !use_short && !bump && !hier && (world == 1 || p2p);
-    const bool graphed = items_only && use_graph && !early_out && !verbose && n_bounces >= 4;
+    // One bounce of the forms that are nothing but kernel launches whose arguments depend only on the bounce number: the flat gather
+    // (plain kernel on one GPU, work-item kernel with the fused exchange on several) and the hierarchical gather (short rows +
+    // CollectLight, with the fused exchange and the barrier wait in the collect kernel on several GPUs).
+    const bool launch_only = !bump && (world == 1 || p2p || p2p_hier) && (!use_short || short_cfg == 884);
+    auto enqueue_bounce = [&](int b, int c, bool want_add) -> cudaError_t {
+        if (!use_short) return launch_gather(e, p2p, p2p && use_pdl && b > 0, c, want_add, p2p ? (uint32_t)b : 0u, (uint32_t)b + 1u, total_local);
+        if (p2p_hier) {
+            const ShortPeers SP{e->peers.d_table.p, e->peers.d_flags.p, c ^ 1, (uint32_t)b + 1u};
+            k4_gather_short<8, 8, 4, false, true><<<short_blocks, kGatherBlock, 0, e->stream>>>(n_short, d_rows, T.row0, T.rowptr.p, T.tr.p, e->d_er[c].p,
+                                                                                              e->patches.refl.p, e->d_er[c ^ 1].p, total_local, e->d_partials.p, SP);
+        } else {
+            k4_gather_short<8, 8, 4, false><<<short_blocks, kGatherBlock, 0, e->stream>>>(n_short, d_rows, T.row0, T.rowptr.p, T.tr.p, e->d_er[c].p,
+                                                                                        e->patches.refl.p, e->d_er[c ^ 1].p, total_local, e->d_partials.p);
+        }
+        if (hier)
+            k4_collect_parents<<<collect_blocks, 256, 0, e->stream>>>(PD.n_interior, PD.n_collect_long, collect_long_blocks, PD.collect_ids.p, PD.collect_ptr.p, PD.collect_ent.p, e->d_er[c ^ 1].p,
+                                                                      p2p_hier ? e->peers.d_flags.p : nullptr, e->peers.table_world, p2p_hier ? (uint32_t)b + 1u : 0u);
+        return cudaGetLastError();
+    };
+    const int launches_per_bounce = use_short && hier ? 2 : 1;
+    // Such a loop is captured once per (bounce count, buffers, plan) as a CUDA graph and replayed: the host issues one graph launch
+    // per call instead of one or two kernels per bounce.
+    const bool graphed = launch_only && use_graph && !early_out && !verbose && n_bounces >= 4;
     if (graphed) {
         GraphCache& G = e->bounce_graph;
-        const int64_t graph_tag = T.plan_serial * 4 + (use_pdl ? 2 : 0) + (p2p ? 1 : 0);
-        const bool hit = G.exec && G.n_bounces == n_bounces && G.items == T.items.p && G.n_items == T.n_items && G.er0 == e->d_er[0].p && G.total == total_local &&
+        const int64_t graph_tag = (T.plan_serial * 8 + (use_pdl ? 4 : 0) + (p2p ? 2 : 0) + (p2p_hier ? 1 : 0)) * 4 + (use_short ? 2 : 0) + (hier ? 1 : 0);
+        const void* key_items = use_short ? (const void*)d_rows : (const void*)T.items.p;
+        const int key_n = use_short ? n_short : T.n_items;
+        const bool hit = G.exec && G.n_bounces == n_bounces && G.items == key_items && G.n_items == key_n && G.er0 == e->d_er[0].p && G.total == total_local &&
                          G.p2p == p2p && G.row0 == T.row0 && G.add == e->d_add.p && G.tr == T.tr.p && G.tag == graph_tag;
         if (!hit) {
             if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
@@ -1244,7 +1264,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
             int c = 0;
             for (int b = 0; b < n_bounces && ce == cudaSuccess; b++) {
-                ce = launch_gather(e, p2p, p2p && use_pdl && b > 0, c, b + 1 == n_bounces, p2p ? (uint32_t)b : 0u, (uint32_t)b + 1u, total_local);
+                ce = enqueue_bounce(b, c, b + 1 == n_bounces);
                 c ^= 1;
             }
             cudaGraph_t g = nullptr;
@@ -1258,18 +1278,18 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
                 if (getenv("VRAD_VERBOSE")) fprintf(stderr, "[vrad] bounce-loop graph capture failed (%s); using stream launches\n", cudaGetErrorString(ce));
                 e->opt.k4_graph = 0;
             }
-            G.n_bounces = n_bounces; G.items = T.items.p; G.n_items = T.n_items; G.er0 = e->d_er[0].p; G.total = total_local; G.p2p = p2p; G.row0 = T.row0;
+            G.n_bounces = n_bounces; G.items = key_items; G.n_items = key_n; G.er0 = e->d_er[0].p; G.total = total_local; G.p2p = p2p; G.row0 = T.row0;
             G.add = e->d_add.p; G.tr = T.tr.p; G.tag = graph_tag;
         }
         if (G.exec) {
             VRAD_CUDA_CHECK(cudaGraphLaunch(G.exec, e->stream));
-            launches += n_bounces;
+            launches += n_bounces * launches_per_bounce;
             done = n_bounces; cur = n_bounces & 1;
             if (p2p) {
                 k4_sum_added_rows<<<add_blocks, 256, 0, e->stream>>>(nloc, e->d_add.p, e->d_partials.p);
                 k4_reduce_added<<<1, 256, 0, e->stream>>>(add_blocks, e->d_partials.p, d_added);
                 launches += 2;
-            } else { k4_reduce_added<<<1, 256, 0, e->stream>>>(nblocks, e->d_partials.p, d_added); launches++; }
+            } else { k4_reduce_added<<<1, 256, 0, e->stream>>>(use_short ? short_blocks : nblocks, e->d_partials.p, d_added); launches++; }
             if (world > 1 && !sim && (rc = comm_allreduce3(e, d_added))) return rc;
         }
     }
