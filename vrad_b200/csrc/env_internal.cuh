@@ -195,6 +195,7 @@ struct EnvOptions {
     int k4_seg = 16384;    // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
     int k4_block = 192;    // VRAD_K4_BLOCK: threads per work-item gather block: 192 (6 blocks/SM, 56 registers) or 256 (5 blocks/SM, 48 registers: spills in the loop)
+    int k2_stream = 0;     // VRAD_K2_STREAM: pass A of the transfer build as compacted ray queues with lane refill (experiment, slower: DESIGN section 7; 0 = one ray slot per (row, candidate) thread)
     int k4_l2_mb = 0;      // VRAD_K4_L2_MB: MB of L2 set aside for the head of the transfer stream of the multi-GPU gather (0 = off)
     int k4_hier_p2p = 1;   // VRAD_K4_HIER_P2P: patch hierarchy on several GPUs: leaf rows by peer stores (0 = all-gather pass per bounce)
     int k4_pool = 12;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early

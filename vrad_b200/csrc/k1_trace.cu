@@ -17,51 +17,6 @@ constexpr int kTraceBlock = 128;
 constexpr int kTraceWarps = kTraceBlock / 32;
 constexpr int kRaysPerWarp = 512;              // each warp streams a contiguous chunk of the batch
 
-// Streaming traversal with lane refill: a warp owns rays [base, base + kRaysPerWarp) and keeps its 32
-// lanes busy -- whenever lanes retire (their ray finished) they take the next rays of the chunk before
-// the next descend/leaf round, so the warp does not idle on the longest ray of a fixed batch of 32
-// (ncu r01 v2: 6.2 threads per instruction with fixed batches; rays average 2.9 leaf visits but a
-// batch needs 9.3 rounds).  Results are per ray, so the order in which lanes pick rays is irrelevant.
-// `more` (warp-uniform) is asked for another range of rays when the current one is used up and lanes are idle: a
-// warp whose supply comes in many small ranges (the sorted order hands them out through a global counter) never
-// drains -- its lanes go from the last rays of one range straight to the first rays of the next.
-struct NoMoreRays { __device__ __forceinline__ bool operator()(int64_t&, int64_t&) const { return false; } };
-
-template <typename Fetch, typename Retire, bool ANY_HIT, bool TOP = false, typename More = NoMoreRays>
-__device__ __forceinline__ void stream_rays(const DevScene& S, int64_t base, int64_t end, int skip_id, Fetch fetch, Retire retire, const int2* top_s = nullptr,
-                                            More more = More()) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    Traversal T;
-    TraversalStack st;
-    T.idle();
-    int64_t my_ray = -1;
-    float my_len = 0.0f;
-    int64_t next = base;
-    bool exhausted = false;
-    for (;;) {
-        if (my_ray >= 0 && !T.active) { retire(my_ray, T.hit_tri, T.hit_t, my_len); my_ray = -1; }
-        const unsigned idle = __ballot_sync(0xffffffffu, my_ray < 0);
-        if (idle && next >= end && !exhausted) exhausted = !more(next, end);
-        if (idle && next < end) {
-            const int64_t idx = next + __popc(idle & lt_mask);
-            if (my_ray < 0 && idx < end) {
-                Ray r; float t0, t1;
-                my_ray = idx;
-                const bool ok = fetch(my_ray, r, t0, t1, my_len);   // false: nothing to trace (zero-length segment); may rename the ray (sorted order)
-                T.begin(S, r, ok, t0, t1, TOP ? kTopRef : 0);
-            }
-            next += __popc(idle);
-        }
-        if (!__any_sync(0xffffffffu, T.active)) {
-            if (__all_sync(0xffffffffu, my_ray < 0) && next >= end && exhausted) break;
-            continue;                                               // only retirements / refills pending
-        }
-        const int2 nd = T.template descend<TOP>(S, st, top_s);
-        T.leaf<ANY_HIT>(S, st, nd, skip_id, ANY_HIT ? my_len : 0.0f);
-    }
-}
-
 // Closest hit (batched Trace4Rays).  Same supply as the visibility kernel below: persistent warps draw ranges of kTraceRange rays from
 // a global counter and refill their lanes across ranges (round 1: a fixed 512-ray chunk per warp, drained at its end).
 constexpr int kTraceRange = 128;

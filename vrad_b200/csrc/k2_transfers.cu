@@ -151,6 +151,107 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
     }
 }
 
+// Pass A, streaming form (round 2 experiment, k2_stream=1; NOT the default).  The idea: decouple the cheap tests from the rays per warp --
+// a warp draws rows from a global counter and sweeps the row's candidate list 32 at a time, pairs that need a ray are compacted by
+// ballot into the warp's queue in shared memory, and the traversal takes its rays from that queue through stream_rays (common.cuh)
+// with lane refill, testing further candidates (of this row or the next) whenever the queue runs dry.  Same pairs, same segments,
+// same bits as above (checked: tools/k2_stream_probe.py) -- but slower: 114 ms against 86 ms on the C4 build, 99e9 against 75e9 warp
+// instructions at 16 instead of 22 threads per instruction (profiles/r02_k2_stream_ncu.csv).  The per-candidate kernel was never
+// short of rays: 2.1e9 (row, candidate) pairs produce ~5e8 rays (most pairs between rooms face each other and are blocked by a wall),
+// 8 per 32-pair batch, all towards one end point and mostly ended by the first wall they meet -- ~150 warp instructions per ray,
+// the rate K1 reaches on this scene; queueing adds its loop overhead and takes the rays out of candidate order.
+constexpr int kVsBlock = 128, kVsWarps = kVsBlock / 32, kVsQueue = 64, kVsBlocksPerSM = 8;
+template <bool HIER>
+__global__ void __launch_bounds__(kVsBlock, kVsBlocksPerSM)
+k2_visibility_stream(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __restrict__ cluster,
+                     const int64_t* __restrict__ cand_ptr, const int32_t* __restrict__ cand_idx,
+                     const int64_t* __restrict__ bit_ptr, uint32_t* __restrict__ bits,
+                     const uint8_t* __restrict__ pvs, int n_clusters, const int4* __restrict__ tree, unsigned int* __restrict__ row_counter) {
+    __shared__ int4 queue[kVsWarps][kVsQueue];          // {row, candidate position | pass_ij << 30 | pass_ji << 31, j, -}
+    const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+    int4* q = queue[threadIdx.x >> 5];
+    int cur_row = 0, cur_p = 0, cur_K = 0;              // warp-uniform: the row being swept and the next candidate position
+    int my_row = 0, my_pf = 0, my_j = 0;                // the pair whose ray this lane holds
+    auto more = [&](int64_t& next, int64_t& end) {
+        int count = 0;
+        while (count <= kVsQueue - 32) {
+            if (cur_p >= cur_K) {                       // next row
+                unsigned r = 0;
+                if (lane == 0) r = atomicAdd(row_counter, 1u);
+                r = __shfl_sync(0xffffffffu, r, 0);
+                if (r >= (unsigned)nloc) { cur_p = cur_K = 0; break; }
+                const int c = __ldg(&cluster[row0 + r]);
+                cur_row = (int)r; cur_p = 0; cur_K = (int)(__ldg(&cand_ptr[c + 1]) - __ldg(&cand_ptr[c]));
+                continue;
+            }
+            const int i = (int)(row0 + cur_row);
+            const int p = cur_p + (int)lane;
+            bool pass_ij = false, pass_ji = false;
+            int j = i;
+            if (p < cur_K) {
+                const float4 oi = __ldg(&P.origin_area[i]), ni = __ldg(&P.normal_dist[i]);
+                const float sky_i = __ldg(&P.refl[i]).w;
+                const int ci = __ldg(&cluster[i]);
+                int4 ti = make_int4(-1, -1, -1, ci);
+                if (HIER) ti = __ldg(&tree[i]);
+                j = __ldg(&cand_idx[__ldg(&cand_ptr[ci]) + p]);
+                if (j != i) {
+                    const int cj = __ldg(&cluster[j]);
+                    const bool mirror = j >= row0 && j < row0 + nloc && (pvs == nullptr || (ti.w >= 0 && ti.w < n_clusters && __ldg(&pvs[(size_t)cj * n_clusters + ti.w]) != 0));
+                    if (!(mirror && j < i)) {           // otherwise pair (j, i) of row j covers this one
+                        const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
+                        const float sky_j = __ldg(&P.refl[j]).w;
+                        pass_ij = sky_i == 0.0f && transfer_weight(oi, ni, oj, nj, sky_j) != 0.0f;
+                        pass_ji = mirror && sky_j == 0.0f && transfer_weight(oj, nj, oi, ni, sky_i) != 0.0f;
+                        if (HIER && (pass_ij || pass_ji)) {
+                            const int4 tj = __ldg(&tree[j]);
+                            const bool other_face = !(ti.z >= 0 && ti.z == tj.z);
+                            pass_ij = pass_ij && ti.y == -1 && other_face && emitter_accepted(P, tree, oi, oj, tj);
+                            pass_ji = pass_ji && tj.y == -1 && other_face && emitter_accepted(P, tree, oj, oi, ti);
+                        }
+                    }
+                }
+            }
+            const bool need_ray = pass_ij || pass_ji;
+            const unsigned m = __ballot_sync(0xffffffffu, need_ray);
+            if (need_ray) q[count + __popc(m & lt_mask)] = make_int4(cur_row, p | (pass_ij ? 1 << 30 : 0) | (pass_ji ? (int)(1u << 31) : 0), j, 0);
+            count += __popc(m);
+            cur_p += 32;
+        }
+        __syncwarp(0xffffffffu);
+        next = 0; end = count;
+        return count > 0;
+    };
+    auto fetch = [&](int64_t& qi, Ray& r, float& t0, float& t1, float& len) {
+        const int4 en = q[(int)qi];
+        my_row = en.x; my_pf = en.y; my_j = en.z;
+        const int i = (int)(row0 + en.x);
+        const bool lower = i < en.z;                    // the segment runs from the lower to the higher patch index
+        const int ia = lower ? i : en.z, ib = lower ? en.z : i;
+        const float4 a = __ldg(&P.origin_area[ia]), an = __ldg(&P.normal_dist[ia]);
+        const float4 b = __ldg(&P.origin_area[ib]), bn = __ldg(&P.normal_dist[ib]);
+        t0 = 0.0f; len = 0.0f;
+        r = Ray{0.f, 0.f, 0.f, 1.f, 1.f, 1.f};
+        const bool ok = segment_to_ray(a.x + an.x, a.y + an.y, a.z + an.z, b.x + bn.x, b.y + bn.y, b.z + bn.z, r, len);
+        t1 = len;
+        return ok;
+    };
+    auto retire = [&](int64_t, int tri, float, float) {
+        if (tri != -1) return;                          // any-hit with the segment length as the limit: a recorded hit occludes
+        const int p = my_pf & 0x3fffffff;
+        if (my_pf & (1 << 30)) atomicOr(&bits[__ldg(&bit_ptr[my_row]) + (p >> 5)], 1u << (p & 31));
+        if (my_pf < 0) {
+            const int i = (int)(row0 + my_row);
+            const int cj = __ldg(&cluster[my_j]);
+            const int64_t j0 = __ldg(&cand_ptr[cj]);
+            int lo = 0, hi = (int)(__ldg(&cand_ptr[cj + 1]) - j0);
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&cand_idx[j0 + mid]) < i) lo = mid + 1; else hi = mid; }
+            atomicOr(&bits[__ldg(&bit_ptr[my_j - row0]) + (lo >> 5)], 1u << (lo & 31));
+        }
+    };
+    stream_rays<decltype(fetch), decltype(retire), true, false, decltype(more)>(S, 0, 0, -1, fetch, retire, nullptr, more);
+}
+
 // Pass A, hierarchical form, top down (the walk as upstream runs it).  The per-candidate kernel above evaluates every
 // patch of every visible face tree for every row (5.8e9 (row, candidate) pairs on the full S2 map for 23.5 M kept
 // transfers); here a block expands receiver i's emitter set level by level from the face roots its cluster sees:
@@ -540,6 +641,21 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
             if (!done) K2_CHECK(cudaMemsetAsync(d_bits.p, 0, (size_t)(nwords + 1) * 4, e->stream));   // a list overflowed: per-candidate form
         }
         if (done) { }
+        else if (e->opt.k2_stream) {
+            DevBuf<unsigned int> d_ctr;
+            if (d_ctr.alloc(1)) { cleanup(); set_error("out of device memory (row counter)"); return VRAD_E_NOMEM; }
+            cudaError_t ce = cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned int), e->stream);
+            const int grid = std::max(1, std::min((nloc + kVsWarps - 1) / kVsWarps, e->sm_count * kVsBlocksPerSM));
+            if (ce == cudaSuccess) {
+                if (hier) k2_visibility_stream<true><<<grid, kVsBlock, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
+                                                                                       pvs ? d_pvs.p : nullptr, C, d_tree, d_ctr.p);
+                else k2_visibility_stream<false><<<grid, kVsBlock, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
+                                                                                   pvs ? d_pvs.p : nullptr, C, nullptr, d_ctr.p);
+                ce = cudaStreamSynchronize(e->stream);      // the counter is released below
+            }
+            d_ctr.release();
+            if (ce != cudaSuccess) { cleanup(); set_error("transfer build (visibility pass) failed: %s", cudaGetErrorString(ce)); return VRAD_E_CUDA; }
+        }
         else if (hier) k2_visibility<true><<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
                                                                                              pvs ? d_pvs.p : nullptr, C, d_tree);
         else k2_visibility<false><<<std::min(nloc, e->sm_count * 32), 256, 0, e->stream>>>(e->scene, pv, nloc, row0, d_clus.p, d_cand_ptr.p, d_cand_idx.p, d_bit_ptr.p, d_bits.p,
