@@ -266,6 +266,14 @@ int  vrad_patches_upload(vrad_env*, int n, const float* origin3, const float* no
  * interior patches (area-weighted average of the two children).  Clusters given to vrad_patches_upload apply to every
  * patch; the PVS test uses the cluster of an emitter's face root. */
 int  vrad_patches_set_hierarchy(vrad_env*, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face);
+/* Patch.Winding (common/types/patch.go; the polygons vrad_patches_subdivide returns as wind_first / wind_count / wind_points3) of the
+ * patches uploaded before.  With windings set, MakeTransfer (vrad_build_transfers) switches from the differential-to-differential
+ * form factor to the polygon-to-differential contour integral for emitters that are large for their distance
+ * (pi * 0.04 * |delta|^2 < area_j; SURVEY App. B.3 "optional" -- upstream vismat.cpp, absent from the reference: parity unpinned,
+ * pinned by the closed form for a rectangle instead).  Patches with count < 3 keep the differential form.  Points run clockwise
+ * seen from the patch's front (BSP face convention); a winding the other way round is reversed on upload.  n = 0 removes the
+ * windings again.  vrad_patches_upload clears them. */
+int  vrad_patches_set_windings(vrad_env*, int n, const int32_t* first, const int32_t* count, int n_points, const float* points3);
 /* Bump-mapped patches (Patch.NeedsBumpMap, common/types/patch.go:23; BumpLights = NUM_BUMP_VECTS + 1 light values per patch,
  * common/types/bumpLights.go:8-10, common/constants/constants.go:33).  vrad_bump_normals is upstream's GetBumpNormals for one
  * face (texture S/T vectors, flat and phong normal -> the three bump-basis normals; host-only).  After vrad_patches_set_bump

@@ -134,6 +134,7 @@ struct Options {
     bool  hdr = false;                // -hdr
     bool  fast = false;               // -fast: here the binned kd build (RTE_FLAGS_FAST_TREE_GENERATION)
     bool  textureShadows = false;     // -textureshadows
+    bool  polygonFormFactor = false;  // MakeTransfer: polygon-to-differential form factor for near pairs (vrad_patches_set_windings; upstream's rule, not in the reference)
     std::string lightsRad;            // -lights (path of a lights.rad; empty = none)
     float SmoothingThreshold() const { return smoothDegrees == 45.0f ? 0.7071067f : static_cast<float>(std::cos(static_cast<double>(smoothDegrees) * 3.14159265358979323846 / 180.0)); }
 };
@@ -343,7 +344,7 @@ inline void UploadBsp(raytracer::Environment& env, const vrad_bsp_lumps& L) {
 }
 
 // the device stages: geometry + kd build (K1), transfers (K2), direct light on luxels and patches (K3), bounces (K4)
-inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vector<float>& skyDirs3, int bounces = 8, bool fastTree = false, bool textureShadows = false) {
+inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vector<float>& skyDirs3, int bounces = 8, bool fastTree = false, bool textureShadows = false, bool polygonFormFactor = false) {
     const vrad_bsp_lumps& L = P.lumps;
     const int N = P.tree.size();
     std::vector<uint8_t> triFlags(P.tris.ids.size(), 0);
@@ -373,6 +374,8 @@ inline Lit Light(raytracer::Environment& env, const Prepared& P, const std::vect
     }
     fatal_on(vrad_patches_upload(env.handle(), N, P.tree.origin.data(), P.tree.normal.data(), P.tree.plane_dist.data(), P.tree.area.data(), P.refl3.data(), cluster.data(), P.flags.data()), "vrad_patches_upload");
     fatal_on(vrad_patches_set_hierarchy(env.handle(), N, P.tree.parent.data(), P.tree.child1.data(), P.tree.child2.data(), P.tree.face.data()), "vrad_patches_set_hierarchy");
+    if (polygonFormFactor)
+        fatal_on(vrad_patches_set_windings(env.handle(), N, P.tree.wind_first.data(), P.tree.wind_count.data(), static_cast<int>(P.tree.wind_points.size() / 3), P.tree.wind_points.data()), "vrad_patches_set_windings");
     Lit out;
     bool bumped = false;
     for (uint8_t b : P.needs_bump) bumped = bumped || b;
@@ -470,7 +473,7 @@ inline Lit BakeFile(const char* pathIn, const char* pathOut, const std::string& 
     if (lightsRadPath) { LoadTexLights(bsp, pathIn, lightsRadPath, tex); tex.hdr = opt.hdr; }
     Prepare(bsp.lumps, text, P, lightsRadPath ? &tex : nullptr, opt.chop, opt.maxChop, opt.SmoothingThreshold(), opt.luxelDensity);
     raytracer::Environment env(device);
-    const Lit lit = Light(env, P, ReadSkyDirs(skyDirsPath), bounces, opt.fast, opt.textureShadows);
+    const Lit lit = Light(env, P, ReadSkyDirs(skyDirsPath), bounces, opt.fast, opt.textureShadows, opt.polygonFormFactor);
     const std::vector<uint8_t> lump = Finish(env, P, lit);
     fatal_on(vrad_bspfile_set_lump(bsp.file, bsp.lightingLump, lump.data(), static_cast<int64_t>(lump.size()), 1), "vrad_bspfile_set_lump");
     // P.lumps.faces points at P.lit_faces (our copy), so replacing the face lump does not pull the rug from under it

@@ -36,6 +36,10 @@ func fatal(rc C.int, what string) {
 
 // LightEntities is filled by the caller from cache.GetAllEntities() with Entity.FloatForKey / VectorForKey /
 // LightForKey (C.vrad_light_for_string), one record per "light*" entity (lights.go:90-113).
+// PolygonFormFactor switches MakeTransfer to the polygon-to-differential form factor for emitters that are large for their
+// distance (upstream's rule; off = the differential form everywhere).
+var PolygonFormFactor = false
+
 func RadWorldCUDA(luxelPos, luxelNormal []float32, lightEntities []C.vrad_light_entity, numBounce int) (lightmap []float32) {
 	env := (*C.vrad_env)(raytracer.GetEnvironment().CudaHandle())
 	patches := *cache.GetPatches()
@@ -78,6 +82,22 @@ func RadWorldCUDA(luxelPos, luxelNormal []float32, lightEntities []C.vrad_light_
 	fatal(C.vrad_patches_set_hierarchy(env, C.int(n), &parent[0], &child1[0], &child2[0], &face[0]), "vrad_patches_set_hierarchy")
 	if anyBump {
 		fatal(C.vrad_patches_set_bump(env, C.int(n), &needsBump[0], &bumpNormals[0]), "vrad_patches_set_bump")
+	}
+	if PolygonFormFactor { // Patch.Winding (common/types/patch.go:10): MakeTransfer integrates over the emitter's polygon for near pairs
+		windFirst, windCount := make([]C.int32_t, n), make([]C.int32_t, n)
+		var windPoints []C.float
+		for i := range patches {
+			windFirst[i] = C.int32_t(len(windPoints) / 3)
+			if w := patches[i].Winding; w != nil {
+				windCount[i] = C.int32_t(w.NumPoints)
+				for q := 0; q < w.NumPoints; q++ {
+					windPoints = append(windPoints, C.float(w.Points[q][0]), C.float(w.Points[q][1]), C.float(w.Points[q][2]))
+				}
+			}
+		}
+		if len(windPoints) > 0 {
+			fatal(C.vrad_patches_set_windings(env, C.int(n), &windFirst[0], &windCount[0], C.int(len(windPoints)/3), &windPoints[0]), "vrad_patches_set_windings")
+		}
 	}
 
 	// ---- lights: surface lights from the emitting leaf patches, then the light entities (lights.go:49-113) ----

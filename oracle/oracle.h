@@ -114,6 +114,10 @@ int  orc_patches_set(orc_env*, int n, const float* origin3, const float* normal3
  * K2 to the hierarchical candidate walk (vismat.cpp TestPatchToPatch) and K4's CollectLight to
  * the parent/child form (App. B.4).  face may be NULL. */
 int  orc_patches_set_hierarchy(orc_env*, int n, const int32_t* parent, const int32_t* child1, const int32_t* child2, const int32_t* face);
+/* Patch.Winding of the patches set before (n = 0 removes them): MakeTransfer then uses the polygon-to-differential form factor for
+ * emitters that are large for their distance (pi * 0.04 * |delta|^2 < area_j; SURVEY App. B.3 "optional").  Clockwise seen from the
+ * patch's front; a winding the other way round is reversed. */
+int  orc_patches_set_windings(orc_env*, int n, const int32_t* first, const int32_t* count, int n_points, const float* points3);
 /* K2: builds CSR transfers.  pvs: n_clusters x n_clusters bytes (nonzero = visible) or NULL. */
 int  orc_build_transfers(orc_env*, int n_clusters, const uint8_t* pvs, int64_t* nnz_out, int threads);
 int  orc_transfers_get(orc_env*, int64_t* rowptr, int32_t* col, float* w);

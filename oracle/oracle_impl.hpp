@@ -33,6 +33,9 @@ struct Patches {
     // Patch.Parent / Child1 / Child2 / FaceNumber (common/types/patch.go:33,49-51); empty = flat (leaf patches only)
     std::vector<int32_t> parent, child1, child2, face;
     bool hier() const { return !child1.empty(); }
+    // Patch.Winding (common/types/patch.go): first point / count per patch + points, clockwise seen from the front; empty = none
+    std::vector<int32_t> wind_first, wind_count;
+    std::vector<float> wind_pts;
     // Patch.NeedsBumpMap (common/types/patch.go:23) and the three bump normals of such a patch (normals[1..3]; normals[0] is
     // the flat patch normal); empty = no bump-mapped patches
     std::vector<uint8_t> needs_bump;

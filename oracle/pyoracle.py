@@ -208,6 +208,14 @@ class OracleEnv:
         parent, child1, child2, face = i32(parent), i32(child1), i32(child2), i32(face)
         assert self._l.orc_patches_set_hierarchy(self._h, C.c_int(parent.shape[0]), _p(parent), _p(child1), _p(child2), _p(face)) == 0
 
+    def set_windings(self, first, count, points):
+        """Patch.Winding per patch (None removes them): near pairs then use the polygon-to-differential form factor."""
+        if first is None:
+            assert self._l.orc_patches_set_windings(self._h, C.c_int(0), None, None, C.c_int(0), None) == 0
+            return
+        first = np.ascontiguousarray(first, np.int32); count = np.ascontiguousarray(count, np.int32); points = _f32(points).reshape(-1, 3)
+        assert self._l.orc_patches_set_windings(self._h, C.c_int(first.shape[0]), _p(first), _p(count), C.c_int(points.shape[0]), _p(points)) == 0
+
     def build_transfers(self, pvs=None, threads=1):
         nnz = C.c_int64()
         nc = 0

@@ -20,8 +20,35 @@ static const float MAX_TRACE_LENGTH = 1.732050807569f * 32768.0f;   // common/co
 
 static inline float dot3(const float* a, const float* b) { return ((a[0] * b[0]) + (a[1] * b[1])) + (a[2] * b[2]); }
 
-// App. B.3 MakeTransfer: differential-to-differential form factor * emitter area.
-// Returns 0 when the pair transfers nothing.
+// Polygon-to-differential form factor (upstream vismat.cpp, near pairs; SURVEY App. B.3 "optional"; not in the reference): the
+// contour integral over the emitter's edges -- angle subtended by the edge at the receiver times the unit normal of the plane
+// through the receiver and the edge, dotted with the receiver's normal.  Per unit emitter area, without the 1/pi.  NaN = no polygon.
+static inline float poly_to_diff_form_factor(const Patches& P, int j, const float* oi, const float* ni) {
+    const int first = P.wind_first[j], cnt = P.wind_count[j];
+    if (cnt < 3) return NAN;
+    float ff = 0.0f;
+    for (int k = 0; k < cnt; k++) {
+        const float* p1 = &P.wind_pts[3 * (size_t)(first + k)];
+        const float* p2 = &P.wind_pts[3 * (size_t)(first + (k + 1 < cnt ? k + 1 : 0))];
+        float a[3] = {p1[0] - oi[0], p1[1] - oi[1], p1[2] - oi[2]};
+        float b[3] = {p2[0] - oi[0], p2[1] - oi[1], p2[2] - oi[2]};
+        const float la = sqrtf(dot3(a, a)), lb = sqrtf(dot3(b, b));
+        if (la > 0.0f) { const float r = 1.0f / la; a[0] = a[0] * r; a[1] = a[1] * r; a[2] = a[2] * r; }
+        if (lb > 0.0f) { const float r = 1.0f / lb; b[0] = b[0] * r; b[1] = b[1] * r; b[2] = b[2] * r; }
+        float g[3] = {(a[1] * b[2]) - (a[2] * b[1]), (a[2] * b[0]) - (a[0] * b[2]), (a[0] * b[1]) - (a[1] * b[0])};
+        const float sin_alpha = sqrtf(dot3(g, g));
+        if (sin_alpha > 1.0f) return 0.0f;
+        if (sin_alpha > 0.0f) {
+            const float m = asinf(sin_alpha) * (1.0f / sin_alpha);
+            g[0] = g[0] * m; g[1] = g[1] * m; g[2] = g[2] * m;
+        }
+        ff = ff + dot3(g, ni);
+    }
+    return ff * (0.5f / P.area[j]);
+}
+
+// App. B.3 MakeTransfer: differential-to-differential form factor * emitter area (polygon-to-differential for an emitter that is
+// large for its distance, once windings are set).  Returns 0 when the pair transfers nothing.
 static inline float transfer_weight(const Patches& P, int i, int j) {
     if ((P.flags[j] & 1) || !(P.area[j] > 0.0f)) return 0.0f;
     const float* oi = &P.origin[3 * i]; const float* oj = &P.origin[3 * j];
@@ -36,6 +63,11 @@ static inline float transfer_weight(const Patches& P, int i, int j) {
     float d1 = dot3(dl, ni), d2 = dot3(dl, nj);
     float scale = -(d1 * d2) / ((len * len) * PI_F);
     if (!(scale > 0.0f)) return 0.0f;
+    if (!P.wind_count.empty() && ((len * len) * PI_F) * 0.04f < P.area[j]) {
+        const float ff = poly_to_diff_form_factor(P, j, oi, ni);
+        if (ff == ff) scale = ff / PI_F;
+        if (!(scale > 0.0f)) return 0.0f;
+    }
     float trans = P.area[j] * scale;
     if (!(trans > TRANS_EPSILON)) return 0.0f;
     return trans;
@@ -126,6 +158,31 @@ int orc_patches_set_hierarchy(orc_env* e, int n, const int32_t* parent, const in
     P.parent.assign(parent, parent + n); P.child1.assign(child1, child1 + n); P.child2.assign(child2, child2 + n);
     if (face) P.face.assign(face, face + n); else P.face.assign(n, -1);
     e->rowptr.clear(); e->col.clear(); e->w.clear();
+    return 0;
+}
+
+int orc_patches_set_windings(orc_env* e, int n, const int32_t* first, const int32_t* count, int n_points, const float* points3) {
+    if (!e || n < 0 || n_points < 0) return -1;
+    Patches& P = e->patches;
+    e->rowptr.clear(); e->col.clear(); e->w.clear();
+    if (n == 0) { P.wind_first.clear(); P.wind_count.clear(); P.wind_pts.clear(); return 0; }
+    if (n != P.n || !first || !count || (n_points > 0 && !points3)) return -1;
+    P.wind_first.assign(first, first + n); P.wind_count.assign(count, count + n);
+    P.wind_pts.assign(points3, points3 + 3 * (size_t)n_points);
+    for (int i = 0; i < n; i++) {
+        const int f = first[i], c = count[i];
+        if (c < 0 || f < 0 || (int64_t)f + c > n_points) return -1;
+        if (c < 3) { P.wind_count[i] = 0; continue; }
+        double nrm[3] = {0, 0, 0};                            // Newell normal: along the patch normal for a counter-clockwise winding
+        for (int k = 0; k < c; k++) {
+            const float* a = &P.wind_pts[3 * (size_t)(f + k)]; const float* b = &P.wind_pts[3 * (size_t)(f + (k + 1 < c ? k + 1 : 0))];
+            nrm[0] += ((double)a[1] - b[1]) * ((double)a[2] + b[2]); nrm[1] += ((double)a[2] - b[2]) * ((double)a[0] + b[0]); nrm[2] += ((double)a[0] - b[0]) * ((double)a[1] + b[1]);
+        }
+        const double o = nrm[0] * P.normal[3 * (size_t)i] + nrm[1] * P.normal[3 * (size_t)i + 1] + nrm[2] * P.normal[3 * (size_t)i + 2];
+        if (o > 0.0)
+            for (int k = 0; k < c / 2; k++)
+                for (int d = 0; d < 3; d++) std::swap(P.wind_pts[3 * (size_t)(f + k) + d], P.wind_pts[3 * (size_t)(f + c - 1 - k) + d]);
+    }
     return 0;
 }
 

@@ -257,7 +257,7 @@ def all_gather_blocks(local: np.ndarray, parts, rank: int, device=None) -> np.nd
 
 
 def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int = 0, world: int = 1, device=None, use_light_pvs: bool = True,
-          fast_tree: bool = False, texture_shadows: bool = False) -> dict:
+          fast_tree: bool = False, texture_shadows: bool = False, poly_form_factor: bool = False) -> dict:
     """The device stages, on any object with the Environment call surface: geometry + kd build (K1), transfers (K2), direct
     light on the luxels and on the patches (K3; the patch value is Patch.DirectLight, what the first bounce emits), bounces (K4).
     world > 1 (one process per GPU, torch.distributed initialised): luxels and patch origins are independent work items, each
@@ -275,6 +275,8 @@ def light(env, prep: dict, bounces: int = 8, early_out: bool = True, rank: int =
     cluster = patch_clusters(env, prep)
     env.patches_upload(t["origin"], t["normal"], t["plane_dist"], t["area"], prep["refl"], cluster, prep["flags"])
     env.set_hierarchy(t["parent"], t["child1"], t["child2"], t["face"])
+    if poly_form_factor:                                              # MakeTransfer: polygon-to-differential form factor for near pairs
+        env.set_windings(t["wind_first"], t["wind_count"], t["wind_points"])
     if prep["needs_bump"].any() and world == 1:                       # TotalLight.Light[1..3] of the bump-mapped leaf patches (single GPU)
         env.set_bump(prep["needs_bump"], prep["bump_basis"])
     nnz = env.build_transfers(prep["pvs"])

@@ -45,8 +45,12 @@ struct PatchesDev {
     DevBuf<float4> normal_dist;     // normal.xyz, plane_dist
     DevBuf<float4> refl;            // reflectivity.rgb, sky flag (1.0 = sky)
     DevBuf<int32_t> cluster;
+    // Patch.Winding (common/types/patch.go): {first point, count} per patch + the points, clockwise seen from the front; empty = MakeTransfer
+    // uses the differential form factor everywhere (vrad_patches_set_windings)
+    DevBuf<int2> wind; DevBuf<float4> wind_pts; bool has_windings = false;
     std::vector<int32_t> h_cluster;
     std::vector<uint8_t> h_flags;
+    std::vector<float> h_normal;                // for the winding orientation check
     std::vector<float> h_area, h_refl;          // host copies for the hierarchy checks / collect weights
     // patch hierarchy (Patch.Parent / Child1 / FaceNumber, common/types/patch.go:33,49-51); empty = flat
     bool hier = false;
@@ -331,6 +335,7 @@ int group_transfers_info(vrad_env* g, int64_t* row0, int64_t* row1, int64_t* nnz
 int group_transfers_download(vrad_env* g, int64_t* rowptr, int32_t* col, float* w);
 int group_direct_light(vrad_env* g, int64_t n, const float* pos3, const float* normal3, int n_lights, const vrad_light* lights, float* rgb_out);
 int group_set_bump(vrad_env* g, int n, const uint8_t* needs_bump, const float* bump_normals9);
+int group_set_windings(vrad_env* g, int n, const int32_t* first, const int32_t* count, int n_points, const float* points3);
 int group_bounce(vrad_env* g, const float* emit0_rgb, int n_bounces, int early_out, float* total_rgb_out, float added_last[3], int* bounces_done);
 inline int group_unsupported(const char* what) { set_error("%s is not available on a multi-GPU handle (vrad_env_create_multi)", what); return VRAD_E_UNSUPPORTED; }
 }

@@ -186,6 +186,10 @@ int group_set_bump(vrad_env* g, int n, const uint8_t* needs_bump, const float* b
     return group_all(g, [&](vrad_env* c) -> int { return vrad_patches_set_bump(c, n, needs_bump, bump_normals9); });
 }
 
+int group_set_windings(vrad_env* g, int n, const int32_t* first, const int32_t* count, int n_points, const float* points3) {
+    return group_all(g, [&](vrad_env* c) -> int { return vrad_patches_set_windings(c, n, first, count, n_points, points3); });
+}
+
 int group_build_transfers(vrad_env* g, int n_clusters, const uint8_t* pvs, int64_t* nnz_out) {
     std::vector<int64_t> nnz(g->multi->world, 0);
     int rc = group_run(g, [&](vrad_env* c, int r) -> int { return vrad_build_transfers(c, n_clusters, pvs, &nnz[r]); });

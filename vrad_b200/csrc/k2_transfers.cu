@@ -44,10 +44,43 @@ struct PatchView {
     const float4* origin_area;
     const float4* normal_dist;
     const float4* refl;        // .w = sky flag
+    const int2*   wind;        // Patch.Winding {first point, count}; nullptr = differential form factor everywhere
+    const float4* wind_pts;
 };
 
+// Form factor from the emitter's polygon to the differential receiver (upstream vismat.cpp uses it for near pairs; SURVEY App. B.3
+// "optional"): the contour integral of Hottel / Baum -- for every edge of the polygon, the angle it subtends at the receiver times
+// the unit normal of the plane through the receiver and the edge, dotted with the receiver's normal; the sum over the edges is
+// 2*pi times the fraction of the receiver's hemisphere the polygon covers.  Returned per unit emitter area and without the 1/pi
+// (MakeTransfer divides by pi and multiplies by the area, as for the differential form).  Windings are clockwise seen from the
+// emitter's front, which makes the sum positive for a receiver in front of it.  The angle comes from asin of the cross product's
+// length, as upstream (exact up to 90 degrees per edge).  PARITY UNPINNED (not in the reference).
+__device__ __forceinline__ float poly_to_diff_form_factor(const PatchView& P, int j, float area_j, const float4 oi, const float4 ni) {
+    const int2 w = __ldg(&P.wind[j]);
+    if (w.y < 3) return __int_as_float(0x7fc00000);          // no polygon for this patch: the caller keeps the differential form
+    float ff = 0.0f;
+    for (int k = 0; k < w.y; k++) {
+        const float4 p1 = __ldg(&P.wind_pts[w.x + k]);
+        const float4 p2 = __ldg(&P.wind_pts[w.x + (k + 1 < w.y ? k + 1 : 0)]);
+        float ax = p1.x - oi.x, ay = p1.y - oi.y, az = p1.z - oi.z;
+        float bx = p2.x - oi.x, by = p2.y - oi.y, bz = p2.z - oi.z;
+        const float la = sqrtf(((ax * ax) + (ay * ay)) + (az * az)), lb = sqrtf(((bx * bx) + (by * by)) + (bz * bz));
+        if (la > 0.0f) { const float r = 1.0f / la; ax = ax * r; ay = ay * r; az = az * r; }
+        if (lb > 0.0f) { const float r = 1.0f / lb; bx = bx * r; by = by * r; bz = bz * r; }
+        float gx = (ay * bz) - (az * by), gy = (az * bx) - (ax * bz), gz = (ax * by) - (ay * bx);
+        const float sin_alpha = sqrtf(((gx * gx) + (gy * gy)) + (gz * gz));
+        if (sin_alpha > 1.0f) return 0.0f;
+        if (sin_alpha > 0.0f) {
+            const float m = asinf(sin_alpha) * (1.0f / sin_alpha);
+            gx = gx * m; gy = gy * m; gz = gz * m;
+        }
+        ff = ff + (((gx * ni.x) + (gy * ni.y)) + (gz * ni.z));
+    }
+    return ff * (0.5f / area_j);
+}
+
 // MakeTransfer weight (0 = nothing transfers).  Same operation order as the CPU formulation.
-__device__ __forceinline__ float transfer_weight(const float4 oi, const float4 ni, const float4 oj, const float4 nj, float sky_j) {
+__device__ __forceinline__ float transfer_weight(const PatchView& P, const float4 oi, const float4 ni, int j, const float4 oj, const float4 nj, float sky_j) {
     if (sky_j != 0.0f || !(oj.w > 0.0f)) return 0.0f;
     const float side = ((oj.x * ni.x) + (oj.y * ni.y)) + (oj.z * ni.z);
     if (!(side > ni.w + kPlaneTestEpsilon)) return 0.0f;
@@ -59,8 +92,13 @@ __device__ __forceinline__ float transfer_weight(const float4 oi, const float4 n
     dx = dx * r; dy = dy * r; dz = dz * r;
     const float d1 = ((dx * ni.x) + (dy * ni.y)) + (dz * ni.z);
     const float d2 = ((dx * nj.x) + (dy * nj.y)) + (dz * nj.z);
-    const float scale = -(d1 * d2) / ((len * len) * kPiF);
+    float scale = -(d1 * d2) / ((len * len) * kPiF);
     if (!(scale > 0.0f)) return 0.0f;
+    if (P.wind != nullptr && ((len * len) * kPiF) * 0.04f < oj.w) {          // emitter large for its distance: integrate over its polygon
+        const float ff = poly_to_diff_form_factor(P, j, oj.w, oi, ni);
+        if (ff == ff) scale = ff / kPiF;                                     // NaN: keep the differential form
+        if (!(scale > 0.0f)) return 0.0f;
+    }
     const float trans = oj.w * scale;
     if (!(trans > kTransEpsilon)) return 0.0f;
     return trans;
@@ -122,8 +160,8 @@ k2_visibility(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __
                     if (!(mirror && j < i)) {                       // otherwise thread (j, i) covers this pair
                         const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
                         const float sky_j = __ldg(&P.refl[j]).w;
-                        pass_ij = sky_i == 0.0f && transfer_weight(oi, ni, oj, nj, sky_j) != 0.0f;
-                        pass_ji = mirror && sky_j == 0.0f && transfer_weight(oj, nj, oi, ni, sky_i) != 0.0f;
+                        pass_ij = sky_i == 0.0f && transfer_weight(P, oi, ni, j, oj, nj, sky_j) != 0.0f;
+                        pass_ji = mirror && sky_j == 0.0f && transfer_weight(P, oj, nj, i, oi, ni, sky_i) != 0.0f;
                         if (HIER && (pass_ij || pass_ji)) {           // cheap tests first: the parent-chain walk runs only for pairs that could transfer
                             const int4 tj = __ldg(&tree[j]);
                             const bool other_face = !(ti.z >= 0 && ti.z == tj.z);       // "don't check patches on the same face"
@@ -201,8 +239,8 @@ k2_visibility_stream(DevScene S, PatchView P, int nloc, int64_t row0, const int3
                     if (!(mirror && j < i)) {           // otherwise pair (j, i) of row j covers this one
                         const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
                         const float sky_j = __ldg(&P.refl[j]).w;
-                        pass_ij = sky_i == 0.0f && transfer_weight(oi, ni, oj, nj, sky_j) != 0.0f;
-                        pass_ji = mirror && sky_j == 0.0f && transfer_weight(oj, nj, oi, ni, sky_i) != 0.0f;
+                        pass_ij = sky_i == 0.0f && transfer_weight(P, oi, ni, j, oj, nj, sky_j) != 0.0f;
+                        pass_ji = mirror && sky_j == 0.0f && transfer_weight(P, oj, nj, i, oi, ni, sky_i) != 0.0f;
                         if (HIER && (pass_ij || pass_ji)) {
                             const int4 tj = __ldg(&tree[j]);
                             const bool other_face = !(ti.z >= 0 && ti.z == tj.z);
@@ -297,7 +335,7 @@ k2_visibility_topdown(DevScene S, PatchView P, int n_rows, const int32_t* __rest
                     j = acc[p];
                     if (j != i) {
                         const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
-                        need = transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w) != 0.0f;
+                        need = transfer_weight(P, oi, ni, j, oj, nj, __ldg(&P.refl[j]).w) != 0.0f;
                         if (i < j) { b = oj; bn = nj; } else { a = oj; an = nj; }
                     }
                 }
@@ -379,7 +417,7 @@ k2_estimate(DevScene S, PatchView P, int nloc, int64_t row0, const int32_t* __re
                 const int j = __ldg(&cand_idx[c0 + p]);
                 if (j != i) {
                     const float4 oj = __ldg(&P.origin_area[j]), nj = __ldg(&P.normal_dist[j]);
-                    bool ok = transfer_weight(oi, ni, oj, nj, __ldg(&P.refl[j]).w) != 0.0f;
+                    bool ok = transfer_weight(P, oi, ni, j, oj, nj, __ldg(&P.refl[j]).w) != 0.0f;
                     if (HIER && ok) {
                         const int4 tj = __ldg(&tree[j]);
                         ok = !(ti.z >= 0 && ti.z == tj.z) && emitter_accepted(P, tree, oi, oj, tj);
@@ -437,7 +475,7 @@ __global__ void k2_fill(PatchView P, int nloc, int64_t row0, const int32_t* __re
         if ((m >> lane) & 1u) {
             const int j = cand_idx[c0 + (wd - w0) * 32 + lane];
             const int k = pos + __popc(m & ((1u << lane) - 1u));
-            tr[base + k] = make_int2(j, __float_as_int(transfer_weight(oi, ni, P.origin_area[j], P.normal_dist[j], P.refl[j].w)));
+            tr[base + k] = make_int2(j, __float_as_int(transfer_weight(P, oi, ni, j, P.origin_area[j], P.normal_dist[j], P.refl[j].w)));
         }
         pos += __popc(m);
     }
@@ -535,7 +573,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     const int world = e->cfg.world;
     const int64_t rpr = ((int64_t)N + world - 1) / world;
     int64_t row0 = std::min<int64_t>(N, e->cfg.rank * rpr), row1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
-    PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p};
+    PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p, P.has_windings ? P.wind.p : nullptr, P.has_windings ? P.wind_pts.p : nullptr};
     static const bool no_balance = [] { const char* v = getenv("VRAD_K2_BALANCE"); return v && v[0] == '0'; }();
     if (world > 1 && has_comm(e) && !no_balance) {
         // Balance the contiguous row blocks by estimated transfers instead of by row count (collective): every

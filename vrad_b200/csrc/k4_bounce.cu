@@ -770,6 +770,8 @@ int vrad_patches_upload(vrad_env* e, int n, const float* origin3, const float* n
     P.h_area.assign(area, area + n); P.h_refl.assign(reflectivity3, reflectivity3 + 3 * (size_t)n);
     P.hier = false; P.n_interior = 0; P.h_root_cluster.clear();
     P.bump = false; P.h_needs_bump.clear();
+    P.has_windings = false;
+    P.h_normal.assign(normal3, normal3 + 3 * (size_t)n);
     for (int i = 0; i < n; i++) {
         oa[i] = make_float4(origin3[3 * i], origin3[3 * i + 1], origin3[3 * i + 2], area[i]);
         nd[i] = make_float4(normal3[3 * i], normal3[3 * i + 1], normal3[3 * i + 2], plane_dist[i]);
@@ -784,6 +786,51 @@ int vrad_patches_upload(vrad_env* e, int n, const float* origin3, const float* n
     VRAD_CUDA_CHECK(cudaMemcpyAsync(P.cluster.p, P.h_cluster.data(), (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     P.n = n;
+    e->transfers.ready = false;
+    return VRAD_OK;
+}
+
+int vrad_patches_set_windings(vrad_env* e, int n, const int32_t* first, const int32_t* count, int n_points, const float* points3) {
+    VRAD_MULTI(e, group_set_windings(e, n, first, count, n_points, points3));
+    if (!e || n < 0 || n_points < 0) { set_error("vrad_patches_set_windings: bad arguments"); return VRAD_E_INVALID; }
+    PatchesDev& P = e->patches;
+    if (n == 0) {                                             // back to the differential form factor everywhere
+        P.has_windings = false; P.wind.release(); P.wind_pts.release();
+        e->transfers.ready = false;
+        return VRAD_OK;
+    }
+    if (!first || !count || (n_points > 0 && !points3)) { set_error("vrad_patches_set_windings: bad arguments"); return VRAD_E_INVALID; }
+    if (P.n == 0 || n != P.n) { set_error("vrad_patches_set_windings: %d windings for %d uploaded patches", n, P.n); return VRAD_E_STATE; }
+    VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    std::vector<int2> w(n);
+    std::vector<float4> pts((size_t)n_points + 1);
+    for (int i = 0; i < n_points; i++) pts[i] = make_float4(points3[3 * (size_t)i], points3[3 * (size_t)i + 1], points3[3 * (size_t)i + 2], 0.f);
+    std::vector<uint8_t> owned((size_t)n_points + 1, 0);
+    for (int i = 0; i < n; i++) {
+        const int f = first[i], c = count[i];
+        if (c < 0 || f < 0 || (int64_t)f + c > n_points) { set_error("vrad_patches_set_windings: winding of patch %d ([%d, %d + %d)) is outside the %d points", i, f, f, c, n_points); return VRAD_E_INVALID; }
+        w[i] = make_int2(f, c < 3 ? 0 : c);
+        if (c < 3) continue;
+        // the contour integral assumes the points run clockwise seen from the patch's front (the BSP face convention,
+        // kept by ClipWindingEpsilon); a winding the other way round is reversed here -- unless it shares its points with another patch
+        double nx = 0, ny = 0, nz = 0;                       // Newell normal: along the patch normal for a counter-clockwise winding
+        for (int k = 0; k < c; k++) {
+            const float4 a = pts[f + k], b = pts[f + (k + 1 < c ? k + 1 : 0)];
+            nx += ((double)a.y - b.y) * ((double)a.z + b.z); ny += ((double)a.z - b.z) * ((double)a.x + b.x); nz += ((double)a.x - b.x) * ((double)a.y + b.y);
+        }
+        const double o = nx * P.h_normal[3 * (size_t)i] + ny * P.h_normal[3 * (size_t)i + 1] + nz * P.h_normal[3 * (size_t)i + 2];
+        bool shared = false;
+        for (int k = 0; k < c; k++) shared |= owned[f + k] != 0;
+        if (o > 0.0) {
+            if (shared) { set_error("vrad_patches_set_windings: patch %d is wound counter-clockwise and shares its points with another patch", i); return VRAD_E_INVALID; }
+            std::reverse(pts.begin() + f, pts.begin() + f + c);
+        }
+        for (int k = 0; k < c; k++) owned[f + k] = 1;
+    }
+    if (P.wind.alloc(n) || P.wind_pts.alloc((size_t)n_points + 1)) { set_error("out of device memory for patch windings"); return VRAD_E_NOMEM; }
+    VRAD_CUDA_CHECK(cudaMemcpy(P.wind.p, w.data(), (size_t)n * sizeof(int2), cudaMemcpyHostToDevice));
+    VRAD_CUDA_CHECK(cudaMemcpy(P.wind_pts.p, pts.data(), pts.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    P.has_windings = true;
     e->transfers.ready = false;
     return VRAD_OK;
 }

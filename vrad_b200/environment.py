@@ -301,6 +301,16 @@ class Environment:
         parent, child1, child2, face = i32(parent), i32(child1), i32(child2), i32(face)
         check(self._l.vrad_patches_set_hierarchy(self._h, C.c_int(parent.shape[0]), ptr(parent), ptr(child1), ptr(child2), ptr(face)))
 
+    def set_windings(self, first, count, points):
+        """Patch.Winding per uploaded patch (vrad_patches_subdivide's wind_first / wind_count / wind_points; None removes them):
+        build_transfers then uses the polygon-to-differential form factor for emitters that are large for their distance."""
+        if first is None:
+            check(self._l.vrad_patches_set_windings(self._h, C.c_int(0), None, None, C.c_int(0), None))
+            return
+        first = np.ascontiguousarray(first, np.int32); count = np.ascontiguousarray(count, np.int32)
+        points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        check(self._l.vrad_patches_set_windings(self._h, C.c_int(first.shape[0]), ptr(first), ptr(count), C.c_int(points.shape[0]), ptr(points)))
+
     def set_bump(self, needs_bump, bump_normals):
         """Patch.NeedsBumpMap + the three bump normals per patch ([N, 3, 3]); bounce() then accumulates TotalLight.Light[1..3]."""
         nb = np.ascontiguousarray(needs_bump, np.uint8); bn = np.ascontiguousarray(bump_normals, np.float32).reshape(-1, 9)

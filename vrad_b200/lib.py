@@ -26,7 +26,7 @@ SYMBOLS = [
     "vrad_comm_init", "vrad_version",
     "vrad_env_set_triangle_colors", "vrad_bsp_upload", "vrad_point_leafnum", "vrad_cluster_from_point",
     "vrad_sky_cameras_set", "vrad_sky_cameras_get", "vrad_test_lines_sky", "vrad_leafs_trace_to_sky",
-    "vrad_decompress_vis", "vrad_pvs_from_vis_lump", "vrad_patches_subdivide", "vrad_patches_set_hierarchy", "vrad_set_light_trace_flags",
+    "vrad_decompress_vis", "vrad_pvs_from_vis_lump", "vrad_patches_subdivide", "vrad_patches_set_hierarchy", "vrad_patches_set_windings", "vrad_set_light_trace_flags",
     "vrad_light_for_string", "vrad_lights_from_entities", "vrad_lights_from_patches",
     "vrad_bump_normals", "vrad_patches_set_bump", "vrad_bounce_bump_totals",
     "vrad_env_build_fast", "vrad_kd_build_binned_host",
