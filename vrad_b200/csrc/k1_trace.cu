@@ -399,6 +399,7 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         return 0;
     }
     const SortGrid G = sort_grid(e);
+    const int sort_lo = 30 - std::min(30, std::max(8, e->opt.k1_sort_bits));     // only the key's leading bits take part in the sort (one radix pass per 8)
     for (int64_t c0 = 0; c0 < n; c0 += kSortBatch) {
         const int64_t m = std::min(kSortBatch, n - c0);
         void *d_rec = nullptr, *d_k0 = nullptr, *d_k1 = nullptr, *d_i0 = nullptr, *d_i1 = nullptr, *d_tmp = nullptr;
@@ -407,7 +408,7 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         if (sorted) {
             if ((rc = scratch_get(e, 12, indexed ? 32 : (size_t)m * 32, &d_rec)) || (rc = scratch_get(e, 13, (size_t)m * 4, &d_k0)) || (rc = scratch_get(e, 14, (size_t)m * 4, &d_k1)) ||
                 (rc = scratch_get(e, 15, (size_t)m * 4, &d_i0)) || (rc = scratch_get(e, 16, (size_t)m * 4, &d_i1))) return rc;
-            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream);
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, sort_lo, 30, e->stream);
             if ((rc = scratch_get(e, 17, tmp_bytes + 16, &d_tmp))) return rc;
         }
         SegSource sub = src;
@@ -422,7 +423,7 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
             const int kb = (int)((m + 255) / 256);
             if (indexed) k1_sort_keys<true><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
             else k1_sort_keys<false><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
-            VRAD_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, 0, 30, e->stream));
+            VRAD_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t*)d_k0, (uint32_t*)d_k1, (const uint32_t*)d_i0, (uint32_t*)d_i1, (int)m, sort_lo, 30, e->stream));
         }
         const size_t sm = (size_t)e->scene.n_top * sizeof(int2);
         const uint32_t* pm = (const uint32_t*)d_i1; const float4* rc4 = indexed ? nullptr : (const float4*)d_rec; unsigned long long* ctr = (unsigned long long*)d_ctr;
