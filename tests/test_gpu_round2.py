@@ -209,3 +209,56 @@ def test_simulated_peers_runs_the_multi_gpu_kernel_on_one_device(s2_small_scene)
     torch.cuda.synchronize()
     assert np.isfinite(d_out.cpu().numpy()).all()
     env.close()
+
+
+def test_packed_streams_rows_over_several_column_windows():
+    """The 6-byte packed transfer streams (k4_pack): rows whose columns span several 65,536-column windows become several segments;
+    the result must equal the {col,w} pair kernel's to rounding and a float64 gather, and the single-GPU kernel and the work-item
+    (multi-GPU) kernel must agree bit for bit -- segments of a row are parts there, added in the same order."""
+    from vrad_b200.environment import Environment
+    rng = np.random.default_rng(5)
+    N = 200_000
+    env = Environment()
+    env.add_triangles(np.int32([0]), np.float32([[0, 0, 0, 1, 0, 0, 0, 1, 0]])); env.setup_acceleration_structure()
+    origin = rng.uniform(-100, 100, (N, 3)).astype(np.float32)
+    normal = np.tile(np.float32([0, 0, 1]), (N, 1))
+    refl = rng.uniform(0.2, 0.8, (N, 3)).astype(np.float32)
+    env.patches_upload(origin, normal, np.zeros(N, np.float32), np.ones(N, np.float32), refl)
+    # rows of 0 .. 900 entries: some empty, some inside one window, some over all four, some with > 32 in one window then a jump
+    want = rng.integers(1, 900, N); want[np.arange(N) % 8 != 1] = 0; want[9] = 40_000     # most rows empty; one longer than a segment may be
+    cols = []
+    for i in range(N):
+        if want[i] == 0: cols.append(np.empty(0, np.int32)); continue
+        lo, hi = (max(0, i - 30_000), min(N, i + 30_000)) if i % 16 == 1 else (0, N)        # one window (mostly) / every window
+        cols.append(np.unique(rng.integers(lo, hi, want[i])).astype(np.int32))
+    lens = np.array([len(c) for c in cols])
+    rp = np.zeros(N + 1, np.int64); np.cumsum(lens, out=rp[1:])
+    col = np.concatenate(cols)
+    w = rng.uniform(0.0, 1.0 / 900, rp[-1]).astype(np.float32)
+    emit0 = rng.uniform(0, 100, (N, 3)).astype(np.float32)
+    env.transfers_upload(0, N, rp, col, w)
+    env.set_option("k4_short", 0)                  # rows this sparse would otherwise go to the short-row kernel
+    out = {}
+    for name, opts in (("pairs", {"k4_pack": 0}), ("packed", {"k4_pack": 1}), ("packed_items", {"k4_pack": 1, "k4_items": 1}),
+                       ("pairs_items", {"k4_pack": 0, "k4_items": 1}), ("packed_items_seg512", {"k4_pack": 1, "k4_items": 1, "k4_seg": 512})):
+        for k in ("k4_items", "k4_pack"): env.set_option(k, opts.get(k, 0))
+        env.set_option("k4_seg", opts.get("k4_seg", 16384))
+        out[name], _, _ = env.bounce(emit0, 3)
+        out[name + "_1"], _, _ = env.bounce(emit0, 1)
+    env.close()
+    # float64 reference of three bounces
+    import scipy.sparse as sp
+    A = sp.csr_matrix((w.astype(np.float64), col, rp), shape=(N, N))
+    emit = emit0.astype(np.float64); total = np.zeros((N, 3))
+    for _ in range(3):
+        add = A @ (emit * refl.astype(np.float64)); total += add; emit = add
+    for name, t in out.items():
+        if not name.endswith("_1"): assert np.abs(t - total).max() <= 1e-5 * np.abs(total).max(), name
+    diff = np.nonzero((out["packed_1"] != out["packed_items_1"]).any(axis=1))[0]
+    nwin = np.array([len(np.unique((c - c[0]) >> 16)) if len(c) else 0 for c in cols])
+    cmp = {f"{a}~{b}": (int((out[a] != out[b]).any(axis=1).sum()), float(np.abs(out[a] - out[b]).max() / np.abs(out[a]).max()))
+           for a, b in (("pairs_1", "pairs_items_1"), ("packed_1", "pairs_1"), ("packed_items_1", "pairs_items_1"), ("packed_1", "packed_items_1"))}
+    assert cmp["packed_1~pairs_1"][0] > 1000 and cmp["packed_1~pairs_1"][1] < 1e-6          # the packed kernel did run: several-segment rows round differently
+    assert cmp["pairs_1~pairs_items_1"][0] <= 1                                             # only the 36k-entry row is split in the pair plan
+    assert diff.size == 0, (cmp, diff.size, diff[:8], nwin[diff[:8]], lens[diff[:8]], np.bincount(nwin[diff]), np.bincount(nwin))
+    assert np.abs(out["packed_items_seg512"] - out["packed"]).max() <= 1e-6 * np.abs(total).max()

@@ -21,9 +21,10 @@ env.set_async(True)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 res = {"world": world, "nnz_local_rank0": nnz, "rows_rank0": [row0, row1]}
 ref = None
-# (block, persist, pool, pdl, graph)
-for blk, per, pool, pdl, graph in ((192, 1, 12, 1, 1), (192, 1, 12, 0, 1), (192, 1, 12, 1, 0), (192, 1, 0, 1, 1), (192, 1, 25, 1, 1), (256, 1, 12, 1, 1), (192, 0, 0, 1, 1)):
-    for k, v in (("k4_block", blk), ("k4_persist", per), ("k4_pool", pool), ("k4_pdl", pdl), ("k4_graph", graph)):
+# (block, persist, pool, pdl, graph, pack)
+for blk, per, pool, pdl, graph, pack in ((192, 1, 12, 1, 1, 1), (192, 1, 12, 1, 1, 0), (192, 1, 12, 0, 1, 1), (192, 1, 12, 1, 0, 1), (192, 1, 0, 1, 1, 1), (192, 1, 25, 1, 1, 1),
+                                         (256, 1, 12, 1, 1, 1), (192, 0, 0, 1, 1, 1), (192, 1, 25, 1, 1, 0)):
+    for k, v in (("k4_block", blk), ("k4_persist", per), ("k4_pool", pool), ("k4_pdl", pdl), ("k4_graph", graph), ("k4_pack", pack)):
         env.set_option(k, v)
     env.bounce(e0, 100, out=out, want_added=False)
     if world > 1: dist.barrier()
@@ -36,8 +37,8 @@ for blk, per, pool, pdl, graph in ((192, 1, 12, 1, 1), (192, 1, 12, 0, 1), (192,
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     got = out.cpu().numpy()
     if ref is None: ref = got
-    res[f"block{blk}_persist{per}_pool{pool}_pdl{pdl}_graph{graph}"] = {"us_per_bounce": float(t.item()), "max_rel_vs_first": float(np.abs(got - ref).max() / np.abs(ref).max())}
-    if rank == 0: print(blk, per, pool, pdl, graph, float(t.item()), flush=True)
+    res[f"block{blk}_persist{per}_pool{pool}_pdl{pdl}_graph{graph}_pack{pack}"] = {"us_per_bounce": float(t.item()), "max_rel_vs_first": float(np.abs(got - ref).max() / np.abs(ref).max())}
+    if rank == 0: print(blk, per, pool, pdl, graph, pack, float(t.item()), float(np.abs(got - ref).max() / np.abs(ref).max()), flush=True)
 env.close()
 # the same map with its patch hierarchy: leaf rows by peer stores (k4_hier_p2p=1) against the all-gather pass per bounce (0)
 hs = scenes.multi_room_hier(nx=12, ny=11); tr = hs.meta["tree"]

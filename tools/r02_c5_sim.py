@@ -24,15 +24,15 @@ print(res, flush=True)
 e0 = torch.full((N, 3), 100.0, device=dev); out = torch.empty_like(e0)
 env.set_async(True)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for seg, pool, blk in ((2048, 12, 192), (8192, 12, 192), (32768, 12, 192), (8192, 0, 192), (8192, 12, 256)):
-    env.set_option("k4_seg", seg); env.set_option("k4_pool", pool); env.set_option("k4_block", blk)
+for seg, pool, blk, pack in ((16384, 12, 192, 0), (16384, 12, 192, 1), (16384, 25, 192, 1), (16384, 25, 192, 0), (4096, 12, 192, 1), (16384, 12, 256, 1)):
+    env.set_option("k4_seg", seg); env.set_option("k4_pool", pool); env.set_option("k4_block", blk); env.set_option("k4_pack", pack)
     env.bounce(e0, 4, out=out, want_added=False)
     torch.cuda.synchronize(); ev0.record()
     env.bounce(e0, 20, out=out, want_added=False)
     ev1.record(); torch.cuda.synchronize()
     us = ev0.elapsed_time(ev1) / 20 * 1e3
-    res[f"seg{seg}_pool{pool}_block{blk}"] = {"us_per_bounce": us, "frac_of_hbm_peak": (8 * nnz + 40 * (row1 - row0) + 12 * N) / us / 1e3 / 6455.3}
-    print(seg, pool, blk, us, flush=True)
+    res[f"seg{seg}_pool{pool}_block{blk}_pack{pack}"] = {"us_per_bounce": us, "frac_of_hbm_peak": (8 * nnz + 40 * (row1 - row0) + 12 * N) / us / 1e3 / 6455.3}
+    print(seg, pool, blk, pack, us, float(out.sum().item()), flush=True)
 env.close()
-json.dump(res, open("gpurun_out/r02_c5_sim.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/r02_c5_sim_pack.json", "w"), indent=1)
 print(json.dumps(res))

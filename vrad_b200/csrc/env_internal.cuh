@@ -96,6 +96,18 @@ struct TransfersDev {
     DevBuf<float4>  part_sum;       // one slot per part of a split row
     DevBuf<int32_t> row_ctr;        // arrivals per local row (split rows only; the finisher resets it)
     int n_items = 0, n_slots = 0, n_blocks = 0, seg_shift = 11, plan_warps = 8, pool_begin = 0;
+    // Packed transfer streams (K4, k4_pack): the same entries as tr[], split into a weight stream (f32) and a column stream (u16,
+    // relative to its segment's base) -- 6 bytes per transfer instead of 8.  A segment is a run of a row's entries whose columns
+    // lie within one 65,536-column window counted from the row's first column (and at most pk_max_seg entries); it starts on a
+    // 64-entry boundary of both streams (padding: weight 0, column offset 0), and inside each group of 64 the entries are interleaved
+    // (positions 2L, 2L+1 = entries L, 32+L) so that one vector load hands a lane two entries 32 apart.
+    //   segment int4 = {first entry (position in the packed streams) lo, hi, padded entries, column base}
+    DevBuf<float>    pk_w;
+    DevBuf<uint16_t> pk_c;
+    DevBuf<int4>     pk_segs;
+    DevBuf<int32_t>  pk_seg_ptr;    // row1-row0+1 offsets into pk_segs
+    int64_t pk_entries = 0; int pk_n_segs = 0; bool packed = false;
+    bool plan_packed = false;       // the items of the plan below are segments of the packed streams
     int64_t plan_serial = 0;        // bumped by every re-plan (invalidates the captured bounce graph)
     int64_t rows_serial = 0;        // bumped when the resident rows change (vrad_build_transfers / vrad_transfers_upload: collective calls)
 };
@@ -201,6 +213,8 @@ struct EnvOptions {
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
     int k4_block = 192;    // VRAD_K4_BLOCK: threads per work-item gather block: 192 (6 blocks/SM, 56 registers) or 256 (5 blocks/SM, 48 registers: spills in the loop)
     int k2_stream = 0;     // VRAD_K2_STREAM: pass A of the transfer build as compacted ray queues with lane refill (experiment, slower: DESIGN section 7; 0 = one ray slot per (row, candidate) thread)
+    int k4_short = -1;     // VRAD_K4_SHORT: the short-row gather (8 lanes per row) on one GPU: -1 = where rows average < 400 transfers, 0 = never, 1 = always
+    int k4_pack = 1;       // VRAD_K4_PACK: gather from the packed 6-byte streams (0 = from the {col,w} pairs)
     int k4_l2_mb = 0;      // VRAD_K4_L2_MB: MB of L2 set aside for the head of the transfer stream of the multi-GPU gather (0 = off)
     int k4_hier_p2p = 1;   // VRAD_K4_HIER_P2P: patch hierarchy on several GPUs: leaf rows by peer stores (0 = all-gather pass per bounce)
     int k4_pool = 12;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early

@@ -13,6 +13,7 @@
 // bytes per bounce: 8*nnz + 40*N; the kernel is HBM-bound on the 8*nnz stream.
 // One warp per row, warp-shuffle reduction, collect step fused into the epilogue.
 #include "env_internal.cuh"
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -117,6 +118,175 @@ k4_gather(int nloc, int64_t row0, const int64_t* __restrict__ rowptr, const int2
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Packed transfer streams (TransfersDev::pk_*): 6 bytes per transfer instead of the 8 of the {col, w} pair -- the gather is
+// HBM-bound on that stream, so the bytes are the time.  Columns of a row ascend and stay within the patches its cluster sees,
+// so a 16-bit offset from a per-segment base covers them: one segment per row on the C4 map, a handful on the C5 map (a row
+// there spans several 65,536-patch windows).  Weights stay f32, bit for bit.
+// ---------------------------------------------------------------------------------------------------------
+// Warp-uniform walk over the segments of one row of tr[]: f(index in row, first entry (relative), entries, column base).
+template <typename F>
+__device__ __forceinline__ void for_each_segment(const int2* __restrict__ tr, int64_t k0, int len, int max_seg, F f) {
+    if (len <= 0) return;
+    const int lane = threadIdx.x & 31;
+    const int col0 = tr[k0].x;
+    int seg_start = 0, n = 0;
+    auto emit = [&](int a, int b) {
+        const int base = col0 + (((tr[k0 + a].x - col0) >> 16) << 16);
+        while (a < b) { const int l = min(b - a, max_seg); f(n++, a, l, base); a += l; }
+    };
+    for (int c = 0; c < len; c += 32) {
+        const int en = c + lane;
+        bool brk = false;
+        if (en < len && en > 0) brk = ((tr[k0 + en].x - col0) >> 16) != ((tr[k0 + en - 1].x - col0) >> 16);
+        unsigned m = __ballot_sync(0xffffffffu, brk);
+        while (m) {
+            const int pos = c + __ffs(m) - 1;
+            m &= m - 1;
+            emit(seg_start, pos);
+            seg_start = pos;
+        }
+    }
+    emit(seg_start, len);
+}
+
+__global__ void __launch_bounds__(256)
+k4_pack_count(int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen, const int2* __restrict__ tr, int max_seg,
+              int32_t* __restrict__ n_segs, int64_t* __restrict__ padded) {
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= nloc) return;
+    int ns = 0; int64_t pad = 0;
+    for_each_segment(tr, rowptr[row], rowlen[row], max_seg, [&](int, int, int l, int) { ns++; pad += (l + 63) & ~63; });
+    if ((threadIdx.x & 31) == 0) { n_segs[row] = ns; padded[row] = pad; }
+}
+
+__global__ void __launch_bounds__(256)
+k4_pack_fill(int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen, const int2* __restrict__ tr, int max_seg,
+             const int32_t* __restrict__ seg_ptr, const int64_t* __restrict__ pk_rowptr, int4* __restrict__ segs,
+             float* __restrict__ pw, uint16_t* __restrict__ pc) {
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= nloc) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t k0 = rowptr[row];
+    int64_t out = pk_rowptr[row];
+    const int s0 = seg_ptr[row];
+    for_each_segment(tr, k0, rowlen[row], max_seg, [&](int idx, int a, int l, int base) {
+        const int lp = (l + 63) & ~63;
+        if (lane == 0) segs[s0 + idx] = make_int4((int)(uint32_t)(out & 0xffffffff), (int)(out >> 32), lp, base);
+        for (int t = lane; t < lp; t += 32) {
+            // position t of a 64-entry group holds entry (t odd ? 32 : 0) + t/2 of the group: the gather's lane L reads positions
+            // 2L, 2L+1 with one vector load and so holds entries L and 32+L -- its er[] gathers then run over CONSECUTIVE entries
+            // across the warp, like the pair kernel's (adjacent columns share cache lines; with lanes on entries 2L, 2L+1 every
+            // line was touched by two gather instructions: 305 us per bounce on the C4 matrix against 276 us for the pairs)
+            const int src = (t & ~63) + ((t & 1) << 5) + ((t & 63) >> 1);
+            int2 en = make_int2(base, 0);
+            if (src < l) en = tr[k0 + a + src];
+            pw[out + t] = __int_as_float(en.y);
+            pc[out + t] = (uint16_t)(en.x - base);
+        }
+        out += lp;
+    });
+}
+
+// The gather from the packed streams, one warp per row (the single-GPU form of k4_gather above): a lane takes two consecutive
+// entries per step -- one 8-byte weight load and one 4-byte column load, both coalesced -- four steps in flight.
+struct PackedRows { const int32_t* seg_ptr; const int4* segs; const float* w; const uint16_t* c; };
+
+template <int kPackUnroll>
+__device__ __forceinline__ void gather_packed_segments(const PackedRows& P, int sg0, int sg1, const float4* __restrict__ er, int lane,
+                                                       float& s0, float& s1, float& s2) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int sg = sg0; sg < sg1; sg++) {
+        const int4 d = __ldg(&P.segs[sg]);
+        const int64_t k0 = (int64_t)(uint32_t)d.x | ((int64_t)d.y << 32);
+        const int npairs = d.z >> 1, base = d.w;
+        const float2* __restrict__ w2 = reinterpret_cast<const float2*>(P.w + k0);
+        const uint32_t* __restrict__ c2 = reinterpret_cast<const uint32_t*>(P.c + k0);
+        float2 cw[kPackUnroll], nw[kPackUnroll];
+        uint32_t cc[kPackUnroll], nc[kPackUnroll];
+        int p = lane;
+#pragma unroll
+        for (int j = 0; j < kPackUnroll; j++) {
+            const bool in = p + 32 * j < npairs;
+            cw[j] = in ? __ldcs(&w2[p + 32 * j]) : make_float2(0.f, 0.f);
+            cc[j] = in ? __ldcs(&c2[p + 32 * j]) : 0u;
+        }
+        for (; p < npairs; p += 32 * kPackUnroll) {
+#pragma unroll
+            for (int j = 0; j < kPackUnroll; j++) {
+                const bool in = p + 32 * (kPackUnroll + j) < npairs;
+                nw[j] = in ? __ldcs(&w2[p + 32 * (kPackUnroll + j)]) : make_float2(0.f, 0.f);
+                nc[j] = in ? __ldcs(&c2[p + 32 * (kPackUnroll + j)]) : 0u;
+            }
+            float4 x[2 * kPackUnroll];
+#pragma unroll
+            for (int j = 0; j < kPackUnroll; j++) {
+                x[2 * j] = __ldg(&er[base + (int)(cc[j] & 0xffffu)]);
+                x[2 * j + 1] = __ldg(&er[base + (int)(cc[j] >> 16)]);
+            }
+#pragma unroll
+            for (int j = 0; j < kPackUnroll; j++) {
+                s0 += cw[j].x * x[2 * j].x; s1 += cw[j].x * x[2 * j].y; s2 += cw[j].x * x[2 * j].z;
+                s0 += cw[j].y * x[2 * j + 1].x; s1 += cw[j].y * x[2 * j + 1].y; s2 += cw[j].y * x[2 * j + 1].z;
+            }
+#pragma unroll
+            for (int j = 0; j < kPackUnroll; j++) { cw[j] = nw[j]; cc[j] = nc[j]; }
+        }
+        if (sg1 - sg0 > 1) {
+            // a row of several segments: each segment's sum is reduced on its own and the sums are added in segment order, lane-strided
+            // and then by the xor tree -- the arithmetic of combine_parts() below, where the multi-GPU kernel treats the segments of
+            // such a row as parts (so that one GPU and several give the same bits)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == ((sg - sg0) & 31)) { a0 += s0; a1 += s1; a2 += s2; }
+            s0 = s1 = s2 = 0.f;
+        }
+    }
+    if (sg1 - sg0 > 1) { s0 = a0; s1 = a1; s2 = a2; }
+}
+
+template <int kPackUnroll, int kMinBlocks>
+__global__ void __launch_bounds__(kGatherBlock, kMinBlocks)
+k4_gather_packed(int nloc, int64_t row0, PackedRows P, const float4* __restrict__ er, const float4* __restrict__ refl,
+                 float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * kGatherWarps + warp;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    if (row < nloc) {
+        gather_packed_segments<kPackUnroll>(P, P.seg_ptr[row], P.seg_ptr[row + 1], er, lane, s0, s1, s2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            const float4 r = refl[row0 + row];
+            if (r.w == 0.0f) {                                              // CollectLight, leaf patch
+                float4 t = total[row];
+                t.x += s0; t.y += s1; t.z += s2;
+                total[row] = t;
+                er_next[row0 + row] = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                e0 = s0; e1 = s1; e2 = s2;
+            } else {
+                er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);     // sky: emit = 0
+            }
+        }
+    }
+    __shared__ float sm[kGatherWarps][3];
+    if (lane == 0) { sm[warp][0] = e0; sm[warp][1] = e1; sm[warp][2] = e2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < kGatherWarps; k++) a += sm[k][threadIdx.x];
+        partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // The gather.  One warp per WORK ITEM (TransfersDev::items): a whole row, or -- for a row longer than `seg`
 // entries -- one `seg`-entry part of it.  Entries are {col, w} pairs -- the reference's Transfer struct
 // (common/types/transfer.go:3-6) -- read as one coalesced 64-bit load per lane with lanes on CONSECUTIVE
@@ -158,6 +328,8 @@ struct GatherAux {                 // rarely used pointers, kept in the paramete
     uint32_t wait_rel, signal_rel; // epochs relative to flags[kFlagBase]; wait_rel 0 = nothing to wait for
     int wait_world;
     int pool_begin, n_items;       // items [pool_begin, n_items) belong to no block: whoever runs dry takes them one by one (flags[kFlagPool])
+    const float* pk_w;             // PACKED only: the weight and column streams (TransfersDev::pk_w / pk_c)
+    const uint16_t* pk_c;
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -282,7 +454,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // access-policy window (k4_l2_mb), which keeps the head of the stream resident from bounce to bounce
 template <bool CS> __device__ __forceinline__ int2 load_tr(const int2* p) { return CS ? __ldcs(p) : *p; }
 
-template <bool MULTI, int WARPS, bool CS = true>
+// PACKED: an item is one SEGMENT of the packed streams -- {row, padded entries | parts | part index, first entry / 64, column base} --
+// and a lane holds kGatherUnroll / 2 pairs of entries (8-byte weight load + 4-byte column load) instead of kGatherUnroll {col,w} pairs;
+// a row of several segments is a row of several parts.  Same lane-to-entry mapping as k4_gather_packed: the two kernels agree bit for bit.
+template <bool CS> __device__ __forceinline__ float2 load_w2(const float2* p) { return CS ? __ldcs(p) : *p; }
+template <bool CS> __device__ __forceinline__ uint32_t load_c2(const uint32_t* p) { return CS ? __ldcs(p) : *p; }
+
+template <bool MULTI, int WARPS, bool CS = true, bool PACKED = false>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 5 : 6)
 k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ items, const int32_t* __restrict__ item_slot, int64_t row0,
                 const int2* __restrict__ tr, const float4* er, const float4* __restrict__ refl,
@@ -314,8 +492,22 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
     int w = claim();
     int4 it = make_int4(0, 0, 0, 0);
     if (w != kNoItem) it = __ldg(&items[w]);
-    int2 cur[kGatherUnroll], nxt[kGatherUnroll];
-    {
+    constexpr int kHalf = kGatherUnroll / 2;
+    int2 cur[PACKED ? 1 : kGatherUnroll], nxt[PACKED ? 1 : kGatherUnroll];
+    float2 cw[PACKED ? kHalf : 1], nw[PACKED ? kHalf : 1];
+    uint32_t cc[PACKED ? kHalf : 1], nc[PACKED ? kHalf : 1];
+    if (PACKED) {
+        const int64_t k0 = (int64_t)(uint32_t)it.z << 6;
+        const float2* w0 = reinterpret_cast<const float2*>(A.pk_w + k0);
+        const uint32_t* c0 = reinterpret_cast<const uint32_t*>(A.pk_c + k0);
+        const int l0 = (it.y & 0xffff) >> 1;
+#pragma unroll
+        for (int j = 0; j < kHalf; j++) {
+            const bool in = lane + 32 * j < l0;
+            cw[j] = in ? load_w2<CS>(&w0[lane + 32 * j]) : make_float2(0.f, 0.f);
+            cc[j] = in ? load_c2<CS>(&c0[lane + 32 * j]) : 0u;
+        }
+    } else {
         const int2* p0 = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
         const int l0 = it.y & 0xffff;
 #pragma unroll
@@ -333,10 +525,37 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
         // warp-uniform bookkeeping sits in shared memory while the item streams: the loop below runs at the register
         // limit that keeps 5 blocks per SM resident, and anything live across it is paid for in spills inside it
         if (lane == 0) hold_s[warp] = make_int4(it.x, it.y, w, wn);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        if (PACKED) {
+            const int64_t k0 = (int64_t)(uint32_t)it.z << 6;
+            const float2* w2 = reinterpret_cast<const float2*>(A.pk_w + k0);
+            const uint32_t* c2 = reinterpret_cast<const uint32_t*>(A.pk_c + k0);
+            const int npairs = (it.y & 0xffff) >> 1, base = it.w;
+            for (int off = lane; off < npairs; off += 32 * kHalf) {
+#pragma unroll
+                for (int j = 0; j < kHalf; j++) {
+                    const bool in = off + 32 * (kHalf + j) < npairs;
+                    nw[j] = in ? load_w2<CS>(&w2[off + 32 * (kHalf + j)]) : make_float2(0.f, 0.f);
+                    nc[j] = in ? load_c2<CS>(&c2[off + 32 * (kHalf + j)]) : 0u;
+                }
+                float4 x[kGatherUnroll];
+#pragma unroll
+                for (int j = 0; j < kHalf; j++) {
+                    x[2 * j] = load_er<MULTI>(er, base + (int)(cc[j] & 0xffffu));
+                    x[2 * j + 1] = load_er<MULTI>(er, base + (int)(cc[j] >> 16));
+                }
+#pragma unroll
+                for (int j = 0; j < kHalf; j++) {
+                    s0 += cw[j].x * x[2 * j].x; s1 += cw[j].x * x[2 * j].y; s2 += cw[j].x * x[2 * j].z;
+                    s0 += cw[j].y * x[2 * j + 1].x; s1 += cw[j].y * x[2 * j + 1].y; s2 += cw[j].y * x[2 * j + 1].z;
+                }
+#pragma unroll
+                for (int j = 0; j < kHalf; j++) { cw[j] = nw[j]; cc[j] = nc[j]; }
+            }
+        } else {
         const int2* p = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
         const int len = it.y & 0xffff;
         int off = lane;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
         for (; off < len; off += 32 * kGatherUnroll) {
 #pragma unroll
             for (int j = 0; j < kGatherUnroll; j++)
@@ -352,6 +571,7 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
 #pragma unroll
             for (int j = 0; j < kGatherUnroll; j++) cur[j] = nxt[j];
         }
+        }
         // hand over to the next item before finishing this one: its first loads run under the reduction and epilogue
         __syncwarp();
         const int4 hold = hold_s[warp];
@@ -362,7 +582,18 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
         __syncwarp();
         it = desc_s[warp];                                          // stale when !has_next: no entries are read from it then
         __syncwarp();                                               // every lane has its copy before the slots are refilled
-        {
+        if (PACKED) {
+            const int64_t k0 = (int64_t)(uint32_t)it.z << 6;
+            const float2* wn2 = reinterpret_cast<const float2*>(A.pk_w + k0);
+            const uint32_t* cn2 = reinterpret_cast<const uint32_t*>(A.pk_c + k0);
+            const int ln = has_next ? ((it.y & 0xffff) >> 1) : 0;
+#pragma unroll
+            for (int j = 0; j < kHalf; j++) {
+                const bool in = lane + 32 * j < ln;
+                cw[j] = in ? load_w2<CS>(&wn2[lane + 32 * j]) : make_float2(0.f, 0.f);
+                cc[j] = in ? load_c2<CS>(&cn2[lane + 32 * j]) : 0u;
+            }
+        } else {
             const int2* pn = tr + (((int64_t)it.w << 32) | (uint32_t)it.z);
             const int ln = has_next ? (it.y & 0xffff) : 0;
 #pragma unroll
@@ -673,8 +904,60 @@ k4_collect_parents(int n_interior, int n_long, int long_blocks, const int32_t* _
 
 // Work items of the gather for the resident rows (rowlen = logical row lengths, host copy).  Called by
 // vrad_build_transfers and vrad_transfers_upload once the rows are in place.
+// the packed streams from tr[] (after vrad_build_transfers / vrad_transfers_upload); device passes, two scans
+static int build_packed_streams(vrad_env* e, int64_t nloc) {
+    TransfersDev& T = e->transfers;
+    T.packed = false;
+    if (!e->opt.k4_pack || e->patches.hier || nloc <= 0) return 0;
+    int max_seg = 1 << 8;                                  // the longest segment = the longest part of the pair plan (k4_seg)
+    while ((max_seg << 1) <= e->opt.k4_seg && max_seg < (1 << 15)) max_seg <<= 1;
+    DevBuf<int32_t> d_ns; DevBuf<int64_t> d_pad, d_rowptr; DevBuf<unsigned char> d_tmp;
+    auto drop = [&]() { d_ns.release(); d_pad.release(); d_rowptr.release(); d_tmp.release(); };
+    if (d_ns.alloc(nloc + 1) || d_pad.alloc(nloc + 1) || d_rowptr.alloc(nloc + 1) || T.pk_seg_ptr.alloc(nloc + 1)) { drop(); set_error("out of device memory (packed transfer streams)"); return VRAD_E_NOMEM; }
+#define PK_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { drop(); set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); return VRAD_E_CUDA; } } while (0)
+    PK_CHECK(cudaMemsetAsync(d_ns.p, 0, ((size_t)nloc + 1) * 4, e->stream));
+    PK_CHECK(cudaMemsetAsync(d_pad.p, 0, ((size_t)nloc + 1) * 8, e->stream));
+    const int wblocks = (int)((nloc * 32 + 255) / 256);
+    k4_pack_count<<<wblocks, 256, 0, e->stream>>>((int)nloc, T.rowptr.p, T.rowlen.p, T.tr.p, max_seg, d_ns.p, d_pad.p);
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b1, d_ns.p, T.pk_seg_ptr.p, (int)nloc + 1, e->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, d_pad.p, d_rowptr.p, (int)nloc + 1, e->stream);
+    if (d_tmp.alloc(std::max(b1, b2) + 16)) { drop(); set_error("out of device memory (scan scratch)"); return VRAD_E_NOMEM; }
+    PK_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, b1, d_ns.p, T.pk_seg_ptr.p, (int)nloc + 1, e->stream));
+    PK_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, b2, d_pad.p, d_rowptr.p, (int)nloc + 1, e->stream));
+    int32_t n_segs = 0; int64_t n_entries = 0;
+    PK_CHECK(cudaMemcpyAsync(&n_segs, T.pk_seg_ptr.p + nloc, 4, cudaMemcpyDeviceToHost, e->stream));
+    PK_CHECK(cudaMemcpyAsync(&n_entries, d_rowptr.p + nloc, 8, cudaMemcpyDeviceToHost, e->stream));
+    PK_CHECK(cudaStreamSynchronize(e->stream));
+    // Rows that span several column windows become several segments; the multi-GPU kernel runs them as parts of a split row (cross-warp
+    // combine: an atomic, a fence and a second pass per row), which costs more than the narrower stream saves once most rows are
+    // like that (C5 map, 3.0 segments per row: 1224 us per bounce on the 8-rank slice against 926 us from the pairs).  Such a matrix
+    // keeps the {col,w} pairs.  k4_pack = 9 packs regardless (measurements).
+    if (e->opt.k4_pack != 9 && (int64_t)n_segs > nloc + nloc / 20) {
+        if (getenv("VRAD_VERBOSE")) fprintf(stderr, "[vrad] rank %d: %d segments for %lld rows -- transfers stay {col,w} pairs\n", e->cfg.rank, n_segs, (long long)nloc);
+        drop();
+        return 0;
+    }
+    if (T.pk_segs.alloc((size_t)n_segs + 1) || T.pk_w.alloc((size_t)n_entries + 8) || T.pk_c.alloc((size_t)n_entries + 8)) {
+        // not enough memory for a second copy of the matrix: gather from the pairs
+        T.pk_segs.release(); T.pk_w.release(); T.pk_c.release(); drop();
+        return 0;
+    }
+    k4_pack_fill<<<wblocks, 256, 0, e->stream>>>((int)nloc, T.rowptr.p, T.rowlen.p, T.tr.p, max_seg, T.pk_seg_ptr.p, d_rowptr.p, T.pk_segs.p, T.pk_w.p, T.pk_c.p);
+    PK_CHECK(cudaGetLastError());
+    PK_CHECK(cudaStreamSynchronize(e->stream));
+#undef PK_CHECK
+    drop();
+    T.pk_entries = n_entries; T.pk_n_segs = n_segs; T.packed = true;
+    if (getenv("VRAD_VERBOSE"))
+        fprintf(stderr, "[vrad] rank %d packed transfer streams: %d segments for %lld rows, %lld entries for %lld transfers (%.1f %% padding), 6 B each\n", e->cfg.rank, n_segs,
+                (long long)nloc, (long long)n_entries, (long long)T.nnz, T.nnz > 0 ? 100.0 * (double)(n_entries - T.nnz) / (double)T.nnz : 0.0);
+    return 0;
+}
+
 int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     TransfersDev& T = e->transfers;
+    { const int rcp = build_packed_streams(e, nloc); if (rcp) return rcp; }
     const bool long_first = e->opt.k4_long_first != 0;
     int max_len = 0;
     for (int64_t r = 0; r < nloc; r++) max_len = std::max(max_len, rowlen[r]);
@@ -689,7 +972,31 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     items.reserve((size_t)nloc + 1024); slots.reserve((size_t)nloc + 1024);
     int n_slots = 0;
     int64_t pos = 0;                                       // rows start on 4-entry boundaries (vrad_transfers_upload / k2_fill)
-    for (int64_t r = 0; r < nloc; r++) {
+    T.plan_packed = false;
+    if (T.packed) {
+        // packed plan: one item per segment {row, padded entries | n_parts << 16 | part index << 24, first entry / 64, column base}
+        std::vector<int4> segs((size_t)T.pk_n_segs + 1);
+        std::vector<int32_t> sp((size_t)nloc + 1);
+        VRAD_CUDA_CHECK(cudaMemcpy(segs.data(), T.pk_segs.p, (size_t)T.pk_n_segs * sizeof(int4), cudaMemcpyDeviceToHost));
+        VRAD_CUDA_CHECK(cudaMemcpy(sp.data(), T.pk_seg_ptr.p, ((size_t)nloc + 1) * 4, cudaMemcpyDeviceToHost));
+        bool fits = true;
+        for (int64_t r = 0; r < nloc && fits; r++) fits = sp[r + 1] - sp[r] <= 255;
+        if (fits) {
+            for (int64_t r = 0; r < nloc; r++) {
+                const int n_parts = std::max(1, sp[r + 1] - sp[r]);
+                if (sp[r + 1] == sp[r]) { items.push_back(make_int4((int)r, 1 << 16, 0, 0)); slots.push_back(-1); continue; }     // empty row: epilogue only
+                for (int q = 0; q < n_parts; q++) {
+                    const int4 sg = segs[sp[r] + q];
+                    const int64_t start = (int64_t)(uint32_t)sg.x | ((int64_t)sg.y << 32);
+                    items.push_back(make_int4((int)r, sg.z | (n_parts << 16) | (q << 24), (int)(uint32_t)(start >> 6), sg.w));
+                    slots.push_back(n_parts > 1 ? n_slots : -1);
+                }
+                if (n_parts > 1) n_slots += n_parts;
+            }
+            T.plan_packed = true;
+        }
+    }
+    for (int64_t r = 0; r < nloc && !T.plan_packed; r++) {
         const int len = rowlen[r];
         const int n_parts = len > seg ? (len + seg - 1) / seg : 1;
         for (int p = 0; p < n_parts; p++) {
@@ -1082,8 +1389,24 @@ static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, b
     if (!p2p) {
         const int nloc = (int)(T.row1 - T.row0);
         const int nblocks = std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
-        k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
-                                                         e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
+        if (T.packed) {
+            const PackedRows pk{T.pk_seg_ptr.p, T.pk_segs.p, T.pk_w.p, T.pk_c.p};
+#define VRAD_PACKED(U, B) k4_gather_packed<U, B><<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, pk, e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p)
+            switch (e->opt.k4_pack) {
+                case 2: VRAD_PACKED(6, 5); break;
+                case 3: VRAD_PACKED(6, 4); break;
+                case 4: VRAD_PACKED(8, 4); break;
+                case 5: VRAD_PACKED(3, 6); break;
+                case 6: VRAD_PACKED(2, 6); break;
+                case 7: VRAD_PACKED(4, 4); break;
+                case 8: VRAD_PACKED(4, 6); break;
+                default: VRAD_PACKED(4, 5); break;
+            }
+#undef VRAD_PACKED
+        }
+        else
+            k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
+                                                             e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
         return cudaGetLastError();
     }
     const int nblocks = T.n_blocks;
@@ -1118,7 +1441,9 @@ static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, b
     }
     cfg.attrs = attr; cfg.numAttrs = na;
     const bool cs = e->l2_window_bytes == 0 || e->opt.k4_l2_mb < 0;
+    A.pk_w = T.pk_w.p; A.pk_c = T.pk_c.p;
     auto kern = w6 ? (cs ? k4_gather_items<true, 6, true> : k4_gather_items<true, 6, false>) : (cs ? k4_gather_items<true, 8, true> : k4_gather_items<true, 8, false>);
+    if (T.plan_packed) kern = w6 ? k4_gather_items<true, 6, true, true> : k4_gather_items<true, 8, true, true>;
     return cudaLaunchKernelEx(&cfg, kern, (const int32_t*)T.block_ptr.p, (const int4*)T.items.p, (const int32_t*)T.item_slot.p, T.row0,
                               (const int2*)T.tr.p, (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
 }
@@ -1233,7 +1558,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
             VRAD_CUDA_CHECK(cudaMemsetAsync(PM.total_bump[b].p, 0, (size_t)n_pad * 16, e->stream));
         }
     }
-    static const int force_short = [] { const char* v = getenv("VRAD_K4_SHORT"); return v ? atoi(v) : -1; }();
+    const int force_short = e->opt.k4_short;
     const bool use_short = !p2p && (hier || (force_short >= 0 ? force_short != 0 : (T.nnz < (int64_t)400 * std::max(1, n_short))));
     static const int short_cfg = [] { const char* v = getenv("VRAD_K4_SHORT_CFG"); return v ? atoi(v) : 884; }();   // experiments; see the switch below
     const int short_lanes = short_cfg / 10 == 16 ? 16 : (short_cfg / 10 == 4 ? 4 : 8);
@@ -1297,7 +1622,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     const bool graphed = launch_only && use_graph && !early_out && !verbose && n_bounces >= 4;
     if (graphed) {
         GraphCache& G = e->bounce_graph;
-        const int64_t graph_tag = (T.plan_serial * 8 + (use_pdl ? 4 : 0) + (p2p ? 2 : 0) + (p2p_hier ? 1 : 0)) * 4 + (use_short ? 2 : 0) + (hier ? 1 : 0);
+        const int64_t graph_tag = ((T.plan_serial * 8 + (use_pdl ? 4 : 0) + (p2p ? 2 : 0) + (p2p_hier ? 1 : 0)) * 4 + (use_short ? 2 : 0) + (hier ? 1 : 0)) * 16 + (T.packed ? (e->opt.k4_pack & 15) : 0);
         const void* key_items = use_short ? (const void*)d_rows : (const void*)T.items.p;
         const int key_n = use_short ? n_short : T.n_items;
         const bool hit = G.exec && G.n_bounces == n_bounces && G.items == key_items && G.n_items == key_n && G.er0 == e->d_er[0].p && G.total == total_local &&
