@@ -22,8 +22,8 @@ ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=
 res = {"world": world, "nnz_local_rank0": nnz, "rows_rank0": [row0, row1]}
 ref = None
 # (block, persist, pool, pdl, graph, pack)
-for blk, per, pool, pdl, graph, pack in ((192, 1, 12, 1, 1, 1), (192, 1, 12, 1, 1, 0), (192, 1, 12, 0, 1, 1), (192, 1, 12, 1, 0, 1), (192, 1, 0, 1, 1, 1), (192, 1, 25, 1, 1, 1),
-                                         (256, 1, 12, 1, 1, 1), (192, 0, 0, 1, 1, 1), (192, 1, 25, 1, 1, 0)):
+for blk, per, pool, pdl, graph, pack in ((192, 1, 25, 1, 1, 1), (192, 1, 25, 1, 1, 0), (192, 1, 12, 1, 1, 1), (192, 1, 12, 1, 1, 0), (192, 1, 40, 1, 1, 1), (192, 1, 25, 0, 1, 1),
+                                         (192, 1, 25, 1, 0, 1), (192, 1, 0, 1, 1, 1), (256, 1, 25, 1, 1, 1), (192, 0, 0, 1, 1, 1)):
     for k, v in (("k4_block", blk), ("k4_persist", per), ("k4_pool", pool), ("k4_pdl", pdl), ("k4_graph", graph), ("k4_pack", pack)):
         env.set_option(k, v)
     env.bounce(e0, 100, out=out, want_added=False)

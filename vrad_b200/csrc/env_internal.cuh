@@ -217,7 +217,7 @@ struct EnvOptions {
     int k4_pack = 1;       // VRAD_K4_PACK: gather from the packed 6-byte streams (0 = from the {col,w} pairs)
     int k4_l2_mb = 0;      // VRAD_K4_L2_MB: MB of L2 set aside for the head of the transfer stream of the multi-GPU gather (0 = off)
     int k4_hier_p2p = 1;   // VRAD_K4_HIER_P2P: patch hierarchy on several GPUs: leaf rows by peer stores (0 = all-gather pass per bounce)
-    int k4_pool = 12;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early
+    int k4_pool = 25;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early
     int k4_items = 0;      // VRAD_K4_ITEMS: run the multi-GPU (work-item) gather on a single-GPU handle too (a one-rank peer table)
     int k4_persist = 1;    // VRAD_K4_PERSIST: one gather block per resident slot over equal-work item ranges (0 = 8 items per block)
     int k4_pdl = 1;        // VRAD_K4_PDL: chain the bounces of the multi-GPU gather with programmatic dependent launch

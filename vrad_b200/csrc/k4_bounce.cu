@@ -1324,6 +1324,27 @@ int vrad_transfers_info(vrad_env* e, int64_t* row0, int64_t* row1, int64_t* nnz)
     return VRAD_OK;
 }
 
+int vrad_transfers_layout(vrad_env* e, int64_t* pair_entries, int64_t* packed_entries, int64_t* packed_segments) {
+    if (!e) return VRAD_E_INVALID;
+    int64_t a = 0, b = 0, c = 0;
+    if (e->multi) {
+        for (vrad_env* r : e->multi->ranks) {
+            int64_t x, y, z;
+            const int rc = vrad_transfers_layout(r, &x, &y, &z);
+            if (rc) return rc;
+            a += x; b += y; c += z;
+        }
+    } else {
+        if (!e->transfers.ready) { set_error("vrad_transfers_layout: no transfers resident"); return VRAD_E_STATE; }
+        a = e->transfers.nnz_padded;
+        if (e->transfers.packed) { b = e->transfers.pk_entries; c = e->transfers.pk_n_segs; }
+    }
+    if (pair_entries) *pair_entries = a;
+    if (packed_entries) *packed_entries = b;
+    if (packed_segments) *packed_segments = c;
+    return VRAD_OK;
+}
+
 int vrad_transfers_download(vrad_env* e, int64_t* rowptr, int32_t* col, float* w) {
     VRAD_MULTI(e, group_transfers_download(e, rowptr, col, w));
     if (!e) return VRAD_E_INVALID;

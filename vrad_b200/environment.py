@@ -337,6 +337,12 @@ class Environment:
         check(self._l.vrad_transfers_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def transfers_layout(self):
+        """(entries of the {col,w} pair array, entries of the packed 6-byte streams, their segments); packed = (0, 0) when unused."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._l.vrad_transfers_layout(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def transfers_download(self):
         row0, row1, nnz = self.transfers_info()
         rowptr = np.empty(row1 - row0 + 1, np.int64); col = np.empty(nnz, np.int32); w = np.empty(nnz, np.float32)

@@ -30,7 +30,7 @@ SYMBOLS = [
     "vrad_light_for_string", "vrad_lights_from_entities", "vrad_lights_from_patches",
     "vrad_bump_normals", "vrad_patches_set_bump", "vrad_bounce_bump_totals",
     "vrad_env_build_fast", "vrad_kd_build_binned_host",
-    "vrad_points_upload", "vrad_test_lines_indexed", "vrad_env_set_option", "vrad_env_create_multi",
+    "vrad_points_upload", "vrad_test_lines_indexed", "vrad_env_set_option", "vrad_env_create_multi", "vrad_transfers_layout",
 ]
 
 # == vrad_face_patch in include/vrad_cuda.h
