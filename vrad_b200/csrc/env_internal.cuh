@@ -211,7 +211,7 @@ struct EnvOptions {
     int k1_top = 0;        // VRAD_K1_TOP: stage the top levels of the kd tree in shared memory (0 = off, else node budget)
     int k4_seg = 16384;    // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
-    int k4_block = 192;    // VRAD_K4_BLOCK: threads per work-item gather block: 192 (6 blocks/SM, 56 registers) or 256 (5 blocks/SM, 48 registers: spills in the loop)
+    int k4_block = 0;      // VRAD_K4_BLOCK: threads per block of the multi-GPU gather: 192 (6 warps, 6 blocks/SM, 56 registers), 256 (8 warps, 5 blocks/SM, 48 registers), 0 = 256 with the packed streams, 192 with the pairs
     int k2_stream = 0;     // VRAD_K2_STREAM: pass A of the transfer build as compacted ray queues with lane refill (experiment, slower: DESIGN section 7; 0 = one ray slot per (row, candidate) thread)
     int k4_short = -1;     // VRAD_K4_SHORT: the short-row gather (8 lanes per row) on one GPU: -1 = where rows average < 400 transfers, 0 = never, 1 = always
     int k4_pack = 1;       // VRAD_K4_PACK: gather from the packed 6-byte streams (0 = from the {col,w} pairs)

@@ -1021,7 +1021,8 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     std::vector<int32_t> bp;
     const int n_it = (int)items.size();
     int pool_begin = n_it;
-    const int plan_warps = e->opt.k4_block == 192 ? 6 : 8;
+    // 0 = automatic: 8 warps x 5 blocks per SM at 48 registers for the packed streams, 6 x 6 at 56 registers for the pairs (measured at 2, 4 and 8 GPUs)
+    const int plan_warps = e->opt.k4_block ? (e->opt.k4_block == 192 ? 6 : 8) : (T.plan_packed ? 8 : 6);
     const int n_resident = e->sm_count * (plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS>
     if (e->opt.k4_persist && n_it > n_resident * plan_warps) {
         // persistent plan: `slots` contiguous ranges of equal work (entries + a per-item constant), longest item first inside each
