@@ -612,7 +612,7 @@ def run_graft(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "achieved": gather_gbs_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": gather_gbs_gpu / hbm_peak,
                      "traffic": (1.2047e9 if packed_entries else 1.5537e9) if world == 1 else None,
                      "traffic_source": "profiles/r02_k4_packed_ncu_summary.txt (dram read+write per launch, N=1; same kernels)",
-                     "kernel": ("k4_gather_packed<4, 5>" if packed_entries else "k4_gather") if world == 1 else ("k4_gather_items<true, 6, true, PACKED>" if packed_entries else "k4_gather_items<true, 6>"),
+                     "kernel": ("k4_gather_packed<4, 5>" if packed_entries else "k4_gather") if world == 1 else ("k4_gather_items<true, 8, true, PACKED>" if packed_entries else "k4_gather_items<true, 6>"),
                      "bytes_per_iter_per_gpu": bytes_gpu_max, "peak_source": peak_src,
                      "note": "achieved / frac are quoted on the ALGORITHMIC bytes of SURVEY 8(d): 8 B per transfer (the reference's Transfer struct) + 40 B per row. "
                              "The gather reads the transfers from packed streams of 6 B per entry (weights bit-exact f32, columns as u16 offsets from a per-segment base), "
