@@ -214,7 +214,7 @@ struct EnvOptions {
     int k4_block = 0;      // VRAD_K4_BLOCK: threads per block of the multi-GPU gather: 192 (6 warps, 6 blocks/SM, 56 registers), 256 (8 warps, 5 blocks/SM, 48 registers), 0 = 256 with the packed streams, 192 with the pairs
     int k2_stream = 0;     // VRAD_K2_STREAM: pass A of the transfer build as compacted ray queues with lane refill (experiment, slower: DESIGN section 7; 0 = one ray slot per (row, candidate) thread)
     int k4_short = -1;     // VRAD_K4_SHORT: the short-row gather (8 lanes per row) on one GPU: -1 = where rows average < 400 transfers, 0 = never, 1 = always
-    int k4_pack = 1;       // VRAD_K4_PACK: gather from the packed 6-byte streams (0 = from the {col,w} pairs)
+    int k4_pack = 1;       // VRAD_K4_PACK: gather from the packed 6-byte streams where rows are (nearly) one segment each (0 = from the {col,w} pairs; 9 = pack whatever the segment count)
     int k4_l2_mb = 0;      // VRAD_K4_L2_MB: MB of L2 set aside for the head of the transfer stream of the multi-GPU gather (0 = off)
     int k4_hier_p2p = 1;   // VRAD_K4_HIER_P2P: patch hierarchy on several GPUs: leaf rows by peer stores (0 = all-gather pass per bounce)
     int k4_pool = 25;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early

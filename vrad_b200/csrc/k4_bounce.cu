@@ -1413,18 +1413,9 @@ static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, b
         const int nblocks = std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
         if (T.packed) {
             const PackedRows pk{T.pk_seg_ptr.p, T.pk_segs.p, T.pk_w.p, T.pk_c.p};
-#define VRAD_PACKED(U, B) k4_gather_packed<U, B><<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, pk, e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p)
-            switch (e->opt.k4_pack) {
-                case 2: VRAD_PACKED(6, 5); break;
-                case 3: VRAD_PACKED(6, 4); break;
-                case 4: VRAD_PACKED(8, 4); break;
-                case 5: VRAD_PACKED(3, 6); break;
-                case 6: VRAD_PACKED(2, 6); break;
-                case 7: VRAD_PACKED(4, 4); break;
-                case 8: VRAD_PACKED(4, 6); break;
-                default: VRAD_PACKED(4, 5); break;
-            }
-#undef VRAD_PACKED
+            // 4 pairs in flight per lane at 48 registers / 5 blocks per SM; measured alternatives on the C4 matrix (us per bounce, this form 250):
+            // 6 pairs 277 (spills), 6 pairs / 4 blocks 282, 8 pairs / 4 blocks 417, 3 pairs / 6 blocks 258, 2 pairs / 6 blocks 286, 4 pairs / 4 blocks 303, 4 pairs / 6 blocks 323
+            k4_gather_packed<4, 5><<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, pk, e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
         }
         else
             k4_gather<<<nblocks, kGatherBlock, 0, e->stream>>>(nloc, T.row0, T.rowptr.p, T.tr.p, e->d_er[cur].p, e->patches.refl.p,
@@ -1644,7 +1635,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     const bool graphed = launch_only && use_graph && !early_out && !verbose && n_bounces >= 4;
     if (graphed) {
         GraphCache& G = e->bounce_graph;
-        const int64_t graph_tag = ((T.plan_serial * 8 + (use_pdl ? 4 : 0) + (p2p ? 2 : 0) + (p2p_hier ? 1 : 0)) * 4 + (use_short ? 2 : 0) + (hier ? 1 : 0)) * 16 + (T.packed ? (e->opt.k4_pack & 15) : 0);
+        const int64_t graph_tag = ((T.plan_serial * 8 + (use_pdl ? 4 : 0) + (p2p ? 2 : 0) + (p2p_hier ? 1 : 0)) * 4 + (use_short ? 2 : 0) + (hier ? 1 : 0)) * 2 + (T.packed ? 1 : 0);
         const void* key_items = use_short ? (const void*)d_rows : (const void*)T.items.p;
         const int key_n = use_short ? n_short : T.n_items;
         const bool hit = G.exec && G.n_bounces == n_bounces && G.items == key_items && G.n_items == key_n && G.er0 == e->d_er[0].p && G.total == total_local &&
