@@ -207,6 +207,7 @@ struct EnvOptions {
     int k1_sort = -1;      // VRAD_K1_SORT: order segment batches before tracing; -1 = batches of >= 65536 segments, 0 never, 1 always
     int k1_key = -1;       // VRAD_K1_KEY: layout of the sort key (k1_trace.cu: -1 by the scene box, 0 start-major Morton, 1 6-D Morton, 2 cubic start cells)
     int k1_sort_bits = 30; // VRAD_K1_SORT_BITS: leading key bits that take part in the radix sort (8..30; one pass per 8 bits)
+    int k1_bpsm = 12;      // VRAD_K1_BPSM: resident blocks per SM of the streaming traversal kernel: 12 (40 registers), 10 (51), 8 (64)
     int k1_stream = 1;     // VRAD_K1_STREAM: unordered batches also go through the persistent streaming kernel (0 = the per-chunk kernels)
     int k1_top = 0;        // VRAD_K1_TOP: stage the top levels of the kd tree in shared memory (0 = off, else node budget)
     int k4_seg = 16384;    // VRAD_K4_SEG: entries per gather work item (rows longer than this are split)

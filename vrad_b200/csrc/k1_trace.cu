@@ -205,8 +205,8 @@ __device__ __noinline__ void wait_for_chunk(const uint32_t* flag, uint32_t* err)
 
 constexpr int kSortedRange = 128;
 constexpr int kSortedBlocksPerSM = 12;       // 40 registers: 48 resident warps (the traversal waits on memory: on the 1 M-triangle map L1 hits are 44 %)
-template <bool SKY, bool TOP, bool INDEXED>
-__global__ void __launch_bounds__(kTraceBlock, TOP ? 8 : kSortedBlocksPerSM)
+template <bool SKY, bool TOP, bool INDEXED, int BPSM = kSortedBlocksPerSM>
+__global__ void __launch_bounds__(kTraceBlock, TOP ? 8 : BPSM)
 k1_test_lines_sorted(DevScene S, int64_t n, const uint32_t* __restrict__ perm, const float4* __restrict__ rec, SegSource src, uint32_t* __restrict__ bits,
                      unsigned long long* __restrict__ counter, const uint32_t* arrive, int chunk_shift, uint32_t* arrive_err) {
     extern __shared__ int2 top_s[];
@@ -418,7 +418,8 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         if ((rc = scratch_get(e, 19, 8, &d_ctr))) return rc;
         VRAD_CUDA_CHECK(cudaMemsetAsync(d_ctr, 0, 8, e->stream));
         VRAD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)((m + 31) >> 5) * 4, e->stream));
-        const int sgrid = (int)std::min<int64_t>((int64_t)e->sm_count * kSortedBlocksPerSM, (m + kSortedRange * kTraceWarps - 1) / (kSortedRange * kTraceWarps));
+        const int bpsm = e->opt.k1_bpsm == 10 || e->opt.k1_bpsm == 8 ? e->opt.k1_bpsm : kSortedBlocksPerSM;
+        const int sgrid = (int)std::min<int64_t>((int64_t)e->sm_count * bpsm, (m + kSortedRange * kTraceWarps - 1) / (kSortedRange * kTraceWarps));
         if (sorted) {
             const int kb = (int)((m + 255) / 256);
             if (indexed) k1_sort_keys<true><<<kb, 256, 0, e->stream>>>(m, sub, G, (float4*)d_rec, (uint32_t*)d_k0, (uint32_t*)d_i0);
@@ -427,7 +428,8 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
         }
         const size_t sm = (size_t)e->scene.n_top * sizeof(int2);
         const uint32_t* pm = (const uint32_t*)d_i1; const float4* rc4 = indexed ? nullptr : (const float4*)d_rec; unsigned long long* ctr = (unsigned long long*)d_ctr;
-#define VRAD_SORTED(SKY, TOP, IDX) k1_test_lines_sorted<SKY, TOP, IDX><<<sgrid, kTraceBlock, (TOP) ? sm : 0, e->stream>>>(e->scene, m, pm, rc4, sub, out, ctr, arrive ? arrive + (c0 >> chunk_shift) : nullptr, chunk_shift, arrive_err)
+#define VRAD_SORTED_B(SKY, TOP, IDX, B) k1_test_lines_sorted<SKY, TOP, IDX, B><<<sgrid, kTraceBlock, (TOP) ? sm : 0, e->stream>>>(e->scene, m, pm, rc4, sub, out, ctr, arrive ? arrive + (c0 >> chunk_shift) : nullptr, chunk_shift, arrive_err)
+#define VRAD_SORTED(SKY, TOP, IDX) do { if (bpsm == 10) VRAD_SORTED_B(SKY, TOP, IDX, 10); else if (bpsm == 8) VRAD_SORTED_B(SKY, TOP, IDX, 8); else VRAD_SORTED_B(SKY, TOP, IDX, kSortedBlocksPerSM); } while (0)
         if (indexed) {
             if (sm) { if (sky_mode) VRAD_SORTED(true, true, true); else VRAD_SORTED(false, true, true); }
             else { if (sky_mode) VRAD_SORTED(true, false, true); else VRAD_SORTED(false, false, true); }
@@ -436,6 +438,7 @@ static int enqueue_test_lines(vrad_env* e, int64_t n, const SegSource& src, int 
             else { if (sky_mode) VRAD_SORTED(true, false, false); else VRAD_SORTED(false, false, false); }
         }
 #undef VRAD_SORTED
+#undef VRAD_SORTED_B
         *launches += sorted ? 2 + 6 : 1;       // keys + traversal + cub's histogram / scan / onesweep passes (4 digit passes of 8 bits)
     }
     return 0;

@@ -194,6 +194,7 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
     e->opt.k1_top = env_int("VRAD_K1_TOP", e->opt.k1_top);
     e->opt.k1_key = env_int("VRAD_K1_KEY", e->opt.k1_key);
     e->opt.k1_stream = env_int("VRAD_K1_STREAM", e->opt.k1_stream);
+    e->opt.k1_bpsm = env_int("VRAD_K1_BPSM", e->opt.k1_bpsm);
     e->opt.k1_sort_bits = env_int("VRAD_K1_SORT_BITS", e->opt.k1_sort_bits);
     e->opt.k4_seg = env_int("VRAD_K4_SEG", e->opt.k4_seg);
     { const char* v = getenv("VRAD_K4_ORDER"); e->opt.k4_long_first = v && std::string(v) == "long"; }
@@ -275,6 +276,7 @@ int vrad_env_set_option(vrad_env* e, const char* name, int value) {
     if (n == "k1_sort") o.k1_sort = value;
     else if (n == "k1_key") o.k1_key = value;
     else if (n == "k1_stream") o.k1_stream = value;
+    else if (n == "k1_bpsm") o.k1_bpsm = value;
     else if (n == "k1_sort_bits") o.k1_sort_bits = value;
     else if (n == "k1_top") { o.k1_top = value; if (e->built) { VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device)); VRAD_CUDA_CHECK(cudaStreamSynchronize(e->stream)); return upload_top_levels(e); } }
     else if (n == "k4_items") o.k4_items = value;
