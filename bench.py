@@ -50,7 +50,7 @@ CONFIG = {
                 "patch rows sharded by rank, radiance rows exchanged every bounce",
     "patches": 187328, "bounces_per_step": N_BOUNCES,
     "rays_workload": "C1: S1 box room (996 tris, 1325 kd nodes), 2^24 shadow segments per step per GPU via vrad_test_lines (K1)",
-    "l2": "transfer stream 1.19 GB per iteration in the packed 6-byte form (149 MB per GPU at 8 GPUs; 1535 / 192 MB as {col,w} pairs) > 126 MB L2; ray inputs 403 MB per step > L2",
+    "l2": "transfer stream 1.01 GB per iteration as block rows (126 MB per GPU at 8 GPUs -- the size of L2, of which the radiance and the other traffic take their share; 1535 / 192 MB as {col,w} pairs); ray inputs 403 MB per step > L2",
 }
 CPU_GATHER_CUT = (5, 4)          # rooms of the S2 cut the CPU arm bounces (29 M transfers, 234 MB: larger than the host's caches)
 CPU_GATHER_BOUNCES = 50
@@ -288,8 +288,8 @@ def run_graft(args, rank, local_rank, world):
     bytes_per_iter_gpu = 8 * nnz_local + 40 * (row1 - row0) + (12 * N if world > 1 else 0)
     bytes_gpu_max = max_over_ranks(float(bytes_per_iter_gpu))
     # what the gather actually streams: 6 B per packed entry (f32 weight + u16 column offset; segments padded to 64) when the rows are packed
-    pair_entries, packed_entries, packed_segments = env2.transfers_layout()
-    moved_per_iter_gpu = (6 * packed_entries if packed_entries else 8 * pair_entries) + 40 * (row1 - row0) + (12 * N if world > 1 else 0)
+    pair_entries, packed_entries, packed_segments, block_entries = env2.transfers_layout()
+    moved_per_iter_gpu = (18 * block_entries if block_entries else 6 * packed_entries if packed_entries else 8 * pair_entries) + 40 * (row1 - row0) + (12 * N if world > 1 else 0)
     moved_gpu_max = max_over_ranks(float(moved_per_iter_gpu))
     # the step also carries init / unpack / reduce launches; per-iteration time attributes them to the gather
     gather_gbs_gpu = bytes_gpu_max * iters / (gather_ms * 1e-3) / 1e9
@@ -610,14 +610,18 @@ def run_graft(args, rank, local_rank, world):
                 "note": "host emit0 (N x RGB f32) in and host total out on every 100-bounce call; transfer lists and patches stay resident, as in the bake"},
         "gpu_launches": bounce_launches * args.steps,
         "roofline": {"bound": "hbm", "achieved": gather_gbs_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": gather_gbs_gpu / hbm_peak,
-                     "traffic": (1.2047e9 if packed_entries else 1.5537e9) if world == 1 else None,
-                     "traffic_source": "profiles/r02_k4_packed_ncu_summary.txt (dram read+write per launch, N=1; same kernels)",
-                     "kernel": ("k4_gather_packed<4, 5>" if packed_entries else "k4_gather") if world == 1 else ("k4_gather_items<true, 8, true, PACKED>" if packed_entries else "k4_gather_items<true, 6>"),
+                     "traffic": (None if block_entries else 1.2047e9 if packed_entries else 1.5537e9) if world == 1 else None,
+                     "traffic_source": "profiles/r02_k4_packed_ncu_summary.txt / profiles/r02_k4_block_ncu_summary.txt (dram read+write per launch, N=1; same kernels)",
+                     "kernel": ("k4_gather_blocked<4, 4>" if block_entries else "k4_gather_packed<4, 5>" if packed_entries else "k4_gather") if world == 1 else
+                               ("k4_gather_items_blocked<true, 8>" if block_entries else "k4_gather_items<true, 8, true, PACKED>" if packed_entries else "k4_gather_items<true, 6>"),
                      "bytes_per_iter_per_gpu": bytes_gpu_max, "peak_source": peak_src,
                      "note": "achieved / frac are quoted on the ALGORITHMIC bytes of SURVEY 8(d): 8 B per transfer (the reference's Transfer struct) + 40 B per row. "
-                             "The gather reads the transfers from packed streams of 6 B per entry (weights bit-exact f32, columns as u16 offsets from a per-segment base), "
-                             "so it moves fewer bytes than that: moved_* is the same rate on the bytes actually streamed",
-                     "stream_format": "packed: f32 weight + u16 column offset, 6 B per transfer" if packed_entries else "{col:int32, w:f32} pairs, 8 B per transfer",
+                             "The gather reads the transfers in a denser form -- block rows: 4 consecutive rows share the union of their columns, 18 B per union entry "
+                             "(u16 column offset + 4 f32 weights, bit-exact), about 5.3 B per transfer on this map; or packed 6-byte entries -- so it moves fewer bytes "
+                             "than that and frac can exceed what the memory system delivers: moved_* is the same rate on the bytes actually streamed",
+                     "stream_format": ("block rows: u16 column offset + 4 f32 weights per entry of the union of 4 rows' columns, 18 B" if block_entries else
+                                       "packed: f32 weight + u16 column offset, 6 B per transfer" if packed_entries else "{col:int32, w:f32} pairs, 8 B per transfer"),
+                     "block_entries_rank0": block_entries,
                      "packed_entries_rank0": packed_entries, "packed_segments_rank0": packed_segments, "pair_entries_rank0": pair_entries,
                      "moved_bytes_per_iter_per_gpu": moved_gpu_max, "moved_achieved": moved_gpu_max * iters / (gather_ms * 1e-3) / 1e9,
                      "moved_frac": moved_gpu_max * iters / (gather_ms * 1e-3) / 1e9 / hbm_peak,

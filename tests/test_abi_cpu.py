@@ -67,8 +67,8 @@ def test_row_partition_rule():
         parts = row_partition(n, w)
         assert parts[0][0] == 0 and parts[-1][1] == n and len(parts) == w
         assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
-        rpr = (n + w - 1) // w
-        assert all(hi - lo <= rpr for lo, hi in parts)
+        rpr = ((n + w - 1) // w + 3) & ~3
+        assert all(hi - lo <= rpr for lo, hi in parts) and all(lo % 4 == 0 or lo == n for lo, _ in parts)
 
 
 def test_splitmix64_reference_vector():

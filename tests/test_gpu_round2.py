@@ -262,3 +262,35 @@ def test_packed_streams_rows_over_several_column_windows():
     assert cmp["pairs_1~pairs_items_1"][0] <= 1                                             # only the 36k-entry row is split in the pair plan
     assert diff.size == 0, (cmp, diff.size, diff[:8], nwin[diff[:8]], lens[diff[:8]], np.bincount(nwin[diff]), np.bincount(nwin))
     assert np.abs(out["packed_items_seg512"] - out["packed"]).max() <= 1e-6 * np.abs(total).max()
+
+
+def test_block_row_streams_same_light(s2_small_scene, s2_small_oracle):
+    """Block-row transfer streams (k4_pack = 2, the default): 4 consecutive rows share the union of their columns, one er[] gather serves
+    the four.  Same light as the packed streams and the pairs to rounding, within 1e-4 of the oracle, and the single-GPU kernel and the
+    work-item (multi-GPU) kernel agree bit for bit."""
+    from vrad_b200.environment import environment_from_scene
+    scene = s2_small_scene
+    env = environment_from_scene(scene)
+    nnz = env.build_transfers(scene.pvs)
+    assert nnz == s2_small_oracle.build_transfers(scene.pvs, threads=8)
+    pairs, packed, segs, blocked = env.transfers_layout()
+    assert blocked > 0 and packed == 0                      # block rows in use; their union is far below 4 rows' worth of entries
+    assert blocked * 18 < nnz * 6
+    N = scene.n_patches
+    emit0 = scenes.SplitMix64(33).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
+    out = {}
+    for name, opts in (("block", {"k4_pack": 2}), ("block_items", {"k4_pack": 3, "k4_items": 1}), ("packed", {"k4_pack": 1}), ("pairs", {"k4_pack": 0})):
+        for k in ("k4_items", "k4_pack"): env.set_option(k, opts.get(k, 0))
+        out[name] = [env.bounce(emit0, nb) for nb in (1, 8)]            # below and above the graph threshold
+    lay = {k: None for k in out}
+    to1, ao1, _ = _gather_reference(s2_small_oracle, scene, emit0, 1)
+    to8, ao8, _ = _gather_reference(s2_small_oracle, scene, emit0, 8)
+    for name, ((t1, a1, _), (t8, a8, _)) in out.items():
+        assert np.abs(t1 - to1).max() <= 1e-4 * np.abs(to1).max() and np.allclose(a1, ao1, rtol=1e-4), name
+        assert np.abs(t8 - to8).max() <= 1e-4 * np.abs(to8).max() and np.allclose(a8, ao8, rtol=1e-4), name
+    assert np.array_equal(out["block"][0][0], out["block_items"][0][0]) and np.array_equal(out["block"][1][0], out["block_items"][1][0])
+    assert np.abs(out["block"][1][0] - out["pairs"][1][0]).max() <= 2e-6 * np.abs(to8).max()
+    te, ae, de = (env.set_option("k4_pack", 2), env.bounce(emit0, 100, early_out=True))[1]
+    toe, aoe, doe = s2_small_oracle.bounce(emit0, 100, early_out=True, threads=8)
+    assert de == doe and np.abs(te - toe).max() <= 1e-4 * np.abs(toe).max()
+    env.close()

@@ -79,7 +79,7 @@ def test_partition_helpers():
     rp = np.array([0, 2, 2, 5, 9]); col = np.arange(9); w = np.arange(9, dtype=np.float32)
     lrp, lcol, lw = sharding.slice_csr(rp, col, w, 1, 3)
     assert list(lrp) == [0, 0, 3] and list(lcol) == [2, 3, 4]
-    assert sharding.padded_gather_buffer(10, 4).shape == (12, 3)
+    assert sharding.padded_gather_buffer(10, 4).shape == (16, 3)          # 4 ranks x 4 rows: blocks start on multiples of 4
 
 
 # ---- patch hierarchy: rows sharded, interior patches recomputed on every rank after the exchange ----

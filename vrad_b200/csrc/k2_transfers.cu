@@ -571,7 +571,8 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     }
     const auto t_lists = now();
     const int world = e->cfg.world;
-    const int64_t rpr = ((int64_t)N + world - 1) / world;
+    // row blocks start on multiples of 4: the gather's block-row streams group 4 consecutive GLOBAL rows, so that any number of ranks sums a row in the same order
+    const int64_t rpr = ((((int64_t)N + world - 1) / world) + 3) & ~(int64_t)3;
     int64_t row0 = std::min<int64_t>(N, e->cfg.rank * rpr), row1 = std::min<int64_t>(N, (e->cfg.rank + 1) * rpr);
     PatchView pv{P.origin_area.p, P.normal_dist.p, P.refl.p, P.has_windings ? P.wind.p : nullptr, P.has_windings ? P.wind_pts.p : nullptr};
     static const bool no_balance = [] { const char* v = getenv("VRAD_K2_BALANCE"); return v && v[0] == '0'; }();
@@ -606,7 +607,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
         int64_t acc = 0; int r = 1;
         for (int i = 0; i < N && r < world; i++) {
             acc += counts[i] + 1;
-            while (r < world && acc >= (total * r) / world) bounds[r++] = i + 1;
+            while (r < world && acc >= (total * r) / world) bounds[r++] = std::min<int64_t>(N, ((int64_t)i + 1 + 3) & ~(int64_t)3);
         }
         while (r < world) bounds[r++] = N;
         row0 = bounds[e->cfg.rank]; row1 = bounds[e->cfg.rank + 1];

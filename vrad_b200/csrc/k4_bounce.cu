@@ -287,6 +287,229 @@ k4_gather_packed(int nloc, int64_t row0, PackedRows P, const float4* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Block-row streams (TransfersDev::bk_*): kBlockRows consecutive rows share one column list, the union of theirs.
+// Built per block of rows by one warp with a bitmap of the current 65,536-column window in shared memory: the rows' entries set their
+// column's bit; the union position of a column is the number of set bits below it (per-word popcount prefix); the rows' weights go to
+// component r of the float4 at that position.  Two passes (sizes, then contents) around two scans, like the packed streams.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBlockRows = 4;
+constexpr int kBkWords = 65536 / 32;
+constexpr int kBkBuildWarps = 2;
+
+struct BkRowSet { int64_t k0[kBlockRows]; int len[kBlockRows]; };
+
+// FILL = false: calls seg(n_entries) per window piece and returns; FILL = true: also writes columns and weights.
+template <bool FILL>
+__device__ __forceinline__ void block_row_build(const int2* __restrict__ tr, const BkRowSet& R, int max_seg, uint32_t* bm, uint16_t* pre,
+                                                int& n_segs, int64_t& n_padded, int4* __restrict__ segs, int64_t out,
+                                                float4* __restrict__ bw, uint16_t* __restrict__ bc) {
+    const int lane = threadIdx.x & 31;
+    int col_min = 0x7fffffff, col_max = -1;
+#pragma unroll
+    for (int r = 0; r < kBlockRows; r++)
+        if (R.len[r] > 0) { col_min = min(col_min, tr[R.k0[r]].x); col_max = max(col_max, tr[R.k0[r] + R.len[r] - 1].x); }
+    n_segs = 0; n_padded = 0;
+    if (col_max < 0) return;
+    int cur[kBlockRows];
+#pragma unroll
+    for (int r = 0; r < kBlockRows; r++) cur[r] = 0;
+    for (int base = col_min; base <= col_max; base += 65536) {
+        for (int q = lane; q < kBkWords; q += 32) bm[q] = 0u;
+        __syncwarp();
+        int first[kBlockRows];
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            first[r] = cur[r];
+            for (;;) {
+                const int en = cur[r] + lane;
+                int c = 0;
+                const bool in = en < R.len[r] && (c = tr[R.k0[r] + en].x - base) < 65536;
+                if (in) atomicOr(&bm[c >> 5], 1u << (c & 31));
+                const int took = __popc(__ballot_sync(0xffffffffu, in));
+                cur[r] += took;
+                if (took < 32) break;
+            }
+        }
+        __syncwarp();
+        // per-word exclusive popcount prefix: lane owns 64 consecutive words
+        int mine = 0;
+        for (int q = 0; q < kBkWords / 32; q++) mine += __popc(bm[lane * (kBkWords / 32) + q]);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int count = __shfl_sync(0xffffffffu, incl, 31);
+        if (count == 0) continue;
+        if (FILL) {
+            int run = incl - mine;
+            for (int q = 0; q < kBkWords / 32; q++) { pre[lane * (kBkWords / 32) + q] = (uint16_t)run; run += __popc(bm[lane * (kBkWords / 32) + q]); }
+            __syncwarp();
+        }
+        // this window's union, cut into pieces of at most max_seg entries
+        const int n_pieces = (count + max_seg - 1) / max_seg;
+        const int64_t win_out = out + n_padded;                 // pieces are contiguous: piece p starts at win_out + p * max_seg (max_seg is a multiple of 32)
+        for (int p = 0; p < n_pieces; p++) {
+            const int l = min(max_seg, count - p * max_seg), lp = (l + 31) & ~31;
+            if (FILL && lane == 0) {
+                const int64_t st = win_out + (int64_t)p * max_seg;
+                segs[n_segs] = make_int4((int)(uint32_t)(st & 0xffffffff), (int)(st >> 32), lp, base);
+            }
+            n_segs++; n_padded += lp;
+        }
+        if (FILL) {
+            // columns: every set bit writes its offset at its union position
+            for (int q = lane; q < kBkWords; q += 32) {
+                uint32_t m = bm[q];
+                int pos = pre[q];
+                while (m) { const int b = __ffs(m) - 1; m &= m - 1; bc[win_out + pos] = (uint16_t)(q * 32 + b); pos++; }
+            }
+            // weights: component r of the entry at the column's union position
+#pragma unroll
+            for (int r = 0; r < kBlockRows; r++) {
+                for (int en = first[r] + lane; en < cur[r]; en += 32) {
+                    const int2 t = tr[R.k0[r] + en];
+                    const int c = t.x - base;
+                    const int pos = pre[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u));
+                    reinterpret_cast<float*>(&bw[win_out + pos])[r] = __int_as_float(t.y);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__device__ __forceinline__ BkRowSet block_rows_of(int blk, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen) {
+    BkRowSet R;
+#pragma unroll
+    for (int r = 0; r < kBlockRows; r++) {
+        const int row = blk * kBlockRows + r;
+        R.k0[r] = row < nloc ? rowptr[row] : 0;
+        R.len[r] = row < nloc ? rowlen[row] : 0;
+    }
+    return R;
+}
+
+__global__ void __launch_bounds__(kBkBuildWarps * 32)
+k4_block_count(int n_blocks, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen, const int2* __restrict__ tr, int max_seg,
+               int32_t* __restrict__ n_segs, int64_t* __restrict__ padded) {
+    __shared__ uint32_t bm_s[kBkBuildWarps][kBkWords];
+    const int warp = threadIdx.x >> 5;
+    const int blk = blockIdx.x * kBkBuildWarps + warp;
+    if (blk >= n_blocks) return;
+    int ns; int64_t np;
+    block_row_build<false>(tr, block_rows_of(blk, nloc, rowptr, rowlen), max_seg, bm_s[warp], nullptr, ns, np, nullptr, 0, nullptr, nullptr);
+    if ((threadIdx.x & 31) == 0) { n_segs[blk] = ns; padded[blk] = np; }
+}
+
+__global__ void __launch_bounds__(kBkBuildWarps * 32)
+k4_block_fill(int n_blocks, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen, const int2* __restrict__ tr, int max_seg,
+              const int32_t* __restrict__ seg_ptr, const int64_t* __restrict__ bk_start, int4* __restrict__ segs, float4* __restrict__ bw, uint16_t* __restrict__ bc) {
+    __shared__ uint32_t bm_s[kBkBuildWarps][kBkWords];
+    __shared__ uint16_t pre_s[kBkBuildWarps][kBkWords];
+    const int warp = threadIdx.x >> 5;
+    const int blk = blockIdx.x * kBkBuildWarps + warp;
+    if (blk >= n_blocks) return;
+    int ns; int64_t np;
+    block_row_build<true>(tr, block_rows_of(blk, nloc, rowptr, rowlen), max_seg, bm_s[warp], pre_s[warp], ns, np, segs + seg_ptr[blk], bk_start[blk], bw, bc);
+}
+
+// The gather from the block-row streams: one warp per block of kBlockRows rows; a lane takes one entry per step -- a 2-byte column, a
+// 16-byte weight vector, ONE 16-byte er[] gather -- and keeps kBlockRows x 3 sums.
+struct BlockedRows { const int32_t* seg_ptr; const int4* segs; const float4* w; const uint16_t* c; };
+
+template <int U>
+__device__ __forceinline__ void gather_block_segments(const BlockedRows& P, int sg0, int sg1, const float4* __restrict__ er, int lane, float (&acc)[kBlockRows][3]) {
+    for (int sg = sg0; sg < sg1; sg++) {
+        const int4 d = __ldg(&P.segs[sg]);
+        const int64_t k0 = (int64_t)(uint32_t)d.x | ((int64_t)d.y << 32);
+        const int len = d.z, base = d.w;
+        const float4* __restrict__ w4 = P.w + k0;
+        const uint16_t* __restrict__ c1 = P.c + k0;
+        float4 cw[U], nw[U];
+        int cc[U], nc[U];
+        int p = lane;
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const bool in = p + 32 * j < len;
+            cw[j] = in ? __ldcs(&w4[p + 32 * j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            cc[j] = in ? (int)__ldcs(&c1[p + 32 * j]) : 0;
+        }
+        for (; p < len; p += 32 * U) {
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const bool in = p + 32 * (U + j) < len;
+                nw[j] = in ? __ldcs(&w4[p + 32 * (U + j)]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                nc[j] = in ? (int)__ldcs(&c1[p + 32 * (U + j)]) : 0;
+            }
+            float4 x[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) x[j] = __ldg(&er[base + cc[j]]);
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                acc[0][0] += cw[j].x * x[j].x; acc[0][1] += cw[j].x * x[j].y; acc[0][2] += cw[j].x * x[j].z;
+                acc[1][0] += cw[j].y * x[j].x; acc[1][1] += cw[j].y * x[j].y; acc[1][2] += cw[j].y * x[j].z;
+                acc[2][0] += cw[j].z * x[j].x; acc[2][1] += cw[j].z * x[j].y; acc[2][2] += cw[j].z * x[j].z;
+                acc[3][0] += cw[j].w * x[j].x; acc[3][1] += cw[j].w * x[j].y; acc[3][2] += cw[j].w * x[j].z;
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) { cw[j] = nw[j]; cc[j] = nc[j]; }
+        }
+    }
+}
+
+template <int U, int kMinBlocks>
+__global__ void __launch_bounds__(kGatherBlock, kMinBlocks)
+k4_gather_blocked(int n_blocks, int nloc, int64_t row0, BlockedRows P, const float4* __restrict__ er, const float4* __restrict__ refl,
+                  float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blk = blockIdx.x * kGatherWarps + warp;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f;
+    if (blk < n_blocks) {
+        float acc[kBlockRows][3];
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; }
+        gather_block_segments<U>(P, P.seg_ptr[blk], P.seg_ptr[blk + 1], er, lane, acc);
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], o);
+        // lane r finishes row r of the block (CollectLight); the block's share of `added` is summed in row order
+        float s0 = acc[0][0], s1 = acc[0][1], s2 = acc[0][2];
+        if (lane == 1) { s0 = acc[1][0]; s1 = acc[1][1]; s2 = acc[1][2]; }
+        if (lane == 2) { s0 = acc[2][0]; s1 = acc[2][1]; s2 = acc[2][2]; }
+        if (lane == 3) { s0 = acc[3][0]; s1 = acc[3][1]; s2 = acc[3][2]; }
+        const int row = blk * kBlockRows + lane;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (lane < kBlockRows && row < nloc) {
+            const float4 r = refl[row0 + row];
+            if (r.w == 0.0f) {
+                float4 t = total[row];
+                t.x += s0; t.y += s1; t.z += s2;
+                total[row] = t;
+                er_next[row0 + row] = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                a0 = s0; a1 = s1; a2 = s2;
+            } else {
+                er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            e0 += __shfl_sync(0xffffffffu, a0, r); e1 += __shfl_sync(0xffffffffu, a1, r); e2 += __shfl_sync(0xffffffffu, a2, r);
+        }
+    }
+    __shared__ float sm[kGatherWarps][3];
+    if (lane == 0) { sm[warp][0] = e0; sm[warp][1] = e1; sm[warp][2] = e2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < kGatherWarps; k++) a += sm[k][threadIdx.x];
+        partials[3 * (size_t)blockIdx.x + threadIdx.x] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // The gather.  One warp per WORK ITEM (TransfersDev::items): a whole row, or -- for a row longer than `seg`
 // entries -- one `seg`-entry part of it.  Entries are {col, w} pairs -- the reference's Transfer struct
 // (common/types/transfer.go:3-6) -- read as one coalesced 64-bit load per lane with lanes on CONSECUTIVE
@@ -330,6 +553,9 @@ struct GatherAux {                 // rarely used pointers, kept in the paramete
     int pool_begin, n_items;       // items [pool_begin, n_items) belong to no block: whoever runs dry takes them one by one (flags[kFlagPool])
     const float* pk_w;             // PACKED only: the weight and column streams (TransfersDev::pk_w / pk_c)
     const uint16_t* pk_c;
+    const float4* bk_w;            // block-row kernel only (TransfersDev::bk_w / bk_c)
+    const uint16_t* bk_c;
+    int nloc;
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -629,6 +855,144 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
             // fused exchange: lane p stores the finished row straight into rank p's next-bounce buffer
             // (NVLink peer store; slot `rank` is the local buffer) -- no separate all-gather pass
             if (MULTI) store_row_to_peers(A.peers, A.next_buf, row0 + row, nv.x, nv.y, nv.z);
+        }
+        has = has_next;
+    }
+    if (MULTI) {
+        __syncthreads();
+        if (threadIdx.x == 0) signal_if_last(A.peers, A.flags, A.signal_rel);
+    }
+}
+
+// The multi-GPU gather from the block-row streams: the same persistent blocks, claims, pool, barrier and launch chain as k4_gather_items,
+// with a block of kBlockRows rows as the work item {block of rows, padded entries | 1 << 16, first entry / 32, column base} (a block
+// whose union spans several segments keeps the matrix on the packed streams: build_gather_plan) and kBlockRows epilogues per item.
+// Lane-to-entry mapping and accumulation order are those of k4_gather_blocked: one GPU and several give the same bits.
+constexpr int kBkUnroll = 4;
+template <bool MULTI, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 4)
+k4_gather_items_blocked(const int32_t* __restrict__ block_ptr, const int4* __restrict__ items, int64_t row0, const float4* er, const float4* __restrict__ refl,
+                        float4* er_next, float4* __restrict__ total, GatherAux A) {
+    __shared__ int next_item;
+    __shared__ int4 desc_s[WARPS], hold_s[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (MULTI) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) next_item = __ldg(&block_ptr[blockIdx.x]);
+    __syncthreads();
+    auto claim = [&]() {
+        int c = kNoItem;
+        if (lane == 0) {
+            c = atomicAdd(&next_item, 1);
+            if (c >= __ldg(&block_ptr[blockIdx.x + 1])) {
+                c = kNoItem;
+                if (MULTI && A.pool_begin < A.n_items) {
+                    const int q = A.pool_begin + (int)atomicAdd((unsigned int*)A.flags + kFlagPool, 1u);
+                    if (q < A.n_items) c = q;
+                }
+            }
+        }
+        return __shfl_sync(0xffffffffu, c, 0);
+    };
+    int w = claim();
+    int4 it = make_int4(0, 0, 0, 0);
+    if (w != kNoItem) it = __ldg(&items[w]);
+    float4 cw[kBkUnroll], nw[kBkUnroll];
+    int cc[kBkUnroll], nc[kBkUnroll];
+    {
+        const int64_t k0 = (int64_t)(uint32_t)it.z << 5;
+        const int l0 = it.y & 0xffff;
+#pragma unroll
+        for (int j = 0; j < kBkUnroll; j++) {
+            const bool in = lane + 32 * j < l0;
+            cw[j] = in ? __ldcs(&A.bk_w[k0 + lane + 32 * j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            cc[j] = in ? (int)__ldcs(&A.bk_c[k0 + lane + 32 * j]) : 0;
+        }
+    }
+    int wn = w != kNoItem ? claim() : kNoItem;
+    if (wn != kNoItem && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
+    if (MULTI) {
+        if (A.wait_rel) wait_for_peers(A.flags, A.wait_world, A.wait_rel);
+    }
+    bool has = w != kNoItem;
+    while (has) {
+        if (lane == 0) hold_s[warp] = make_int4(it.x, it.y, w, wn);
+        float acc[kBlockRows][3];
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; }
+        {
+            const int64_t k0 = (int64_t)(uint32_t)it.z << 5;
+            const float4* w4 = A.bk_w + k0;
+            const uint16_t* c1 = A.bk_c + k0;
+            const int len = it.y & 0xffff, base = it.w;
+            for (int off = lane; off < len; off += 32 * kBkUnroll) {
+#pragma unroll
+                for (int j = 0; j < kBkUnroll; j++) {
+                    const bool in = off + 32 * (kBkUnroll + j) < len;
+                    nw[j] = in ? __ldcs(&w4[off + 32 * (kBkUnroll + j)]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    nc[j] = in ? (int)__ldcs(&c1[off + 32 * (kBkUnroll + j)]) : 0;
+                }
+                float4 x[kBkUnroll];
+#pragma unroll
+                for (int j = 0; j < kBkUnroll; j++) x[j] = load_er<MULTI>(er, base + cc[j]);
+#pragma unroll
+                for (int j = 0; j < kBkUnroll; j++) {
+                    acc[0][0] += cw[j].x * x[j].x; acc[0][1] += cw[j].x * x[j].y; acc[0][2] += cw[j].x * x[j].z;
+                    acc[1][0] += cw[j].y * x[j].x; acc[1][1] += cw[j].y * x[j].y; acc[1][2] += cw[j].y * x[j].z;
+                    acc[2][0] += cw[j].z * x[j].x; acc[2][1] += cw[j].z * x[j].y; acc[2][2] += cw[j].z * x[j].z;
+                    acc[3][0] += cw[j].w * x[j].x; acc[3][1] += cw[j].w * x[j].y; acc[3][2] += cw[j].w * x[j].z;
+                }
+#pragma unroll
+                for (int j = 0; j < kBkUnroll; j++) { cw[j] = nw[j]; cc[j] = nc[j]; }
+            }
+        }
+        __syncwarp();
+        const int4 hold = hold_s[warp];
+        const int blk = hold.x;
+        wn = hold.w;
+        const bool has_next = wn != kNoItem;
+        cp_async_wait_all();
+        __syncwarp();
+        it = desc_s[warp];
+        __syncwarp();
+        {
+            const int64_t k0 = (int64_t)(uint32_t)it.z << 5;
+            const int ln = has_next ? (it.y & 0xffff) : 0;
+#pragma unroll
+            for (int j = 0; j < kBkUnroll; j++) {
+                const bool in = lane + 32 * j < ln;
+                cw[j] = in ? __ldcs(&A.bk_w[k0 + lane + 32 * j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cc[j] = in ? (int)__ldcs(&A.bk_c[k0 + lane + 32 * j]) : 0;
+            }
+        }
+        w = wn;
+        wn = has_next ? claim() : kNoItem;
+        if (wn != kNoItem && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], o);
+#pragma unroll
+        for (int r = 0; r < kBlockRows; r++) {
+            const int row = blk * kBlockRows + r;
+            if (row < A.nloc) {                                             // warp-uniform
+                float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);                // sky: emit = 0
+                if (lane == 0) {
+                    const float4 rf = refl[row0 + row];
+                    float4 a = nv;
+                    if (rf.w == 0.0f) {                                     // CollectLight, leaf patch
+                        float4 t = total[row];
+                        t.x += acc[r][0]; t.y += acc[r][1]; t.z += acc[r][2];
+                        total[row] = t;
+                        nv = make_float4(acc[r][0] * rf.x, acc[r][1] * rf.y, acc[r][2] * rf.z, 0.f);
+                        a = make_float4(acc[r][0], acc[r][1], acc[r][2], 0.f);
+                    }
+                    if (A.add) A.add[row] = a;
+                    if (!MULTI) er_next[row0 + row] = nv;
+                }
+                if (MULTI) store_row_to_peers(A.peers, A.next_buf, row0 + row, nv.x, nv.y, nv.z);
+            }
         }
         has = has_next;
     }
@@ -955,9 +1319,76 @@ static int build_packed_streams(vrad_env* e, int64_t nloc) {
     return 0;
 }
 
+// the block-row streams from tr[] (k4_pack = 2); device passes, two scans
+static int build_block_streams(vrad_env* e, int64_t nloc) {
+    TransfersDev& T = e->transfers;
+    T.blocked = false;
+    if ((e->opt.k4_pack != 2 && e->opt.k4_pack != 3) || e->patches.hier || nloc <= 0 || (T.row0 % kBlockRows) != 0) return 0;
+    int max_seg = 1 << 8;
+    while ((max_seg << 1) <= e->opt.k4_seg && max_seg < (1 << 15)) max_seg <<= 1;
+    const int nb = (int)((nloc + kBlockRows - 1) / kBlockRows);
+    // With several ranks a block of rows is ONE work item of the persistent kernel (4 blocks x 8 warps per SM): below ~4 items per resident
+    // warp the ranges no longer balance (C4 at 8 ranks: 5,854 items for 4,736 warps -- 48 us per bounce on the slice against 40 us from
+    // the packed streams, whose items are single rows), so such a slice stays on the packed streams.  k4_pack = 3 keeps the block rows.
+    const bool work_items = e->cfg.world > 1 || e->opt.k4_items;
+    if (work_items && e->opt.k4_pack != 3 && (int64_t)nb < (int64_t)4 * e->sm_count * 4 * 8) return 0;
+    DevBuf<int32_t> d_ns; DevBuf<int64_t> d_pad, d_start; DevBuf<unsigned char> d_tmp;
+    auto drop = [&]() { d_ns.release(); d_pad.release(); d_start.release(); d_tmp.release(); };
+    if (d_ns.alloc(nb + 1) || d_pad.alloc(nb + 1) || d_start.alloc(nb + 1) || T.bk_seg_ptr.alloc(nb + 1)) { drop(); set_error("out of device memory (block-row transfer streams)"); return VRAD_E_NOMEM; }
+#define BK_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { drop(); set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); return VRAD_E_CUDA; } } while (0)
+    BK_CHECK(cudaMemsetAsync(d_ns.p, 0, ((size_t)nb + 1) * 4, e->stream));
+    BK_CHECK(cudaMemsetAsync(d_pad.p, 0, ((size_t)nb + 1) * 8, e->stream));
+    const int grid = (nb + kBkBuildWarps - 1) / kBkBuildWarps;
+    k4_block_count<<<grid, kBkBuildWarps * 32, 0, e->stream>>>(nb, (int)nloc, T.rowptr.p, T.rowlen.p, T.tr.p, max_seg, d_ns.p, d_pad.p);
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b1, d_ns.p, T.bk_seg_ptr.p, nb + 1, e->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, d_pad.p, d_start.p, nb + 1, e->stream);
+    if (d_tmp.alloc(std::max(b1, b2) + 16)) { drop(); set_error("out of device memory (scan scratch)"); return VRAD_E_NOMEM; }
+    BK_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, b1, d_ns.p, T.bk_seg_ptr.p, nb + 1, e->stream));
+    BK_CHECK(cub::DeviceScan::ExclusiveSum(d_tmp.p, b2, d_pad.p, d_start.p, nb + 1, e->stream));
+    int32_t n_segs = 0; int64_t n_entries = 0;
+    BK_CHECK(cudaMemcpyAsync(&n_segs, T.bk_seg_ptr.p + nb, 4, cudaMemcpyDeviceToHost, e->stream));
+    BK_CHECK(cudaMemcpyAsync(&n_entries, d_start.p + nb, 8, cudaMemcpyDeviceToHost, e->stream));
+    BK_CHECK(cudaStreamSynchronize(e->stream));
+    if (getenv("VRAD_VERBOSE"))
+        fprintf(stderr, "[vrad] rank %d block-row streams: %d blocks of %d rows, %d segments, %lld union entries for %lld transfers (%.2f x one row per block, %.2f B per transfer)\n",
+                e->cfg.rank, nb, kBlockRows, n_segs, (long long)n_entries, (long long)T.nnz, T.nnz > 0 ? (double)n_entries * kBlockRows / (double)T.nnz : 0.0,
+                T.nnz > 0 ? (double)n_entries * 18.0 / (double)T.nnz : 0.0);
+    // worth it only where neighbouring rows share their columns (18 B per union entry against 4 rows x 6 B per packed entry), and the work-item
+    // kernel takes a block of rows as ONE item: every block must be a single segment (its union inside one 65,536-column window, at most k4_seg entries)
+    bool single = (int64_t)n_segs <= nb;
+    if (single) {
+        std::vector<int32_t> hns((size_t)nb);
+        BK_CHECK(cudaMemcpy(hns.data(), d_ns.p, (size_t)nb * 4, cudaMemcpyDeviceToHost));
+        for (int b = 0; b < nb && single; b++) single = hns[b] <= 1;
+    }
+    if (!single || (double)n_entries * 18.0 > (double)T.nnz * 6.0 * 1.1) { drop(); return 0; }
+    if (T.bk_segs.alloc((size_t)n_segs + 1) || T.bk_w.alloc((size_t)n_entries + 32) || T.bk_c.alloc((size_t)n_entries + 32)) {
+        T.bk_segs.release(); T.bk_w.release(); T.bk_c.release(); drop();
+        return 0;
+    }
+    BK_CHECK(cudaMemsetAsync(T.bk_w.p, 0, ((size_t)n_entries + 32) * sizeof(float4), e->stream));
+    BK_CHECK(cudaMemsetAsync(T.bk_c.p, 0, ((size_t)n_entries + 32) * sizeof(uint16_t), e->stream));
+    k4_block_fill<<<grid, kBkBuildWarps * 32, 0, e->stream>>>(nb, (int)nloc, T.rowptr.p, T.rowlen.p, T.tr.p, max_seg, T.bk_seg_ptr.p, d_start.p, T.bk_segs.p, T.bk_w.p, T.bk_c.p);
+    BK_CHECK(cudaGetLastError());
+    BK_CHECK(cudaStreamSynchronize(e->stream));
+#undef BK_CHECK
+    drop();
+    T.bk_entries = n_entries; T.bk_n_segs = n_segs; T.bk_n_blocks = nb; T.blocked = true;
+    return 0;
+}
+
+// blocks of the single-GPU gather grid (one warp per row, or per block of rows)
+static inline int plain_gather_blocks(const TransfersDev& T, int nloc) {
+    if (T.blocked) return std::max(1, (T.bk_n_blocks + kGatherWarps - 1) / kGatherWarps);
+    return std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
+}
+
 int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     TransfersDev& T = e->transfers;
-    { const int rcp = build_packed_streams(e, nloc); if (rcp) return rcp; }
+    { const int rcb = build_block_streams(e, nloc); if (rcb) return rcb; }
+    T.packed = false;
+    if (!T.blocked) { const int rcp = build_packed_streams(e, nloc); if (rcp) return rcp; }
     const bool long_first = e->opt.k4_long_first != 0;
     int max_len = 0;
     for (int64_t r = 0; r < nloc; r++) max_len = std::max(max_len, rowlen[r]);
@@ -972,8 +1403,23 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     items.reserve((size_t)nloc + 1024); slots.reserve((size_t)nloc + 1024);
     int n_slots = 0;
     int64_t pos = 0;                                       // rows start on 4-entry boundaries (vrad_transfers_upload / k2_fill)
-    T.plan_packed = false;
-    if (T.packed) {
+    T.plan_packed = false; T.plan_blocked = false;
+    if (T.blocked) {
+        // block-row plan: one item per block of rows {block, padded entries | 1 << 16, first entry / 32, column base}; every block must be one segment
+        std::vector<int4> segs((size_t)T.bk_n_segs + 1);
+        std::vector<int32_t> sp((size_t)T.bk_n_blocks + 1);
+        VRAD_CUDA_CHECK(cudaMemcpy(segs.data(), T.bk_segs.p, (size_t)T.bk_n_segs * sizeof(int4), cudaMemcpyDeviceToHost));
+        VRAD_CUDA_CHECK(cudaMemcpy(sp.data(), T.bk_seg_ptr.p, ((size_t)T.bk_n_blocks + 1) * 4, cudaMemcpyDeviceToHost));
+        for (int b = 0; b < T.bk_n_blocks; b++) {
+            if (sp[b + 1] == sp[b]) { items.push_back(make_int4(b, 1 << 16, 0, 0)); slots.push_back(-1); continue; }      // empty rows: epilogues only
+            const int4 sg = segs[sp[b]];
+            const int64_t start = (int64_t)(uint32_t)sg.x | ((int64_t)sg.y << 32);
+            items.push_back(make_int4(b, sg.z | (1 << 16), (int)(uint32_t)(start >> 5), sg.w));
+            slots.push_back(-1);
+        }
+        T.plan_blocked = true;
+    }
+    if (T.packed && !T.plan_blocked) {
         // packed plan: one item per segment {row, padded entries | n_parts << 16 | part index << 24, first entry / 64, column base}
         std::vector<int4> segs((size_t)T.pk_n_segs + 1);
         std::vector<int32_t> sp((size_t)nloc + 1);
@@ -996,7 +1442,7 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
             T.plan_packed = true;
         }
     }
-    for (int64_t r = 0; r < nloc && !T.plan_packed; r++) {
+    for (int64_t r = 0; r < nloc && !T.plan_packed && !T.plan_blocked; r++) {
         const int len = rowlen[r];
         const int n_parts = len > seg ? (len + seg - 1) / seg : 1;
         for (int p = 0; p < n_parts; p++) {
@@ -1022,8 +1468,8 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     const int n_it = (int)items.size();
     int pool_begin = n_it;
     // 0 = automatic: 8 warps x 5 blocks per SM at 48 registers for the packed streams, 6 x 6 at 56 registers for the pairs (measured at 2, 4 and 8 GPUs)
-    const int plan_warps = e->opt.k4_block ? (e->opt.k4_block == 192 ? 6 : 8) : (T.plan_packed ? 8 : 6);
-    const int n_resident = e->sm_count * (plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS>
+    const int plan_warps = T.plan_blocked ? 8 : e->opt.k4_block ? (e->opt.k4_block == 192 ? 6 : 8) : (T.plan_packed ? 8 : 6);
+    const int n_resident = e->sm_count * (T.plan_blocked ? 4 : plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS> / k4_gather_items_blocked
     if (e->opt.k4_persist && n_it > n_resident * plan_warps) {
         // persistent plan: `slots` contiguous ranges of equal work (entries + a per-item constant), longest item first inside each
         constexpr int64_t kItemCost = 96;                  // a row's fixed work (index loads, reduction, epilogue) in entry equivalents
@@ -1325,24 +1771,26 @@ int vrad_transfers_info(vrad_env* e, int64_t* row0, int64_t* row1, int64_t* nnz)
     return VRAD_OK;
 }
 
-int vrad_transfers_layout(vrad_env* e, int64_t* pair_entries, int64_t* packed_entries, int64_t* packed_segments) {
+int vrad_transfers_layout(vrad_env* e, int64_t* pair_entries, int64_t* packed_entries, int64_t* packed_segments, int64_t* block_entries) {
     if (!e) return VRAD_E_INVALID;
-    int64_t a = 0, b = 0, c = 0;
+    int64_t a = 0, b = 0, c = 0, d = 0;
     if (e->multi) {
         for (vrad_env* r : e->multi->ranks) {
-            int64_t x, y, z;
-            const int rc = vrad_transfers_layout(r, &x, &y, &z);
+            int64_t x, y, z, u;
+            const int rc = vrad_transfers_layout(r, &x, &y, &z, &u);
             if (rc) return rc;
-            a += x; b += y; c += z;
+            a += x; b += y; c += z; d += u;
         }
     } else {
         if (!e->transfers.ready) { set_error("vrad_transfers_layout: no transfers resident"); return VRAD_E_STATE; }
         a = e->transfers.nnz_padded;
         if (e->transfers.packed) { b = e->transfers.pk_entries; c = e->transfers.pk_n_segs; }
+        if (e->transfers.blocked) d = e->transfers.bk_entries;
     }
     if (pair_entries) *pair_entries = a;
     if (packed_entries) *packed_entries = b;
     if (packed_segments) *packed_segments = c;
+    if (block_entries) *block_entries = d;
     return VRAD_OK;
 }
 
@@ -1410,8 +1858,14 @@ static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, b
     TransfersDev& T = e->transfers;
     if (!p2p) {
         const int nloc = (int)(T.row1 - T.row0);
-        const int nblocks = std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
-        if (T.packed) {
+        const int nblocks = plain_gather_blocks(T, nloc);
+        if (T.blocked) {
+            const BlockedRows bk{T.bk_seg_ptr.p, T.bk_segs.p, T.bk_w.p, T.bk_c.p};
+            // 4 entries in flight per lane, 4 blocks per SM (64 registers); measured alternatives on the C4 matrix (us per bounce, this form 159):
+            // 1 entry 256, 2 entries 180 (193 at 5 blocks, 182 at 3), 3 entries 170, 4 entries at 3 blocks per SM 175
+            k4_gather_blocked<4, 4><<<nblocks, kGatherBlock, 0, e->stream>>>(T.bk_n_blocks, nloc, T.row0, bk, e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
+        }
+        else if (T.packed) {
             const PackedRows pk{T.pk_seg_ptr.p, T.pk_segs.p, T.pk_w.p, T.pk_c.p};
             // 4 pairs in flight per lane at 48 registers / 5 blocks per SM; measured alternatives on the C4 matrix (us per bounce, this form 250):
             // 6 pairs 277 (spills), 6 pairs / 4 blocks 282, 8 pairs / 4 blocks 417, 3 pairs / 6 blocks 258, 2 pairs / 6 blocks 286, 4 pairs / 4 blocks 303, 4 pairs / 6 blocks 323
@@ -1457,6 +1911,10 @@ static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, b
     A.pk_w = T.pk_w.p; A.pk_c = T.pk_c.p;
     auto kern = w6 ? (cs ? k4_gather_items<true, 6, true> : k4_gather_items<true, 6, false>) : (cs ? k4_gather_items<true, 8, true> : k4_gather_items<true, 8, false>);
     if (T.plan_packed) kern = w6 ? k4_gather_items<true, 6, true, true> : k4_gather_items<true, 8, true, true>;
+    A.bk_w = T.bk_w.p; A.bk_c = T.bk_c.p; A.nloc = (int)(T.row1 - T.row0);
+    if (T.plan_blocked)
+        return cudaLaunchKernelEx(&cfg, k4_gather_items_blocked<true, 8>, (const int32_t*)T.block_ptr.p, (const int4*)T.items.p, T.row0,
+                                  (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
     return cudaLaunchKernelEx(&cfg, kern, (const int32_t*)T.block_ptr.p, (const int4*)T.items.p, (const int32_t*)T.item_slot.p, T.row0,
                               (const int2*)T.tr.p, (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
 }
@@ -1514,6 +1972,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     }
     const int nloc = (int)(T.row1 - T.row0);
     const int nblocks = std::max(1, (nloc + kGatherWarps - 1) / kGatherWarps);
+    const int plain_blocks = plain_gather_blocks(T, nloc);          // partials the single-GPU gather writes (fewer with block rows)
     const int add_blocks = std::max(1, (nloc + 1023) / 1024);
     // `total` is indexed by global row too, so that the final gather is in place
     if (e->d_er[0].alloc(n_pad) || e->d_er[1].alloc(n_pad) || e->d_total.alloc(n_pad) || e->d_add.alloc((size_t)nloc + 1) ||
@@ -1635,7 +2094,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
     const bool graphed = launch_only && use_graph && !early_out && !verbose && n_bounces >= 4;
     if (graphed) {
         GraphCache& G = e->bounce_graph;
-        const int64_t graph_tag = ((T.plan_serial * 8 + (use_pdl ? 4 : 0) + (p2p ? 2 : 0) + (p2p_hier ? 1 : 0)) * 4 + (use_short ? 2 : 0) + (hier ? 1 : 0)) * 2 + (T.packed ? 1 : 0);
+        const int64_t graph_tag = ((T.plan_serial * 8 + (use_pdl ? 4 : 0) + (p2p ? 2 : 0) + (p2p_hier ? 1 : 0)) * 4 + (use_short ? 2 : 0) + (hier ? 1 : 0)) * 4 + (T.blocked ? 2 : T.packed ? 1 : 0);
         const void* key_items = use_short ? (const void*)d_rows : (const void*)T.items.p;
         const int key_n = use_short ? n_short : T.n_items;
         const bool hit = G.exec && G.n_bounces == n_bounces && G.items == key_items && G.n_items == key_n && G.er0 == e->d_er[0].p && G.total == total_local &&
@@ -1674,7 +2133,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
                 k4_sum_added_rows<<<add_blocks, 256, 0, e->stream>>>(nloc, e->d_add.p, e->d_partials.p);
                 k4_reduce_added<<<1, 256, 0, e->stream>>>(add_blocks, e->d_partials.p, d_added);
                 launches += 2;
-            } else { k4_reduce_added<<<1, 256, 0, e->stream>>>(use_short ? short_blocks : nblocks, e->d_partials.p, d_added); launches++; }
+            } else { k4_reduce_added<<<1, 256, 0, e->stream>>>(use_short ? short_blocks : plain_blocks, e->d_partials.p, d_added); launches++; }
             if (world > 1 && !sim && (rc = comm_allreduce3(e, d_added))) return rc;
         }
     }
@@ -1717,7 +2176,7 @@ int vrad_bounce(vrad_env* e, const float* emit0_rgb, int n_bounces, int early_ou
         if (probe) { cudaEventRecord(pe[n_probe][2], e->stream); n_probe++; }
         cur ^= 1; done++;
         if (early_out || last) {
-            if (use_short || !p2p) { k4_reduce_added<<<1, 256, 0, e->stream>>>(use_short ? short_blocks : nblocks, e->d_partials.p, d_added); launches++; }
+            if (use_short || !p2p) { k4_reduce_added<<<1, 256, 0, e->stream>>>(use_short ? short_blocks : plain_blocks, e->d_partials.p, d_added); launches++; }
             else {
                 k4_sum_added_rows<<<add_blocks, 256, 0, e->stream>>>(nloc, e->d_add.p, e->d_partials.p);
                 k4_reduce_added<<<1, 256, 0, e->stream>>>(add_blocks, e->d_partials.p, d_added);

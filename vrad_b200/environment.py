@@ -338,10 +338,11 @@ class Environment:
         return a.value, b.value, c.value
 
     def transfers_layout(self):
-        """(entries of the {col,w} pair array, entries of the packed 6-byte streams, their segments); packed = (0, 0) when unused."""
-        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
-        check(self._l.vrad_transfers_layout(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
+        """(entries of the {col,w} pair array, entries of the packed 6-byte streams, their segments, entries of the block-row streams);
+        0 where a form is not in use."""
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._l.vrad_transfers_layout(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
 
     def transfers_download(self):
         row0, row1, nnz = self.transfers_info()
@@ -526,6 +527,7 @@ def kd_build_binned_host(verts9):
 
 
 def row_partition(n_rows: int, world: int):
-    """Row ranges owned by each rank (equal blocks of ceil(n/world); the same rule the library uses)."""
-    rpr = (n_rows + world - 1) // world
+    """Row ranges owned by each rank (equal blocks of ceil(n/world) rounded up to a multiple of 4 -- the gather's block-row streams group
+    4 consecutive global rows; the same rule the library uses)."""
+    rpr = ((n_rows + world - 1) // world + 3) & ~3
     return [(min(n_rows, r * rpr), min(n_rows, (r + 1) * rpr)) for r in range(world)]

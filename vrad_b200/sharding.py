@@ -2,7 +2,7 @@
 
 Rays / luxels are independent: each rank takes a contiguous range.  Patch rows of the transfer matrix
 are partitioned in contiguous blocks that tile [0, N) in rank order.  `row_partition` is the default rule (equal
-blocks of ceil(N / world) rows, what vrad_build_transfers uses without a communicator and what callers of
+blocks of ceil(N / world) rows rounded up to a multiple of 4, what vrad_build_transfers uses without a communicator and what callers of
 vrad_transfers_upload typically pass); with a communicator vrad_build_transfers balances the blocks by estimated
 transfers instead.  Radiance buffers are indexed by global patch number, so any such tiling works.  The only
 data-path exchange is the per-bounce hand-over of the new radiance rows.
@@ -15,7 +15,7 @@ from .environment import row_partition  # noqa: F401  (re-exported)
 
 
 def rows_per_rank(n_rows: int, world: int) -> int:
-    return (n_rows + world - 1) // world
+    return ((n_rows + world - 1) // world + 3) & ~3          # blocks start on multiples of 4 (environment.row_partition)
 
 
 def range_partition(n: int, world: int):
