@@ -288,8 +288,8 @@ def run_graft(args, rank, local_rank, world):
     bytes_per_iter_gpu = 8 * nnz_local + 40 * (row1 - row0) + (12 * N if world > 1 else 0)
     bytes_gpu_max = max_over_ranks(float(bytes_per_iter_gpu))
     # what the gather actually streams: 6 B per packed entry (f32 weight + u16 column offset; segments padded to 64) when the rows are packed
-    pair_entries, packed_entries, packed_segments, block_entries = env2.transfers_layout()
-    moved_per_iter_gpu = (18 * block_entries if block_entries else 6 * packed_entries if packed_entries else 8 * pair_entries) + 40 * (row1 - row0) + (12 * N if world > 1 else 0)
+    pair_entries, packed_entries, packed_segments, block_entries, block_rows = env2.transfers_layout()
+    moved_per_iter_gpu = ((2 + 4 * block_rows) * block_entries if block_entries else 6 * packed_entries if packed_entries else 8 * pair_entries) + 40 * (row1 - row0) + (12 * N if world > 1 else 0)
     moved_gpu_max = max_over_ranks(float(moved_per_iter_gpu))
     # the step also carries init / unpack / reduce launches; per-iteration time attributes them to the gather
     gather_gbs_gpu = bytes_gpu_max * iters / (gather_ms * 1e-3) / 1e9
@@ -612,16 +612,16 @@ def run_graft(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "achieved": gather_gbs_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": gather_gbs_gpu / hbm_peak,
                      "traffic": (None if block_entries else 1.2047e9 if packed_entries else 1.5537e9) if world == 1 else None,
                      "traffic_source": "profiles/r02_k4_packed_ncu_summary.txt / profiles/r02_k4_block_ncu_summary.txt (dram read+write per launch, N=1; same kernels)",
-                     "kernel": ("k4_gather_blocked<4, 4>" if block_entries else "k4_gather_packed<4, 5>" if packed_entries else "k4_gather") if world == 1 else
-                               ("k4_gather_items_blocked<true, 8>" if block_entries else "k4_gather_items<true, 8, true, PACKED>" if packed_entries else "k4_gather_items<true, 6>"),
+                     "kernel": (f"k4_gather_blocked<{block_rows}, 4, {4 if block_rows == 4 else 5}>" if block_entries else "k4_gather_packed<4, 5>" if packed_entries else "k4_gather") if world == 1 else
+                               (f"k4_gather_items_blocked<true, 8, {block_rows}>" if block_entries else "k4_gather_items<true, 8, true, PACKED>" if packed_entries else "k4_gather_items<true, 6>"),
                      "bytes_per_iter_per_gpu": bytes_gpu_max, "peak_source": peak_src,
                      "note": "achieved / frac are quoted on the ALGORITHMIC bytes of SURVEY 8(d): 8 B per transfer (the reference's Transfer struct) + 40 B per row. "
                              "The gather reads the transfers in a denser form -- block rows: 4 consecutive rows share the union of their columns, 18 B per union entry "
                              "(u16 column offset + 4 f32 weights, bit-exact), about 5.3 B per transfer on this map; or packed 6-byte entries -- so it moves fewer bytes "
                              "than that and frac can exceed what the memory system delivers: moved_* is the same rate on the bytes actually streamed",
-                     "stream_format": ("block rows: u16 column offset + 4 f32 weights per entry of the union of 4 rows' columns, 18 B" if block_entries else
+                     "stream_format": (f"block rows: u16 column offset + {block_rows} f32 weights per entry of the union of {block_rows} rows' columns, {2 + 4 * block_rows} B" if block_entries else
                                        "packed: f32 weight + u16 column offset, 6 B per transfer" if packed_entries else "{col:int32, w:f32} pairs, 8 B per transfer"),
-                     "block_entries_rank0": block_entries,
+                     "block_entries_rank0": block_entries, "block_rows": block_rows,
                      "packed_entries_rank0": packed_entries, "packed_segments_rank0": packed_segments, "pair_entries_rank0": pair_entries,
                      "moved_bytes_per_iter_per_gpu": moved_gpu_max, "moved_achieved": moved_gpu_max * iters / (gather_ms * 1e-3) / 1e9,
                      "moved_frac": moved_gpu_max * iters / (gather_ms * 1e-3) / 1e9 / hbm_peak,

@@ -298,10 +298,10 @@ int  vrad_transfers_info(vrad_env*, int64_t* row0, int64_t* row1, int64_t* nnz);
 /* how the resident rows are stored for the gather (any pointer may be NULL): entries of the {col,w} pair array (rows padded to 4);
  * entries and segments of the packed streams (f32 weight + u16 column offset from a per-segment base, 6 bytes per entry, segments
  * padded to 64; 0 / 0 when unused -- hierarchy, rows over many column windows, k4_pack = 0); entries of the block-row streams
- * (4 consecutive rows share one column list: u16 column offset + 4 f32 weights = 18 bytes per entry of the union; 0 when unused).
+ * (block_rows = 2 or 4 consecutive rows share one column list: u16 column offset + block_rows f32 weights per entry of the union; 0 when unused).
  * The gather reads the block-row streams if present, else the packed streams, else the pairs.
  * In-process multi-GPU handle: sums over the ranks. */
-int  vrad_transfers_layout(vrad_env*, int64_t* pair_entries, int64_t* packed_entries, int64_t* packed_segments, int64_t* block_entries);
+int  vrad_transfers_layout(vrad_env*, int64_t* pair_entries, int64_t* packed_entries, int64_t* packed_segments, int64_t* block_entries, int64_t* block_rows);
 int  vrad_transfers_download(vrad_env*, int64_t* rowptr, int32_t* col, float* w);
 /* rows [row_begin,row_end) of the resident lists (global row numbers, must be owned by this rank): rowptr gets
  * row_end-row_begin+1 offsets starting at 0; col/w must hold `capacity` entries (VRAD_E_INVALID if too small).

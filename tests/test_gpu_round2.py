@@ -273,9 +273,9 @@ def test_block_row_streams_same_light(s2_small_scene, s2_small_oracle):
     env = environment_from_scene(scene)
     nnz = env.build_transfers(scene.pvs)
     assert nnz == s2_small_oracle.build_transfers(scene.pvs, threads=8)
-    pairs, packed, segs, blocked = env.transfers_layout()
-    assert blocked > 0 and packed == 0                      # block rows in use; their union is far below 4 rows' worth of entries
-    assert blocked * 18 < nnz * 6
+    pairs, packed, segs, blocked, rows = env.transfers_layout()
+    assert blocked > 0 and packed == 0 and rows in (2, 4)   # block rows in use; their union is far below that many rows' worth of entries
+    assert blocked * (2 + 4 * rows) < nnz * 6
     N = scene.n_patches
     emit0 = scenes.SplitMix64(33).uniform(3 * N, 0.0, 200.0).reshape(N, 3)
     out = {}

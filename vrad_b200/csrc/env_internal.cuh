@@ -115,11 +115,11 @@ struct TransfersDev {
     // matters more -- ONE 16-byte er[] gather serves 4 rows.  Segments as for the packed streams (column windows of 65,536 from the
     // block's first column, at most bk_max_seg entries, padded to 32 entries).
     //   segment int4 = {first entry (position in bk_c / bk_w) lo, hi, padded entries, column base}
-    DevBuf<float4>   bk_w;          // weights of the block's rows 0..3 for this column
+    DevBuf<float>    bk_w;          // bk_rows weights per entry: those of the block's rows for this column
     DevBuf<uint16_t> bk_c;
     DevBuf<int4>     bk_segs;
     DevBuf<int32_t>  bk_seg_ptr;    // per block of rows: offsets into bk_segs (n_row_blocks + 1)
-    int64_t bk_entries = 0; int bk_n_segs = 0, bk_n_blocks = 0; bool blocked = false;
+    int64_t bk_entries = 0; int bk_n_segs = 0, bk_n_blocks = 0, bk_rows = 4; bool blocked = false;
     int64_t plan_serial = 0;        // bumped by every re-plan (invalidates the captured bounce graph)
     int64_t rows_serial = 0;        // bumped when the resident rows change (vrad_build_transfers / vrad_transfers_upload: collective calls)
 };
@@ -226,8 +226,9 @@ struct EnvOptions {
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
     int k4_block = 0;      // VRAD_K4_BLOCK: threads per block of the multi-GPU gather: 192 (6 warps, 6 blocks/SM, 56 registers), 256 (8 warps, 5 blocks/SM, 48 registers), 0 = 256 with the packed streams, 192 with the pairs
     int k2_stream = 0;     // VRAD_K2_STREAM: pass A of the transfer build as compacted ray queues with lane refill (experiment, slower: DESIGN section 7; 0 = one ray slot per (row, candidate) thread)
+    int k4_bk_rows = 4;    // VRAD_K4_BK_ROWS: rows per block of the block-row streams (2 or 4)
     int k4_short = -1;     // VRAD_K4_SHORT: the short-row gather (8 lanes per row) on one GPU: -1 = where rows average < 400 transfers, 0 = never, 1 = always
-    int k4_pack = 2;       // VRAD_K4_PACK: 2 = gather from the block-row streams where neighbouring rows share their columns and the work items stay fine enough (else as 1), 3 = the same without the item-count rule, 1 = gather from the packed 6-byte streams where rows are (nearly) one segment each, 0 = from the {col,w} pairs; 9 = pack whatever the segment count
+    int k4_pack = 2;       // VRAD_K4_PACK: 2 = gather from the block-row streams where neighbouring rows share their columns and the work items stay fine enough (else as 1), 3 / 4 = block rows with a warp / a thread block per work item whatever the item count (2 chooses), 1 = gather from the packed 6-byte streams where rows are (nearly) one segment each, 0 = from the {col,w} pairs; 9 = pack whatever the segment count
     int k4_l2_mb = 0;      // VRAD_K4_L2_MB: MB of L2 set aside for the head of the transfer stream of the multi-GPU gather (0 = off)
     int k4_hier_p2p = 1;   // VRAD_K4_HIER_P2P: patch hierarchy on several GPUs: leaf rows by peer stores (0 = all-gather pass per bounce)
     int k4_pool = 25;      // VRAD_K4_POOL: percent of the work left out of the persistent blocks' ranges for whoever finishes early

@@ -292,7 +292,7 @@ k4_gather_packed(int nloc, int64_t row0, PackedRows P, const float4* __restrict_
 // column's bit; the union position of a column is the number of set bits below it (per-word popcount prefix); the rows' weights go to
 // component r of the float4 at that position.  Two passes (sizes, then contents) around two scans, like the packed streams.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kBlockRows = 4;
+constexpr int kBlockRows = 4;                       // the most rows a block of rows may hold (TransfersDev::bk_rows = 2 or 4)
 constexpr int kBkWords = 65536 / 32;
 constexpr int kBkBuildWarps = 2;
 
@@ -302,7 +302,7 @@ struct BkRowSet { int64_t k0[kBlockRows]; int len[kBlockRows]; };
 template <bool FILL>
 __device__ __forceinline__ void block_row_build(const int2* __restrict__ tr, const BkRowSet& R, int max_seg, uint32_t* bm, uint16_t* pre,
                                                 int& n_segs, int64_t& n_padded, int4* __restrict__ segs, int64_t out,
-                                                float4* __restrict__ bw, uint16_t* __restrict__ bc) {
+                                                float* __restrict__ bw, uint16_t* __restrict__ bc, int rows) {
     const int lane = threadIdx.x & 31;
     int col_min = 0x7fffffff, col_max = -1;
 #pragma unroll
@@ -369,7 +369,7 @@ __device__ __forceinline__ void block_row_build(const int2* __restrict__ tr, con
                     const int2 t = tr[R.k0[r] + en];
                     const int c = t.x - base;
                     const int pos = pre[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31)) - 1u));
-                    reinterpret_cast<float*>(&bw[win_out + pos])[r] = __int_as_float(t.y);
+                    bw[(win_out + pos) * rows + r] = __int_as_float(t.y);
                 }
             }
             __syncwarp();
@@ -377,86 +377,95 @@ __device__ __forceinline__ void block_row_build(const int2* __restrict__ tr, con
     }
 }
 
-__device__ __forceinline__ BkRowSet block_rows_of(int blk, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen) {
+__device__ __forceinline__ BkRowSet block_rows_of(int blk, int rows, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen) {
     BkRowSet R;
 #pragma unroll
     for (int r = 0; r < kBlockRows; r++) {
-        const int row = blk * kBlockRows + r;
-        R.k0[r] = row < nloc ? rowptr[row] : 0;
-        R.len[r] = row < nloc ? rowlen[row] : 0;
+        const int row = blk * rows + r;
+        const bool in = r < rows && row < nloc;
+        R.k0[r] = in ? rowptr[row] : 0;
+        R.len[r] = in ? rowlen[row] : 0;
     }
     return R;
 }
 
 __global__ void __launch_bounds__(kBkBuildWarps * 32)
-k4_block_count(int n_blocks, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen, const int2* __restrict__ tr, int max_seg,
+k4_block_count(int n_blocks, int rows, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen, const int2* __restrict__ tr, int max_seg,
                int32_t* __restrict__ n_segs, int64_t* __restrict__ padded) {
     __shared__ uint32_t bm_s[kBkBuildWarps][kBkWords];
     const int warp = threadIdx.x >> 5;
     const int blk = blockIdx.x * kBkBuildWarps + warp;
     if (blk >= n_blocks) return;
     int ns; int64_t np;
-    block_row_build<false>(tr, block_rows_of(blk, nloc, rowptr, rowlen), max_seg, bm_s[warp], nullptr, ns, np, nullptr, 0, nullptr, nullptr);
+    block_row_build<false>(tr, block_rows_of(blk, rows, nloc, rowptr, rowlen), max_seg, bm_s[warp], nullptr, ns, np, nullptr, 0, nullptr, nullptr, rows);
     if ((threadIdx.x & 31) == 0) { n_segs[blk] = ns; padded[blk] = np; }
 }
 
 __global__ void __launch_bounds__(kBkBuildWarps * 32)
-k4_block_fill(int n_blocks, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen, const int2* __restrict__ tr, int max_seg,
-              const int32_t* __restrict__ seg_ptr, const int64_t* __restrict__ bk_start, int4* __restrict__ segs, float4* __restrict__ bw, uint16_t* __restrict__ bc) {
+k4_block_fill(int n_blocks, int rows, int nloc, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ rowlen, const int2* __restrict__ tr, int max_seg,
+              const int32_t* __restrict__ seg_ptr, const int64_t* __restrict__ bk_start, int4* __restrict__ segs, float* __restrict__ bw, uint16_t* __restrict__ bc) {
     __shared__ uint32_t bm_s[kBkBuildWarps][kBkWords];
     __shared__ uint16_t pre_s[kBkBuildWarps][kBkWords];
     const int warp = threadIdx.x >> 5;
     const int blk = blockIdx.x * kBkBuildWarps + warp;
     if (blk >= n_blocks) return;
     int ns; int64_t np;
-    block_row_build<true>(tr, block_rows_of(blk, nloc, rowptr, rowlen), max_seg, bm_s[warp], pre_s[warp], ns, np, segs + seg_ptr[blk], bk_start[blk], bw, bc);
+    block_row_build<true>(tr, block_rows_of(blk, rows, nloc, rowptr, rowlen), max_seg, bm_s[warp], pre_s[warp], ns, np, segs + seg_ptr[blk], bk_start[blk], bw, bc, rows);
 }
 
 // The gather from the block-row streams: one warp per block of kBlockRows rows; a lane takes one entry per step -- a 2-byte column, a
 // 16-byte weight vector, ONE 16-byte er[] gather -- and keeps kBlockRows x 3 sums.
-struct BlockedRows { const int32_t* seg_ptr; const int4* segs; const float4* w; const uint16_t* c; };
+struct BlockedRows { const int32_t* seg_ptr; const int4* segs; const float* w; const uint16_t* c; };
 
-template <int U>
-__device__ __forceinline__ void gather_block_segments(const BlockedRows& P, int sg0, int sg1, const float4* __restrict__ er, int lane, float (&acc)[kBlockRows][3]) {
+// R weights of one entry: one 8- or 16-byte load
+template <int R> __device__ __forceinline__ void load_weights(const float* __restrict__ w, int64_t entry, float (&out)[R]) {
+    if constexpr (R == 4) { const float4 v = __ldcs(reinterpret_cast<const float4*>(w) + entry); out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+    else { const float2 v = __ldcs(reinterpret_cast<const float2*>(w) + entry); out[0] = v.x; out[1] = v.y; }
+}
+
+template <int R, int U>
+__device__ __forceinline__ void gather_block_segments(const BlockedRows& P, int sg0, int sg1, const float4* __restrict__ er, int lane, float (&acc)[R][3]) {
     for (int sg = sg0; sg < sg1; sg++) {
         const int4 d = __ldg(&P.segs[sg]);
         const int64_t k0 = (int64_t)(uint32_t)d.x | ((int64_t)d.y << 32);
         const int len = d.z, base = d.w;
-        const float4* __restrict__ w4 = P.w + k0;
         const uint16_t* __restrict__ c1 = P.c + k0;
-        float4 cw[U], nw[U];
+        float cw[U][R], nw[U][R];
         int cc[U], nc[U];
         int p = lane;
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            const bool in = p + 32 * j < len;
-            cw[j] = in ? __ldcs(&w4[p + 32 * j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            cc[j] = in ? (int)__ldcs(&c1[p + 32 * j]) : 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) cw[j][r] = 0.f;
+            cc[j] = 0;
+            if (p + 32 * j < len) { load_weights<R>(P.w, k0 + p + 32 * j, cw[j]); cc[j] = (int)__ldcs(&c1[p + 32 * j]); }
         }
         for (; p < len; p += 32 * U) {
 #pragma unroll
             for (int j = 0; j < U; j++) {
-                const bool in = p + 32 * (U + j) < len;
-                nw[j] = in ? __ldcs(&w4[p + 32 * (U + j)]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                nc[j] = in ? (int)__ldcs(&c1[p + 32 * (U + j)]) : 0;
+#pragma unroll
+                for (int r = 0; r < R; r++) nw[j][r] = 0.f;
+                nc[j] = 0;
+                if (p + 32 * (U + j) < len) { load_weights<R>(P.w, k0 + p + 32 * (U + j), nw[j]); nc[j] = (int)__ldcs(&c1[p + 32 * (U + j)]); }
             }
             float4 x[U];
 #pragma unroll
             for (int j = 0; j < U; j++) x[j] = __ldg(&er[base + cc[j]]);
 #pragma unroll
-            for (int j = 0; j < U; j++) {
-                acc[0][0] += cw[j].x * x[j].x; acc[0][1] += cw[j].x * x[j].y; acc[0][2] += cw[j].x * x[j].z;
-                acc[1][0] += cw[j].y * x[j].x; acc[1][1] += cw[j].y * x[j].y; acc[1][2] += cw[j].y * x[j].z;
-                acc[2][0] += cw[j].z * x[j].x; acc[2][1] += cw[j].z * x[j].y; acc[2][2] += cw[j].z * x[j].z;
-                acc[3][0] += cw[j].w * x[j].x; acc[3][1] += cw[j].w * x[j].y; acc[3][2] += cw[j].w * x[j].z;
-            }
+            for (int j = 0; j < U; j++)
 #pragma unroll
-            for (int j = 0; j < U; j++) { cw[j] = nw[j]; cc[j] = nc[j]; }
+                for (int r = 0; r < R; r++) { acc[r][0] += cw[j][r] * x[j].x; acc[r][1] += cw[j][r] * x[j].y; acc[r][2] += cw[j][r] * x[j].z; }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+#pragma unroll
+                for (int r = 0; r < R; r++) cw[j][r] = nw[j][r];
+                cc[j] = nc[j];
+            }
         }
     }
 }
 
-template <int U, int kMinBlocks>
+template <int R, int U, int kMinBlocks>
 __global__ void __launch_bounds__(kGatherBlock, kMinBlocks)
 k4_gather_blocked(int n_blocks, int nloc, int64_t row0, BlockedRows P, const float4* __restrict__ er, const float4* __restrict__ refl,
                   float4* __restrict__ er_next, float4* __restrict__ total, float* __restrict__ partials) {
@@ -464,37 +473,36 @@ k4_gather_blocked(int n_blocks, int nloc, int64_t row0, BlockedRows P, const flo
     const int blk = blockIdx.x * kGatherWarps + warp;
     float e0 = 0.f, e1 = 0.f, e2 = 0.f;
     if (blk < n_blocks) {
-        float acc[kBlockRows][3];
+        float acc[R][3];
 #pragma unroll
-        for (int r = 0; r < kBlockRows; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; }
-        gather_block_segments<U>(P, P.seg_ptr[blk], P.seg_ptr[blk + 1], er, lane, acc);
+        for (int r = 0; r < R; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; }
+        gather_block_segments<R, U>(P, P.seg_ptr[blk], P.seg_ptr[blk + 1], er, lane, acc);
 #pragma unroll
-        for (int r = 0; r < kBlockRows; r++)
+        for (int r = 0; r < R; r++)
 #pragma unroll
             for (int c = 0; c < 3; c++)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], o);
         // lane r finishes row r of the block (CollectLight); the block's share of `added` is summed in row order
         float s0 = acc[0][0], s1 = acc[0][1], s2 = acc[0][2];
-        if (lane == 1) { s0 = acc[1][0]; s1 = acc[1][1]; s2 = acc[1][2]; }
-        if (lane == 2) { s0 = acc[2][0]; s1 = acc[2][1]; s2 = acc[2][2]; }
-        if (lane == 3) { s0 = acc[3][0]; s1 = acc[3][1]; s2 = acc[3][2]; }
-        const int row = blk * kBlockRows + lane;
+#pragma unroll
+        for (int r = 1; r < R; r++) if (lane == r) { s0 = acc[r][0]; s1 = acc[r][1]; s2 = acc[r][2]; }
+        const int row = blk * R + lane;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        if (lane < kBlockRows && row < nloc) {
-            const float4 r = refl[row0 + row];
-            if (r.w == 0.0f) {
+        if (lane < R && row < nloc) {
+            const float4 rf = refl[row0 + row];
+            if (rf.w == 0.0f) {
                 float4 t = total[row];
                 t.x += s0; t.y += s1; t.z += s2;
                 total[row] = t;
-                er_next[row0 + row] = make_float4(s0 * r.x, s1 * r.y, s2 * r.z, 0.f);
+                er_next[row0 + row] = make_float4(s0 * rf.x, s1 * rf.y, s2 * rf.z, 0.f);
                 a0 = s0; a1 = s1; a2 = s2;
             } else {
                 er_next[row0 + row] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
-        for (int r = 0; r < kBlockRows; r++) {
+        for (int r = 0; r < R; r++) {
             e0 += __shfl_sync(0xffffffffu, a0, r); e1 += __shfl_sync(0xffffffffu, a1, r); e2 += __shfl_sync(0xffffffffu, a2, r);
         }
     }
@@ -553,7 +561,7 @@ struct GatherAux {                 // rarely used pointers, kept in the paramete
     int pool_begin, n_items;       // items [pool_begin, n_items) belong to no block: whoever runs dry takes them one by one (flags[kFlagPool])
     const float* pk_w;             // PACKED only: the weight and column streams (TransfersDev::pk_w / pk_c)
     const uint16_t* pk_c;
-    const float4* bk_w;            // block-row kernel only (TransfersDev::bk_w / bk_c)
+    const float* bk_w;             // block-row kernel only (TransfersDev::bk_w / bk_c)
     const uint16_t* bk_c;
     int nloc;
 };
@@ -869,8 +877,8 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
 // whose union spans several segments keeps the matrix on the packed streams: build_gather_plan) and kBlockRows epilogues per item.
 // Lane-to-entry mapping and accumulation order are those of k4_gather_blocked: one GPU and several give the same bits.
 constexpr int kBkUnroll = 4;
-template <bool MULTI, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 4)
+template <bool MULTI, int WARPS, int R>
+__global__ void __launch_bounds__(WARPS * 32, R == 4 ? 4 : 5)
 k4_gather_items_blocked(const int32_t* __restrict__ block_ptr, const int4* __restrict__ items, int64_t row0, const float4* er, const float4* __restrict__ refl,
                         float4* er_next, float4* __restrict__ total, GatherAux A) {
     __shared__ int next_item;
@@ -896,18 +904,19 @@ k4_gather_items_blocked(const int32_t* __restrict__ block_ptr, const int4* __res
     int w = claim();
     int4 it = make_int4(0, 0, 0, 0);
     if (w != kNoItem) it = __ldg(&items[w]);
-    float4 cw[kBkUnroll], nw[kBkUnroll];
+    float cw[kBkUnroll][R], nw[kBkUnroll][R];
     int cc[kBkUnroll], nc[kBkUnroll];
-    {
-        const int64_t k0 = (int64_t)(uint32_t)it.z << 5;
-        const int l0 = it.y & 0xffff;
+    auto first_loads = [&](const int4& d, int l0) {
+        const int64_t k0 = (int64_t)(uint32_t)d.z << 5;
 #pragma unroll
         for (int j = 0; j < kBkUnroll; j++) {
-            const bool in = lane + 32 * j < l0;
-            cw[j] = in ? __ldcs(&A.bk_w[k0 + lane + 32 * j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            cc[j] = in ? (int)__ldcs(&A.bk_c[k0 + lane + 32 * j]) : 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) cw[j][r] = 0.f;
+            cc[j] = 0;
+            if (lane + 32 * j < l0) { load_weights<R>(A.bk_w, k0 + lane + 32 * j, cw[j]); cc[j] = (int)__ldcs(&A.bk_c[k0 + lane + 32 * j]); }
         }
-    }
+    };
+    first_loads(it, it.y & 0xffff);
     int wn = w != kNoItem ? claim() : kNoItem;
     if (wn != kNoItem && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
     if (MULTI) {
@@ -916,33 +925,34 @@ k4_gather_items_blocked(const int32_t* __restrict__ block_ptr, const int4* __res
     bool has = w != kNoItem;
     while (has) {
         if (lane == 0) hold_s[warp] = make_int4(it.x, it.y, w, wn);
-        float acc[kBlockRows][3];
+        float acc[R][3];
 #pragma unroll
-        for (int r = 0; r < kBlockRows; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; }
+        for (int r = 0; r < R; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; }
         {
             const int64_t k0 = (int64_t)(uint32_t)it.z << 5;
-            const float4* w4 = A.bk_w + k0;
             const uint16_t* c1 = A.bk_c + k0;
             const int len = it.y & 0xffff, base = it.w;
             for (int off = lane; off < len; off += 32 * kBkUnroll) {
 #pragma unroll
                 for (int j = 0; j < kBkUnroll; j++) {
-                    const bool in = off + 32 * (kBkUnroll + j) < len;
-                    nw[j] = in ? __ldcs(&w4[off + 32 * (kBkUnroll + j)]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    nc[j] = in ? (int)__ldcs(&c1[off + 32 * (kBkUnroll + j)]) : 0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) nw[j][r] = 0.f;
+                    nc[j] = 0;
+                    if (off + 32 * (kBkUnroll + j) < len) { load_weights<R>(A.bk_w, k0 + off + 32 * (kBkUnroll + j), nw[j]); nc[j] = (int)__ldcs(&c1[off + 32 * (kBkUnroll + j)]); }
                 }
                 float4 x[kBkUnroll];
 #pragma unroll
                 for (int j = 0; j < kBkUnroll; j++) x[j] = load_er<MULTI>(er, base + cc[j]);
 #pragma unroll
-                for (int j = 0; j < kBkUnroll; j++) {
-                    acc[0][0] += cw[j].x * x[j].x; acc[0][1] += cw[j].x * x[j].y; acc[0][2] += cw[j].x * x[j].z;
-                    acc[1][0] += cw[j].y * x[j].x; acc[1][1] += cw[j].y * x[j].y; acc[1][2] += cw[j].y * x[j].z;
-                    acc[2][0] += cw[j].z * x[j].x; acc[2][1] += cw[j].z * x[j].y; acc[2][2] += cw[j].z * x[j].z;
-                    acc[3][0] += cw[j].w * x[j].x; acc[3][1] += cw[j].w * x[j].y; acc[3][2] += cw[j].w * x[j].z;
-                }
+                for (int j = 0; j < kBkUnroll; j++)
 #pragma unroll
-                for (int j = 0; j < kBkUnroll; j++) { cw[j] = nw[j]; cc[j] = nc[j]; }
+                    for (int r = 0; r < R; r++) { acc[r][0] += cw[j][r] * x[j].x; acc[r][1] += cw[j][r] * x[j].y; acc[r][2] += cw[j][r] * x[j].z; }
+#pragma unroll
+                for (int j = 0; j < kBkUnroll; j++) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) cw[j][r] = nw[j][r];
+                    cc[j] = nc[j];
+                }
             }
         }
         __syncwarp();
@@ -954,28 +964,19 @@ k4_gather_items_blocked(const int32_t* __restrict__ block_ptr, const int4* __res
         __syncwarp();
         it = desc_s[warp];
         __syncwarp();
-        {
-            const int64_t k0 = (int64_t)(uint32_t)it.z << 5;
-            const int ln = has_next ? (it.y & 0xffff) : 0;
-#pragma unroll
-            for (int j = 0; j < kBkUnroll; j++) {
-                const bool in = lane + 32 * j < ln;
-                cw[j] = in ? __ldcs(&A.bk_w[k0 + lane + 32 * j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                cc[j] = in ? (int)__ldcs(&A.bk_c[k0 + lane + 32 * j]) : 0;
-            }
-        }
+        first_loads(it, has_next ? (it.y & 0xffff) : 0);
         w = wn;
         wn = has_next ? claim() : kNoItem;
         if (wn != kNoItem && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
 #pragma unroll
-        for (int r = 0; r < kBlockRows; r++)
+        for (int r = 0; r < R; r++)
 #pragma unroll
             for (int c = 0; c < 3; c++)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], o);
 #pragma unroll
-        for (int r = 0; r < kBlockRows; r++) {
-            const int row = blk * kBlockRows + r;
+        for (int r = 0; r < R; r++) {
+            const int row = blk * R + r;
             if (row < A.nloc) {                                             // warp-uniform
                 float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);                // sky: emit = 0
                 if (lane == 0) {
@@ -1323,15 +1324,19 @@ static int build_packed_streams(vrad_env* e, int64_t nloc) {
 static int build_block_streams(vrad_env* e, int64_t nloc) {
     TransfersDev& T = e->transfers;
     T.blocked = false;
+    const int rows = e->opt.k4_bk_rows == 2 ? 2 : 4;
     if ((e->opt.k4_pack != 2 && e->opt.k4_pack != 3) || e->patches.hier || nloc <= 0 || (T.row0 % kBlockRows) != 0) return 0;
     int max_seg = 1 << 8;
     while ((max_seg << 1) <= e->opt.k4_seg && max_seg < (1 << 15)) max_seg <<= 1;
-    const int nb = (int)((nloc + kBlockRows - 1) / kBlockRows);
-    // With several ranks a block of rows is ONE work item of the persistent kernel (4 blocks x 8 warps per SM): below ~4 items per resident
-    // warp the ranges no longer balance (C4 at 8 ranks: 5,854 items for 4,736 warps -- 48 us per bounce on the slice against 40 us from
-    // the packed streams, whose items are single rows), so such a slice stays on the packed streams.  k4_pack = 3 keeps the block rows.
+    const int nb = (int)((nloc + rows - 1) / rows);
+    // With several ranks a block of rows is ONE work item of the persistent kernel (4 blocks x 8 warps per SM).  Below ~2 items per resident
+    // warp the warps' ranges no longer balance -- C4 slices on one GPU, us per bounce, block rows / packed streams: 2 ranks 88 / 127,
+    // 4 ranks (2.5 items per warp) 56 / 69, 8 ranks (1.2 per warp) 50 / 40 -- and the slice stays on the packed streams, whose items are
+    // single rows.  (2 rows per block instead of 4 doubles the items for the same bytes but also the gathers: 43 at 8 ranks, 100 at 2; a
+    // thread block per item with the sums combined in shared memory: 43 at 8 ranks, 153 at 2.  profiles/r02_k4_block_rows_sim.json)
+    // k4_pack = 3 keeps the block rows whatever the count.
     const bool work_items = e->cfg.world > 1 || e->opt.k4_items;
-    if (work_items && e->opt.k4_pack != 3 && (int64_t)nb < (int64_t)4 * e->sm_count * 4 * 8) return 0;
+    if (work_items && e->opt.k4_pack != 3 && (int64_t)nb < (int64_t)2 * e->sm_count * 4 * 8) return 0;
     DevBuf<int32_t> d_ns; DevBuf<int64_t> d_pad, d_start; DevBuf<unsigned char> d_tmp;
     auto drop = [&]() { d_ns.release(); d_pad.release(); d_start.release(); d_tmp.release(); };
     if (d_ns.alloc(nb + 1) || d_pad.alloc(nb + 1) || d_start.alloc(nb + 1) || T.bk_seg_ptr.alloc(nb + 1)) { drop(); set_error("out of device memory (block-row transfer streams)"); return VRAD_E_NOMEM; }
@@ -1339,7 +1344,7 @@ static int build_block_streams(vrad_env* e, int64_t nloc) {
     BK_CHECK(cudaMemsetAsync(d_ns.p, 0, ((size_t)nb + 1) * 4, e->stream));
     BK_CHECK(cudaMemsetAsync(d_pad.p, 0, ((size_t)nb + 1) * 8, e->stream));
     const int grid = (nb + kBkBuildWarps - 1) / kBkBuildWarps;
-    k4_block_count<<<grid, kBkBuildWarps * 32, 0, e->stream>>>(nb, (int)nloc, T.rowptr.p, T.rowlen.p, T.tr.p, max_seg, d_ns.p, d_pad.p);
+    k4_block_count<<<grid, kBkBuildWarps * 32, 0, e->stream>>>(nb, rows, (int)nloc, T.rowptr.p, T.rowlen.p, T.tr.p, max_seg, d_ns.p, d_pad.p);
     size_t b1 = 0, b2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, b1, d_ns.p, T.bk_seg_ptr.p, nb + 1, e->stream);
     cub::DeviceScan::ExclusiveSum(nullptr, b2, d_pad.p, d_start.p, nb + 1, e->stream);
@@ -1352,8 +1357,8 @@ static int build_block_streams(vrad_env* e, int64_t nloc) {
     BK_CHECK(cudaStreamSynchronize(e->stream));
     if (getenv("VRAD_VERBOSE"))
         fprintf(stderr, "[vrad] rank %d block-row streams: %d blocks of %d rows, %d segments, %lld union entries for %lld transfers (%.2f x one row per block, %.2f B per transfer)\n",
-                e->cfg.rank, nb, kBlockRows, n_segs, (long long)n_entries, (long long)T.nnz, T.nnz > 0 ? (double)n_entries * kBlockRows / (double)T.nnz : 0.0,
-                T.nnz > 0 ? (double)n_entries * 18.0 / (double)T.nnz : 0.0);
+                e->cfg.rank, nb, rows, n_segs, (long long)n_entries, (long long)T.nnz, T.nnz > 0 ? (double)n_entries * rows / (double)T.nnz : 0.0,
+                T.nnz > 0 ? (double)n_entries * (2.0 + 4.0 * rows) / (double)T.nnz : 0.0);
     // worth it only where neighbouring rows share their columns (18 B per union entry against 4 rows x 6 B per packed entry), and the work-item
     // kernel takes a block of rows as ONE item: every block must be a single segment (its union inside one 65,536-column window, at most k4_seg entries)
     bool single = (int64_t)n_segs <= nb;
@@ -1362,19 +1367,19 @@ static int build_block_streams(vrad_env* e, int64_t nloc) {
         BK_CHECK(cudaMemcpy(hns.data(), d_ns.p, (size_t)nb * 4, cudaMemcpyDeviceToHost));
         for (int b = 0; b < nb && single; b++) single = hns[b] <= 1;
     }
-    if (!single || (double)n_entries * 18.0 > (double)T.nnz * 6.0 * 1.1) { drop(); return 0; }
-    if (T.bk_segs.alloc((size_t)n_segs + 1) || T.bk_w.alloc((size_t)n_entries + 32) || T.bk_c.alloc((size_t)n_entries + 32)) {
+    if (!single || (double)n_entries * (2.0 + 4.0 * rows) > (double)T.nnz * 6.0 * 1.1) { drop(); return 0; }
+    if (T.bk_segs.alloc((size_t)n_segs + 1) || T.bk_w.alloc(((size_t)n_entries + 32) * rows) || T.bk_c.alloc((size_t)n_entries + 32)) {
         T.bk_segs.release(); T.bk_w.release(); T.bk_c.release(); drop();
         return 0;
     }
-    BK_CHECK(cudaMemsetAsync(T.bk_w.p, 0, ((size_t)n_entries + 32) * sizeof(float4), e->stream));
+    BK_CHECK(cudaMemsetAsync(T.bk_w.p, 0, ((size_t)n_entries + 32) * rows * sizeof(float), e->stream));
     BK_CHECK(cudaMemsetAsync(T.bk_c.p, 0, ((size_t)n_entries + 32) * sizeof(uint16_t), e->stream));
-    k4_block_fill<<<grid, kBkBuildWarps * 32, 0, e->stream>>>(nb, (int)nloc, T.rowptr.p, T.rowlen.p, T.tr.p, max_seg, T.bk_seg_ptr.p, d_start.p, T.bk_segs.p, T.bk_w.p, T.bk_c.p);
+    k4_block_fill<<<grid, kBkBuildWarps * 32, 0, e->stream>>>(nb, rows, (int)nloc, T.rowptr.p, T.rowlen.p, T.tr.p, max_seg, T.bk_seg_ptr.p, d_start.p, T.bk_segs.p, T.bk_w.p, T.bk_c.p);
     BK_CHECK(cudaGetLastError());
     BK_CHECK(cudaStreamSynchronize(e->stream));
 #undef BK_CHECK
     drop();
-    T.bk_entries = n_entries; T.bk_n_segs = n_segs; T.bk_n_blocks = nb; T.blocked = true;
+    T.bk_entries = n_entries; T.bk_n_segs = n_segs; T.bk_n_blocks = nb; T.bk_rows = rows; T.blocked = true;
     return 0;
 }
 
@@ -1469,7 +1474,7 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     int pool_begin = n_it;
     // 0 = automatic: 8 warps x 5 blocks per SM at 48 registers for the packed streams, 6 x 6 at 56 registers for the pairs (measured at 2, 4 and 8 GPUs)
     const int plan_warps = T.plan_blocked ? 8 : e->opt.k4_block ? (e->opt.k4_block == 192 ? 6 : 8) : (T.plan_packed ? 8 : 6);
-    const int n_resident = e->sm_count * (T.plan_blocked ? 4 : plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS> / k4_gather_items_blocked
+    const int n_resident = e->sm_count * (T.plan_blocked ? (T.bk_rows == 4 ? 4 : 5) : plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS> / k4_gather_items_blocked
     if (e->opt.k4_persist && n_it > n_resident * plan_warps) {
         // persistent plan: `slots` contiguous ranges of equal work (entries + a per-item constant), longest item first inside each
         constexpr int64_t kItemCost = 96;                  // a row's fixed work (index loads, reduction, epilogue) in entry equivalents
@@ -1771,26 +1776,27 @@ int vrad_transfers_info(vrad_env* e, int64_t* row0, int64_t* row1, int64_t* nnz)
     return VRAD_OK;
 }
 
-int vrad_transfers_layout(vrad_env* e, int64_t* pair_entries, int64_t* packed_entries, int64_t* packed_segments, int64_t* block_entries) {
+int vrad_transfers_layout(vrad_env* e, int64_t* pair_entries, int64_t* packed_entries, int64_t* packed_segments, int64_t* block_entries, int64_t* block_rows) {
     if (!e) return VRAD_E_INVALID;
-    int64_t a = 0, b = 0, c = 0, d = 0;
+    int64_t a = 0, b = 0, c = 0, d = 0, br = 0;
     if (e->multi) {
         for (vrad_env* r : e->multi->ranks) {
-            int64_t x, y, z, u;
-            const int rc = vrad_transfers_layout(r, &x, &y, &z, &u);
+            int64_t x, y, z, u, v;
+            const int rc = vrad_transfers_layout(r, &x, &y, &z, &u, &v);
             if (rc) return rc;
-            a += x; b += y; c += z; d += u;
+            a += x; b += y; c += z; d += u; br = v;
         }
     } else {
         if (!e->transfers.ready) { set_error("vrad_transfers_layout: no transfers resident"); return VRAD_E_STATE; }
         a = e->transfers.nnz_padded;
         if (e->transfers.packed) { b = e->transfers.pk_entries; c = e->transfers.pk_n_segs; }
-        if (e->transfers.blocked) d = e->transfers.bk_entries;
+        if (e->transfers.blocked) { d = e->transfers.bk_entries; br = e->transfers.bk_rows; }
     }
     if (pair_entries) *pair_entries = a;
     if (packed_entries) *packed_entries = b;
     if (packed_segments) *packed_segments = c;
     if (block_entries) *block_entries = d;
+    if (block_rows) *block_rows = br;
     return VRAD_OK;
 }
 
@@ -1861,9 +1867,12 @@ static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, b
         const int nblocks = plain_gather_blocks(T, nloc);
         if (T.blocked) {
             const BlockedRows bk{T.bk_seg_ptr.p, T.bk_segs.p, T.bk_w.p, T.bk_c.p};
-            // 4 entries in flight per lane, 4 blocks per SM (64 registers); measured alternatives on the C4 matrix (us per bounce, this form 159):
+            // 4 rows per block: 4 entries in flight per lane, 4 blocks per SM (64 registers); measured alternatives on the C4 matrix (us per bounce, this form 159):
             // 1 entry 256, 2 entries 180 (193 at 5 blocks, 182 at 3), 3 entries 170, 4 entries at 3 blocks per SM 175
-            k4_gather_blocked<4, 4><<<nblocks, kGatherBlock, 0, e->stream>>>(T.bk_n_blocks, nloc, T.row0, bk, e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
+            if (T.bk_rows == 4)
+                k4_gather_blocked<4, 4, 4><<<nblocks, kGatherBlock, 0, e->stream>>>(T.bk_n_blocks, nloc, T.row0, bk, e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
+            else
+                k4_gather_blocked<2, 4, 5><<<nblocks, kGatherBlock, 0, e->stream>>>(T.bk_n_blocks, nloc, T.row0, bk, e->d_er[cur].p, e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, e->d_partials.p);
         }
         else if (T.packed) {
             const PackedRows pk{T.pk_seg_ptr.p, T.pk_segs.p, T.pk_w.p, T.pk_c.p};
@@ -1913,8 +1922,8 @@ static cudaError_t launch_gather(vrad_env* e, bool p2p, bool chained, int cur, b
     if (T.plan_packed) kern = w6 ? k4_gather_items<true, 6, true, true> : k4_gather_items<true, 8, true, true>;
     A.bk_w = T.bk_w.p; A.bk_c = T.bk_c.p; A.nloc = (int)(T.row1 - T.row0);
     if (T.plan_blocked)
-        return cudaLaunchKernelEx(&cfg, k4_gather_items_blocked<true, 8>, (const int32_t*)T.block_ptr.p, (const int4*)T.items.p, T.row0,
-                                  (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
+        return cudaLaunchKernelEx(&cfg, T.bk_rows == 4 ? k4_gather_items_blocked<true, 8, 4> : k4_gather_items_blocked<true, 8, 2>, (const int32_t*)T.block_ptr.p,
+                                  (const int4*)T.items.p, T.row0, (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
     return cudaLaunchKernelEx(&cfg, kern, (const int32_t*)T.block_ptr.p, (const int4*)T.items.p, (const int32_t*)T.item_slot.p, T.row0,
                               (const int2*)T.tr.p, (const float4*)e->d_er[cur].p, (const float4*)e->patches.refl.p, e->d_er[cur ^ 1].p, total_local, A);
 }

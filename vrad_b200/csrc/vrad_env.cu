@@ -206,6 +206,7 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
     e->opt.k2_stream = env_int("VRAD_K2_STREAM", e->opt.k2_stream);
     e->opt.k4_pack = env_int("VRAD_K4_PACK", e->opt.k4_pack);
     e->opt.k4_short = env_int("VRAD_K4_SHORT", e->opt.k4_short);
+    e->opt.k4_bk_rows = env_int("VRAD_K4_BK_ROWS", e->opt.k4_bk_rows);
     e->opt.k4_items = env_int("VRAD_K4_ITEMS", e->opt.k4_items);
     e->opt.k4_pdl = env_int("VRAD_K4_PDL", e->opt.k4_pdl);
     e->opt.k4_graph = env_int("VRAD_K4_GRAPH", e->opt.k4_graph);
@@ -283,8 +284,8 @@ int vrad_env_set_option(vrad_env* e, const char* name, int value) {
     else if (n == "k4_hier_p2p") o.k4_hier_p2p = value;
     else if (n == "k4_l2_mb") o.k4_l2_mb = value;
     else if (n == "k2_stream") o.k2_stream = value;
-    else if (n == "k4_pack" || n == "k4_seg" || n == "k4_long_first" || n == "k4_persist" || n == "k4_block" || n == "k4_pool") {
-        (n == "k4_pack" ? o.k4_pack : n == "k4_seg" ? o.k4_seg : (n == "k4_persist" ? o.k4_persist : (n == "k4_block" ? o.k4_block : (n == "k4_pool" ? o.k4_pool : o.k4_long_first)))) = value;
+    else if (n == "k4_bk_rows" || n == "k4_pack" || n == "k4_seg" || n == "k4_long_first" || n == "k4_persist" || n == "k4_block" || n == "k4_pool") {
+        (n == "k4_bk_rows" ? o.k4_bk_rows : n == "k4_pack" ? o.k4_pack : n == "k4_seg" ? o.k4_seg : (n == "k4_persist" ? o.k4_persist : (n == "k4_block" ? o.k4_block : (n == "k4_pool" ? o.k4_pool : o.k4_long_first)))) = value;
         if (e->transfers.ready) {           // re-plan the resident rows
             VRAD_CUDA_CHECK(cudaSetDevice(e->cfg.device));
             const int64_t nloc = e->transfers.row1 - e->transfers.row0;

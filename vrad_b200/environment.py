@@ -338,11 +338,11 @@ class Environment:
         return a.value, b.value, c.value
 
     def transfers_layout(self):
-        """(entries of the {col,w} pair array, entries of the packed 6-byte streams, their segments, entries of the block-row streams);
-        0 where a form is not in use."""
-        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
-        check(self._l.vrad_transfers_layout(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return a.value, b.value, c.value, d.value
+        """(entries of the {col,w} pair array, entries of the packed 6-byte streams, their segments, entries of the block-row streams,
+        rows per block); 0 where a form is not in use."""
+        a, b, c, d, r = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self._l.vrad_transfers_layout(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(r)))
+        return a.value, b.value, c.value, d.value, r.value
 
     def transfers_download(self):
         row0, row1, nnz = self.transfers_info()
