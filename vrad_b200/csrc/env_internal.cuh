@@ -226,6 +226,7 @@ struct EnvOptions {
     int k4_long_first = 0; // VRAD_K4_ORDER=long: work items longest first
     int k4_block = 0;      // VRAD_K4_BLOCK: threads per block of the multi-GPU gather: 192 (6 warps, 6 blocks/SM, 56 registers), 256 (8 warps, 5 blocks/SM, 48 registers), 0 = 256 with the packed streams, 192 with the pairs
     int k2_stream = 0;     // VRAD_K2_STREAM: pass A of the transfer build as compacted ray queues with lane refill (experiment, slower: DESIGN section 7; 0 = one ray slot per (row, candidate) thread)
+    int k4_bk_min_items = 80; // VRAD_K4_BK_MIN_ITEMS: tenths of a block-row item per (SM x 8 warps) below which several ranks stay on the packed streams
     int k4_bk_rows = 4;    // VRAD_K4_BK_ROWS: rows per block of the block-row streams (2 or 4)
     int k4_short = -1;     // VRAD_K4_SHORT: the short-row gather (8 lanes per row) on one GPU: -1 = where rows average < 400 transfers, 0 = never, 1 = always
     int k4_pack = 2;       // VRAD_K4_PACK: 2 = gather from the block-row streams where neighbouring rows share their columns and the work items stay fine enough (else as 1), 3 / 4 = block rows with a warp / a thread block per work item whatever the item count (2 chooses), 1 = gather from the packed 6-byte streams where rows are (nearly) one segment each, 0 = from the {col,w} pairs; 9 = pack whatever the segment count

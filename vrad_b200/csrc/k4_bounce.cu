@@ -708,13 +708,16 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
     // next item of this block's range; when the range is used up, of the common pool (global counter) -- equal work is
     // not equal time (cache hit rates and DRAM conflicts differ from range to range), and with a barrier behind every
     // bounce the slots that finish early would otherwise idle until the slowest range is done
+    // the common pool's counter belongs to the bounce that is running: a block of the NEXT bounce (launched behind it, PDL) may take from the
+    // pool only after its barrier wait, i.e. after the running bounce's last block has reset the counter
+    bool pool_ok = !MULTI || A.wait_rel == 0;
     auto claim = [&]() {
         int c = kNoItem;
         if (lane == 0) {
             c = atomicAdd(&next_item, 1);
             if (c >= __ldg(&block_ptr[blockIdx.x + 1])) {
                 c = kNoItem;
-                if (MULTI && A.pool_begin < A.n_items) {
+                if (MULTI && pool_ok && A.pool_begin < A.n_items) {
                     const int q = A.pool_begin + (int)atomicAdd((unsigned int*)A.flags + kFlagPool, 1u);
                     if (q < A.n_items) c = q;
                 }
@@ -753,6 +756,7 @@ k4_gather_items(const int32_t* __restrict__ block_ptr, const int4* __restrict__ 
         // the radiance this bounce reads is complete once every rank's previous-bounce epoch has arrived; every warp
         // passes here exactly once, with its first {col,w} loads (which do not depend on the peers) in flight
         if (A.wait_rel) wait_for_peers(A.flags, A.wait_world, A.wait_rel);
+        pool_ok = true;
     }
     bool has = w != kNoItem;
     while (has) {
@@ -887,13 +891,16 @@ k4_gather_items_blocked(const int32_t* __restrict__ block_ptr, const int4* __res
     if (MULTI) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) next_item = __ldg(&block_ptr[blockIdx.x]);
     __syncthreads();
+    // the common pool's counter belongs to the bounce that is running: a block of the NEXT bounce (launched behind it, PDL) may take from the
+    // pool only after its barrier wait, i.e. after the running bounce's last block has reset the counter
+    bool pool_ok = !MULTI || A.wait_rel == 0;
     auto claim = [&]() {
         int c = kNoItem;
         if (lane == 0) {
             c = atomicAdd(&next_item, 1);
             if (c >= __ldg(&block_ptr[blockIdx.x + 1])) {
                 c = kNoItem;
-                if (MULTI && A.pool_begin < A.n_items) {
+                if (MULTI && pool_ok && A.pool_begin < A.n_items) {
                     const int q = A.pool_begin + (int)atomicAdd((unsigned int*)A.flags + kFlagPool, 1u);
                     if (q < A.n_items) c = q;
                 }
@@ -921,6 +928,7 @@ k4_gather_items_blocked(const int32_t* __restrict__ block_ptr, const int4* __res
     if (wn != kNoItem && lane == 0) cp_async16(&desc_s[warp], &items[wn]);
     if (MULTI) {
         if (A.wait_rel) wait_for_peers(A.flags, A.wait_world, A.wait_rel);
+        pool_ok = true;
     }
     bool has = w != kNoItem;
     while (has) {
@@ -1336,7 +1344,7 @@ static int build_block_streams(vrad_env* e, int64_t nloc) {
     // thread block per item with the sums combined in shared memory: 43 at 8 ranks, 153 at 2.  profiles/r02_k4_block_rows_sim.json)
     // k4_pack = 3 keeps the block rows whatever the count.
     const bool work_items = e->cfg.world > 1 || e->opt.k4_items;
-    if (work_items && e->opt.k4_pack != 3 && (int64_t)nb < (int64_t)2 * e->sm_count * 4 * 8) return 0;
+    if (work_items && e->opt.k4_pack != 3 && (int64_t)nb < (int64_t)e->opt.k4_bk_min_items * e->sm_count * 8 / 10) return 0;
     DevBuf<int32_t> d_ns; DevBuf<int64_t> d_pad, d_start; DevBuf<unsigned char> d_tmp;
     auto drop = [&]() { d_ns.release(); d_pad.release(); d_start.release(); d_tmp.release(); };
     if (d_ns.alloc(nb + 1) || d_pad.alloc(nb + 1) || d_start.alloc(nb + 1) || T.bk_seg_ptr.alloc(nb + 1)) { drop(); set_error("out of device memory (block-row transfer streams)"); return VRAD_E_NOMEM; }
@@ -1474,7 +1482,7 @@ int build_gather_plan(vrad_env* e, const int32_t* rowlen, int64_t nloc) {
     int pool_begin = n_it;
     // 0 = automatic: 8 warps x 5 blocks per SM at 48 registers for the packed streams, 6 x 6 at 56 registers for the pairs (measured at 2, 4 and 8 GPUs)
     const int plan_warps = T.plan_blocked ? 8 : e->opt.k4_block ? (e->opt.k4_block == 192 ? 6 : 8) : (T.plan_packed ? 8 : 6);
-    const int n_resident = e->sm_count * (T.plan_blocked ? (T.bk_rows == 4 ? 4 : 5) : plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS> / k4_gather_items_blocked
+    const int n_resident = e->sm_count * (T.plan_blocked ? (T.bk_rows == 4 ? 4 : 5) : plan_warps == 6 ? 6 : 5);      // resident blocks of k4_gather_items<.., WARPS> / k4_gather_items_blocked      // resident blocks of k4_gather_items<.., WARPS> / k4_gather_items_blocked
     if (e->opt.k4_persist && n_it > n_resident * plan_warps) {
         // persistent plan: `slots` contiguous ranges of equal work (entries + a per-item constant), longest item first inside each
         constexpr int64_t kItemCost = 96;                  // a row's fixed work (index loads, reduction, epilogue) in entry equivalents

@@ -207,6 +207,7 @@ int vrad_env_create(const vrad_config* cfg, vrad_env** out) {
     e->opt.k4_pack = env_int("VRAD_K4_PACK", e->opt.k4_pack);
     e->opt.k4_short = env_int("VRAD_K4_SHORT", e->opt.k4_short);
     e->opt.k4_bk_rows = env_int("VRAD_K4_BK_ROWS", e->opt.k4_bk_rows);
+    e->opt.k4_bk_min_items = env_int("VRAD_K4_BK_MIN_ITEMS", e->opt.k4_bk_min_items);
     e->opt.k4_items = env_int("VRAD_K4_ITEMS", e->opt.k4_items);
     e->opt.k4_pdl = env_int("VRAD_K4_PDL", e->opt.k4_pdl);
     e->opt.k4_graph = env_int("VRAD_K4_GRAPH", e->opt.k4_graph);
