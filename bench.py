@@ -610,7 +610,7 @@ def run_graft(args, rank, local_rank, world):
                 "note": "host emit0 (N x RGB f32) in and host total out on every 100-bounce call; transfer lists and patches stay resident, as in the bake"},
         "gpu_launches": bounce_launches * args.steps,
         "roofline": {"bound": "hbm", "achieved": gather_gbs_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": gather_gbs_gpu / hbm_peak,
-                     "traffic": (None if block_entries else 1.2047e9 if packed_entries else 1.5537e9) if world == 1 else None,
+                     "traffic": (1.0260e9 if block_entries else 1.2047e9 if packed_entries else 1.5537e9) if world == 1 else None,
                      "traffic_source": "profiles/r02_k4_packed_ncu_summary.txt / profiles/r02_k4_block_ncu_summary.txt (dram read+write per launch, N=1; same kernels)",
                      "kernel": (f"k4_gather_blocked<{block_rows}, 4, {4 if block_rows == 4 else 5}>" if block_entries else "k4_gather_packed<4, 5>" if packed_entries else "k4_gather") if world == 1 else
                                (f"k4_gather_items_blocked<true, 8, {block_rows}>" if block_entries else "k4_gather_items<true, 8, true, PACKED>" if packed_entries else "k4_gather_items<true, 6>"),
