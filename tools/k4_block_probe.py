@@ -1,5 +1,6 @@
 """Development probe: the C4 gather from the block-row streams (k4_pack 2: 4 rows share a column list) against the packed streams (1)
-and the pairs (0) on one GPU; kernel forms k4_bk_variant 0..6.  gpurun_out/r02_k4_block.json."""
+and the pairs (0) on one GPU.  (The committed profiles/r02_k4_block.json also holds the kernel forms tried while the kernel was written --
+entries in flight x resident blocks per SM, "variant" 1..6 -- the shipped form is variant 4.)  gpurun_out/r02_k4_block.json."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,8 +16,7 @@ e0 = torch.from_numpy(scenes.SplitMix64(0xE1).uniform(3 * N, 0.0, 200.0).reshape
 env.set_async(True)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = None
-for pack, var in ((0, 0), (1, 0), (2, 0), (2, 1), (2, 2), (2, 3), (2, 4), (2, 5), (2, 6), (2, 0), (1, 0), (0, 0)):
-    env.set_option("k4_bk_variant", var)
+for pack, var in ((0, 0), (1, 0), (2, 0), (2, 0), (1, 0), (0, 0)):
     t0 = time.perf_counter(); env.set_option("k4_pack", pack); torch.cuda.synchronize(); replan = time.perf_counter() - t0
     t1, a1, _ = env.bounce(e0, 5)
     t1, a1 = (np.asarray(v.cpu()) if hasattr(v, 'cpu') else np.asarray(v) for v in (t1, a1))
