@@ -294,3 +294,41 @@ def test_block_row_streams_same_light(s2_small_scene, s2_small_oracle):
     toe, aoe, doe = s2_small_oracle.bounce(emit0, 100, early_out=True, threads=8)
     assert de == doe and np.abs(te - toe).max() <= 1e-4 * np.abs(toe).max()
     env.close()
+
+
+def test_uploaded_rows_in_any_column_order_keep_the_pairs():
+    """vrad_transfers_upload takes rows as given: columns unsorted or listed twice are legal for the {col,w} pair kernels; the packed and
+    block-row streams (which rely on ascending columns) must then stay out of the way."""
+    from vrad_b200.environment import Environment
+    rng = np.random.default_rng(9)
+    N = 4096
+    env = Environment()
+    env.add_triangles(np.int32([0]), np.float32([[0, 0, 0, 1, 0, 0, 0, 1, 0]])); env.setup_acceleration_structure()
+    refl = rng.uniform(0.2, 0.8, (N, 3)).astype(np.float32)
+    env.patches_upload(rng.uniform(-10, 10, (N, 3)).astype(np.float32), np.tile(np.float32([0, 0, 1]), (N, 1)), np.zeros(N, np.float32), np.ones(N, np.float32), refl)
+    lens = rng.integers(0, 700, N)
+    rp = np.zeros(N + 1, np.int64); np.cumsum(lens, out=rp[1:])
+    col = rng.integers(0, N, rp[-1]).astype(np.int32)                  # any order, duplicates included
+    w = rng.uniform(0.0, 1.0 / 700, rp[-1]).astype(np.float32)
+    env.set_option("k4_short", 0)
+    env.transfers_upload(0, N, rp, col, w)
+    pairs, packed, segs, blocked, rows = env.transfers_layout()
+    assert packed == 0 and blocked == 0
+    emit0 = rng.uniform(0, 100, (N, 3)).astype(np.float32)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((w.astype(np.float64), col, rp), shape=(N, N))    # duplicates are summed, as the gather does
+    emit = emit0.astype(np.float64); total = np.zeros((N, 3))
+    for _ in range(3):
+        add = A @ (emit * refl.astype(np.float64)); total += add; emit = add
+    for items in (0, 1):
+        env.set_option("k4_items", items)
+        t, _, _ = env.bounce(emit0, 3)
+        assert np.abs(t - total).max() <= 1e-5 * np.abs(total).max(), items
+    # the same rows sorted and de-duplicated may be packed again
+    rows_sorted = [np.unique(col[rp[i]:rp[i + 1]]) for i in range(N)]
+    rp2 = np.zeros(N + 1, np.int64); np.cumsum([len(r) for r in rows_sorted], out=rp2[1:])
+    env.set_option("k4_items", 0)
+    env.transfers_upload(0, N, rp2, np.concatenate(rows_sorted).astype(np.int32), np.full(rp2[-1], 1e-3, np.float32))
+    pairs, packed, segs, blocked, rows = env.transfers_layout()
+    assert packed > 0 or blocked > 0
+    env.close()

@@ -86,6 +86,7 @@ struct TransfersDev {
     DevBuf<int32_t> rowlen;         // logical row lengths
     DevBuf<int2>    tr;             // {col, w bits} pairs == the reference's Transfer struct (transfer.go:3-6)
     bool ready = false;
+    bool rows_ascending = true;     // columns strictly ascending inside every row (always so from vrad_build_transfers; checked by vrad_transfers_upload)
     // Gather plan (K4): one warp per work item.  A row longer than `seg` entries is cut into parts of `seg` entries
     // (one item each) so that no warp carries a 30 us row into the tail of a 40 us kernel; the parts' sums meet in
     // part_sum[] and the part that arrives last (row_ctr) adds them in part order and runs the row's epilogue.

@@ -736,6 +736,7 @@ int vrad_build_transfers(vrad_env* e, int n_clusters, const uint8_t* pvs, int64_
     int64_t nnz = 0;
     for (int r = 0; r < nloc; r++) nnz += rl[r];
     T.row0 = row0; T.row1 = row1; T.nnz = nnz; T.nnz_padded = np; T.rows_serial++;
+    T.rows_ascending = true;                 // k2_fill expands the bit matrix in candidate order = ascending patch index
     const auto t_kernels = now();
     cleanup();
     int rcp = build_gather_plan(e, rl.data(), nloc);

@@ -1281,7 +1281,7 @@ k4_collect_parents(int n_interior, int n_long, int long_blocks, const int32_t* _
 static int build_packed_streams(vrad_env* e, int64_t nloc) {
     TransfersDev& T = e->transfers;
     T.packed = false;
-    if (!e->opt.k4_pack || e->patches.hier || nloc <= 0) return 0;
+    if (!e->opt.k4_pack || e->patches.hier || nloc <= 0 || !T.rows_ascending) return 0;
     int max_seg = 1 << 8;                                  // the longest segment = the longest part of the pair plan (k4_seg)
     while ((max_seg << 1) <= e->opt.k4_seg && max_seg < (1 << 15)) max_seg <<= 1;
     DevBuf<int32_t> d_ns; DevBuf<int64_t> d_pad, d_rowptr; DevBuf<unsigned char> d_tmp;
@@ -1332,6 +1332,7 @@ static int build_packed_streams(vrad_env* e, int64_t nloc) {
 static int build_block_streams(vrad_env* e, int64_t nloc) {
     TransfersDev& T = e->transfers;
     T.blocked = false;
+    if (!T.rows_ascending) return 0;
     const int rows = e->opt.k4_bk_rows == 2 ? 2 : 4;
     if ((e->opt.k4_pack != 2 && e->opt.k4_pack != 3) || e->patches.hier || nloc <= 0 || (T.row0 % kBlockRows) != 0) return 0;
     int max_seg = 1 << 8;
@@ -1751,17 +1752,22 @@ int vrad_transfers_upload(vrad_env* e, int64_t row0, int64_t row1, const int64_t
         prow[i + 1] = prow[i] + ((len + 3) & ~(int64_t)3);
     }
     const int64_t np = prow[nloc];
+    bool ascending = true;
     std::vector<int2> ptr(np ? np : 4, make_int2(0, 0));              // {col, w bits}; padding = {0, 0.0f}
     for (int64_t i = 0; i < nloc; i++) {
         const int64_t s = rowptr[i] - rowptr[0];
         for (int64_t k = 0; k < rlen[i]; k++) {
             int32_t c = col[s + k];
             if (c < 0 || c >= N) { set_error("vrad_transfers_upload: column %d out of range at row %lld", c, (long long)(row0 + i)); return VRAD_E_INVALID; }
+            if (k > 0 && c <= col[s + k - 1]) ascending = false;
             int2 v; v.x = c; memcpy(&v.y, &w[s + k], 4);
             ptr[prow[i] + k] = v;
         }
     }
     TransfersDev& T = e->transfers;
+    // the packed and block-row streams rely on what vrad_build_transfers guarantees -- columns strictly ascending inside a row (MakeScales walks
+    // the row in patch order); rows uploaded in another order, or with a column twice, are gathered from the {col,w} pairs as given
+    T.rows_ascending = ascending;
     if (T.rowptr.alloc(nloc + 1) || T.rowlen.alloc(nloc ? nloc : 1) || T.tr.alloc(ptr.size())) { set_error("out of device memory for transfers"); return VRAD_E_NOMEM; }
     VRAD_CUDA_CHECK(cudaMemcpyAsync(T.rowptr.p, prow.data(), (nloc + 1) * 8, cudaMemcpyHostToDevice, e->stream));
     VRAD_CUDA_CHECK(cudaMemcpyAsync(T.rowlen.p, rlen.data(), rlen.size() * 4, cudaMemcpyHostToDevice, e->stream));
