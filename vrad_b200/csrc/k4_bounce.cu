@@ -12,6 +12,15 @@
 // kept as one float4 per patch (16 B gathers that live in L2: 3.2 MB at 200k patches, 32 MB at 2M).  Algorithmic
 // bytes per bounce: 8*nnz + 40*N; the kernel is HBM-bound on the 8*nnz stream.
 // One warp per row, warp-shuffle reduction, collect step fused into the epilogue.
+//
+// The pairs are what vrad_build_transfers / vrad_transfers_upload leave and what downloads, the bump-mapped and the short-row kernels
+// read.  The gather itself streams a denser form derived from them where the rows allow it (build_gather_plan; TransfersDev):
+//   block rows  4 consecutive rows share the union of their columns: u16 column offset + 4 f32 weights per union entry -- 5.25 B per
+//               transfer and one er[] gather per four rows on the C4 map (k4_gather_blocked, k4_gather_items_blocked);
+//   packed      f32 weight + u16 column offset, 6 B per transfer (k4_gather_packed, k4_gather_items<.., PACKED>) -- rows that do not share
+//               their columns, and slices too small for block-row work items (8 ranks on the C4 map);
+//   pairs       everything else (rows over many 65,536-column windows, rows uploaded with unsorted columns, the patch hierarchy).
+// Weights are the same f32 values in every form; the forms differ in the order a row's products are added (results agree to ~2e-7).
 #include "env_internal.cuh"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
