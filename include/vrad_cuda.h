@@ -103,9 +103,20 @@ int  vrad_env_set_async(vrad_env*, int async);
  *   "k4_persist"    (VRAD_K4_PERSIST)   gather grid = one block per resident slot over equal-work item ranges (default 1);
  *                                       0 = 8 items per block, as many blocks as that takes
  *   "k4_pool"       (VRAD_K4_POOL)      percent of the gather work kept out of the persistent blocks' ranges, for whoever
- *                                       finishes its range early (default 12)
+ *                                       finishes its range early (default 25)
  *   "k4_items"      (VRAD_K4_ITEMS)     run the multi-GPU (work-item) gather kernel on a single-GPU handle too (default 0)
- *   "k4_block"      (VRAD_K4_BLOCK)     threads per gather block: 256 (5 blocks per SM) or 192 (6 per SM, more registers)
+ *   "k4_block"      (VRAD_K4_BLOCK)     threads per gather block: 256 (5 blocks per SM) or 192 (6 per SM, more registers);
+ *                                       0 (default) = 256 with the packed streams, 192 with the pairs
+ *   "k4_pack"       (VRAD_K4_PACK)      form the gather streams the transfers in: 2 (default) = block rows where neighbouring rows share
+ *                                       their columns (4 rows per column list), else packed 6-byte entries, else the {col,w} pairs;
+ *                                       1 = packed or pairs; 0 = pairs; 3 = block rows regardless of the work-item count; 9 = packed
+ *                                       regardless of the segment count (vrad_transfers_layout reports what is in use)
+ *   "k4_bk_rows"    (VRAD_K4_BK_ROWS)   rows per block of the block-row streams: 4 (default) or 2
+ *   "k4_short"      (VRAD_K4_SHORT)     the short-row gather (8 lanes per row) on one GPU: -1 (default) = where rows average under
+ *                                       400 transfers, 0 = never, 1 = always
+ *   "k1_bpsm"       (VRAD_K1_BPSM)      resident blocks per SM of the streaming traversal kernel: 12 (default), 10, 8
+ *   "k1_sort_bits"  (VRAD_K1_SORT_BITS) leading bits of the 30-bit order key that take part in the radix sort (default 30)
+ *   "k2_stream"     (VRAD_K2_STREAM)    K2 pass A as per-warp ray queues with lane refill (default 0: measured slower)
  *   "k4_pdl"        (VRAD_K4_PDL)       multi-GPU gather: chain the bounces by programmatic dependent launch (default 1)
  *   "k4_graph"      (VRAD_K4_GRAPH)     replay the bounce loop as a CUDA graph (default 1)
  *   "k4_sim_peers"  (VRAD_K4_SIM_PEERS) world > 1 without a communicator: this device stands in for every peer -- timing
